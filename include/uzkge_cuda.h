@@ -1,0 +1,135 @@
+/*
+ * uzkge_cuda.h -- C ABI of the B200 (sm_100a) MSM / NTT backend for zypher-game/uzkge.
+ *
+ * The reference has no FFI today; this header is the seam a thin Rust `extern "C"` crate
+ * binds (INTEGRATION.md shows the crate and the two patched call sites).  Each entry point names the
+ * reference code it replaces.
+ *
+ * Data layout (identical to arkworks' in-memory types, so Rust copies limbs, never converts):
+ *   field element  : 4 x uint64 little-endian limbs, MONTGOMERY form, R = 2^256   (ark_ff::Fp, BigInt<4>)
+ *   affine G1      : x[4], y[4]  (64 B).  The identity is x = y = 0 and is skipped
+ *                    (the padded monomial SRS holds identities, uzkge/src/gen_params/mod.rs:160-161)
+ *   Jacobian G1    : X[4], Y[4], Z[4]  (96 B), Z == 0 <=> identity               (G1Projective)
+ *
+ * Ownership: the caller owns every host buffer; the library copies in / out and owns all device memory.
+ * Errors: 0 = OK, otherwise one of UZKGE_ERR_*; uzkge_cuda_last_error() gives a thread-local message.
+ * There is NO CPU fallback: without a usable CUDA device every call fails with UZKGE_ERR_NO_DEVICE.
+ * Threading: every entry point may be called from any thread; calls are serialised per process
+ * (one process drives one GPU; multi-GPU = one process per GPU, see uzkge_b200/dist.py).
+ */
+#ifndef UZKGE_CUDA_H
+#define UZKGE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define UZKGE_API __attribute__((visibility("default")))
+#else
+#define UZKGE_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UZKGE_OK 0
+#define UZKGE_ERR_NO_DEVICE 1   /* no CUDA device / driver: the backend refuses to run (no CPU path)   */
+#define UZKGE_ERR_SIZE 2        /* unsupported domain size, length mismatch, range outside the SRS     */
+#define UZKGE_ERR_CUDA 3        /* CUDA runtime failure (message in uzkge_cuda_last_error)             */
+#define UZKGE_ERR_OOM 4         /* device allocation failed                                            */
+#define UZKGE_ERR_HANDLE 5      /* unknown SRS handle                                                  */
+#define UZKGE_ERR_ARG 6         /* null pointer / bad flag                                             */
+#define UZKGE_ERR_INTERNAL 7
+
+/* Bind this process to CUDA device `device` (-1: keep the current device, e.g. the one torch selected).
+ * Idempotent and thread-safe.  Must be called before any other entry point. */
+UZKGE_API int32_t uzkge_cuda_init(int32_t device);
+UZKGE_API int32_t uzkge_cuda_device_count(void);
+UZKGE_API const char* uzkge_cuda_last_error(void);
+/* "uzkge-b200 <version> sm_100a" */
+UZKGE_API const char* uzkge_cuda_version(void);
+
+/* ---- SRS ------------------------------------------------------------------------------------------
+ * Upload the G1 part of an SRS (monomial or Lagrange) once.  Replaces the per-commit
+ * `G1Projective::normalize_batch(&self.public_parameter_group_1[0..degree + 1])`
+ * (uzkge/src/poly_commit/kzg_poly_commitment.rs:287-288): bases live on the GPU in affine form together with
+ * the fixed-base window tables 2^(c*f) * P_i that the MSM uses (built on the device, once).
+ * window_bits = 0 lets the library choose c from n. */
+UZKGE_API int32_t uzkge_cuda_srs_upload(const uint64_t* affine_xy, size_t n, uint32_t window_bits, uint64_t* handle);
+UZKGE_API int32_t uzkge_cuda_srs_free(uint64_t handle);
+
+/* ---- MSM ------------------------------------------------------------------------------------------
+ * out = sum_{i < n} scalars[i] * srs[base_offset + i].  Replaces `G1Projective::msm(&points_raw, &coefs)`
+ * (kzg_poly_commitment.rs:290) for KZGCommitmentSchemeBN254::commit (:278-293).
+ * n == 0 gives the identity.  base_offset + n must not exceed the SRS length (UZKGE_ERR_SIZE; the Rust
+ * caller raises DegreeError before calling, kzg_poly_commitment.rs:283-285). */
+UZKGE_API int32_t uzkge_cuda_msm_g1(uint64_t handle, size_t base_offset, const uint64_t* scalars, size_t n, uint64_t out_jac[12]);
+/* k independent MSMs over the same SRS prefix (the round-1 wire commitments, the split quotient, ...:
+ * uzkge/src/plonk/prover.rs:132-192, helpers.rs:1323-1408).  out_jac holds k * 12 words. */
+UZKGE_API int32_t uzkge_cuda_msm_g1_batch(uint64_t handle, const uint64_t* const* scalars, const size_t* n, size_t k, uint64_t* out_jac);
+
+/* ---- NTT ------------------------------------------------------------------------------------------
+ * In-place transform of `inout` (capacity domain_size elements; the first len_in are the input, the rest
+ * is treated as zero).  domain_size = 2^k (Radix2EvaluationDomain) or 3 * 2^k (MixedRadixEvaluationDomain),
+ * natural order in and out, generator = arkworks' get_root_of_unity(domain_size).
+ *   inverse = 0, coset_shift = NULL : FpPolynomial::fft_with_domain        (field_polynomial.rs:583-586)
+ *   inverse = 0, coset_shift = k    : FpPolynomial::coset_fft_with_domain  (:589-591)  c_j * k^j, then fft
+ *   inverse = 1, coset_shift = NULL : domain.ifft of ifft_with_domain      (:594-597)  incl. 1/N; the
+ *                                     trailing-zero trim stays in Rust (`from_coefs`)
+ *   inverse = 1, coset_shift = k^-1 : coset_ifft_with_domain               (:601-607)  ifft, then c_j * (k^-1)^j */
+UZKGE_API int32_t uzkge_cuda_ntt_fr(uint64_t* inout, size_t len_in, size_t domain_size, int32_t inverse, const uint64_t* coset_shift);
+/* generator of the size-n domain (Montgomery), for the Rust side's consistency assert against
+ * `domain.group_gen`; UZKGE_ERR_SIZE if n is not 3^a 2^b with a <= 2, b <= 28. */
+UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]);
+
+/* ---- device-resident variants ----------------------------------------------------------------------
+ * Same semantics with DEVICE pointers and a caller-provided cudaStream_t (NULL = default stream); nothing
+ * is copied and nothing synchronises: this is what a device-resident prover pipeline and the
+ * HBM-resident benchmark call.  d_out may equal d_in for the NTT; d_scratch holds domain_size elements. */
+UZKGE_API int32_t uzkge_cuda_msm_g1_device(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, void* d_out_jac, void* stream);
+UZKGE_API int32_t uzkge_cuda_ntt_fr_device(const void* d_in, void* d_out, void* d_scratch, size_t len_in, size_t domain_size,
+                                 int32_t inverse, const uint64_t* coset_shift_host, void* stream);
+
+/* ---- small group helpers (combine per-GPU partial MSMs; blinds) --------------------------------------
+ * out = a + b on Jacobian points (host pointers, tiny device kernel).  Used for the G - 1 projective adds
+ * that merge per-GPU partial sums. */
+UZKGE_API int32_t uzkge_cuda_g1_add(const uint64_t a_jac[12], const uint64_t b_jac[12], uint64_t out_jac[12]);
+/* Jacobian -> affine (x = y = 0 for the identity): the normalisation `into_affine` performs before a
+ * commitment is serialised (kzg_poly_commitment.rs:37-53). */
+UZKGE_API int32_t uzkge_cuda_g1_to_affine(const uint64_t in_jac[12], uint64_t out_affine[8]);
+
+/* ---- pinned host memory ---------------------------------------------------------------------------------
+ * Optional.  Every host-pointer entry point accepts pageable memory (a Rust Vec); buffers obtained here, or
+ * registered in place, are page-locked so the PCIe copies run at full rate.  The Rust side can register the
+ * long-lived vectors (SRS, prover-parameter evaluations) once. */
+UZKGE_API int32_t uzkge_cuda_host_alloc(size_t bytes, void** out);
+UZKGE_API int32_t uzkge_cuda_host_free(void* p);
+UZKGE_API int32_t uzkge_cuda_host_register(void* p, size_t bytes);
+UZKGE_API int32_t uzkge_cuda_host_unregister(void* p);
+
+/* ---- introspection for benchmarks / profiling --------------------------------------------------------*/
+typedef struct {
+    uint32_t window_bits;   /* c */
+    uint32_t windows;       /* ceil(255 / c) = number of fixed-base tables */
+    uint64_t n;             /* SRS length */
+    uint64_t device_bytes;  /* device bytes held for this SRS (tables + MSM workspace) */
+    double precompute_ms;   /* device time spent building the tables */
+} uzkge_srs_info;
+UZKGE_API int32_t uzkge_cuda_srs_info(uint64_t handle, uzkge_srs_info* info);
+/* number of kernel launches issued by this library since init (bench.py's gpu_launches) */
+UZKGE_API uint64_t uzkge_cuda_launch_count(void);
+/* tuning knobs for experiments: "msm_lanes" (0 = auto, else 1..32 lanes per bucket), "ntt_log_tile",
+ * "ntt_max_log_r", "ntt_two_pass_max".  Affects plans created afterwards. */
+UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value);
+/* K1 field kernels, exposed for parity tests and for the integer-pipe roof measurement:
+ *   out[i] = a[i] * b[i] (Montgomery), field = 0: Fr, 1: Fq; host pointers. */
+UZKGE_API int32_t uzkge_cuda_field_mul(int32_t field, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* `chains` dependent multiplication chains of length `iters` per thread over the whole GPU; reports achieved
+ * field multiplications per second (device time). */
+UZKGE_API int32_t uzkge_cuda_bench_field_mul(int32_t field, uint32_t iters, double* muls_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UZKGE_CUDA_H */

@@ -1,0 +1,472 @@
+// api.cu -- the C ABI of include/uzkge_cuda.h: process-wide state, host<->device staging, error mapping.
+//
+// The Rust side binds exactly these symbols from the bodies of
+// KZGCommitmentSchemeBN254::commit (/root/reference/uzkge/src/poly_commit/kzg_poly_commitment.rs:278-293) and
+// FpPolynomial::{fft,ifft,coset_fft,coset_ifft}_with_domain (/root/reference/uzkge/src/poly_commit/field_polynomial.rs:583-607).
+// There is no CPU path in this library: without a Blackwell device every call fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "devmem.cuh"
+#include "internal.h"
+
+namespace uz {
+std::atomic<uint64_t> g_launches{0};
+}
+
+using namespace uz;
+
+namespace {
+
+thread_local std::string t_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+};
+
+struct State {
+    std::mutex mu;
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::unique_ptr<NttEngine> ntt;
+    std::unique_ptr<MsmEngine> msm;
+    std::map<uint64_t, MsmSrs> srs;
+    uint64_t next_handle = 1;
+    DevBuf data, scratch, scalars, small;
+    uint32_t ntt_log_tile = 12, ntt_max_log_r = 11, ntt_two_pass_max = 22;
+};
+State g;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) {
+        snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+        cudaGetLastError();  // clear the sticky-free error state
+    } else {
+        snprintf(buf, sizeof buf, "%s", what);
+    }
+    t_error = buf;
+    return code;
+}
+int fail_cuda(const char* what, cudaError_t e) { return fail(cuda_err_code(e), what, e); }
+
+int engine_fail(int rc, const char* what) {
+    if (rc == UZKGE_OK) return rc;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(rc, what, e);
+    return fail(rc, what);
+}
+
+// caller holds g.mu
+int ensure_init(int device) {
+    if (g.ready) {
+        cudaError_t e = cudaSetDevice(g.device);
+        if (e != cudaSuccess) return fail_cuda("cudaSetDevice", e);
+        return UZKGE_OK;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(UZKGE_ERR_NO_DEVICE, "no CUDA device: uzkge-b200 has no CPU path");
+    }
+    if (device >= 0) {
+        if (device >= count) return fail(UZKGE_ERR_NO_DEVICE, "device index out of range");
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) return fail_cuda("cudaSetDevice", e);
+    }
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail_cuda("cudaGetDevice", e);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return fail_cuda("cudaGetDeviceProperties", e);
+    if (prop.major != 10) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "device %d (%.64s, sm_%d%d) is not a Blackwell sm_100 part: kernels are built for sm_100a only",
+                 dev, prop.name, prop.major, prop.minor);
+        return fail(UZKGE_ERR_NO_DEVICE, buf);
+    }
+    e = cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail_cuda("cudaStreamCreate", e);
+    g.device = dev;
+    g.sm_count = prop.multiProcessorCount;
+    g.ntt.reset(new NttEngine(g.sm_count));
+    g.ntt->configure(g.ntt_log_tile, g.ntt_max_log_r, g.ntt_two_pass_max);
+    g.msm.reset(new MsmEngine(g.sm_count));
+    g.ready = true;
+    return UZKGE_OK;
+}
+
+#define API_ENTER(dev)                           \
+    std::lock_guard<std::mutex> lock__(g.mu);    \
+    do {                                         \
+        int rc__ = ensure_init(dev);             \
+        if (rc__ != UZKGE_OK) return rc__;       \
+    } while (0)
+
+#define CUDA_OR_FAIL(expr, what)                         \
+    do {                                                 \
+        cudaError_t e__ = (expr);                        \
+        if (e__ != cudaSuccess) return fail_cuda(what, e__); \
+    } while (0)
+
+// ---- K1 test / roof kernels
+template <class P>
+__global__ void field_mul_kernel(const fe* a, const fe* b, fe* o, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_fe(o + i, fe_mul<P>(ld_fe(a + i), ld_fe(b + i)));
+}
+// 4 independent dependent-chains per thread: x_k <- x_k * y_k, `iters` times
+template <class P>
+__global__ void __launch_bounds__(256) field_mul_bench_kernel(fe* sink, uint32_t iters) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    fe x[4], y;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = fe_one<P>();
+        x[k].l[0] += t * 4 + k;
+    }
+    y = fe_one<P>();
+    y.l[1] ^= t;
+#pragma unroll 1
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) x[k] = fe_mul<P>(x[k], y);
+    }
+    fe r = fe_add<P>(fe_add<P>(x[0], x[1]), fe_add<P>(x[2], x[3]));
+    if (r.l[7] == 0xffffffffu) st_fe(sink + t, r);  // never true for reduced values: keeps the chain alive
+}
+
+}  // namespace
+
+extern "C" {
+
+UZKGE_API int32_t uzkge_cuda_init(int32_t device) {
+    API_ENTER(device);
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+UZKGE_API const char* uzkge_cuda_last_error(void) { return t_error.c_str(); }
+UZKGE_API const char* uzkge_cuda_version(void) { return "uzkge-b200 0.1.0 sm_100a"; }
+
+UZKGE_API int32_t uzkge_cuda_srs_upload(const uint64_t* affine_xy, size_t n, uint32_t window_bits, uint64_t* handle) {
+    if (!affine_xy || !handle) return fail(UZKGE_ERR_ARG, "srs_upload: null pointer");
+    API_ENTER(-1);
+    MsmSrs s;
+    int rc = g.msm->upload(affine_xy, n, window_bits, &s, g.stream);
+    if (rc != UZKGE_OK) {
+        g.msm->release(&s);
+        return engine_fail(rc, "srs_upload");
+    }
+    const uint64_t h = g.next_handle++;
+    g.srs[h] = s;
+    *handle = h;
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_srs_free(uint64_t handle) {
+    API_ENTER(-1);
+    auto it = g.srs.find(handle);
+    if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "srs_free: unknown handle");
+    cudaStreamSynchronize(g.stream);
+    g.msm->release(&it->second);
+    g.srs.erase(it);
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_srs_info(uint64_t handle, uzkge_srs_info* info) {
+    if (!info) return fail(UZKGE_ERR_ARG, "srs_info: null pointer");
+    API_ENTER(-1);
+    auto it = g.srs.find(handle);
+    if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "srs_info: unknown handle");
+    info->window_bits = it->second.c;
+    info->windows = it->second.windows;
+    info->n = it->second.n;
+    info->device_bytes = it->second.bytes;
+    info->precompute_ms = it->second.precompute_ms;
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_msm_g1_batch(uint64_t handle, const uint64_t* const* scalars, const size_t* n, size_t k, uint64_t* out_jac) {
+    if (k && (!scalars || !n || !out_jac)) return fail(UZKGE_ERR_ARG, "msm_g1_batch: null pointer");
+    API_ENTER(-1);
+    auto it = g.srs.find(handle);
+    if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1: unknown handle");
+    if (k == 0) return UZKGE_OK;
+    MsmSrs& s = it->second;
+    size_t total = 0;
+    for (size_t j = 0; j < k; j++) {
+        if (n[j] > s.n) return fail(UZKGE_ERR_SIZE, "msm_g1: more scalars than SRS points");
+        if (n[j] && !scalars[j]) return fail(UZKGE_ERR_ARG, "msm_g1: null scalar vector");
+        total += n[j];
+    }
+    CUDA_OR_FAIL(g.scalars.reserve(total * sizeof(fe) + 32), "msm_g1: scalar buffer");
+    CUDA_OR_FAIL(g.small.reserve(k * sizeof(jacobian) + 4096), "msm_g1: output buffer");
+    fe* d_s = (fe*)g.scalars.p;
+    jacobian* d_o = (jacobian*)g.small.p;
+    size_t off = 0;
+    for (size_t j = 0; j < k; j++) {
+        if (n[j]) CUDA_OR_FAIL(cudaMemcpyAsync(d_s + off, scalars[j], n[j] * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "msm_g1: H2D");
+        off += n[j];
+    }
+    off = 0;
+    for (size_t j = 0; j < k; j++) {
+        int rc = g.msm->run(&s, 0, d_s + off, n[j], d_o + j, g.stream);
+        if (rc != UZKGE_OK) {
+            cudaStreamSynchronize(g.stream);
+            return engine_fail(rc, "msm_g1: launch");
+        }
+        off += n[j];
+    }
+    CUDA_OR_FAIL(cudaMemcpyAsync(out_jac, d_o, k * sizeof(jacobian), cudaMemcpyDeviceToHost, g.stream), "msm_g1: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "msm_g1: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_msm_g1(uint64_t handle, size_t base_offset, const uint64_t* scalars, size_t n, uint64_t out_jac[12]) {
+    if (!out_jac || (n && !scalars)) return fail(UZKGE_ERR_ARG, "msm_g1: null pointer");
+    API_ENTER(-1);
+    auto it = g.srs.find(handle);
+    if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1: unknown handle");
+    MsmSrs& s = it->second;
+    if (base_offset > s.n || n > s.n - base_offset) return fail(UZKGE_ERR_SIZE, "msm_g1: range outside the SRS");
+    CUDA_OR_FAIL(g.scalars.reserve(n * sizeof(fe) + 32), "msm_g1: scalar buffer");
+    CUDA_OR_FAIL(g.small.reserve(4096), "msm_g1: output buffer");
+    if (n) CUDA_OR_FAIL(cudaMemcpyAsync(g.scalars.p, scalars, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "msm_g1: H2D");
+    int rc = g.msm->run(&s, base_offset, (const fe*)g.scalars.p, n, (jacobian*)g.small.p, g.stream);
+    if (rc != UZKGE_OK) {
+        cudaStreamSynchronize(g.stream);
+        return engine_fail(rc, "msm_g1: launch");
+    }
+    CUDA_OR_FAIL(cudaMemcpyAsync(out_jac, g.small.p, sizeof(jacobian), cudaMemcpyDeviceToHost, g.stream), "msm_g1: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "msm_g1: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_msm_g1_device(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, void* d_out_jac, void* stream) {
+    if (!d_out_jac || (n && !d_scalars)) return fail(UZKGE_ERR_ARG, "msm_g1_device: null pointer");
+    API_ENTER(-1);
+    auto it = g.srs.find(handle);
+    if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1_device: unknown handle");
+    int rc = g.msm->run(&it->second, base_offset, (const fe*)d_scalars, n, (jacobian*)d_out_jac, (cudaStream_t)stream);
+    return engine_fail(rc, "msm_g1_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_ntt_fr(uint64_t* inout, size_t len_in, size_t domain_size, int32_t inverse, const uint64_t* coset_shift) {
+    if (!inout) return fail(UZKGE_ERR_ARG, "ntt_fr: null pointer");
+    if (inverse != 0 && inverse != 1) return fail(UZKGE_ERR_ARG, "ntt_fr: inverse must be 0 or 1");
+    if (len_in > domain_size) return fail(UZKGE_ERR_SIZE, "ntt_fr: input longer than the domain");
+    API_ENTER(-1);
+    bool ok = false;
+    ntt_root_of_unity(domain_size, &ok);
+    if (!ok || domain_size % 9 == 0) return fail(UZKGE_ERR_SIZE, "ntt_fr: domain size must be 2^k or 3 * 2^k, k <= 28");
+    CUDA_OR_FAIL(g.data.reserve(domain_size * sizeof(fe)), "ntt_fr: data buffer");
+    CUDA_OR_FAIL(g.scratch.reserve(domain_size * sizeof(fe)), "ntt_fr: scratch buffer");
+    if (len_in) CUDA_OR_FAIL(cudaMemcpyAsync(g.data.p, inout, len_in * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "ntt_fr: H2D");
+    fe shift;
+    if (coset_shift) memcpy(&shift, coset_shift, sizeof(fe));
+    int rc = g.ntt->run((const fe*)g.data.p, (fe*)g.data.p, (fe*)g.scratch.p, len_in, domain_size, inverse != 0,
+                        coset_shift ? &shift : nullptr, g.stream);
+    if (rc != UZKGE_OK) {
+        cudaStreamSynchronize(g.stream);
+        return engine_fail(rc, "ntt_fr: launch");
+    }
+    CUDA_OR_FAIL(cudaMemcpyAsync(inout, g.data.p, domain_size * sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "ntt_fr: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "ntt_fr: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_ntt_fr_device(const void* d_in, void* d_out, void* d_scratch, size_t len_in, size_t domain_size,
+                                 int32_t inverse, const uint64_t* coset_shift_host, void* stream) {
+    if (!d_in || !d_out || !d_scratch) return fail(UZKGE_ERR_ARG, "ntt_fr_device: null pointer");
+    if (d_scratch == d_in || d_scratch == d_out) return fail(UZKGE_ERR_ARG, "ntt_fr_device: scratch must not alias");
+    if (len_in > domain_size) return fail(UZKGE_ERR_SIZE, "ntt_fr_device: input longer than the domain");
+    API_ENTER(-1);
+    bool ok = false;
+    ntt_root_of_unity(domain_size, &ok);
+    if (!ok || domain_size % 9 == 0) return fail(UZKGE_ERR_SIZE, "ntt_fr_device: domain size must be 2^k or 3 * 2^k");
+    fe shift;
+    if (coset_shift_host) memcpy(&shift, coset_shift_host, sizeof(fe));
+    int rc = g.ntt->run((const fe*)d_in, (fe*)d_out, (fe*)d_scratch, len_in, domain_size, inverse != 0,
+                        coset_shift_host ? &shift : nullptr, (cudaStream_t)stream);
+    return engine_fail(rc, "ntt_fr_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]) {
+    if (!out) return fail(UZKGE_ERR_ARG, "fr_root_of_unity: null pointer");
+    bool ok = false;
+    const fe w = ntt_root_of_unity(n, &ok);
+    if (!ok) return fail(UZKGE_ERR_SIZE, "fr_root_of_unity: n must be 3^a 2^b, a <= 2, b <= 28");
+    memcpy(out, &w, sizeof(fe));
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_g1_add(const uint64_t a_jac[12], const uint64_t b_jac[12], uint64_t out_jac[12]) {
+    if (!a_jac || !b_jac || !out_jac) return fail(UZKGE_ERR_ARG, "g1_add: null pointer");
+    API_ENTER(-1);
+    CUDA_OR_FAIL(g.small.reserve(4096), "g1_add: buffer");
+    jacobian* d = (jacobian*)g.small.p;
+    CUDA_OR_FAIL(cudaMemcpyAsync(d, a_jac, sizeof(jacobian), cudaMemcpyHostToDevice, g.stream), "g1_add: H2D");
+    CUDA_OR_FAIL(cudaMemcpyAsync(d + 1, b_jac, sizeof(jacobian), cudaMemcpyHostToDevice, g.stream), "g1_add: H2D");
+    int rc = g.msm->g1_add(d, d + 1, d + 2, g.stream);
+    if (rc != UZKGE_OK) return engine_fail(rc, "g1_add");
+    CUDA_OR_FAIL(cudaMemcpyAsync(out_jac, d + 2, sizeof(jacobian), cudaMemcpyDeviceToHost, g.stream), "g1_add: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "g1_add: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_g1_to_affine(const uint64_t in_jac[12], uint64_t out_affine[8]) {
+    if (!in_jac || !out_affine) return fail(UZKGE_ERR_ARG, "g1_to_affine: null pointer");
+    API_ENTER(-1);
+    CUDA_OR_FAIL(g.small.reserve(4096), "g1_to_affine: buffer");
+    jacobian* d = (jacobian*)g.small.p;
+    CUDA_OR_FAIL(cudaMemcpyAsync(d, in_jac, sizeof(jacobian), cudaMemcpyHostToDevice, g.stream), "g1_to_affine: H2D");
+    int rc = g.msm->g1_to_affine(d, (affine*)(d + 1), g.stream);
+    if (rc != UZKGE_OK) return engine_fail(rc, "g1_to_affine");
+    CUDA_OR_FAIL(cudaMemcpyAsync(out_affine, d + 1, sizeof(affine), cudaMemcpyDeviceToHost, g.stream), "g1_to_affine: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "g1_to_affine: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(UZKGE_ERR_ARG, "host_alloc: null pointer");
+    API_ENTER(-1);
+    CUDA_OR_FAIL(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault), "host_alloc");
+    return UZKGE_OK;
+}
+UZKGE_API int32_t uzkge_cuda_host_free(void* p) {
+    API_ENTER(-1);
+    CUDA_OR_FAIL(cudaFreeHost(p), "host_free");
+    return UZKGE_OK;
+}
+UZKGE_API int32_t uzkge_cuda_host_register(void* p, size_t bytes) {
+    if (!p) return fail(UZKGE_ERR_ARG, "host_register: null pointer");
+    API_ENTER(-1);
+    CUDA_OR_FAIL(cudaHostRegister(p, bytes, cudaHostRegisterDefault), "host_register");
+    return UZKGE_OK;
+}
+UZKGE_API int32_t uzkge_cuda_host_unregister(void* p) {
+    API_ENTER(-1);
+    CUDA_OR_FAIL(cudaHostUnregister(p), "host_unregister");
+    return UZKGE_OK;
+}
+
+UZKGE_API uint64_t uzkge_cuda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
+    if (!key) return fail(UZKGE_ERR_ARG, "configure: null key");
+    std::lock_guard<std::mutex> lock(g.mu);
+    const std::string k(key);
+    if (k == "msm_lanes") {
+        if (value > 32 || (value & (value - 1))) return fail(UZKGE_ERR_ARG, "configure: msm_lanes must be 0 or a power of two <= 32");
+        int rc = ensure_init(-1);
+        if (rc != UZKGE_OK) return rc;
+        g.msm->force_lanes((uint32_t)value);
+        return UZKGE_OK;
+    }
+    if (k == "ntt_log_tile" || k == "ntt_max_log_r" || k == "ntt_two_pass_max") {
+        if (k == "ntt_log_tile") {
+            if (value < 4 || value > 12) return fail(UZKGE_ERR_ARG, "configure: ntt_log_tile in 4..12");
+            g.ntt_log_tile = (uint32_t)value;
+        } else if (k == "ntt_max_log_r") {
+            if (value < 4 || value > 12) return fail(UZKGE_ERR_ARG, "configure: ntt_max_log_r in 4..12");
+            g.ntt_max_log_r = (uint32_t)value;
+        } else {
+            g.ntt_two_pass_max = (uint32_t)value;
+        }
+        if (g.ready) {  // plans are cached per size: start over with the new limits
+            cudaStreamSynchronize(g.stream);
+            g.ntt.reset(new NttEngine(g.sm_count));
+            g.ntt->configure(g.ntt_log_tile, g.ntt_max_log_r, g.ntt_two_pass_max);
+        }
+        return UZKGE_OK;
+    }
+    return fail(UZKGE_ERR_ARG, "configure: unknown key");
+}
+
+UZKGE_API int32_t uzkge_cuda_field_mul(int32_t field, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    if (n && (!a || !b || !out)) return fail(UZKGE_ERR_ARG, "field_mul: null pointer");
+    if (field != 0 && field != 1) return fail(UZKGE_ERR_ARG, "field_mul: field must be 0 (Fr) or 1 (Fq)");
+    API_ENTER(-1);
+    if (n == 0) return UZKGE_OK;
+    CUDA_OR_FAIL(g.data.reserve(n * sizeof(fe)), "field_mul: buffer");
+    CUDA_OR_FAIL(g.scratch.reserve(n * sizeof(fe)), "field_mul: buffer");
+    CUDA_OR_FAIL(cudaMemcpyAsync(g.data.p, a, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "field_mul: H2D");
+    CUDA_OR_FAIL(cudaMemcpyAsync(g.scratch.p, b, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "field_mul: H2D");
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (field == 0)
+        field_mul_kernel<FrP><<<grid, 256, 0, g.stream>>>((const fe*)g.data.p, (const fe*)g.scratch.p, (fe*)g.data.p, n);
+    else
+        field_mul_kernel<FqP><<<grid, 256, 0, g.stream>>>((const fe*)g.data.p, (const fe*)g.scratch.p, (fe*)g.data.p, n);
+    UZ_COUNT_LAUNCH(1);
+    CUDA_OR_FAIL(cudaGetLastError(), "field_mul: launch");
+    CUDA_OR_FAIL(cudaMemcpyAsync(out, g.data.p, n * sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "field_mul: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "field_mul: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_bench_field_mul(int32_t field, uint32_t iters, double* muls_per_s) {
+    if (!muls_per_s) return fail(UZKGE_ERR_ARG, "bench_field_mul: null pointer");
+    if (field != 0 && field != 1) return fail(UZKGE_ERR_ARG, "bench_field_mul: field must be 0 (Fr) or 1 (Fq)");
+    API_ENTER(-1);
+    const unsigned grid = (unsigned)g.sm_count * 8, nt = 256;
+    CUDA_OR_FAIL(g.data.reserve((size_t)grid * nt * sizeof(fe)), "bench_field_mul: buffer");
+    cudaEvent_t e0, e1;
+    CUDA_OR_FAIL(cudaEventCreate(&e0), "event");
+    CUDA_OR_FAIL(cudaEventCreate(&e1), "event");
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, g.stream);
+        if (field == 0)
+            field_mul_bench_kernel<FrP><<<grid, nt, 0, g.stream>>>((fe*)g.data.p, iters);
+        else
+            field_mul_bench_kernel<FqP><<<grid, nt, 0, g.stream>>>((fe*)g.data.p, iters);
+        UZ_COUNT_LAUNCH(1);
+        cudaEventRecord(e1, g.stream);
+        cudaError_t e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess) return fail_cuda("bench_field_mul: execution", e);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *muls_per_s = (double)grid * nt * 4.0 * iters / (best * 1e-3);
+    return UZKGE_OK;
+}
+
+}  // extern "C"

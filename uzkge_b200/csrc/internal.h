@@ -1,0 +1,105 @@
+// internal.h -- host-side engine declarations shared by ntt.cu, msm.cu and api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <vector>
+
+#include "../../include/uzkge_cuda.h"
+#include "ec.cuh"
+#include "ntt_plan.h"
+
+namespace uz {
+
+extern std::atomic<uint64_t> g_launches;  // kernels launched by this library (uzkge_cuda_launch_count)
+#define UZ_COUNT_LAUNCH(k) (::uz::g_launches.fetch_add((k), std::memory_order_relaxed))
+
+// ---------------------------------------------------------------- NTT
+struct NttDomain {
+    NttPlan plan;
+    fe omega, n_inv, w3, w3sq;
+    fe* w_lo = nullptr;   // one allocation: w_lo | w_hi | stage
+    fe* w_hi = nullptr;
+    fe* stage = nullptr;
+    uint32_t n_hi = 0, n_stage = 0;
+};
+struct NttCoset {
+    uint64_t n;
+    fe g;
+    bool with_ninv;
+    fe* g_lo = nullptr;   // one allocation: g_lo | g_hi
+    fe* g_hi = nullptr;
+    uint32_t n_hi = 0;
+};
+
+fe ntt_root_of_unity(uint64_t n, bool* ok);
+
+class NttEngine {
+public:
+    explicit NttEngine(int sm_count) : sm_count_(sm_count) {}
+    ~NttEngine();
+    void configure(uint32_t log_tile, uint32_t max_log_r, uint32_t two_pass_max) {
+        cfg_log_tile_ = log_tile;
+        cfg_max_log_r_ = max_log_r;
+        cfg_two_pass_max_ = two_pass_max;
+    }
+    int run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, uint64_t n, bool inverse, const fe* coset_shift,
+            cudaStream_t st);
+
+private:
+    const NttDomain* domain(uint64_t n, cudaStream_t st);
+    const NttCoset* coset(uint64_t n, const fe& g, bool with_ninv, const NttDomain* d, cudaStream_t st);
+    std::map<uint64_t, NttDomain> domains_;
+    std::vector<NttCoset> cosets_;
+    int sm_count_;
+    uint32_t cfg_log_tile_ = 12, cfg_max_log_r_ = 11, cfg_two_pass_max_ = 22;
+};
+
+// ---------------------------------------------------------------- MSM
+struct MsmSrs {
+    uint64_t n = 0;            // points
+    uint32_t c = 0;            // window bits
+    uint32_t windows = 0;      // number of windows == number of fixed-base tables
+    uint32_t nbuckets = 0;     // 2^(c-1) + 1 (bucket 0 = zero digit, never accumulated)
+    // reduction matrix: bucket b = hi * cols + lo
+    uint32_t logcols = 0, cols = 0, rows = 0, nb_padded = 0;
+    uint32_t large_cap = 0, max_slices = 0;
+    double precompute_ms = 0;
+    void* arena = nullptr;     // one device allocation holding everything below
+    size_t bytes = 0;
+    affine* tables = nullptr;  // windows x n affine points: table f holds 2^(c*f) * P_i
+    // workspace, sized for an MSM over the whole SRS
+    uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
+    uint32_t* offsets = nullptr;      // nbuckets + 1
+    uint32_t* large_list = nullptr;   // [0] = count, then bucket ids
+    uint32_t* slice_start = nullptr;  // prefix of CTA slices per oversized bucket
+    xyzz* slice_sums = nullptr;
+    xyzz* buckets = nullptr;          // nb_padded
+    xyzz* marg = nullptr;             // rows + cols marginal sums
+    xyzz* partial = nullptr;          // 2
+    uint32_t* ticket = nullptr;
+    void* cub_temp = nullptr;
+    size_t cub_temp_bytes = 0;
+};
+
+class MsmEngine {
+public:
+    explicit MsmEngine(int sm_count) : sm_count_(sm_count) {}
+    int upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_bits, MsmSrs* out, cudaStream_t st);
+    void release(MsmSrs* s);
+    // d_scalars: n Montgomery Fr on the device; d_out: 12 x u64 Jacobian on the device
+    int run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n, jacobian* d_out, cudaStream_t st);
+    int g1_add(const jacobian* d_a, const jacobian* d_b, jacobian* d_out, cudaStream_t st);
+    int g1_to_affine(const jacobian* d_in, affine* d_out, cudaStream_t st);
+    void force_lanes(uint32_t g) { force_lanes_ = g; }  // tuning knob (0 = automatic)
+
+private:
+    int sm_count_;
+    uint32_t force_lanes_ = 0;
+};
+
+static inline int cuda_err_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? UZKGE_ERR_OOM : UZKGE_ERR_CUDA; }
+
+}  // namespace uz

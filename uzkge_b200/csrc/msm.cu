@@ -1,0 +1,741 @@
+// msm.cu -- BN254 G1 variable-base MSM for sm_100a: fixed-base window tables + single-pass bucket method.
+//
+// Replaces `G1Projective::normalize_batch` + `G1Projective::msm(&points_raw, &coefs)` inside
+// KZGCommitmentSchemeBN254::commit (/root/reference/uzkge/src/poly_commit/kzg_poly_commitment.rs:278-293).
+//
+// Design (KZG bases are fixed per SRS, HBM is 180 GB):
+//   upload   : table f holds 2^(c*f) * P_i in affine form, f < W = ceil(255 / c)  (built on the device, once)
+//   recode   : scalar -> canonical integer -> W signed radix-2^c digits d_f in [-2^(c-1), 2^(c-1)];
+//              emits (key = |d_f|, val = sign | f*n + i) for every window
+//   sort     : cub::DeviceRadixSort on the c-bit keys                      -> all windows share ONE bucket set
+//   offsets  : bucket boundaries of the sorted key array
+//   accumulate: G lanes per bucket walk the bucket's segment, mixed XYZZ additions (8M + 2S), points gathered
+//              with cp.async through per-thread shared-memory slots (double buffered), then a warp-shuffle
+//              reduction over the G lanes.  Buckets far above the mean (skewed witness scalars: 0/1/small
+//              values) go to a list handled by whole CTAs (slices of LARGE_SLICE entries).
+//   reduce   : sum_b b * B_b without a serial running sum: the buckets form a rows x cols matrix, b = hi*cols+lo;
+//              row sums R_hi and column sums C_lo are plain parallel sums, and
+//              sum_b b*B_b = cols * sum_hi hi*R_hi + sum_lo lo*C_lo, the two small weighted sums are done by
+//              suffix scans with warp shuffles.  No doubling ladder: the tables removed the window combine.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "devmem.cuh"
+#include "internal.h"
+
+namespace uz {
+
+static constexpr int ACC_NT = 256;            // threads per CTA of the accumulate kernel
+static constexpr uint32_t LARGE_SLICE = 4096; // entries per CTA slice of an oversized bucket
+static constexpr int LARGE_NT = 256;
+static constexpr int RED_NT = 128;            // marginal-sum CTAs
+static constexpr int FIN_NT = 256;            // final weighted-sum CTAs
+
+// ------------------------------------------------------------------ recode
+struct RecodeArgs {
+    const fe* scalars;
+    uint32_t n;             // scalars in this MSM
+    uint32_t c, windows;
+    uint32_t table_stride;  // SRS length (distance between tables, in points)
+    uint32_t base_offset;
+    uint32_t* keys;
+    uint32_t* vals;
+};
+
+__global__ void __launch_bounds__(256) msm_recode_kernel(const RecodeArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    fe s = fe_from_mont<FrP>(ld_fe(a.scalars + i));
+    const uint32_t c = a.c, mask = (1u << c) - 1, half = 1u << (c - 1);
+    uint32_t carry = 0;
+    const uint32_t point = a.base_offset + i;
+    for (uint32_t f = 0; f < a.windows; f++) {
+        uint32_t d = (s.l[0] & mask) + carry;
+#pragma unroll
+        for (int k = 0; k < 7; k++) s.l[k] = __funnelshift_r(s.l[k], s.l[k + 1], c);
+        s.l[7] >>= c;
+        uint32_t neg = 0;
+        carry = 0;
+        if (d > half) {  // d in (2^(c-1), 2^c]  ->  d - 2^c in (-2^(c-1), 0]
+            d = (1u << c) - d;
+            neg = d ? 0x80000000u : 0u;
+            carry = 1;
+        }
+        const size_t o = (size_t)f * a.n + i;
+        a.keys[o] = d;
+        a.vals[o] = (f * a.table_stride + point) | neg;
+    }
+}
+
+// offsets[b] = first sorted position whose key is >= b, for b in [0, nbuckets]; offsets[nbuckets] = m
+__global__ void __launch_bounds__(256) msm_offsets_kernel(const uint32_t* __restrict__ keys, uint32_t m, uint32_t nbuckets,
+                                                          uint32_t* __restrict__ offsets) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > m) return;
+    const uint32_t cur = (i == m) ? nbuckets : min(keys[i], nbuckets);
+    const uint32_t lo = (i == 0) ? 0 : min(keys[i - 1], nbuckets) + 1;
+    for (uint32_t b = lo; b <= cur; b++) offsets[b] = i;
+}
+
+// ------------------------------------------------------------------ accumulate
+struct AccArgs {
+    const affine* tables;
+    const uint32_t* vals;     // sorted
+    const uint32_t* offsets;  // nbuckets + 1
+    xyzz* buckets;            // nb_padded
+    uint32_t nbuckets;        // valid bucket ids are 1 .. nbuckets-1
+    uint32_t nb_padded;       // rows * cols of the reduction matrix
+    uint32_t large_threshold;
+    uint32_t* large_list;     // [0] = count, [1 + k] = bucket id
+    uint32_t large_cap;
+};
+
+__device__ __forceinline__ affine lds_point(const uint4* slot, uint32_t stride) {
+    affine p;
+    p.x = fe_from_u4(slot[0], slot[stride]);
+    p.y = fe_from_u4(slot[2 * stride], slot[3 * stride]);
+    return p;
+}
+__device__ __forceinline__ void cp_async_point(uint4* slot, uint32_t stride, const affine* src) {
+    const uint4* g = reinterpret_cast<const uint4*>(src);
+    cp_async16(slot, g);
+    cp_async16(slot + stride, g + 1);
+    cp_async16(slot + 2 * stride, g + 2);
+    cp_async16(slot + 3 * stride, g + 3);
+}
+
+// Walk sorted entries first, first + step, ... < end and add the referenced table points into acc.
+// smem: per-thread slots, stage s chunk k of thread t lives at sm[(s * 4 + k) * NT + t].
+template <int NT>
+__device__ __forceinline__ void accumulate_segment(xyzz& acc, const affine* __restrict__ tables, const uint32_t* __restrict__ vals,
+                                                   uint32_t first, uint32_t end, uint32_t step, uint4* sm) {
+    uint4* slot0 = sm + threadIdx.x;
+    uint4* slot1 = sm + 4 * NT + threadIdx.x;
+    uint32_t j = first;
+    uint32_t v = 0;
+    if (j < end) {
+        v = vals[j];
+        cp_async_point(slot0, NT, tables + (v & 0x7fffffffu));
+    }
+    cp_async_commit();
+    uint32_t stage = 0;
+#pragma unroll 1
+    while (j < end) {
+        const uint32_t jn = j + step;
+        uint32_t vn = 0;
+        if (jn < end) {
+            vn = vals[jn];
+            cp_async_point(stage ? slot0 : slot1, NT, tables + (vn & 0x7fffffffu));
+        }
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the newest group has landed: the current stage is readable
+        affine p = lds_point(stage ? slot1 : slot0, NT);
+        if (v >> 31) p.y = fe_neg<FqP>(p.y);
+        xyzz_madd(acc, p);
+        j = jn;
+        v = vn;
+        stage ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
+template <int G>
+__global__ void __launch_bounds__(ACC_NT) msm_accumulate_kernel(const AccArgs a) {
+    extern __shared__ uint4 acc_smem[];
+    const uint32_t gtid = blockIdx.x * ACC_NT + threadIdx.x;
+    const uint32_t lane = gtid & (G - 1);
+    const uint32_t b = gtid / G;
+    uint32_t start = 0, end = 0;
+    bool write = b < a.nb_padded;
+    if (b >= 1 && b < a.nbuckets) {
+        start = a.offsets[b];
+        end = a.offsets[b + 1];
+        if (end - start > a.large_threshold) {
+            if (lane == 0) {
+                const uint32_t k = atomicAdd(a.large_list, 1u);
+                if (k < a.large_cap) a.large_list[1 + k] = b;
+            }
+            write = false;
+            end = start;
+        }
+    }
+    xyzz acc = xyzz_identity();
+    accumulate_segment<ACC_NT>(acc, a.tables, a.vals, start + lane, end, G, acc_smem);
+#pragma unroll 1
+    for (int off = G >> 1; off > 0; off >>= 1) {
+        const xyzz o = shfl_xor_xyzz(acc, off);
+        xyzz_add(acc, o);
+    }
+    if (write && lane == 0) st_xyzz(a.buckets + b, acc);
+}
+
+// sum of the `acc` of all threads of the CTA, valid in thread 0.  scratch: (NT / 32) xyzz in shared memory.
+template <int NT>
+__device__ __forceinline__ void block_sum_xyzz(xyzz& acc, xyzz* scratch) {
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        const xyzz o = shfl_down_xyzz(acc, off);
+        xyzz_add(acc, o);
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t NW = NT / 32;
+    if (NW > 1) {
+        if (lane == 0) scratch[warp] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            acc = (lane < NW) ? scratch[lane] : xyzz_identity();
+#pragma unroll 1
+            for (int off = NW >> 1; off > 0; off >>= 1) {
+                const xyzz o = shfl_down_xyzz(acc, off);
+                xyzz_add(acc, o);
+            }
+        }
+    }
+}
+
+// ---- oversized buckets: plan (slices per bucket, prefix sum), accumulate per slice, finish per bucket
+struct LargeArgs {
+    const affine* tables;
+    const uint32_t* vals;
+    const uint32_t* offsets;
+    xyzz* buckets;
+    uint32_t* large_list;   // [0] = count, [1 + k] = bucket
+    uint32_t* slice_start;  // large_cap + 1: exclusive prefix of slices per listed bucket
+    xyzz* slice_sums;       // one per slice
+    uint32_t large_cap;
+    uint32_t max_slices;
+};
+
+__global__ void __launch_bounds__(1024) msm_large_plan_kernel(const LargeArgs a) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t nl = min(a.large_list[0], a.large_cap);
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nl; base += 1024) {
+        const uint32_t k = base + threadIdx.x;
+        uint32_t cnt = 0;
+        if (k < nl) {
+            const uint32_t b = a.large_list[1 + k];
+            cnt = (a.offsets[b + 1] - a.offsets[b] + LARGE_SLICE - 1) / LARGE_SLICE;
+        }
+        uint32_t x = cnt;  // inclusive warp scan
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+            if ((threadIdx.x & 31) >= (uint32_t)off) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) wbase += warp_tot[w];
+        const uint32_t carry = carry_s;
+        if (k < nl) a.slice_start[k] = carry + wbase + x - cnt;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + wbase + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.slice_start[nl] = carry_s;
+}
+
+__global__ void __launch_bounds__(LARGE_NT) msm_large_accumulate_kernel(const LargeArgs a) {
+    extern __shared__ uint4 acc_smem[];
+    __shared__ xyzz scratch[LARGE_NT / 32];
+    const uint32_t nl = min(a.large_list[0], a.large_cap);
+    const uint32_t total = min(a.slice_start[nl], a.max_slices);
+    const uint32_t s = blockIdx.x;
+    if (s >= total) return;
+    // largest k with slice_start[k] <= s
+    uint32_t lo = 0, hi = nl;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.slice_start[mid] <= s) lo = mid; else hi = mid;
+    }
+    const uint32_t b = a.large_list[1 + lo];
+    const uint32_t first = a.offsets[b] + (s - a.slice_start[lo]) * LARGE_SLICE;
+    const uint32_t end = min(first + LARGE_SLICE, a.offsets[b + 1]);
+    xyzz acc = xyzz_identity();
+    accumulate_segment<LARGE_NT>(acc, a.tables, a.vals, first + threadIdx.x, end, LARGE_NT, acc_smem);
+    block_sum_xyzz<LARGE_NT>(acc, scratch);
+    if (threadIdx.x == 0) st_xyzz(a.slice_sums + s, acc);
+}
+
+// one warp per listed bucket: sum its slice sums
+__global__ void __launch_bounds__(32) msm_large_finish_kernel(const LargeArgs a) {
+    const uint32_t nl = min(a.large_list[0], a.large_cap);
+    const uint32_t k = blockIdx.x;
+    if (k >= nl) return;
+    const uint32_t s0 = a.slice_start[k], s1 = min(a.slice_start[k + 1], a.max_slices);
+    xyzz acc = xyzz_identity();
+#pragma unroll 1
+    for (uint32_t s = s0 + threadIdx.x; s < s1; s += 32) {
+        const xyzz v = ld_xyzz(a.slice_sums + s);
+        xyzz_add(acc, v);
+    }
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        const xyzz o = shfl_down_xyzz(acc, off);
+        xyzz_add(acc, o);
+    }
+    if (threadIdx.x == 0) st_xyzz(a.buckets + a.large_list[1 + k], acc);
+}
+
+// ------------------------------------------------------------------ reduce
+// CTA o < rows: R[o] = sum_c B[o][c];  CTA rows + o: C[o] = sum_r B[r][o]
+struct MarginalArgs {
+    const xyzz* buckets;
+    xyzz* marg;  // rows + cols
+    uint32_t rows, cols;
+};
+__global__ void __launch_bounds__(RED_NT) msm_marginals_kernel(const MarginalArgs a) {
+    __shared__ xyzz scratch[RED_NT / 32];
+    uint32_t o = blockIdx.x;
+    const xyzz* base;
+    uint32_t count, stride;
+    if (o < a.rows) {
+        base = a.buckets + (size_t)o * a.cols;
+        count = a.cols;
+        stride = 1;
+    } else {
+        base = a.buckets + (o - a.rows);
+        count = a.rows;
+        stride = a.cols;
+    }
+    xyzz acc = xyzz_identity();
+#pragma unroll 1
+    for (uint32_t e = threadIdx.x; e < count; e += RED_NT) {
+        const xyzz v = ld_xyzz(base + (size_t)e * stride);
+        xyzz_add(acc, v);
+    }
+    block_sum_xyzz<RED_NT>(acc, scratch);
+    if (threadIdx.x == 0) st_xyzz(a.marg + blockIdx.x, acc);
+}
+
+// Lanes 0..nl-1 of a warp hold consecutive blocks (lane 0 lowest) of 2^loglen indices each, as
+// (S = plain sum, T = sum of (index - block start) * X).  Returns the combined (S, T) in lane 0:
+//   S = sum_l S_l,  T = sum_l T_l + 2^loglen * sum_{l >= 1} (sum_{m >= l} S_m).
+__device__ __forceinline__ void warp_weighted_combine(xyzz& S, xyzz& T, uint32_t loglen) {
+    const uint32_t lane = threadIdx.x & 31;
+    // inclusive suffix scan of S
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        const xyzz o = shfl_down_xyzz(S, off);
+        if (lane + off < 32) xyzz_add(S, o);
+    }
+    // W = sum_{l >= 1} P_l ; lane 0 contributes nothing
+    xyzz W = lane ? S : xyzz_identity();
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        const xyzz o = shfl_down_xyzz(W, off);
+        xyzz_add(W, o);
+        const xyzz t = shfl_down_xyzz(T, off);
+        xyzz_add(T, t);
+    }
+    if (lane == 0) {
+        for (uint32_t i = 0; i < loglen; i++) W = xyzz_dbl(W);
+        xyzz_add(T, W);
+    }
+}
+
+// weighted sum sum_j j * X[j], j < m, by one CTA of FIN_NT threads; result in thread 0.
+__device__ __forceinline__ xyzz block_weighted_sum(const xyzz* X, uint32_t m, xyzz* sh_s, xyzz* sh_t) {
+    uint32_t logq = 0;
+    while (((uint32_t)FIN_NT << logq) < m) logq++;
+    const uint32_t q = 1u << logq;
+    const uint32_t lo = min(threadIdx.x * q, m), hi = min(lo + q, m);
+    xyzz run = xyzz_identity(), acc = xyzz_identity();
+#pragma unroll 1
+    for (uint32_t j = hi; j > lo + 1; j--) {
+        const xyzz v = ld_xyzz(X + j - 1);
+        xyzz_add(run, v);
+        xyzz_add(acc, run);
+    }
+    if (hi > lo) {
+        const xyzz v = ld_xyzz(X + lo);
+        xyzz_add(run, v);
+    }
+    warp_weighted_combine(run, acc, logq);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sh_s[warp] = run;
+        sh_t[warp] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        constexpr uint32_t NW = FIN_NT / 32;
+        run = lane < NW ? sh_s[lane] : xyzz_identity();
+        acc = lane < NW ? sh_t[lane] : xyzz_identity();
+        warp_weighted_combine(run, acc, logq + 5);
+    }
+    return acc;
+}
+
+struct FinalArgs {
+    const xyzz* marg;    // rows + cols marginal sums
+    xyzz* partial;       // 2 entries
+    uint32_t* ticket;
+    jacobian* out;
+    uint32_t rows, cols, logcols;
+};
+// CTA 0: sum_hi hi * R[hi];  CTA 1: sum_lo lo * C[lo];  the CTA that finishes last combines:
+//   result = 2^logcols * A + B
+__global__ void __launch_bounds__(FIN_NT) msm_final_kernel(const FinalArgs a) {
+    __shared__ xyzz sh_s[FIN_NT / 32], sh_t[FIN_NT / 32];
+    __shared__ uint32_t is_last;
+    const xyzz* X = blockIdx.x == 0 ? a.marg : a.marg + a.rows;
+    const uint32_t m = blockIdx.x == 0 ? a.rows : a.cols;
+    xyzz r = block_weighted_sum(X, m, sh_s, sh_t);
+    if (threadIdx.x == 0) {
+        st_xyzz(a.partial + blockIdx.x, r);
+        __threadfence();
+        is_last = (atomicAdd(a.ticket, 1u) == 1u);
+    }
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    __threadfence();
+    xyzz A = ld_xyzz(a.partial), B = ld_xyzz(a.partial + 1);
+    for (uint32_t i = 0; i < a.logcols; i++) A = xyzz_dbl(A);
+    xyzz_add(A, B);
+    const jacobian j = xyzz_to_jacobian(A);
+    st_fe(&a.out->x, j.x);
+    st_fe(&a.out->y, j.y);
+    st_fe(&a.out->z, j.z);
+    *a.ticket = 0;
+}
+
+__global__ void msm_identity_kernel(jacobian* out) {
+    const jacobian j = xyzz_to_jacobian(xyzz_identity());
+    st_fe(&out->x, j.x);
+    st_fe(&out->y, j.y);
+    st_fe(&out->z, j.z);
+}
+
+// ------------------------------------------------------------------ small group helpers
+__device__ __forceinline__ xyzz jacobian_to_xyzz(const jacobian& p) {
+    xyzz r;
+    if (fe_is_zero(p.z)) return xyzz_identity();
+    r.x = p.x;
+    r.y = p.y;
+    r.zz = FQ_SQR(p.z);
+    r.zzz = FQ_MUL(r.zz, p.z);
+    return r;
+}
+__device__ __forceinline__ jacobian ld_jacobian(const jacobian* p) {
+    jacobian r;
+    r.x = ld_fe(&p->x);
+    r.y = ld_fe(&p->y);
+    r.z = ld_fe(&p->z);
+    return r;
+}
+__global__ void g1_add_kernel(const jacobian* a, const jacobian* b, jacobian* out) {
+    xyzz x = jacobian_to_xyzz(ld_jacobian(a));
+    const xyzz y = jacobian_to_xyzz(ld_jacobian(b));
+    xyzz_add(x, y);
+    const jacobian j = xyzz_to_jacobian(x);
+    st_fe(&out->x, j.x);
+    st_fe(&out->y, j.y);
+    st_fe(&out->z, j.z);
+}
+__global__ void g1_to_affine_kernel(const jacobian* in, affine* out) {
+    const affine r = xyzz_to_affine(jacobian_to_xyzz(ld_jacobian(in)));
+    st_affine(out, r);
+}
+
+// ------------------------------------------------------------------ fixed-base tables
+// next[i] = 2^c * prev[i] for i in the slab [first, first + count).  Thread t handles the points
+// first + t + j * nthreads, j < B: doubles each in XYZZ (kept in `tmp`), then normalises the B points with
+// one shared inversion (Montgomery's trick; `pre` holds the running products).
+struct TableArgs {
+    const affine* prev;
+    affine* next;
+    xyzz* tmp;   // count entries
+    fe* pre;     // count entries
+    uint32_t count, c, per_thread, nthreads;
+};
+__global__ void __launch_bounds__(128) msm_table_kernel(const TableArgs a) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nthreads) return;
+    fe prod = fe_one<FqP>();
+#pragma unroll 1
+    for (uint32_t j = 0; j < a.per_thread; j++) {
+        const uint32_t i = t + j * a.nthreads;
+        if (i >= a.count) break;
+        const affine p = ld_affine(a.prev + i);
+        xyzz q;
+        if (affine_is_identity(p)) {
+            q = xyzz_identity();
+        } else {
+            q = xyzz_dbl_affine(p);
+            for (uint32_t k = 1; k < a.c; k++) q = xyzz_dbl(q);
+        }
+        st_xyzz(a.tmp + i, q);
+        if (!xyzz_is_identity(q)) prod = FQ_MUL(prod, FQ_MUL(q.zz, q.zzz));
+        st_fe(a.pre + i, prod);
+    }
+    fe inv = fe_inv<FqP>(prod);
+#pragma unroll 1
+    for (uint32_t j = a.per_thread; j-- > 0;) {
+        const uint32_t i = t + j * a.nthreads;
+        if (i >= a.count) continue;
+        const xyzz q = ld_xyzz(a.tmp + i);
+        affine r;
+        if (xyzz_is_identity(q)) {
+            r.x = fe_zero();
+            r.y = fe_zero();
+        } else {
+            const fe before = j ? ld_fe(a.pre + (i - a.nthreads)) : fe_one<FqP>();
+            const fe ti = FQ_MUL(inv, before);            // 1 / (zz * zzz)
+            inv = FQ_MUL(inv, FQ_MUL(q.zz, q.zzz));
+            r.x = FQ_MUL(q.x, FQ_MUL(ti, q.zzz));         // X / ZZ
+            r.y = FQ_MUL(q.y, FQ_MUL(ti, q.zz));          // Y / ZZZ
+        }
+        st_affine(a.next + i, r);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+
+static uint32_t choose_window_bits(size_t n) {
+    // minimise  windows * n * 10 (mixed adds) + 2^(c-1) * 2 * 14 (marginal sums)  over c, ties to the smaller c
+    double best = 1e300;
+    uint32_t best_c = 8;
+    for (uint32_t c = 8; c <= 22; c++) {
+        const uint32_t w = (255 + c - 1) / c;
+        if ((uint64_t)w * n >= (1ull << 31)) continue;
+        const double cost = (double)w * (double)n * 10.0 + (double)(1ull << (c - 1)) * 28.0 * 1.5;
+        if (cost < best * 0.97) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
+}
+
+#define UZ_CUDA_TRY(expr)                                   \
+    do {                                                    \
+        cudaError_t e__ = (expr);                           \
+        if (e__ != cudaSuccess) return cuda_err_code(e__);  \
+    } while (0)
+
+int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_bits, MsmSrs* s, cudaStream_t st) {
+    if (n == 0 || n >= (1ull << 28)) return UZKGE_ERR_SIZE;
+    uint32_t c = window_bits ? window_bits : choose_window_bits(n);
+    if (c < 2 || c > 24) return UZKGE_ERR_SIZE;
+    const uint32_t windows = (255 + c - 1) / c;
+    if ((uint64_t)windows * n >= (1ull << 31)) return UZKGE_ERR_SIZE;
+    *s = MsmSrs();
+    s->n = n;
+    s->c = c;
+    s->windows = windows;
+    s->nbuckets = (1u << (c - 1)) + 1;
+    s->logcols = c / 2;                       // cols = 2^ceil((c-1)/2)
+    s->cols = 1u << s->logcols;
+    s->rows = (1u << (c - 1 - s->logcols)) + 1;  // + 1: the top bucket 2^(c-1) sits alone in the last row
+    s->nb_padded = s->rows * s->cols;
+    const size_t m = (size_t)windows * n;
+    s->large_cap = (uint32_t)(m / LARGE_SLICE + 1);
+    s->max_slices = (uint32_t)(m / LARGE_SLICE + s->large_cap);
+
+    size_t total = 0;
+    auto take = [&](size_t bytes) {
+        const size_t off = total;
+        total += (bytes + 255) & ~(size_t)255;
+        return off;
+    };
+    const size_t o_tables = take(sizeof(affine) * m);
+    const size_t o_keys_a = take(4 * m), o_keys_b = take(4 * m), o_vals_a = take(4 * m), o_vals_b = take(4 * m);
+    const size_t o_offsets = take(4 * ((size_t)s->nbuckets + 1));
+    const size_t o_large = take(4 * ((size_t)s->large_cap + 1));
+    const size_t o_slice_start = take(4 * ((size_t)s->large_cap + 1));
+    const size_t o_slice_sums = take(sizeof(xyzz) * s->max_slices);
+    const size_t o_buckets = take(sizeof(xyzz) * s->nb_padded);
+    const size_t o_marg = take(sizeof(xyzz) * ((size_t)s->rows + s->cols));
+    const size_t o_partial = take(sizeof(xyzz) * 2);
+    const size_t o_ticket = take(256);
+    cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
+    s->cub_temp_bytes = 0;
+    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_temp_bytes, dk, dv, (int)m, 0, (int)c, st));
+    const size_t o_cub = take(s->cub_temp_bytes + 256);
+    UZ_CUDA_TRY(cudaMalloc(&s->arena, total));
+    s->bytes = total;
+    char* base = (char*)s->arena;
+    s->tables = (affine*)(base + o_tables);
+    s->keys_a = (uint32_t*)(base + o_keys_a);
+    s->keys_b = (uint32_t*)(base + o_keys_b);
+    s->vals_a = (uint32_t*)(base + o_vals_a);
+    s->vals_b = (uint32_t*)(base + o_vals_b);
+    s->offsets = (uint32_t*)(base + o_offsets);
+    s->large_list = (uint32_t*)(base + o_large);
+    s->slice_start = (uint32_t*)(base + o_slice_start);
+    s->slice_sums = (xyzz*)(base + o_slice_sums);
+    s->buckets = (xyzz*)(base + o_buckets);
+    s->marg = (xyzz*)(base + o_marg);
+    s->partial = (xyzz*)(base + o_partial);
+    s->ticket = (uint32_t*)(base + o_ticket);
+    s->cub_temp = base + o_cub;
+
+    cudaEvent_t e0, e1;
+    UZ_CUDA_TRY(cudaEventCreate(&e0));
+    UZ_CUDA_TRY(cudaEventCreate(&e1));
+    UZ_CUDA_TRY(cudaMemsetAsync(s->ticket, 0, 256, st));
+    UZ_CUDA_TRY(cudaMemcpyAsync(s->tables, affine_xy_host, sizeof(affine) * n, cudaMemcpyHostToDevice, st));
+    UZ_CUDA_TRY(cudaEventRecord(e0, st));
+    // slabs of at most 2^20 points bound the XYZZ / prefix-product scratch
+    const size_t slab = n < (1u << 20) ? n : (1u << 20);
+    xyzz* tmp = nullptr;
+    UZ_CUDA_TRY(cudaMalloc(&tmp, slab * (sizeof(xyzz) + sizeof(fe))));
+    fe* pre = (fe*)(tmp + slab);
+    for (uint32_t f = 1; f < windows; f++) {
+        for (size_t first = 0; first < n; first += slab) {
+            TableArgs ta;
+            ta.count = (uint32_t)((n - first) < slab ? (n - first) : slab);
+            ta.prev = s->tables + (size_t)(f - 1) * n + first;
+            ta.next = s->tables + (size_t)f * n + first;
+            ta.tmp = tmp;
+            ta.pre = pre;
+            ta.c = c;
+            uint32_t per = (uint32_t)(ta.count / ((size_t)sm_count_ * 512));
+            per = per < 1 ? 1 : (per > 16 ? 16 : per);
+            ta.per_thread = per;
+            ta.nthreads = (ta.count + per - 1) / per;
+            msm_table_kernel<<<(ta.nthreads + 127) / 128, 128, 0, st>>>(ta);
+            UZ_COUNT_LAUNCH(1);
+        }
+    }
+    UZ_CUDA_TRY(cudaGetLastError());
+    UZ_CUDA_TRY(cudaEventRecord(e1, st));
+    UZ_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    s->precompute_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(tmp);
+    return UZKGE_OK;
+}
+
+void MsmEngine::release(MsmSrs* s) {
+    if (s->arena) cudaFree(s->arena);
+    *s = MsmSrs();
+}
+
+template <int G>
+static cudaError_t launch_accumulate(const AccArgs& a, cudaStream_t st) {
+    const uint64_t threads = (uint64_t)a.nb_padded * G;
+    const uint32_t grid = (uint32_t)((threads + ACC_NT - 1) / ACC_NT);
+    msm_accumulate_kernel<G><<<grid, ACC_NT, 2 * 4 * ACC_NT * sizeof(uint4), st>>>(a);
+    return cudaGetLastError();
+}
+
+int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n, jacobian* d_out, cudaStream_t st) {
+    if (base_offset > s->n || n > s->n - base_offset) return UZKGE_ERR_SIZE;
+    if (n == 0) {
+        msm_identity_kernel<<<1, 1, 0, st>>>(d_out);
+        UZ_COUNT_LAUNCH(1);
+        UZ_CUDA_TRY(cudaGetLastError());
+        return UZKGE_OK;
+    }
+    const uint32_t m = (uint32_t)(s->windows * n);
+    RecodeArgs ra;
+    ra.scalars = d_scalars;
+    ra.n = (uint32_t)n;
+    ra.c = s->c;
+    ra.windows = s->windows;
+    ra.table_stride = (uint32_t)s->n;
+    ra.base_offset = (uint32_t)base_offset;
+    ra.keys = s->keys_a;
+    ra.vals = s->vals_a;
+    msm_recode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ra);
+    UZ_CUDA_TRY(cudaGetLastError());
+
+    cub::DoubleBuffer<uint32_t> dk(s->keys_a, s->keys_b), dv(s->vals_a, s->vals_b);
+    size_t temp = s->cub_temp_bytes;
+    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_temp, temp, dk, dv, (int)m, 0, (int)s->c, st));
+    const uint32_t* keys = dk.Current();
+    const uint32_t* vals = dv.Current();
+
+    msm_offsets_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(keys, m, s->nbuckets, s->offsets);
+    UZ_CUDA_TRY(cudaGetLastError());
+    UZ_CUDA_TRY(cudaMemsetAsync(s->large_list, 0, 4, st));
+
+    // lanes per bucket: aim at ~48 entries per lane
+    const double mean = (double)m / (double)(s->nbuckets - 1);
+    uint32_t g = 1;
+    while (g < 32 && mean / (g * 2) >= 40.0) g *= 2;
+    if (force_lanes_) g = force_lanes_;
+    AccArgs aa;
+    aa.tables = s->tables;
+    aa.vals = vals;
+    aa.offsets = s->offsets;
+    aa.buckets = s->buckets;
+    aa.nbuckets = s->nbuckets;
+    aa.nb_padded = s->nb_padded;
+    uint32_t thr = (uint32_t)(mean * 8.0);
+    const uint32_t thr_min = 128 * g < LARGE_SLICE ? LARGE_SLICE : 128 * g;
+    aa.large_threshold = thr < thr_min ? thr_min : thr;
+    aa.large_list = s->large_list;
+    aa.large_cap = s->large_cap;
+    cudaError_t e;
+    switch (g) {
+        case 1: e = launch_accumulate<1>(aa, st); break;
+        case 2: e = launch_accumulate<2>(aa, st); break;
+        case 4: e = launch_accumulate<4>(aa, st); break;
+        case 8: e = launch_accumulate<8>(aa, st); break;
+        case 16: e = launch_accumulate<16>(aa, st); break;
+        default: e = launch_accumulate<32>(aa, st); break;
+    }
+    UZ_CUDA_TRY(e);
+
+    LargeArgs la;
+    la.tables = s->tables;
+    la.vals = vals;
+    la.offsets = s->offsets;
+    la.buckets = s->buckets;
+    la.large_list = s->large_list;
+    la.slice_start = s->slice_start;
+    la.slice_sums = s->slice_sums;
+    la.large_cap = s->large_cap;
+    la.max_slices = s->max_slices;
+    // upper bounds for this m (the kernels read the real counts on the device; surplus CTAs exit at once)
+    const uint32_t cap_now = (uint32_t)(m / aa.large_threshold + 1);
+    const uint32_t slices_now = m / LARGE_SLICE + cap_now;
+    msm_large_plan_kernel<<<1, 1024, 0, st>>>(la);
+    msm_large_accumulate_kernel<<<slices_now, LARGE_NT, 2 * 4 * LARGE_NT * sizeof(uint4), st>>>(la);
+    msm_large_finish_kernel<<<cap_now, 32, 0, st>>>(la);
+    UZ_CUDA_TRY(cudaGetLastError());
+
+    MarginalArgs ma;
+    ma.buckets = s->buckets;
+    ma.marg = s->marg;
+    ma.rows = s->rows;
+    ma.cols = s->cols;
+    msm_marginals_kernel<<<s->rows + s->cols, RED_NT, 0, st>>>(ma);
+    FinalArgs fa;
+    fa.marg = s->marg;
+    fa.partial = s->partial;
+    fa.ticket = s->ticket;
+    fa.out = d_out;
+    fa.rows = s->rows;
+    fa.cols = s->cols;
+    fa.logcols = s->logcols;
+    msm_final_kernel<<<2, FIN_NT, 0, st>>>(fa);
+    UZ_CUDA_TRY(cudaGetLastError());
+    UZ_COUNT_LAUNCH(8 + 3);  // own kernels + CUB's radix-sort launches (histogram, scan, onesweep passes: >= 3)
+    return UZKGE_OK;
+}
+
+int MsmEngine::g1_add(const jacobian* d_a, const jacobian* d_b, jacobian* d_out, cudaStream_t st) {
+    g1_add_kernel<<<1, 1, 0, st>>>(d_a, d_b, d_out);
+    UZ_COUNT_LAUNCH(1);
+    UZ_CUDA_TRY(cudaGetLastError());
+    return UZKGE_OK;
+}
+int MsmEngine::g1_to_affine(const jacobian* d_in, affine* d_out, cudaStream_t st) {
+    g1_to_affine_kernel<<<1, 1, 0, st>>>(d_in, d_out);
+    UZ_COUNT_LAUNCH(1);
+    UZ_CUDA_TRY(cudaGetLastError());
+    return UZKGE_OK;
+}
+
+}  // namespace uz

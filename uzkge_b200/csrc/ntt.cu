@@ -1,0 +1,386 @@
+// ntt.cu -- Fr NTT / iNTT / coset-FFT kernels (radix-2 and 3 * 2^k domains) for sm_100a.
+//
+// Replaces domain.fft / domain.ifft behind FpPolynomial::{fft,ifft,coset_fft,coset_ifft}_with_domain
+// (/root/reference/uzkge/src/poly_commit/field_polynomial.rs:583-607) and the serial coset scaling of
+// mul_var_assign (:470-477).  See ntt_plan.h for the decomposition.
+//
+// One CTA transforms one R x C tile staged in shared memory: the tile is loaded with 128-bit accesses,
+// log2(R) decimation-in-frequency butterfly stages run on it, and it is written back with the
+// digit-reversed row index, the inter-pass twiddle, and (last pass) the inverse-transform index flip, the
+// 1/N factor and the coset post-scale all fused into the store.  Twiddles come from small HBM/L2-resident
+// tables: w_R^j for the butterfly stages and a two-level table x^e = hi[e >> 12] * lo[e & 4095] for the
+// inter-pass twiddles and the coset powers.
+#include <cuda_runtime.h>
+
+#include "devmem.cuh"
+#include "internal.h"
+#include "ntt_plan.h"
+
+namespace uz {
+
+// shared-memory tile: two 16-byte planes so that a warp's 128-bit accesses to consecutive elements are
+// conflict-free; columns are rotated by the row index so that row-major and column-major walks both spread
+// over the banks.
+struct TileView {
+    uint4* lo;
+    uint4* hi;
+    uint32_t logC, cmask;
+    __device__ __forceinline__ uint32_t pos(uint32_t r, uint32_t c) const { return (r << logC) | ((c + r) & cmask); }
+    __device__ __forceinline__ fe ld(uint32_t p) const {
+        fe x;
+        uint4 a = lo[p], b = hi[p];
+        x.l[0] = a.x; x.l[1] = a.y; x.l[2] = a.z; x.l[3] = a.w;
+        x.l[4] = b.x; x.l[5] = b.y; x.l[6] = b.z; x.l[7] = b.w;
+        return x;
+    }
+    __device__ __forceinline__ void st(uint32_t p, const fe& x) const {
+        lo[p] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
+        hi[p] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
+    }
+};
+
+__device__ __forceinline__ fe pow2l(const fe* lo, const fe* hi, uint64_t e) {
+    fe a = ldg_fe(lo + (e & ((1u << NTT_LOG_TWLO) - 1)));
+    uint64_t h = e >> NTT_LOG_TWLO;
+    if (h == 0) return a;
+    return fe_mul<FrP>(a, ldg_fe(hi + h));
+}
+
+struct NttKernelArgs {
+    NttPass p;
+    const fe* in;
+    fe* out;
+    uint64_t n;
+    uint64_t len_in;
+    const fe* stage_tab;
+    const fe* w_lo;
+    const fe* w_hi;
+    const fe* g_lo;  // coset powers (forward: g^j, inverse: g^j / N) or null
+    const fe* g_hi;
+    fe scale;        // 1/N (inverse without coset)
+    uint32_t inverse, pre_coset, post_coset, has_scale, zero_pad;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
+    extern __shared__ uint4 ntt_smem[];
+    const NttPass& p = a.p;
+    const uint32_t logR = p.logR, logC = p.logC;
+    const uint32_t R = 1u << logR, C = 1u << logC, T = R << logC;
+    TileView tv{ntt_smem, ntt_smem + T, logC, C - 1};
+
+    uint32_t tile = blockIdx.x;
+    const uint32_t t = tile % p.inner_tiles;
+    tile /= p.inner_tiles;
+    const uint32_t o = tile % p.outer;
+    const uint32_t b = tile / p.outer;
+
+    // ---- load (+ zero padding, + coset pre-scale on the very first read of the input)
+    for (uint32_t idx = threadIdx.x; idx < T; idx += NT) {
+        uint32_t r, c;
+        if (p.in_r_contig) {
+            r = idx & (R - 1);
+            c = idx >> logR;
+        } else {
+            c = idx & (C - 1);
+            r = idx >> logC;
+        }
+        const uint64_t g = ntt_in_index(p, b, o, t, r, c);
+        fe x;
+        if (a.zero_pad && g >= a.len_in) {
+            x = fe_zero();
+        } else {
+            x = ld_fe(a.in + g);
+            if (a.pre_coset) x = fe_mul<FrP>(x, pow2l(a.g_lo, a.g_hi, g));
+        }
+        tv.st(tv.pos(r, c), x);
+    }
+    __syncthreads();
+
+    // ---- decimation-in-frequency stages: (u, v) -> (u + v, (u - v) * w_{2h}^j); result row = bitrev(k)
+    for (int s = (int)logR - 1; s >= 0; s--) {
+        const uint32_t h = 1u << s;
+        const uint32_t tw_shift = logR - 1 - s;
+        for (uint32_t bb = threadIdx.x; bb < (T >> 1); bb += NT) {
+            const uint32_t c = bb & (C - 1), pr = bb >> logC;
+            const uint32_t j = pr & (h - 1);
+            const uint32_t r = ((pr >> s) << (s + 1)) | j;
+            const uint32_t p0 = tv.pos(r, c), p1 = tv.pos(r + h, c);
+            const fe u = tv.ld(p0), v = tv.ld(p1);
+            fe d = fe_sub<FrP>(u, v);
+            if (s > 0) d = fe_mul<FrP>(d, ldg_fe(a.stage_tab + (size_t)(j << tw_shift) * p.stage_stride));
+            tv.st(p0, fe_add<FrP>(u, v));
+            tv.st(p1, d);
+        }
+        __syncthreads();
+    }
+
+    // ---- store: natural row index k lives at row bitrev(k)
+    for (uint32_t idx = threadIdx.x; idx < T; idx += NT) {
+        const uint32_t c = idx & (C - 1), k = idx >> logC;
+        fe x = tv.ld(tv.pos(ntt_bitrev(k, logR), c));
+        if (p.tw_mul) {
+            const uint64_t e = ntt_tw_exponent(p, t, k, c);
+            if (e) x = fe_mul<FrP>(x, pow2l(a.w_lo, a.w_hi, e));
+        }
+        uint64_t g = ntt_out_index(p, b, o, t, k, c);
+        if (p.last) {
+            if (a.inverse && g) g = a.n - g;
+            if (a.post_coset)
+                x = fe_mul<FrP>(x, pow2l(a.g_lo, a.g_hi, g));
+            else if (a.has_scale)
+                x = fe_mul<FrP>(x, a.scale);
+        }
+        st_fe(a.out + g, x);
+    }
+}
+
+// radix-3 pre-pass for N = 3 * M:  y[k*M + n] = w_N^(n*k) * sum_{m<3} x[m*M + n] * w_3^(m*k)
+struct Radix3Args {
+    const fe* in;
+    fe* out;
+    uint64_t m, len_in;
+    const fe* w_lo;
+    const fe* w_hi;
+    const fe* g_lo;
+    const fe* g_hi;
+    fe w3, w3sq;
+    uint32_t pre_coset;
+};
+__global__ void __launch_bounds__(256) ntt_radix3_kernel(const Radix3Args a) {
+    const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.m) return;
+    fe x[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const uint64_t g = (uint64_t)i * a.m + n;
+        if (g < a.len_in) {
+            x[i] = ld_fe(a.in + g);
+            if (a.pre_coset) x[i] = fe_mul<FrP>(x[i], pow2l(a.g_lo, a.g_hi, g));
+        } else {
+            x[i] = fe_zero();
+        }
+    }
+    const fe y0 = fe_add<FrP>(fe_add<FrP>(x[0], x[1]), x[2]);
+    const fe b1 = fe_mul<FrP>(x[1], a.w3), c1 = fe_mul<FrP>(x[2], a.w3sq);
+    const fe b2 = fe_mul<FrP>(x[1], a.w3sq), c2 = fe_mul<FrP>(x[2], a.w3);
+    fe y1 = fe_add<FrP>(fe_add<FrP>(x[0], b1), c1);
+    fe y2 = fe_add<FrP>(fe_add<FrP>(x[0], b2), c2);
+    if (n) {
+        y1 = fe_mul<FrP>(y1, pow2l(a.w_lo, a.w_hi, n));
+        y2 = fe_mul<FrP>(y2, pow2l(a.w_lo, a.w_hi, 2 * n));
+    }
+    st_fe(a.out + n, y0);
+    st_fe(a.out + a.m + n, y1);
+    st_fe(a.out + 2 * a.m + n, y2);
+}
+
+// lo[i] = premul * base^i (i < 2^12);  hi[i] = base^(i << 12) (i < n_hi)
+__global__ void ntt_build_pow_tables(fe base, fe premul, fe* lo, fe* hi, uint32_t n_hi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nlo = 1u << NTT_LOG_TWLO;
+    if (i < nlo) {
+        st_fe(lo + i, fe_mul<FrP>(fe_pow_u64<FrP>(base, i), premul));
+    } else if (i - nlo < n_hi) {
+        st_fe(hi + (i - nlo), fe_pow_u64<FrP>(base, (uint64_t)(i - nlo) << NTT_LOG_TWLO));
+    }
+}
+// tab[j] = base^j, j < cnt
+__global__ void ntt_build_stage_table(fe base, fe* tab, uint32_t cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) st_fe(tab + i, fe_pow_u64<FrP>(base, i));
+}
+
+// ------------------------------------------------------------------ host side
+// LARGE = 5^((r-1)/(2^28 * 9)) in Montgomery form: generator of the 2^28 * 3^2 subgroup;
+// w_N = LARGE^(3^(2-a) * 2^(28-b)) for N = 3^a 2^b.  Pinned by tests/golden/domain_kat.json.
+static fe fr_large_subgroup_root() {
+    fe g = fe_zero();
+    g.l[0] = 5;
+    g = fe_to_mont<FrP>(g);
+    // exponent (r - 1) / (2^28 * 9), little-endian 32-bit limbs
+    static const uint32_t e[8] = {0x2358d107u, 0x9f828f3bu, 0xd5b19cf2u, 0x58026433u,
+                                  0x2b395f7du, 0xacca004au, 0x5607a7e8u, 0x00000000u};
+    fe acc = fe_one<FrP>();
+    for (int i = 255; i >= 0; i--) {
+        acc = fe_sqr<FrP>(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = fe_mul<FrP>(acc, g);
+    }
+    return acc;
+}
+
+fe ntt_root_of_unity(uint64_t n, bool* ok) {
+    uint32_t a = 0, b = 0;
+    uint64_t m = n;
+    *ok = false;
+    if (n == 0) return fe_zero();
+    while (m % 3 == 0) { m /= 3; a++; }
+    while (m % 2 == 0) { m /= 2; b++; }
+    if (m != 1 || a > 2 || b > 28) return fe_zero();
+    static const fe large = fr_large_subgroup_root();
+    fe w = large;
+    for (uint32_t i = 0; i < 2 - a; i++) w = fe_mul<FrP>(fe_sqr<FrP>(w), w);
+    for (uint32_t i = 0; i < 28 - b; i++) w = fe_sqr<FrP>(w);
+    *ok = true;
+    return w;
+}
+
+static fe host_pow(fe a, uint64_t e) { return fe_pow_u64<FrP>(a, e); }
+
+const NttDomain* NttEngine::domain(uint64_t n, cudaStream_t st) {
+    auto it = domains_.find(n);
+    if (it != domains_.end()) return &it->second;
+    NttDomain d;
+    if (!ntt_make_plan(n, cfg_log_tile_, cfg_max_log_r_, cfg_two_pass_max_, &d.plan)) return nullptr;
+    // small transforms: shrink the column count until there are enough CTAs to cover the SMs
+    for (uint32_t i = 0; i < d.plan.npass; i++) {
+        NttPass& p = d.plan.pass[i];
+        while (p.logC > 2 && (uint64_t)p.inner_tiles * p.outer * p.batch < 2ull * sm_count_) {
+            p.logC--;
+            p.inner_tiles <<= 1;
+        }
+    }
+    bool ok;
+    d.omega = ntt_root_of_unity(n, &ok);
+    if (!ok) return nullptr;
+    fe nf = fe_zero();
+    nf.l[0] = (uint32_t)n;
+    nf.l[1] = (uint32_t)(n >> 32);
+    d.n_inv = fe_inv<FrP>(fe_to_mont<FrP>(nf));
+    d.w3 = host_pow(d.omega, d.plan.m);  // only meaningful when mixed
+    d.w3sq = fe_sqr<FrP>(d.w3);
+    const uint32_t nlo = 1u << NTT_LOG_TWLO;
+    d.n_hi = (uint32_t)((n >> NTT_LOG_TWLO) + 1);
+    const uint32_t log_rtab = d.plan.logm < 12 ? d.plan.logm : 12;
+    d.n_stage = log_rtab ? (1u << (log_rtab - 1)) : 1;
+    if (cudaMalloc(&d.w_lo, sizeof(fe) * ((size_t)nlo + d.n_hi + d.n_stage)) != cudaSuccess) return nullptr;
+    d.w_hi = d.w_lo + nlo;
+    d.stage = d.w_hi + d.n_hi;
+    const uint32_t tot = nlo + d.n_hi;
+    ntt_build_pow_tables<<<(tot + 127) / 128, 128, 0, st>>>(d.omega, fe_one<FrP>(), d.w_lo, d.w_hi, d.n_hi);
+    const fe w_rtab = host_pow(d.omega, n >> log_rtab);
+    ntt_build_stage_table<<<(d.n_stage + 127) / 128, 128, 0, st>>>(w_rtab, d.stage, d.n_stage);
+    UZ_COUNT_LAUNCH(2);
+    // tables are built once; later calls may come on other streams
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
+    auto res = domains_.emplace(n, d);
+    return &res.first->second;
+}
+
+const NttCoset* NttEngine::coset(uint64_t n, const fe& g, bool with_ninv, const NttDomain* d, cudaStream_t st) {
+    for (auto& c : cosets_)
+        if (c.n == n && c.with_ninv == with_ninv && fe_eq(c.g, g)) return &c;
+    if (cosets_.size() >= 16) {  // tiny FIFO cache: the prover uses one shift (k[1]) and its inverse
+        cudaStreamSynchronize(st);
+        cudaFree(cosets_.front().g_lo);
+        cosets_.erase(cosets_.begin());
+    }
+    NttCoset c;
+    c.n = n;
+    c.g = g;
+    c.with_ninv = with_ninv;
+    const uint32_t nlo = 1u << NTT_LOG_TWLO;
+    c.n_hi = (uint32_t)((n >> NTT_LOG_TWLO) + 1);
+    if (cudaMalloc(&c.g_lo, sizeof(fe) * ((size_t)nlo + c.n_hi)) != cudaSuccess) return nullptr;
+    c.g_hi = c.g_lo + nlo;
+    const uint32_t tot = nlo + c.n_hi;
+    ntt_build_pow_tables<<<(tot + 127) / 128, 128, 0, st>>>(g, with_ninv ? d->n_inv : fe_one<FrP>(), c.g_lo, c.g_hi, c.n_hi);
+    UZ_COUNT_LAUNCH(1);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
+    cosets_.push_back(c);
+    return &cosets_.back();
+}
+
+template <int NT>
+static cudaError_t launch_pass(const NttKernelArgs& ka, cudaStream_t st) {
+    const NttPass& p = ka.p;
+    const size_t T = (size_t)1 << (p.logR + p.logC);
+    const size_t smem = T * 32;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        if (e != cudaSuccess) return e;
+        configured = 200 * 1024;
+    }
+    const uint32_t grid = p.inner_tiles * p.outer * p.batch;
+    ntt_pass_kernel<NT><<<grid, NT, smem, st>>>(ka);
+    UZ_COUNT_LAUNCH(1);
+    return cudaGetLastError();
+}
+
+// d_in: len_in elements readable; d_out: n elements; d_scratch: n elements (may alias neither).
+// d_in == d_out is allowed.
+int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, uint64_t n, bool inverse,
+                   const fe* coset_shift /* host, Montgomery, or null */, cudaStream_t st) {
+    const NttDomain* d = domain(n, st);
+    if (!d) return UZKGE_ERR_SIZE;
+    if (len_in > n) return UZKGE_ERR_SIZE;
+    const NttCoset* cs = nullptr;
+    if (coset_shift) {
+        cs = coset(n, *coset_shift, inverse, d, st);
+        if (!cs) return UZKGE_ERR_CUDA;
+    }
+    const NttPlan& pl = d->plan;
+    const fe* src = d_in;
+    bool input_consumed = false;
+    if (pl.mixed) {
+        Radix3Args ra;
+        ra.in = d_in;
+        ra.out = d_scratch;
+        ra.m = pl.m;
+        ra.len_in = len_in;
+        ra.w_lo = d->w_lo;
+        ra.w_hi = d->w_hi;
+        ra.g_lo = cs ? cs->g_lo : nullptr;
+        ra.g_hi = cs ? cs->g_hi : nullptr;
+        ra.w3 = d->w3;
+        ra.w3sq = d->w3sq;
+        ra.pre_coset = (cs && !inverse) ? 1 : 0;
+        ntt_radix3_kernel<<<(unsigned)((pl.m + 255) / 256), 256, 0, st>>>(ra);
+        UZ_COUNT_LAUNCH(1);
+        if (cudaGetLastError() != cudaSuccess) return UZKGE_ERR_CUDA;
+        src = d_scratch;
+        input_consumed = true;
+    }
+    for (uint32_t i = 0; i < pl.npass; i++) {
+        NttKernelArgs ka;
+        ka.p = pl.pass[i];
+        ka.in = src;
+        // non-last passes write into scratch (in place once the data lives there); the last pass writes d_out
+        ka.out = ka.p.last ? d_out : d_scratch;
+        ka.n = n;
+        ka.len_in = len_in;
+        ka.stage_tab = d->stage;
+        ka.w_lo = d->w_lo;
+        ka.w_hi = d->w_hi;
+        ka.g_lo = cs ? cs->g_lo : nullptr;
+        ka.g_hi = cs ? cs->g_hi : nullptr;
+        ka.scale = d->n_inv;
+        ka.inverse = inverse ? 1 : 0;
+        ka.zero_pad = (!input_consumed && len_in < n) ? 1 : 0;
+        ka.pre_coset = (!input_consumed && cs && !inverse) ? 1 : 0;
+        ka.post_coset = (ka.p.last && cs && inverse) ? 1 : 0;
+        ka.has_scale = (ka.p.last && inverse && !cs) ? 1 : 0;
+        // a single-tile last pass may run in place; a multi-tile last pass transposes and must not alias
+        if (ka.p.last && ka.in == ka.out && (ka.p.inner_tiles * ka.p.outer * ka.p.batch) > 1) return UZKGE_ERR_INTERNAL;
+        const uint32_t T = 1u << (ka.p.logR + ka.p.logC);
+        cudaError_t e;
+        if (T >= 2048)
+            e = launch_pass<512>(ka, st);
+        else if (T >= 512)
+            e = launch_pass<256>(ka, st);
+        else
+            e = launch_pass<64>(ka, st);
+        if (e != cudaSuccess) return UZKGE_ERR_CUDA;
+        src = ka.out;
+        input_consumed = true;
+    }
+    return UZKGE_OK;
+}
+
+NttEngine::~NttEngine() {
+    for (auto& kv : domains_) cudaFree(kv.second.w_lo);
+    for (auto& c : cosets_) cudaFree(c.g_lo);
+}
+
+}  // namespace uz

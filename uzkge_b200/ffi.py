@@ -1,0 +1,268 @@
+"""ctypes binding of the C ABI in include/uzkge_cuda.h -- the same symbols the Rust `uzkge-cuda-sys` crate binds
+(INTEGRATION.md).  Arrays are numpy uint64 in the ABI layout: Fr/Fq (n, 4) Montgomery limbs, affine (n, 8),
+Jacobian (12,).  Loading fails loudly when the library is missing: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from .errors import BackendUnavailable, CommitmentError, FFTError, ParameterError, UzkgeError
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libuzkge_cuda.so")
+HEADER_PATH = os.path.join(HERE, "..", "include", "uzkge_cuda.h")
+
+OK, ERR_NO_DEVICE, ERR_SIZE, ERR_CUDA, ERR_OOM, ERR_HANDLE, ERR_ARG, ERR_INTERNAL = range(8)
+
+u64p = C.POINTER(C.c_uint64)
+
+
+class SrsInfo(C.Structure):
+    _fields_ = [
+        ("window_bits", C.c_uint32),
+        ("windows", C.c_uint32),
+        ("n", C.c_uint64),
+        ("device_bytes", C.c_uint64),
+        ("precompute_ms", C.c_double),
+    ]
+
+
+_SIGNATURES = {
+    "uzkge_cuda_init": (C.c_int32, [C.c_int32]),
+    "uzkge_cuda_device_count": (C.c_int32, []),
+    "uzkge_cuda_last_error": (C.c_char_p, []),
+    "uzkge_cuda_version": (C.c_char_p, []),
+    "uzkge_cuda_srs_upload": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, u64p]),
+    "uzkge_cuda_srs_free": (C.c_int32, [C.c_uint64]),
+    "uzkge_cuda_msm_g1": (C.c_int32, [C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uzkge_cuda_msm_g1_batch": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p]),
+    "uzkge_cuda_ntt_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p]),
+    "uzkge_cuda_fr_root_of_unity": (C.c_int32, [C.c_size_t, C.c_void_p]),
+    "uzkge_cuda_msm_g1_device": (C.c_int32, [C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_ntt_fr_device": (
+        C.c_int32,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p],
+    ),
+    "uzkge_cuda_g1_add": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_g1_to_affine": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "uzkge_cuda_host_free": (C.c_int32, [C.c_void_p]),
+    "uzkge_cuda_host_register": (C.c_int32, [C.c_void_p, C.c_size_t]),
+    "uzkge_cuda_host_unregister": (C.c_int32, [C.c_void_p]),
+    "uzkge_cuda_srs_info": (C.c_int32, [C.c_uint64, C.POINTER(SrsInfo)]),
+    "uzkge_cuda_launch_count": (C.c_uint64, []),
+    "uzkge_cuda_configure": (C.c_int32, [C.c_char_p, C.c_uint64]),
+    "uzkge_cuda_field_mul": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "uzkge_cuda_bench_field_mul": (C.c_int32, [C.c_int32, C.c_uint32, C.POINTER(C.c_double)]),
+}
+
+
+def header_symbols() -> list[str]:
+    """Every entry point include/uzkge_cuda.h declares (used by the CPU test-suite's export check)."""
+    txt = open(HEADER_PATH).read()
+    return sorted(set(re.findall(r"UZKGE_API\s+[\w\s\*]+?\b(uzkge_cuda_\w+)\s*\(", txt)))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libuzkge_cuda.so and declare every prototype.  No GPU is touched until an entry point is called."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BackendUnavailable(
+                f"{LIB_PATH} is missing: build it with `python -m uzkge_b200.build` (nvcc, sm_100a). "
+                "uzkge_b200 has no CPU fallback."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return (lib().uzkge_cuda_last_error() or b"").decode()
+
+
+def check(rc: int, exc=UzkgeError):
+    if rc == OK:
+        return
+    msg = f"uzkge_cuda error {rc}: {last_error()}"
+    if rc == ERR_NO_DEVICE:
+        raise BackendUnavailable(msg)
+    if rc in (ERR_SIZE, ERR_ARG, ERR_HANDLE) and exc is UzkgeError:
+        raise ParameterError(msg)
+    raise exc(msg)
+
+
+def as_u64(a, cols: int | None = None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if cols is not None:
+        a = a.reshape(-1, cols)
+    return a
+
+
+def ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def init(device: int = -1) -> None:
+    check(lib().uzkge_cuda_init(device))
+
+
+def device_count() -> int:
+    return int(lib().uzkge_cuda_device_count())
+
+
+def version() -> str:
+    return lib().uzkge_cuda_version().decode()
+
+
+def launch_count() -> int:
+    return int(lib().uzkge_cuda_launch_count())
+
+
+def configure(key: str, value: int) -> None:
+    check(lib().uzkge_cuda_configure(key.encode(), value))
+
+
+def srs_upload(affine_xy: np.ndarray, window_bits: int = 0) -> int:
+    pts = as_u64(affine_xy, 8)
+    h = C.c_uint64(0)
+    check(lib().uzkge_cuda_srs_upload(ptr(pts), pts.shape[0], window_bits, C.byref(h)), CommitmentError)
+    return int(h.value)
+
+
+def srs_free(handle: int) -> None:
+    check(lib().uzkge_cuda_srs_free(handle))
+
+
+def srs_info(handle: int) -> dict:
+    info = SrsInfo()
+    check(lib().uzkge_cuda_srs_info(handle, C.byref(info)))
+    return {k: getattr(info, k) for k, _ in SrsInfo._fields_}
+
+
+def msm_g1(handle: int, scalars: np.ndarray, base_offset: int = 0) -> np.ndarray:
+    s = as_u64(scalars, 4)
+    out = np.zeros(12, dtype=np.uint64)
+    check(lib().uzkge_cuda_msm_g1(handle, base_offset, ptr(s), s.shape[0], ptr(out)), CommitmentError)
+    return out
+
+
+def msm_g1_batch(handle: int, scalar_vectors) -> np.ndarray:
+    vecs = [as_u64(v, 4) for v in scalar_vectors]
+    k = len(vecs)
+    out = np.zeros((k, 12), dtype=np.uint64)
+    if k == 0:
+        return out
+    ptrs = (C.c_void_p * k)(*[v.ctypes.data for v in vecs])
+    lens = (C.c_size_t * k)(*[v.shape[0] for v in vecs])
+    check(lib().uzkge_cuda_msm_g1_batch(handle, ptrs, lens, k, ptr(out)), CommitmentError)
+    return out
+
+
+def ntt_fr(data: np.ndarray, domain_size: int, inverse: bool = False, coset_shift=None) -> np.ndarray:
+    """Returns a new (domain_size, 4) array; `data` holds the first len_in elements."""
+    d = as_u64(data, 4)
+    len_in = d.shape[0]
+    if len_in > domain_size:
+        raise ParameterError("input longer than the domain")
+    buf = np.empty((domain_size, 4), dtype=np.uint64)
+    buf[:len_in] = d
+    shift = as_u64(coset_shift, 4) if coset_shift is not None else None
+    check(
+        lib().uzkge_cuda_ntt_fr(ptr(buf), len_in, domain_size, 1 if inverse else 0, ptr(shift) if shift is not None else None),
+        FFTError,
+    )
+    return buf
+
+
+def ntt_fr_inplace(buf: np.ndarray, len_in: int, domain_size: int, inverse: bool = False, coset_shift=None) -> None:
+    """The raw call: `buf` (capacity domain_size, any host memory incl. pinned) is transformed in place."""
+    assert buf.dtype == np.uint64 and buf.flags["C_CONTIGUOUS"] and buf.size >= 4 * domain_size
+    shift = as_u64(coset_shift, 4) if coset_shift is not None else None
+    check(
+        lib().uzkge_cuda_ntt_fr(ptr(buf), len_in, domain_size, 1 if inverse else 0, ptr(shift) if shift is not None else None),
+        FFTError,
+    )
+
+
+def fr_root_of_unity(n: int) -> np.ndarray:
+    out = np.zeros(4, dtype=np.uint64)
+    check(lib().uzkge_cuda_fr_root_of_unity(n, ptr(out)))
+    return out
+
+
+def msm_g1_device(handle: int, d_scalars: int, n: int, d_out: int, stream: int = 0, base_offset: int = 0) -> None:
+    check(lib().uzkge_cuda_msm_g1_device(handle, base_offset, d_scalars, n, d_out, stream), CommitmentError)
+
+
+def ntt_fr_device(d_in: int, d_out: int, d_scratch: int, len_in: int, domain_size: int, inverse: bool = False,
+                  coset_shift=None, stream: int = 0) -> None:
+    shift = as_u64(coset_shift, 4) if coset_shift is not None else None
+    check(
+        lib().uzkge_cuda_ntt_fr_device(d_in, d_out, d_scratch, len_in, domain_size, 1 if inverse else 0,
+                                       ptr(shift) if shift is not None else None, stream),
+        FFTError,
+    )
+
+
+def g1_add(a_jac, b_jac) -> np.ndarray:
+    a, b = as_u64(a_jac).reshape(12), as_u64(b_jac).reshape(12)
+    out = np.zeros(12, dtype=np.uint64)
+    check(lib().uzkge_cuda_g1_add(ptr(a), ptr(b), ptr(out)), CommitmentError)
+    return out
+
+
+def g1_to_affine(jac) -> np.ndarray:
+    a = as_u64(jac).reshape(12)
+    out = np.zeros(8, dtype=np.uint64)
+    check(lib().uzkge_cuda_g1_to_affine(ptr(a), ptr(out)), CommitmentError)
+    return out
+
+
+def field_mul(a, b, field: str = "fr") -> np.ndarray:
+    a, b = as_u64(a, 4), as_u64(b, 4)
+    assert a.shape == b.shape
+    out = np.empty_like(a)
+    check(lib().uzkge_cuda_field_mul(0 if field == "fr" else 1, ptr(a), ptr(b), ptr(out), a.shape[0]))
+    return out
+
+
+def bench_field_mul(field: str = "fr", iters: int = 2000) -> float:
+    v = C.c_double(0)
+    check(lib().uzkge_cuda_bench_field_mul(0 if field == "fr" else 1, iters, C.byref(v)))
+    return float(v.value)
+
+
+class PinnedArray:
+    """A page-locked uint64 host buffer from uzkge_cuda_host_alloc, viewed as a numpy array."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+        n = int(np.prod(self.shape))
+        p = C.c_void_p()
+        check(lib().uzkge_cuda_host_alloc(n * 8, C.byref(p)))
+        self._p = p
+        self.array = np.ctypeslib.as_array(C.cast(p, u64p), shape=(n,)).reshape(self.shape)
+
+    def free(self):
+        if self._p:
+            lib().uzkge_cuda_host_free(self._p)
+            self._p = None
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
