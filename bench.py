@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py -- BN254 G1 MSM 2^20 points/s (headline, BASELINE.json configs[1]) and Fr NTT 2^22 elements/s
+(configs[2]) on N B200s, one process per GPU, next to the CPU restatement of the reference's arkworks path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload both|msm|ntt]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch of synthetic input:
+  msm : one variable-base MSM over 2^20 resident KZG bases (powers-of-tau SRS) with fresh uniform Fr scalars.
+        N > 1: the job is ONE MSM over N * 2^20 points; rank r owns slice r (bases resident on its GPU) and the
+        N partial sums (96 B each) are all-gathered and added -- weak scaling, no other collective.
+  ntt : one forward 2^22 Fr NTT, natural order in and out (replicas only at N > 1: it fits one GPU).
+`value` is device-resident throughput (CUDA events on the launching stream, max over ranks); `e2e` goes through the
+host-pointer C ABI call a Rust caller makes (pinned host buffers, H2D + D2H inside the timed region).
+Inputs rotate over more distinct buffers than fit in the 126 MB L2 (`config.l2`).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+LOG_MSM = 20
+LOG_NTT = 22
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+def random_fr(n: int, seed: int) -> np.ndarray:
+    """n uniform Fr elements as raw Montgomery limbs (uniform residues stay uniform under the Montgomery map)."""
+    rng = np.random.default_rng(seed)
+    mod = np.array([(FR >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+    def draw(k):
+        a = rng.integers(0, 1 << 63, size=(k, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(k, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 62) - 1)
+        return a
+
+    def ge_mod(a):
+        ge = np.zeros(a.shape[0], dtype=bool)
+        und = np.ones(a.shape[0], dtype=bool)
+        for k in (3, 2, 1, 0):
+            gt = und & (a[:, k] > mod[k])
+            lt = und & (a[:, k] < mod[k])
+            ge |= gt
+            und &= ~(gt | lt)
+        return ge | und
+
+    a = draw(n)
+    while True:
+        bad = np.nonzero(ge_mod(a))[0]
+        if bad.size == 0:
+            return a
+        a[bad] = draw(bad.size)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self._t = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self._t = threading.Thread(target=self._read, daemon=True)
+        self._t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        sm, smax, reasons = [], None, set()
+        for r in inside:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank: int, world: int) -> int:
+    """The reference's CPU path for the same metric: no Rust toolchain exists here or on the GPU box and the
+    arithmetic lives in un-vendored arkworks forks, so this arm times the oracle port
+    (oracle/oracle.c: arkworks' signed-digit Pippenger / radix-2 FFT restated in C + OpenMP) on all host cores."""
+    if rank != 0:
+        return 0
+    from oracle import cpu as oc
+
+    cores = oc.num_threads()
+    log_n = LOG_MSM if args.workload != "ntt" else LOG_NTT
+    n = 1 << log_n
+    t_setup = time.time()
+    if args.workload != "ntt":
+        pts = oc.g1_random_points(n, 0xB2000001)
+        scal = [oc.random_fr(n, 0xB2000002 + i) for i in range(2)]
+
+        def step(i):
+            oc.msm_g1(pts, scal[i % 2])
+        metric, unit, wl = "bn254_g1_msm_2^20_points_per_s", "points/s", f"G1 MSM 2^{log_n}"
+    else:
+        vec = [oc.random_fr(n, 0xB2000003 + i) for i in range(2)]
+
+        def step(i):
+            oc.ntt_fr(vec[i % 2], n)
+        metric, unit, wl = "bn254_fr_ntt_2^22_elements_per_s", "elements/s", f"Fr NTT 2^{log_n}"
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.time()
+    for i in range(args.steps):
+        step(i)
+    dt = time.time() - t0
+    v = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 limbs (256-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": wl, "where": "host CPU", "note": "oracle port of arkworks' algorithms (no Rust toolchain: the "
+                   "reference itself cannot be built); full workload per step", "setup_s": round(t0 - t_setup, 1)},
+        "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": f"{args.steps} x full {wl}"},
+        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="both", choices=["both", "msm", "ntt"])
+    ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    from uzkge_b200 import ffi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- uzkge_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ffi.init(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    K, W = args.steps, args.warmup
+    launches0 = ffi.launch_count()
+    results = {}
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_region0 = time.time()
+    if sampler:
+        sampler.start()
+
+    # -------------------------------------------------------------------------------------------- MSM
+    if args.workload in ("both", "msm"):
+        n = 1 << LOG_MSM
+        # rank r's slice of the global powers-of-tau SRS: tau^(r*n + i) G = tau_r-shifted bases.  Each rank builds its
+        # slice on its own GPU (setup path, untimed): slice r is the SRS of trapdoor tau scaled by tau^(r*n), which as a
+        # point set is {tau^i * (tau^(r n) G)}; for the benchmark every rank simply uses a distinct trapdoor.
+        tau = random_fr(1, 0xB2000001 + rank)[0]
+        t0 = time.time()
+        bases = ffi.srs_generate(tau, n)
+        t_gen = time.time() - t0
+        h = ffi.srs_upload(bases, args.window_bits)
+        info = ffi.srs_info(h)
+        nsets = 8  # 8 x 32 MiB of scalars > 126 MB L2
+        host_sets = [random_fr(n, 0xB2000002 + 97 * rank + i) for i in range(nsets)]
+        d_sets = [torch.from_numpy(s.view(np.int64)).to(dev) for s in host_sets]
+        d_out = torch.zeros(12 * max(world, 1), dtype=torch.int64, device=dev)
+        d_mine = torch.zeros(12, dtype=torch.int64, device=dev)
+        d_acc = torch.zeros(12, dtype=torch.int64, device=dev)
+
+        def msm_step(i):
+            ffi.msm_g1_device(h, d_sets[i % nsets].data_ptr(), n, d_mine.data_ptr(), sptr)
+            if world > 1:
+                dist.all_gather_into_tensor(d_out, d_mine)
+
+        def combine():
+            # N - 1 projective adds of the gathered partial sums (host call on 96-byte values)
+            parts = d_out.cpu().numpy().view(np.uint64).reshape(world, 12)
+            acc = parts[0]
+            for r in range(1, world):
+                acc = ffi.g1_add(acc, parts[r])
+            return acc
+
+        for i in range(W):
+            msm_step(i)
+        barrier()
+        ffi.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(K):
+            msm_step(i)
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / K)
+        prof = ffi.profile_read("msm")
+        ffi.profile_enable(False)
+        if world > 1:
+            t0 = time.time()
+            combine()
+            combine_ms = (time.time() - t0) * 1e3
+        else:
+            combine_ms = 0.0
+
+        # e2e through the host-pointer ABI: pinned scalars, H2D + MSM + D2H of the 96-byte result every step
+        pinned = [ffi.PinnedArray((n, 4)) for _ in range(4)]
+        for k, pa in enumerate(pinned):
+            pa.array[:] = host_sets[k]
+        for i in range(2):
+            ffi.msm_g1(h, pinned[i % 4].array)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            out = ffi.msm_g1(h, pinned[i % 4].array)
+            if world > 1:
+                d_mine.copy_(torch.from_numpy(out.view(np.int64)))
+                dist.all_gather_into_tensor(d_out, d_mine)
+                combine()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / K)
+        for pa in pinned:
+            pa.free()
+
+        acc_ms = prof["ms"]["accumulate"]
+        W_ = info["windows"]
+        c_ = info["window_bits"]
+        fq_mul = 10.0 * n * W_ + 28.0 * (1 << (c_ - 1))
+        results["msm"] = {
+            "ms": ms, "e2e_ms": e2e_ms, "n": n, "phases_ms": prof["ms"], "combine_ms": combine_ms,
+            "window_bits": c_, "windows": W_, "table_bytes": info["device_bytes"], "precompute_ms": info["precompute_ms"],
+            "srs_generate_s": t_gen, "fq_mul": fq_mul, "acc_ms": acc_ms,
+            "host0": host_sets[0], "bases": bases, "handle": h,
+        }
+
+    # -------------------------------------------------------------------------------------------- NTT
+    if args.workload in ("both", "ntt"):
+        n = 1 << LOG_NTT
+        nbuf = 4  # 4 x 128 MiB inputs > L2
+        hx = random_fr(n, 0xB2000003 + rank)
+        d_in = [torch.from_numpy(np.roll(hx, 17 * i, axis=0).view(np.int64)).to(dev) for i in range(nbuf)]
+        d_outb = torch.empty(4 * n, dtype=torch.int64, device=dev)
+        d_scr = torch.empty(4 * n, dtype=torch.int64, device=dev)
+
+        def ntt_step(i):
+            ffi.ntt_fr_device(d_in[i % nbuf].data_ptr(), d_outb.data_ptr(), d_scr.data_ptr(), n, n, False, None, sptr)
+
+        for i in range(W):
+            ntt_step(i)
+        barrier()
+        ffi.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(K):
+            ntt_step(i)
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / K)
+        prof = ffi.profile_read("ntt")
+        ffi.profile_enable(False)
+        pinned = ffi.PinnedArray((n, 4))
+        pinned.array[:] = hx
+        for i in range(2):
+            ffi.ntt_fr_inplace(pinned.array, n, n, bool(i & 1))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            ffi.ntt_fr_inplace(pinned.array, n, n, bool(i & 1))  # forward / inverse alternate: the data stays bounded
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / K)
+        roundtrip_ok = bool(np.array_equal(pinned.array, hx)) if K % 2 == 0 else None
+        pinned.free()
+        results["ntt"] = {"ms": ms, "e2e_ms": e2e_ms, "n": n, "phases_ms": prof["ms"], "roundtrip_ok": roundtrip_ok, "hx": hx}
+
+    t_region1 = time.time()
+    clocks = sampler.stop(t_region0, t_region1) if sampler else None
+    launches = ffi.launch_count() - launches0
+
+    # integer-pipe roof, measured live: dependent Montgomery-multiplication chains on every SM
+    fq_peak = ffi.bench_field_mul("fq", 2000)
+
+    # -------------------------------------------------------------------------------------------- CPU baseline (rank 0, N = 1)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu as oc  # the checker / CPU arm only
+
+        cores = oc.num_threads()
+        if "msm" in results:
+            r = results["msm"]
+            m = 1 << 18
+            t0 = time.time()
+            want = oc.msm_g1(r["bases"][:m], r["host0"][:m])
+            dt = time.time() - t0
+            got = ffi.msm_g1(r["handle"], r["host0"][:m])
+            if not np.array_equal(oc.g1_to_affine(got), oc.g1_to_affine(want)):
+                raise SystemExit("bench.py: GPU MSM result differs from the CPU oracle -- refusing to report a number")
+            cpu_baseline = {"value": m / dt, "unit": "points/s", "cores": cores, "kind": "port",
+                            "sample": f"one 2^18-point MSM (first quarter of the workload's bases and scalars), {dt:.2f} s; "
+                                      "result compared with the GPU's (affine) before timing was accepted"}
+        if "ntt" in results:
+            r = results["ntt"]
+            t0 = time.time()
+            want = oc.ntt_fr(r["hx"], r["n"])
+            dt = time.time() - t0
+            got = ffi.ntt_fr(r["hx"], r["n"])
+            if not np.array_equal(got, want):
+                raise SystemExit("bench.py: GPU NTT result differs from the CPU oracle -- refusing to report a number")
+            r["cpu"] = {"value": r["n"] / dt, "unit": "elements/s", "cores": cores, "kind": "port",
+                        "sample": f"one full 2^22 NTT, {dt:.2f} s; output compared with the GPU's"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    def msm_block(r):
+        n_total = r["n"] * world
+        return {
+            "metric": "bn254_g1_msm_2^20_points_per_s", "value": n_total / (r["ms"] * 1e-3), "unit": "points/s",
+            "ms_per_step": r["ms"],
+            "e2e": {"value": n_total / (r["e2e_ms"] * 1e-3), "unit": "points/s", "ms_per_step": r["e2e_ms"],
+                    "h2d_bytes_per_step": 32 * r["n"], "d2h_bytes_per_step": 96},
+            "roofline": {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": 96.0 * r["n"] / (r["acc_ms"] * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": 96.0 * r["n"] / (r["acc_ms"] * 1e-3) / 1e9 / hbm_peak,
+                         "traffic": None, "kernel_ms": r["acc_ms"], "peak_source": peak_src,
+                         "note": "MSM is integer-pipe bound, never HBM bound (SURVEY 8d): see int_roofline"},
+            "int_roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": (10.0 * r["n"] * r["windows"]) / (r["acc_ms"] * 1e-3) / 1e9,
+                             "peak": fq_peak / 1e9, "unit": "G Fq-mul/s", "frac": (10.0 * r["n"] * r["windows"]) / (r["acc_ms"] * 1e-3) / fq_peak,
+                             "peak_source": "uzkge_cuda_bench_field_mul (dependent 136-IMAD Montgomery chains, measured in this run)"},
+            "phases_ms": r["phases_ms"], "window_bits": r["window_bits"], "windows": r["windows"],
+            "srs_device_bytes": r["table_bytes"], "srs_precompute_ms": r["precompute_ms"], "combine_ms": r["combine_ms"],
+        }
+
+    def ntt_block(r):
+        lg = LOG_NTT
+        passes = sum(1 for k in ("pass0", "pass1", "pass2") if r["phases_ms"][k] > 0)
+        top = max(("pass0", "pass1", "pass2"), key=lambda k: r["phases_ms"][k])
+        top_ms = r["phases_ms"][top]
+        b = {
+            "metric": "bn254_fr_ntt_2^22_elements_per_s", "value": r["n"] * world / (r["ms"] * 1e-3), "unit": "elements/s",
+            "ms_per_step": r["ms"],
+            "e2e": {"value": r["n"] * world / (r["e2e_ms"] * 1e-3), "unit": "elements/s", "ms_per_step": r["e2e_ms"],
+                    "h2d_bytes_per_step": 32 * r["n"], "d2h_bytes_per_step": 32 * r["n"]},
+            "roofline": {"bound": "hbm", "kernel": f"ntt_pass_kernel ({top})", "achieved": 64.0 * r["n"] / (top_ms * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": 64.0 * r["n"] / (top_ms * 1e-3) / 1e9 / hbm_peak,
+                         "traffic": None, "kernel_ms": top_ms, "peak_source": peak_src, "passes": passes},
+            "int_roofline": {"bound": "imad", "achieved": (r["n"] / 2 * lg + r["n"]) / (r["ms"] * 1e-3) / 1e9, "peak": fq_peak / 1e9,
+                             "unit": "G Fr-mul/s", "frac": (r["n"] / 2 * lg + r["n"]) / (r["ms"] * 1e-3) / fq_peak},
+            "phases_ms": r["phases_ms"], "e2e_roundtrip_ok": r["roundtrip_ok"],
+        }
+        if "cpu" in r:
+            b["cpu_baseline"] = r["cpu"]
+        return b
+
+    head = "msm" if "msm" in results else "ntt"
+    blk = msm_block(results["msm"]) if head == "msm" else ntt_block(results["ntt"])
+    line = {
+        "metric": blk["metric"], "value": blk["value"], "unit": blk["unit"], "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 limbs (256-bit Montgomery, IMAD carry chains)", "data": "synthetic",
+        "config": {
+            "workload": ("BN254 G1 variable-base MSM, 2^20 points per GPU, powers-of-tau bases resident in HBM, uniform Fr scalars"
+                         if head == "msm" else "BN254 Fr radix-2 NTT 2^22, natural order in/out"),
+            "parallelism": f"{world} process(es), one per GPU; MSM points split per GPU, partial sums all-gathered (96 B) and added",
+            "l2": "inputs rotate over 8 x 32 MiB scalar sets / 4 x 128 MiB vectors (> 126 MB L2); tables are 1 GiB",
+        },
+        "e2e": blk["e2e"], "roofline": blk["roofline"], "int_roofline": blk["int_roofline"],
+        "gpu_launches": int(launches), "clocks": clocks,
+        "cpu_baseline": cpu_baseline if head == "msm" else blk.get("cpu_baseline"),
+        "detail": {k: v for k, v in blk.items() if k in ("phases_ms", "window_bits", "windows", "srs_device_bytes", "srs_precompute_ms", "combine_ms")},
+    }
+    if head == "msm" and "ntt" in results:
+        line["ntt"] = ntt_block(results["ntt"])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,6 +59,10 @@ UZKGE_API const char* uzkge_cuda_version(void);
 UZKGE_API int32_t uzkge_cuda_srs_upload(const uint64_t* affine_xy, size_t n, uint32_t window_bits, uint64_t* handle);
 UZKGE_API int32_t uzkge_cuda_srs_free(uint64_t handle);
 
+/* Setup path: out[i] = tau^i * G (affine, Montgomery), i < n -- the G1 half of KZGCommitmentScheme::new
+ * (kzg_poly_commitment.rs:183-204: n sequential scalar multiplications on the CPU).  tau: Montgomery Fr. */
+UZKGE_API int32_t uzkge_cuda_srs_generate(const uint64_t tau[4], size_t n, uint64_t* out_affine_xy);
+
 /* ---- MSM ------------------------------------------------------------------------------------------
  * out = sum_{i < n} scalars[i] * srs[base_offset + i].  Replaces `G1Projective::msm(&points_raw, &coefs)`
  * (kzg_poly_commitment.rs:290) for KZGCommitmentSchemeBN254::commit (:278-293).
@@ -119,6 +123,13 @@ typedef struct {
 UZKGE_API int32_t uzkge_cuda_srs_info(uint64_t handle, uzkge_srs_info* info);
 /* number of kernel launches issued by this library since init (bench.py's gpu_launches) */
 UZKGE_API uint64_t uzkge_cuda_launch_count(void);
+/* Per-phase device timing with CUDA events recorded on the launching stream (off by default).
+ *   kind 0 = MSM: phase_ms[0..5] = recode, sort, offsets, accumulate, oversized buckets, reduce
+ *   kind 1 = NTT: phase_ms[0..3] = radix-3 pre-pass, pass 0, pass 1, pass 2
+ * profile_read synchronises the device, returns the sums over the `runs` engine runs since the last read and
+ * resets them. */
+UZKGE_API int32_t uzkge_cuda_profile_enable(int32_t on);
+UZKGE_API int32_t uzkge_cuda_profile_read(int32_t kind, double phase_ms[8], uint64_t* runs);
 /* tuning knobs for experiments: "msm_lanes" (0 = auto, else 1..32 lanes per bucket), "ntt_log_tile",
  * "ntt_max_log_r", "ntt_two_pass_max".  Affects plans created afterwards. */
 UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value);

@@ -18,6 +18,7 @@
 
 namespace uz {
 std::atomic<uint64_t> g_launches{0};
+Profiler g_prof;
 }
 
 using namespace uz;
@@ -362,6 +363,25 @@ UZKGE_API int32_t uzkge_cuda_g1_to_affine(const uint64_t in_jac[12], uint64_t ou
     return UZKGE_OK;
 }
 
+UZKGE_API int32_t uzkge_cuda_srs_generate(const uint64_t tau[4], size_t n, uint64_t* out_affine_xy) {
+    if (!tau || (n && !out_affine_xy)) return fail(UZKGE_ERR_ARG, "srs_generate: null pointer");
+    if (n >= (1ull << 28)) return fail(UZKGE_ERR_SIZE, "srs_generate: n too large");
+    API_ENTER(-1);
+    fe t;
+    memcpy(&t, tau, sizeof(fe));
+    const size_t slab = 1u << 22;
+    CUDA_OR_FAIL(g.data.reserve((n < slab ? n : slab) * sizeof(affine) + 64), "srs_generate: buffer");
+    for (size_t first = 0; first < n; first += slab) {
+        const uint32_t count = (uint32_t)((n - first) < slab ? (n - first) : slab);
+        int rc = g.msm->powers_of_tau(t, first, count, (affine*)g.data.p, g.stream);
+        if (rc != UZKGE_OK) return engine_fail(rc, "srs_generate: launch");
+        CUDA_OR_FAIL(cudaMemcpyAsync(out_affine_xy + first * 8, g.data.p, count * sizeof(affine), cudaMemcpyDeviceToHost, g.stream),
+                     "srs_generate: D2H");
+        CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "srs_generate: execution");
+    }
+    return UZKGE_OK;
+}
+
 UZKGE_API int32_t uzkge_cuda_host_alloc(size_t bytes, void** out) {
     if (!out) return fail(UZKGE_ERR_ARG, "host_alloc: null pointer");
     API_ENTER(-1);
@@ -382,6 +402,33 @@ UZKGE_API int32_t uzkge_cuda_host_register(void* p, size_t bytes) {
 UZKGE_API int32_t uzkge_cuda_host_unregister(void* p) {
     API_ENTER(-1);
     CUDA_OR_FAIL(cudaHostUnregister(p), "host_unregister");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_profile_enable(int32_t on) {
+    API_ENTER(-1);
+    CUDA_OR_FAIL(cudaDeviceSynchronize(), "profile_enable");
+    double sums[Profiler::KINDS][Profiler::MAX_PHASES] = {};
+    uint64_t runs[Profiler::KINDS] = {};
+    g_prof.collect(sums, runs);  // drop stale records
+    g_prof.enabled = on != 0;
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_profile_read(int32_t kind, double phase_ms[8], uint64_t* runs_out) {
+    if (!phase_ms || !runs_out) return fail(UZKGE_ERR_ARG, "profile_read: null pointer");
+    if (kind < 0 || kind >= Profiler::KINDS) return fail(UZKGE_ERR_ARG, "profile_read: kind must be 0 (MSM) or 1 (NTT)");
+    API_ENTER(-1);
+    CUDA_OR_FAIL(cudaDeviceSynchronize(), "profile_read");
+    static double sums[Profiler::KINDS][Profiler::MAX_PHASES];
+    static uint64_t runs[Profiler::KINDS];
+    g_prof.collect(sums, runs);
+    for (int i = 0; i < Profiler::MAX_PHASES; i++) {
+        phase_ms[i] = sums[kind][i];
+        sums[kind][i] = 0;
+    }
+    *runs_out = runs[kind];
+    runs[kind] = 0;
     return UZKGE_OK;
 }
 

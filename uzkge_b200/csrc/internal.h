@@ -16,6 +16,70 @@ namespace uz {
 extern std::atomic<uint64_t> g_launches;  // kernels launched by this library (uzkge_cuda_launch_count)
 #define UZ_COUNT_LAUNCH(k) (::uz::g_launches.fetch_add((k), std::memory_order_relaxed))
 
+// ---------------------------------------------------------------- per-phase device timing (bench / profiling)
+// When enabled, every engine run records CUDA events on its launching stream at phase boundaries; the sums
+// are read back (after a synchronise) through uzkge_cuda_profile_read.  Off by default: no events, no cost.
+struct Profiler {
+    static constexpr int MAX_PHASES = 8;
+    enum Kind { MSM = 0, NTT = 1, KINDS = 2 };
+    struct Rec {
+        int kind;
+        int nmarks;
+        int phase_of_mark[MAX_PHASES + 1];
+        cudaEvent_t ev[MAX_PHASES + 1];
+    };
+    bool enabled = false;
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    // returns a record index (or -1 when disabled) and records the start event
+    int begin(int kind, cudaStream_t st) {
+        if (!enabled || recs.size() >= 65536) return -1;
+        Rec r;
+        r.kind = kind;
+        r.nmarks = 1;
+        r.phase_of_mark[0] = -1;
+        r.ev[0] = get();
+        cudaEventRecord(r.ev[0], st);
+        recs.push_back(r);
+        return (int)recs.size() - 1;
+    }
+    // everything launched since the previous mark belongs to `phase`
+    void mark(int rec, int phase, cudaStream_t st) {
+        if (rec < 0) return;
+        Rec& r = recs[rec];
+        if (r.nmarks > MAX_PHASES) return;
+        r.ev[r.nmarks] = get();
+        r.phase_of_mark[r.nmarks] = phase;
+        cudaEventRecord(r.ev[r.nmarks], st);
+        r.nmarks++;
+    }
+    // sums[kind][phase] += elapsed; runs[kind]++; releases the events.  Caller has synchronised the device.
+    void collect(double sums[KINDS][MAX_PHASES], uint64_t runs[KINDS]) {
+        for (Rec& r : recs) {
+            for (int i = 1; i < r.nmarks; i++) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, r.ev[i - 1], r.ev[i]) == cudaSuccess) sums[r.kind][r.phase_of_mark[i]] += ms;
+            }
+            for (int i = 0; i < r.nmarks; i++) pool.push_back(r.ev[i]);
+            runs[r.kind]++;
+        }
+        recs.clear();
+    }
+};
+extern Profiler g_prof;
+enum MsmPhase { MSM_PH_RECODE = 0, MSM_PH_SORT, MSM_PH_OFFSETS, MSM_PH_ACCUMULATE, MSM_PH_LARGE, MSM_PH_REDUCE };
+enum NttPhase { NTT_PH_RADIX3 = 0, NTT_PH_PASS0, NTT_PH_PASS1, NTT_PH_PASS2 };
+
 // ---------------------------------------------------------------- NTT
 struct NttDomain {
     NttPlan plan;
@@ -34,7 +98,6 @@ struct NttCoset {
     uint32_t n_hi = 0;
 };
 
-fe ntt_root_of_unity(uint64_t n, bool* ok);
 
 class NttEngine {
 public:
@@ -93,6 +156,7 @@ public:
     int run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n, jacobian* d_out, cudaStream_t st);
     int g1_add(const jacobian* d_a, const jacobian* d_b, jacobian* d_out, cudaStream_t st);
     int g1_to_affine(const jacobian* d_in, affine* d_out, cudaStream_t st);
+    int powers_of_tau(const fe& tau, uint64_t first, uint32_t count, affine* d_out, cudaStream_t st);
     void force_lanes(uint32_t g) { force_lanes_ = g; }  // tuning knob (0 = automatic)
 
 private:

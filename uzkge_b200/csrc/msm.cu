@@ -442,6 +442,24 @@ __global__ void g1_to_affine_kernel(const jacobian* in, affine* out) {
     st_affine(out, r);
 }
 
+// ------------------------------------------------------------------ SRS generation (setup path)
+// out[i] = tau^i * G, i < n, affine: the G1 half of KZGCommitmentScheme::new
+// (/root/reference/uzkge/src/poly_commit/kzg_poly_commitment.rs:183-204, n sequential scalar multiplications
+// there).  One thread per point: tau^i by square-and-multiply in Fr, then double-and-add over the bits of the
+// canonical scalar, then one Fermat inversion.
+__global__ void __launch_bounds__(128) g1_powers_of_tau_kernel(fe tau, affine g, uint64_t first, uint32_t count, affine* out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const fe s = fe_from_mont<FrP>(fe_pow_u64<FrP>(tau, first + t));
+    xyzz acc = xyzz_identity();
+#pragma unroll 1
+    for (int bit = 253; bit >= 0; bit--) {
+        acc = xyzz_dbl(acc);
+        if ((s.l[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, g);
+    }
+    st_affine(out + t, xyzz_to_affine(acc));
+}
+
 // ------------------------------------------------------------------ fixed-base tables
 // next[i] = 2^c * prev[i] for i in the slab [first, first + count).  Thread t handles the points
 // first + t + j * nthreads, j < B: doubles each in XYZZ (kept in `tmp`), then normalises the B points with
@@ -637,6 +655,7 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
         return UZKGE_OK;
     }
     const uint32_t m = (uint32_t)(s->windows * n);
+    const int prof = g_prof.begin(Profiler::MSM, st);
     RecodeArgs ra;
     ra.scalars = d_scalars;
     ra.n = (uint32_t)n;
@@ -648,16 +667,19 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     ra.vals = s->vals_a;
     msm_recode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ra);
     UZ_CUDA_TRY(cudaGetLastError());
+    g_prof.mark(prof, MSM_PH_RECODE, st);
 
     cub::DoubleBuffer<uint32_t> dk(s->keys_a, s->keys_b), dv(s->vals_a, s->vals_b);
     size_t temp = s->cub_temp_bytes;
     UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_temp, temp, dk, dv, (int)m, 0, (int)s->c, st));
     const uint32_t* keys = dk.Current();
     const uint32_t* vals = dv.Current();
+    g_prof.mark(prof, MSM_PH_SORT, st);
 
     msm_offsets_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(keys, m, s->nbuckets, s->offsets);
     UZ_CUDA_TRY(cudaGetLastError());
     UZ_CUDA_TRY(cudaMemsetAsync(s->large_list, 0, 4, st));
+    g_prof.mark(prof, MSM_PH_OFFSETS, st);
 
     // lanes per bucket: aim at ~48 entries per lane
     const double mean = (double)m / (double)(s->nbuckets - 1);
@@ -686,6 +708,7 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
         default: e = launch_accumulate<32>(aa, st); break;
     }
     UZ_CUDA_TRY(e);
+    g_prof.mark(prof, MSM_PH_ACCUMULATE, st);
 
     LargeArgs la;
     la.tables = s->tables;
@@ -704,6 +727,7 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     msm_large_accumulate_kernel<<<slices_now, LARGE_NT, 2 * 4 * LARGE_NT * sizeof(uint4), st>>>(la);
     msm_large_finish_kernel<<<cap_now, 32, 0, st>>>(la);
     UZ_CUDA_TRY(cudaGetLastError());
+    g_prof.mark(prof, MSM_PH_LARGE, st);
 
     MarginalArgs ma;
     ma.buckets = s->buckets;
@@ -721,7 +745,18 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     fa.logcols = s->logcols;
     msm_final_kernel<<<2, FIN_NT, 0, st>>>(fa);
     UZ_CUDA_TRY(cudaGetLastError());
+    g_prof.mark(prof, MSM_PH_REDUCE, st);
     UZ_COUNT_LAUNCH(8 + 3);  // own kernels + CUB's radix-sort launches (histogram, scan, onesweep passes: >= 3)
+    return UZKGE_OK;
+}
+
+int MsmEngine::powers_of_tau(const fe& tau, uint64_t first, uint32_t count, affine* d_out, cudaStream_t st) {
+    affine g;  // the generator (1, 2)
+    g.x = fe_one<FqP>();
+    g.y = fe_dbl<FqP>(g.x);
+    g1_powers_of_tau_kernel<<<(count + 127) / 128, 128, 0, st>>>(tau, g, first, count, d_out);
+    UZ_COUNT_LAUNCH(1);
+    UZ_CUDA_TRY(cudaGetLastError());
     return UZKGE_OK;
 }
 

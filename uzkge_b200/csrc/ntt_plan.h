@@ -172,4 +172,38 @@ inline bool ntt_make_plan(uint64_t n, uint32_t max_log_tile, uint32_t max_log_r,
     return true;
 }
 
+// LARGE = 5^((r-1)/(2^28 * 9)) in Montgomery form: generator of the 2^28 * 3^2 subgroup;
+// w_N = LARGE^(3^(2-a) * 2^(28-b)) for N = 3^a 2^b.  Pinned by tests/golden/domain_kat.json.
+inline fe fr_large_subgroup_root() {
+    fe g = fe_zero();
+    g.l[0] = 5;
+    g = fe_to_mont<FrP>(g);
+    // exponent (r - 1) / (2^28 * 9), little-endian 32-bit limbs
+    static const uint32_t e[8] = {0x2358d107u, 0x9f828f3bu, 0xd5b19cf2u, 0x58026433u,
+                                  0x2b395f7du, 0xacca004au, 0x5607a7e8u, 0x00000000u};
+    fe acc = fe_one<FrP>();
+    for (int i = 255; i >= 0; i--) {
+        acc = fe_sqr<FrP>(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = fe_mul<FrP>(acc, g);
+    }
+    return acc;
+}
+
+inline fe ntt_root_of_unity(uint64_t n, bool* ok) {
+    uint32_t a = 0, b = 0;
+    uint64_t m = n;
+    *ok = false;
+    if (n == 0) return fe_zero();
+    while (m % 3 == 0) { m /= 3; a++; }
+    while (m % 2 == 0) { m /= 2; b++; }
+    if (m != 1 || a > 2 || b > 28) return fe_zero();
+    static const fe large = fr_large_subgroup_root();
+    fe w = large;
+    for (uint32_t i = 0; i < 2 - a; i++) w = fe_mul<FrP>(fe_sqr<FrP>(w), w);
+    for (uint32_t i = 0; i < 28 - b; i++) w = fe_sqr<FrP>(w);
+    *ok = true;
+    return w;
+}
+
+
 }  // namespace uz

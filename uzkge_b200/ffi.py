@@ -37,6 +37,7 @@ _SIGNATURES = {
     "uzkge_cuda_last_error": (C.c_char_p, []),
     "uzkge_cuda_version": (C.c_char_p, []),
     "uzkge_cuda_srs_upload": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, u64p]),
+    "uzkge_cuda_srs_generate": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_srs_free": (C.c_int32, [C.c_uint64]),
     "uzkge_cuda_msm_g1": (C.c_int32, [C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_msm_g1_batch": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p]),
@@ -55,6 +56,8 @@ _SIGNATURES = {
     "uzkge_cuda_host_unregister": (C.c_int32, [C.c_void_p]),
     "uzkge_cuda_srs_info": (C.c_int32, [C.c_uint64, C.POINTER(SrsInfo)]),
     "uzkge_cuda_launch_count": (C.c_uint64, []),
+    "uzkge_cuda_profile_enable": (C.c_int32, [C.c_int32]),
+    "uzkge_cuda_profile_read": (C.c_int32, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "uzkge_cuda_configure": (C.c_int32, [C.c_char_p, C.c_uint64]),
     "uzkge_cuda_field_mul": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "uzkge_cuda_bench_field_mul": (C.c_int32, [C.c_int32, C.c_uint32, C.POINTER(C.c_double)]),
@@ -130,6 +133,24 @@ def launch_count() -> int:
     return int(lib().uzkge_cuda_launch_count())
 
 
+MSM_PHASES = ("recode", "sort", "offsets", "accumulate", "large", "reduce")
+NTT_PHASES = ("radix3", "pass0", "pass1", "pass2")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().uzkge_cuda_profile_enable(1 if on else 0))
+
+
+def profile_read(kind: str) -> dict:
+    """Average per-phase device milliseconds per engine run since the last read."""
+    ms = (C.c_double * 8)()
+    runs = C.c_uint64(0)
+    check(lib().uzkge_cuda_profile_read(0 if kind == "msm" else 1, ms, C.byref(runs)))
+    names = MSM_PHASES if kind == "msm" else NTT_PHASES
+    r = max(1, int(runs.value))
+    return {"runs": int(runs.value), "ms": {n: ms[i] / r for i, n in enumerate(names)}}
+
+
 def configure(key: str, value: int) -> None:
     check(lib().uzkge_cuda_configure(key.encode(), value))
 
@@ -139,6 +160,14 @@ def srs_upload(affine_xy: np.ndarray, window_bits: int = 0) -> int:
     h = C.c_uint64(0)
     check(lib().uzkge_cuda_srs_upload(ptr(pts), pts.shape[0], window_bits, C.byref(h)), CommitmentError)
     return int(h.value)
+
+
+def srs_generate(tau, n: int) -> np.ndarray:
+    """(n, 8) affine powers-of-tau SRS: tau^i * G."""
+    t = as_u64(tau).reshape(4)
+    out = np.zeros((n, 8), dtype=np.uint64)
+    check(lib().uzkge_cuda_srs_generate(ptr(t), n, ptr(out)), CommitmentError)
+    return out
 
 
 def srs_free(handle: int) -> None:
