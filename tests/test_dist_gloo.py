@@ -1,0 +1,81 @@
+"""CPU, world_size 2, gloo: the N > 1 host logic (slice ownership, the 96-byte all-gather, the combine order) with the
+CPU oracle injected as the compute callable -- the CUDA kernels themselves are covered by the -m gpu tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import cpu as oc
+        from uzkge_b200 import dist as udist
+
+        pts = oc.g1_random_points(n, 3)
+        sc = oc.random_fr(n - 5, 4)  # shorter than the SRS: the last slice is ragged
+        store = {}
+
+        def upload(p):
+            store[1] = p
+            return 1
+
+        srs = udist.ShardedSrs(pts, rank, world, upload=upload)
+        assert (srs.lo, srs.hi) == udist.shard_range(n, rank, world)
+        got = udist.msm_sharded(srs, sc, msm_fn=lambda h, s: oc.msm_g1(store[h][: s.shape[0]], s), add_fn=oc.g1_add_jac)
+        want = oc.msm_g1(pts[: n - 5], sc)
+        ok1 = np.array_equal(oc.g1_to_affine(got), oc.g1_to_affine(want))
+
+        polys = [oc.random_fr(m, 10 + m) for m in (7, 64, 33, 1, 50)]
+        outs = udist.commit_distributed(polys, rank, world, lambda c: oc.msm_g1(pts[: c.shape[0]], c))
+        ok2 = all(np.array_equal(oc.g1_to_affine(outs[j]), oc.g1_to_affine(oc.msm_g1(pts[: p.shape[0]], p)))
+                  for j, p in enumerate(polys))
+        # scalars shorter than the first slice: the other rank contributes the identity
+        short = sc[:3]
+        got3 = udist.msm_sharded(srs, short, msm_fn=lambda h, s: oc.msm_g1(store[h][: s.shape[0]], s), add_fn=oc.g1_add_jac)
+        ok3 = np.array_equal(oc.g1_to_affine(got3), oc.g1_to_affine(oc.msm_g1(pts[:3], short)))
+        q.put((rank, ok1, ok2, ok3))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_covers_everything():
+    from uzkge_b200.dist import shard_range
+
+    for n in (0, 1, 7, 8, 1 << 20, (1 << 20) + 3):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_sharded_msm_and_distributed_commits_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, n = 2, 301
+    port = free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] and r[3] for r in res), res
