@@ -445,6 +445,13 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
         g.msm->force_lanes((uint32_t)value);
         return UZKGE_OK;
     }
+    if (k == "ntt_big_threads") {
+        if (value != 512 && value != 1024) return fail(UZKGE_ERR_ARG, "configure: ntt_big_threads is 512 or 1024");
+        int rc = ensure_init(-1);
+        if (rc != UZKGE_OK) return rc;
+        g.ntt->set_big_threads((uint32_t)value);
+        return UZKGE_OK;
+    }
     if (k == "ntt_log_tile" || k == "ntt_max_log_r" || k == "ntt_two_pass_max") {
         if (k == "ntt_log_tile") {
             if (value < 4 || value > 12) return fail(UZKGE_ERR_ARG, "configure: ntt_log_tile in 4..12");

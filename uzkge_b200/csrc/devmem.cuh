@@ -77,6 +77,17 @@ __device__ __forceinline__ xyzz shfl_xor_xyzz(const xyzz& a, int mask) {
     r.zzz = shfl_xor_fe(a.zzz, mask);
     return r;
 }
+__device__ __forceinline__ xyzz shfl_xyzz(const xyzz& a, int src) {
+    xyzz r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.l[i] = __shfl_sync(0xffffffffu, a.x.l[i], src);
+        r.y.l[i] = __shfl_sync(0xffffffffu, a.y.l[i], src);
+        r.zz.l[i] = __shfl_sync(0xffffffffu, a.zz.l[i], src);
+        r.zzz.l[i] = __shfl_sync(0xffffffffu, a.zzz.l[i], src);
+    }
+    return r;
+}
 __device__ __forceinline__ fe shfl_down_fe(const fe& a, int delta) {
     fe r;
 #pragma unroll

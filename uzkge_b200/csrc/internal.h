@@ -103,6 +103,7 @@ class NttEngine {
 public:
     explicit NttEngine(int sm_count) : sm_count_(sm_count) {}
     ~NttEngine();
+    void set_big_threads(uint32_t nt) { cfg_big_threads_ = nt; }
     void configure(uint32_t log_tile, uint32_t max_log_r, uint32_t two_pass_max) {
         cfg_log_tile_ = log_tile;
         cfg_max_log_r_ = max_log_r;
@@ -117,7 +118,7 @@ private:
     std::map<uint64_t, NttDomain> domains_;
     std::vector<NttCoset> cosets_;
     int sm_count_;
-    uint32_t cfg_log_tile_ = 12, cfg_max_log_r_ = 11, cfg_two_pass_max_ = 22;
+    uint32_t cfg_log_tile_ = 12, cfg_max_log_r_ = 11, cfg_two_pass_max_ = 22, cfg_big_threads_ = 1024;
 };
 
 // ---------------------------------------------------------------- MSM

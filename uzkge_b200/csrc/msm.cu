@@ -29,8 +29,8 @@ namespace uz {
 static constexpr int ACC_NT = 256;            // threads per CTA of the accumulate kernel
 static constexpr uint32_t LARGE_SLICE = 4096; // entries per CTA slice of an oversized bucket
 static constexpr int LARGE_NT = 256;
-static constexpr int RED_NT = 128;            // marginal-sum CTAs
-static constexpr int FIN_NT = 256;            // final weighted-sum CTAs
+static constexpr int RED_NT = 128;            // marginal-sum CTAs: one warp per sum
+static constexpr int FIN_NT = 128;            // final weighted-sum CTAs: one warp per SM sub-partition
 
 // ------------------------------------------------------------------ recode
 struct RecodeArgs {
@@ -282,15 +282,23 @@ __global__ void __launch_bounds__(32) msm_large_finish_kernel(const LargeArgs a)
 }
 
 // ------------------------------------------------------------------ reduce
-// CTA o < rows: R[o] = sum_c B[o][c];  CTA rows + o: C[o] = sum_r B[r][o]
+// sum_b b * B_b over the 2^(c-1) + 1 buckets.  Every sequential group operation of a warp costs >= 14 field
+// multiplications of fma-pipe time (~4 us) no matter how few lanes are active, so the reduction is organised
+// to minimise the number of DEPENDENT warp-level operations (about 35) rather than the amount of work:
+//   matrix  : b = hi * cols + lo for b < 2^(c-1); the top bucket 2^(c-1) is handled on its own
+//   marginals: R_hi = sum_lo B[hi][lo],  C_lo = sum_hi B[hi][lo]   -- one warp per sum, plain additions
+//   weighted : A = sum_hi hi R_hi,  B = sum_lo lo C_lo             -- suffix scans, no scalar multiplication
+//   result  = 2^logcols A + B + 2^(c-1) B_top
 struct MarginalArgs {
     const xyzz* buckets;
     xyzz* marg;  // rows + cols
     uint32_t rows, cols;
 };
+// warp w of the grid: w < rows: R[w];  else C[w - rows]
 __global__ void __launch_bounds__(RED_NT) msm_marginals_kernel(const MarginalArgs a) {
-    __shared__ xyzz scratch[RED_NT / 32];
-    uint32_t o = blockIdx.x;
+    const uint32_t o = blockIdx.x * (RED_NT / 32) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (o >= a.rows + a.cols) return;
     const xyzz* base;
     uint32_t count, stride;
     if (o < a.rows) {
@@ -304,99 +312,105 @@ __global__ void __launch_bounds__(RED_NT) msm_marginals_kernel(const MarginalArg
     }
     xyzz acc = xyzz_identity();
 #pragma unroll 1
-    for (uint32_t e = threadIdx.x; e < count; e += RED_NT) {
+    for (uint32_t e = lane; e < count; e += 32) {
         const xyzz v = ld_xyzz(base + (size_t)e * stride);
         xyzz_add(acc, v);
     }
-    block_sum_xyzz<RED_NT>(acc, scratch);
-    if (threadIdx.x == 0) st_xyzz(a.marg + blockIdx.x, acc);
-}
-
-// Lanes 0..nl-1 of a warp hold consecutive blocks (lane 0 lowest) of 2^loglen indices each, as
-// (S = plain sum, T = sum of (index - block start) * X).  Returns the combined (S, T) in lane 0:
-//   S = sum_l S_l,  T = sum_l T_l + 2^loglen * sum_{l >= 1} (sum_{m >= l} S_m).
-__device__ __forceinline__ void warp_weighted_combine(xyzz& S, xyzz& T, uint32_t loglen) {
-    const uint32_t lane = threadIdx.x & 31;
-    // inclusive suffix scan of S
-#pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
-        const xyzz o = shfl_down_xyzz(S, off);
-        if (lane + off < 32) xyzz_add(S, o);
-    }
-    // W = sum_{l >= 1} P_l ; lane 0 contributes nothing
-    xyzz W = lane ? S : xyzz_identity();
 #pragma unroll 1
     for (int off = 16; off > 0; off >>= 1) {
-        const xyzz o = shfl_down_xyzz(W, off);
-        xyzz_add(W, o);
-        const xyzz t = shfl_down_xyzz(T, off);
-        xyzz_add(T, t);
+        const xyzz t = shfl_down_xyzz(acc, off);
+        xyzz_add(acc, t);
     }
-    if (lane == 0) {
-        for (uint32_t i = 0; i < loglen; i++) W = xyzz_dbl(W);
-        xyzz_add(T, W);
-    }
+    if (lane == 0) st_xyzz(a.marg + o, acc);
 }
 
 // weighted sum sum_j j * X[j], j < m, by one CTA of FIN_NT threads; result in thread 0.
-__device__ __forceinline__ xyzz block_weighted_sum(const xyzz* X, uint32_t m, xyzz* sh_s, xyzz* sh_t) {
+//   thread t owns the 2^logq consecutive indices starting at t * 2^logq:  S_t = sum X, T_t = sum (j - start) X[j]
+//   P_t = sum_{u >= t} S_u (suffix scan: warp shuffles, then the warp totals)
+//   sum_j j X[j] = sum_t T_t + 2^logq * sum_{t >= 1} P_t
+__device__ __forceinline__ xyzz block_weighted_sum(const xyzz* X, uint32_t m, xyzz* sh) {
+    constexpr uint32_t NW = FIN_NT / 32;
     uint32_t logq = 0;
     while (((uint32_t)FIN_NT << logq) < m) logq++;
     const uint32_t q = 1u << logq;
     const uint32_t lo = min(threadIdx.x * q, m), hi = min(lo + q, m);
-    xyzz run = xyzz_identity(), acc = xyzz_identity();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    xyzz P = xyzz_identity(), T = xyzz_identity();
 #pragma unroll 1
     for (uint32_t j = hi; j > lo + 1; j--) {
         const xyzz v = ld_xyzz(X + j - 1);
-        xyzz_add(run, v);
-        xyzz_add(acc, run);
+        xyzz_add(P, v);
+        xyzz_add(T, P);
     }
     if (hi > lo) {
         const xyzz v = ld_xyzz(X + lo);
-        xyzz_add(run, v);
+        xyzz_add(P, v);
     }
-    warp_weighted_combine(run, acc, logq);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        sh_s[warp] = run;
-        sh_t[warp] = acc;
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        const xyzz o = shfl_down_xyzz(P, off);
+        if (lane + off < 32) xyzz_add(P, o);
     }
+    if (lane == 0) sh[warp] = P;
     __syncthreads();
-    if (warp == 0) {
-        constexpr uint32_t NW = FIN_NT / 32;
-        run = lane < NW ? sh_s[lane] : xyzz_identity();
-        acc = lane < NW ? sh_t[lane] : xyzz_identity();
-        warp_weighted_combine(run, acc, logq + 5);
+    {   // suffix scan of the warp totals (every warp redundantly), then add the total of the warps above
+        xyzz w = lane < NW ? sh[lane] : xyzz_identity();
+#pragma unroll 1
+        for (int off = 1; off < (int)NW; off <<= 1) {
+            const xyzz o = shfl_down_xyzz(w, off);
+            if (lane + off < NW) xyzz_add(w, o);
+        }
+        const xyzz above = shfl_xyzz(w, (warp + 1) & 31);
+        if (warp + 1 < NW) xyzz_add(P, above);
     }
-    return acc;
+    if (threadIdx.x == 0) {
+        P = xyzz_identity();
+    } else {
+        for (uint32_t i = 0; i < logq; i++) P = xyzz_dbl(P);
+    }
+    xyzz_add(P, T);
+    __syncthreads();  // sh is reused by block_sum_xyzz
+    block_sum_xyzz<FIN_NT>(P, sh);
+    return P;
 }
 
 struct FinalArgs {
     const xyzz* marg;    // rows + cols marginal sums
-    xyzz* partial;       // 2 entries
+    const xyzz* top;     // bucket 2^(c-1)
+    xyzz* partial;       // 3 entries
     uint32_t* ticket;
     jacobian* out;
-    uint32_t rows, cols, logcols;
+    uint32_t rows, cols, logcols, c;
 };
-// CTA 0: sum_hi hi * R[hi];  CTA 1: sum_lo lo * C[lo];  the CTA that finishes last combines:
-//   result = 2^logcols * A + B
+// CTA 0: 2^logcols * sum_hi hi R[hi];  CTA 1: sum_lo lo C[lo];  CTA 2: 2^(c-1) * top;  the last one to finish adds them
 __global__ void __launch_bounds__(FIN_NT) msm_final_kernel(const FinalArgs a) {
-    __shared__ xyzz sh_s[FIN_NT / 32], sh_t[FIN_NT / 32];
+    __shared__ xyzz sh[FIN_NT / 32];
     __shared__ uint32_t is_last;
-    const xyzz* X = blockIdx.x == 0 ? a.marg : a.marg + a.rows;
-    const uint32_t m = blockIdx.x == 0 ? a.rows : a.cols;
-    xyzz r = block_weighted_sum(X, m, sh_s, sh_t);
+    xyzz r;
+    if (blockIdx.x == 0) {
+        r = block_weighted_sum(a.marg, a.rows, sh);
+        if (threadIdx.x == 0)
+            for (uint32_t i = 0; i < a.logcols; i++) r = xyzz_dbl(r);
+    } else if (blockIdx.x == 1) {
+        r = block_weighted_sum(a.marg + a.rows, a.cols, sh);
+    } else {
+        if (threadIdx.x == 0) {
+            r = ld_xyzz(a.top);
+            for (uint32_t i = 0; i + 1 < a.c; i++) r = xyzz_dbl(r);
+        }
+    }
     if (threadIdx.x == 0) {
         st_xyzz(a.partial + blockIdx.x, r);
         __threadfence();
-        is_last = (atomicAdd(a.ticket, 1u) == 1u);
+        is_last = (atomicAdd(a.ticket, 1u) == 2u);
     }
     __syncthreads();
     if (!is_last || threadIdx.x != 0) return;
     __threadfence();
-    xyzz A = ld_xyzz(a.partial), B = ld_xyzz(a.partial + 1);
-    for (uint32_t i = 0; i < a.logcols; i++) A = xyzz_dbl(A);
+    xyzz A = ld_xyzz(a.partial);
+    const xyzz B = ld_xyzz(a.partial + 1), C = ld_xyzz(a.partial + 2);
     xyzz_add(A, B);
+    xyzz_add(A, C);
     const jacobian j = xyzz_to_jacobian(A);
     st_fe(&a.out->x, j.x);
     st_fe(&a.out->y, j.y);
@@ -549,8 +563,8 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     s->nbuckets = (1u << (c - 1)) + 1;
     s->logcols = c / 2;                       // cols = 2^ceil((c-1)/2)
     s->cols = 1u << s->logcols;
-    s->rows = (1u << (c - 1 - s->logcols)) + 1;  // + 1: the top bucket 2^(c-1) sits alone in the last row
-    s->nb_padded = s->rows * s->cols;
+    s->rows = 1u << (c - 1 - s->logcols);     // rows * cols = 2^(c-1); the top bucket 2^(c-1) is stored after the matrix
+    s->nb_padded = s->nbuckets;
     const size_t m = (size_t)windows * n;
     s->large_cap = (uint32_t)(m / LARGE_SLICE + 1);
     s->max_slices = (uint32_t)(m / LARGE_SLICE + s->large_cap);
@@ -569,7 +583,7 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     const size_t o_slice_sums = take(sizeof(xyzz) * s->max_slices);
     const size_t o_buckets = take(sizeof(xyzz) * s->nb_padded);
     const size_t o_marg = take(sizeof(xyzz) * ((size_t)s->rows + s->cols));
-    const size_t o_partial = take(sizeof(xyzz) * 2);
+    const size_t o_partial = take(sizeof(xyzz) * 4);
     const size_t o_ticket = take(256);
     cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
     s->cub_temp_bytes = 0;
@@ -734,16 +748,18 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     ma.marg = s->marg;
     ma.rows = s->rows;
     ma.cols = s->cols;
-    msm_marginals_kernel<<<s->rows + s->cols, RED_NT, 0, st>>>(ma);
+    msm_marginals_kernel<<<(s->rows + s->cols + RED_NT / 32 - 1) / (RED_NT / 32), RED_NT, 0, st>>>(ma);
     FinalArgs fa;
     fa.marg = s->marg;
+    fa.top = s->buckets + (size_t)s->rows * s->cols;
+    fa.c = s->c;
     fa.partial = s->partial;
     fa.ticket = s->ticket;
     fa.out = d_out;
     fa.rows = s->rows;
     fa.cols = s->cols;
     fa.logcols = s->logcols;
-    msm_final_kernel<<<2, FIN_NT, 0, st>>>(fa);
+    msm_final_kernel<<<3, FIN_NT, 0, st>>>(fa);
     UZ_CUDA_TRY(cudaGetLastError());
     g_prof.mark(prof, MSM_PH_REDUCE, st);
     UZ_COUNT_LAUNCH(8 + 3);  // own kernels + CUB's radix-sort launches (histogram, scan, onesweep passes: >= 3)

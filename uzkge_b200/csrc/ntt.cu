@@ -334,7 +334,9 @@ int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, ui
         if (ka.p.last && ka.in == ka.out && (ka.p.inner_tiles * ka.p.outer * ka.p.batch) > 1) return UZKGE_ERR_INTERNAL;
         const uint32_t T = 1u << (ka.p.logR + ka.p.logC);
         cudaError_t e;
-        if (T >= 2048)
+        if (T >= 4096 && cfg_big_threads_ == 1024)
+            e = launch_pass<1024>(ka, st);
+        else if (T >= 2048)
             e = launch_pass<512>(ka, st);
         else if (T >= 512)
             e = launch_pass<256>(ka, st);
