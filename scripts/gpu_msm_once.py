@@ -1,0 +1,18 @@
+"""One MSM configuration, a few launches (for ncu): python scripts/gpu_msm_once.py LOG_N [C]"""
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch
+from uzkge_b200 import ffi
+import bench as B
+lg = int(sys.argv[1]); c = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+ffi.init(0)
+dev = torch.device("cuda", 0)
+n = 1 << lg
+bases = ffi.srs_generate(B.random_fr(1, 5)[0], n)
+h = ffi.srs_upload(bases, c)
+sc = torch.from_numpy(B.random_fr(n, 2).view(np.int64)).to(dev)
+out = torch.zeros(12, dtype=torch.int64, device=dev)
+for _ in range(4):
+    ffi.msm_g1_device(h, sc.data_ptr(), n, out.data_ptr())
+torch.cuda.synchronize()
+print(ffi.srs_info(h))

@@ -22,8 +22,14 @@ struct jacobian {
     fe x, y, z;
 };
 
-#define FQ_MUL(a, b) fe_mul<FqP>(a, b)
-#define FQ_SQR(a) fe_sqr<FqP>(a)
+// Multiplication policy: the throughput-bound kernels inline every product; the latency-bound reduction kernels
+// call ONE shared copy (ec_compact.cuh) so that their code stays inside the instruction caches.
+struct FqInline {
+    UZ_HD static fe mul(const fe& a, const fe& b) { return fe_mul<FqP>(a, b); }
+    UZ_HD static fe sqr(const fe& a) { return fe_sqr<FqP>(a); }
+};
+#define FQ_MUL(a, b) M::mul(a, b)
+#define FQ_SQR(a) M::sqr(a)
 #define FQ_ADD(a, b) fe_add<FqP>(a, b)
 #define FQ_SUB(a, b) fe_sub<FqP>(a, b)
 #define FQ_DBL(a) fe_dbl<FqP>(a)
@@ -50,6 +56,7 @@ UZ_HD xyzz xyzz_from_affine(const affine& p) {
 }
 
 // 2 * (affine p), p != identity  (mdbl-2008-s-1)
+template <class M = FqInline>
 UZ_HD xyzz xyzz_dbl_affine(const affine& p) {
     xyzz r;
     fe u = FQ_DBL(p.y);
@@ -66,6 +73,7 @@ UZ_HD xyzz xyzz_dbl_affine(const affine& p) {
 }
 
 // 2 * p  (dbl-2008-s-1); a point of order 2 does not exist on G1 (odd prime order), y == 0 only at identity
+template <class M = FqInline>
 UZ_HD xyzz xyzz_dbl(const xyzz& p) {
     if (xyzz_is_identity(p)) return p;
     xyzz r;
@@ -83,6 +91,7 @@ UZ_HD xyzz xyzz_dbl(const xyzz& p) {
 }
 
 // acc += (x2, y2) with y2 already sign-adjusted by the caller  (madd-2008-s: 8M + 2S)
+template <class M = FqInline>
 UZ_HD void xyzz_madd(xyzz& acc, const affine& q) {
     if (affine_is_identity(q)) return;
     if (xyzz_is_identity(acc)) {
@@ -95,7 +104,7 @@ UZ_HD void xyzz_madd(xyzz& acc, const affine& q) {
     fe r = FQ_SUB(s2, acc.y);
     if (fe_is_zero(p)) {
         if (fe_is_zero(r))
-            acc = xyzz_dbl_affine(q);
+            acc = xyzz_dbl_affine<M>(q);
         else
             acc = xyzz_identity();
         return;
@@ -112,6 +121,7 @@ UZ_HD void xyzz_madd(xyzz& acc, const affine& q) {
 }
 
 // acc += q  (add-2008-s: 12M + 2S)
+template <class M = FqInline>
 UZ_HD void xyzz_add(xyzz& acc, const xyzz& q) {
     if (xyzz_is_identity(q)) return;
     if (xyzz_is_identity(acc)) {
@@ -126,7 +136,7 @@ UZ_HD void xyzz_add(xyzz& acc, const xyzz& q) {
     fe r = FQ_SUB(s2, s1);
     if (fe_is_zero(p)) {
         if (fe_is_zero(r))
-            acc = xyzz_dbl(acc);
+            acc = xyzz_dbl<M>(acc);
         else
             acc = xyzz_identity();
         return;
@@ -142,6 +152,7 @@ UZ_HD void xyzz_add(xyzz& acc, const xyzz& q) {
     acc.zzz = FQ_MUL(FQ_MUL(acc.zzz, q.zzz), ppp);
 }
 
+template <class M = FqInline>
 UZ_HD jacobian xyzz_to_jacobian(const xyzz& p) {
     jacobian r;
     if (xyzz_is_identity(p)) {  // arkworks' Projective::zero() is (1, 1, 0)
@@ -157,6 +168,7 @@ UZ_HD jacobian xyzz_to_jacobian(const xyzz& p) {
 }
 
 // XYZZ -> affine (one inversion); identity -> (0, 0)
+template <class M = FqInline>
 UZ_HD affine xyzz_to_affine(const xyzz& p) {
     affine r;
     if (xyzz_is_identity(p)) {
@@ -182,11 +194,12 @@ UZ_HD affine affine_neg(const affine& p) {
 }
 
 // k * p for a small unsigned k (bucket-segment offsets); double-and-add, MSB first
+template <class M = FqInline>
 UZ_HD xyzz xyzz_mul_u32(const xyzz& p, uint32_t k) {
     xyzz acc = xyzz_identity();
     for (int i = 31; i >= 0; i--) {
-        acc = xyzz_dbl(acc);
-        if ((k >> i) & 1) xyzz_add(acc, p);
+        acc = xyzz_dbl<M>(acc);
+        if ((k >> i) & 1) xyzz_add<M>(acc, p);
     }
     return acc;
 }

@@ -137,6 +137,7 @@ struct MsmSrs {
     // workspace, sized for an MSM over the whole SRS
     uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
     uint32_t* offsets = nullptr;      // nbuckets + 1
+    uint32_t *ord_keys_a = nullptr, *ord_keys_b = nullptr, *ord_vals_a = nullptr, *ord_vals_b = nullptr;  // size-ordered bucket ids
     uint32_t* large_list = nullptr;   // [0] = count, then bucket ids
     uint32_t* slice_start = nullptr;  // prefix of CTA slices per oversized bucket
     xyzz* slice_sums = nullptr;

@@ -22,12 +22,13 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "devmem.cuh"
+#include "ec_compact.cuh"
 #include "internal.h"
 
 namespace uz {
 
 static constexpr int ACC_NT = 256;            // threads per CTA of the accumulate kernel
-static constexpr uint32_t LARGE_SLICE = 4096; // entries per CTA slice of an oversized bucket
+static constexpr uint32_t LARGE_SLICE = 1024; // entries per warp slice of an oversized bucket
 static constexpr int LARGE_NT = 256;
 static constexpr int RED_NT = 128;            // marginal-sum CTAs: one warp per sum
 static constexpr int FIN_NT = 128;            // final weighted-sum CTAs: one warp per SM sub-partition
@@ -78,11 +79,22 @@ __global__ void __launch_bounds__(256) msm_offsets_kernel(const uint32_t* __rest
     for (uint32_t b = lo; b <= cur; b++) offsets[b] = i;
 }
 
+// key = cap - min(size, cap): an ascending sort visits the largest segments first
+__global__ void __launch_bounds__(256) msm_sizes_kernel(const uint32_t* __restrict__ offsets, uint32_t nbuckets, uint32_t cap,
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    const uint32_t size = b ? offsets[b + 1] - offsets[b] : 0;
+    keys[b] = cap - min(size, cap);
+    vals[b] = b;
+}
+
 // ------------------------------------------------------------------ accumulate
 struct AccArgs {
     const affine* tables;
     const uint32_t* vals;     // sorted
     const uint32_t* offsets;  // nbuckets + 1
+    const uint32_t* order;    // bucket ids, largest segment first
     xyzz* buckets;            // nb_padded
     uint32_t nbuckets;        // valid bucket ids are 1 .. nbuckets-1
     uint32_t nb_padded;       // rows * cols of the reduction matrix
@@ -141,11 +153,13 @@ __device__ __forceinline__ void accumulate_segment(xyzz& acc, const affine* __re
 }
 
 template <int G>
-__global__ void __launch_bounds__(ACC_NT) msm_accumulate_kernel(const AccArgs a) {
+__global__ void __launch_bounds__(ACC_NT, 2) msm_accumulate_kernel(const AccArgs a) {
     extern __shared__ uint4 acc_smem[];
     const uint32_t gtid = blockIdx.x * ACC_NT + threadIdx.x;
     const uint32_t lane = gtid & (G - 1);
-    const uint32_t b = gtid / G;
+    const uint32_t slot = gtid / G;
+    // buckets are visited in decreasing size: the lanes of a warp get equal work and the longest segments start first
+    const uint32_t b = slot < a.nb_padded ? a.order[slot] : a.nb_padded;
     uint32_t start = 0, end = 0;
     bool write = b < a.nb_padded;
     if (b >= 1 && b < a.nbuckets) {
@@ -163,10 +177,7 @@ __global__ void __launch_bounds__(ACC_NT) msm_accumulate_kernel(const AccArgs a)
     xyzz acc = xyzz_identity();
     accumulate_segment<ACC_NT>(acc, a.tables, a.vals, start + lane, end, G, acc_smem);
 #pragma unroll 1
-    for (int off = G >> 1; off > 0; off >>= 1) {
-        const xyzz o = shfl_xor_xyzz(acc, off);
-        xyzz_add(acc, o);
-    }
+    for (int off = G >> 1; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_xor_xyzz(acc, off));
     if (write && lane == 0) st_xyzz(a.buckets + b, acc);
 }
 
@@ -174,10 +185,7 @@ __global__ void __launch_bounds__(ACC_NT) msm_accumulate_kernel(const AccArgs a)
 template <int NT>
 __device__ __forceinline__ void block_sum_xyzz(xyzz& acc, xyzz* scratch) {
 #pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) {
-        const xyzz o = shfl_down_xyzz(acc, off);
-        xyzz_add(acc, o);
-    }
+    for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t NW = NT / 32;
     if (NW > 1) {
@@ -186,10 +194,7 @@ __device__ __forceinline__ void block_sum_xyzz(xyzz& acc, xyzz* scratch) {
         if (warp == 0) {
             acc = (lane < NW) ? scratch[lane] : xyzz_identity();
 #pragma unroll 1
-            for (int off = NW >> 1; off > 0; off >>= 1) {
-                const xyzz o = shfl_down_xyzz(acc, off);
-                xyzz_add(acc, o);
-            }
+            for (int off = NW >> 1; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
         }
     }
 }
@@ -239,13 +244,14 @@ __global__ void __launch_bounds__(1024) msm_large_plan_kernel(const LargeArgs a)
     if (threadIdx.x == 0) a.slice_start[nl] = carry_s;
 }
 
-__global__ void __launch_bounds__(LARGE_NT) msm_large_accumulate_kernel(const LargeArgs a) {
+// one WARP per slice of LARGE_SLICE entries: lanes stride over the slice, then a shuffle tree
+__global__ void __launch_bounds__(LARGE_NT, 2) msm_large_accumulate_kernel(const LargeArgs a) {
     extern __shared__ uint4 acc_smem[];
-    __shared__ xyzz scratch[LARGE_NT / 32];
     const uint32_t nl = min(a.large_list[0], a.large_cap);
     const uint32_t total = min(a.slice_start[nl], a.max_slices);
-    const uint32_t s = blockIdx.x;
-    if (s >= total) return;
+    const uint32_t s = blockIdx.x * (LARGE_NT / 32) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (s >= total) return;  // warp-uniform
     // largest k with slice_start[k] <= s
     uint32_t lo = 0, hi = nl;
     while (hi - lo > 1) {
@@ -256,9 +262,10 @@ __global__ void __launch_bounds__(LARGE_NT) msm_large_accumulate_kernel(const La
     const uint32_t first = a.offsets[b] + (s - a.slice_start[lo]) * LARGE_SLICE;
     const uint32_t end = min(first + LARGE_SLICE, a.offsets[b + 1]);
     xyzz acc = xyzz_identity();
-    accumulate_segment<LARGE_NT>(acc, a.tables, a.vals, first + threadIdx.x, end, LARGE_NT, acc_smem);
-    block_sum_xyzz<LARGE_NT>(acc, scratch);
-    if (threadIdx.x == 0) st_xyzz(a.slice_sums + s, acc);
+    accumulate_segment<LARGE_NT>(acc, a.tables, a.vals, first + lane, end, 32, acc_smem);
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
+    if (lane == 0) st_xyzz(a.slice_sums + s, acc);
 }
 
 // one warp per listed bucket: sum its slice sums
@@ -269,15 +276,9 @@ __global__ void __launch_bounds__(32) msm_large_finish_kernel(const LargeArgs a)
     const uint32_t s0 = a.slice_start[k], s1 = min(a.slice_start[k + 1], a.max_slices);
     xyzz acc = xyzz_identity();
 #pragma unroll 1
-    for (uint32_t s = s0 + threadIdx.x; s < s1; s += 32) {
-        const xyzz v = ld_xyzz(a.slice_sums + s);
-        xyzz_add(acc, v);
-    }
+    for (uint32_t s = s0 + threadIdx.x; s < s1; s += 32) acc = xyzz_add_call(acc, ld_xyzz(a.slice_sums + s));
 #pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) {
-        const xyzz o = shfl_down_xyzz(acc, off);
-        xyzz_add(acc, o);
-    }
+    for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
     if (threadIdx.x == 0) st_xyzz(a.buckets + a.large_list[1 + k], acc);
 }
 
@@ -312,15 +313,9 @@ __global__ void __launch_bounds__(RED_NT) msm_marginals_kernel(const MarginalArg
     }
     xyzz acc = xyzz_identity();
 #pragma unroll 1
-    for (uint32_t e = lane; e < count; e += 32) {
-        const xyzz v = ld_xyzz(base + (size_t)e * stride);
-        xyzz_add(acc, v);
-    }
+    for (uint32_t e = lane; e < count; e += 32) acc = xyzz_add_call(acc, ld_xyzz(base + (size_t)e * stride));
 #pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) {
-        const xyzz t = shfl_down_xyzz(acc, off);
-        xyzz_add(acc, t);
-    }
+    for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
     if (lane == 0) st_xyzz(a.marg + o, acc);
 }
 
@@ -338,18 +333,15 @@ __device__ __forceinline__ xyzz block_weighted_sum(const xyzz* X, uint32_t m, xy
     xyzz P = xyzz_identity(), T = xyzz_identity();
 #pragma unroll 1
     for (uint32_t j = hi; j > lo + 1; j--) {
-        const xyzz v = ld_xyzz(X + j - 1);
-        xyzz_add(P, v);
-        xyzz_add(T, P);
+        P = xyzz_add_call(P, ld_xyzz(X + j - 1));
+        T = xyzz_add_call(T, P);
     }
-    if (hi > lo) {
-        const xyzz v = ld_xyzz(X + lo);
-        xyzz_add(P, v);
-    }
+    if (hi > lo) P = xyzz_add_call(P, ld_xyzz(X + lo));
 #pragma unroll 1
     for (int off = 1; off < 32; off <<= 1) {
-        const xyzz o = shfl_down_xyzz(P, off);
-        if (lane + off < 32) xyzz_add(P, o);
+        xyzz o = shfl_down_xyzz(P, off);
+        if (lane + off >= 32) o = xyzz_identity();
+        P = xyzz_add_call(P, o);
     }
     if (lane == 0) sh[warp] = P;
     __syncthreads();
@@ -357,18 +349,17 @@ __device__ __forceinline__ xyzz block_weighted_sum(const xyzz* X, uint32_t m, xy
         xyzz w = lane < NW ? sh[lane] : xyzz_identity();
 #pragma unroll 1
         for (int off = 1; off < (int)NW; off <<= 1) {
-            const xyzz o = shfl_down_xyzz(w, off);
-            if (lane + off < NW) xyzz_add(w, o);
+            xyzz o = shfl_down_xyzz(w, off);
+            if (lane + off >= NW) o = xyzz_identity();
+            w = xyzz_add_call(w, o);
         }
-        const xyzz above = shfl_xyzz(w, (warp + 1) & 31);
-        if (warp + 1 < NW) xyzz_add(P, above);
+        xyzz above = shfl_xyzz(w, (warp + 1) & 31);
+        if (warp + 1 >= NW) above = xyzz_identity();
+        P = xyzz_add_call(P, above);
     }
-    if (threadIdx.x == 0) {
-        P = xyzz_identity();
-    } else {
-        for (uint32_t i = 0; i < logq; i++) P = xyzz_dbl(P);
-    }
-    xyzz_add(P, T);
+    if (threadIdx.x == 0) P = xyzz_identity();
+    for (uint32_t i = 0; i < logq; i++) P = xyzz_dbl_call(P);
+    P = xyzz_add_call(P, T);
     __syncthreads();  // sh is reused by block_sum_xyzz
     block_sum_xyzz<FIN_NT>(P, sh);
     return P;
@@ -390,13 +381,13 @@ __global__ void __launch_bounds__(FIN_NT) msm_final_kernel(const FinalArgs a) {
     if (blockIdx.x == 0) {
         r = block_weighted_sum(a.marg, a.rows, sh);
         if (threadIdx.x == 0)
-            for (uint32_t i = 0; i < a.logcols; i++) r = xyzz_dbl(r);
+            for (uint32_t i = 0; i < a.logcols; i++) r = xyzz_dbl_call(r);
     } else if (blockIdx.x == 1) {
         r = block_weighted_sum(a.marg + a.rows, a.cols, sh);
     } else {
         if (threadIdx.x == 0) {
             r = ld_xyzz(a.top);
-            for (uint32_t i = 0; i + 1 < a.c; i++) r = xyzz_dbl(r);
+            for (uint32_t i = 0; i + 1 < a.c; i++) r = xyzz_dbl_call(r);
         }
     }
     if (threadIdx.x == 0) {
@@ -409,9 +400,9 @@ __global__ void __launch_bounds__(FIN_NT) msm_final_kernel(const FinalArgs a) {
     __threadfence();
     xyzz A = ld_xyzz(a.partial);
     const xyzz B = ld_xyzz(a.partial + 1), C = ld_xyzz(a.partial + 2);
-    xyzz_add(A, B);
-    xyzz_add(A, C);
-    const jacobian j = xyzz_to_jacobian(A);
+    A = xyzz_add_call(A, B);
+    A = xyzz_add_call(A, C);
+    const jacobian j = xyzz_to_jacobian<FqCall>(A);
     st_fe(&a.out->x, j.x);
     st_fe(&a.out->y, j.y);
     st_fe(&a.out->z, j.z);
@@ -431,8 +422,8 @@ __device__ __forceinline__ xyzz jacobian_to_xyzz(const jacobian& p) {
     if (fe_is_zero(p.z)) return xyzz_identity();
     r.x = p.x;
     r.y = p.y;
-    r.zz = FQ_SQR(p.z);
-    r.zzz = FQ_MUL(r.zz, p.z);
+    r.zz = fe_sqr<FqP>(p.z);
+    r.zzz = fe_mul<FqP>(r.zz, p.z);
     return r;
 }
 __device__ __forceinline__ jacobian ld_jacobian(const jacobian* p) {
@@ -502,7 +493,7 @@ __global__ void __launch_bounds__(128) msm_table_kernel(const TableArgs a) {
             for (uint32_t k = 1; k < a.c; k++) q = xyzz_dbl(q);
         }
         st_xyzz(a.tmp + i, q);
-        if (!xyzz_is_identity(q)) prod = FQ_MUL(prod, FQ_MUL(q.zz, q.zzz));
+        if (!xyzz_is_identity(q)) prod = fe_mul<FqP>(prod, fe_mul<FqP>(q.zz, q.zzz));
         st_fe(a.pre + i, prod);
     }
     fe inv = fe_inv<FqP>(prod);
@@ -517,10 +508,10 @@ __global__ void __launch_bounds__(128) msm_table_kernel(const TableArgs a) {
             r.y = fe_zero();
         } else {
             const fe before = j ? ld_fe(a.pre + (i - a.nthreads)) : fe_one<FqP>();
-            const fe ti = FQ_MUL(inv, before);            // 1 / (zz * zzz)
-            inv = FQ_MUL(inv, FQ_MUL(q.zz, q.zzz));
-            r.x = FQ_MUL(q.x, FQ_MUL(ti, q.zzz));         // X / ZZ
-            r.y = FQ_MUL(q.y, FQ_MUL(ti, q.zz));          // Y / ZZZ
+            const fe ti = fe_mul<FqP>(inv, before);            // 1 / (zz * zzz)
+            inv = fe_mul<FqP>(inv, fe_mul<FqP>(q.zz, q.zzz));
+            r.x = fe_mul<FqP>(q.x, fe_mul<FqP>(ti, q.zzz));         // X / ZZ
+            r.y = fe_mul<FqP>(q.y, fe_mul<FqP>(ti, q.zz));          // Y / ZZZ
         }
         st_affine(a.next + i, r);
     }
@@ -566,7 +557,8 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     s->rows = 1u << (c - 1 - s->logcols);     // rows * cols = 2^(c-1); the top bucket 2^(c-1) is stored after the matrix
     s->nb_padded = s->nbuckets;
     const size_t m = (size_t)windows * n;
-    s->large_cap = (uint32_t)(m / LARGE_SLICE + 1);
+    // segments longer than max(8 * mean, 64 * lanes) are "large": at most nbuckets / 8 of them can exist
+    s->large_cap = s->nbuckets / 8 + 2;
     s->max_slices = (uint32_t)(m / LARGE_SLICE + s->large_cap);
 
     size_t total = 0;
@@ -578,6 +570,7 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     const size_t o_tables = take(sizeof(affine) * m);
     const size_t o_keys_a = take(4 * m), o_keys_b = take(4 * m), o_vals_a = take(4 * m), o_vals_b = take(4 * m);
     const size_t o_offsets = take(4 * ((size_t)s->nbuckets + 1));
+    const size_t o_ord = take(4 * 4 * (size_t)s->nbuckets);
     const size_t o_large = take(4 * ((size_t)s->large_cap + 1));
     const size_t o_slice_start = take(4 * ((size_t)s->large_cap + 1));
     const size_t o_slice_sums = take(sizeof(xyzz) * s->max_slices);
@@ -588,6 +581,9 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
     s->cub_temp_bytes = 0;
     UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_temp_bytes, dk, dv, (int)m, 0, (int)c, st));
+    size_t ord_temp = 0;
+    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, ord_temp, dk, dv, (int)s->nbuckets, 0, 32, st));
+    if (ord_temp > s->cub_temp_bytes) s->cub_temp_bytes = ord_temp;
     const size_t o_cub = take(s->cub_temp_bytes + 256);
     UZ_CUDA_TRY(cudaMalloc(&s->arena, total));
     s->bytes = total;
@@ -598,6 +594,10 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     s->vals_a = (uint32_t*)(base + o_vals_a);
     s->vals_b = (uint32_t*)(base + o_vals_b);
     s->offsets = (uint32_t*)(base + o_offsets);
+    s->ord_keys_a = (uint32_t*)(base + o_ord);
+    s->ord_keys_b = s->ord_keys_a + s->nbuckets;
+    s->ord_vals_a = s->ord_keys_b + s->nbuckets;
+    s->ord_vals_b = s->ord_vals_a + s->nbuckets;
     s->large_list = (uint32_t*)(base + o_large);
     s->slice_start = (uint32_t*)(base + o_slice_start);
     s->slice_sums = (xyzz*)(base + o_slice_sums);
@@ -693,23 +693,39 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     msm_offsets_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(keys, m, s->nbuckets, s->offsets);
     UZ_CUDA_TRY(cudaGetLastError());
     UZ_CUDA_TRY(cudaMemsetAsync(s->large_list, 0, 4, st));
-    g_prof.mark(prof, MSM_PH_OFFSETS, st);
 
-    // lanes per bucket: aim at ~48 entries per lane
+    // lanes per bucket: ~48 entries per lane, but at least enough groups to fill every SM
     const double mean = (double)m / (double)(s->nbuckets - 1);
     uint32_t g = 1;
     while (g < 32 && mean / (g * 2) >= 40.0) g *= 2;
+    while (g < 32 && (uint64_t)s->nbuckets * g * 2 <= (uint64_t)sm_count_ * 512) g *= 2;
     if (force_lanes_) g = force_lanes_;
+    // segments above the threshold are split into CTA slices (msm_large_*)
+    uint32_t thr = (uint32_t)(mean * 8.0);
+    {
+        uint32_t per_lane = (uint32_t)(m / (2ull * sm_count_ * 512));
+        if (per_lane < 64) per_lane = 64;
+        if (thr < per_lane * g) thr = per_lane * g;
+    }
+
+    uint32_t cap_bits = 1;
+    while ((1u << cap_bits) <= thr + 1) cap_bits++;
+    msm_sizes_kernel<<<(s->nbuckets + 255) / 256, 256, 0, st>>>(s->offsets, s->nbuckets, thr + 1, s->ord_keys_a, s->ord_vals_a);
+    UZ_CUDA_TRY(cudaGetLastError());
+    cub::DoubleBuffer<uint32_t> ok(s->ord_keys_a, s->ord_keys_b), ov(s->ord_vals_a, s->ord_vals_b);
+    temp = s->cub_temp_bytes;
+    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_temp, temp, ok, ov, (int)s->nbuckets, 0, (int)cap_bits, st));
+    g_prof.mark(prof, MSM_PH_OFFSETS, st);
+
     AccArgs aa;
     aa.tables = s->tables;
     aa.vals = vals;
     aa.offsets = s->offsets;
+    aa.order = ov.Current();
     aa.buckets = s->buckets;
     aa.nbuckets = s->nbuckets;
     aa.nb_padded = s->nb_padded;
-    uint32_t thr = (uint32_t)(mean * 8.0);
-    const uint32_t thr_min = 128 * g < LARGE_SLICE ? LARGE_SLICE : 128 * g;
-    aa.large_threshold = thr < thr_min ? thr_min : thr;
+    aa.large_threshold = thr;
     aa.large_list = s->large_list;
     aa.large_cap = s->large_cap;
     cudaError_t e;
@@ -735,10 +751,11 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     la.large_cap = s->large_cap;
     la.max_slices = s->max_slices;
     // upper bounds for this m (the kernels read the real counts on the device; surplus CTAs exit at once)
-    const uint32_t cap_now = (uint32_t)(m / aa.large_threshold + 1);
+    uint32_t cap_now = (uint32_t)(m / aa.large_threshold + 1);
+    if (cap_now > s->large_cap) cap_now = s->large_cap;
     const uint32_t slices_now = m / LARGE_SLICE + cap_now;
     msm_large_plan_kernel<<<1, 1024, 0, st>>>(la);
-    msm_large_accumulate_kernel<<<slices_now, LARGE_NT, 2 * 4 * LARGE_NT * sizeof(uint4), st>>>(la);
+    msm_large_accumulate_kernel<<<(slices_now + LARGE_NT / 32 - 1) / (LARGE_NT / 32), LARGE_NT, 2 * 4 * LARGE_NT * sizeof(uint4), st>>>(la);
     msm_large_finish_kernel<<<cap_now, 32, 0, st>>>(la);
     UZ_CUDA_TRY(cudaGetLastError());
     g_prof.mark(prof, MSM_PH_LARGE, st);
@@ -762,7 +779,7 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     msm_final_kernel<<<3, FIN_NT, 0, st>>>(fa);
     UZ_CUDA_TRY(cudaGetLastError());
     g_prof.mark(prof, MSM_PH_REDUCE, st);
-    UZ_COUNT_LAUNCH(8 + 3);  // own kernels + CUB's radix-sort launches (histogram, scan, onesweep passes: >= 3)
+    UZ_COUNT_LAUNCH(9 + 3 + 3);  // own kernels + CUB's radix-sort launches (histogram, scan, onesweep passes: >= 3 per sort)
     return UZKGE_OK;
 }
 
