@@ -95,6 +95,14 @@ UZKGE_API int32_t uzkge_cuda_msm_g1_device(uint64_t handle, size_t base_offset, 
 UZKGE_API int32_t uzkge_cuda_ntt_fr_device(const void* d_in, void* d_out, void* d_scratch, size_t len_in, size_t domain_size,
                                  int32_t inverse, const uint64_t* coset_shift_host, void* stream);
 
+/* Cross-GPU step of a distributed transform of size n_total = G * L over G = 2^log_ranks ranks (four-step NTT, SURVEY 8e:
+ * "NTTs of size 2^22 and above use a four-step transpose over NVLink with NCCL all-to-all").  d_in holds G rows of
+ * `cols` elements: row n1 = the columns [col_offset, col_offset + cols) of rank n1's contiguous slice (what the first
+ * all-to-all delivers).  d_out row k1 = w^(n2 * k1) * sum_n1 in[n1][.] * w_G^(n1 * k1): it travels to rank k1 (second
+ * all-to-all), which then runs the size-L transform with uzkge_cuda_ntt_fr_device.  uzkge_b200/dist.py drives it. */
+UZKGE_API int32_t uzkge_cuda_ntt_cross_fr_device(const void* d_in, void* d_out, uint32_t log_ranks, size_t cols, size_t col_offset,
+                                                 size_t n_total, int32_t inverse, void* stream);
+
 /* ---- small group helpers (combine per-GPU partial MSMs; blinds) --------------------------------------
  * out = a + b on Jacobian points (host pointers, tiny device kernel).  Used for the G - 1 projective adds
  * that merge per-GPU partial sums. */

@@ -36,7 +36,10 @@ if what in ("ntt", "all"):
 
 if what in ("msm", "all"):
     tau = B.random_fr(1, 5)[0]
-    for lg, cs in ((14, (0, 11, 12, 13, 14)), (16, (0, 13, 15)), (20, (0, 16, 17, 19, 20)), (22, (0,))):
+    cfgs = ((14, (0, 11, 12, 13, 14)), (16, (0, 13, 15)), (20, (0, 16, 17, 19, 20)), (22, (0,)))
+    if "quick" in sys.argv:
+        cfgs = ((14, (13,)), (16, (15,)), (20, (17, 20)), (22, (20,)))
+    for lg, cs in cfgs:
         n = 1 << lg
         bases = ffi.srs_generate(tau, n)
         sc = torch.from_numpy(B.random_fr(n, 2).view(np.int64)).to(dev)
@@ -44,7 +47,9 @@ if what in ("msm", "all"):
         for c in cs:
             h = ffi.srs_upload(bases, c)
             info = ffi.srs_info(h)
-            for lanes in ((0,) if lg >= 20 and c not in (0,17) else (0, 1, 2, 4, 8, 16, 32)):
+            for lanes in ((0, -1) if "quick" in sys.argv else (0,) if lg >= 20 and c not in (0,17) else (0, 1, 2, 4, 8, 16, 32)):
+                ffi.configure("msm_counting_sort", 0 if lanes < 0 else 1)
+                if lanes < 0: lanes = 0
                 ffi.configure("msm_lanes", lanes)
                 ms = timeit(lambda: ffi.msm_g1_device(h, sc.data_ptr(), n, out.data_ptr()), 5, 2)
                 ffi.profile_enable(True); timeit(lambda: ffi.msm_g1_device(h, sc.data_ptr(), n, out.data_ptr()), 3, 0); p = ffi.profile_read("msm"); ffi.profile_enable(False)

@@ -47,7 +47,44 @@ def _worker(rank, world, port, n, q):
         short = sc[:3]
         got3 = udist.msm_sharded(srs, short, msm_fn=lambda h, s: oc.msm_g1(store[h][: s.shape[0]], s), add_fn=oc.g1_add_jac)
         ok3 = np.array_equal(oc.g1_to_affine(got3), oc.g1_to_affine(oc.msm_g1(pts[:3], short)))
-        q.put((rank, ok1, ok2, ok3))
+        # distributed NTT: the exchange pattern with the compute steps injected (numpy + oracle on CPU tensors)
+        import torch
+
+        class CpuOps:
+            def empty_like(self, t):
+                return torch.empty_like(t)
+
+            def cross(self, t_in, log_g, cols, col_offset, n_total, inverse):
+                g = 1 << log_g
+                a = t_in.numpy().view(np.uint64).reshape(g, cols, 4)
+                w = oc.fr_root_of_unity(n_total)
+                if inverse:
+                    w = oc.fr_inv(w)
+                out = np.zeros_like(a)
+                for t in range(cols):
+                    col = np.ascontiguousarray(a[:, t, :])
+                    y = oc.ntt_fr(col, g, inverse=inverse)  # G-point transform (inverse includes 1/G)
+                    for k1 in range(g):
+                        tw = oc.fr_pow(w, ((col_offset + t) * k1) % n_total)
+                        out[k1, t] = oc.fr_mul(y[k1 : k1 + 1], tw.reshape(1, 4))[0]
+                return torch.from_numpy(out.view(np.int64).reshape(-1))
+
+            def local_ntt(self, t_in, n, inverse):
+                a = t_in.numpy().view(np.uint64).reshape(n, 4)
+                return torch.from_numpy(oc.ntt_fr(a, n, inverse=inverse).view(np.int64).reshape(-1))
+
+        nt = 64
+        L = nt // world
+        x = oc.random_fr(nt, 99)
+        mine = torch.from_numpy(np.ascontiguousarray(x[rank * L : (rank + 1) * L]).view(np.int64).reshape(-1))
+        y = udist.ntt_fr_distributed(mine, nt, rank, world, ops=CpuOps())
+        want = oc.ntt_fr(x, nt)
+        ok4 = np.array_equal(y.numpy().view(np.uint64).reshape(L, 4), want[rank * L : (rank + 1) * L])
+        yc = udist.ntt_fr_distributed(mine, nt, rank, world, natural_output=False, ops=CpuOps())
+        ok4 = ok4 and np.array_equal(yc.numpy().view(np.uint64).reshape(L, 4), want[rank::world])
+        back = udist.ntt_fr_distributed(y, nt, rank, world, inverse=True, ops=CpuOps())
+        ok4 = ok4 and np.array_equal(back.numpy().view(np.uint64).reshape(L, 4), x[rank * L : (rank + 1) * L])
+        q.put((rank, ok1, ok2, ok3 and ok4))
     finally:
         dist.destroy_process_group()
 

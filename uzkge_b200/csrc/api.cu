@@ -327,6 +327,14 @@ UZKGE_API int32_t uzkge_cuda_ntt_fr_device(const void* d_in, void* d_out, void* 
     return engine_fail(rc, "ntt_fr_device");
 }
 
+UZKGE_API int32_t uzkge_cuda_ntt_cross_fr_device(const void* d_in, void* d_out, uint32_t log_ranks, size_t cols, size_t col_offset,
+                                                 size_t n_total, int32_t inverse, void* stream) {
+    if (!d_in || !d_out || d_in == d_out) return fail(UZKGE_ERR_ARG, "ntt_cross_fr_device: null or aliasing pointers");
+    API_ENTER(-1);
+    int rc = g.ntt->cross((const fe*)d_in, (fe*)d_out, log_ranks, cols, col_offset, n_total, inverse != 0, (cudaStream_t)stream);
+    return engine_fail(rc, "ntt_cross_fr_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]) {
     if (!out) return fail(UZKGE_ERR_ARG, "fr_root_of_unity: null pointer");
     bool ok = false;
@@ -443,6 +451,12 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
         int rc = ensure_init(-1);
         if (rc != UZKGE_OK) return rc;
         g.msm->force_lanes((uint32_t)value);
+        return UZKGE_OK;
+    }
+    if (k == "msm_counting_sort") {
+        int rc = ensure_init(-1);
+        if (rc != UZKGE_OK) return rc;
+        g.msm->counting_sort(value != 0);
         return UZKGE_OK;
     }
     if (k == "ntt_big_threads") {

@@ -111,6 +111,9 @@ public:
     }
     int run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, uint64_t n, bool inverse, const fe* coset_shift,
             cudaStream_t st);
+    // cross-rank step of a distributed transform (see ntt.cu)
+    int cross(const fe* d_in, fe* d_out, uint32_t log_g, uint64_t cols, uint64_t col_offset, uint64_t n_total, bool inverse,
+              cudaStream_t st);
 
 private:
     const NttDomain* domain(uint64_t n, cudaStream_t st);
@@ -137,6 +140,7 @@ struct MsmSrs {
     // workspace, sized for an MSM over the whole SRS
     uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
     uint32_t* offsets = nullptr;      // nbuckets + 1
+    uint32_t* counts = nullptr;       // nbuckets + 1 (counting sort)
     uint32_t *ord_keys_a = nullptr, *ord_keys_b = nullptr, *ord_vals_a = nullptr, *ord_vals_b = nullptr;  // size-ordered bucket ids
     uint32_t* large_list = nullptr;   // [0] = count, then bucket ids
     uint32_t* slice_start = nullptr;  // prefix of CTA slices per oversized bucket
@@ -160,10 +164,12 @@ public:
     int g1_to_affine(const jacobian* d_in, affine* d_out, cudaStream_t st);
     int powers_of_tau(const fe& tau, uint64_t first, uint32_t count, affine* d_out, cudaStream_t st);
     void force_lanes(uint32_t g) { force_lanes_ = g; }  // tuning knob (0 = automatic)
+    void counting_sort(bool on) { counting_sort_ = on; }
 
 private:
     int sm_count_;
     uint32_t force_lanes_ = 0;
+    bool counting_sort_ = true;
 };
 
 static inline int cuda_err_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? UZKGE_ERR_OOM : UZKGE_ERR_CUDA; }

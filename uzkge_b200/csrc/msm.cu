@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "devmem.cuh"
 #include "ec_compact.cuh"
@@ -66,6 +67,39 @@ __global__ void __launch_bounds__(256) msm_recode_kernel(const RecodeArgs a) {
         const size_t o = (size_t)f * a.n + i;
         a.keys[o] = d;
         a.vals[o] = (f * a.table_stride + point) | neg;
+    }
+}
+
+// ---- counting sort by bucket (alternative to the radix sort; zero digits are dropped, order inside a bucket is
+// arbitrary).  Pass 1 counts, a scan turns counts into offsets, pass 2 recomputes the digits and scatters.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) msm_count_scatter_kernel(const RecodeArgs a, uint32_t* __restrict__ counts,
+                                                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted_vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    fe s = fe_from_mont<FrP>(ld_fe(a.scalars + i));
+    const uint32_t c = a.c, mask = (1u << c) - 1, half = 1u << (c - 1);
+    uint32_t carry = 0;
+    const uint32_t point = a.base_offset + i;
+    for (uint32_t f = 0; f < a.windows; f++) {
+        uint32_t d = (s.l[0] & mask) + carry;
+#pragma unroll
+        for (int k = 0; k < 7; k++) s.l[k] = __funnelshift_r(s.l[k], s.l[k + 1], c);
+        s.l[7] >>= c;
+        uint32_t neg = 0;
+        carry = 0;
+        if (d > half) {
+            d = (1u << c) - d;
+            neg = 0x80000000u;
+            carry = 1;
+        }
+        if (d == 0) continue;
+        if (SCATTER) {
+            const uint32_t pos = offsets[d] + atomicAdd(counts + d, 1u);
+            sorted_vals[pos] = (f * a.table_stride + point) | neg;
+        } else {
+            atomicAdd(counts + d, 1u);
+        }
     }
 }
 
@@ -571,6 +605,7 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     const size_t o_keys_a = take(4 * m), o_keys_b = take(4 * m), o_vals_a = take(4 * m), o_vals_b = take(4 * m);
     const size_t o_offsets = take(4 * ((size_t)s->nbuckets + 1));
     const size_t o_ord = take(4 * 4 * (size_t)s->nbuckets);
+    const size_t o_counts = take(4 * ((size_t)s->nbuckets + 1));
     const size_t o_large = take(4 * ((size_t)s->large_cap + 1));
     const size_t o_slice_start = take(4 * ((size_t)s->large_cap + 1));
     const size_t o_slice_sums = take(sizeof(xyzz) * s->max_slices);
@@ -584,6 +619,9 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     size_t ord_temp = 0;
     UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, ord_temp, dk, dv, (int)s->nbuckets, 0, 32, st));
     if (ord_temp > s->cub_temp_bytes) s->cub_temp_bytes = ord_temp;
+    size_t scan_temp = 0;
+    UZ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)s->nbuckets + 1, st));
+    if (scan_temp > s->cub_temp_bytes) s->cub_temp_bytes = scan_temp;
     const size_t o_cub = take(s->cub_temp_bytes + 256);
     UZ_CUDA_TRY(cudaMalloc(&s->arena, total));
     s->bytes = total;
@@ -594,6 +632,7 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     s->vals_a = (uint32_t*)(base + o_vals_a);
     s->vals_b = (uint32_t*)(base + o_vals_b);
     s->offsets = (uint32_t*)(base + o_offsets);
+    s->counts = (uint32_t*)(base + o_counts);
     s->ord_keys_a = (uint32_t*)(base + o_ord);
     s->ord_keys_b = s->ord_keys_a + s->nbuckets;
     s->ord_vals_a = s->ord_keys_b + s->nbuckets;
@@ -679,19 +718,37 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     ra.base_offset = (uint32_t)base_offset;
     ra.keys = s->keys_a;
     ra.vals = s->vals_a;
-    msm_recode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ra);
-    UZ_CUDA_TRY(cudaGetLastError());
-    g_prof.mark(prof, MSM_PH_RECODE, st);
+    const uint32_t* vals;
+    size_t temp;
+    if (counting_sort_) {
+        // count -> scan -> scatter: 2 x N*W global atomics instead of 3 radix passes over N*W pairs
+        const size_t cbytes = 4 * ((size_t)s->nbuckets + 1);
+        UZ_CUDA_TRY(cudaMemsetAsync(s->counts, 0, cbytes, st));
+        msm_count_scatter_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ra, s->counts, nullptr, nullptr);
+        UZ_CUDA_TRY(cudaGetLastError());
+        g_prof.mark(prof, MSM_PH_RECODE, st);
+        temp = s->cub_temp_bytes;
+        UZ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->cub_temp, temp, s->counts, s->offsets, (int)s->nbuckets + 1, st));
+        UZ_CUDA_TRY(cudaMemsetAsync(s->counts, 0, cbytes, st));
+        msm_count_scatter_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ra, s->counts, s->offsets, s->vals_b);
+        UZ_CUDA_TRY(cudaGetLastError());
+        vals = s->vals_b;
+        g_prof.mark(prof, MSM_PH_SORT, st);
+    } else {
+        msm_recode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ra);
+        UZ_CUDA_TRY(cudaGetLastError());
+        g_prof.mark(prof, MSM_PH_RECODE, st);
 
-    cub::DoubleBuffer<uint32_t> dk(s->keys_a, s->keys_b), dv(s->vals_a, s->vals_b);
-    size_t temp = s->cub_temp_bytes;
-    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_temp, temp, dk, dv, (int)m, 0, (int)s->c, st));
-    const uint32_t* keys = dk.Current();
-    const uint32_t* vals = dv.Current();
-    g_prof.mark(prof, MSM_PH_SORT, st);
+        cub::DoubleBuffer<uint32_t> dk(s->keys_a, s->keys_b), dv(s->vals_a, s->vals_b);
+        temp = s->cub_temp_bytes;
+        UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_temp, temp, dk, dv, (int)m, 0, (int)s->c, st));
+        const uint32_t* keys = dk.Current();
+        vals = dv.Current();
+        g_prof.mark(prof, MSM_PH_SORT, st);
 
-    msm_offsets_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(keys, m, s->nbuckets, s->offsets);
-    UZ_CUDA_TRY(cudaGetLastError());
+        msm_offsets_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(keys, m, s->nbuckets, s->offsets);
+        UZ_CUDA_TRY(cudaGetLastError());
+    }
     UZ_CUDA_TRY(cudaMemsetAsync(s->large_list, 0, 4, st));
 
     // lanes per bucket: ~48 entries per lane, but at least enough groups to fill every SM

@@ -175,6 +175,60 @@ __global__ void __launch_bounds__(256) ntt_radix3_kernel(const Radix3Args a) {
     st_fe(a.out + 2 * a.m + n, y2);
 }
 
+// ---- cross-GPU step of a distributed transform of size N = G * L (G = 2, 4, 8 ranks, L = N / G per rank).
+// After the first all-to-all a rank holds, for its `cols` columns n2 = col_offset + t, the G elements
+// x[n1 * L + n2] (row n1 came from rank n1).  This kernel does the G-point transforms over n1 in registers and
+// applies the four-step twiddle:   out[k1][t] = w_N^(n2 * k1) * sum_{n1} in[n1][t] * w_G^(n1 * k1)
+// (inverse: conjugate roots and a factor 1/G).  Row k1 then travels to rank k1, which runs the size-L transform.
+struct CrossArgs {
+    const fe* in;
+    fe* out;
+    uint64_t cols, col_offset, n_total;
+    const fe* w_lo;   // power table of w_N
+    const fe* w_hi;
+    fe wg[4];         // w_G^j (conjugated for the inverse), j < G / 2
+    fe scale;         // 1 / G
+    uint32_t inverse;
+};
+template <int LOGG>
+__global__ void __launch_bounds__(128) ntt_cross_kernel(const CrossArgs a) {
+    constexpr int G = 1 << LOGG;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.cols) return;
+    fe x[G];
+#pragma unroll
+    for (int i = 0; i < G; i++) x[i] = ld_fe(a.in + (uint64_t)i * a.cols + t);
+#pragma unroll
+    for (int s = LOGG - 1; s >= 0; s--) {
+        const int h = 1 << s;
+#pragma unroll
+        for (int pr = 0; pr < G / 2; pr++) {
+            const int j = pr & (h - 1);
+            const int r = ((pr >> s) << (s + 1)) | j;
+            const fe u = x[r], v = x[r + h];
+            fe d = fe_sub<FrP>(u, v);
+            if (j) d = fe_mul<FrP>(d, a.wg[j << (LOGG - 1 - s)]);
+            x[r] = fe_add<FrP>(u, v);
+            x[r + h] = d;
+        }
+    }
+    const uint64_t c = a.col_offset + t;
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+        int br = 0;
+#pragma unroll
+        for (int b = 0; b < LOGG; b++) br |= ((k >> b) & 1) << (LOGG - 1 - b);
+        fe y = x[br];
+        uint64_t e = (c * (uint64_t)k) % a.n_total;
+        if (a.inverse) {
+            if (e) e = a.n_total - e;
+            y = fe_mul<FrP>(y, a.scale);
+        }
+        if (e) y = fe_mul<FrP>(y, pow2l(a.w_lo, a.w_hi, e));
+        st_fe(a.out + (uint64_t)k * a.cols + t, y);
+    }
+}
+
 // lo[i] = premul * base^i (i < 2^12);  hi[i] = base^(i << 12) (i < n_hi)
 __global__ void ntt_build_pow_tables(fe base, fe premul, fe* lo, fe* hi, uint32_t n_hi) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -348,6 +402,44 @@ int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, ui
         input_consumed = true;
     }
     return UZKGE_OK;
+}
+
+int NttEngine::cross(const fe* d_in, fe* d_out, uint32_t log_g, uint64_t cols, uint64_t col_offset, uint64_t n_total,
+                     bool inverse, cudaStream_t st) {
+    if (log_g < 1 || log_g > 3 || cols == 0 || (n_total >> log_g) == 0 || col_offset + cols > (n_total >> log_g))
+        return UZKGE_ERR_SIZE;
+    if (n_total & (n_total - 1)) return UZKGE_ERR_SIZE;
+    const NttDomain* d = domain(n_total, st);
+    if (!d) return UZKGE_ERR_SIZE;
+    CrossArgs ca;
+    ca.in = d_in;
+    ca.out = d_out;
+    ca.cols = cols;
+    ca.col_offset = col_offset;
+    ca.n_total = n_total;
+    ca.w_lo = d->w_lo;
+    ca.w_hi = d->w_hi;
+    ca.inverse = inverse ? 1 : 0;
+    const uint32_t g = 1u << log_g;
+    fe wg = host_pow(d->omega, n_total >> log_g);
+    if (inverse) wg = fe_inv<FrP>(wg);
+    fe acc = fe_one<FrP>();
+    for (uint32_t j = 0; j < 4; j++) {
+        ca.wg[j] = acc;
+        acc = fe_mul<FrP>(acc, wg);
+    }
+    fe gf = fe_zero();
+    gf.l[0] = g;
+    ca.scale = fe_inv<FrP>(fe_to_mont<FrP>(gf));
+    const unsigned grid = (unsigned)((cols + 127) / 128);
+    if (log_g == 1)
+        ntt_cross_kernel<1><<<grid, 128, 0, st>>>(ca);
+    else if (log_g == 2)
+        ntt_cross_kernel<2><<<grid, 128, 0, st>>>(ca);
+    else
+        ntt_cross_kernel<3><<<grid, 128, 0, st>>>(ca);
+    UZ_COUNT_LAUNCH(1);
+    return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
 }
 
 NttEngine::~NttEngine() {

@@ -89,3 +89,90 @@ def commit_distributed(polys: Sequence[np.ndarray], rank: int, world: int, commi
     for j in range(k):
         out[j] = allp[j % world, j // world]
     return out
+
+
+# ------------------------------------------------------------------------------------------------ distributed NTT
+# Four-step transform of size N = G * L over G ranks: rank r owns the contiguous slice
+# x[r*L : (r+1)*L] (n = n1*L + n2 with n1 = r).
+#   1. all-to-all: column block j (n2 in [j*S, (j+1)*S), S = L / G) of every rank goes to rank j
+#   2. cross kernel (uzkge_cuda_ntt_cross_fr_device): G-point transforms over n1 + twiddle w_N^(n2*k1)
+#   3. all-to-all: row k1 goes to rank k1, which now holds B[k1][n2], n2 = 0..L-1
+#   4. local size-L transform (uzkge_cuda_ntt_fr_device) -> X[k1 + G*k2], k2 = 0..L-1   ("cyclic" layout)
+#   5. optional all-to-all + local interleave -> natural contiguous slices X[r*L : (r+1)*L]
+# The inverse runs the same steps with conjugate roots and the 1/N factor split as 1/G (cross) * 1/L (local).
+
+
+class CudaNttOps:
+    """The compute steps on torch CUDA tensors (int64 views of (n, 4) uint64 limbs) through the device ABI."""
+
+    def __init__(self, stream: int = 0):
+        self.stream = stream
+
+    def empty_like(self, t):
+        import torch
+
+        return torch.empty_like(t)
+
+    def cross(self, t_in, log_g: int, cols: int, col_offset: int, n_total: int, inverse: bool):
+        out = self.empty_like(t_in)
+        ffi.ntt_cross_fr_device(t_in.data_ptr(), out.data_ptr(), log_g, cols, col_offset, n_total, inverse, self.stream)
+        return out
+
+    def local_ntt(self, t_in, n: int, inverse: bool):
+        out, scratch = self.empty_like(t_in), self.empty_like(t_in)
+        ffi.ntt_fr_device(t_in.data_ptr(), out.data_ptr(), scratch.data_ptr(), n, n, inverse, None, self.stream)
+        return out
+
+
+def _check_dist_sizes(n_total: int, world: int):
+    if world not in (2, 4, 8):
+        raise ValueError("distributed NTT supports 2, 4 or 8 ranks")
+    if n_total & (n_total - 1) or n_total < world * world:
+        raise ValueError("distributed NTT needs a power-of-two size >= world^2")
+    L = n_total // world
+    return L, L // world, world.bit_length() - 1
+
+
+def ntt_fr_distributed(x_local, n_total: int, rank: int, world: int, inverse: bool = False, natural_output: bool = True,
+                       group=None, ops=None):
+    """x_local: this rank's contiguous slice as a flat int64 torch tensor of 4 * L words.  Returns the rank's slice of the
+    transform: natural contiguous (default) or cyclic (X[rank + world * k2]) when natural_output is False."""
+    import torch.distributed as dist
+
+    ops = ops or CudaNttOps()
+    L, S, log_g = _check_dist_sizes(n_total, world)
+    assert x_local.numel() == 4 * L
+    recv = ops.empty_like(x_local)
+    dist.all_to_all_single(recv, x_local.contiguous(), group=group)                    # 1
+    crossed = ops.cross(recv, log_g, S, rank * S, n_total, inverse)                    # 2
+    rows = ops.empty_like(crossed)
+    dist.all_to_all_single(rows, crossed, group=group)                                 # 3
+    y = ops.local_ntt(rows, L, inverse)                                                # 4
+    if not natural_output:
+        return y
+    back = ops.empty_like(y)
+    dist.all_to_all_single(back, y, group=group)                                       # 5
+    return back.view(world, S, 4).permute(1, 0, 2).contiguous().view(-1)
+
+
+def ntt_fr_distributed_emulated(xs, n_total: int, inverse: bool = False, natural_output: bool = True, ops=None):
+    """The same steps with all `world` ranks' slices held by ONE process (list of tensors) and the all-to-alls done by
+    indexing: runs the multi-rank path on a single GPU (tests) -- no collective, no waiting kernels."""
+    import torch
+
+    ops = ops or CudaNttOps()
+    world = len(xs)
+    L, S, log_g = _check_dist_sizes(n_total, world)
+
+    def all_to_all(ts):
+        views = [t.view(world, S * 4) for t in ts]
+        return [torch.cat([views[src][dst] for src in range(world)]).contiguous() for dst in range(world)]
+
+    recv = all_to_all(xs)
+    crossed = [ops.cross(recv[r], log_g, S, r * S, n_total, inverse) for r in range(world)]
+    rows = all_to_all(crossed)
+    ys = [ops.local_ntt(rows[r], L, inverse) for r in range(world)]
+    if not natural_output:
+        return ys
+    back = all_to_all(ys)
+    return [b.view(world, S, 4).permute(1, 0, 2).contiguous().view(-1) for b in back]

@@ -48,6 +48,10 @@ _SIGNATURES = {
         C.c_int32,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p],
     ),
+    "uzkge_cuda_ntt_cross_fr_device": (
+        C.c_int32,
+        [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p],
+    ),
     "uzkge_cuda_g1_add": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_g1_to_affine": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "uzkge_cuda_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -243,6 +247,12 @@ def ntt_fr_device(d_in: int, d_out: int, d_scratch: int, len_in: int, domain_siz
                                        ptr(shift) if shift is not None else None, stream),
         FFTError,
     )
+
+
+def ntt_cross_fr_device(d_in: int, d_out: int, log_ranks: int, cols: int, col_offset: int, n_total: int,
+                        inverse: bool = False, stream: int = 0) -> None:
+    check(lib().uzkge_cuda_ntt_cross_fr_device(d_in, d_out, log_ranks, cols, col_offset, n_total, 1 if inverse else 0, stream),
+          FFTError)
 
 
 def g1_add(a_jac, b_jac) -> np.ndarray:
