@@ -37,7 +37,9 @@ if what in ("ntt", "all"):
 if what in ("msm", "all"):
     tau = B.random_fr(1, 5)[0]
     cfgs = ((14, (0, 11, 12, 13, 14)), (16, (0, 13, 15)), (20, (0, 16, 17, 19, 20)), (22, (0,)))
-    if "quick" in sys.argv:
+    if "csweep" in sys.argv:
+        cfgs = ((12, (9, 10, 11, 12)), (14, (11, 12, 13, 14)), (16, (13, 14, 15, 16)), (18, (15, 16, 17, 18)), (20, (17, 18, 19, 20, 21)), (22, (19, 20, 21, 22)), (24, (21, 22, 23)))
+    elif "quick" in sys.argv:
         cfgs = ((14, (13,)), (16, (15,)), (20, (17, 20)), (22, (20,)))
     for lg, cs in cfgs:
         n = 1 << lg
@@ -47,7 +49,7 @@ if what in ("msm", "all"):
         for c in cs:
             h = ffi.srs_upload(bases, c)
             info = ffi.srs_info(h)
-            for lanes in ((0, -1) if "quick" in sys.argv else (0,) if lg >= 20 and c not in (0,17) else (0, 1, 2, 4, 8, 16, 32)):
+            for lanes in ((0,) if "csweep" in sys.argv else (0, -1) if "quick" in sys.argv else (0,) if lg >= 20 and c not in (0,17) else (0, 1, 2, 4, 8, 16, 32)):
                 ffi.configure("msm_counting_sort", 0 if lanes < 0 else 1)
                 if lanes < 0: lanes = 0
                 ffi.configure("msm_lanes", lanes)

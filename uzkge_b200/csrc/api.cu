@@ -58,7 +58,7 @@ struct State {
     std::map<uint64_t, MsmSrs> srs;
     uint64_t next_handle = 1;
     DevBuf data, scratch, scalars, small;
-    uint32_t ntt_log_tile = 12, ntt_max_log_r = 11, ntt_two_pass_max = 22;
+    uint32_t ntt_log_tile = 10, ntt_max_log_r = 10, ntt_two_pass_max = 18;  // measured best on B200 (scripts/gpu_ntt_cfg.py)
 };
 State g;
 

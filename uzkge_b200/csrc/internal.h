@@ -121,10 +121,11 @@ private:
     std::map<uint64_t, NttDomain> domains_;
     std::vector<NttCoset> cosets_;
     int sm_count_;
-    uint32_t cfg_log_tile_ = 12, cfg_max_log_r_ = 11, cfg_two_pass_max_ = 22, cfg_big_threads_ = 1024;
+    uint32_t cfg_log_tile_ = 10, cfg_max_log_r_ = 10, cfg_two_pass_max_ = 18, cfg_big_threads_ = 1024;
 };
 
 // ---------------------------------------------------------------- MSM
+struct ReducePlan;
 struct MsmSrs {
     uint64_t n = 0;            // points
     uint32_t c = 0;            // window bits
@@ -146,12 +147,17 @@ struct MsmSrs {
     uint32_t* slice_start = nullptr;  // prefix of CTA slices per oversized bucket
     xyzz* slice_sums = nullptr;
     xyzz* buckets = nullptr;          // nb_padded
-    xyzz* marg = nullptr;             // rows + cols marginal sums
-    xyzz* partial = nullptr;          // 2
     uint32_t* ticket = nullptr;
+    struct ReducePlan* reduce = nullptr;  // launch plan of the bucket reduction (msm_reduce.cu)
     void* cub_temp = nullptr;
     size_t cub_temp_bytes = 0;
 };
+
+// bucket reduction (msm_reduce.cu): workspace size for window size c, plan over fixed buffers, run
+size_t msm_reduce_workspace_bytes(uint32_t c);
+ReducePlan* msm_reduce_plan_create(uint32_t c, xyzz* buckets, void* workspace, uint32_t* ticket);
+void msm_reduce_plan_destroy(ReducePlan* p);
+int msm_reduce_run(const ReducePlan* p, jacobian* d_out, cudaStream_t st);
 
 class MsmEngine {
 public:

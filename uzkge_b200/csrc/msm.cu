@@ -13,10 +13,9 @@
 //              with cp.async through per-thread shared-memory slots (double buffered), then a warp-shuffle
 //              reduction over the G lanes.  Buckets far above the mean (skewed witness scalars: 0/1/small
 //              values) go to a list handled by whole CTAs (slices of LARGE_SLICE entries).
-//   reduce   : sum_b b * B_b without a serial running sum: the buckets form a rows x cols matrix, b = hi*cols+lo;
-//              row sums R_hi and column sums C_lo are plain parallel sums, and
-//              sum_b b*B_b = cols * sum_hi hi*R_hi + sum_lo lo*C_lo, the two small weighted sums are done by
-//              suffix scans with warp shuffles.  No doubling ladder: the tables removed the window combine.
+//   reduce   : sum_b b * B_b (msm_reduce.cu): recursive row / column marginal sums of the bucket matrix, leaves
+//              finished by bit decomposition, additions split over teams of 4 lanes where parallelism is scarce.
+//              No doubling ladder over windows: the tables removed the window combine.
 #include <cuda_runtime.h>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -31,8 +30,6 @@ namespace uz {
 static constexpr int ACC_NT = 256;            // threads per CTA of the accumulate kernel
 static constexpr uint32_t LARGE_SLICE = 1024; // entries per warp slice of an oversized bucket
 static constexpr int LARGE_NT = 256;
-static constexpr int RED_NT = 128;            // marginal-sum CTAs: one warp per sum
-static constexpr int FIN_NT = 128;            // final weighted-sum CTAs: one warp per SM sub-partition
 
 // ------------------------------------------------------------------ recode
 struct RecodeArgs {
@@ -215,24 +212,6 @@ __global__ void __launch_bounds__(ACC_NT, 2) msm_accumulate_kernel(const AccArgs
     if (write && lane == 0) st_xyzz(a.buckets + b, acc);
 }
 
-// sum of the `acc` of all threads of the CTA, valid in thread 0.  scratch: (NT / 32) xyzz in shared memory.
-template <int NT>
-__device__ __forceinline__ void block_sum_xyzz(xyzz& acc, xyzz* scratch) {
-#pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t NW = NT / 32;
-    if (NW > 1) {
-        if (lane == 0) scratch[warp] = acc;
-        __syncthreads();
-        if (warp == 0) {
-            acc = (lane < NW) ? scratch[lane] : xyzz_identity();
-#pragma unroll 1
-            for (int off = NW >> 1; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
-        }
-    }
-}
-
 // ---- oversized buckets: plan (slices per bucket, prefix sum), accumulate per slice, finish per bucket
 struct LargeArgs {
     const affine* tables;
@@ -314,133 +293,6 @@ __global__ void __launch_bounds__(32) msm_large_finish_kernel(const LargeArgs a)
 #pragma unroll 1
     for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
     if (threadIdx.x == 0) st_xyzz(a.buckets + a.large_list[1 + k], acc);
-}
-
-// ------------------------------------------------------------------ reduce
-// sum_b b * B_b over the 2^(c-1) + 1 buckets.  Every sequential group operation of a warp costs >= 14 field
-// multiplications of fma-pipe time (~4 us) no matter how few lanes are active, so the reduction is organised
-// to minimise the number of DEPENDENT warp-level operations (about 35) rather than the amount of work:
-//   matrix  : b = hi * cols + lo for b < 2^(c-1); the top bucket 2^(c-1) is handled on its own
-//   marginals: R_hi = sum_lo B[hi][lo],  C_lo = sum_hi B[hi][lo]   -- one warp per sum, plain additions
-//   weighted : A = sum_hi hi R_hi,  B = sum_lo lo C_lo             -- suffix scans, no scalar multiplication
-//   result  = 2^logcols A + B + 2^(c-1) B_top
-struct MarginalArgs {
-    const xyzz* buckets;
-    xyzz* marg;  // rows + cols
-    uint32_t rows, cols;
-};
-// warp w of the grid: w < rows: R[w];  else C[w - rows]
-__global__ void __launch_bounds__(RED_NT) msm_marginals_kernel(const MarginalArgs a) {
-    const uint32_t o = blockIdx.x * (RED_NT / 32) + (threadIdx.x >> 5);
-    const uint32_t lane = threadIdx.x & 31;
-    if (o >= a.rows + a.cols) return;
-    const xyzz* base;
-    uint32_t count, stride;
-    if (o < a.rows) {
-        base = a.buckets + (size_t)o * a.cols;
-        count = a.cols;
-        stride = 1;
-    } else {
-        base = a.buckets + (o - a.rows);
-        count = a.rows;
-        stride = a.cols;
-    }
-    xyzz acc = xyzz_identity();
-#pragma unroll 1
-    for (uint32_t e = lane; e < count; e += 32) acc = xyzz_add_call(acc, ld_xyzz(base + (size_t)e * stride));
-#pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
-    if (lane == 0) st_xyzz(a.marg + o, acc);
-}
-
-// weighted sum sum_j j * X[j], j < m, by one CTA of FIN_NT threads; result in thread 0.
-//   thread t owns the 2^logq consecutive indices starting at t * 2^logq:  S_t = sum X, T_t = sum (j - start) X[j]
-//   P_t = sum_{u >= t} S_u (suffix scan: warp shuffles, then the warp totals)
-//   sum_j j X[j] = sum_t T_t + 2^logq * sum_{t >= 1} P_t
-__device__ __forceinline__ xyzz block_weighted_sum(const xyzz* X, uint32_t m, xyzz* sh) {
-    constexpr uint32_t NW = FIN_NT / 32;
-    uint32_t logq = 0;
-    while (((uint32_t)FIN_NT << logq) < m) logq++;
-    const uint32_t q = 1u << logq;
-    const uint32_t lo = min(threadIdx.x * q, m), hi = min(lo + q, m);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    xyzz P = xyzz_identity(), T = xyzz_identity();
-#pragma unroll 1
-    for (uint32_t j = hi; j > lo + 1; j--) {
-        P = xyzz_add_call(P, ld_xyzz(X + j - 1));
-        T = xyzz_add_call(T, P);
-    }
-    if (hi > lo) P = xyzz_add_call(P, ld_xyzz(X + lo));
-#pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
-        xyzz o = shfl_down_xyzz(P, off);
-        if (lane + off >= 32) o = xyzz_identity();
-        P = xyzz_add_call(P, o);
-    }
-    if (lane == 0) sh[warp] = P;
-    __syncthreads();
-    {   // suffix scan of the warp totals (every warp redundantly), then add the total of the warps above
-        xyzz w = lane < NW ? sh[lane] : xyzz_identity();
-#pragma unroll 1
-        for (int off = 1; off < (int)NW; off <<= 1) {
-            xyzz o = shfl_down_xyzz(w, off);
-            if (lane + off >= NW) o = xyzz_identity();
-            w = xyzz_add_call(w, o);
-        }
-        xyzz above = shfl_xyzz(w, (warp + 1) & 31);
-        if (warp + 1 >= NW) above = xyzz_identity();
-        P = xyzz_add_call(P, above);
-    }
-    if (threadIdx.x == 0) P = xyzz_identity();
-    for (uint32_t i = 0; i < logq; i++) P = xyzz_dbl_call(P);
-    P = xyzz_add_call(P, T);
-    __syncthreads();  // sh is reused by block_sum_xyzz
-    block_sum_xyzz<FIN_NT>(P, sh);
-    return P;
-}
-
-struct FinalArgs {
-    const xyzz* marg;    // rows + cols marginal sums
-    const xyzz* top;     // bucket 2^(c-1)
-    xyzz* partial;       // 3 entries
-    uint32_t* ticket;
-    jacobian* out;
-    uint32_t rows, cols, logcols, c;
-};
-// CTA 0: 2^logcols * sum_hi hi R[hi];  CTA 1: sum_lo lo C[lo];  CTA 2: 2^(c-1) * top;  the last one to finish adds them
-__global__ void __launch_bounds__(FIN_NT) msm_final_kernel(const FinalArgs a) {
-    __shared__ xyzz sh[FIN_NT / 32];
-    __shared__ uint32_t is_last;
-    xyzz r;
-    if (blockIdx.x == 0) {
-        r = block_weighted_sum(a.marg, a.rows, sh);
-        if (threadIdx.x == 0)
-            for (uint32_t i = 0; i < a.logcols; i++) r = xyzz_dbl_call(r);
-    } else if (blockIdx.x == 1) {
-        r = block_weighted_sum(a.marg + a.rows, a.cols, sh);
-    } else {
-        if (threadIdx.x == 0) {
-            r = ld_xyzz(a.top);
-            for (uint32_t i = 0; i + 1 < a.c; i++) r = xyzz_dbl_call(r);
-        }
-    }
-    if (threadIdx.x == 0) {
-        st_xyzz(a.partial + blockIdx.x, r);
-        __threadfence();
-        is_last = (atomicAdd(a.ticket, 1u) == 2u);
-    }
-    __syncthreads();
-    if (!is_last || threadIdx.x != 0) return;
-    __threadfence();
-    xyzz A = ld_xyzz(a.partial);
-    const xyzz B = ld_xyzz(a.partial + 1), C = ld_xyzz(a.partial + 2);
-    A = xyzz_add_call(A, B);
-    A = xyzz_add_call(A, C);
-    const jacobian j = xyzz_to_jacobian<FqCall>(A);
-    st_fe(&a.out->x, j.x);
-    st_fe(&a.out->y, j.y);
-    st_fe(&a.out->z, j.z);
-    *a.ticket = 0;
 }
 
 __global__ void msm_identity_kernel(jacobian* out) {
@@ -610,8 +462,9 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     const size_t o_slice_start = take(4 * ((size_t)s->large_cap + 1));
     const size_t o_slice_sums = take(sizeof(xyzz) * s->max_slices);
     const size_t o_buckets = take(sizeof(xyzz) * s->nb_padded);
-    const size_t o_marg = take(sizeof(xyzz) * ((size_t)s->rows + s->cols));
-    const size_t o_partial = take(sizeof(xyzz) * 4);
+    const size_t reduce_bytes = msm_reduce_workspace_bytes(c);
+    if (reduce_bytes == 0) return UZKGE_ERR_SIZE;
+    const size_t o_reduce = take(reduce_bytes);
     const size_t o_ticket = take(256);
     cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
     s->cub_temp_bytes = 0;
@@ -641,9 +494,9 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     s->slice_start = (uint32_t*)(base + o_slice_start);
     s->slice_sums = (xyzz*)(base + o_slice_sums);
     s->buckets = (xyzz*)(base + o_buckets);
-    s->marg = (xyzz*)(base + o_marg);
-    s->partial = (xyzz*)(base + o_partial);
     s->ticket = (uint32_t*)(base + o_ticket);
+    s->reduce = msm_reduce_plan_create(c, s->buckets, base + o_reduce, s->ticket);
+    if (!s->reduce) return UZKGE_ERR_INTERNAL;
     s->cub_temp = base + o_cub;
 
     cudaEvent_t e0, e1;
@@ -687,6 +540,7 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
 }
 
 void MsmEngine::release(MsmSrs* s) {
+    if (s->reduce) msm_reduce_plan_destroy(s->reduce);
     if (s->arena) cudaFree(s->arena);
     *s = MsmSrs();
 }
@@ -817,26 +671,12 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     UZ_CUDA_TRY(cudaGetLastError());
     g_prof.mark(prof, MSM_PH_LARGE, st);
 
-    MarginalArgs ma;
-    ma.buckets = s->buckets;
-    ma.marg = s->marg;
-    ma.rows = s->rows;
-    ma.cols = s->cols;
-    msm_marginals_kernel<<<(s->rows + s->cols + RED_NT / 32 - 1) / (RED_NT / 32), RED_NT, 0, st>>>(ma);
-    FinalArgs fa;
-    fa.marg = s->marg;
-    fa.top = s->buckets + (size_t)s->rows * s->cols;
-    fa.c = s->c;
-    fa.partial = s->partial;
-    fa.ticket = s->ticket;
-    fa.out = d_out;
-    fa.rows = s->rows;
-    fa.cols = s->cols;
-    fa.logcols = s->logcols;
-    msm_final_kernel<<<3, FIN_NT, 0, st>>>(fa);
-    UZ_CUDA_TRY(cudaGetLastError());
+    {
+        const int rc = msm_reduce_run(s->reduce, d_out, st);
+        if (rc != UZKGE_OK) return rc;
+    }
     g_prof.mark(prof, MSM_PH_REDUCE, st);
-    UZ_COUNT_LAUNCH(9 + 3 + 3);  // own kernels + CUB's radix-sort launches (histogram, scan, onesweep passes: >= 3 per sort)
+    UZ_COUNT_LAUNCH(7 + 3 + 2);  // own kernels (the reduction counts its own) + CUB's sort / scan launches
     return UZKGE_OK;
 }
 

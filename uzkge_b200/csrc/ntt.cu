@@ -252,7 +252,13 @@ const NttDomain* NttEngine::domain(uint64_t n, cudaStream_t st) {
     auto it = domains_.find(n);
     if (it != domains_.end()) return &it->second;
     NttDomain d;
-    if (!ntt_make_plan(n, cfg_log_tile_, cfg_max_log_r_, cfg_two_pass_max_, &d.plan)) return nullptr;
+    // small transforms: smaller tiles give more CTAs (measured: 2^16 takes 28 us with 2^9 tiles, 42 us with 2^10)
+    uint32_t lg = 0;
+    while ((1ull << (lg + 1)) <= n) lg++;
+    uint32_t tile = lg > 16 ? lg - 7 : 9;
+    if (tile > cfg_log_tile_) tile = cfg_log_tile_;
+    const uint32_t max_r = cfg_max_log_r_ < tile ? cfg_max_log_r_ : tile;
+    if (!ntt_make_plan(n, tile, max_r, cfg_two_pass_max_, &d.plan)) return nullptr;
     // small transforms: shrink the column count until there are enough CTAs to cover the SMs
     for (uint32_t i = 0; i < d.plan.npass; i++) {
         NttPass& p = d.plan.pass[i];
