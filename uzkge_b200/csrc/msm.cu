@@ -405,20 +405,19 @@ __global__ void __launch_bounds__(128) msm_table_kernel(const TableArgs a) {
 
 // ------------------------------------------------------------------ host side
 
+// Window size for an SRS of n points, from B200 measurements (scripts/gpu_tune.py csweep).  Only sizes whose TOP
+// window is wide enough are used: the top window holds t = 255 - c (W - 1) bits, its digits land in 2^(t-1) buckets,
+// and when that is far fewer than the other windows' 2^(c-1) those buckets receive 2^(c-t) / W times the mean load
+// (c = 18: 2 bits, c = 19: 7 bits, c = 21: 3 bits ... measured 20-30 % slower than their neighbours).
 static uint32_t choose_window_bits(size_t n) {
-    // minimise  windows * n * 10 (mixed adds) + 2^(c-1) * 2 * 14 (marginal sums)  over c, ties to the smaller c
-    double best = 1e300;
-    uint32_t best_c = 8;
-    for (uint32_t c = 8; c <= 22; c++) {
-        const uint32_t w = (255 + c - 1) / c;
-        if ((uint64_t)w * n >= (1ull << 31)) continue;
-        const double cost = (double)w * (double)n * 10.0 + (double)(1ull << (c - 1)) * 28.0 * 1.5;
-        if (cost < best * 0.97) {
-            best = cost;
-            best_c = c;
-        }
-    }
-    return best_c;
+    uint32_t lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    if (lg <= 9) return 9;     // t = 3 of 9: balanced
+    if (lg <= 13) return 10;   // 2^12: 296 us
+    if (lg <= 15) return 13;   // 2^14: 350 us
+    if (lg <= 16) return 15;   // 2^16: 510 us
+    if (lg <= 18) return 17;   // 2^18: 1181 us
+    return 20;                 // 2^20: 2.90 ms, 2^22: 10.4 ms
 }
 
 #define UZ_CUDA_TRY(expr)                                   \
