@@ -124,6 +124,7 @@ def run_reference(args, rank: int, world: int) -> int:
         return 0
     from oracle import cpu as oc
 
+    oc.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1: use every host core we may use
     cores = oc.num_threads()
     log_n = LOG_MSM if args.workload != "ntt" else LOG_NTT
     n = 1 << log_n
@@ -360,6 +361,7 @@ def main() -> int:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu as oc  # the checker / CPU arm only
 
+        oc.set_num_threads(len(os.sched_getaffinity(0)))
         cores = oc.num_threads()
         if "msm" in results:
             r = results["msm"]

@@ -54,6 +54,8 @@ def lib():
         L.oracle_fr_weighted_sums.argtypes = [u64p, sz, u64p, u64p]
         L.oracle_fr_weighted_sums.restype = None
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
+        L.oracle_set_num_threads.restype = None
         L.oracle_init()
         _lib = L
     return _lib
@@ -66,6 +68,10 @@ def _p(a: np.ndarray):
 
 def _c(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def set_num_threads(n: int) -> None:
+    lib().oracle_set_num_threads(int(n))
 
 
 def num_threads() -> int:

@@ -758,6 +758,14 @@ void oracle_fr_weighted_sums(const uint64_t *s, size_t n, uint64_t *s0_out, uint
     memcpy(s0_out, &s0, 32);
     memcpy(s1_out, &s1, 32);
 }
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm of bench.py asks for every host core explicitly */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

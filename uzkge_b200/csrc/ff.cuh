@@ -9,7 +9,11 @@
 // (mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into IMAD.WIDE.U32(.X)): the partial products of the
 // even and the odd limbs of the multiplicand are accumulated in two separate 8-limb rows so that each row
 // is ONE uninterrupted carry chain; the rows swap roles after every 32-bit reduction step instead of being
-// shifted.  8 x (8 + 8 + 1) = 136 IMAD per product.
+// shifted.  8 x (8 + 8 + 1) = 136 IMAD per product (SASS: 120 IMAD.WIDE.U32[.X] + 8 IMAD.HI + 8 IMAD).
+//
+// Tried and rejected on B200 (measured): replacing the low-limb product of the Fr reduction steps
+// (r = 1 mod 2^28) by shifts saves 8 IMAD.HI but lengthens the dependency chain: the 2^22 NTT got 3.5 % slower;
+// forming the reduction multiplier with shifts made ptxas stop fusing mad.lo/madc.hi pairs into IMAD.WIDE.
 //
 // Every primitive has a plain-C twin for host compilation (tests/host, and the few host-side constants the
 // library derives); the twin is bit-identical by construction and is what the CPU test-suite exercises.
