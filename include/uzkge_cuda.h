@@ -92,6 +92,10 @@ UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]);
  * is copied and nothing synchronises: this is what a device-resident prover pipeline and the
  * HBM-resident benchmark call.  d_out may equal d_in for the NTT; d_scratch holds domain_size elements. */
 UZKGE_API int32_t uzkge_cuda_msm_g1_device(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, void* d_out_jac, void* stream);
+/* k MSMs over srs[base_offset ..] in one pass (one sort, one accumulate launch, concurrent reductions); d_scalars is a HOST
+ * array of k device pointers, d_out_jac holds k * 12 words on the device. */
+UZKGE_API int32_t uzkge_cuda_msm_g1_batch_device(uint64_t handle, size_t base_offset, const void* const* d_scalars, const size_t* n,
+                                                 size_t k, void* d_out_jac, void* stream);
 UZKGE_API int32_t uzkge_cuda_ntt_fr_device(const void* d_in, void* d_out, void* d_scratch, size_t len_in, size_t domain_size,
                                  int32_t inverse, const uint64_t* coset_shift_host, void* stream);
 
@@ -126,6 +130,8 @@ typedef struct {
     uint32_t windows;       /* ceil(255 / c) = number of fixed-base tables */
     uint64_t n;             /* SRS length */
     uint64_t device_bytes;  /* device bytes held for this SRS (tables + MSM workspace) */
+    uint32_t batch_slots;   /* independent MSMs one pass can carry (uzkge_cuda_msm_g1_batch) */
+    uint32_t reserved;
     double precompute_ms;   /* device time spent building the tables */
 } uzkge_srs_info;
 UZKGE_API int32_t uzkge_cuda_srs_info(uint64_t handle, uzkge_srs_info* info);

@@ -50,11 +50,27 @@ if what in ("msm", "all"):
             h = ffi.srs_upload(bases, c)
             info = ffi.srs_info(h)
             for lanes in ((0,) if "csweep" in sys.argv else (0, -1) if "quick" in sys.argv else (0,) if lg >= 20 and c not in (0,17) else (0, 1, 2, 4, 8, 16, 32)):
-                ffi.configure("msm_counting_sort", 0 if lanes < 0 else 1)
-                if lanes < 0: lanes = 0
+                if lanes < 0: continue
                 ffi.configure("msm_lanes", lanes)
                 ms = timeit(lambda: ffi.msm_g1_device(h, sc.data_ptr(), n, out.data_ptr()), 5, 2)
                 ffi.profile_enable(True); timeit(lambda: ffi.msm_g1_device(h, sc.data_ptr(), n, out.data_ptr()), 3, 0); p = ffi.profile_read("msm"); ffi.profile_enable(False)
                 print(f"msm 2^{lg} c={info['window_bits']} W={info['windows']} lanes={lanes}: {ms*1e3:8.1f} us  {n/ms/1e3:8.1f} Mpts/s  {({k: round(v*1e3,1) for k,v in p['ms'].items()})}", flush=True)
             ffi.configure("msm_lanes", 0)
             ffi.srs_free(h)
+
+if what in ("batch",):
+    tau = B.random_fr(1, 5)[0]
+    for lg in (12, 13, 14, 16):
+        n = 1 << lg
+        bases = ffi.srs_generate(tau, n)
+        h = ffi.srs_upload(bases, 0)
+        info = ffi.srs_info(h)
+        K = 16
+        scs = [torch.from_numpy(B.random_fr(n, 20 + j).view(np.int64)).to(dev) for j in range(K)]
+        out = torch.zeros(12 * K, dtype=torch.int64, device=dev)
+        for k in (1, 2, 4, 8, 16):
+            ptrs = [t.data_ptr() for t in scs[:k]]
+            ms = timeit(lambda: ffi.msm_g1_batch_device(h, ptrs, [n] * k, out.data_ptr()), 5, 2)
+            ffi.profile_enable(True); timeit(lambda: ffi.msm_g1_batch_device(h, ptrs, [n] * k, out.data_ptr()), 3, 0); p = ffi.profile_read("msm"); ffi.profile_enable(False)
+            print(f"msm batch 2^{lg} c={info['window_bits']} slots={info['batch_slots']} k={k}: {ms*1e3:8.1f} us total {ms*1e3/k:8.1f} us/MSM  {({kk: round(v*1e3,1) for kk,v in p['ms'].items()})}", flush=True)
+        ffi.srs_free(h)

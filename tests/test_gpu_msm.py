@@ -141,6 +141,27 @@ def test_lagrange_srs_known_answers(gpu, oc, bn, srs_padding_head, request, n, f
         gpu.srs_free(h)
 
 
+def test_batched_msm_matches_one_by_one(gpu, oc, bn):
+    """uzkge_cuda_msm_g1_batch: independent MSMs of one prover round in one pass (ragged lengths, an empty and an
+    all-zero vector, skewed scalars, more vectors than batch slots)."""
+    n = 3000
+    pts = oc.g1_random_points(n, 77)
+    h = gpu.srs_upload(pts)
+    try:
+        slots = gpu.srs_info(h)["batch_slots"]
+        assert slots >= 1
+        vecs = [oc.random_fr(n, 300 + j)[: max(1, (n * (j + 1)) // 21)] for j in range(19)]
+        vecs[3] = np.zeros((0, 4), dtype=np.uint64)
+        vecs[5] = np.zeros((100, 4), dtype=np.uint64)
+        vecs[7] = witness_like(oc, bn, n, 5)
+        outs = gpu.msm_g1_batch(h, vecs)
+        for j, v in enumerate(vecs):
+            want = oc.msm_g1(pts[: v.shape[0]], v) if v.shape[0] else np.zeros(12, dtype=np.uint64)
+            assert same_point(oc, outs[j], want), j
+    finally:
+        gpu.srs_free(h)
+
+
 def test_group_helpers(gpu, oc):
     pts = oc.g1_random_points(4, 3)
     a = oc.g1_mul(pts[0], oc.random_fr(1, 1)[0])

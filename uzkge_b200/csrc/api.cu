@@ -218,6 +218,8 @@ UZKGE_API int32_t uzkge_cuda_srs_info(uint64_t handle, uzkge_srs_info* info) {
     info->windows = it->second.windows;
     info->n = it->second.n;
     info->device_bytes = it->second.bytes;
+    info->batch_slots = it->second.slots;
+    info->reserved = 0;
     info->precompute_ms = it->second.precompute_ms;
     return UZKGE_OK;
 }
@@ -245,13 +247,18 @@ UZKGE_API int32_t uzkge_cuda_msm_g1_batch(uint64_t handle, const uint64_t* const
         off += n[j];
     }
     off = 0;
-    for (size_t j = 0; j < k; j++) {
-        int rc = g.msm->run(&s, 0, d_s + off, n[j], d_o + j, g.stream);
+    for (size_t j0 = 0; j0 < k; j0 += s.slots) {
+        const uint32_t kk = (uint32_t)((k - j0) < s.slots ? (k - j0) : s.slots);
+        const fe* ptrs[16];
+        for (uint32_t j = 0; j < kk; j++) {
+            ptrs[j] = d_s + off;
+            off += n[j0 + j];
+        }
+        int rc = g.msm->run_batch(&s, 0, ptrs, n + j0, kk, d_o + j0, g.stream);
         if (rc != UZKGE_OK) {
             cudaStreamSynchronize(g.stream);
-            return engine_fail(rc, "msm_g1: launch");
+            return engine_fail(rc, "msm_g1_batch: launch");
         }
-        off += n[j];
     }
     CUDA_OR_FAIL(cudaMemcpyAsync(out_jac, d_o, k * sizeof(jacobian), cudaMemcpyDeviceToHost, g.stream), "msm_g1: D2H");
     CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "msm_g1: execution");
@@ -285,6 +292,22 @@ UZKGE_API int32_t uzkge_cuda_msm_g1_device(uint64_t handle, size_t base_offset, 
     if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1_device: unknown handle");
     int rc = g.msm->run(&it->second, base_offset, (const fe*)d_scalars, n, (jacobian*)d_out_jac, (cudaStream_t)stream);
     return engine_fail(rc, "msm_g1_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_msm_g1_batch_device(uint64_t handle, size_t base_offset, const void* const* d_scalars, const size_t* n,
+                                                 size_t k, void* d_out_jac, void* stream) {
+    if (k && (!d_scalars || !n || !d_out_jac)) return fail(UZKGE_ERR_ARG, "msm_g1_batch_device: null pointer");
+    API_ENTER(-1);
+    auto it = g.srs.find(handle);
+    if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1_batch_device: unknown handle");
+    MsmSrs& s = it->second;
+    for (size_t j0 = 0; j0 < k; j0 += s.slots) {
+        const uint32_t kk = (uint32_t)((k - j0) < s.slots ? (k - j0) : s.slots);
+        int rc = g.msm->run_batch(&s, base_offset, (const fe* const*)(d_scalars + j0), n + j0, kk, (jacobian*)d_out_jac + j0,
+                                  (cudaStream_t)stream);
+        if (rc != UZKGE_OK) return engine_fail(rc, "msm_g1_batch_device");
+    }
+    return UZKGE_OK;
 }
 
 UZKGE_API int32_t uzkge_cuda_ntt_fr(uint64_t* inout, size_t len_in, size_t domain_size, int32_t inverse, const uint64_t* coset_shift) {
@@ -451,12 +474,6 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
         int rc = ensure_init(-1);
         if (rc != UZKGE_OK) return rc;
         g.msm->force_lanes((uint32_t)value);
-        return UZKGE_OK;
-    }
-    if (k == "msm_counting_sort") {
-        int rc = ensure_init(-1);
-        if (rc != UZKGE_OK) return rc;
-        g.msm->counting_sort(value != 0);
         return UZKGE_OK;
     }
     if (k == "ntt_big_threads") {

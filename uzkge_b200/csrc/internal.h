@@ -130,25 +130,23 @@ struct MsmSrs {
     uint64_t n = 0;            // points
     uint32_t c = 0;            // window bits
     uint32_t windows = 0;      // number of windows == number of fixed-base tables
-    uint32_t nbuckets = 0;     // 2^(c-1) + 1 (bucket 0 = zero digit, never accumulated)
-    // reduction matrix: bucket b = hi * cols + lo
-    uint32_t logcols = 0, cols = 0, rows = 0, nb_padded = 0;
+    uint32_t nbuckets = 0;     // 2^(c-1) + 1 bucket ids per MSM (id 0 = zero digit, always empty)
+    uint32_t slots = 1;        // independent MSMs one pass can carry (batch)
     uint32_t large_cap = 0, max_slices = 0;
     double precompute_ms = 0;
     void* arena = nullptr;     // one device allocation holding everything below
     size_t bytes = 0;
     affine* tables = nullptr;  // windows x n affine points: table f holds 2^(c*f) * P_i
-    // workspace, sized for an MSM over the whole SRS
-    uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
-    uint32_t* offsets = nullptr;      // nbuckets + 1
-    uint32_t* counts = nullptr;       // nbuckets + 1 (counting sort)
+    // workspace, sized for `slots` MSMs over the whole SRS
+    uint32_t* vals = nullptr;         // entries sorted by global bucket id: sign | (f * n + point)
+    uint32_t* offsets = nullptr;      // slots * nbuckets + 1
+    uint32_t* counts = nullptr;       // slots * nbuckets + 1
     uint32_t *ord_keys_a = nullptr, *ord_keys_b = nullptr, *ord_vals_a = nullptr, *ord_vals_b = nullptr;  // size-ordered bucket ids
     uint32_t* large_list = nullptr;   // [0] = count, then bucket ids
-    uint32_t* slice_start = nullptr;  // prefix of CTA slices per oversized bucket
+    uint32_t* slice_start = nullptr;  // prefix of warp slices per oversized bucket
     xyzz* slice_sums = nullptr;
-    xyzz* buckets = nullptr;          // nb_padded
-    uint32_t* ticket = nullptr;
-    struct ReducePlan* reduce = nullptr;  // launch plan of the bucket reduction (msm_reduce.cu)
+    xyzz* buckets = nullptr;          // slots * nbuckets
+    ReducePlan* reduce[16] = {};      // launch plan of the bucket reduction of every slot (msm_reduce.cu)
     void* cub_temp = nullptr;
     size_t cub_temp_bytes = 0;
 };
@@ -162,20 +160,26 @@ int msm_reduce_run(const ReducePlan* p, jacobian* d_out, cudaStream_t st);
 class MsmEngine {
 public:
     explicit MsmEngine(int sm_count) : sm_count_(sm_count) {}
+    ~MsmEngine();
     int upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_bits, MsmSrs* out, cudaStream_t st);
     void release(MsmSrs* s);
     // d_scalars: n Montgomery Fr on the device; d_out: 12 x u64 Jacobian on the device
     int run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n, jacobian* d_out, cudaStream_t st);
+    // k <= s->slots independent MSMs in one pass (one sort, one accumulate launch, concurrent reductions)
+    int run_batch(MsmSrs* s, size_t base_offset, const fe* const* d_scalars, const size_t* n, uint32_t k, jacobian* d_out,
+                  cudaStream_t st);
     int g1_add(const jacobian* d_a, const jacobian* d_b, jacobian* d_out, cudaStream_t st);
     int g1_to_affine(const jacobian* d_in, affine* d_out, cudaStream_t st);
     int powers_of_tau(const fe& tau, uint64_t first, uint32_t count, affine* d_out, cudaStream_t st);
     void force_lanes(uint32_t g) { force_lanes_ = g; }  // tuning knob (0 = automatic)
-    void counting_sort(bool on) { counting_sort_ = on; }
+
 
 private:
     int sm_count_;
     uint32_t force_lanes_ = 0;
-    bool counting_sort_ = true;
+    std::vector<cudaStream_t> aux_;   // auxiliary streams for the concurrent reductions of a batch
+    std::vector<cudaEvent_t> join_;
+    cudaEvent_t fork_ = nullptr;
 };
 
 static inline int cuda_err_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? UZKGE_ERR_OOM : UZKGE_ERR_CUDA; }

@@ -31,22 +31,30 @@ static constexpr int ACC_NT = 256;            // threads per CTA of the accumula
 static constexpr uint32_t LARGE_SLICE = 1024; // entries per warp slice of an oversized bucket
 static constexpr int LARGE_NT = 256;
 
-// ------------------------------------------------------------------ recode
-struct RecodeArgs {
-    const fe* scalars;
-    uint32_t n;             // scalars in this MSM
+// ------------------------------------------------------------------ digits + counting sort by bucket
+// A launch handles up to MSM_MAX_BATCH independent MSMs over the same SRS (blockIdx.y = MSM j); MSM j owns the global
+// bucket ids j * nbuckets + d.  Pass 1 counts the entries per bucket, a scan turns counts into offsets, pass 2
+// recomputes the digits and scatters  val = sign | (f * table_stride + point)  into its bucket's segment.  Zero
+// digits are dropped; the order inside a bucket is arbitrary (the sum does not depend on it).
+static constexpr uint32_t MSM_MAX_BATCH = 16;
+struct DigitArgs {
+    const fe* scalars[MSM_MAX_BATCH];
+    uint32_t n[MSM_MAX_BATCH];
     uint32_t c, windows;
     uint32_t table_stride;  // SRS length (distance between tables, in points)
     uint32_t base_offset;
-    uint32_t* keys;
-    uint32_t* vals;
+    uint32_t nbuckets;
 };
 
-__global__ void __launch_bounds__(256) msm_recode_kernel(const RecodeArgs a) {
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) msm_count_scatter_kernel(const DigitArgs a, uint32_t* __restrict__ counts,
+                                                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted_vals) {
+    const uint32_t j = blockIdx.y;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    fe s = fe_from_mont<FrP>(ld_fe(a.scalars + i));
+    if (i >= a.n[j]) return;
+    fe s = fe_from_mont<FrP>(ld_fe(a.scalars[j] + i));
     const uint32_t c = a.c, mask = (1u << c) - 1, half = 1u << (c - 1);
+    const uint32_t bucket0 = j * a.nbuckets;
     uint32_t carry = 0;
     const uint32_t point = a.base_offset + i;
     for (uint32_t f = 0; f < a.windows; f++) {
@@ -58,64 +66,25 @@ __global__ void __launch_bounds__(256) msm_recode_kernel(const RecodeArgs a) {
         carry = 0;
         if (d > half) {  // d in (2^(c-1), 2^c]  ->  d - 2^c in (-2^(c-1), 0]
             d = (1u << c) - d;
-            neg = d ? 0x80000000u : 0u;
-            carry = 1;
-        }
-        const size_t o = (size_t)f * a.n + i;
-        a.keys[o] = d;
-        a.vals[o] = (f * a.table_stride + point) | neg;
-    }
-}
-
-// ---- counting sort by bucket (alternative to the radix sort; zero digits are dropped, order inside a bucket is
-// arbitrary).  Pass 1 counts, a scan turns counts into offsets, pass 2 recomputes the digits and scatters.
-template <bool SCATTER>
-__global__ void __launch_bounds__(256) msm_count_scatter_kernel(const RecodeArgs a, uint32_t* __restrict__ counts,
-                                                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted_vals) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    fe s = fe_from_mont<FrP>(ld_fe(a.scalars + i));
-    const uint32_t c = a.c, mask = (1u << c) - 1, half = 1u << (c - 1);
-    uint32_t carry = 0;
-    const uint32_t point = a.base_offset + i;
-    for (uint32_t f = 0; f < a.windows; f++) {
-        uint32_t d = (s.l[0] & mask) + carry;
-#pragma unroll
-        for (int k = 0; k < 7; k++) s.l[k] = __funnelshift_r(s.l[k], s.l[k + 1], c);
-        s.l[7] >>= c;
-        uint32_t neg = 0;
-        carry = 0;
-        if (d > half) {
-            d = (1u << c) - d;
             neg = 0x80000000u;
             carry = 1;
         }
         if (d == 0) continue;
         if (SCATTER) {
-            const uint32_t pos = offsets[d] + atomicAdd(counts + d, 1u);
+            const uint32_t pos = offsets[bucket0 + d] + atomicAdd(counts + bucket0 + d, 1u);
             sorted_vals[pos] = (f * a.table_stride + point) | neg;
         } else {
-            atomicAdd(counts + d, 1u);
+            atomicAdd(counts + bucket0 + d, 1u);
         }
     }
 }
 
-// offsets[b] = first sorted position whose key is >= b, for b in [0, nbuckets]; offsets[nbuckets] = m
-__global__ void __launch_bounds__(256) msm_offsets_kernel(const uint32_t* __restrict__ keys, uint32_t m, uint32_t nbuckets,
-                                                          uint32_t* __restrict__ offsets) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > m) return;
-    const uint32_t cur = (i == m) ? nbuckets : min(keys[i], nbuckets);
-    const uint32_t lo = (i == 0) ? 0 : min(keys[i - 1], nbuckets) + 1;
-    for (uint32_t b = lo; b <= cur; b++) offsets[b] = i;
-}
-
 // key = cap - min(size, cap): an ascending sort visits the largest segments first
-__global__ void __launch_bounds__(256) msm_sizes_kernel(const uint32_t* __restrict__ offsets, uint32_t nbuckets, uint32_t cap,
+__global__ void __launch_bounds__(256) msm_sizes_kernel(const uint32_t* __restrict__ offsets, uint32_t total_buckets, uint32_t cap,
                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbuckets) return;
-    const uint32_t size = b ? offsets[b + 1] - offsets[b] : 0;
+    if (b >= total_buckets) return;
+    const uint32_t size = offsets[b + 1] - offsets[b];  // the zero-digit bucket of every MSM is empty by construction
     keys[b] = cap - min(size, cap);
     vals[b] = b;
 }
@@ -127,8 +96,7 @@ struct AccArgs {
     const uint32_t* offsets;  // nbuckets + 1
     const uint32_t* order;    // bucket ids, largest segment first
     xyzz* buckets;            // nb_padded
-    uint32_t nbuckets;        // valid bucket ids are 1 .. nbuckets-1
-    uint32_t nb_padded;       // rows * cols of the reduction matrix
+    uint32_t nb_padded;       // batch * nbuckets global bucket ids
     uint32_t large_threshold;
     uint32_t* large_list;     // [0] = count, [1 + k] = bucket id
     uint32_t large_cap;
@@ -193,7 +161,7 @@ __global__ void __launch_bounds__(ACC_NT, 2) msm_accumulate_kernel(const AccArgs
     const uint32_t b = slot < a.nb_padded ? a.order[slot] : a.nb_padded;
     uint32_t start = 0, end = 0;
     bool write = b < a.nb_padded;
-    if (b >= 1 && b < a.nbuckets) {
+    if (b < a.nb_padded) {
         start = a.offsets[b];
         end = a.offsets[b + 1];
         if (end - start > a.large_threshold) {
@@ -257,42 +225,48 @@ __global__ void __launch_bounds__(1024) msm_large_plan_kernel(const LargeArgs a)
     if (threadIdx.x == 0) a.slice_start[nl] = carry_s;
 }
 
-// one WARP per slice of LARGE_SLICE entries: lanes stride over the slice, then a shuffle tree
+// one WARP per slice of LARGE_SLICE entries: lanes stride over the slice, then a shuffle tree.  The grid is a fixed
+// number of CTAs; warps walk the slice list (its length is only known on the device).
 __global__ void __launch_bounds__(LARGE_NT, 2) msm_large_accumulate_kernel(const LargeArgs a) {
     extern __shared__ uint4 acc_smem[];
     const uint32_t nl = min(a.large_list[0], a.large_cap);
     const uint32_t total = min(a.slice_start[nl], a.max_slices);
-    const uint32_t s = blockIdx.x * (LARGE_NT / 32) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
-    if (s >= total) return;  // warp-uniform
-    // largest k with slice_start[k] <= s
-    uint32_t lo = 0, hi = nl;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (a.slice_start[mid] <= s) lo = mid; else hi = mid;
-    }
-    const uint32_t b = a.large_list[1 + lo];
-    const uint32_t first = a.offsets[b] + (s - a.slice_start[lo]) * LARGE_SLICE;
-    const uint32_t end = min(first + LARGE_SLICE, a.offsets[b + 1]);
-    xyzz acc = xyzz_identity();
-    accumulate_segment<LARGE_NT>(acc, a.tables, a.vals, first + lane, end, 32, acc_smem);
+    const uint32_t nwarps = gridDim.x * (LARGE_NT / 32);
 #pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
-    if (lane == 0) st_xyzz(a.slice_sums + s, acc);
+    for (uint32_t s = blockIdx.x * (LARGE_NT / 32) + (threadIdx.x >> 5); s < total; s += nwarps) {
+        // largest k with slice_start[k] <= s
+        uint32_t lo = 0, hi = nl;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (a.slice_start[mid] <= s) lo = mid; else hi = mid;
+        }
+        const uint32_t b = a.large_list[1 + lo];
+        const uint32_t first = a.offsets[b] + (s - a.slice_start[lo]) * LARGE_SLICE;
+        const uint32_t end = min(first + LARGE_SLICE, a.offsets[b + 1]);
+        xyzz acc = xyzz_identity();
+        accumulate_segment<LARGE_NT>(acc, a.tables, a.vals, first + lane, end, 32, acc_smem);
+#pragma unroll 1
+        for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
+        if (lane == 0) st_xyzz(a.slice_sums + s, acc);
+    }
 }
 
 // one warp per listed bucket: sum its slice sums
-__global__ void __launch_bounds__(32) msm_large_finish_kernel(const LargeArgs a) {
+__global__ void __launch_bounds__(128) msm_large_finish_kernel(const LargeArgs a) {
     const uint32_t nl = min(a.large_list[0], a.large_cap);
-    const uint32_t k = blockIdx.x;
-    if (k >= nl) return;
-    const uint32_t s0 = a.slice_start[k], s1 = min(a.slice_start[k + 1], a.max_slices);
-    xyzz acc = xyzz_identity();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * 4;
 #pragma unroll 1
-    for (uint32_t s = s0 + threadIdx.x; s < s1; s += 32) acc = xyzz_add_call(acc, ld_xyzz(a.slice_sums + s));
+    for (uint32_t k = blockIdx.x * 4 + (threadIdx.x >> 5); k < nl; k += nwarps) {
+        const uint32_t s0 = a.slice_start[k], s1 = min(a.slice_start[k + 1], a.max_slices);
+        xyzz acc = xyzz_identity();
 #pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
-    if (threadIdx.x == 0) st_xyzz(a.buckets + a.large_list[1 + k], acc);
+        for (uint32_t s = s0 + lane; s < s1; s += 32) acc = xyzz_add_call(acc, ld_xyzz(a.slice_sums + s));
+#pragma unroll 1
+        for (int off = 16; off > 0; off >>= 1) acc = xyzz_add_call(acc, shfl_down_xyzz(acc, off));
+        if (lane == 0) st_xyzz(a.buckets + a.large_list[1 + k], acc);
+    }
 }
 
 __global__ void msm_identity_kernel(jacobian* out) {
@@ -426,6 +400,16 @@ static uint32_t choose_window_bits(size_t n) {
         if (e__ != cudaSuccess) return cuda_err_code(e__);  \
     } while (0)
 
+// Batch slots: how many independent MSMs one pass can carry (their bucket sets, reduction workspaces and sorted-entry
+// segments live side by side).  Small SRS (PlonK-sized commitments, 16 per proof) get up to 16; large ones 1.
+static uint32_t choose_batch_slots(size_t n, uint32_t nbuckets, uint32_t windows, size_t reduce_bytes) {
+    const size_t per_slot = (size_t)nbuckets * (sizeof(xyzz) + 6 * 4) + reduce_bytes + (size_t)windows * n * 4;
+    size_t slots = ((size_t)256 << 20) / (per_slot ? per_slot : 1);
+    if (slots < 1) slots = 1;
+    if (slots > MSM_MAX_BATCH) slots = MSM_MAX_BATCH;
+    return (uint32_t)slots;
+}
+
 int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_bits, MsmSrs* s, cudaStream_t st) {
     if (n == 0 || n >= (1ull << 28)) return UZKGE_ERR_SIZE;
     uint32_t c = window_bits ? window_bits : choose_window_bits(n);
@@ -436,15 +420,17 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     s->n = n;
     s->c = c;
     s->windows = windows;
-    s->nbuckets = (1u << (c - 1)) + 1;
-    s->logcols = c / 2;                       // cols = 2^ceil((c-1)/2)
-    s->cols = 1u << s->logcols;
-    s->rows = 1u << (c - 1 - s->logcols);     // rows * cols = 2^(c-1); the top bucket 2^(c-1) is stored after the matrix
-    s->nb_padded = s->nbuckets;
-    const size_t m = (size_t)windows * n;
-    // segments longer than max(8 * mean, 64 * lanes) are "large": at most nbuckets / 8 of them can exist
-    s->large_cap = s->nbuckets / 8 + 2;
-    s->max_slices = (uint32_t)(m / LARGE_SLICE + s->large_cap);
+    s->nbuckets = (1u << (c - 1)) + 1;  // 0 (zero digit, always empty) .. 2^(c-1)
+    const size_t reduce_bytes = msm_reduce_workspace_bytes(c);
+    if (reduce_bytes == 0) return UZKGE_ERR_SIZE;
+    s->slots = choose_batch_slots(n, s->nbuckets, windows, reduce_bytes);
+    const size_t m = (size_t)windows * n;          // entries of one full-size MSM
+    const size_t m_all = m * s->slots;
+    const size_t nb_all = (size_t)s->nbuckets * s->slots;
+    if (m_all >= (1ull << 31)) return UZKGE_ERR_SIZE;
+    // segments longer than max(8 * mean, 64 * lanes) are "large": at most nb_all / 8 of them can exist
+    s->large_cap = (uint32_t)(nb_all / 8 + 2);
+    s->max_slices = (uint32_t)(m_all / LARGE_SLICE + s->large_cap);
 
     size_t total = 0;
     auto take = [&](size_t bytes) {
@@ -453,55 +439,49 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
         return off;
     };
     const size_t o_tables = take(sizeof(affine) * m);
-    const size_t o_keys_a = take(4 * m), o_keys_b = take(4 * m), o_vals_a = take(4 * m), o_vals_b = take(4 * m);
-    const size_t o_offsets = take(4 * ((size_t)s->nbuckets + 1));
-    const size_t o_ord = take(4 * 4 * (size_t)s->nbuckets);
-    const size_t o_counts = take(4 * ((size_t)s->nbuckets + 1));
+    const size_t o_vals = take(4 * m_all);
+    const size_t o_offsets = take(4 * (nb_all + 1));
+    const size_t o_counts = take(4 * (nb_all + 1));
+    const size_t o_ord = take(4 * 4 * nb_all);
     const size_t o_large = take(4 * ((size_t)s->large_cap + 1));
     const size_t o_slice_start = take(4 * ((size_t)s->large_cap + 1));
     const size_t o_slice_sums = take(sizeof(xyzz) * s->max_slices);
-    const size_t o_buckets = take(sizeof(xyzz) * s->nb_padded);
-    const size_t reduce_bytes = msm_reduce_workspace_bytes(c);
-    if (reduce_bytes == 0) return UZKGE_ERR_SIZE;
-    const size_t o_reduce = take(reduce_bytes);
-    const size_t o_ticket = take(256);
+    const size_t o_buckets = take(sizeof(xyzz) * nb_all);
+    const size_t o_reduce = take(reduce_bytes * s->slots);
+    const size_t o_ticket = take(256 * s->slots);
     cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
     s->cub_temp_bytes = 0;
-    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_temp_bytes, dk, dv, (int)m, 0, (int)c, st));
-    size_t ord_temp = 0;
-    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, ord_temp, dk, dv, (int)s->nbuckets, 0, 32, st));
-    if (ord_temp > s->cub_temp_bytes) s->cub_temp_bytes = ord_temp;
+    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_temp_bytes, dk, dv, (int)nb_all, 0, 32, st));
     size_t scan_temp = 0;
-    UZ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)s->nbuckets + 1, st));
+    UZ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)nb_all + 1, st));
     if (scan_temp > s->cub_temp_bytes) s->cub_temp_bytes = scan_temp;
     const size_t o_cub = take(s->cub_temp_bytes + 256);
     UZ_CUDA_TRY(cudaMalloc(&s->arena, total));
     s->bytes = total;
     char* base = (char*)s->arena;
     s->tables = (affine*)(base + o_tables);
-    s->keys_a = (uint32_t*)(base + o_keys_a);
-    s->keys_b = (uint32_t*)(base + o_keys_b);
-    s->vals_a = (uint32_t*)(base + o_vals_a);
-    s->vals_b = (uint32_t*)(base + o_vals_b);
+    s->vals = (uint32_t*)(base + o_vals);
     s->offsets = (uint32_t*)(base + o_offsets);
     s->counts = (uint32_t*)(base + o_counts);
     s->ord_keys_a = (uint32_t*)(base + o_ord);
-    s->ord_keys_b = s->ord_keys_a + s->nbuckets;
-    s->ord_vals_a = s->ord_keys_b + s->nbuckets;
-    s->ord_vals_b = s->ord_vals_a + s->nbuckets;
+    s->ord_keys_b = s->ord_keys_a + nb_all;
+    s->ord_vals_a = s->ord_keys_b + nb_all;
+    s->ord_vals_b = s->ord_vals_a + nb_all;
     s->large_list = (uint32_t*)(base + o_large);
     s->slice_start = (uint32_t*)(base + o_slice_start);
     s->slice_sums = (xyzz*)(base + o_slice_sums);
     s->buckets = (xyzz*)(base + o_buckets);
-    s->ticket = (uint32_t*)(base + o_ticket);
-    s->reduce = msm_reduce_plan_create(c, s->buckets, base + o_reduce, s->ticket);
-    if (!s->reduce) return UZKGE_ERR_INTERNAL;
     s->cub_temp = base + o_cub;
+    for (uint32_t j = 0; j < s->slots; j++) {
+        s->reduce[j] = msm_reduce_plan_create(c, s->buckets + (size_t)j * s->nbuckets, base + o_reduce + reduce_bytes * j,
+                                              (uint32_t*)(base + o_ticket + 256 * j));
+        if (!s->reduce[j]) return UZKGE_ERR_INTERNAL;
+    }
 
     cudaEvent_t e0, e1;
     UZ_CUDA_TRY(cudaEventCreate(&e0));
     UZ_CUDA_TRY(cudaEventCreate(&e1));
-    UZ_CUDA_TRY(cudaMemsetAsync(s->ticket, 0, 256, st));
+    UZ_CUDA_TRY(cudaMemsetAsync(base + o_ticket, 0, 256 * s->slots, st));
     UZ_CUDA_TRY(cudaMemcpyAsync(s->tables, affine_xy_host, sizeof(affine) * n, cudaMemcpyHostToDevice, st));
     UZ_CUDA_TRY(cudaEventRecord(e0, st));
     // slabs of at most 2^20 points bound the XYZZ / prefix-product scratch
@@ -539,9 +519,16 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
 }
 
 void MsmEngine::release(MsmSrs* s) {
-    if (s->reduce) msm_reduce_plan_destroy(s->reduce);
+    for (uint32_t j = 0; j < MSM_MAX_BATCH; j++)
+        if (s->reduce[j]) msm_reduce_plan_destroy(s->reduce[j]);
     if (s->arena) cudaFree(s->arena);
     *s = MsmSrs();
+}
+
+MsmEngine::~MsmEngine() {
+    for (cudaStream_t a : aux_) cudaStreamDestroy(a);
+    if (fork_) cudaEventDestroy(fork_);
+    for (cudaEvent_t e : join_) cudaEventDestroy(e);
 }
 
 template <int G>
@@ -553,88 +540,86 @@ static cudaError_t launch_accumulate(const AccArgs& a, cudaStream_t st) {
 }
 
 int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n, jacobian* d_out, cudaStream_t st) {
-    if (base_offset > s->n || n > s->n - base_offset) return UZKGE_ERR_SIZE;
-    if (n == 0) {
-        msm_identity_kernel<<<1, 1, 0, st>>>(d_out);
-        UZ_COUNT_LAUNCH(1);
+    const fe* sc[1] = {d_scalars};
+    const size_t nn[1] = {n};
+    return run_batch(s, base_offset, sc, nn, 1, d_out, st);
+}
+
+// k <= s->slots independent MSMs over srs[base_offset ..]; d_out receives k Jacobian points
+int MsmEngine::run_batch(MsmSrs* s, size_t base_offset, const fe* const* d_scalars, const size_t* n, uint32_t k, jacobian* d_out,
+                         cudaStream_t st) {
+    if (k == 0) return UZKGE_OK;
+    if (k > s->slots || base_offset > s->n) return UZKGE_ERR_SIZE;
+    uint64_t n_all = 0;
+    uint32_t n_max = 0;
+    DigitArgs da;
+    for (uint32_t j = 0; j < k; j++) {
+        if (n[j] > s->n - base_offset) return UZKGE_ERR_SIZE;
+        da.scalars[j] = d_scalars[j];
+        da.n[j] = (uint32_t)n[j];
+        n_all += n[j];
+        if (n[j] > n_max) n_max = (uint32_t)n[j];
+    }
+    if (n_all == 0) {
+        for (uint32_t j = 0; j < k; j++) msm_identity_kernel<<<1, 1, 0, st>>>(d_out + j);
+        UZ_COUNT_LAUNCH(k);
         UZ_CUDA_TRY(cudaGetLastError());
         return UZKGE_OK;
     }
-    const uint32_t m = (uint32_t)(s->windows * n);
+    da.c = s->c;
+    da.windows = s->windows;
+    da.table_stride = (uint32_t)s->n;
+    da.base_offset = (uint32_t)base_offset;
+    da.nbuckets = s->nbuckets;
+    const uint32_t nb_all = s->nbuckets * k;
+    const uint64_t m = (uint64_t)s->windows * n_all;
     const int prof = g_prof.begin(Profiler::MSM, st);
-    RecodeArgs ra;
-    ra.scalars = d_scalars;
-    ra.n = (uint32_t)n;
-    ra.c = s->c;
-    ra.windows = s->windows;
-    ra.table_stride = (uint32_t)s->n;
-    ra.base_offset = (uint32_t)base_offset;
-    ra.keys = s->keys_a;
-    ra.vals = s->vals_a;
-    const uint32_t* vals;
-    size_t temp;
-    if (counting_sort_) {
-        // count -> scan -> scatter: 2 x N*W global atomics instead of 3 radix passes over N*W pairs
-        const size_t cbytes = 4 * ((size_t)s->nbuckets + 1);
-        UZ_CUDA_TRY(cudaMemsetAsync(s->counts, 0, cbytes, st));
-        msm_count_scatter_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ra, s->counts, nullptr, nullptr);
-        UZ_CUDA_TRY(cudaGetLastError());
-        g_prof.mark(prof, MSM_PH_RECODE, st);
-        temp = s->cub_temp_bytes;
-        UZ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->cub_temp, temp, s->counts, s->offsets, (int)s->nbuckets + 1, st));
-        UZ_CUDA_TRY(cudaMemsetAsync(s->counts, 0, cbytes, st));
-        msm_count_scatter_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ra, s->counts, s->offsets, s->vals_b);
-        UZ_CUDA_TRY(cudaGetLastError());
-        vals = s->vals_b;
-        g_prof.mark(prof, MSM_PH_SORT, st);
-    } else {
-        msm_recode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ra);
-        UZ_CUDA_TRY(cudaGetLastError());
-        g_prof.mark(prof, MSM_PH_RECODE, st);
 
-        cub::DoubleBuffer<uint32_t> dk(s->keys_a, s->keys_b), dv(s->vals_a, s->vals_b);
-        temp = s->cub_temp_bytes;
-        UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_temp, temp, dk, dv, (int)m, 0, (int)s->c, st));
-        const uint32_t* keys = dk.Current();
-        vals = dv.Current();
-        g_prof.mark(prof, MSM_PH_SORT, st);
-
-        msm_offsets_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(keys, m, s->nbuckets, s->offsets);
-        UZ_CUDA_TRY(cudaGetLastError());
-    }
+    // count -> scan -> scatter
+    const size_t cbytes = 4 * ((size_t)nb_all + 1);
+    const dim3 dgrid((n_max + 255) / 256, k);
+    UZ_CUDA_TRY(cudaMemsetAsync(s->counts, 0, cbytes, st));
+    msm_count_scatter_kernel<false><<<dgrid, 256, 0, st>>>(da, s->counts, nullptr, nullptr);
+    UZ_CUDA_TRY(cudaGetLastError());
+    g_prof.mark(prof, MSM_PH_RECODE, st);
+    size_t temp = s->cub_temp_bytes;
+    UZ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->cub_temp, temp, s->counts, s->offsets, (int)nb_all + 1, st));
+    UZ_CUDA_TRY(cudaMemsetAsync(s->counts, 0, cbytes, st));
+    msm_count_scatter_kernel<true><<<dgrid, 256, 0, st>>>(da, s->counts, s->offsets, s->vals);
+    UZ_CUDA_TRY(cudaGetLastError());
     UZ_CUDA_TRY(cudaMemsetAsync(s->large_list, 0, 4, st));
+    g_prof.mark(prof, MSM_PH_SORT, st);
 
     // lanes per bucket: ~48 entries per lane, but at least enough groups to fill every SM
-    const double mean = (double)m / (double)(s->nbuckets - 1);
+    const double mean = (double)m / (double)(nb_all - k);
     uint32_t g = 1;
     while (g < 32 && mean / (g * 2) >= 40.0) g *= 2;
-    while (g < 32 && (uint64_t)s->nbuckets * g * 2 <= (uint64_t)sm_count_ * 512) g *= 2;
+    while (g < 32 && (uint64_t)nb_all * g * 2 <= (uint64_t)sm_count_ * 512) g *= 2;
     if (force_lanes_) g = force_lanes_;
-    // segments above the threshold are split into CTA slices (msm_large_*)
+    // segments above the threshold are split into warp slices (msm_large_*)
     uint32_t thr = (uint32_t)(mean * 8.0);
     {
         uint32_t per_lane = (uint32_t)(m / (2ull * sm_count_ * 512));
         if (per_lane < 64) per_lane = 64;
         if (thr < per_lane * g) thr = per_lane * g;
     }
-
+    // visit the buckets in decreasing size
     uint32_t cap_bits = 1;
     while ((1u << cap_bits) <= thr + 1) cap_bits++;
-    msm_sizes_kernel<<<(s->nbuckets + 255) / 256, 256, 0, st>>>(s->offsets, s->nbuckets, thr + 1, s->ord_keys_a, s->ord_vals_a);
+    msm_sizes_kernel<<<(nb_all + 255) / 256, 256, 0, st>>>(s->offsets, nb_all, thr + 1, s->ord_keys_a, s->ord_vals_a);
     UZ_CUDA_TRY(cudaGetLastError());
     cub::DoubleBuffer<uint32_t> ok(s->ord_keys_a, s->ord_keys_b), ov(s->ord_vals_a, s->ord_vals_b);
     temp = s->cub_temp_bytes;
-    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_temp, temp, ok, ov, (int)s->nbuckets, 0, (int)cap_bits, st));
+    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_temp, temp, ok, ov, (int)nb_all, 0, (int)cap_bits, st));
     g_prof.mark(prof, MSM_PH_OFFSETS, st);
 
     AccArgs aa;
     aa.tables = s->tables;
-    aa.vals = vals;
+    aa.vals = s->vals;
     aa.offsets = s->offsets;
     aa.order = ov.Current();
     aa.buckets = s->buckets;
-    aa.nbuckets = s->nbuckets;
-    aa.nb_padded = s->nb_padded;
+    aa.nb_padded = nb_all;
     aa.large_threshold = thr;
     aa.large_list = s->large_list;
     aa.large_cap = s->large_cap;
@@ -652,7 +637,7 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
 
     LargeArgs la;
     la.tables = s->tables;
-    la.vals = vals;
+    la.vals = s->vals;
     la.offsets = s->offsets;
     la.buckets = s->buckets;
     la.large_list = s->large_list;
@@ -660,22 +645,41 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     la.slice_sums = s->slice_sums;
     la.large_cap = s->large_cap;
     la.max_slices = s->max_slices;
-    // upper bounds for this m (the kernels read the real counts on the device; surplus CTAs exit at once)
-    uint32_t cap_now = (uint32_t)(m / aa.large_threshold + 1);
-    if (cap_now > s->large_cap) cap_now = s->large_cap;
-    const uint32_t slices_now = m / LARGE_SLICE + cap_now;
+    // the list lengths are only known on the device: fixed grids whose warps walk the lists
     msm_large_plan_kernel<<<1, 1024, 0, st>>>(la);
-    msm_large_accumulate_kernel<<<(slices_now + LARGE_NT / 32 - 1) / (LARGE_NT / 32), LARGE_NT, 2 * 4 * LARGE_NT * sizeof(uint4), st>>>(la);
-    msm_large_finish_kernel<<<cap_now, 32, 0, st>>>(la);
+    msm_large_accumulate_kernel<<<sm_count_ * 4, LARGE_NT, 2 * 4 * LARGE_NT * sizeof(uint4), st>>>(la);
+    msm_large_finish_kernel<<<sm_count_ * 2, 128, 0, st>>>(la);
     UZ_CUDA_TRY(cudaGetLastError());
     g_prof.mark(prof, MSM_PH_LARGE, st);
 
-    {
-        const int rc = msm_reduce_run(s->reduce, d_out, st);
+    // the k bucket reductions are latency-bound chains of small kernels: run them side by side on auxiliary streams
+    if (k == 1) {
+        const int rc = msm_reduce_run(s->reduce[0], d_out, st);
         if (rc != UZKGE_OK) return rc;
+    } else {
+        while (aux_.size() < k - 1) {
+            cudaStream_t a;
+            cudaEvent_t ev;
+            UZ_CUDA_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+            UZ_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            aux_.push_back(a);
+            join_.push_back(ev);
+        }
+        if (!fork_) UZ_CUDA_TRY(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
+        UZ_CUDA_TRY(cudaEventRecord(fork_, st));
+        for (uint32_t j = 0; j < k; j++) {
+            cudaStream_t sj = j == 0 ? st : aux_[j - 1];
+            if (j) UZ_CUDA_TRY(cudaStreamWaitEvent(sj, fork_, 0));
+            const int rc = msm_reduce_run(s->reduce[j], d_out + j, sj);
+            if (rc != UZKGE_OK) return rc;
+            if (j) {
+                UZ_CUDA_TRY(cudaEventRecord(join_[j - 1], sj));
+                UZ_CUDA_TRY(cudaStreamWaitEvent(st, join_[j - 1], 0));
+            }
+        }
     }
     g_prof.mark(prof, MSM_PH_REDUCE, st);
-    UZ_COUNT_LAUNCH(7 + 3 + 2);  // own kernels (the reduction counts its own) + CUB's sort / scan launches
+    UZ_COUNT_LAUNCH(7 + 2 + 3);  // own kernels (the reductions count their own) + CUB's scan / sort launches
     return UZKGE_OK;
 }
 

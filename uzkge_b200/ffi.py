@@ -27,6 +27,8 @@ class SrsInfo(C.Structure):
         ("windows", C.c_uint32),
         ("n", C.c_uint64),
         ("device_bytes", C.c_uint64),
+        ("batch_slots", C.c_uint32),
+        ("reserved", C.c_uint32),
         ("precompute_ms", C.c_double),
     ]
 
@@ -44,6 +46,10 @@ _SIGNATURES = {
     "uzkge_cuda_ntt_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p]),
     "uzkge_cuda_fr_root_of_unity": (C.c_int32, [C.c_size_t, C.c_void_p]),
     "uzkge_cuda_msm_g1_device": (C.c_int32, [C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_msm_g1_batch_device": (
+        C.c_int32,
+        [C.c_uint64, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p, C.c_void_p],
+    ),
     "uzkge_cuda_ntt_fr_device": (
         C.c_int32,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p],
@@ -237,6 +243,13 @@ def fr_root_of_unity(n: int) -> np.ndarray:
 
 def msm_g1_device(handle: int, d_scalars: int, n: int, d_out: int, stream: int = 0, base_offset: int = 0) -> None:
     check(lib().uzkge_cuda_msm_g1_device(handle, base_offset, d_scalars, n, d_out, stream), CommitmentError)
+
+
+def msm_g1_batch_device(handle: int, d_scalar_ptrs, ns, d_out: int, stream: int = 0, base_offset: int = 0) -> None:
+    k = len(d_scalar_ptrs)
+    ptrs = (C.c_void_p * k)(*d_scalar_ptrs)
+    lens = (C.c_size_t * k)(*ns)
+    check(lib().uzkge_cuda_msm_g1_batch_device(handle, base_offset, ptrs, lens, k, d_out, stream), CommitmentError)
 
 
 def ntt_fr_device(d_in: int, d_out: int, d_scratch: int, len_in: int, domain_size: int, inverse: bool = False,
