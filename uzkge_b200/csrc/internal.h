@@ -88,6 +88,9 @@ struct NttDomain {
     fe* w_hi = nullptr;
     fe* stage = nullptr;
     uint32_t n_hi = 0, n_stage = 0;
+    fe* tw_all = nullptr;                          // one allocation: the per-element twiddle tables below
+    fe* tw_pass[3] = {nullptr, nullptr, nullptr};  // inter-pass twiddles, indexed by the pass's output position
+    fe* tw3 = nullptr;                             // radix-3 pre-pass twiddles w^n | w^(2n)
 };
 struct NttCoset {
     uint64_t n;
@@ -95,6 +98,7 @@ struct NttCoset {
     bool with_ninv;
     fe* g_lo = nullptr;   // one allocation: g_lo | g_hi
     fe* g_hi = nullptr;
+    fe* g_full = nullptr;  // premul * g^j for every j < n
     uint32_t n_hi = 0;
 };
 

@@ -62,6 +62,8 @@ struct NttKernelArgs {
     const fe* w_hi;
     const fe* g_lo;  // coset powers (forward: g^j, inverse: g^j / N) or null
     const fe* g_hi;
+    const fe* g_full;   // g_full[j] = the same powers, one entry per element (resident in HBM)
+    const fe* tw_pass;  // inter-pass twiddles of this pass, one entry per output position (resident in HBM)
     fe scale;        // 1/N (inverse without coset)
     uint32_t inverse, pre_coset, post_coset, has_scale, zero_pad;
 };
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
             x = fe_zero();
         } else {
             x = ld_fe(a.in + g);
-            if (a.pre_coset) x = fe_mul<FrP>(x, pow2l(a.g_lo, a.g_hi, g));
+            if (a.pre_coset) x = fe_mul<FrP>(x, ldg_fe(a.g_full + g));
         }
         tv.st(tv.pos(r, c), x);
     }
@@ -124,15 +126,12 @@ __global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
     for (uint32_t idx = threadIdx.x; idx < T; idx += NT) {
         const uint32_t c = idx & (C - 1), k = idx >> logC;
         fe x = tv.ld(tv.pos(ntt_bitrev(k, logR), c));
-        if (p.tw_mul) {
-            const uint64_t e = ntt_tw_exponent(p, t, k, c);
-            if (e) x = fe_mul<FrP>(x, pow2l(a.w_lo, a.w_hi, e));
-        }
         uint64_t g = ntt_out_index(p, b, o, t, k, c);
+        if (p.tw_mul) x = fe_mul<FrP>(x, ldg_fe(a.tw_pass + g));
         if (p.last) {
             if (a.inverse && g) g = a.n - g;
             if (a.post_coset)
-                x = fe_mul<FrP>(x, pow2l(a.g_lo, a.g_hi, g));
+                x = fe_mul<FrP>(x, ldg_fe(a.g_full + g));
             else if (a.has_scale)
                 x = fe_mul<FrP>(x, a.scale);
         }
@@ -147,8 +146,8 @@ struct Radix3Args {
     uint64_t m, len_in;
     const fe* w_lo;
     const fe* w_hi;
-    const fe* g_lo;
-    const fe* g_hi;
+    const fe* g_full;
+    const fe* tw3;   // tw3[n] = w^n, tw3[m + n] = w^(2n)
     fe w3, w3sq;
     uint32_t pre_coset;
 };
@@ -161,7 +160,7 @@ __global__ void __launch_bounds__(256) ntt_radix3_kernel(const Radix3Args a) {
         const uint64_t g = (uint64_t)i * a.m + n;
         if (g < a.len_in) {
             x[i] = ld_fe(a.in + g);
-            if (a.pre_coset) x[i] = fe_mul<FrP>(x[i], pow2l(a.g_lo, a.g_hi, g));
+            if (a.pre_coset) x[i] = fe_mul<FrP>(x[i], ldg_fe(a.g_full + g));
         } else {
             x[i] = fe_zero();
         }
@@ -171,10 +170,8 @@ __global__ void __launch_bounds__(256) ntt_radix3_kernel(const Radix3Args a) {
     const fe b2 = fe_mul<FrP>(x[1], a.w3sq), c2 = fe_mul<FrP>(x[2], a.w3);
     fe y1 = fe_add<FrP>(fe_add<FrP>(x[0], b1), c1);
     fe y2 = fe_add<FrP>(fe_add<FrP>(x[0], b2), c2);
-    if (n) {
-        y1 = fe_mul<FrP>(y1, pow2l(a.w_lo, a.w_hi, n));
-        y2 = fe_mul<FrP>(y2, pow2l(a.w_lo, a.w_hi, 2 * n));
-    }
+    y1 = fe_mul<FrP>(y1, ldg_fe(a.tw3 + n));
+    y2 = fe_mul<FrP>(y2, ldg_fe(a.tw3 + a.m + n));
     st_fe(a.out + n, y0);
     st_fe(a.out + a.m + n, y1);
     st_fe(a.out + 2 * a.m + n, y2);
@@ -244,6 +241,32 @@ __global__ void ntt_build_pow_tables(fe base, fe premul, fe* lo, fe* hi, uint32_
         st_fe(hi + (i - nlo), fe_pow_u64<FrP>(base, (uint64_t)(i - nlo) << NTT_LOG_TWLO));
     }
 }
+// full[j] = lo[j & 4095] * hi[j >> 12]  (= premul * base^j), j < n
+__global__ void ntt_expand_pow_table(const fe* lo, const fe* hi, fe* full, uint64_t n) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) st_fe(full + j, pow2l(lo, hi, j));
+}
+// tw3[n] = w^n, tw3[m + n] = w^(2n), n < m
+__global__ void ntt_build_radix3_twiddles(const fe* lo, const fe* hi, fe* tw3, uint64_t m) {
+    const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= m) return;
+    st_fe(tw3 + n, pow2l(lo, hi, n));
+    st_fe(tw3 + m + n, pow2l(lo, hi, 2 * n));
+}
+// inter-pass twiddles of one pass, stored at the position the pass writes its result to
+__global__ void __launch_bounds__(256) ntt_build_pass_twiddles(const NttPass p, const fe* lo, const fe* hi, fe* tw) {
+    const uint32_t logR = p.logR, logC = p.logC, C = 1u << logC, T = (1u << logR) << logC;
+    uint32_t tile = blockIdx.x;
+    const uint32_t t = tile % p.inner_tiles;
+    tile /= p.inner_tiles;
+    const uint32_t o = tile % p.outer;
+    const uint32_t b = tile / p.outer;
+    for (uint32_t idx = threadIdx.x; idx < T; idx += blockDim.x) {
+        const uint32_t c = idx & (C - 1), k = idx >> logC;
+        const uint64_t e = ntt_tw_exponent(p, t, k, c);
+        st_fe(tw + ntt_out_index(p, b, o, t, k, c), pow2l(lo, hi, e));
+    }
+}
 // tab[j] = base^j, j < cnt
 __global__ void ntt_build_stage_table(fe base, fe* tab, uint32_t cnt) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,6 +316,30 @@ const NttDomain* NttEngine::domain(uint64_t n, cudaStream_t st) {
     const fe w_rtab = host_pow(d.omega, n >> log_rtab);
     ntt_build_stage_table<<<(d.n_stage + 127) / 128, 128, 0, st>>>(w_rtab, d.stage, d.n_stage);
     UZ_COUNT_LAUNCH(2);
+    // inter-pass twiddles (and the radix-3 pre-pass twiddles), one entry per element: resident in HBM
+    {
+        size_t elems = 0;
+        for (uint32_t i = 0; i < d.plan.npass; i++)
+            if (d.plan.pass[i].tw_mul) elems += n;
+        if (d.plan.mixed) elems += 2 * d.plan.m;
+        if (elems) {
+            if (cudaMalloc(&d.tw_all, sizeof(fe) * elems) != cudaSuccess) return nullptr;
+            fe* cur = d.tw_all;
+            for (uint32_t i = 0; i < d.plan.npass; i++) {
+                const NttPass& p = d.plan.pass[i];
+                if (!p.tw_mul) continue;
+                d.tw_pass[i] = cur;
+                cur += n;
+                ntt_build_pass_twiddles<<<p.inner_tiles * p.outer * p.batch, 256, 0, st>>>(p, d.w_lo, d.w_hi, d.tw_pass[i]);
+                UZ_COUNT_LAUNCH(1);
+            }
+            if (d.plan.mixed) {
+                d.tw3 = cur;
+                ntt_build_radix3_twiddles<<<(unsigned)((d.plan.m + 255) / 256), 256, 0, st>>>(d.w_lo, d.w_hi, d.tw3, d.plan.m);
+                UZ_COUNT_LAUNCH(1);
+            }
+        }
+    }
     // tables are built once; later calls may come on other streams
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
     auto res = domains_.emplace(n, d);
@@ -302,7 +349,7 @@ const NttDomain* NttEngine::domain(uint64_t n, cudaStream_t st) {
 const NttCoset* NttEngine::coset(uint64_t n, const fe& g, bool with_ninv, const NttDomain* d, cudaStream_t st) {
     for (auto& c : cosets_)
         if (c.n == n && c.with_ninv == with_ninv && fe_eq(c.g, g)) return &c;
-    if (cosets_.size() >= 16) {  // tiny FIFO cache: the prover uses one shift (k[1]) and its inverse
+    if (cosets_.size() >= 8) {  // tiny FIFO cache: the prover uses one shift (k[1]) and its inverse
         cudaStreamSynchronize(st);
         cudaFree(cosets_.front().g_lo);
         cosets_.erase(cosets_.begin());
@@ -313,11 +360,13 @@ const NttCoset* NttEngine::coset(uint64_t n, const fe& g, bool with_ninv, const 
     c.with_ninv = with_ninv;
     const uint32_t nlo = 1u << NTT_LOG_TWLO;
     c.n_hi = (uint32_t)((n >> NTT_LOG_TWLO) + 1);
-    if (cudaMalloc(&c.g_lo, sizeof(fe) * ((size_t)nlo + c.n_hi)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&c.g_lo, sizeof(fe) * ((size_t)nlo + c.n_hi + n)) != cudaSuccess) return nullptr;
     c.g_hi = c.g_lo + nlo;
+    c.g_full = c.g_hi + c.n_hi;
     const uint32_t tot = nlo + c.n_hi;
     ntt_build_pow_tables<<<(tot + 127) / 128, 128, 0, st>>>(g, with_ninv ? d->n_inv : fe_one<FrP>(), c.g_lo, c.g_hi, c.n_hi);
-    UZ_COUNT_LAUNCH(1);
+    ntt_expand_pow_table<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.g_lo, c.g_hi, c.g_full, n);
+    UZ_COUNT_LAUNCH(2);
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
     cosets_.push_back(c);
     return &cosets_.back();
@@ -364,8 +413,8 @@ int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, ui
         ra.len_in = len_in;
         ra.w_lo = d->w_lo;
         ra.w_hi = d->w_hi;
-        ra.g_lo = cs ? cs->g_lo : nullptr;
-        ra.g_hi = cs ? cs->g_hi : nullptr;
+        ra.g_full = cs ? cs->g_full : nullptr;
+        ra.tw3 = d->tw3;
         ra.w3 = d->w3;
         ra.w3sq = d->w3sq;
         ra.pre_coset = (cs && !inverse) ? 1 : 0;
@@ -389,6 +438,8 @@ int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, ui
         ka.w_hi = d->w_hi;
         ka.g_lo = cs ? cs->g_lo : nullptr;
         ka.g_hi = cs ? cs->g_hi : nullptr;
+        ka.g_full = cs ? cs->g_full : nullptr;
+        ka.tw_pass = d->tw_pass[i];
         ka.scale = d->n_inv;
         ka.inverse = inverse ? 1 : 0;
         ka.zero_pad = (!input_consumed && len_in < n) ? 1 : 0;
@@ -454,7 +505,10 @@ int NttEngine::cross(const fe* d_in, fe* d_out, uint32_t log_g, uint64_t cols, u
 }
 
 NttEngine::~NttEngine() {
-    for (auto& kv : domains_) cudaFree(kv.second.w_lo);
+    for (auto& kv : domains_) {
+        cudaFree(kv.second.w_lo);
+        if (kv.second.tw_all) cudaFree(kv.second.tw_all);
+    }
     for (auto& c : cosets_) cudaFree(c.g_lo);
 }
 
