@@ -156,8 +156,8 @@ struct MsmSrs {
 };
 
 // bucket reduction (msm_reduce.cu): workspace size for window size c, plan over fixed buffers, run
-size_t msm_reduce_workspace_bytes(uint32_t c);
-ReducePlan* msm_reduce_plan_create(uint32_t c, xyzz* buckets, void* workspace, uint32_t* ticket);
+size_t msm_reduce_workspace_bytes(uint32_t c, uint32_t sm_count);
+ReducePlan* msm_reduce_plan_create(uint32_t c, uint32_t sm_count, xyzz* buckets, void* workspace, uint32_t* ticket);
 void msm_reduce_plan_destroy(ReducePlan* p);
 int msm_reduce_run(const ReducePlan* p, jacobian* d_out, cudaStream_t st);
 

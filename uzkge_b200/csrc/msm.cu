@@ -421,7 +421,7 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     s->c = c;
     s->windows = windows;
     s->nbuckets = (1u << (c - 1)) + 1;  // 0 (zero digit, always empty) .. 2^(c-1)
-    const size_t reduce_bytes = msm_reduce_workspace_bytes(c);
+    const size_t reduce_bytes = msm_reduce_workspace_bytes(c, (uint32_t)sm_count_);
     if (reduce_bytes == 0) return UZKGE_ERR_SIZE;
     s->slots = choose_batch_slots(n, s->nbuckets, windows, reduce_bytes);
     const size_t m = (size_t)windows * n;          // entries of one full-size MSM
@@ -473,7 +473,7 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     s->buckets = (xyzz*)(base + o_buckets);
     s->cub_temp = base + o_cub;
     for (uint32_t j = 0; j < s->slots; j++) {
-        s->reduce[j] = msm_reduce_plan_create(c, s->buckets + (size_t)j * s->nbuckets, base + o_reduce + reduce_bytes * j,
+        s->reduce[j] = msm_reduce_plan_create(c, (uint32_t)sm_count_, s->buckets + (size_t)j * s->nbuckets, base + o_reduce + reduce_bytes * j,
                                               (uint32_t*)(base + o_ticket + 256 * j));
         if (!s->reduce[j]) return UZKGE_ERR_INTERNAL;
     }
