@@ -107,6 +107,19 @@ UZKGE_API int32_t uzkge_cuda_ntt_fr_device(const void* d_in, void* d_out, void* 
 UZKGE_API int32_t uzkge_cuda_ntt_cross_fr_device(const void* d_in, void* d_out, uint32_t log_ranks, size_t cols, size_t col_offset,
                                                  size_t n_total, int32_t inverse, void* stream);
 
+/* ---- polynomial glue over Fr (the prover's O(n) serial loops as scans) ----------------------------------
+ * FpPolynomial::eval (field_polynomial.rs:198-209): out = sum_j coefs[j] * x^j.  n >= 1. */
+UZKGE_API int32_t uzkge_cuda_poly_eval_fr(const uint64_t* coefs, size_t n, const uint64_t x[4], uint64_t out[4]);
+/* FpPolynomial::div_rem by the divisor (X - z) (field_polynomial.rs:519-550 as used by KZG `prove`,
+ * kzg_poly_commitment.rs:322-335): quotient holds n - 1 coefficients (untrimmed), rem = p(z). */
+UZKGE_API int32_t uzkge_cuda_poly_div_linear_fr(const uint64_t* coefs, size_t n, const uint64_t z[4], uint64_t* quotient, uint64_t rem[4]);
+/* Device-resident Horner scan: *d_value = p(z); d_quotient (n - 1 elements, may be NULL) = p / (X - z).  No copies, no sync. */
+UZKGE_API int32_t uzkge_cuda_poly_horner_fr_device(const void* d_coefs, size_t n, const uint64_t z_host[4], void* d_quotient, void* d_value,
+                                                   void* stream);
+/* The grand product of z_poly (plonk/helpers.rs:204-217: batch_inversion of the denominators, then the running product):
+ * out[0] = 1, out[i + 1] = out[i] * num[i] / den[i], i < n  (n + 1 outputs).  UZKGE_ERR_ARG if a denominator is zero. */
+UZKGE_API int32_t uzkge_cuda_grand_product_fr(const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out);
+
 /* ---- small group helpers (combine per-GPU partial MSMs; blinds) --------------------------------------
  * out = a + b on Jacobian points (host pointers, tiny device kernel).  Used for the G - 1 projective adds
  * that merge per-GPU partial sums. */

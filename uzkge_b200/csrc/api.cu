@@ -55,6 +55,7 @@ struct State {
     cudaStream_t stream = nullptr;
     std::unique_ptr<NttEngine> ntt;
     std::unique_ptr<MsmEngine> msm;
+    std::unique_ptr<PolyEngine> poly;
     std::map<uint64_t, MsmSrs> srs;
     uint64_t next_handle = 1;
     DevBuf data, scratch, scalars, small;
@@ -119,6 +120,7 @@ int ensure_init(int device) {
     g.ntt.reset(new NttEngine(g.sm_count));
     g.ntt->configure(g.ntt_log_tile, g.ntt_max_log_r, g.ntt_two_pass_max);
     g.msm.reset(new MsmEngine(g.sm_count));
+    g.poly.reset(new PolyEngine());
     g.ready = true;
     return UZKGE_OK;
 }
@@ -356,6 +358,74 @@ UZKGE_API int32_t uzkge_cuda_ntt_cross_fr_device(const void* d_in, void* d_out, 
     API_ENTER(-1);
     int rc = g.ntt->cross((const fe*)d_in, (fe*)d_out, log_ranks, cols, col_offset, n_total, inverse != 0, (cudaStream_t)stream);
     return engine_fail(rc, "ntt_cross_fr_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_poly_eval_fr(const uint64_t* coefs, size_t n, const uint64_t x[4], uint64_t out[4]) {
+    if (!coefs || !x || !out) return fail(UZKGE_ERR_ARG, "poly_eval_fr: null pointer");
+    if (n == 0) return fail(UZKGE_ERR_SIZE, "poly_eval_fr: empty coefficient vector");
+    API_ENTER(-1);
+    CUDA_OR_FAIL(g.data.reserve(n * sizeof(fe)), "poly_eval_fr: buffer");
+    CUDA_OR_FAIL(g.small.reserve(4096), "poly_eval_fr: buffer");
+    CUDA_OR_FAIL(cudaMemcpyAsync(g.data.p, coefs, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "poly_eval_fr: H2D");
+    fe z;
+    memcpy(&z, x, sizeof(fe));
+    int rc = g.poly->horner((const fe*)g.data.p, n, z, nullptr, (fe*)g.small.p, g.stream);
+    if (rc != UZKGE_OK) return engine_fail(rc, "poly_eval_fr");
+    CUDA_OR_FAIL(cudaMemcpyAsync(out, g.small.p, sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "poly_eval_fr: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "poly_eval_fr: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_poly_div_linear_fr(const uint64_t* coefs, size_t n, const uint64_t z_in[4], uint64_t* quotient, uint64_t rem[4]) {
+    if (!coefs || !z_in || !rem || (n > 1 && !quotient)) return fail(UZKGE_ERR_ARG, "poly_div_linear_fr: null pointer");
+    if (n == 0) return fail(UZKGE_ERR_SIZE, "poly_div_linear_fr: empty coefficient vector");
+    API_ENTER(-1);
+    CUDA_OR_FAIL(g.data.reserve(n * sizeof(fe)), "poly_div_linear_fr: buffer");
+    CUDA_OR_FAIL(g.scratch.reserve(n * sizeof(fe)), "poly_div_linear_fr: buffer");
+    CUDA_OR_FAIL(g.small.reserve(4096), "poly_div_linear_fr: buffer");
+    CUDA_OR_FAIL(cudaMemcpyAsync(g.data.p, coefs, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "poly_div_linear_fr: H2D");
+    fe z;
+    memcpy(&z, z_in, sizeof(fe));
+    int rc = g.poly->horner((const fe*)g.data.p, n, z, (fe*)g.scratch.p, (fe*)g.small.p, g.stream);
+    if (rc != UZKGE_OK) return engine_fail(rc, "poly_div_linear_fr");
+    if (n > 1) CUDA_OR_FAIL(cudaMemcpyAsync(quotient, g.scratch.p, (n - 1) * sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "poly_div_linear_fr: D2H");
+    CUDA_OR_FAIL(cudaMemcpyAsync(rem, g.small.p, sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "poly_div_linear_fr: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "poly_div_linear_fr: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_poly_horner_fr_device(const void* d_coefs, size_t n, const uint64_t z_host[4], void* d_quotient, void* d_value,
+                                                   void* stream) {
+    if (!d_coefs || !z_host || !d_value) return fail(UZKGE_ERR_ARG, "poly_horner_fr_device: null pointer");
+    if (n == 0) return fail(UZKGE_ERR_SIZE, "poly_horner_fr_device: empty coefficient vector");
+    API_ENTER(-1);
+    fe z;
+    memcpy(&z, z_host, sizeof(fe));
+    int rc = g.poly->horner((const fe*)d_coefs, n, z, (fe*)d_quotient, (fe*)d_value, (cudaStream_t)stream);
+    return engine_fail(rc, "poly_horner_fr_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_grand_product_fr(const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out) {
+    if (!out || (n && (!num || !den))) return fail(UZKGE_ERR_ARG, "grand_product_fr: null pointer");
+    API_ENTER(-1);
+    if (n == 0) {
+        const fe one = fe_one<FrP>();
+        memcpy(out, &one, sizeof(fe));
+        return UZKGE_OK;
+    }
+    CUDA_OR_FAIL(g.data.reserve((2 * n + 1) * sizeof(fe)), "grand_product_fr: buffer");
+    CUDA_OR_FAIL(g.scratch.reserve((2 * n + 2) * sizeof(fe)), "grand_product_fr: buffer");
+    fe* d_num = (fe*)g.data.p;
+    fe* d_den = d_num + n;
+    CUDA_OR_FAIL(cudaMemcpyAsync(d_num, num, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "grand_product_fr: H2D");
+    CUDA_OR_FAIL(cudaMemcpyAsync(d_den, den, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "grand_product_fr: H2D");
+    // the result (n + 1 elements) overwrites the inputs' buffer once they are consumed
+    int rc = g.poly->grand_product(d_num, d_den, n, d_num, (fe*)g.scratch.p, g.stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "grand_product_fr: a denominator is zero");
+    if (rc != UZKGE_OK) return engine_fail(rc, "grand_product_fr");
+    CUDA_OR_FAIL(cudaMemcpyAsync(out, d_num, (n + 1) * sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "grand_product_fr: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "grand_product_fr: execution");
+    return UZKGE_OK;
 }
 
 UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]) {

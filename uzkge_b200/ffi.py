@@ -58,6 +58,10 @@ _SIGNATURES = {
         C.c_int32,
         [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p],
     ),
+    "uzkge_cuda_poly_eval_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_poly_div_linear_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_poly_horner_fr_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_grand_product_fr": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_g1_add": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_g1_to_affine": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "uzkge_cuda_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -266,6 +270,34 @@ def ntt_cross_fr_device(d_in: int, d_out: int, log_ranks: int, cols: int, col_of
                         inverse: bool = False, stream: int = 0) -> None:
     check(lib().uzkge_cuda_ntt_cross_fr_device(d_in, d_out, log_ranks, cols, col_offset, n_total, 1 if inverse else 0, stream),
           FFTError)
+
+
+def poly_eval_fr(coefs, x) -> np.ndarray:
+    c = as_u64(coefs, 4)
+    out = np.zeros(4, dtype=np.uint64)
+    check(lib().uzkge_cuda_poly_eval_fr(ptr(c), c.shape[0], ptr(as_u64(x).reshape(4)), ptr(out)))
+    return out
+
+
+def poly_div_linear_fr(coefs, z):
+    """(quotient (n - 1, 4), remainder (4,)) of p / (X - z)."""
+    c = as_u64(coefs, 4)
+    q = np.zeros((max(c.shape[0] - 1, 0), 4), dtype=np.uint64)
+    rem = np.zeros(4, dtype=np.uint64)
+    check(lib().uzkge_cuda_poly_div_linear_fr(ptr(c), c.shape[0], ptr(as_u64(z).reshape(4)), ptr(q) if q.size else None, ptr(rem)))
+    return q, rem
+
+
+def poly_horner_fr_device(d_coefs: int, n: int, z, d_quotient: int, d_value: int, stream: int = 0) -> None:
+    check(lib().uzkge_cuda_poly_horner_fr_device(d_coefs, n, ptr(as_u64(z).reshape(4)), d_quotient or None, d_value, stream))
+
+
+def grand_product_fr(num, den) -> np.ndarray:
+    a, b = as_u64(num, 4), as_u64(den, 4)
+    assert a.shape == b.shape
+    out = np.zeros((a.shape[0] + 1, 4), dtype=np.uint64)
+    check(lib().uzkge_cuda_grand_product_fr(ptr(a), ptr(b), a.shape[0], ptr(out)))
+    return out
 
 
 def g1_add(a_jac, b_jac) -> np.ndarray:

@@ -115,6 +115,17 @@ class FpPolynomial:
     def __eq__(self, other) -> bool:
         return isinstance(other, FpPolynomial) and np.array_equal(self.coefs, other.coefs)
 
+    # ---- evaluation and division by (X - z): the serial loops of field_polynomial.rs:198-209 and :519-550 as GPU scans
+    def eval(self, point) -> np.ndarray:
+        return ffi.poly_eval_fr(self.coefs, point)
+
+    def div_rem_linear(self, z) -> tuple["FpPolynomial", "FpPolynomial"]:
+        """self.div_rem(&FpPolynomial::from_coefs(vec![-z, 1])): (quotient, remainder), both trimmed like the reference."""
+        if self.coefs.shape[0] < 2:
+            return FpPolynomial.zero(), FpPolynomial.from_coefs(self.coefs.copy())
+        q, r = ffi.poly_div_linear_fr(self.coefs, z)
+        return FpPolynomial.from_coefs(q), FpPolynomial.from_coefs(r.reshape(1, 4))
+
     # ---- domains (field_polynomial.rs:554-567)
     @staticmethod
     def evaluation_domain(num_coeffs: int):
