@@ -120,6 +120,30 @@ UZKGE_API int32_t uzkge_cuda_poly_horner_fr_device(const void* d_coefs, size_t n
  * out[0] = 1, out[i + 1] = out[i] * num[i] / den[i], i < n  (n + 1 outputs).  UZKGE_ERR_ARG if a denominator is zero. */
 UZKGE_API int32_t uzkge_cuda_grand_product_fr(const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out);
 
+/* ---- the quotient polynomial's pointwise map -------------------------------------------------------------
+ * t_poly's loop over the m = factor * n points of the coset k[1] * <w_m> (plonk/helpers.rs:284-669, the terms 1-11 that exist
+ * without the `shuffle` feature): every pointer is a DEVICE array of m Fr elements in natural order -- the coset evaluations of
+ * the wire, public-input and z polynomials (helpers.rs:256-266) and of the preprocessed polynomials in PlonkProverParams
+ * (plonk/indexer.rs:77-139).  The omega-shifted reads use index (point + factor) % m (helpers.rs:308).  z_h_inv holds the
+ * `factor` inverses of the vanishing polynomial on the coset (helpers.rs:244-253); scalars are Montgomery Fr on the host. */
+typedef struct {
+    const void* w[5];             /* w_polys_coset_evals */
+    const void* q[9];             /* q_coset_evals (N_SELECTORS = 9, constraint_system/turbo/mod.rs:23) */
+    const void* pi;               /* pi_coset_evals */
+    const void* z;                /* z_coset_evals */
+    const void* s[5];             /* s_coset_evals */
+    const void* coset_quotient;   /* k[1] * w_m^point (plonk/indexer.rs:278-282) */
+    const void* l1;               /* l1_coset_evals */
+    const void* qb;               /* qb_coset_eval */
+    const void* q_prk[4];         /* q_prk_coset_evals */
+    uint64_t k[5][4];
+    uint64_t alpha[4], beta[4], gamma[4];
+    uint64_t anemoi_generator[4], anemoi_generator_inv[4];
+    uint64_t z_h_inv[16][4];
+    size_t m, factor;
+} uzkge_quotient_args;
+UZKGE_API int32_t uzkge_cuda_plonk_quotient_fr_device(const uzkge_quotient_args* args, void* d_out, void* stream);
+
 /* ---- small group helpers (combine per-GPU partial MSMs; blinds) --------------------------------------
  * out = a + b on Jacobian points (host pointers, tiny device kernel).  Used for the G - 1 projective adds
  * that merge per-GPU partial sums. */

@@ -234,6 +234,28 @@ def test_homomorphism_degree_error_and_blinds(gpu, oc, bn):
     pcs.close()
 
 
+def test_prove_like_reference_test_eval(gpu, oc, bn):
+    """test_eval (kzg_poly_commitment.rs:550-586): prove an evaluation; with the trapdoor known the proof must equal
+    ((P(tau) - P(x)) / (tau - x)) * G, which is what the pairing check e(proof, [tau - x]_2) = e(C - P(x) G, H) verifies."""
+    from uzkge_b200 import DegreeError, FpPolynomial, KZGCommitmentSchemeBN254
+
+    srs, tau = small_srs(oc, bn, 11)
+    pcs = KZGCommitmentSchemeBN254(srs)
+    coefs = [1, 2, 3, 4, 5, 6, 7]
+    poly = FpPolynomial.from_coefs(fr(bn, coefs))
+    x = 123456789
+    xm = fr(bn, [x])[0]
+    px = sum(c * pow(x, i, bn.FR) for i, c in enumerate(coefs)) % bn.FR
+    assert bn.array_to_ints(pcs.eval(poly, xm).reshape(1, 4), bn.FR) == [px]
+    proof = pcs.prove(poly, xm, 10)
+    ptau = sum(c * pow(tau, i, bn.FR) for i, c in enumerate(coefs)) % bn.FR
+    qtau = (ptau - px) * bn.inv_mod((tau - x) % bn.FR, bn.FR) % bn.FR
+    assert bn.array_to_affine(proof.to_affine().reshape(1, 8))[0] == bn.g1_mul(bn.G1_GEN, qtau)
+    with pytest.raises(DegreeError):
+        pcs.prove(poly, xm, 5)   # "wrong degree" branch of the reference test
+    pcs.close()
+
+
 def test_full_size_trapdoor_property(gpu, oc, bn):
     """BASELINE size 2^20 through a size-independent property: for bases P_i = P0 + i*Q,
     sum s_i P_i = (sum s_i) P0 + (sum i s_i) Q  (two scalar multiplications on the CPU)."""

@@ -428,6 +428,14 @@ UZKGE_API int32_t uzkge_cuda_grand_product_fr(const uint64_t* num, const uint64_
     return UZKGE_OK;
 }
 
+UZKGE_API int32_t uzkge_cuda_plonk_quotient_fr_device(const uzkge_quotient_args* args, void* d_out, void* stream) {
+    API_ENTER(-1);
+    int rc = plonk_quotient_run(args, d_out, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "plonk_quotient_fr_device: null pointer");
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "plonk_quotient_fr_device: m must be a multiple of factor, 1 <= factor <= 16");
+    return engine_fail(rc, "plonk_quotient_fr_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]) {
     if (!out) return fail(UZKGE_ERR_ARG, "fr_root_of_unity: null pointer");
     bool ok = false;

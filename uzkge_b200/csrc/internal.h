@@ -200,6 +200,9 @@ private:
     size_t ws_cap_ = 0;
 };
 
+// ---------------------------------------------------------------- PlonK quotient map (quotient.cu)
+int plonk_quotient_run(const uzkge_quotient_args* args, void* d_out, cudaStream_t st);
+
 static inline int cuda_err_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? UZKGE_ERR_OOM : UZKGE_ERR_CUDA; }
 
 }  // namespace uz

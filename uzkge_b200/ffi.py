@@ -33,6 +33,31 @@ class SrsInfo(C.Structure):
     ]
 
 
+class QuotientArgs(C.Structure):
+    """uzkge_quotient_args (include/uzkge_cuda.h)."""
+
+    _fields_ = [
+        ("w", C.c_void_p * 5),
+        ("q", C.c_void_p * 9),
+        ("pi", C.c_void_p),
+        ("z", C.c_void_p),
+        ("s", C.c_void_p * 5),
+        ("coset_quotient", C.c_void_p),
+        ("l1", C.c_void_p),
+        ("qb", C.c_void_p),
+        ("q_prk", C.c_void_p * 4),
+        ("k", (C.c_uint64 * 4) * 5),
+        ("alpha", C.c_uint64 * 4),
+        ("beta", C.c_uint64 * 4),
+        ("gamma", C.c_uint64 * 4),
+        ("anemoi_generator", C.c_uint64 * 4),
+        ("anemoi_generator_inv", C.c_uint64 * 4),
+        ("z_h_inv", (C.c_uint64 * 4) * 16),
+        ("m", C.c_size_t),
+        ("factor", C.c_size_t),
+    ]
+
+
 _SIGNATURES = {
     "uzkge_cuda_init": (C.c_int32, [C.c_int32]),
     "uzkge_cuda_device_count": (C.c_int32, []),
@@ -62,6 +87,7 @@ _SIGNATURES = {
     "uzkge_cuda_poly_div_linear_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_poly_horner_fr_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_grand_product_fr": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uzkge_cuda_plonk_quotient_fr_device": (C.c_int32, [C.POINTER(QuotientArgs), C.c_void_p, C.c_void_p]),
     "uzkge_cuda_g1_add": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_g1_to_affine": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "uzkge_cuda_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -298,6 +324,28 @@ def grand_product_fr(num, den) -> np.ndarray:
     out = np.zeros((a.shape[0] + 1, 4), dtype=np.uint64)
     check(lib().uzkge_cuda_grand_product_fr(ptr(a), ptr(b), a.shape[0], ptr(out)))
     return out
+
+
+def plonk_quotient_fr_device(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, alpha, beta, gamma, anemoi_g, anemoi_g_inv,
+                             z_h_inv, m: int, factor: int, d_out: int, stream: int = 0) -> None:
+    """Device pointers (ints) for the arrays, numpy Montgomery limbs for the scalars; see uzkge_quotient_args."""
+    a = QuotientArgs()
+    for j in range(5):
+        a.w[j], a.s[j] = w[j], s[j]
+        a.k[j][:] = [int(v) for v in as_u64(k[j]).reshape(4)]
+    for j in range(9):
+        a.q[j] = q[j]
+    for j in range(4):
+        a.q_prk[j] = q_prk[j]
+    a.pi, a.z, a.coset_quotient, a.l1, a.qb = pi, z, coset_quotient, l1, qb
+    for name, v in (("alpha", alpha), ("beta", beta), ("gamma", gamma), ("anemoi_generator", anemoi_g),
+                    ("anemoi_generator_inv", anemoi_g_inv)):
+        getattr(a, name)[:] = [int(x) for x in as_u64(v).reshape(4)]
+    zh = as_u64(z_h_inv, 4)
+    for i in range(zh.shape[0]):
+        a.z_h_inv[i][:] = [int(x) for x in zh[i]]
+    a.m, a.factor = m, factor
+    check(lib().uzkge_cuda_plonk_quotient_fr_device(C.byref(a), d_out, stream))
 
 
 def g1_add(a_jac, b_jac) -> np.ndarray:

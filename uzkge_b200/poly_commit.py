@@ -255,6 +255,19 @@ class KZGCommitmentSchemeBN254:
         out = ffi.msm_g1_batch(self._handle, vecs)
         return [KZGCommitment(o) for o in out]
 
+    def eval(self, poly: FpPolynomial, point) -> np.ndarray:
+        """PolyComScheme::eval (kzg_poly_commitment.rs:295-297)."""
+        return poly.eval(point)
+
+    def prove(self, poly: FpPolynomial, x, max_degree: int) -> KZGCommitment:
+        """PolyComScheme::prove (kzg_poly_commitment.rs:315-342): the commitment of (P(X) - P(x)) / (X - x).
+        Evaluation, division and commitment all run on the GPU (Horner scan + MSM); the division's remainder is
+        P(x), so the quotient of P itself by (X - x) equals the quotient of P - P(x)."""
+        if poly.degree() > max_degree:
+            raise DegreeError("DegreeError")
+        q, _r = poly.div_rem_linear(x)
+        return self.commit(q)
+
     def apply_blind_factors(self, commitment: KZGCommitment, blinds, zeroing_degree: int) -> KZGCommitment:
         """kzg_poly_commitment.rs:299-313: C + sum_i b_i * (SRS[i] - SRS[zeroing_degree + i]), as two tiny MSMs
         over the resident bases (the negation is folded into the scalars)."""
