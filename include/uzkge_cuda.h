@@ -144,6 +144,37 @@ typedef struct {
 } uzkge_quotient_args;
 UZKGE_API int32_t uzkge_cuda_plonk_quotient_fr_device(const uzkge_quotient_args* args, void* d_out, void* stream);
 
+/* ---- elementwise glue of a device-resident prover; DEVICE pointers, caller's stream, no copies, no sync ------
+ * out[i] = sum_{j < k} coefs[j] * polys[j][i] for i < out_len, where polys[j][i] = 0 for i >= lens[j]; coefs: k Montgomery Fr on
+ * the HOST.  Replaces the mul / add_assign chains of r_poly_or_comm (plonk/helpers.rs:716-745, 986-993) and of batch_prove
+ * (poly_commit/pcs.rs:124-131).  d_out may alias one of the inputs.  1 <= k <= UZKGE_LINCOMB_MAX. */
+#define UZKGE_LINCOMB_MAX 24
+UZKGE_API int32_t uzkge_cuda_fr_lincomb_device(const void* const* d_polys, const size_t* lens, const uint64_t* coefs_host, size_t k,
+                                               void* d_out, size_t out_len, void* stream);
+/* poly[idx[j]] += vals[j], j < k <= UZKGE_SPARSE_MAX, applied in order (indices may repeat): FpPolynomial::add_coef_assign as used by
+ * hide_polynomial (plonk/helpers.rs:139-154) and split_t_and_commit (helpers.rs:1351-1361). */
+#define UZKGE_SPARSE_MAX 16
+UZKGE_API int32_t uzkge_cuda_fr_add_sparse_device(void* d_poly, const size_t* idx, const uint64_t* vals_host, size_t k, void* stream);
+/* out[i] = scale * base^i, i < n (scale NULL = 1): `domain.elements()` and the coset k[1] * w_m^i (plonk/indexer.rs:276-282). */
+UZKGE_API int32_t uzkge_cuda_fr_powers_device(const uint64_t base_host[4], const uint64_t* scale_host, size_t n, void* d_out, void* stream);
+/* out[i] = src[idx[i]], idx: n uint32 on the device: ConstraintSystem::extend_witness (plonk/constraint_system/mod.rs:103-111). */
+UZKGE_API int32_t uzkge_cuda_fr_gather_device(const void* d_src, const void* d_idx_u32, size_t n, void* d_out, void* stream);
+/* out[i] = a[i] * b[i], i < n (witness generation of synthetic circuits; FpPolynomial's pointwise products). */
+UZKGE_API int32_t uzkge_cuda_fr_mul_device(const void* d_a, const void* d_b, size_t n, void* d_out, void* stream);
+/* *len_out = number of coefficients after FpPolynomial::from_coefs' trailing-zero trim (field_polynomial.rs:86-90): 1 + the largest
+ * index holding a non-zero element, 0 for the zero vector.  Synchronises the stream (the prover's split_t_and_commit branches on it,
+ * plonk/helpers.rs:1334-1347). */
+UZKGE_API int32_t uzkge_cuda_fr_trimmed_len_device(const void* d_poly, size_t n, size_t* len_out, void* stream);
+/* Device-resident grand product (see uzkge_cuda_grand_product_fr): d_out holds n + 1 elements, d_tmp 2 n + 2.  Synchronises the
+ * stream once (the single field inversion runs on the host). */
+UZKGE_API int32_t uzkge_cuda_grand_product_fr_device(const void* d_num, const void* d_den, size_t n, void* d_out, void* d_tmp, void* stream);
+/* z_poly's evaluations (plonk/helpers.rs:160-220) from device-resident inputs: d_w[j] / d_sigma[j] = the n values of wire j and of
+ * its encoded permutation k_j' * w^i' (indexer.rs:195-208, :305-313), d_group = w^i; k: 5 Montgomery Fr on the host.
+ * d_z[0] = 1, d_z[i + 1] = d_z[i] * prod_j (w_j + beta k_j w^i + gamma) / prod_j (w_j + beta sigma_j + gamma);  d_tmp: 4 n elements. */
+UZKGE_API int32_t uzkge_cuda_plonk_z_evals_fr_device(const void* const d_w[5], const void* const d_sigma[5], const void* d_group,
+                                                     const uint64_t* k_host, const uint64_t beta_host[4], const uint64_t gamma_host[4], size_t n,
+                                                     void* d_z, void* d_tmp, void* stream);
+
 /* ---- small group helpers (combine per-GPU partial MSMs; blinds) --------------------------------------
  * out = a + b on Jacobian points (host pointers, tiny device kernel).  Used for the G - 1 projective adds
  * that merge per-GPU partial sums. */

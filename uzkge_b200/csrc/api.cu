@@ -436,6 +436,70 @@ UZKGE_API int32_t uzkge_cuda_plonk_quotient_fr_device(const uzkge_quotient_args*
     return engine_fail(rc, "plonk_quotient_fr_device");
 }
 
+UZKGE_API int32_t uzkge_cuda_fr_lincomb_device(const void* const* d_polys, const size_t* lens, const uint64_t* coefs_host, size_t k,
+                                               void* d_out, size_t out_len, void* stream) {
+    API_ENTER(-1);
+    int rc = fr_lincomb_run(d_polys, lens, coefs_host, k, d_out, out_len, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_lincomb_device: null pointer");
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "fr_lincomb_device: 1 <= k <= UZKGE_LINCOMB_MAX");
+    return engine_fail(rc, "fr_lincomb_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_fr_add_sparse_device(void* d_poly, const size_t* idx, const uint64_t* vals_host, size_t k, void* stream) {
+    API_ENTER(-1);
+    int rc = fr_add_sparse_run(d_poly, idx, vals_host, k, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_add_sparse_device: null pointer");
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "fr_add_sparse_device: k <= UZKGE_SPARSE_MAX");
+    return engine_fail(rc, "fr_add_sparse_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_fr_powers_device(const uint64_t base_host[4], const uint64_t* scale_host, size_t n, void* d_out, void* stream) {
+    API_ENTER(-1);
+    int rc = fr_powers_run(base_host, scale_host, n, d_out, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_powers_device: null pointer");
+    return engine_fail(rc, "fr_powers_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_fr_gather_device(const void* d_src, const void* d_idx_u32, size_t n, void* d_out, void* stream) {
+    API_ENTER(-1);
+    int rc = fr_gather_run(d_src, d_idx_u32, n, d_out, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_gather_device: null pointer");
+    return engine_fail(rc, "fr_gather_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_fr_mul_device(const void* d_a, const void* d_b, size_t n, void* d_out, void* stream) {
+    API_ENTER(-1);
+    int rc = fr_mul_run(d_a, d_b, n, d_out, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_mul_device: null pointer");
+    return engine_fail(rc, "fr_mul_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_fr_trimmed_len_device(const void* d_poly, size_t n, size_t* len_out, void* stream) {
+    API_ENTER(-1);
+    CUDA_OR_FAIL(g.small.reserve(4096), "fr_trimmed_len_device: buffer");
+    int rc = fr_trimmed_len_run(d_poly, n, (unsigned long long*)g.small.p, len_out, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_trimmed_len_device: null pointer");
+    return engine_fail(rc, "fr_trimmed_len_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_grand_product_fr_device(const void* d_num, const void* d_den, size_t n, void* d_out, void* d_tmp, void* stream) {
+    if (!d_num || !d_den || !d_out || !d_tmp) return fail(UZKGE_ERR_ARG, "grand_product_fr_device: null pointer");
+    API_ENTER(-1);
+    int rc = g.poly->grand_product((const fe*)d_num, (const fe*)d_den, n, (fe*)d_out, (fe*)d_tmp, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "grand_product_fr_device: a denominator is zero");
+    return engine_fail(rc, "grand_product_fr_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_plonk_z_evals_fr_device(const void* const d_w[5], const void* const d_sigma[5], const void* d_group,
+                                                     const uint64_t* k_host, const uint64_t beta_host[4], const uint64_t gamma_host[4], size_t n,
+                                                     void* d_z, void* d_tmp, void* stream) {
+    API_ENTER(-1);
+    int rc = plonk_z_evals_run(g.poly.get(), d_w, d_sigma, d_group, k_host, beta_host, gamma_host, n, d_z, d_tmp, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "plonk_z_evals_fr_device: null pointer or zero denominator");
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "plonk_z_evals_fr_device: n >= 2");
+    return engine_fail(rc, "plonk_z_evals_fr_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]) {
     if (!out) return fail(UZKGE_ERR_ARG, "fr_root_of_unity: null pointer");
     bool ok = false;

@@ -203,6 +203,16 @@ private:
 // ---------------------------------------------------------------- PlonK quotient map (quotient.cu)
 int plonk_quotient_run(const uzkge_quotient_args* args, void* d_out, cudaStream_t st);
 
+// ---------------------------------------------------------------- elementwise prover glue (plonk_glue.cu)
+int fr_lincomb_run(const void* const* d_polys, const size_t* lens, const uint64_t* coefs, size_t k, void* d_out, size_t out_len, cudaStream_t st);
+int fr_add_sparse_run(void* d_poly, const size_t* idx, const uint64_t* vals, size_t k, cudaStream_t st);
+int fr_powers_run(const uint64_t* base, const uint64_t* scale, size_t n, void* d_out, cudaStream_t st);
+int fr_gather_run(const void* d_src, const void* d_idx, size_t n, void* d_out, cudaStream_t st);
+int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out, cudaStream_t st);
+int fr_trimmed_len_run(const void* d_poly, size_t n, unsigned long long* d_scratch, size_t* len_out, cudaStream_t st);
+int plonk_z_evals_run(PolyEngine* poly, const void* const d_w[5], const void* const d_sigma[5], const void* d_group, const uint64_t* k,
+                      const uint64_t* beta, const uint64_t* gamma, size_t n, void* d_z, void* d_tmp, cudaStream_t st);
+
 static inline int cuda_err_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? UZKGE_ERR_OOM : UZKGE_ERR_CUDA; }
 
 }  // namespace uz

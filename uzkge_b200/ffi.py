@@ -88,6 +88,21 @@ _SIGNATURES = {
     "uzkge_cuda_poly_horner_fr_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_grand_product_fr": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_plonk_quotient_fr_device": (C.c_int32, [C.POINTER(QuotientArgs), C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_fr_lincomb_device": (
+        C.c_int32,
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
+    "uzkge_cuda_fr_add_sparse_device": (C.c_int32, [C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uzkge_cuda_fr_powers_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_fr_gather_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_fr_mul_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_fr_trimmed_len_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]),
+    "uzkge_cuda_grand_product_fr_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_plonk_z_evals_fr_device": (
+        C.c_int32,
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+         C.c_void_p, C.c_void_p],
+    ),
     "uzkge_cuda_g1_add": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_g1_to_affine": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "uzkge_cuda_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -346,6 +361,66 @@ def plonk_quotient_fr_device(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, a
         a.z_h_inv[i][:] = [int(x) for x in zh[i]]
     a.m, a.factor = m, factor
     check(lib().uzkge_cuda_plonk_quotient_fr_device(C.byref(a), d_out, stream))
+
+
+LINCOMB_MAX = 24
+SPARSE_MAX = 16
+
+
+def fr_lincomb_device(d_polys, lens, coefs, d_out: int, out_len: int, stream: int = 0) -> None:
+    """out[i] = sum_j coefs[j] * polys[j][i]  (device pointers as ints; coefs: (k, 4) Montgomery limbs on the host)."""
+    k = len(d_polys)
+    c = as_u64(coefs, 4)
+    assert c.shape[0] == k == len(lens)
+    pp = (C.c_void_p * k)(*[int(x) for x in d_polys])
+    ll = (C.c_size_t * k)(*[int(x) for x in lens])
+    check(lib().uzkge_cuda_fr_lincomb_device(pp, ll, ptr(c), k, d_out, out_len, stream))
+
+
+def fr_add_sparse_device(d_poly: int, idx, vals, stream: int = 0) -> None:
+    """poly[idx[j]] += vals[j] in order."""
+    k = len(idx)
+    if k == 0:
+        return
+    v = as_u64(vals, 4)
+    assert v.shape[0] == k
+    ii = (C.c_size_t * k)(*[int(x) for x in idx])
+    check(lib().uzkge_cuda_fr_add_sparse_device(d_poly, ii, ptr(v), k, stream))
+
+
+def fr_powers_device(base, n: int, d_out: int, scale=None, stream: int = 0) -> None:
+    """out[i] = scale * base^i."""
+    b = as_u64(base).reshape(4)
+    sc = None if scale is None else as_u64(scale).reshape(4)
+    check(lib().uzkge_cuda_fr_powers_device(ptr(b), None if sc is None else ptr(sc), n, d_out, stream))
+
+
+def fr_gather_device(d_src: int, d_idx_u32: int, n: int, d_out: int, stream: int = 0) -> None:
+    check(lib().uzkge_cuda_fr_gather_device(d_src, d_idx_u32, n, d_out, stream))
+
+
+def fr_mul_device(d_a: int, d_b: int, n: int, d_out: int, stream: int = 0) -> None:
+    check(lib().uzkge_cuda_fr_mul_device(d_a, d_b, n, d_out, stream))
+
+
+def fr_trimmed_len_device(d_poly: int, n: int, stream: int = 0) -> int:
+    """Length after FpPolynomial::from_coefs' trim (0 for the zero vector).  Synchronises the stream."""
+    v = C.c_size_t(0)
+    check(lib().uzkge_cuda_fr_trimmed_len_device(d_poly, n, C.byref(v), stream))
+    return int(v.value)
+
+
+def grand_product_fr_device(d_num: int, d_den: int, n: int, d_out: int, d_tmp: int, stream: int = 0) -> None:
+    check(lib().uzkge_cuda_grand_product_fr_device(d_num, d_den, n, d_out, d_tmp, stream))
+
+
+def plonk_z_evals_fr_device(d_w, d_sigma, d_group: int, k, beta, gamma, n: int, d_z: int, d_tmp: int, stream: int = 0) -> None:
+    ww = (C.c_void_p * 5)(*[int(x) for x in d_w])
+    ss = (C.c_void_p * 5)(*[int(x) for x in d_sigma])
+    kk = as_u64(k, 4)
+    assert kk.shape[0] == 5
+    check(lib().uzkge_cuda_plonk_z_evals_fr_device(ww, ss, d_group, ptr(kk), ptr(as_u64(beta).reshape(4)), ptr(as_u64(gamma).reshape(4)),
+                                                   n, d_z, d_tmp, stream))
 
 
 def g1_add(a_jac, b_jac) -> np.ndarray:

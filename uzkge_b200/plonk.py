@@ -1,0 +1,753 @@
+"""Device-resident TurboPlonK prover: the host-side mirror of the reference's `plonk` module on top of the C ABI.
+
+No Rust toolchain exists in this image, so what in production is the patched body of `prover_with_lagrange` is restated here in
+Python with the reference's names and order of operations (the RNG draws and transcript appends are order-sensitive):
+
+  TurboCS (the gates a synthetic circuit needs)  /root/reference/uzkge/src/plonk/constraint_system/turbo/mod.rs:395-537, 853-891, 968-977
+  compute_permutation / extend_witness           /root/reference/uzkge/src/plonk/constraint_system/mod.rs:54-84, 103-111
+  indexer                                        /root/reference/uzkge/src/plonk/indexer.rs:248-536   (default features: no `shuffle`)
+  prover                                         /root/reference/uzkge/src/plonk/prover.rs:76-394     (lagrange_pcs = None)
+  pi_poly, hide_polynomial, z_poly, t_poly,
+  r_poly, split_t_and_commit, first_lagrange_poly /root/reference/uzkge/src/plonk/helpers.rs:111-131, 139-154, 160-220, 223-678, 681-999,
+                                                 1323-1408, 1412-1423
+  batch_prove                                    /root/reference/uzkge/src/poly_commit/pcs.rs:107-168
+
+Every polynomial lives in HBM as 4 x u64 Montgomery limbs per coefficient (arkworks' layout) between the rounds; transforms, MSMs,
+scans and the pointwise maps are the library's CUDA kernels; the host does the Fiat-Shamir transcript, the RNG and O(1) scalar
+arithmetic per round (Python integers).  Only 64-byte commitments and 32-byte evaluations cross PCIe.  torch is used for device
+allocations and device-to-device slice copies only.  There is no CPU path: without the CUDA library every step raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import ffi
+from .errors import DegreeError, ParameterError, UzkgeError
+from .poly_commit import FR_MODULUS, KZGCommitment, KZGCommitmentSchemeBN254
+from .rng import ChaChaRng, choose_ks, fr_rand
+from .transcript import Transcript, init_pcs_batch_eval_transcript, transcript_init_plonk
+
+N_WIRES_PER_GATE = 5
+N_SELECTORS = 9
+_R = (1 << 256) % FR_MODULUS
+_R_INV = pow(_R, -1, FR_MODULUS)
+_M64 = 0xFFFFFFFFFFFFFFFF
+
+
+# ---------------------------------------------------------------------------------------------- scalars
+def mont(x: int) -> np.ndarray:
+    """Canonical integer -> 4 Montgomery limbs."""
+    v = x % FR_MODULUS * _R % FR_MODULUS
+    return np.array([(v >> (64 * i)) & _M64 for i in range(4)], dtype=np.uint64)
+
+
+def mont_rows(xs) -> np.ndarray:
+    return np.stack([mont(x) for x in xs]) if len(xs) else np.zeros((0, 4), dtype=np.uint64)
+
+
+def unmont(row) -> int:
+    """4 Montgomery limbs -> canonical integer."""
+    v = int(row[0]) | (int(row[1]) << 64) | (int(row[2]) << 128) | (int(row[3]) << 192)
+    return v * _R_INV % FR_MODULUS
+
+
+_ZERO, _ONE = mont(0), mont(1)
+
+
+# ---------------------------------------------------------------------------------------------- device vectors
+class DevVec:
+    """`cap` field elements in HBM (a torch int64 tensor of 4 * cap words); `len` = coefficients in use."""
+
+    def __init__(self, cap: int, device, zero: bool = True, length: int | None = None):
+        alloc = torch.zeros if zero else torch.empty
+        self.t = alloc(4 * max(cap, 1), dtype=torch.int64, device=device)
+        self.cap = cap
+        self.len = cap if length is None else length
+
+    @classmethod
+    def from_numpy(cls, a: np.ndarray, device, cap: int | None = None) -> "DevVec":
+        a = ffi.as_u64(a, 4)
+        v = cls(max(cap or 0, a.shape[0]), device, zero=cap is not None and cap > a.shape[0], length=a.shape[0])
+        v.t[: 4 * a.shape[0]].copy_(torch.from_numpy(a.view(np.int64).reshape(-1)))
+        return v
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+    def at(self, i: int) -> int:
+        return self.t.data_ptr() + 32 * i
+
+    def numpy(self, n: int | None = None) -> np.ndarray:
+        n = self.len if n is None else n
+        return self.t[: 4 * n].cpu().numpy().view(np.uint64).reshape(n, 4)
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------------------------- TurboCS
+class TurboCS:
+    """constraint_system/turbo/mod.rs.  Gates are appended one by one (Python lists) or in bulk (`synthetic`); `pad()` freezes
+    the circuit into numpy arrays: selectors (9, n, 4) Montgomery limbs, wiring (5, n) uint32."""
+
+    def __init__(self):
+        self._sel = [[] for _ in range(N_SELECTORS)]     # small codes: index into _sel_values
+        self._sel_values: list[int] = []
+        self._sel_index: dict[int, int] = {}
+        self._wir = [[] for _ in range(N_WIRES_PER_GATE)]
+        self.num_vars = 2
+        self.size = 0
+        self.witness: list[int] | None = [0, 1]
+        self.witness_array: np.ndarray | None = None
+        self.public_vars_constraint_indices: list[int] = []
+        self.public_vars_witness_indices: list[int] = []
+        self.boolean_constraint_indices: list[int] = []
+        self.selectors: np.ndarray | None = None
+        self.wiring: np.ndarray | None = None
+        self.verifier_only = False
+        self.insert_constant_gate(self.zero_var(), 0)
+        self.insert_constant_gate(self.one_var(), 1)
+
+    # ---- ConstraintSystem trait
+    @staticmethod
+    def n_wires_per_gate() -> int:
+        return N_WIRES_PER_GATE
+
+    @staticmethod
+    def num_selectors() -> int:
+        return N_SELECTORS
+
+    def quot_eval_dom_size(self) -> int:
+        return self.size * 6 if self.size > 8 else self.size * 16
+
+    @staticmethod
+    def get_hiding_degree(idx: int) -> int:
+        return 3 if idx < 3 else 2
+
+    def is_verifier_only(self) -> bool:
+        return self.verifier_only
+
+    def zero_var(self) -> int:
+        return 0
+
+    def one_var(self) -> int:
+        return 1
+
+    def _code(self, v: int) -> int:
+        v %= FR_MODULUS
+        c = self._sel_index.get(v)
+        if c is None:
+            c = len(self._sel_values)
+            self._sel_index[v] = c
+            self._sel_values.append(v)
+        return c
+
+    def _push_gate(self, q_add, q_mul, q_c, q_ecc, q_out, wires) -> None:
+        if self.selectors is not None:
+            raise UzkgeError("the circuit is frozen (pad() was called)")
+        if any(w >= self.num_vars for w in wires):
+            raise ParameterError("wire index out of bound")
+        vals = list(q_add) + list(q_mul) + [q_c, q_ecc, q_out]
+        for j in range(N_SELECTORS):
+            self._sel[j].append(self._code(vals[j]))
+        for j in range(N_WIRES_PER_GATE):
+            self._wir[j].append(wires[j])
+        self.size += 1
+
+    def new_variable(self, value: int) -> int:
+        self.num_vars += 1
+        self.witness.append(value % FR_MODULUS)
+        return self.num_vars - 1
+
+    def add_variables(self, values) -> None:
+        for v in values:
+            self.new_variable(v)
+
+    def insert_lc_gate(self, wires_in, wire_out: int, q1: int, q2: int, q3: int, q4: int) -> None:
+        self._push_gate((q1, q2, q3, q4), (0, 0), 0, 0, 1, list(wires_in) + [wire_out])
+
+    def insert_add_gate(self, left_var: int, right_var: int, out_var: int) -> None:
+        self.insert_lc_gate((left_var, right_var, 0, 0), out_var, 1, 1, 0, 0)
+
+    def insert_sub_gate(self, left_var: int, right_var: int, out_var: int) -> None:
+        self.insert_lc_gate((left_var, right_var, 0, 0), out_var, 1, FR_MODULUS - 1, 0, 0)
+
+    def insert_mul_gate(self, left_var: int, right_var: int, out_var: int) -> None:
+        self._push_gate((0, 0, 0, 0), (1, 0), 0, 0, 1, [left_var, right_var, 0, 0, out_var])
+
+    def insert_constant_gate(self, var: int, constant: int) -> None:
+        self._push_gate((0, 0, 0, 0), (0, 0), constant, 0, 1, [var] * N_WIRES_PER_GATE)
+
+    def insert_boolean_gate(self, var: int) -> None:
+        self.insert_mul_gate(var, var, var)
+
+    def prepare_pi_variable(self, var: int) -> None:
+        self.public_vars_witness_indices.append(var)
+        self.public_vars_constraint_indices.append(self.size)
+        self.insert_constant_gate(var, 0)
+
+    def attach_boolean_constraint_to_gate(self) -> None:
+        self.boolean_constraint_indices.append(self.size - 1)
+
+    def add(self, left_var: int, right_var: int) -> int:
+        out = self.new_variable(self.witness[left_var] + self.witness[right_var])
+        self.insert_add_gate(left_var, right_var, out)
+        return out
+
+    def sub(self, left_var: int, right_var: int) -> int:
+        out = self.new_variable(self.witness[left_var] - self.witness[right_var])
+        self.insert_sub_gate(left_var, right_var, out)
+        return out
+
+    def mul(self, left_var: int, right_var: int) -> int:
+        out = self.new_variable(self.witness[left_var] * self.witness[right_var])
+        self.insert_mul_gate(left_var, right_var, out)
+        return out
+
+    def equal(self, left_var: int, right_var: int) -> None:
+        self.insert_sub_gate(left_var, right_var, self.zero_var())
+
+    def pad(self) -> None:
+        """turbo/mod.rs:968-977 (zero selectors, wires on variable 0), then freeze into arrays."""
+        n = 1
+        while n < self.size:
+            n *= 2
+        table = mont_rows(self._sel_values + [0])
+        zero_code = len(self._sel_values)
+        sel = np.full((N_SELECTORS, n), zero_code, dtype=np.int64)
+        wir = np.zeros((N_WIRES_PER_GATE, n), dtype=np.uint32)
+        for j in range(N_SELECTORS):
+            sel[j, : self.size] = self._sel[j]
+        for j in range(N_WIRES_PER_GATE):
+            wir[j, : self.size] = self._wir[j]
+        self.selectors = table[sel]
+        self.wiring = wir
+        self.size = n
+        self._sel = self._wir = None
+
+    def get_witness_array(self) -> np.ndarray:
+        """The witness as (num_vars, 4) Montgomery limbs."""
+        if self.witness_array is None:
+            self.witness_array = mont_rows(self.witness)
+        return self.witness_array
+
+    def compute_permutation(self) -> np.ndarray:
+        """constraint_system/mod.rs:54-84: every variable's positions (wire-major order) form one cycle, each position pointing to
+        the next larger one and the last back to the first.  (The reference's loop is quadratic; this is the same map, sorted.)"""
+        v = self.wiring.reshape(-1).astype(np.int64)
+        order = np.argsort(v, kind="stable")
+        sv = v[order]
+        last_of_group = np.ones(len(v), dtype=bool)
+        last_of_group[:-1] = sv[1:] != sv[:-1]
+        first_of_group = np.ones(len(v), dtype=bool)
+        first_of_group[1:] = sv[1:] != sv[:-1]
+        group_start = np.maximum.accumulate(np.where(first_of_group, np.arange(len(v)), 0))
+        nxt = np.empty(len(v), dtype=np.int64)
+        nxt[:-1] = order[1:]
+        nxt[last_of_group] = order[group_start[last_of_group]]
+        perm = np.empty(len(v), dtype=np.int64)
+        perm[order] = nxt
+        return perm
+
+    @classmethod
+    def synthetic(cls, log_size: int, seed: int = 0xB2000004, layers: int = 8) -> "TurboCS":
+        """a satisfied circuit of 2^log_size gates made of insert_add_gate / insert_mul_gate (turbo/mod.rs:481-522) in
+        `layers` layers, every gate reading two outputs of the previous layer (so the copy constraints are not trivial).  The
+        witness is evaluated layer by layer on the GPU (gather, pointwise product, sum).  No public inputs."""
+        n = 1 << log_size
+        cs = cls()
+        rng = np.random.default_rng(seed)
+        g = n - cs.size                      # gates to add; the two constant gates of `new` come first
+        per = [g // layers + (1 if i < g % layers else 0) for i in range(layers)]
+        dev = _dev()
+        n_inputs = max(per[0], 2)
+        inputs = _random_fr(n_inputs, seed ^ 0x5EED)
+        n_vars = 2 + n_inputs + g
+        wit = DevVec(n_vars, dev)
+        head = np.concatenate([np.stack([_ZERO, _ONE]), inputs])
+        wit.t[: 4 * head.shape[0]].copy_(torch.from_numpy(head.view(np.int64).reshape(-1)))
+        sel = np.zeros((N_SELECTORS, n), dtype=np.int8)     # codes: 0 -> 0, 1 -> 1
+        wir = np.zeros((N_WIRES_PER_GATE, n), dtype=np.uint32)
+        sel[6, 1] = 1                                        # constant gates of TurboCS::new: q_c = 0, 1; q_out = 1
+        sel[8, :2] = 1
+        wir[:, 1] = 1
+        prev_lo, prev_n = 2, n_inputs
+        row, var = 2, 2 + n_inputs
+        ones = np.stack([_ONE, _ONE])
+        for cnt in per:
+            if cnt == 0:
+                continue
+            a = (prev_lo + rng.integers(0, prev_n, cnt)).astype(np.uint32)
+            b = (prev_lo + rng.integers(0, prev_n, cnt)).astype(np.uint32)
+            is_mul = rng.integers(0, 2, cnt).astype(bool)
+            out = np.arange(var, var + cnt, dtype=np.uint32)
+            wir[0, row:row + cnt], wir[1, row:row + cnt], wir[4, row:row + cnt] = a, b, out
+            sel[0, row:row + cnt] = sel[1, row:row + cnt] = ~is_mul
+            sel[4, row:row + cnt] = is_mul
+            sel[8, row:row + cnt] = 1
+            da, db = DevVec(cnt, dev, zero=False), DevVec(cnt, dev, zero=False)
+            ia, ib = torch.from_numpy(a.view(np.int32)).to(dev), torch.from_numpy(b.view(np.int32)).to(dev)
+            ffi.fr_gather_device(wit.ptr, ia.data_ptr(), cnt, da.ptr)
+            ffi.fr_gather_device(wit.ptr, ib.data_ptr(), cnt, db.ptr)
+            prod, summ = DevVec(cnt, dev, zero=False), DevVec(cnt, dev, zero=False)
+            ffi.fr_mul_device(da.ptr, db.ptr, cnt, prod.ptr)
+            ffi.fr_lincomb_device([da.ptr, db.ptr], [cnt, cnt], ones, summ.ptr, cnt)
+            m = torch.from_numpy(is_mul).to(dev).repeat_interleave(4)
+            wit.t[4 * var: 4 * (var + cnt)].copy_(torch.where(m, prod.t[: 4 * cnt], summ.t[: 4 * cnt]))
+            prev_lo, prev_n = var, cnt
+            row += cnt
+            var += cnt
+        torch.cuda.synchronize()
+        cs.selectors = np.stack([_ZERO, _ONE])[sel.astype(np.int64)]
+        cs.wiring = wir
+        cs.size = n
+        cs.num_vars = n_vars
+        cs.witness = None
+        cs.witness_array = wit.numpy(n_vars)
+        cs._sel = cs._wir = None
+        return cs
+
+
+def _random_fr(n: int, seed: int) -> np.ndarray:
+    """n uniform Montgomery residues < r (numpy PCG64, rejection on the top limb)."""
+    rng = np.random.default_rng(seed)
+    out = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    out[:, 3] &= np.uint64((1 << 61) - 1)      # < 2^253 < r: uniform enough for synthetic witnesses
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- parameters
+@dataclass
+class PlonkVerifierParams:
+    """plonk/indexer.rs:155-192 (default features)."""
+    cm_q_vec: list
+    cm_s_vec: list
+    cm_qb: KZGCommitment
+    cm_prk_vec: list
+    anemoi_generator: int
+    anemoi_generator_inv: int
+    k: list
+    cs_size: int
+    public_vars_constraint_indices: list
+    lagrange_constants: list
+
+
+@dataclass
+class PlonkProverParams:
+    """plonk/indexer.rs:77-139: coefficient forms and coset evaluations, all resident in HBM."""
+    q_polys: list
+    s_polys: list
+    qb_poly: DevVec
+    q_prk_polys: list
+    verifier_params: PlonkVerifierParams
+    group: DevVec
+    coset_quotient: DevVec
+    l1_coset_evals: DevVec
+    z_h_inv_coset_evals: np.ndarray
+    q_coset_evals: list
+    s_coset_evals: list
+    qb_coset_eval: DevVec
+    q_prk_coset_evals: list
+    sigma_evals: DevVec                 # encode_perm_to_group of the permutation: 5 n values (the evaluation form of s_polys)
+    wiring: torch.Tensor                # 5 n uint32 variable indices (extend_witness)
+    n: int = 0
+    m: int = 0
+    factor: int = 0
+    root: int = 0
+    root_m: int = 0
+    workspace: dict = field(default_factory=dict)
+
+    def get_verifier_params_ref(self) -> PlonkVerifierParams:
+        return self.verifier_params
+
+
+@dataclass
+class PlonkProof:
+    """plonk/indexer.rs:33-75 (default features)."""
+    cm_w_vec: list
+    cm_t_vec: list
+    cm_z: KZGCommitment
+    prk_3_poly_eval_zeta: int
+    prk_4_poly_eval_zeta: int
+    w_polys_eval_zeta: list
+    w_polys_eval_zeta_omega: list
+    z_eval_zeta_omega: int
+    s_polys_eval_zeta: list
+    opening_witness_zeta: KZGCommitment
+    opening_witness_zeta_omega: KZGCommitment
+
+
+# ---------------------------------------------------------------------------------------------- device helpers
+def _root(n: int) -> int:
+    return unmont(ffi.fr_root_of_unity(n))
+
+
+def _ifft(src_ptr: int, n: int, out: DevVec, scratch: DevVec) -> None:
+    ffi.ntt_fr_device(src_ptr, out.ptr, scratch.ptr, n, n, True, None)
+
+
+def _coset_fft(poly: DevVec, m: int, k1: np.ndarray, out: DevVec, scratch: DevVec) -> None:
+    ffi.ntt_fr_device(poly.ptr, out.ptr, scratch.ptr, poly.len, m, False, k1)
+
+
+def _commit_dev(pcs: KZGCommitmentSchemeBN254, vecs) -> list:
+    """PolyComScheme::commit for device-resident coefficient vectors; independent commitments share one pass when they fit."""
+    dev = vecs[0].t.device
+    for v in vecs:
+        if v.len > pcs.max_degree() + 1:
+            raise DegreeError("DegreeError")
+    out = torch.zeros(12 * len(vecs), dtype=torch.int64, device=dev)
+    slots = pcs.info()["batch_slots"]
+    if 1 < len(vecs) <= slots:
+        ffi.msm_g1_batch_device(pcs.handle, [v.ptr for v in vecs], [v.len for v in vecs], out.data_ptr())
+    else:
+        for i, v in enumerate(vecs):
+            ffi.msm_g1_device(pcs.handle, v.ptr, v.len, out.data_ptr() + 96 * i)
+    jac = out.cpu().numpy().view(np.uint64).reshape(len(vecs), 12)
+    return [KZGCommitment(jac[i].copy()) for i in range(len(vecs))]
+
+
+def _evals(polys_points, dev) -> list[int]:
+    """FpPolynomial::eval for (poly, point) pairs: Horner scans on the device, one small D2H for all values."""
+    vals = torch.zeros(4 * len(polys_points), dtype=torch.int64, device=dev)
+    for i, (p, x) in enumerate(polys_points):
+        ffi.poly_horner_fr_device(p.ptr, max(p.len, 1), mont(x), 0, vals.data_ptr() + 32 * i)
+    rows = vals.cpu().numpy().view(np.uint64).reshape(-1, 4)
+    return [unmont(r) for r in rows]
+
+
+def _add_coefs(poly: DevVec, idx, vals) -> None:
+    """FpPolynomial::add_coef_assign for a few coefficients (grows `len` like the reference's resize)."""
+    for i in range(0, len(idx), ffi.SPARSE_MAX):
+        ffi.fr_add_sparse_device(poly.ptr, idx[i:i + ffi.SPARSE_MAX], mont_rows(vals[i:i + ffi.SPARSE_MAX]))
+    poly.len = max(poly.len, max(idx) + 1)
+    assert poly.len <= poly.cap
+
+
+# ---------------------------------------------------------------------------------------------- indexer
+def indexer(cs: TurboCS, pcs: KZGCommitmentSchemeBN254) -> PlonkProverParams:
+    """plonk/indexer.rs:240-536 with lagrange_pcs = None, permutation = None, verifier_params = None."""
+    if cs.selectors is None:
+        raise UzkgeError("call cs.pad() before indexing")
+    n, m = cs.size, cs.quot_eval_dom_size()
+    factor = m // n
+    if n * factor != m:
+        raise UzkgeError("SetupError")
+    dev = _dev()
+    root, root_m = _root(n), _root(m)
+    k = choose_ks(ChaChaRng.from_seed(bytes(32)), N_WIRES_PER_GATE)       # indexer.rs:258: fixed seed
+    k1 = mont(k[1])
+    scratch = DevVec(m, dev, zero=False)
+    group = DevVec(n, dev, zero=False)
+    ffi.fr_powers_device(mont(root), n, group.ptr)
+    coset_quotient = DevVec(m, dev, zero=False)
+    ffi.fr_powers_device(mont(root_m), m, coset_quotient.ptr, scale=k1)
+
+    # Step 1: permutation polynomials.  table[c n + i] = k_c w^i, sigma = table[perm]
+    perm = cs.compute_permutation()
+    table = DevVec(N_WIRES_PER_GATE * n, dev, zero=False)
+    for c in range(N_WIRES_PER_GATE):
+        ffi.fr_powers_device(mont(root), n, table.at(c * n), scale=mont(k[c]))
+    sigma = DevVec(N_WIRES_PER_GATE * n, dev, zero=False)
+    d_perm = torch.from_numpy(perm.astype(np.uint32).view(np.int32)).to(dev)
+    ffi.fr_gather_device(table.ptr, d_perm.data_ptr(), N_WIRES_PER_GATE * n, sigma.ptr)
+    del table
+
+    def preprocess(evals_ptr: int):
+        coefs = DevVec(n, dev, zero=False)
+        _ifft(evals_ptr, n, coefs, scratch)
+        coset = DevVec(m, dev, zero=False)
+        _coset_fft(coefs, m, k1, coset, scratch)
+        return coefs, coset
+
+    s_polys, s_coset = [], []
+    for i in range(N_WIRES_PER_GATE):
+        c, e = preprocess(sigma.at(i * n))
+        s_polys.append(c)
+        s_coset.append(e)
+    # Step 2: selector polynomials
+    q_polys, q_coset = [], []
+    for i in range(N_SELECTORS):
+        ev = DevVec.from_numpy(cs.selectors[i], dev)
+        c, e = preprocess(ev.ptr)
+        q_polys.append(c)
+        q_coset.append(e)
+    # Step 3: L1 and Z_H
+    l1 = DevVec(n, dev)
+    ffi.fr_add_sparse_device(l1.ptr, [0], mont_rows([n]))
+    _l1_coefs, l1_coset = preprocess(l1.ptr)
+    z_h_inv = []
+    mult, step = pow(k[1], n, FR_MODULUS), pow(root_m, n, FR_MODULUS)
+    for _ in range(factor):
+        z_h_inv.append(pow((mult - 1) % FR_MODULUS, -1, FR_MODULUS))
+        mult = mult * step % FR_MODULUS
+    # Step 4: Lagrange constants (helpers.rs:1170-1179), only for the public-input rows
+    lagrange_constants = []
+    for ci in cs.public_vars_constraint_indices:
+        # prod_{i != j} (w^j - w^i) = n * w^{-j}  (derivative of X^n - 1 at w^j)
+        lagrange_constants.append(pow(n * pow(root, -ci, FR_MODULUS) % FR_MODULUS, -1, FR_MODULUS))
+    # Step 5: boolean constraints; Step 6: Anemoi round keys (none in the supported gate set: zero polynomials)
+    zero_poly, zero_coset = DevVec(n, dev), DevVec(m, dev)
+    if cs.boolean_constraint_indices:
+        qb = DevVec(n, dev)
+        idx = list(cs.boolean_constraint_indices)
+        for i in range(0, len(idx), ffi.SPARSE_MAX):
+            ffi.fr_add_sparse_device(qb.ptr, idx[i:i + ffi.SPARSE_MAX], mont_rows([1] * len(idx[i:i + ffi.SPARSE_MAX])))
+        qb_poly, qb_coset = preprocess(qb.ptr)
+    else:
+        qb_poly, qb_coset = zero_poly, zero_coset
+    q_prk_polys, q_prk_coset = [zero_poly] * 4, [zero_coset] * 4
+
+    cms = _commit_many(pcs, q_polys + s_polys + [qb_poly, zero_poly])
+    identity = cms[-1]
+    vp = PlonkVerifierParams(
+        cm_q_vec=cms[:N_SELECTORS], cm_s_vec=cms[N_SELECTORS:N_SELECTORS + N_WIRES_PER_GATE], cm_qb=cms[-2], cm_prk_vec=[identity] * 4,
+        anemoi_generator=0, anemoi_generator_inv=0, k=k, cs_size=n,
+        public_vars_constraint_indices=list(cs.public_vars_constraint_indices), lagrange_constants=lagrange_constants)
+    d_wiring = torch.from_numpy(cs.wiring.reshape(-1).view(np.int32)).to(dev)
+    torch.cuda.synchronize()
+    return PlonkProverParams(
+        q_polys=q_polys, s_polys=s_polys, qb_poly=qb_poly, q_prk_polys=q_prk_polys, verifier_params=vp, group=group,
+        coset_quotient=coset_quotient, l1_coset_evals=l1_coset, z_h_inv_coset_evals=mont_rows(z_h_inv), q_coset_evals=q_coset,
+        s_coset_evals=s_coset, qb_coset_eval=qb_coset, q_prk_coset_evals=q_prk_coset, sigma_evals=sigma, wiring=d_wiring,
+        n=n, m=m, factor=factor, root=root, root_m=root_m, workspace={"scratch": scratch})
+
+
+def _commit_many(pcs, vecs) -> list:
+    out = []
+    slots = max(1, pcs.info()["batch_slots"])
+    for i in range(0, len(vecs), slots):
+        out.extend(_commit_dev(pcs, vecs[i:i + slots]))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- prover
+def hide_polynomial(prng, polynomial: DevVec, hiding_degree: int, zeroing_degree: int) -> list[int]:
+    """helpers.rs:139-154: add (b_0 + b_1 X + ...) (X^zeroing_degree - 1)."""
+    blinds, idx, vals = [], [], []
+    for i in range(hiding_degree):
+        blind = fr_rand(prng)
+        blinds.append(blind)
+        idx += [i, zeroing_degree + i]
+        vals += [blind, -blind]
+    _add_coefs(polynomial, idx, vals)
+    return blinds
+
+
+def first_lagrange_poly(zeta: int, group_order: int) -> tuple[int, int]:
+    """helpers.rs:1412-1423: (Z_H(zeta), L_1(zeta))."""
+    z_h = (pow(zeta, group_order, FR_MODULUS) - 1) % FR_MODULUS
+    return z_h, z_h * pow((zeta - 1) % FR_MODULUS, -1, FR_MODULUS) % FR_MODULUS
+
+
+def batch_prove(pcs, transcript: Transcript, polys, evals, point: int, max_degree: int, scratch_h: DevVec, scratch_q: DevVec) -> KZGCommitment:
+    """poly_commit/pcs.rs:107-168 (lagrange_pcs = None): h = sum_j alpha^j (p_j - p_j(x)); commit(h / (X - x)).  `evals` are the
+    values p_j(x) the caller already holds (the reference re-evaluates them, pcs.rs:126)."""
+    init_pcs_batch_eval_transcript(transcript, max_degree, point)
+    alpha = transcript.get_challenge_field_elem()
+    mults, mult, const = [], 1, 0
+    for v in evals:
+        mults.append(mult)
+        const = (const + mult * v) % FR_MODULUS
+        mult = mult * alpha % FR_MODULUS
+    hlen = max(p.len for p in polys)
+    ffi.fr_lincomb_device([p.ptr for p in polys], [p.len for p in polys], mont_rows(mults), scratch_h.ptr, hlen)
+    ffi.fr_add_sparse_device(scratch_h.ptr, [0], mont_rows([-const]))
+    rem = torch.zeros(4, dtype=torch.int64, device=scratch_h.t.device)
+    ffi.poly_horner_fr_device(scratch_h.ptr, hlen, mont(point), scratch_q.ptr, rem.data_ptr())
+    if rem.cpu().numpy().any():
+        raise UzkgeError("PCSProveEvalError")
+    scratch_q.len = hlen - 1
+    return _commit_dev(pcs, [scratch_q])[0]
+
+
+def prover(prng, transcript: Transcript, pcs: KZGCommitmentSchemeBN254, cs: TurboCS, prover_params: PlonkProverParams, w,
+           timings: dict | None = None) -> PlonkProof:
+    """plonk/prover.rs:76-394.  `w`: the witness, (num_vars, 4) Montgomery limbs (numpy) or a DevVec already in HBM."""
+    if cs.is_verifier_only():
+        raise UzkgeError("FuncParamsError")
+    P = prover_params
+    vp = P.verifier_params
+    n, m, k = P.n, P.m, vp.k
+    dev = P.group.t.device
+    ws = P.workspace
+    scratch = ws["scratch"]
+    k1, k1_inv = mont(k[1]), mont(pow(k[1], -1, FR_MODULUS))
+    cap = n + 8
+    marks = []
+
+    def mark(name):
+        if timings is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
+    wit = w if isinstance(w, DevVec) else DevVec.from_numpy(w, dev)
+    if wit.len != cs.num_vars:
+        raise ParameterError("witness length != num_vars")
+    if cs.public_vars_witness_indices:
+        rows = wit.t.view(-1, 4)[torch.tensor(cs.public_vars_witness_indices, device=dev)].cpu().numpy().view(np.uint64)
+        online_values = [unmont(r) for r in rows]
+    else:
+        online_values = []
+    transcript_init_plonk(transcript, vp, online_values, P.root)
+
+    # 1. the PI polynomial (helpers.rs:111-131)
+    pi = DevVec(n, dev)
+    if online_values:
+        idx = list(cs.public_vars_constraint_indices)
+        for i in range(0, len(idx), ffi.SPARSE_MAX):
+            ffi.fr_add_sparse_device(pi.ptr, idx[i:i + ffi.SPARSE_MAX], mont_rows(online_values[i:i + ffi.SPARSE_MAX]))
+        _ifft(pi.ptr, n, pi, scratch)
+
+    # 2. witness polynomials: extend, interpolate, hide, commit
+    ext = ws.get("ext") or DevVec(N_WIRES_PER_GATE * n, dev, zero=False)
+    ws["ext"] = ext
+    ffi.fr_gather_device(wit.ptr, P.wiring.data_ptr(), N_WIRES_PER_GATE * n, ext.ptr)
+    w_polys = []
+    for i in range(N_WIRES_PER_GATE):
+        f = DevVec(cap, dev, length=n)
+        _ifft(ext.at(i * n), n, f, scratch)
+        hide_polynomial(prng, f, cs.get_hiding_degree(i), n)
+        w_polys.append(f)
+    cm_w_vec = _commit_many(pcs, w_polys)
+    for cm in cm_w_vec:
+        transcript.append_commitment(cm)
+    mark("round1_wires")
+
+    # 4. beta, gamma
+    beta = transcript.get_challenge_field_elem()
+    transcript.append_single_byte(0x01)
+    gamma = transcript.get_challenge_field_elem()
+
+    # 5. z: running product on H, interpolate, hide, commit (helpers.rs:160-220)
+    z_poly = DevVec(cap, dev, length=n)
+    tmp = ws.get("ztmp") or DevVec(4 * n, dev, zero=False)
+    ws["ztmp"] = tmp
+    z_ev = DevVec(n, dev, zero=False)
+    ffi.plonk_z_evals_fr_device([ext.at(i * n) for i in range(N_WIRES_PER_GATE)], [P.sigma_evals.at(i * n) for i in range(N_WIRES_PER_GATE)],
+                                P.group.ptr, mont_rows(k), mont(beta), mont(gamma), n, z_ev.ptr, tmp.ptr)
+    _ifft(z_ev.ptr, n, z_poly, scratch)
+    hide_polynomial(prng, z_poly, 3, n)
+    cm_z = _commit_dev(pcs, [z_poly])[0]
+    transcript.append_commitment(cm_z)
+    mark("round2_z")
+
+    # 6. alpha;  7. t = numerator / Z_H on the coset k[1] <w_m>, split, commit (helpers.rs:223-678, 1323-1408)
+    alpha = transcript.get_challenge_field_elem()
+    coset = ws.get("coset")
+    if coset is None:
+        coset = ws["coset"] = [DevVec(m, dev, zero=False) for _ in range(N_WIRES_PER_GATE + 3)]
+    w_coset, pi_coset, z_coset, t_buf = coset[:5], coset[5], coset[6], coset[7]
+    for p, c in zip(w_polys, w_coset):
+        _coset_fft(p, m, k1, c, scratch)
+    if online_values:
+        _coset_fft(pi, m, k1, pi_coset, scratch)
+    else:
+        pi_coset.t.zero_()
+    _coset_fft(z_poly, m, k1, z_coset, scratch)
+    ffi.plonk_quotient_fr_device(
+        [c.ptr for c in w_coset], [c.ptr for c in P.q_coset_evals], pi_coset.ptr, z_coset.ptr, [c.ptr for c in P.s_coset_evals],
+        P.coset_quotient.ptr, P.l1_coset_evals.ptr, P.qb_coset_eval.ptr, [c.ptr for c in P.q_prk_coset_evals], mont_rows(k),
+        mont(alpha), mont(beta), mont(gamma), mont(vp.anemoi_generator), mont(vp.anemoi_generator_inv), P.z_h_inv_coset_evals,
+        m, P.factor, t_buf.ptr)
+    ffi.ntt_fr_device(t_buf.ptr, t_buf.ptr, scratch.ptr, m, m, True, k1_inv)
+    coefs_len = ffi.fr_trimmed_len_device(t_buf.ptr, m)
+    mark("round3_quotient")
+    piece = n + 2
+    t_polys, prev = [], 0
+    for i in range(N_WIRES_PER_GATE):
+        start = i * piece
+        end = coefs_len if i == N_WIRES_PER_GATE - 1 else (i + 1) * piece
+        take = max(0, min(coefs_len, end) - start) if start < coefs_len else 0
+        tp = DevVec(max(cap, take + 1), dev, length=take)
+        if take:
+            tp.t[: 4 * take].copy_(t_buf.t[4 * start: 4 * (start + take)])
+        rand = fr_rand(prng)
+        if i != N_WIRES_PER_GATE - 1:
+            _add_coefs(tp, [piece, 0], [rand, -prev])
+            tp.len = piece + 1
+        elif take == 0:
+            _add_coefs(tp, [0], [-prev])
+        else:
+            _add_coefs(tp, [0], [-prev])
+        prev = rand
+        t_polys.append(tp)
+    cm_t_vec = _commit_many(pcs, t_polys)
+    for cm in cm_t_vec:
+        transcript.append_commitment(cm)
+    mark("round3_commit_t")
+
+    # 8. zeta;  9a. openings
+    zeta = transcript.get_challenge_field_elem()
+    zeta_omega = P.root * zeta % FR_MODULUS
+    s_open = P.s_polys[: N_WIRES_PER_GATE - 1]
+    pts = ([(p, zeta) for p in w_polys] + [(p, zeta) for p in s_open] + [(P.q_prk_polys[2], zeta), (P.q_prk_polys[3], zeta)]
+           + [(z_poly, zeta_omega)] + [(p, zeta_omega) for p in w_polys[:3]])
+    ev = _evals(pts, dev)
+    w_polys_eval_zeta, s_polys_eval_zeta = ev[0:5], ev[5:9]
+    prk_3_poly_eval_zeta, prk_4_poly_eval_zeta, z_eval_zeta_omega = ev[9], ev[10], ev[11]
+    w_polys_eval_zeta_omega = ev[12:15]
+    for v in w_polys_eval_zeta + s_polys_eval_zeta:
+        transcript.append_challenge(v)
+    transcript.append_challenge(prk_3_poly_eval_zeta)
+    transcript.append_challenge(prk_4_poly_eval_zeta)
+    transcript.append_challenge(z_eval_zeta_omega)
+    for v in w_polys_eval_zeta_omega:
+        transcript.append_challenge(v)
+    # 10. u
+    _u = transcript.get_challenge_field_elem()
+
+    # 9b. the linearisation polynomial r (helpers.rs:681-999)
+    z_h_eval_zeta, first_lagrange_eval_zeta = first_lagrange_poly(zeta, n)
+    a = [pow(alpha, i, FR_MODULUS) for i in range(8)]
+    we = w_polys_eval_zeta
+    sel_mult = [we[0], we[1], we[2], we[3], we[0] * we[1], we[2] * we[3], 1, we[0] * we[1] * we[2] * we[3] * we[4], -we[4]]
+    terms = [(sel_mult[i], P.q_polys[i]) for i in range(N_SELECTORS)]
+    z_scalar = alpha
+    beta_zeta = beta * zeta % FR_MODULUS
+    for i in range(N_WIRES_PER_GATE):
+        z_scalar = z_scalar * (we[i] + k[i] * beta_zeta + gamma) % FR_MODULUS
+    z_scalar += first_lagrange_eval_zeta * a[2]
+    terms.append((z_scalar, z_poly))
+    s_last = alpha * z_eval_zeta_omega % FR_MODULUS * beta % FR_MODULUS
+    for i in range(N_WIRES_PER_GATE - 1):
+        s_last = s_last * (we[i] + beta * s_polys_eval_zeta[i] + gamma) % FR_MODULUS
+    terms.append((-s_last, P.s_polys[N_WIRES_PER_GATE - 1]))
+    terms.append((we[1] * (we[1] - 1) * a[3] + we[2] * (we[2] - 1) * a[4] + we[3] * (we[3] - 1) * a[5], P.qb_poly))
+    terms.append((prk_3_poly_eval_zeta * a[6], P.q_prk_polys[0]))
+    terms.append((prk_3_poly_eval_zeta * a[7], P.q_prk_polys[1]))
+    zfactor = pow(zeta, piece, FR_MODULUS)
+    exponent = z_h_eval_zeta
+    for tp in t_polys:
+        terms.append((-exponent, tp))
+        exponent = exponent * zfactor % FR_MODULUS
+    rlen = max(p.len for _, p in terms)
+    r_poly = DevVec(max(cap, rlen), dev, zero=False, length=rlen)
+    ffi.fr_lincomb_device([p.ptr for _, p in terms], [p.len for _, p in terms], mont_rows([s for s, _ in terms]), r_poly.ptr, rlen)
+    r_eval_zeta = _evals([(r_poly, zeta)], dev)[0]
+    mark("round4_evals_r")
+
+    polys_to_open = w_polys + s_open + [P.q_prk_polys[2], P.q_prk_polys[3], r_poly]
+    evals_to_open = w_polys_eval_zeta + s_polys_eval_zeta + [prk_3_poly_eval_zeta, prk_4_poly_eval_zeta, r_eval_zeta]
+    hmax = max(p.len for p in polys_to_open + [z_poly])
+    sh, sq = DevVec(hmax, dev, zero=False), DevVec(hmax, dev, zero=False)
+    opening_witness_zeta = batch_prove(pcs, transcript, polys_to_open, evals_to_open, zeta, n + 2, sh, sq)
+    opening_witness_zeta_omega = batch_prove(pcs, transcript, [z_poly] + w_polys[:3], [z_eval_zeta_omega] + w_polys_eval_zeta_omega,
+                                             zeta_omega, n + 2, sh, sq)
+    mark("round5_openings")
+    if timings is not None:
+        torch.cuda.synchronize()
+        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+            timings[name] = timings.get(name, 0.0) + e0.elapsed_time(e1)
+    return PlonkProof(
+        cm_w_vec=cm_w_vec, cm_t_vec=cm_t_vec, cm_z=cm_z, prk_3_poly_eval_zeta=prk_3_poly_eval_zeta,
+        prk_4_poly_eval_zeta=prk_4_poly_eval_zeta, w_polys_eval_zeta=w_polys_eval_zeta, w_polys_eval_zeta_omega=w_polys_eval_zeta_omega,
+        z_eval_zeta_omega=z_eval_zeta_omega, s_polys_eval_zeta=s_polys_eval_zeta, opening_witness_zeta=opening_witness_zeta,
+        opening_witness_zeta_omega=opening_witness_zeta_omega)
