@@ -163,6 +163,62 @@ def run_reference(args, rank: int, world: int) -> int:
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ PlonK proofs
+def plonk_proofs(args, dev, K: int, W: int) -> dict:
+    """BASELINE.json's first metric: full TurboPlonK proofs/s on synthetic circuits (configs[4]; 2^14 is the size of the zshuffle
+    circuit, configs[0]).  A step = one complete `prover` call (5 rounds, 13 MSMs, 7 iFFT(n) + 7 coset FFT(6n) + 1 coset iFFT(6n),
+    quotient map, openings) -- wall clock around a synchronised call, because the Fiat-Shamir transcript puts the host in the loop.
+    `proofs_per_s`: witness resident in HBM; `e2e_proofs_per_s`: witness in host memory, uploaded inside the timed region."""
+    import torch
+
+    from uzkge_b200 import KZGCommitmentSchemeBN254, ffi, plonk
+    from uzkge_b200.rng import ChaChaRng
+    from uzkge_b200.transcript import Transcript
+
+    tau = plonk.mont(0x1234567890ABCDEF1234567890ABCDEF)
+    out = {"metric": "turboplonk_synthetic_proofs_per_s", "unit": "proofs/s", "sizes": []}
+    for lg in [int(x) for x in args.plonk_logs.split(",") if x]:
+        n = 1 << lg
+        t0 = time.perf_counter()
+        cs = plonk.TurboCS.synthetic(lg)
+        pcs = KZGCommitmentSchemeBN254.new(n + 2, tau)
+        params = plonk.indexer(cs, pcs)
+        torch.cuda.synchronize()
+        setup_s = time.perf_counter() - t0
+        wit_host = cs.get_witness_array()
+        wit = plonk.DevVec.from_numpy(wit_host, dev)
+        steps = K if lg <= 18 else max(2, min(K, 5))
+        for _ in range(min(W, 3)):
+            proof = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit)
+        torch.cuda.synchronize()
+        timings = {}
+        l0 = ffi.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit, timings=timings)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        launches = (ffi.launch_count() - l0) // steps
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            proof2 = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit_host)
+        torch.cuda.synchronize()
+        dt_e2e = (time.perf_counter() - t0) / steps
+        same = all(a == b for a, b in zip(proof.cm_t_vec + [proof.opening_witness_zeta], proof2.cm_t_vec + [proof2.opening_witness_zeta]))
+        out["sizes"].append({
+            "log_n": lg, "prove_ms": dt * 1e3, "proofs_per_s": 1.0 / dt, "e2e_prove_ms": dt_e2e * 1e3, "e2e_proofs_per_s": 1.0 / dt_e2e,
+            "h2d_bytes_per_step": int(wit_host.nbytes), "d2h_bytes_per_step": 13 * 96 + 16 * 32, "steps": steps,
+            "launches_per_proof": int(launches), "rounds_ms": {k: v / steps for k, v in timings.items()},
+            "ops_per_proof": {"msm": 13, "ifft_n": 6, "coset_fft_6n": 6, "coset_ifft_6n": 1, "quotient_points": int(params.m), "evals": 16},
+            "setup_s": setup_s, "deterministic": bool(same),
+            "window_bits": pcs.info()["window_bits"], "hbm_peak_gib": torch.cuda.max_memory_allocated() / 2**30,
+        })
+        pcs.close()
+        del params, wit, cs, pcs
+        torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main() -> int:
     ap = argparse.ArgumentParser()
@@ -170,7 +226,8 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="both", choices=["both", "msm", "ntt"])
+    ap.add_argument("--workload", default="all", choices=["all", "both", "msm", "ntt", "plonk"])
+    ap.add_argument("--plonk-logs", default="14,22", help="log2 circuit sizes of the synthetic TurboPlonK proofs")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -227,7 +284,7 @@ def main() -> int:
         sampler.start()
 
     # -------------------------------------------------------------------------------------------- MSM
-    if args.workload in ("both", "msm"):
+    if args.workload in ("all", "both", "msm"):
         n = 1 << LOG_MSM
         # every rank builds its own slice of the synthetic SRS on its own GPU (setup path, untimed): 2^20 powers-of-tau
         # points with a rank-specific trapdoor, so the N slices are N * 2^20 distinct bases
@@ -310,7 +367,7 @@ def main() -> int:
         }
 
     # -------------------------------------------------------------------------------------------- NTT
-    if args.workload in ("both", "ntt"):
+    if args.workload in ("all", "both", "ntt"):
         n = 1 << LOG_NTT
         nbuf = 4  # 4 x 128 MiB inputs > L2
         hx = random_fr(n, 0xB2000003 + rank)
@@ -348,6 +405,10 @@ def main() -> int:
         roundtrip_ok = bool(np.array_equal(pinned.array, hx)) if K % 2 == 0 else None
         pinned.free()
         results["ntt"] = {"ms": ms, "e2e_ms": e2e_ms, "n": n, "phases_ms": prof["ms"], "roundtrip_ok": roundtrip_ok, "hx": hx}
+
+    # -------------------------------------------------------------------------------------------- PlonK (rank 0, N = 1)
+    if args.workload in ("all", "plonk") and world == 1:
+        results["plonk"] = plonk_proofs(args, dev, K, W)
 
     t_region1 = time.time()
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
@@ -435,6 +496,21 @@ def main() -> int:
             b["cpu_baseline"] = r["cpu"]
         return b
 
+    if "msm" not in results and "ntt" not in results:
+        pl = results["plonk"]
+        first = pl["sizes"][-1]
+        line = {
+            "metric": "turboplonk_synthetic_proofs_per_s", "value": first["proofs_per_s"], "unit": "proofs/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": first["prove_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (256-bit Montgomery, IMAD carry chains)", "data": "synthetic",
+            "config": {"workload": f"synthetic TurboPlonK circuit, 2^{first['log_n']} gates, full prove, witness resident in HBM"},
+            "e2e": {"value": first["e2e_proofs_per_s"], "unit": "proofs/s", "h2d_bytes_per_step": first["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": first["d2h_bytes_per_step"]},
+            "gpu_launches": int(launches), "clocks": clocks, "plonk": pl,
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
     head = "msm" if "msm" in results else "ntt"
     blk = msm_block(results["msm"]) if head == "msm" else ntt_block(results["ntt"])
     line = {
@@ -454,6 +530,8 @@ def main() -> int:
     }
     if head == "msm" and "ntt" in results:
         line["ntt"] = ntt_block(results["ntt"])
+    if "plonk" in results:
+        line["plonk"] = results["plonk"]
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -22,12 +22,13 @@ def test_keccak256_known_answers():
     kats = {b"": "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470",
             b"abc": "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"}
     for msg, want in kats.items():
-        assert tr_mod.keccak256(msg).hex() == want
+        assert tr_mod.keccak256(msg).hex() == want        # csrc/hostutil.c
+        assert tr_mod.keccak256_py(msg).hex() == want
         assert pp.keccak256(msg).hex() == want
     rnd = random.Random(1)
     for n in (1, 31, 32, 135, 136, 137, 272, 1000):     # around the 136-byte rate
         msg = bytes(rnd.randrange(256) for _ in range(n))
-        assert tr_mod.keccak256(msg) == pp.keccak256(msg)
+        assert tr_mod.keccak256(msg) == pp.keccak256(msg) == tr_mod.keccak256_py(msg)
 
 
 def test_chacha_fr_rand_reproduces_the_golden_ks(domain_kat):
@@ -41,6 +42,8 @@ def test_chacha_fr_rand_reproduces_the_golden_ks(domain_kat):
     for e in domain_kat.values():
         if "k" in e:
             assert [int(x, 16) for x in e["k"]] == K_GOLDEN[: len(e["k"])]
+    c, d = prng_mod.ChaChaRng.from_seed(bytes(range(32))), prng_mod.ChaChaRng.from_seed(bytes(range(32)))
+    assert [c._block() for _ in range(3)] == [d._block_py() for _ in range(3)]     # csrc/hostutil.c against its Python statement
     a, b = prng_mod.ChaChaRng.from_seed(bytes(range(32))), pp.ChaCha(bytes(range(32)))
     assert [prng_mod.fr_rand(a) for _ in range(40)] == [b.fr() for _ in range(40)]
 

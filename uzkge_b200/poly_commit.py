@@ -22,6 +22,8 @@ from .errors import DegreeError, ParameterError
 
 FR_MODULUS = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 FQ_MODULUS = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+_FQ_R = (1 << 256) % FQ_MODULUS
+_FQ_R_INV = pow(_FQ_R, -1, FQ_MODULUS)
 
 
 def _limbs_to_int(row) -> int:
@@ -172,10 +174,27 @@ class KZGCommitment:
 
     def __init__(self, jac: np.ndarray):
         self.value = ffi.as_u64(jac).reshape(12)
+        self._affine = None   # canonical (x, y) integers, or () for the identity
+
+    def _affine_ints(self):
+        """`into_affine()` + leaving Montgomery form, as the reference does on the host when it serialises a commitment
+        (kzg_poly_commitment.rs:37-53): one modular inversion, O(1) per commitment."""
+        if self._affine is None:
+            x, y, z = (_limbs_to_int(self.value[4 * i: 4 * i + 4]) * _FQ_R_INV % FQ_MODULUS for i in range(3))
+            if z == 0:
+                self._affine = ()
+            else:
+                zi = pow(z, -1, FQ_MODULUS)
+                zi2 = zi * zi % FQ_MODULUS
+                self._affine = (x * zi2 % FQ_MODULUS, y * zi2 % FQ_MODULUS * zi % FQ_MODULUS)
+        return self._affine
 
     def to_affine(self) -> np.ndarray:
         """(x, y) Montgomery limbs, zeros for the identity."""
-        return ffi.g1_to_affine(self.value)
+        a = self._affine_ints()
+        if not a:
+            return np.zeros(8, dtype=np.uint64)
+        return np.concatenate([_int_to_limbs(a[0] * _FQ_R % FQ_MODULUS), _int_to_limbs(a[1] * _FQ_R % FQ_MODULUS)])
 
     def is_identity(self) -> bool:
         return not self.value[8:].any()
@@ -186,13 +205,10 @@ class KZGCommitment:
     def to_transcript_bytes(self) -> bytes:
         """kzg_poly_commitment.rs:37-53: affine x big-endian || y big-endian (canonical), 64 zero bytes for the
         identity."""
-        aff = self.to_affine()
-        if not aff.any():
+        a = self._affine_ints()
+        if not a:
             return bytes(64)
-        # leave Montgomery form: multiply by 1 on the device (Fq)
-        one = np.array([[1, 0, 0, 0]], dtype=np.uint64)
-        xy = ffi.field_mul(aff.reshape(2, 4), np.repeat(one, 2, axis=0), "fq")
-        return _limbs_to_int(xy[0]).to_bytes(32, "big") + _limbs_to_int(xy[1]).to_bytes(32, "big")
+        return a[0].to_bytes(32, "big") + a[1].to_bytes(32, "big")
 
     def __eq__(self, other) -> bool:
         return isinstance(other, KZGCommitment) and np.array_equal(self.to_affine(), other.to_affine())

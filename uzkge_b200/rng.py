@@ -43,6 +43,18 @@ class ChaChaRng:
         return cls(seed)
 
     def _block(self) -> list[int]:
+        import ctypes as C
+
+        from .transcript import host_lib
+
+        key = (C.c_uint32 * 8)(*self._key)
+        out = (C.c_uint32 * 16)()
+        host_lib().uzkge_host_chacha20_block(key, self._counter, self._stream, out)
+        self._counter += 1
+        return list(out)
+
+    def _block_py(self) -> list[int]:
+        """Pure-Python statement of uzkge_host_chacha20_block (csrc/hostutil.c); the tests compare them."""
         init = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + self._key + [
             self._counter & _M32, (self._counter >> 32) & _M32, self._stream & _M32, (self._stream >> 32) & _M32]
         s = list(init)

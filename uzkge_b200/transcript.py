@@ -44,7 +44,8 @@ def _keccak_f(a: list[int]) -> None:
         a[0] ^= rc
 
 
-def keccak256(data: bytes) -> bytes:
+def keccak256_py(data: bytes) -> bytes:
+    """Pure-Python Keccak-256: the readable statement of what uzkge_host_keccak256 (csrc/hostutil.c) computes; the tests compare them."""
     rate = 136
     msg = bytearray(data)
     msg.append(0x01)
@@ -56,6 +57,37 @@ def keccak256(data: bytes) -> bytes:
             a[i] ^= int.from_bytes(msg[off + 8 * i: off + 8 * i + 8], "little")
         _keccak_f(a)
     return b"".join(a[i].to_bytes(8, "little") for i in range(4))
+
+
+_host = None
+
+
+def host_lib():
+    """libuzkge_host.so (csrc/hostutil.c, gcc): Keccak-256 and the ChaCha20 block, so the serial host part of a small proof stays small."""
+    global _host
+    if _host is None:
+        import ctypes as C
+        import os
+
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libuzkge_host.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `python -m uzkge_b200.build`")
+        L = C.CDLL(path)
+        L.uzkge_host_keccak256.restype = None
+        L.uzkge_host_keccak256.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
+        L.uzkge_host_chacha20_block.restype = None
+        L.uzkge_host_chacha20_block.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+        _host = L
+    return _host
+
+
+def keccak256(data: bytes) -> bytes:
+    import ctypes as C
+
+    out = C.create_string_buffer(32)
+    data = bytes(data)
+    host_lib().uzkge_host_keccak256(data, len(data), out)
+    return out.raw
 
 
 def fr_to_bytes_be(x: int) -> bytes:
