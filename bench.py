@@ -164,14 +164,17 @@ def run_reference(args, rank: int, world: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------------ PlonK proofs
-def plonk_proofs(args, dev, K: int, W: int) -> dict:
+def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barrier=None, max_over_ranks=None) -> dict:
     """BASELINE.json's first metric: full TurboPlonK proofs/s on synthetic circuits (configs[4]; 2^14 is the size of the zshuffle
     circuit, configs[0]).  A step = one complete `prover` call (5 rounds, 13 MSMs, 7 iFFT(n) + 7 coset FFT(6n) + 1 coset iFFT(6n),
     quotient map, openings) -- wall clock around a synchronised call, because the Fiat-Shamir transcript puts the host in the loop.
-    `proofs_per_s`: witness resident in HBM; `e2e_proofs_per_s`: witness in host memory, uploaded inside the timed region."""
+    `proofs_per_s`: witness resident in HBM; `e2e_proofs_per_s`: witness in host memory, uploaded inside the timed region.
+    N > 1 GPUs: circuits up to 2^18 gates run as N independent provers (replicas; proofs are latency-bound there); larger ones
+    as ONE proof whose 13 + 16 commitments are point-split over the N GPUs (dist.SplitCommitter), driven by rank 0."""
     import torch
 
     from uzkge_b200 import KZGCommitmentSchemeBN254, ffi, plonk
+    from uzkge_b200 import dist as udist
     from uzkge_b200.rng import ChaChaRng
     from uzkge_b200.transcript import Transcript
 
@@ -179,18 +182,32 @@ def plonk_proofs(args, dev, K: int, W: int) -> dict:
     out = {"metric": "turboplonk_synthetic_proofs_per_s", "unit": "proofs/s", "sizes": []}
     for lg in [int(x) for x in args.plonk_logs.split(",") if x]:
         n = 1 << lg
+        split = world > 1 and lg > 18
+        steps = K if lg <= 18 else max(2, min(K, 5))
         t0 = time.perf_counter()
-        cs = plonk.TurboCS.synthetic(lg)
-        pcs = KZGCommitmentSchemeBN254.new(n + 2, tau)
+        if split:
+            bases = ffi.srs_generate(tau, n + 3)
+            pcs = udist.SplitCommitter(bases, rank, world, device=dev)
+            del bases
+            if rank != 0:
+                pcs.serve()
+                pcs.close()
+                barrier()
+                torch.cuda.empty_cache()
+                continue
+        else:
+            pcs = KZGCommitmentSchemeBN254.new(n + 2, tau)
+        cs = plonk.TurboCS.synthetic(lg, seed=0xB2000004 + (0 if split else rank))
         params = plonk.indexer(cs, pcs)
         torch.cuda.synchronize()
         setup_s = time.perf_counter() - t0
         wit_host = cs.get_witness_array()
         wit = plonk.DevVec.from_numpy(wit_host, dev)
-        steps = K if lg <= 18 else max(2, min(K, 5))
         for _ in range(min(W, 3)):
             proof = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit)
         torch.cuda.synchronize()
+        if not split and barrier:
+            barrier()
         timings = {}
         l0 = ffi.launch_count()
         t0 = time.perf_counter()
@@ -199,23 +216,38 @@ def plonk_proofs(args, dev, K: int, W: int) -> dict:
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / steps
         launches = (ffi.launch_count() - l0) // steps
+        if not split and barrier:
+            barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             proof2 = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit_host)
         torch.cuda.synchronize()
         dt_e2e = (time.perf_counter() - t0) / steps
         same = all(a == b for a, b in zip(proof.cm_t_vec + [proof.opening_witness_zeta], proof2.cm_t_vec + [proof2.opening_witness_zeta]))
+        if split:
+            pcs.shutdown()
+            window_bits = ffi.srs_info(pcs.handle)["window_bits"]
+            proofs_in_flight = 1
+        else:
+            window_bits = pcs.info()["window_bits"]
+            proofs_in_flight = world
+            if world > 1:
+                dt, dt_e2e = max_over_ranks(dt), max_over_ranks(dt_e2e)
         out["sizes"].append({
-            "log_n": lg, "prove_ms": dt * 1e3, "proofs_per_s": 1.0 / dt, "e2e_prove_ms": dt_e2e * 1e3, "e2e_proofs_per_s": 1.0 / dt_e2e,
+            "log_n": lg, "n_gpus": world, "mode": "msm_split" if split else ("replicas" if world > 1 else "single"),
+            "prove_ms": dt * 1e3, "proofs_per_s": proofs_in_flight / dt, "e2e_prove_ms": dt_e2e * 1e3,
+            "e2e_proofs_per_s": proofs_in_flight / dt_e2e,
             "h2d_bytes_per_step": int(wit_host.nbytes), "d2h_bytes_per_step": 13 * 96 + 16 * 32, "steps": steps,
             "launches_per_proof": int(launches), "rounds_ms": {k: v / steps for k, v in timings.items()},
             "ops_per_proof": {"msm": 13, "ifft_n": 6, "coset_fft_6n": 6, "coset_ifft_6n": 1, "quotient_points": int(params.m), "evals": 16},
             "setup_s": setup_s, "deterministic": bool(same),
-            "window_bits": pcs.info()["window_bits"], "hbm_peak_gib": torch.cuda.max_memory_allocated() / 2**30,
+            "window_bits": window_bits, "hbm_peak_gib": torch.cuda.max_memory_allocated() / 2**30,
         })
         pcs.close()
         del params, wit, cs, pcs
         torch.cuda.empty_cache()
+        if split:
+            barrier()
     return out
 
 
@@ -325,9 +357,35 @@ def main() -> int:
             msm_step(i)
         e1.record(stream)
         barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1) / K)
+        single_ms = max_over_ranks(e0.elapsed_time(e1) / K)      # one API call per MSM: the latency of a single commitment
         prof = ffi.profile_read("msm")
         ffi.profile_enable(False)
+
+        # throughput: the K steps travel in ONE batch call (uzkge_cuda_msm_g1_batch_device): the engine pipelines them over two
+        # workspaces -- counting sort of step i + 1 and bucket reduction of step i - 1 under the accumulate kernel of step i
+        d_outs = torch.zeros(12 * K, dtype=torch.int64, device=dev)
+        d_gath = torch.zeros(12 * K * max(world, 1), dtype=torch.int64, device=dev)
+        ptrs = [d_sets[i % nsets].data_ptr() for i in range(K)]
+
+        def msm_batch():
+            ffi.msm_g1_batch_device(h, ptrs, [n] * K, d_outs.data_ptr(), sptr)
+            if world > 1:
+                dist.all_gather_into_tensor(d_gath, d_outs)
+
+        msm_batch()
+        barrier()
+        e0.record(stream)
+        msm_batch()
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / K)
+        # the pipelined results must equal the one-by-one results
+        chk = torch.zeros(12, dtype=torch.int64, device=dev)
+        for i in (0, K - 1):
+            ffi.msm_g1_device(h, ptrs[i], n, chk.data_ptr(), sptr)
+            a, b = chk.cpu().numpy().view(np.uint64), d_outs[12 * i: 12 * i + 12].cpu().numpy().view(np.uint64)
+            if not np.array_equal(ffi.g1_to_affine(a), ffi.g1_to_affine(b)):
+                raise SystemExit("bench.py: pipelined batch MSM differs from the single-call MSM -- refusing to report a number")
         if world > 1:
             t0 = time.time()
             combine()
@@ -335,7 +393,9 @@ def main() -> int:
         else:
             combine_ms = 0.0
 
-        # e2e through the host-pointer ABI: pinned scalars, H2D + MSM + D2H of the 96-byte result every step
+        # e2e through the host-pointer ABI: pinned scalars, H2D + MSM + D2H of the 96-byte results inside the timed region.
+        # uzkge_cuda_msm_g1_batch takes the K host vectors in one call (copies of later steps run under the kernels of earlier
+        # ones); the one-call-per-MSM figure is reported next to it.
         pinned = [ffi.PinnedArray((n, 4)) for _ in range(4)]
         for k, pa in enumerate(pinned):
             pa.array[:] = host_sets[k]
@@ -350,6 +410,21 @@ def main() -> int:
                 dist.all_gather_into_tensor(d_out, d_mine)
                 combine()
         barrier()
+        e2e_single_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / K)
+        vecs = [pinned[i % 4].array for i in range(K)]
+        ffi.msm_g1_batch(h, vecs)
+        barrier()
+        t0 = time.perf_counter()
+        outs = ffi.msm_g1_batch(h, vecs)
+        if world > 1:
+            d_outs.copy_(torch.from_numpy(outs.view(np.int64).reshape(-1)))
+            dist.all_gather_into_tensor(d_gath, d_outs)
+            parts = d_gath.cpu().numpy().view(np.uint64).reshape(world, K, 12)
+            for i in range(K):
+                acc = parts[0, i]
+                for r in range(1, world):
+                    acc = ffi.g1_add(acc, parts[r, i])
+        barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / K)
         for pa in pinned:
             pa.free()
@@ -360,7 +435,8 @@ def main() -> int:
         fq_mul = 10.0 * n * W_ + 28.0 * (1 << (c_ - 1))
         acc_fq_mul = 10.0 * max(0, n * W_ - (1 << (c_ - 1)))
         results["msm"] = {
-            "ms": ms, "e2e_ms": e2e_ms, "n": n, "phases_ms": prof["ms"], "combine_ms": combine_ms,
+            "ms": ms, "e2e_ms": e2e_ms, "single_ms": single_ms, "e2e_single_ms": e2e_single_ms, "n": n, "phases_ms": prof["ms"],
+            "combine_ms": combine_ms,
             "window_bits": c_, "windows": W_, "table_bytes": info["device_bytes"], "precompute_ms": info["precompute_ms"],
             "srs_generate_s": t_gen, "fq_mul": fq_mul, "acc_fq_mul": acc_fq_mul, "acc_ms": acc_ms,
             "host0": host_sets[0], "bases": bases, "handle": h,
@@ -407,8 +483,8 @@ def main() -> int:
         results["ntt"] = {"ms": ms, "e2e_ms": e2e_ms, "n": n, "phases_ms": prof["ms"], "roundtrip_ok": roundtrip_ok, "hx": hx}
 
     # -------------------------------------------------------------------------------------------- PlonK (rank 0, N = 1)
-    if args.workload in ("all", "plonk") and world == 1:
-        results["plonk"] = plonk_proofs(args, dev, K, W)
+    if args.workload in ("all", "plonk"):
+        results["plonk"] = plonk_proofs(args, dev, K, W, rank, world, barrier, max_over_ranks)
 
     t_region1 = time.time()
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
@@ -468,7 +544,8 @@ def main() -> int:
                              "peak": fq_peak / 1e9, "unit": "G Fq-mul/s", "frac": r["acc_fq_mul"] / (r["acc_ms"] * 1e-3) / fq_peak,
                              "fq_mul": r["acc_fq_mul"],
                              "peak_source": "uzkge_cuda_bench_field_mul (dependent 136-IMAD Montgomery chains, measured in this run)"},
-            "phases_ms": r["phases_ms"], "window_bits": r["window_bits"], "windows": r["windows"],
+            "phases_ms": r["phases_ms"], "single_call_ms": r["single_ms"], "single_call_e2e_ms": r["e2e_single_ms"],
+            "window_bits": r["window_bits"], "windows": r["windows"],
             "srs_device_bytes": r["table_bytes"], "srs_precompute_ms": r["precompute_ms"], "combine_ms": r["combine_ms"],
         }
 
@@ -521,12 +598,15 @@ def main() -> int:
             "workload": ("BN254 G1 variable-base MSM, 2^20 points per GPU, powers-of-tau bases resident in HBM, uniform Fr scalars"
                          if head == "msm" else "BN254 Fr radix-2 NTT 2^22, natural order in/out"),
             "parallelism": f"{world} process(es), one per GPU; MSM points split per GPU, partial sums all-gathered (96 B) and added",
+            "pipelining": "the K steps are submitted in one batch call and software-pipelined by the engine (sort / reduce of neighbouring "
+                          "steps under the accumulate kernel); detail.single_call_ms is one MSM per call",
             "l2": "inputs rotate over 8 x 32 MiB scalar sets / 4 x 128 MiB vectors (> 126 MB L2); the MSM's window tables are 0.8 GiB",
         },
         "e2e": blk["e2e"], "roofline": blk["roofline"], "int_roofline": blk["int_roofline"],
         "gpu_launches": int(launches), "clocks": clocks,
         "cpu_baseline": cpu_baseline if head == "msm" else blk.get("cpu_baseline"),
-        "detail": {k: v for k, v in blk.items() if k in ("phases_ms", "window_bits", "windows", "srs_device_bytes", "srs_precompute_ms", "combine_ms")},
+        "detail": {k: v for k, v in blk.items() if k in ("phases_ms", "single_call_ms", "single_call_e2e_ms", "window_bits", "windows", "srs_device_bytes",
+                                                   "srs_precompute_ms", "combine_ms")},
     }
     if head == "msm" and "ntt" in results:
         line["ntt"] = ntt_block(results["ntt"])

@@ -116,3 +116,63 @@ def test_sharded_msm_and_distributed_commits_world2():
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] and r[3] for r in res), res
+
+
+def _split_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch
+
+        from oracle import cpu as oc
+        from uzkge_b200 import dist as udist
+
+        pts = oc.g1_random_points(n, 3)
+        store = {}
+
+        def upload(p):
+            store[1] = p
+            return 1
+
+        def msm_fn(handle, t, k):
+            s = t.numpy().view(np.uint64).reshape(-1, 4)[:k]
+            return torch.from_numpy(oc.msm_g1(store[handle][:k], s).view(np.int64).copy())
+
+        sc = udist.SplitCommitter(pts, rank, world, upload=upload, msm_fn=msm_fn, add_fn=oc.g1_add_jac)
+        assert sc.max_degree() == n - 1
+        if rank != 0:
+            served = sc.serve()
+            q.put((rank, served == 4))
+            return
+
+        class Vec:
+            def __init__(self, a):
+                self.t = torch.from_numpy(a.view(np.int64).reshape(-1).copy())
+                self.len = a.shape[0]
+
+        # full length, ragged, shorter than the first slice (the other rank adds the identity), and a single coefficient
+        polys = [oc.random_fr(m, 20 + m) for m in (n, n - 7, 5, 1)]
+        cms = sc.commit_device([Vec(p) for p in polys])
+        ok = all(np.array_equal(oc.g1_to_affine(c.value), oc.g1_to_affine(oc.msm_g1(pts[: p.shape[0]], p))) for c, p in zip(cms, polys))
+        sc.shutdown()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_split_committer_world2():
+    """The prover's point-split commitment service (dist.SplitCommitter): header broadcast, scatter, partial MSMs, gather, combine."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, n = 2, 203
+    port = free_port()
+    procs = [ctx.Process(target=_split_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res

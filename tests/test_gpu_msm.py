@@ -162,6 +162,41 @@ def test_batched_msm_matches_one_by_one(gpu, oc, bn):
         gpu.srs_free(h)
 
 
+def test_pipelined_batch_matches_one_by_one(gpu, oc, bn):
+    """More MSMs than one pass carries: groups alternate between the SRS's two workspaces on the engine's internal streams
+    (MsmEngine::run_pipelined).  Host-pointer and device-pointer entry points, ragged lengths, empty groups, repeated calls."""
+    import torch
+
+    n = 2500
+    pts = oc.g1_random_points(n, 78)
+    h = gpu.srs_upload(pts)
+    try:
+        slots = gpu.srs_info(h)["batch_slots"]
+        k = 3 * slots + 5                       # four groups: both workspaces are reused
+        vecs = [oc.random_fr(n, 900 + j)[: 1 + (j * 131) % n] for j in range(k)]
+        vecs[1] = np.zeros((0, 4), dtype=np.uint64)
+        vecs[slots + 2] = witness_like(oc, bn, n, 6)
+        for j in range(2 * slots, 3 * slots):   # one whole group of all-zero scalars
+            vecs[j] = np.zeros((7, 4), dtype=np.uint64)
+        want = [oc.msm_g1(pts[: v.shape[0]], v) if v.shape[0] else np.zeros(12, dtype=np.uint64) for v in vecs]
+        for _ in range(2):
+            outs = gpu.msm_g1_batch(h, vecs)
+            for j in range(k):
+                assert same_point(oc, outs[j], want[j]), j
+        d_vecs = [torch.from_numpy(np.ascontiguousarray(v).view(np.int64).reshape(-1)).cuda() if v.shape[0] else torch.zeros(4, dtype=torch.int64).cuda()
+                  for v in vecs]
+        d_out = torch.zeros(12 * k, dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            d_out.zero_()
+            gpu.msm_g1_batch_device(h, [t.data_ptr() for t in d_vecs], [v.shape[0] for v in vecs], d_out.data_ptr())
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy().view(np.uint64).reshape(k, 12)
+            for j in range(k):
+                assert same_point(oc, got[j], want[j]), j
+    finally:
+        gpu.srs_free(h)
+
+
 def test_group_helpers(gpu, oc):
     pts = oc.g1_random_points(4, 3)
     a = oc.g1_mul(pts[0], oc.random_fr(1, 1)[0])

@@ -59,6 +59,8 @@ struct State {
     std::map<uint64_t, MsmSrs> srs;
     uint64_t next_handle = 1;
     DevBuf data, scratch, scalars, small;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
     uint32_t ntt_log_tile = 10, ntt_max_log_r = 10, ntt_two_pass_max = 18;  // measured best on B200 (scripts/gpu_ntt_cfg.py)
 };
 State g;
@@ -243,24 +245,27 @@ UZKGE_API int32_t uzkge_cuda_msm_g1_batch(uint64_t handle, const uint64_t* const
     CUDA_OR_FAIL(g.small.reserve(k * sizeof(jacobian) + 4096), "msm_g1: output buffer");
     fe* d_s = (fe*)g.scalars.p;
     jacobian* d_o = (jacobian*)g.small.p;
+    // H2D copies on a copy stream, one event per vector: the engine's pipeline starts group g as soon as its scalars have
+    // landed, so the copies of later groups run under the kernels of earlier ones
+    if (!g.copy_stream) CUDA_OR_FAIL(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking), "msm_g1_batch: stream");
+    while (g.copy_events.size() < k) {
+        cudaEvent_t ev;
+        CUDA_OR_FAIL(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "msm_g1_batch: event");
+        g.copy_events.push_back(ev);
+    }
+    std::vector<const fe*> ptrs(k);
     size_t off = 0;
     for (size_t j = 0; j < k; j++) {
-        if (n[j]) CUDA_OR_FAIL(cudaMemcpyAsync(d_s + off, scalars[j], n[j] * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "msm_g1: H2D");
+        if (n[j]) CUDA_OR_FAIL(cudaMemcpyAsync(d_s + off, scalars[j], n[j] * sizeof(fe), cudaMemcpyHostToDevice, g.copy_stream), "msm_g1: H2D");
+        CUDA_OR_FAIL(cudaEventRecord(g.copy_events[j], g.copy_stream), "msm_g1_batch: event");
+        ptrs[j] = d_s + off;
         off += n[j];
     }
-    off = 0;
-    for (size_t j0 = 0; j0 < k; j0 += s.slots) {
-        const uint32_t kk = (uint32_t)((k - j0) < s.slots ? (k - j0) : s.slots);
-        const fe* ptrs[16];
-        for (uint32_t j = 0; j < kk; j++) {
-            ptrs[j] = d_s + off;
-            off += n[j0 + j];
-        }
-        int rc = g.msm->run_batch(&s, 0, ptrs, n + j0, kk, d_o + j0, g.stream);
-        if (rc != UZKGE_OK) {
-            cudaStreamSynchronize(g.stream);
-            return engine_fail(rc, "msm_g1_batch: launch");
-        }
+    int rc = g.msm->run_pipelined(&s, 0, ptrs.data(), n, k, d_o, g.stream, g.copy_events.data());
+    if (rc != UZKGE_OK) {
+        cudaStreamSynchronize(g.copy_stream);
+        cudaStreamSynchronize(g.stream);
+        return engine_fail(rc, "msm_g1_batch: launch");
     }
     CUDA_OR_FAIL(cudaMemcpyAsync(out_jac, d_o, k * sizeof(jacobian), cudaMemcpyDeviceToHost, g.stream), "msm_g1: D2H");
     CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "msm_g1: execution");
@@ -302,14 +307,9 @@ UZKGE_API int32_t uzkge_cuda_msm_g1_batch_device(uint64_t handle, size_t base_of
     API_ENTER(-1);
     auto it = g.srs.find(handle);
     if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1_batch_device: unknown handle");
-    MsmSrs& s = it->second;
-    for (size_t j0 = 0; j0 < k; j0 += s.slots) {
-        const uint32_t kk = (uint32_t)((k - j0) < s.slots ? (k - j0) : s.slots);
-        int rc = g.msm->run_batch(&s, base_offset, (const fe* const*)(d_scalars + j0), n + j0, kk, (jacobian*)d_out_jac + j0,
-                                  (cudaStream_t)stream);
-        if (rc != UZKGE_OK) return engine_fail(rc, "msm_g1_batch_device");
-    }
-    return UZKGE_OK;
+    int rc = g.msm->run_pipelined(&it->second, base_offset, (const fe* const*)d_scalars, n, k, (jacobian*)d_out_jac, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "msm_g1_batch_device: range outside the SRS");
+    return engine_fail(rc, "msm_g1_batch_device");
 }
 
 UZKGE_API int32_t uzkge_cuda_ntt_fr(uint64_t* inout, size_t len_in, size_t domain_size, int32_t inverse, const uint64_t* coset_shift) {

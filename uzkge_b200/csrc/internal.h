@@ -130,6 +130,22 @@ private:
 
 // ---------------------------------------------------------------- MSM
 struct ReducePlan;
+// One set of per-pass buffers, sized for `slots` MSMs over the whole SRS.  An SRS owns two: a run of more MSMs than fit one pass
+// alternates between them so that the counting sort of group g + 1 and the bucket reduction of group g - 1 overlap the accumulate
+// kernel of group g (MsmEngine::run_pipelined).
+struct MsmWork {
+    uint32_t* vals = nullptr;         // entries sorted by global bucket id: sign | (f * n + point)
+    uint32_t* offsets = nullptr;      // slots * nbuckets + 1
+    uint32_t* counts = nullptr;       // slots * nbuckets + 1
+    uint32_t *ord_keys_a = nullptr, *ord_keys_b = nullptr, *ord_vals_a = nullptr, *ord_vals_b = nullptr;  // size-ordered bucket ids
+    uint32_t* large_list = nullptr;   // [0] = count, then bucket ids
+    uint32_t* slice_start = nullptr;  // prefix of warp slices per oversized bucket
+    xyzz* slice_sums = nullptr;
+    xyzz* buckets = nullptr;          // slots * nbuckets
+    ReducePlan* reduce[16] = {};      // launch plan of the bucket reduction of every slot (msm_reduce.cu)
+    void* cub_temp = nullptr;
+    cudaEvent_t sorted = nullptr, accumulated = nullptr, reduced = nullptr;  // pipeline hand-offs
+};
 struct MsmSrs {
     uint64_t n = 0;            // points
     uint32_t c = 0;            // window bits
@@ -141,17 +157,7 @@ struct MsmSrs {
     void* arena = nullptr;     // one device allocation holding everything below
     size_t bytes = 0;
     affine* tables = nullptr;  // windows x n affine points: table f holds 2^(c*f) * P_i
-    // workspace, sized for `slots` MSMs over the whole SRS
-    uint32_t* vals = nullptr;         // entries sorted by global bucket id: sign | (f * n + point)
-    uint32_t* offsets = nullptr;      // slots * nbuckets + 1
-    uint32_t* counts = nullptr;       // slots * nbuckets + 1
-    uint32_t *ord_keys_a = nullptr, *ord_keys_b = nullptr, *ord_vals_a = nullptr, *ord_vals_b = nullptr;  // size-ordered bucket ids
-    uint32_t* large_list = nullptr;   // [0] = count, then bucket ids
-    uint32_t* slice_start = nullptr;  // prefix of warp slices per oversized bucket
-    xyzz* slice_sums = nullptr;
-    xyzz* buckets = nullptr;          // slots * nbuckets
-    ReducePlan* reduce[16] = {};      // launch plan of the bucket reduction of every slot (msm_reduce.cu)
-    void* cub_temp = nullptr;
+    MsmWork work[2];
     size_t cub_temp_bytes = 0;
 };
 
@@ -172,6 +178,12 @@ public:
     // k <= s->slots independent MSMs in one pass (one sort, one accumulate launch, concurrent reductions)
     int run_batch(MsmSrs* s, size_t base_offset, const fe* const* d_scalars, const size_t* n, uint32_t k, jacobian* d_out,
                   cudaStream_t st);
+    // any number of independent MSMs: groups of s->slots, software-pipelined over the SRS's two workspaces on internal streams
+    // (sort of group g + 1 and reduction of group g - 1 run under the accumulate kernel of group g); joins `st` at the end
+    // `ready` (optional, k events): MSM j's scalars are complete once ready[j] has fired (host-pointer API: the H2D copy of group
+    // g + 1 then runs under the kernels of group g)
+    int run_pipelined(MsmSrs* s, size_t base_offset, const fe* const* d_scalars, const size_t* n, size_t k, jacobian* d_out,
+                      cudaStream_t st, const cudaEvent_t* ready = nullptr);
     int g1_add(const jacobian* d_a, const jacobian* d_b, jacobian* d_out, cudaStream_t st);
     int g1_to_affine(const jacobian* d_in, affine* d_out, cudaStream_t st);
     int powers_of_tau(const fe& tau, uint64_t first, uint32_t count, affine* d_out, cudaStream_t st);
@@ -179,7 +191,14 @@ public:
 
 
 private:
+    struct GroupPlan;
+    int stage_sort(MsmSrs* s, MsmWork& w, size_t base_offset, const fe* const* d_scalars, const size_t* n, uint32_t k, GroupPlan* plan,
+                   cudaStream_t st, int prof);
+    int stage_accumulate(MsmSrs* s, MsmWork& w, const GroupPlan& plan, cudaStream_t st, int prof);
+    int stage_reduce(MsmSrs* s, MsmWork& w, uint32_t k, jacobian* d_out, cudaStream_t st);
     int sm_count_;
+    cudaStream_t s_sort_ = nullptr, s_acc_ = nullptr, s_red_ = nullptr;  // the pipeline's streams
+    cudaEvent_t start_ = nullptr;
     uint32_t force_lanes_ = 0;
     std::vector<cudaStream_t> aux_;   // auxiliary streams for the concurrent reductions of a batch
     std::vector<cudaEvent_t> join_;

@@ -439,49 +439,59 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
         return off;
     };
     const size_t o_tables = take(sizeof(affine) * m);
-    const size_t o_vals = take(4 * m_all);
-    const size_t o_offsets = take(4 * (nb_all + 1));
-    const size_t o_counts = take(4 * (nb_all + 1));
-    const size_t o_ord = take(4 * 4 * nb_all);
-    const size_t o_large = take(4 * ((size_t)s->large_cap + 1));
-    const size_t o_slice_start = take(4 * ((size_t)s->large_cap + 1));
-    const size_t o_slice_sums = take(sizeof(xyzz) * s->max_slices);
-    const size_t o_buckets = take(sizeof(xyzz) * nb_all);
-    const size_t o_reduce = take(reduce_bytes * s->slots);
-    const size_t o_ticket = take(256 * s->slots);
     cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
     s->cub_temp_bytes = 0;
     UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, s->cub_temp_bytes, dk, dv, (int)nb_all, 0, 32, st));
     size_t scan_temp = 0;
     UZ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)nb_all + 1, st));
     if (scan_temp > s->cub_temp_bytes) s->cub_temp_bytes = scan_temp;
-    const size_t o_cub = take(s->cub_temp_bytes + 256);
+    size_t o_vals[2], o_offsets[2], o_counts[2], o_ord[2], o_large[2], o_slice_start[2], o_slice_sums[2], o_buckets[2], o_reduce[2], o_ticket[2],
+        o_cub[2];
+    for (int l = 0; l < 2; l++) {
+        o_vals[l] = take(4 * m_all);
+        o_offsets[l] = take(4 * (nb_all + 1));
+        o_counts[l] = take(4 * (nb_all + 1));
+        o_ord[l] = take(4 * 4 * nb_all);
+        o_large[l] = take(4 * ((size_t)s->large_cap + 1));
+        o_slice_start[l] = take(4 * ((size_t)s->large_cap + 1));
+        o_slice_sums[l] = take(sizeof(xyzz) * s->max_slices);
+        o_buckets[l] = take(sizeof(xyzz) * nb_all);
+        o_reduce[l] = take(reduce_bytes * s->slots);
+        o_ticket[l] = take(256 * s->slots);
+        o_cub[l] = take(s->cub_temp_bytes + 256);
+    }
     UZ_CUDA_TRY(cudaMalloc(&s->arena, total));
     s->bytes = total;
     char* base = (char*)s->arena;
     s->tables = (affine*)(base + o_tables);
-    s->vals = (uint32_t*)(base + o_vals);
-    s->offsets = (uint32_t*)(base + o_offsets);
-    s->counts = (uint32_t*)(base + o_counts);
-    s->ord_keys_a = (uint32_t*)(base + o_ord);
-    s->ord_keys_b = s->ord_keys_a + nb_all;
-    s->ord_vals_a = s->ord_keys_b + nb_all;
-    s->ord_vals_b = s->ord_vals_a + nb_all;
-    s->large_list = (uint32_t*)(base + o_large);
-    s->slice_start = (uint32_t*)(base + o_slice_start);
-    s->slice_sums = (xyzz*)(base + o_slice_sums);
-    s->buckets = (xyzz*)(base + o_buckets);
-    s->cub_temp = base + o_cub;
-    for (uint32_t j = 0; j < s->slots; j++) {
-        s->reduce[j] = msm_reduce_plan_create(c, (uint32_t)sm_count_, s->buckets + (size_t)j * s->nbuckets, base + o_reduce + reduce_bytes * j,
-                                              (uint32_t*)(base + o_ticket + 256 * j));
-        if (!s->reduce[j]) return UZKGE_ERR_INTERNAL;
+    for (int l = 0; l < 2; l++) {
+        MsmWork& w = s->work[l];
+        w.vals = (uint32_t*)(base + o_vals[l]);
+        w.offsets = (uint32_t*)(base + o_offsets[l]);
+        w.counts = (uint32_t*)(base + o_counts[l]);
+        w.ord_keys_a = (uint32_t*)(base + o_ord[l]);
+        w.ord_keys_b = w.ord_keys_a + nb_all;
+        w.ord_vals_a = w.ord_keys_b + nb_all;
+        w.ord_vals_b = w.ord_vals_a + nb_all;
+        w.large_list = (uint32_t*)(base + o_large[l]);
+        w.slice_start = (uint32_t*)(base + o_slice_start[l]);
+        w.slice_sums = (xyzz*)(base + o_slice_sums[l]);
+        w.buckets = (xyzz*)(base + o_buckets[l]);
+        w.cub_temp = base + o_cub[l];
+        for (uint32_t j = 0; j < s->slots; j++) {
+            w.reduce[j] = msm_reduce_plan_create(c, (uint32_t)sm_count_, w.buckets + (size_t)j * s->nbuckets, base + o_reduce[l] + reduce_bytes * j,
+                                                 (uint32_t*)(base + o_ticket[l] + 256 * j));
+            if (!w.reduce[j]) return UZKGE_ERR_INTERNAL;
+        }
+        UZ_CUDA_TRY(cudaEventCreateWithFlags(&w.sorted, cudaEventDisableTiming));
+        UZ_CUDA_TRY(cudaEventCreateWithFlags(&w.accumulated, cudaEventDisableTiming));
+        UZ_CUDA_TRY(cudaEventCreateWithFlags(&w.reduced, cudaEventDisableTiming));
+        UZ_CUDA_TRY(cudaMemsetAsync(base + o_ticket[l], 0, 256 * s->slots, st));
     }
 
     cudaEvent_t e0, e1;
     UZ_CUDA_TRY(cudaEventCreate(&e0));
     UZ_CUDA_TRY(cudaEventCreate(&e1));
-    UZ_CUDA_TRY(cudaMemsetAsync(base + o_ticket, 0, 256 * s->slots, st));
     UZ_CUDA_TRY(cudaMemcpyAsync(s->tables, affine_xy_host, sizeof(affine) * n, cudaMemcpyHostToDevice, st));
     UZ_CUDA_TRY(cudaEventRecord(e0, st));
     // slabs of at most 2^20 points bound the XYZZ / prefix-product scratch
@@ -519,14 +529,22 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
 }
 
 void MsmEngine::release(MsmSrs* s) {
-    for (uint32_t j = 0; j < MSM_MAX_BATCH; j++)
-        if (s->reduce[j]) msm_reduce_plan_destroy(s->reduce[j]);
+    for (MsmWork& w : s->work) {
+        for (uint32_t j = 0; j < MSM_MAX_BATCH; j++)
+            if (w.reduce[j]) msm_reduce_plan_destroy(w.reduce[j]);
+        if (w.sorted) cudaEventDestroy(w.sorted);
+        if (w.accumulated) cudaEventDestroy(w.accumulated);
+        if (w.reduced) cudaEventDestroy(w.reduced);
+    }
     if (s->arena) cudaFree(s->arena);
     *s = MsmSrs();
 }
 
 MsmEngine::~MsmEngine() {
     for (cudaStream_t a : aux_) cudaStreamDestroy(a);
+    for (cudaStream_t a : {s_sort_, s_acc_, s_red_})
+        if (a) cudaStreamDestroy(a);
+    if (start_) cudaEventDestroy(start_);
     if (fork_) cudaEventDestroy(fork_);
     for (cudaEvent_t e : join_) cudaEventDestroy(e);
 }
@@ -545,27 +563,27 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
     return run_batch(s, base_offset, sc, nn, 1, d_out, st);
 }
 
-// k <= s->slots independent MSMs over srs[base_offset ..]; d_out receives k Jacobian points
-int MsmEngine::run_batch(MsmSrs* s, size_t base_offset, const fe* const* d_scalars, const size_t* n, uint32_t k, jacobian* d_out,
-                         cudaStream_t st) {
-    if (k == 0) return UZKGE_OK;
-    if (k > s->slots || base_offset > s->n) return UZKGE_ERR_SIZE;
+struct MsmEngine::GroupPlan {
+    uint32_t k = 0, nb_all = 0, lanes = 1, thr = 0;
+    const uint32_t* order = nullptr;
+    bool empty = false;
+};
+
+// digits -> counting sort by bucket -> bucket ids in decreasing size.  Everything the accumulate kernel needs is left in `w`.
+int MsmEngine::stage_sort(MsmSrs* s, MsmWork& w, size_t base_offset, const fe* const* d_scalars, const size_t* n, uint32_t k,
+                          GroupPlan* plan, cudaStream_t st, int prof) {
     uint64_t n_all = 0;
     uint32_t n_max = 0;
     DigitArgs da;
     for (uint32_t j = 0; j < k; j++) {
-        if (n[j] > s->n - base_offset) return UZKGE_ERR_SIZE;
         da.scalars[j] = d_scalars[j];
         da.n[j] = (uint32_t)n[j];
         n_all += n[j];
         if (n[j] > n_max) n_max = (uint32_t)n[j];
     }
-    if (n_all == 0) {
-        for (uint32_t j = 0; j < k; j++) msm_identity_kernel<<<1, 1, 0, st>>>(d_out + j);
-        UZ_COUNT_LAUNCH(k);
-        UZ_CUDA_TRY(cudaGetLastError());
-        return UZKGE_OK;
-    }
+    plan->k = k;
+    plan->empty = n_all == 0;
+    if (plan->empty) return UZKGE_OK;
     da.c = s->c;
     da.windows = s->windows;
     da.table_stride = (uint32_t)s->n;
@@ -573,21 +591,20 @@ int MsmEngine::run_batch(MsmSrs* s, size_t base_offset, const fe* const* d_scala
     da.nbuckets = s->nbuckets;
     const uint32_t nb_all = s->nbuckets * k;
     const uint64_t m = (uint64_t)s->windows * n_all;
-    const int prof = g_prof.begin(Profiler::MSM, st);
 
     // count -> scan -> scatter
     const size_t cbytes = 4 * ((size_t)nb_all + 1);
     const dim3 dgrid((n_max + 255) / 256, k);
-    UZ_CUDA_TRY(cudaMemsetAsync(s->counts, 0, cbytes, st));
-    msm_count_scatter_kernel<false><<<dgrid, 256, 0, st>>>(da, s->counts, nullptr, nullptr);
+    UZ_CUDA_TRY(cudaMemsetAsync(w.counts, 0, cbytes, st));
+    msm_count_scatter_kernel<false><<<dgrid, 256, 0, st>>>(da, w.counts, nullptr, nullptr);
     UZ_CUDA_TRY(cudaGetLastError());
     g_prof.mark(prof, MSM_PH_RECODE, st);
     size_t temp = s->cub_temp_bytes;
-    UZ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->cub_temp, temp, s->counts, s->offsets, (int)nb_all + 1, st));
-    UZ_CUDA_TRY(cudaMemsetAsync(s->counts, 0, cbytes, st));
-    msm_count_scatter_kernel<true><<<dgrid, 256, 0, st>>>(da, s->counts, s->offsets, s->vals);
+    UZ_CUDA_TRY(cub::DeviceScan::ExclusiveSum(w.cub_temp, temp, w.counts, w.offsets, (int)nb_all + 1, st));
+    UZ_CUDA_TRY(cudaMemsetAsync(w.counts, 0, cbytes, st));
+    msm_count_scatter_kernel<true><<<dgrid, 256, 0, st>>>(da, w.counts, w.offsets, w.vals);
     UZ_CUDA_TRY(cudaGetLastError());
-    UZ_CUDA_TRY(cudaMemsetAsync(s->large_list, 0, 4, st));
+    UZ_CUDA_TRY(cudaMemsetAsync(w.large_list, 0, 4, st));
     g_prof.mark(prof, MSM_PH_SORT, st);
 
     // lanes per bucket: ~48 entries per lane, but at least enough groups to fill every SM
@@ -606,25 +623,34 @@ int MsmEngine::run_batch(MsmSrs* s, size_t base_offset, const fe* const* d_scala
     // visit the buckets in decreasing size
     uint32_t cap_bits = 1;
     while ((1u << cap_bits) <= thr + 1) cap_bits++;
-    msm_sizes_kernel<<<(nb_all + 255) / 256, 256, 0, st>>>(s->offsets, nb_all, thr + 1, s->ord_keys_a, s->ord_vals_a);
+    msm_sizes_kernel<<<(nb_all + 255) / 256, 256, 0, st>>>(w.offsets, nb_all, thr + 1, w.ord_keys_a, w.ord_vals_a);
     UZ_CUDA_TRY(cudaGetLastError());
-    cub::DoubleBuffer<uint32_t> ok(s->ord_keys_a, s->ord_keys_b), ov(s->ord_vals_a, s->ord_vals_b);
+    cub::DoubleBuffer<uint32_t> ok(w.ord_keys_a, w.ord_keys_b), ov(w.ord_vals_a, w.ord_vals_b);
     temp = s->cub_temp_bytes;
-    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s->cub_temp, temp, ok, ov, (int)nb_all, 0, (int)cap_bits, st));
+    UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_temp, temp, ok, ov, (int)nb_all, 0, (int)cap_bits, st));
     g_prof.mark(prof, MSM_PH_OFFSETS, st);
+    plan->nb_all = nb_all;
+    plan->lanes = g;
+    plan->thr = thr;
+    plan->order = ov.Current();
+    UZ_COUNT_LAUNCH(3 + 2);  // own kernels + CUB's scan / sort launches
+    return UZKGE_OK;
+}
 
+int MsmEngine::stage_accumulate(MsmSrs* s, MsmWork& w, const GroupPlan& plan, cudaStream_t st, int prof) {
+    if (plan.empty) return UZKGE_OK;
     AccArgs aa;
     aa.tables = s->tables;
-    aa.vals = s->vals;
-    aa.offsets = s->offsets;
-    aa.order = ov.Current();
-    aa.buckets = s->buckets;
-    aa.nb_padded = nb_all;
-    aa.large_threshold = thr;
-    aa.large_list = s->large_list;
+    aa.vals = w.vals;
+    aa.offsets = w.offsets;
+    aa.order = plan.order;
+    aa.buckets = w.buckets;
+    aa.nb_padded = plan.nb_all;
+    aa.large_threshold = plan.thr;
+    aa.large_list = w.large_list;
     aa.large_cap = s->large_cap;
     cudaError_t e;
-    switch (g) {
+    switch (plan.lanes) {
         case 1: e = launch_accumulate<1>(aa, st); break;
         case 2: e = launch_accumulate<2>(aa, st); break;
         case 4: e = launch_accumulate<4>(aa, st); break;
@@ -637,12 +663,12 @@ int MsmEngine::run_batch(MsmSrs* s, size_t base_offset, const fe* const* d_scala
 
     LargeArgs la;
     la.tables = s->tables;
-    la.vals = s->vals;
-    la.offsets = s->offsets;
-    la.buckets = s->buckets;
-    la.large_list = s->large_list;
-    la.slice_start = s->slice_start;
-    la.slice_sums = s->slice_sums;
+    la.vals = w.vals;
+    la.offsets = w.offsets;
+    la.buckets = w.buckets;
+    la.large_list = w.large_list;
+    la.slice_start = w.slice_start;
+    la.slice_sums = w.slice_sums;
     la.large_cap = s->large_cap;
     la.max_slices = s->max_slices;
     // the list lengths are only known on the device: fixed grids whose warps walk the lists
@@ -651,35 +677,121 @@ int MsmEngine::run_batch(MsmSrs* s, size_t base_offset, const fe* const* d_scala
     msm_large_finish_kernel<<<sm_count_ * 2, 128, 0, st>>>(la);
     UZ_CUDA_TRY(cudaGetLastError());
     g_prof.mark(prof, MSM_PH_LARGE, st);
+    UZ_COUNT_LAUNCH(4);
+    return UZKGE_OK;
+}
 
-    // the k bucket reductions are latency-bound chains of small kernels: run them side by side on auxiliary streams
-    if (k == 1) {
-        const int rc = msm_reduce_run(s->reduce[0], d_out, st);
+// the k bucket reductions are latency-bound chains of small kernels: run them side by side on auxiliary streams
+int MsmEngine::stage_reduce(MsmSrs* s, MsmWork& w, uint32_t k, jacobian* d_out, cudaStream_t st) {
+    if (k == 1) return msm_reduce_run(w.reduce[0], d_out, st);
+    while (aux_.size() < k - 1) {
+        cudaStream_t a;
+        cudaEvent_t ev;
+        UZ_CUDA_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        UZ_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        aux_.push_back(a);
+        join_.push_back(ev);
+    }
+    if (!fork_) UZ_CUDA_TRY(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
+    UZ_CUDA_TRY(cudaEventRecord(fork_, st));
+    for (uint32_t j = 0; j < k; j++) {
+        cudaStream_t sj = j == 0 ? st : aux_[j - 1];
+        if (j) UZ_CUDA_TRY(cudaStreamWaitEvent(sj, fork_, 0));
+        const int rc = msm_reduce_run(w.reduce[j], d_out + j, sj);
         if (rc != UZKGE_OK) return rc;
-    } else {
-        while (aux_.size() < k - 1) {
-            cudaStream_t a;
-            cudaEvent_t ev;
-            UZ_CUDA_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-            UZ_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            aux_.push_back(a);
-            join_.push_back(ev);
-        }
-        if (!fork_) UZ_CUDA_TRY(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
-        UZ_CUDA_TRY(cudaEventRecord(fork_, st));
-        for (uint32_t j = 0; j < k; j++) {
-            cudaStream_t sj = j == 0 ? st : aux_[j - 1];
-            if (j) UZ_CUDA_TRY(cudaStreamWaitEvent(sj, fork_, 0));
-            const int rc = msm_reduce_run(s->reduce[j], d_out + j, sj);
-            if (rc != UZKGE_OK) return rc;
-            if (j) {
-                UZ_CUDA_TRY(cudaEventRecord(join_[j - 1], sj));
-                UZ_CUDA_TRY(cudaStreamWaitEvent(st, join_[j - 1], 0));
-            }
+        if (j) {
+            UZ_CUDA_TRY(cudaEventRecord(join_[j - 1], sj));
+            UZ_CUDA_TRY(cudaStreamWaitEvent(st, join_[j - 1], 0));
         }
     }
+    return UZKGE_OK;
+}
+
+static int msm_check_group(const MsmSrs* s, size_t base_offset, const size_t* n, size_t k) {
+    if (base_offset > s->n) return UZKGE_ERR_SIZE;
+    for (size_t j = 0; j < k; j++)
+        if (n[j] > s->n - base_offset) return UZKGE_ERR_SIZE;
+    return UZKGE_OK;
+}
+
+// k <= s->slots independent MSMs over srs[base_offset ..] in one pass on `st`; d_out receives k Jacobian points
+int MsmEngine::run_batch(MsmSrs* s, size_t base_offset, const fe* const* d_scalars, const size_t* n, uint32_t k, jacobian* d_out,
+                         cudaStream_t st) {
+    if (k == 0) return UZKGE_OK;
+    if (k > s->slots || msm_check_group(s, base_offset, n, k) != UZKGE_OK) return UZKGE_ERR_SIZE;
+    MsmWork& w = s->work[0];
+    GroupPlan plan;
+    const int prof = g_prof.begin(Profiler::MSM, st);
+    int rc = stage_sort(s, w, base_offset, d_scalars, n, k, &plan, st, prof);
+    if (rc != UZKGE_OK) return rc;
+    if (plan.empty) {
+        for (uint32_t j = 0; j < k; j++) msm_identity_kernel<<<1, 1, 0, st>>>(d_out + j);
+        UZ_COUNT_LAUNCH(k);
+        UZ_CUDA_TRY(cudaGetLastError());
+        return UZKGE_OK;
+    }
+    rc = stage_accumulate(s, w, plan, st, prof);
+    if (rc != UZKGE_OK) return rc;
+    rc = stage_reduce(s, w, k, d_out, st);
+    if (rc != UZKGE_OK) return rc;
     g_prof.mark(prof, MSM_PH_REDUCE, st);
-    UZ_COUNT_LAUNCH(7 + 2 + 3);  // own kernels (the reductions count their own) + CUB's scan / sort launches
+    return UZKGE_OK;
+}
+
+// Any number of MSMs, in groups of s->slots.  Group g uses workspace g % 2 and three internal streams:
+//   s_sort : sort(g)        after  the caller's stream at entry,  accumulate(g - 2)   (it read this workspace's entries)
+//   s_acc  : accumulate(g)  after  sort(g),  reduce(g - 2)                          (it read this workspace's buckets)
+//   s_red  : reduce(g)      after  accumulate(g)
+// so the L2-atomic-bound sort and the latency-bound reduction run under the multiplier-bound accumulate kernel of a neighbour.
+int MsmEngine::run_pipelined(MsmSrs* s, size_t base_offset, const fe* const* d_scalars, const size_t* n, size_t k, jacobian* d_out,
+                             cudaStream_t st, const cudaEvent_t* ready) {
+    if (k == 0) return UZKGE_OK;
+    if (msm_check_group(s, base_offset, n, k) != UZKGE_OK) return UZKGE_ERR_SIZE;
+    if (k <= s->slots) {
+        if (ready) UZ_CUDA_TRY(cudaStreamWaitEvent(st, ready[k - 1], 0));
+        return run_batch(s, base_offset, d_scalars, n, (uint32_t)k, d_out, st);
+    }
+    if (!s_sort_) {
+        // the short sort / reduction kernels must not queue behind the thousands of pending CTAs of an accumulate launch
+        int prio_lo = 0, prio_hi = 0;
+        UZ_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        UZ_CUDA_TRY(cudaStreamCreateWithPriority(&s_sort_, cudaStreamNonBlocking, prio_hi));
+        UZ_CUDA_TRY(cudaStreamCreateWithPriority(&s_acc_, cudaStreamNonBlocking, prio_lo));
+        UZ_CUDA_TRY(cudaStreamCreateWithPriority(&s_red_, cudaStreamNonBlocking, prio_hi));
+        UZ_CUDA_TRY(cudaEventCreateWithFlags(&start_, cudaEventDisableTiming));
+    }
+    UZ_CUDA_TRY(cudaEventRecord(start_, st));
+    UZ_CUDA_TRY(cudaStreamWaitEvent(s_sort_, start_, 0));
+    UZ_CUDA_TRY(cudaStreamWaitEvent(s_red_, start_, 0));   // d_out may be in use by earlier work of the caller's stream
+    size_t g = 0;
+    for (size_t j0 = 0; j0 < k; j0 += s->slots, g++) {
+        const uint32_t kk = (uint32_t)((k - j0) < s->slots ? (k - j0) : s->slots);
+        MsmWork& w = s->work[g & 1];
+        GroupPlan plan;
+        if (g >= 2) UZ_CUDA_TRY(cudaStreamWaitEvent(s_sort_, w.accumulated, 0));
+        if (ready) UZ_CUDA_TRY(cudaStreamWaitEvent(s_sort_, ready[j0 + kk - 1], 0));   // events of one stream fire in order
+        int rc = stage_sort(s, w, base_offset, d_scalars + j0, n + j0, kk, &plan, s_sort_, -1);
+        if (rc != UZKGE_OK) return rc;
+        UZ_CUDA_TRY(cudaEventRecord(w.sorted, s_sort_));
+        UZ_CUDA_TRY(cudaStreamWaitEvent(s_acc_, w.sorted, 0));
+        if (g >= 2) UZ_CUDA_TRY(cudaStreamWaitEvent(s_acc_, w.reduced, 0));
+        rc = stage_accumulate(s, w, plan, s_acc_, -1);
+        if (rc != UZKGE_OK) return rc;
+        UZ_CUDA_TRY(cudaEventRecord(w.accumulated, s_acc_));
+        UZ_CUDA_TRY(cudaStreamWaitEvent(s_red_, w.accumulated, 0));
+        if (plan.empty) {
+            for (uint32_t j = 0; j < kk; j++) msm_identity_kernel<<<1, 1, 0, s_red_>>>(d_out + j0 + j);
+            UZ_COUNT_LAUNCH(kk);
+            UZ_CUDA_TRY(cudaGetLastError());
+        } else {
+            rc = stage_reduce(s, w, kk, d_out + j0, s_red_);
+            if (rc != UZKGE_OK) return rc;
+        }
+        UZ_CUDA_TRY(cudaEventRecord(w.reduced, s_red_));
+    }
+    // the caller's stream continues once every group is reduced (s_red_ is in order: its last event covers them all)
+    UZ_CUDA_TRY(cudaStreamWaitEvent(st, s->work[(g - 1) & 1].reduced, 0));
+    if (g >= 2) UZ_CUDA_TRY(cudaStreamWaitEvent(st, s->work[g & 1].reduced, 0));
     return UZKGE_OK;
 }
 

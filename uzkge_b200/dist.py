@@ -176,3 +176,115 @@ def ntt_fr_distributed_emulated(xs, n_total: int, inverse: bool = False, natural
         return ys
     back = all_to_all(ys)
     return [b.view(world, S, 4).permute(1, 0, 2).contiguous().view(-1) for b in back]
+
+
+# ------------------------------------------------------------------------------------------------ point-split commitments for the prover
+class SplitCommitter:
+    """KZG commitments of DEVICE-RESIDENT coefficient vectors with the SRS points split over the ranks (SURVEY 8e, row "MSM"),
+    driven by rank 0 -- the rank that runs the prover (uzkge_b200/plonk.py) and owns the polynomials.
+
+    Rank r keeps the bases [r * chunk, (r + 1) * chunk) resident (window tables included).  Per commitment: rank 0 broadcasts a
+    16-byte header, scatters the scalar vector in `chunk`-sized pieces (NCCL scatter over NVLink: 32 B per point leave rank 0
+    once), every rank runs the MSM over its piece, the 96-byte partial sums are gathered to rank 0 and combined with world - 1
+    projective additions.  Ranks > 0 sit in `serve()` until rank 0 calls `shutdown()`.
+
+    `msm_fn(handle, t_scalars, n) -> 12 x int64 tensor` and `add_fn` default to the CUDA backend; the CPU tests (gloo) inject the
+    checker to exercise the protocol without a GPU.
+    """
+
+    OP_EXIT, OP_COMMIT = 0, 1
+
+    def __init__(self, affine_xy: np.ndarray, rank: int, world: int, device=None, group=None, window_bits: int = 0,
+                 upload: Callable = None, msm_fn: Callable = None, add_fn: Callable = None):
+        import torch
+
+        pts = ffi.as_u64(affine_xy, 8)
+        self.n = pts.shape[0]
+        self.rank, self.world, self.group = rank, world, group
+        self.device = device if device is not None else torch.device("cpu")
+        self.chunk = (self.n + world - 1) // world
+        self.lo = min(self.n, rank * self.chunk)
+        self.hi = min(self.n, self.lo + self.chunk)
+        upload = upload or (lambda p: ffi.srs_upload(p, window_bits))
+        self.handle = upload(pts[self.lo: self.hi]) if self.hi > self.lo else None
+        self._msm = msm_fn or self._msm_cuda
+        self._add = add_fn or ffi.g1_add
+        self._recv = torch.zeros(4 * self.chunk, dtype=torch.int64, device=self.device)
+        self._pad = torch.zeros(4 * self.chunk * world, dtype=torch.int64, device=self.device) if rank == 0 else None
+        self._hdr = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._part = torch.zeros(12, dtype=torch.int64, device=self.device)
+        self._parts = [torch.zeros(12, dtype=torch.int64, device=self.device) for _ in range(world)] if rank == 0 else None
+        self.commits = 0
+
+    def max_degree(self) -> int:
+        return self.n - 1
+
+    def _msm_cuda(self, handle, t_scalars, n: int):
+        ffi.msm_g1_device(handle, t_scalars.data_ptr(), n, self._part.data_ptr())
+        return self._part
+
+    def _step(self, length: int, src_tensor=None) -> np.ndarray | None:
+        """One commitment; collective: every rank calls it with the same `length`."""
+        import torch.distributed as dist
+
+        if self.rank == 0:
+            self._pad[: 4 * length].copy_(src_tensor[: 4 * length])
+            dist.scatter(self._recv, list(self._pad.split(4 * self.chunk)), src=0, group=self.group)
+        else:
+            dist.scatter(self._recv, None, src=0, group=self.group)
+        mine = max(0, min(length, self.hi) - self.lo)
+        if mine and self.handle is not None:
+            part = self._msm(self.handle, self._recv, mine)
+        else:
+            part = self._part.zero_()   # Z = 0: the identity
+        dist.gather(part, self._parts, dst=0, group=self.group)
+        if self.rank != 0:
+            return None
+        parts = [p.cpu().numpy().view(np.uint64) for p in self._parts]
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = self._add(acc, p)
+        return np.asarray(acc, dtype=np.uint64).reshape(12).copy()
+
+    def commit_device(self, vecs) -> list:
+        """Rank 0: commit to device vectors (objects with `.t` = int64 tensor of 4 words per element and `.len`)."""
+        import torch.distributed as dist
+
+        from .errors import DegreeError
+        from .poly_commit import KZGCommitment
+
+        assert self.rank == 0, "only rank 0 drives commitments; the other ranks call serve()"
+        out = []
+        for v in vecs:
+            if v.len > self.n:
+                raise DegreeError("DegreeError")
+            self._hdr[0], self._hdr[1] = self.OP_COMMIT, v.len
+            dist.broadcast(self._hdr, src=0, group=self.group)
+            out.append(KZGCommitment(self._step(v.len, v.t)))
+            self.commits += 1
+        return out
+
+    def serve(self) -> int:
+        """Ranks > 0: answer rank 0's commitments until it shuts the service down.  Returns the number served."""
+        import torch.distributed as dist
+
+        assert self.rank != 0
+        while True:
+            dist.broadcast(self._hdr, src=0, group=self.group)
+            op, length = (int(x) for x in self._hdr.cpu())
+            if op == self.OP_EXIT:
+                return self.commits
+            self._step(length)
+            self.commits += 1
+
+    def shutdown(self) -> None:
+        import torch.distributed as dist
+
+        assert self.rank == 0
+        self._hdr[0], self._hdr[1] = self.OP_EXIT, 0
+        dist.broadcast(self._hdr, src=0, group=self.group)
+
+    def close(self) -> None:
+        if self.handle is not None:
+            ffi.srs_free(self.handle)
+            self.handle = None

@@ -395,15 +395,18 @@ def _coset_fft(poly: DevVec, m: int, k1: np.ndarray, out: DevVec, scratch: DevVe
     ffi.ntt_fr_device(poly.ptr, out.ptr, scratch.ptr, poly.len, m, False, k1)
 
 
-def _commit_dev(pcs: KZGCommitmentSchemeBN254, vecs) -> list:
-    """PolyComScheme::commit for device-resident coefficient vectors; independent commitments share one pass when they fit."""
-    dev = vecs[0].t.device
+def _commit_dev(pcs, vecs) -> list:
+    """PolyComScheme::commit for device-resident coefficient vectors; independent commitments share one pass when they fit.
+    `pcs` is a KZGCommitmentSchemeBN254 (bases on this GPU) or anything with `commit_device` (dist.SplitCommitter: bases split
+    over the GPUs of the box)."""
     for v in vecs:
         if v.len > pcs.max_degree() + 1:
             raise DegreeError("DegreeError")
+    if hasattr(pcs, "commit_device"):
+        return pcs.commit_device(vecs)
+    dev = vecs[0].t.device
     out = torch.zeros(12 * len(vecs), dtype=torch.int64, device=dev)
-    slots = pcs.info()["batch_slots"]
-    if 1 < len(vecs) <= slots:
+    if len(vecs) > 1:   # one call: the engine batches what fits one pass and pipelines the rest
         ffi.msm_g1_batch_device(pcs.handle, [v.ptr for v in vecs], [v.len for v in vecs], out.data_ptr())
     else:
         for i, v in enumerate(vecs):
@@ -430,7 +433,7 @@ def _add_coefs(poly: DevVec, idx, vals) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- indexer
-def indexer(cs: TurboCS, pcs: KZGCommitmentSchemeBN254) -> PlonkProverParams:
+def indexer(cs: TurboCS, pcs) -> PlonkProverParams:
     """plonk/indexer.rs:240-536 with lagrange_pcs = None, permutation = None, verifier_params = None."""
     if cs.selectors is None:
         raise UzkgeError("call cs.pad() before indexing")
@@ -519,11 +522,7 @@ def indexer(cs: TurboCS, pcs: KZGCommitmentSchemeBN254) -> PlonkProverParams:
 
 
 def _commit_many(pcs, vecs) -> list:
-    out = []
-    slots = max(1, pcs.info()["batch_slots"])
-    for i in range(0, len(vecs), slots):
-        out.extend(_commit_dev(pcs, vecs[i:i + slots]))
-    return out
+    return _commit_dev(pcs, vecs)
 
 
 # ---------------------------------------------------------------------------------------------- prover
@@ -566,7 +565,7 @@ def batch_prove(pcs, transcript: Transcript, polys, evals, point: int, max_degre
     return _commit_dev(pcs, [scratch_q])[0]
 
 
-def prover(prng, transcript: Transcript, pcs: KZGCommitmentSchemeBN254, cs: TurboCS, prover_params: PlonkProverParams, w,
+def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkProverParams, w,
            timings: dict | None = None) -> PlonkProof:
     """plonk/prover.rs:76-394.  `w`: the witness, (num_vars, 4) Montgomery limbs (numpy) or a DevVec already in HBM."""
     if cs.is_verifier_only():
