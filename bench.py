@@ -537,7 +537,8 @@ def main() -> int:
                     "h2d_bytes_per_step": 32 * r["n"], "d2h_bytes_per_step": 96},
             "roofline": {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": 96.0 * r["n"] / (r["acc_ms"] * 1e-3) / 1e9,
                          "peak": hbm_peak, "unit": "GB/s", "frac": 96.0 * r["n"] / (r["acc_ms"] * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": None, "kernel_ms": r["acc_ms"], "peak_source": peak_src,
+                         "traffic": 1.791135e9 + 62.801664e6, "traffic_source": "ncu --set full, profiles/r1c_msm_raw.csv (dram read + write per "
+                         "launch at 2^20, c = 20: 13.1 M random 64-byte table gathers)", "kernel_ms": r["acc_ms"], "peak_source": peak_src,
                          "note": "MSM is integer-pipe bound, never HBM bound (SURVEY 8d): see int_roofline"},
             # 10 Fq products per mixed addition; the first point of a bucket is a copy: N*W - 2^(c-1) additions
             "int_roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": r["acc_fq_mul"] / (r["acc_ms"] * 1e-3) / 1e9,
@@ -561,7 +562,9 @@ def main() -> int:
                     "h2d_bytes_per_step": 32 * r["n"], "d2h_bytes_per_step": 32 * r["n"]},
             "roofline": {"bound": "hbm", "kernel": f"ntt_pass_kernel ({top})", "achieved": 64.0 * r["n"] / (top_ms * 1e-3) / 1e9,
                          "peak": hbm_peak, "unit": "GB/s", "frac": 64.0 * r["n"] / (top_ms * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": None, "kernel_ms": top_ms, "peak_source": peak_src, "passes": passes},
+                         "traffic": 134.431744e6 + 85.389312e6, "traffic_source": "ncu --set full, profiles/r1c_ntt_raw.csv (pass 0 of a 2^22 "
+                         "transform: dram read + write; part of the 128 MiB written stays in L2)", "kernel_ms": top_ms,
+                         "peak_source": peak_src, "passes": passes},
             # Fr products per transform: (N/2) log2 N butterflies + N inter-pass twiddles per pass boundary
             "int_roofline": {"bound": "imad", "achieved": (r["n"] / 2 * lg + r["n"] * (passes - 1)) / (r["ms"] * 1e-3) / 1e9,
                              "peak": fq_peak / 1e9, "unit": "G Fr-mul/s",

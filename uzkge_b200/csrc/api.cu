@@ -23,6 +23,10 @@ Profiler g_prof;
 
 using namespace uz;
 
+namespace uz {
+extern int g_quotient_min_blocks;  // quotient.cu
+}
+
 namespace {
 
 thread_local std::string t_error;
@@ -640,6 +644,10 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
             g.ntt.reset(new NttEngine(g.sm_count));
             g.ntt->configure(g.ntt_log_tile, g.ntt_max_log_r, g.ntt_two_pass_max);
         }
+        return UZKGE_OK;
+    }
+    if (k == "quotient_min_blocks") {
+        g_quotient_min_blocks = (int)value;
         return UZKGE_OK;
     }
     return fail(UZKGE_ERR_ARG, "configure: unknown key");

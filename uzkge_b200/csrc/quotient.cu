@@ -42,7 +42,10 @@ __device__ __forceinline__ fe fr_pow5(const fe& x) {
     return FR_MUL(x, FR_MUL(x2, x2));
 }
 
-__global__ void __launch_bounds__(128) plonk_quotient_kernel(const QuotientDev a) {
+int g_quotient_min_blocks = 4;  // tuning knob (uzkge_cuda_configure "quotient_min_blocks"): 1 = 138 registers, 4 = 128 registers
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) plonk_quotient_kernel(const QuotientDev a) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.m) return;
     const uint64_t pn = (p + a.factor) % a.m;  // the omega-shifted point (helpers.rs:308, 349-351)
@@ -78,14 +81,23 @@ __global__ void __launch_bounds__(128) plonk_quotient_kernel(const QuotientDev a
     const fe t4 = FR_MUL(FR_MUL(a.alpha_pow[2], ld_fe(a.l1 + p)), FR_SUB(z, one));
     t = FR_ADD(t, FR_SUB(t4, t3));
     // term5..7: boolean constraints (helpers.rs:324-346)
+    // (every term carries the factor qb: rows without the boolean selector -- almost all -- skip the 9 products)
     const fe qb = ld_fe(a.qb + p);
+    if (!fe_is_zero(qb)) {
 #pragma unroll
-    for (int j = 1; j <= 3; j++)
-        t = FR_ADD(t, FR_MUL(FR_MUL(FR_MUL(a.alpha_pow[2 + j], qb), w[j]), FR_SUB(w[j], one)));
+        for (int j = 1; j <= 3; j++)
+            t = FR_ADD(t, FR_MUL(FR_MUL(FR_MUL(a.alpha_pow[2 + j], qb), w[j]), FR_SUB(w[j], one)));
+    }
 
     // term8..11: the Anemoi round constraints (helpers.rs:348-433)
+    // all four carry the factor q_prk3, which is zero outside the Anemoi rows: those points skip the 34 products and 7 loads
+    const fe prk3 = ld_fe(a.q_prk[2] + p);
+    if (fe_is_zero(prk3)) {
+        st_fe(a.out + p, FR_MUL(t, a.z_h_inv[p % a.factor]));
+        return;
+    }
     const fe w0n = ld_fe(a.w[0] + pn), w1n = ld_fe(a.w[1] + pn), w2n = ld_fe(a.w[2] + pn);
-    const fe prk1 = ld_fe(a.q_prk[0] + p), prk2 = ld_fe(a.q_prk[1] + p), prk3 = ld_fe(a.q_prk[2] + p), prk4 = ld_fe(a.q_prk[3] + p);
+    const fe prk1 = ld_fe(a.q_prk[0] + p), prk2 = ld_fe(a.q_prk[1] + p), prk4 = ld_fe(a.q_prk[3] + p);
     const fe w30 = FR_ADD(w[0], w[3]), w21 = FR_ADD(w[1], w[2]);
     const fe w320 = FR_ADD(w[0], w30), w221 = FR_ADD(w[1], w21);
     {
@@ -146,7 +158,10 @@ int plonk_quotient_run(const uzkge_quotient_args* args, void* d_out, cudaStream_
     d.m = args->m;
     d.factor = (uint32_t)args->factor;
     d.out = (fe*)d_out;
-    plonk_quotient_kernel<<<(unsigned)((d.m + 127) / 128), 128, 0, st>>>(d);
+    if (g_quotient_min_blocks >= 4)
+        plonk_quotient_kernel<4><<<(unsigned)((d.m + 127) / 128), 128, 0, st>>>(d);
+    else
+        plonk_quotient_kernel<1><<<(unsigned)((d.m + 127) / 128), 128, 0, st>>>(d);
     UZ_COUNT_LAUNCH(1);
     return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
 }
