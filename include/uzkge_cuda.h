@@ -116,6 +116,11 @@ UZKGE_API int32_t uzkge_cuda_poly_div_linear_fr(const uint64_t* coefs, size_t n,
 /* Device-resident Horner scan: *d_value = p(z); d_quotient (n - 1 elements, may be NULL) = p / (X - z).  No copies, no sync. */
 UZKGE_API int32_t uzkge_cuda_poly_horner_fr_device(const void* d_coefs, size_t n, const uint64_t z_host[4], void* d_quotient, void* d_value,
                                                    void* stream);
+/* k <= UZKGE_EVAL_BATCH_MAX evaluations in two launches: d_values[j] = polys[j](points[point_index[j]]), at most two distinct
+ * points (the prover opens 11 polynomials at zeta and 4 at zeta * omega, plonk/prover.rs:217-244).  No copies, no sync. */
+#define UZKGE_EVAL_BATCH_MAX 32
+UZKGE_API int32_t uzkge_cuda_poly_eval_batch_fr_device(const void* const* d_polys, const size_t* lens, const uint32_t* point_index, size_t k,
+                                                       const uint64_t* points_host, size_t npoints, void* d_values, void* stream);
 /* The grand product of z_poly (plonk/helpers.rs:204-217: batch_inversion of the denominators, then the running product):
  * out[0] = 1, out[i + 1] = out[i] * num[i] / den[i], i < n  (n + 1 outputs).  UZKGE_ERR_ARG if a denominator is zero. */
 UZKGE_API int32_t uzkge_cuda_grand_product_fr(const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out);

@@ -119,3 +119,28 @@ def test_grand_product_edge_cases(gpu, oc, bn):
     # num == den: z stays 1 (the permutation argument's invariant z(1) = 1 ... prod = 1, helpers.rs:1441-1473)
     same = gpu.grand_product_fr(num, num)
     assert ints(bn, same) == [1] * 11
+
+
+def test_eval_batch_matches_oracle(gpu, oc):
+    """uzkge_cuda_poly_eval_batch_fr_device: ragged polynomials (one coefficient ... several hundred tiles), two points, k = 1 and
+    k = 32, against the oracle's Horner evaluation."""
+    import torch
+
+    lens = [1, 2, 5, 1023, 1024, 1025, 4099, 16387, 300007, (1 << 18) + 3]
+    lens = (lens * 4)[:32]
+    polys = [oc.random_fr(n, 700 + i) for i, n in enumerate(lens)]
+    pts = oc.random_fr(2, 9)
+    d = [torch.from_numpy(p.view(np.int64).reshape(-1)).cuda() for p in polys]
+    for k in (1, 7, 32):
+        idx = [(j * 5 + 1) % 2 for j in range(k)]
+        vals = torch.zeros(4 * k, dtype=torch.int64, device="cuda")
+        gpu.poly_eval_batch_fr_device([t.data_ptr() for t in d[:k]], lens[:k], idx, pts, vals.data_ptr())
+        torch.cuda.synchronize()
+        got = vals.cpu().numpy().view(np.uint64).reshape(k, 4)
+        for j in range(k):
+            assert np.array_equal(got[j], oc.fr_eval(polys[j], pts[idx[j]])), (k, j, lens[j])
+    # a single point
+    vals = torch.zeros(8, dtype=torch.int64, device="cuda")
+    gpu.poly_eval_batch_fr_device([d[3].data_ptr(), d[8].data_ptr()], [lens[3], lens[8]], [0, 0], pts[:1], vals.data_ptr())
+    got = vals.cpu().numpy().view(np.uint64).reshape(2, 4)
+    assert np.array_equal(got[0], oc.fr_eval(polys[3], pts[0])) and np.array_equal(got[1], oc.fr_eval(polys[8], pts[0]))

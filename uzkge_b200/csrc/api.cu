@@ -409,6 +409,21 @@ UZKGE_API int32_t uzkge_cuda_poly_horner_fr_device(const void* d_coefs, size_t n
     return engine_fail(rc, "poly_horner_fr_device");
 }
 
+UZKGE_API int32_t uzkge_cuda_poly_eval_batch_fr_device(const void* const* d_polys, const size_t* lens, const uint32_t* point_index, size_t k,
+                                                       const uint64_t* points_host, size_t npoints, void* d_values, void* stream) {
+    if (k && (!d_polys || !lens || !point_index || !points_host || !d_values)) return fail(UZKGE_ERR_ARG, "poly_eval_batch_fr_device: null pointer");
+    if (k > UZKGE_EVAL_BATCH_MAX || npoints > 2) return fail(UZKGE_ERR_SIZE, "poly_eval_batch_fr_device: k <= 32, at most two points");
+    API_ENTER(-1);
+    fe pts[2];
+    memcpy(pts, points_host, npoints * sizeof(fe));
+    uint64_t n64[UZKGE_EVAL_BATCH_MAX];
+    for (size_t j = 0; j < k; j++) n64[j] = lens[j];
+    int rc = g.poly->eval_batch((const fe* const*)d_polys, n64, point_index, (uint32_t)k, pts, (uint32_t)npoints, (fe*)d_values, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "poly_eval_batch_fr_device: empty polynomial or bad point index");
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "poly_eval_batch_fr_device: null polynomial");
+    return engine_fail(rc, "poly_eval_batch_fr_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_grand_product_fr(const uint64_t* num, const uint64_t* den, size_t n, uint64_t* out) {
     if (!out || (n && (!num || !den))) return fail(UZKGE_ERR_ARG, "grand_product_fr: null pointer");
     API_ENTER(-1);

@@ -211,6 +211,9 @@ public:
     ~PolyEngine();
     // T_k = c_k + z T_{k+1}: *d_value = T_0 = p(z);  d_quot (n - 1 coefficients, may be null) = p / (X - z)
     int horner(const fe* d_c, uint64_t n, const fe& z, fe* d_quot, fe* d_value, cudaStream_t st);
+    // d_values[j] = p_j(points[point[j]]), k pairs in two launches
+    int eval_batch(const fe* const* d_c, const uint64_t* n, const uint32_t* point, uint32_t k, const fe* points, uint32_t npoints,
+                   fe* d_values, cudaStream_t st);
     // d_out[0] = 1, d_out[i + 1] = prod_{j <= i} num_j / den_j  (n + 1 outputs);  d_tmp: 2 n + 2 elements
     int grand_product(const fe* d_num, const fe* d_den, uint64_t n, fe* d_out, fe* d_tmp, cudaStream_t st);
 

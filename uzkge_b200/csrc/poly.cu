@@ -135,6 +135,69 @@ __global__ void __launch_bounds__(PT) horner_apply_kernel(const fe* __restrict__
     }
 }
 
+// ------------------------------------------------------------------ batched evaluation: k (polynomial, point) pairs in two launches
+// (the prover's 15 openings at zeta / zeta * omega, plonk/prover.rs:217-244: at n = 2^14 one pair is two latency-bound launches)
+struct EvalBatch {
+    const fe* c[UZKGE_EVAL_BATCH_MAX];
+    uint64_t n[UZKGE_EVAL_BATCH_MAX];
+    uint32_t tile0[UZKGE_EVAL_BATCH_MAX + 1];  // first tile of pair j in the aggregate array
+    uint32_t point[UZKGE_EVAL_BATCH_MAX];      // index into zt[]
+    Pow2Table zt[2];                           // at most two distinct points per batch
+    uint32_t k;
+};
+
+__global__ void __launch_bounds__(PT) horner_batch_agg_kernel(const __grid_constant__ EvalBatch b, fe* __restrict__ agg) {
+    // blockIdx.x enumerates the tiles of all pairs: find the pair by a linear walk (k <= 32)
+    uint32_t j = 0;
+    while (j + 1 < b.k && blockIdx.x >= b.tile0[j + 1]) j++;
+    const uint32_t tile = blockIdx.x - b.tile0[j];
+    const Pow2Table& zt = b.zt[b.point[j]];
+    const fe* c = b.c[j];
+    const uint64_t n = b.n[j];
+    __shared__ fe sh[PT];
+    const uint64_t lo = (uint64_t)tile * TILE + (uint64_t)threadIdx.x * PE;
+    fe a = fe_zero();
+#pragma unroll
+    for (int i = PE - 1; i >= 0; i--) {
+        a = fe_mul<FrP>(a, zt.p[0]);
+        if (lo + i < n) a = fe_add<FrP>(a, ld_fe(c + lo + i));
+    }
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (uint32_t s = 0; (1u << s) < PT; s++) {
+        const uint32_t stride = 1u << s;
+        if ((threadIdx.x & (2 * stride - 1)) == 0)
+            sh[threadIdx.x] = fe_add<FrP>(sh[threadIdx.x], fe_mul<FrP>(sh[threadIdx.x + stride], zt.p[s + 2]));
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_fe(agg + blockIdx.x, sh[0]);
+}
+
+// one CTA per pair: value = sum_t agg[t] z^(TILE t), a tree over the tile aggregates
+__global__ void __launch_bounds__(256) horner_batch_total_kernel(const __grid_constant__ EvalBatch b, const fe* __restrict__ agg, fe* __restrict__ values) {
+    const uint32_t j = blockIdx.x;
+    const Pow2Table& zt = b.zt[b.point[j]];
+    const uint32_t nt = b.tile0[j + 1] - b.tile0[j];
+    const fe* a = agg + b.tile0[j];
+    __shared__ fe sh[256];
+    // thread t folds the tiles t, t + 256, ... (Horner in z^(256 TILE)), then a 256-wide tree in z^TILE
+    const fe zbig = zt.p[LOG_TILE + 8];
+    fe acc = fe_zero();
+    if (threadIdx.x < nt) {
+        uint32_t last = threadIdx.x + ((nt - 1 - threadIdx.x) / 256) * 256;
+        for (int64_t t = last; t >= (int64_t)threadIdx.x; t -= 256) acc = fe_add<FrP>(fe_mul<FrP>(acc, zbig), ld_fe(a + t));
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = 0; s < 8; s++) {
+        const uint32_t stride = 1u << s;
+        if ((threadIdx.x & (2 * stride - 1)) == 0)
+            sh[threadIdx.x] = fe_add<FrP>(sh[threadIdx.x], fe_mul<FrP>(sh[threadIdx.x + stride], zt.p[LOG_TILE + s]));
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_fe(values + j, sh[0]);
+}
+
 // ------------------------------------------------------------------ product scans
 // REVERSE = false: inclusive prefix products P_i;  true: inclusive suffix products S_i
 template <bool REVERSE>
@@ -267,6 +330,34 @@ int PolyEngine::horner(const fe* d_c, uint64_t n, const fe& z, fe* d_quot, fe* d
     horner_carry_kernel<<<1, 1024, 0, st>>>(agg, nt, zt, carry, d_value);
     if (d_quot && n > 1) horner_apply_kernel<<<nt, PT, 0, st>>>(d_c, n, zt, carry, d_quot);
     UZ_COUNT_LAUNCH(d_quot && n > 1 ? 3 : 2);
+    return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
+}
+
+// values[j] = p_j(x_{point[j]}): k <= UZKGE_EVAL_BATCH_MAX pairs, at most two distinct points
+int PolyEngine::eval_batch(const fe* const* d_c, const uint64_t* n, const uint32_t* point, uint32_t k, const fe* points, uint32_t npoints,
+                           fe* d_values, cudaStream_t st) {
+    if (k == 0) return UZKGE_OK;
+    if (k > UZKGE_EVAL_BATCH_MAX || npoints == 0 || npoints > 2) return UZKGE_ERR_SIZE;
+    EvalBatch b;
+    memset(&b, 0, sizeof(b));
+    uint32_t tiles = 0;
+    for (uint32_t j = 0; j < k; j++) {
+        if (n[j] == 0 || n[j] > (1ull << 32) || point[j] >= npoints) return UZKGE_ERR_SIZE;
+        if (!d_c[j]) return UZKGE_ERR_ARG;
+        b.c[j] = d_c[j];
+        b.n[j] = n[j];
+        b.point[j] = point[j];
+        b.tile0[j] = tiles;
+        tiles += (uint32_t)((n[j] + TILE - 1) / TILE);
+    }
+    b.tile0[k] = tiles;
+    b.k = k;
+    for (uint32_t i = 0; i < npoints; i++) b.zt[i] = make_pow2(points[i]);
+    if (reserve(&ws_, &ws_cap_, sizeof(fe) * ((size_t)tiles + 8)) != cudaSuccess) return UZKGE_ERR_OOM;
+    fe* agg = (fe*)ws_;
+    horner_batch_agg_kernel<<<tiles, PT, 0, st>>>(b, agg);
+    horner_batch_total_kernel<<<k, 256, 0, st>>>(b, agg, d_values);
+    UZ_COUNT_LAUNCH(2);
     return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
 }
 

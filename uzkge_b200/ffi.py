@@ -86,6 +86,10 @@ _SIGNATURES = {
     "uzkge_cuda_poly_eval_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_poly_div_linear_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_poly_horner_fr_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_poly_eval_batch_fr_device": (
+        C.c_int32,
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
+    ),
     "uzkge_cuda_grand_product_fr": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_plonk_quotient_fr_device": (C.c_int32, [C.POINTER(QuotientArgs), C.c_void_p, C.c_void_p]),
     "uzkge_cuda_fr_lincomb_device": (
@@ -331,6 +335,19 @@ def poly_div_linear_fr(coefs, z):
 
 def poly_horner_fr_device(d_coefs: int, n: int, z, d_quotient: int, d_value: int, stream: int = 0) -> None:
     check(lib().uzkge_cuda_poly_horner_fr_device(d_coefs, n, ptr(as_u64(z).reshape(4)), d_quotient or None, d_value, stream))
+
+
+EVAL_BATCH_MAX = 32
+
+
+def poly_eval_batch_fr_device(d_polys, lens, point_index, points, d_values: int, stream: int = 0) -> None:
+    """d_values[j] = polys[j](points[point_index[j]]); points: (1 or 2, 4) Montgomery limbs on the host."""
+    k = len(d_polys)
+    pts = as_u64(points, 4)
+    pp = (C.c_void_p * k)(*[int(x) for x in d_polys])
+    ll = (C.c_size_t * k)(*[int(x) for x in lens])
+    ii = (C.c_uint32 * k)(*[int(x) for x in point_index])
+    check(lib().uzkge_cuda_poly_eval_batch_fr_device(pp, ll, ii, k, ptr(pts), pts.shape[0], d_values, stream))
 
 
 def grand_product_fr(num, den) -> np.ndarray:

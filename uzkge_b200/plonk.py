@@ -416,10 +416,18 @@ def _commit_dev(pcs, vecs) -> list:
 
 
 def _evals(polys_points, dev) -> list[int]:
-    """FpPolynomial::eval for (poly, point) pairs: Horner scans on the device, one small D2H for all values."""
+    """FpPolynomial::eval for (poly, point) pairs: one batched Horner evaluation on the device (two launches), one small D2H."""
     vals = torch.zeros(4 * len(polys_points), dtype=torch.int64, device=dev)
-    for i, (p, x) in enumerate(polys_points):
-        ffi.poly_horner_fr_device(p.ptr, max(p.len, 1), mont(x), 0, vals.data_ptr() + 32 * i)
+    points = []
+    for _, x in polys_points:
+        if x not in points:
+            points.append(x)
+    if len(points) <= 2 and len(polys_points) <= ffi.EVAL_BATCH_MAX:
+        ffi.poly_eval_batch_fr_device([p.ptr for p, _ in polys_points], [max(p.len, 1) for p, _ in polys_points],
+                                      [points.index(x) for _, x in polys_points], mont_rows(points), vals.data_ptr())
+    else:
+        for i, (p, x) in enumerate(polys_points):
+            ffi.poly_horner_fr_device(p.ptr, max(p.len, 1), mont(x), 0, vals.data_ptr() + 32 * i)
     rows = vals.cpu().numpy().view(np.uint64).reshape(-1, 4)
     return [unmont(r) for r in rows]
 
@@ -544,9 +552,10 @@ def first_lagrange_poly(zeta: int, group_order: int) -> tuple[int, int]:
     return z_h, z_h * pow((zeta - 1) % FR_MODULUS, -1, FR_MODULUS) % FR_MODULUS
 
 
-def batch_prove(pcs, transcript: Transcript, polys, evals, point: int, max_degree: int, scratch_h: DevVec, scratch_q: DevVec) -> KZGCommitment:
-    """poly_commit/pcs.rs:107-168 (lagrange_pcs = None): h = sum_j alpha^j (p_j - p_j(x)); commit(h / (X - x)).  `evals` are the
-    values p_j(x) the caller already holds (the reference re-evaluates them, pcs.rs:126)."""
+def batch_prove_quotient(transcript: Transcript, polys, evals, point: int, max_degree: int, scratch_h: DevVec, out_q: DevVec):
+    """The polynomial part of poly_commit/pcs.rs:107-168 (lagrange_pcs = None): h = sum_j alpha^j (p_j - p_j(x)), out_q = h / (X - x).
+    `evals` are the values p_j(x) the caller already holds (the reference re-evaluates them, pcs.rs:126).  Returns the device
+    scalar holding the remainder, which the caller checks (PCSProveEvalError) when it next synchronises."""
     init_pcs_batch_eval_transcript(transcript, max_degree, point)
     alpha = transcript.get_challenge_field_elem()
     mults, mult, const = [], 1, 0
@@ -558,10 +567,16 @@ def batch_prove(pcs, transcript: Transcript, polys, evals, point: int, max_degre
     ffi.fr_lincomb_device([p.ptr for p in polys], [p.len for p in polys], mont_rows(mults), scratch_h.ptr, hlen)
     ffi.fr_add_sparse_device(scratch_h.ptr, [0], mont_rows([-const]))
     rem = torch.zeros(4, dtype=torch.int64, device=scratch_h.t.device)
-    ffi.poly_horner_fr_device(scratch_h.ptr, hlen, mont(point), scratch_q.ptr, rem.data_ptr())
+    ffi.poly_horner_fr_device(scratch_h.ptr, hlen, mont(point), out_q.ptr, rem.data_ptr())
+    out_q.len = hlen - 1
+    return rem
+
+
+def batch_prove(pcs, transcript: Transcript, polys, evals, point: int, max_degree: int, scratch_h: DevVec, scratch_q: DevVec) -> KZGCommitment:
+    """poly_commit/pcs.rs:107-168: the commitment of the quotient above."""
+    rem = batch_prove_quotient(transcript, polys, evals, point, max_degree, scratch_h, scratch_q)
     if rem.cpu().numpy().any():
         raise UzkgeError("PCSProveEvalError")
-    scratch_q.len = hlen - 1
     return _commit_dev(pcs, [scratch_q])[0]
 
 
@@ -735,11 +750,15 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
 
     polys_to_open = w_polys + s_open + [P.q_prk_polys[2], P.q_prk_polys[3], r_poly]
     evals_to_open = w_polys_eval_zeta + s_polys_eval_zeta + [prk_3_poly_eval_zeta, prk_4_poly_eval_zeta, r_eval_zeta]
+    # the first opening proof does not enter the transcript before the second is built (prover.rs:359-381), so the two
+    # quotients are committed in one batch
     hmax = max(p.len for p in polys_to_open + [z_poly])
-    sh, sq = DevVec(hmax, dev, zero=False), DevVec(hmax, dev, zero=False)
-    opening_witness_zeta = batch_prove(pcs, transcript, polys_to_open, evals_to_open, zeta, n + 2, sh, sq)
-    opening_witness_zeta_omega = batch_prove(pcs, transcript, [z_poly] + w_polys[:3], [z_eval_zeta_omega] + w_polys_eval_zeta_omega,
-                                             zeta_omega, n + 2, sh, sq)
+    sh, q1, q2 = DevVec(hmax, dev, zero=False), DevVec(hmax, dev, zero=False), DevVec(hmax, dev, zero=False)
+    rem1 = batch_prove_quotient(transcript, polys_to_open, evals_to_open, zeta, n + 2, sh, q1)
+    rem2 = batch_prove_quotient(transcript, [z_poly] + w_polys[:3], [z_eval_zeta_omega] + w_polys_eval_zeta_omega, zeta_omega, n + 2, sh, q2)
+    opening_witness_zeta, opening_witness_zeta_omega = _commit_dev(pcs, [q1, q2])
+    if torch.cat([rem1, rem2]).cpu().numpy().any():
+        raise UzkgeError("PCSProveEvalError")
     mark("round5_openings")
     if timings is not None:
         torch.cuda.synchronize()
