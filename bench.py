@@ -482,6 +482,43 @@ def main() -> int:
         pinned.free()
         results["ntt"] = {"ms": ms, "e2e_ms": e2e_ms, "n": n, "phases_ms": prof["ms"], "roundtrip_ok": roundtrip_ok, "hx": hx}
 
+    # -------------------------------------------------------------------------------------------- distributed NTT (N = 2, 4, 8)
+    if args.workload in ("all", "both", "ntt") and world in (2, 4, 8):
+        from uzkge_b200 import dist as udist
+
+        lg = 24
+        nt = 1 << lg
+        Lr = nt // world
+        mine = torch.from_numpy(random_fr(Lr, 0xB2000005 + rank).view(np.int64).reshape(-1)).to(dev)
+        y = udist.ntt_fr_distributed(mine, nt, rank, world)
+        back = udist.ntt_fr_distributed(y, nt, rank, world, inverse=True)
+        rt_ok = bool(torch.equal(back, mine))
+        reps = max(3, min(K, 10))
+        out_dn = {}
+        for name, natural in (("natural", True), ("cyclic", False)):
+            for _ in range(2):
+                udist.ntt_fr_distributed(mine, nt, rank, world, natural_output=natural)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                udist.ntt_fr_distributed(mine, nt, rank, world, natural_output=natural)
+            e1.record(stream)
+            barrier()
+            out_dn[name] = max_over_ranks(e0.elapsed_time(e1) / reps)
+        flag = torch.tensor([1.0 if rt_ok else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        results["ntt_distributed"] = {
+            "metric": "bn254_fr_ntt_2^24_four_step_elements_per_s", "log_n": lg, "n_gpus": world,
+            "value": nt / (out_dn["natural"] * 1e-3), "unit": "elements/s", "ms_per_step": out_dn["natural"],
+            "cyclic_output_ms": out_dn["cyclic"], "roundtrip_ok": bool(flag.item() == 1.0), "steps": reps,
+            "what": "ONE 2^24 transform over the N GPUs: all-to-all, cross-rank G-point transforms + twiddles, all-to-all, local "
+                    "2^24/N transform, all-to-all back to natural contiguous slices (cyclic_output_ms: without the last exchange)",
+            "single_gpu_ms_reference": "profiles/r1d_sweep.json: 3.83 ms on one GPU",
+        }
+        del mine, y, back
+        torch.cuda.empty_cache()
+
     # -------------------------------------------------------------------------------------------- PlonK (rank 0, N = 1)
     if args.workload in ("all", "plonk"):
         results["plonk"] = plonk_proofs(args, dev, K, W, rank, world, barrier, max_over_ranks)
@@ -512,6 +549,30 @@ def main() -> int:
             cpu_baseline = {"value": m / dt, "unit": "points/s", "cores": cores, "kind": "port",
                             "sample": f"one 2^18-point MSM (first quarter of the workload's bases and scalars), {dt:.2f} s; "
                                       "result compared with the GPU's (affine) before timing was accepted"}
+        if "plonk" in results and results["plonk"]["sizes"]:
+            # the reference's prover cannot run here (no Rust): a LOWER BOUND of its CPU time is the MSM / NTT inventory of one
+            # proof replayed on the oracle port (13 MSMs of n + 3 points, 7 iFFT(n), 7 coset FFT(6n), 1 coset iFFT(6n)); the
+            # quotient map, evaluations, divisions and circuit bookkeeping of the real prover come on top
+            sz = results["plonk"]["sizes"][0]
+            lgp = sz["log_n"]
+            if lgp <= 16:
+                npl = 1 << lgp
+                pts = oc.g1_random_points(npl + 3, 0xB2000006)
+                scal = oc.random_fr(npl + 3, 0xB2000007)
+                vec_n, vec_m = oc.random_fr(npl, 0xB2000008), oc.random_fr(6 * npl, 0xB2000009)
+                t0 = time.time()
+                for _ in range(13):
+                    oc.msm_g1(pts, scal)
+                for _ in range(7):
+                    oc.ntt_fr(vec_n, npl, inverse=True)
+                for _ in range(7):
+                    oc.ntt_fr(vec_m, 6 * npl)
+                oc.ntt_fr(vec_m, 6 * npl, inverse=True)
+                dt = time.time() - t0
+                results["plonk"]["cpu_baseline"] = {
+                    "value": 1.0 / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
+                    "sample": f"MSM + NTT inventory of one 2^{lgp}-gate proof on the oracle port, {dt:.2f} s: an upper bound of the CPU "
+                              "prover's proofs/s (its quotient map, evaluations and divisions are not included)"}
         if "ntt" in results:
             r = results["ntt"]
             t0 = time.time()
@@ -615,6 +676,8 @@ def main() -> int:
         line["ntt"] = ntt_block(results["ntt"])
     if "plonk" in results:
         line["plonk"] = results["plonk"]
+    if "ntt_distributed" in results:
+        line["ntt_distributed"] = results["ntt_distributed"]
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
