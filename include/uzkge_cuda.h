@@ -107,6 +107,20 @@ UZKGE_API int32_t uzkge_cuda_ntt_fr_device(const void* d_in, void* d_out, void* 
 UZKGE_API int32_t uzkge_cuda_ntt_cross_fr_device(const void* d_in, void* d_out, uint32_t log_ranks, size_t cols, size_t col_offset,
                                                  size_t n_total, int32_t inverse, void* stream);
 
+/* The same step with one base pointer per row (2^log_ranks HOST arrays of device pointers).  With rows mapped from PEER GPUs
+ * (uzkge_cuda_ipc_*) the kernel itself performs both exchanges of the four-step transform over NVLink: d_in_rows[n1] = rank n1's
+ * slice + col_offset (P2P loads instead of the first all-to-all), d_out_rows[k1] = rank k1's receive buffer + col_offset (P2P
+ * stores instead of the second).  The caller orders the ranks around it (inputs ready before, stores complete after). */
+UZKGE_API int32_t uzkge_cuda_ntt_cross_rows_fr_device(const void* const* d_in_rows, void* const* d_out_rows, uint32_t log_ranks, size_t cols,
+                                                      size_t col_offset, size_t n_total, int32_t inverse, void* stream);
+/* Device buffers that other processes of the box can map (one process per GPU): cudaMalloc + cudaIpcGetMemHandle /
+ * cudaIpcOpenMemHandle.  `handle` is 64 opaque bytes to ship through any host channel (torch.distributed all_gather_object). */
+UZKGE_API int32_t uzkge_cuda_dev_alloc(size_t bytes, void** d_ptr);
+UZKGE_API int32_t uzkge_cuda_dev_free(void* d_ptr);
+UZKGE_API int32_t uzkge_cuda_ipc_export(const void* d_ptr, uint8_t handle[64]);
+UZKGE_API int32_t uzkge_cuda_ipc_open(const uint8_t handle[64], void** d_ptr);
+UZKGE_API int32_t uzkge_cuda_ipc_close(void* d_ptr);
+
 /* ---- polynomial glue over Fr (the prover's O(n) serial loops as scans) ----------------------------------
  * FpPolynomial::eval (field_polynomial.rs:198-209): out = sum_j coefs[j] * x^j.  n >= 1. */
 UZKGE_API int32_t uzkge_cuda_poly_eval_fr(const uint64_t* coefs, size_t n, const uint64_t x[4], uint64_t out[4]);

@@ -46,11 +46,25 @@ for lg in (16, 22, 24, 26):
         del full, o, s
     else:
         t1 = float("nan")
+    # both exchanges fused into the cross kernel over peer memory (cudaIpc / NVLink P2P)
+    peer = udist.PeerNtt(n, rank, world, dev)
+    peer.x_view.copy_(mine)
+    yp = peer.transform()
+    yc = udist.ntt_fr_distributed(mine, n, rank, world, natural_output=False)
+    good_peer = bool(torch.equal(yp, yc))
+    peer.x_view.copy_(yc)      # the inverse of the cyclic output is NOT the input (layouts differ): check the inverse kernel path
+    ypi = peer.transform(inverse=True).clone()
+    yci = udist.ntt_fr_distributed(yc, n, rank, world, inverse=True, natural_output=False)
+    good_peer = good_peer and bool(torch.equal(ypi, yci))
+    peer.x_view.copy_(mine)
+    tp = sync_time(lambda: peer.transform())
+    peer.close()
+    good = good and good_peer
     tn = sync_time(lambda: udist.ntt_fr_distributed(mine, n, rank, world))
     tc = sync_time(lambda: udist.ntt_fr_distributed(mine, n, rank, world, natural_output=False))
     ok &= good
     if rank == 0:
-        print(f"dist ntt 2^{lg} world={world}: parity={'ok' if good else 'FAIL'}  single-GPU {t1*1e3:.0f} us  distributed {tn*1e3:.0f} us (cyclic out {tc*1e3:.0f} us)", flush=True)
+        print(f"dist ntt 2^{lg} world={world}: parity={'ok' if good else 'FAIL'}  single-GPU {t1*1e3:.0f} us  distributed {tn*1e3:.0f} us (cyclic out {tc*1e3:.0f} us, peer-memory fused {tp*1e3:.0f} us, parity={'ok' if good_peer else 'FAIL'})", flush=True)
 
 # MSM: points split per rank, 96-byte partial sums gathered and added
 n = 1 << 20

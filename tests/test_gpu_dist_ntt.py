@@ -50,3 +50,41 @@ def test_distributed_ntt_full_size_round_trip(gpu, oc):
     assert np.array_equal(np.concatenate([to_np(y) for y in ys]), single)
     back = udist.ntt_fr_distributed_emulated(ys, n, inverse=True)
     assert np.array_equal(np.concatenate([to_np(b) for b in back]), x)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("log_n", [6, 13, 18])
+def test_peer_fused_cross_step_matches_oracle(gpu, oc, world, log_n):
+    """uzkge_cuda_ntt_cross_rows_fr_device: the cross-rank step with one base pointer per row, which is how dist.PeerNtt fuses both
+    exchanges into the kernel's loads and stores over peer memory.  The `world` ranks are emulated on one GPU: every "rank" launches
+    the kernel with in_rows = every rank's slice + its column offset, out_rows = every rank's receive buffer + that offset."""
+    n = 1 << log_n
+    L, S, log_g = n // world, n // world // world, world.bit_length() - 1
+    x = oc.random_fr(n, 60 + log_n + world)
+    want = oc.ntt_fr(x, n)
+    for inverse in (False, True):
+        src = want if inverse else x
+        xs = [to_dev(src[r * L:(r + 1) * L]) for r in range(world)]
+        rows = [torch.zeros(4 * L, dtype=torch.int64, device="cuda") for _ in range(world)]
+        for r in range(world):
+            off = 32 * r * S
+            gpu.ntt_cross_rows_fr_device([t.data_ptr() + off for t in xs], [t.data_ptr() + off for t in rows], log_g, S, r * S, n, inverse)
+        outs = []
+        for r in range(world):
+            y, scr = torch.empty_like(rows[r]), torch.empty_like(rows[r])
+            gpu.ntt_fr_device(rows[r].data_ptr(), y.data_ptr(), scr.data_ptr(), L, L, inverse, None)
+            outs.append(to_np(y))
+        ref = oc.ntt_fr(src, n, inverse=inverse)
+        for r in range(world):                       # cyclic layout: rank r holds X[r + world * k2]
+            assert np.array_equal(outs[r], ref[r::world]), (inverse, r)
+
+
+def test_ipc_export_of_library_buffers(gpu):
+    """Buffers from uzkge_cuda_dev_alloc can be exported for other processes (dist.PeerNtt maps them on the peer GPUs; opening
+    a handle needs a second process, covered by scripts/dist_check.py under torchrun)."""
+    p = gpu.dev_alloc(1 << 20)
+    try:
+        h = gpu.ipc_export(p)
+        assert len(h) == 64 and any(h)
+    finally:
+        gpu.dev_free(p)

@@ -364,6 +364,51 @@ UZKGE_API int32_t uzkge_cuda_ntt_cross_fr_device(const void* d_in, void* d_out, 
     return engine_fail(rc, "ntt_cross_fr_device");
 }
 
+UZKGE_API int32_t uzkge_cuda_ntt_cross_rows_fr_device(const void* const* d_in_rows, void* const* d_out_rows, uint32_t log_ranks, size_t cols,
+                                                      size_t col_offset, size_t n_total, int32_t inverse, void* stream) {
+    if (!d_in_rows || !d_out_rows) return fail(UZKGE_ERR_ARG, "ntt_cross_rows_fr_device: null pointer");
+    API_ENTER(-1);
+    int rc = g.ntt->cross_rows((const fe* const*)d_in_rows, (fe* const*)d_out_rows, log_ranks, cols, col_offset, n_total, inverse != 0,
+                               (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "ntt_cross_rows_fr_device: 2, 4 or 8 ranks, power-of-two size, columns inside a slice");
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "ntt_cross_rows_fr_device: null row pointer");
+    return engine_fail(rc, "ntt_cross_rows_fr_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_dev_alloc(size_t bytes, void** d_ptr) {
+    if (!d_ptr) return fail(UZKGE_ERR_ARG, "dev_alloc: null pointer");
+    API_ENTER(-1);
+    CUDA_OR_FAIL(cudaMalloc(d_ptr, bytes ? bytes : 1), "dev_alloc");
+    return UZKGE_OK;
+}
+UZKGE_API int32_t uzkge_cuda_dev_free(void* d_ptr) {
+    API_ENTER(-1);
+    CUDA_OR_FAIL(cudaFree(d_ptr), "dev_free");
+    return UZKGE_OK;
+}
+UZKGE_API int32_t uzkge_cuda_ipc_export(const void* d_ptr, uint8_t handle[64]) {
+    if (!d_ptr || !handle) return fail(UZKGE_ERR_ARG, "ipc_export: null pointer");
+    API_ENTER(-1);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CUDA_OR_FAIL(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)), "ipc_export");
+    memcpy(handle, &h, 64);
+    return UZKGE_OK;
+}
+UZKGE_API int32_t uzkge_cuda_ipc_open(const uint8_t handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return fail(UZKGE_ERR_ARG, "ipc_open: null pointer");
+    API_ENTER(-1);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_OR_FAIL(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess), "ipc_open");
+    return UZKGE_OK;
+}
+UZKGE_API int32_t uzkge_cuda_ipc_close(void* d_ptr) {
+    API_ENTER(-1);
+    CUDA_OR_FAIL(cudaIpcCloseMemHandle(d_ptr), "ipc_close");
+    return UZKGE_OK;
+}
+
 UZKGE_API int32_t uzkge_cuda_poly_eval_fr(const uint64_t* coefs, size_t n, const uint64_t x[4], uint64_t out[4]) {
     if (!coefs || !x || !out) return fail(UZKGE_ERR_ARG, "poly_eval_fr: null pointer");
     if (n == 0) return fail(UZKGE_ERR_SIZE, "poly_eval_fr: empty coefficient vector");

@@ -118,6 +118,8 @@ public:
     // cross-rank step of a distributed transform (see ntt.cu)
     int cross(const fe* d_in, fe* d_out, uint32_t log_g, uint64_t cols, uint64_t col_offset, uint64_t n_total, bool inverse,
               cudaStream_t st);
+    int cross_rows(const fe* const* in_rows, fe* const* out_rows, uint32_t log_g, uint64_t cols, uint64_t col_offset, uint64_t n_total,
+                   bool inverse, cudaStream_t st);
 
 private:
     const NttDomain* domain(uint64_t n, cudaStream_t st);

@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(256) ntt_radix3_kernel(const Radix3Args a) {
 // applies the four-step twiddle:   out[k1][t] = w_N^(n2 * k1) * sum_{n1} in[n1][t] * w_G^(n1 * k1)
 // (inverse: conjugate roots and a factor 1/G).  Row k1 then travels to rank k1, which runs the size-L transform.
 struct CrossArgs {
-    const fe* in;
-    fe* out;
+    const fe* in_rows[8];   // row n1: `cols` elements -- local memory after an all-to-all, or rank n1's slice itself (peer memory)
+    fe* out_rows[8];        // row k1: local memory before an all-to-all, or rank k1's receive buffer itself (peer memory)
     uint64_t cols, col_offset, n_total;
     const fe* w_lo;   // power table of w_N
     const fe* w_hi;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) ntt_cross_kernel(const CrossArgs a) {
     if (t >= a.cols) return;
     fe x[G];
 #pragma unroll
-    for (int i = 0; i < G; i++) x[i] = ld_fe(a.in + (uint64_t)i * a.cols + t);
+    for (int i = 0; i < G; i++) x[i] = ld_fe(a.in_rows[i] + t);
 #pragma unroll
     for (int s = LOGG - 1; s >= 0; s--) {
         const int h = 1 << s;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) ntt_cross_kernel(const CrossArgs a) {
             y = fe_mul<FrP>(y, a.scale);
         }
         if (e) y = fe_mul<FrP>(y, pow2l(a.w_lo, a.w_hi, e));
-        st_fe(a.out + (uint64_t)k * a.cols + t, y);
+        st_fe(a.out_rows[k] + t, y);
     }
 }
 
@@ -468,21 +468,38 @@ int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, ui
 
 int NttEngine::cross(const fe* d_in, fe* d_out, uint32_t log_g, uint64_t cols, uint64_t col_offset, uint64_t n_total,
                      bool inverse, cudaStream_t st) {
+    if (log_g < 1 || log_g > 3) return UZKGE_ERR_SIZE;
+    const fe* in_rows[8];
+    fe* out_rows[8];
+    for (uint32_t i = 0; i < (1u << log_g); i++) {
+        in_rows[i] = d_in + (uint64_t)i * cols;
+        out_rows[i] = d_out + (uint64_t)i * cols;
+    }
+    return cross_rows(in_rows, out_rows, log_g, cols, col_offset, n_total, inverse, st);
+}
+
+// the same step with one base pointer per row: rows may live in the memory of peer GPUs (cudaIpc mappings), which fuses
+// the two exchanges of the four-step transform into the kernel's own loads and stores over NVLink
+int NttEngine::cross_rows(const fe* const* in_rows, fe* const* out_rows, uint32_t log_g, uint64_t cols, uint64_t col_offset,
+                          uint64_t n_total, bool inverse, cudaStream_t st) {
     if (log_g < 1 || log_g > 3 || cols == 0 || (n_total >> log_g) == 0 || col_offset + cols > (n_total >> log_g))
         return UZKGE_ERR_SIZE;
     if (n_total & (n_total - 1)) return UZKGE_ERR_SIZE;
     const NttDomain* d = domain(n_total, st);
     if (!d) return UZKGE_ERR_SIZE;
     CrossArgs ca;
-    ca.in = d_in;
-    ca.out = d_out;
+    const uint32_t g = 1u << log_g;
+    for (uint32_t i = 0; i < 8; i++) {
+        ca.in_rows[i] = i < g ? in_rows[i] : nullptr;
+        ca.out_rows[i] = i < g ? out_rows[i] : nullptr;
+        if (i < g && (!ca.in_rows[i] || !ca.out_rows[i])) return UZKGE_ERR_ARG;
+    }
     ca.cols = cols;
     ca.col_offset = col_offset;
     ca.n_total = n_total;
     ca.w_lo = d->w_lo;
     ca.w_hi = d->w_hi;
     ca.inverse = inverse ? 1 : 0;
-    const uint32_t g = 1u << log_g;
     fe wg = host_pow(d->omega, n_total >> log_g);
     if (inverse) wg = fe_inv<FrP>(wg);
     fe acc = fe_one<FrP>();

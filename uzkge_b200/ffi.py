@@ -83,6 +83,15 @@ _SIGNATURES = {
         C.c_int32,
         [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p],
     ),
+    "uzkge_cuda_ntt_cross_rows_fr_device": (
+        C.c_int32,
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p],
+    ),
+    "uzkge_cuda_dev_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "uzkge_cuda_dev_free": (C.c_int32, [C.c_void_p]),
+    "uzkge_cuda_ipc_export": (C.c_int32, [C.c_void_p, C.c_char_p]),
+    "uzkge_cuda_ipc_open": (C.c_int32, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "uzkge_cuda_ipc_close": (C.c_int32, [C.c_void_p]),
     "uzkge_cuda_poly_eval_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_poly_div_linear_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_poly_horner_fr_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -315,6 +324,40 @@ def ntt_cross_fr_device(d_in: int, d_out: int, log_ranks: int, cols: int, col_of
                         inverse: bool = False, stream: int = 0) -> None:
     check(lib().uzkge_cuda_ntt_cross_fr_device(d_in, d_out, log_ranks, cols, col_offset, n_total, 1 if inverse else 0, stream),
           FFTError)
+
+
+def ntt_cross_rows_fr_device(d_in_rows, d_out_rows, log_ranks: int, cols: int, col_offset: int, n_total: int,
+                             inverse: bool = False, stream: int = 0) -> None:
+    g = 1 << log_ranks
+    ii = (C.c_void_p * g)(*[int(x) for x in d_in_rows])
+    oo = (C.c_void_p * g)(*[int(x) for x in d_out_rows])
+    check(lib().uzkge_cuda_ntt_cross_rows_fr_device(ii, oo, log_ranks, cols, col_offset, n_total, 1 if inverse else 0, stream), FFTError)
+
+
+def dev_alloc(nbytes: int) -> int:
+    p = C.c_void_p()
+    check(lib().uzkge_cuda_dev_alloc(nbytes, C.byref(p)))
+    return int(p.value)
+
+
+def dev_free(d_ptr: int) -> None:
+    check(lib().uzkge_cuda_dev_free(d_ptr))
+
+
+def ipc_export(d_ptr: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    check(lib().uzkge_cuda_ipc_export(d_ptr, buf))
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    p = C.c_void_p()
+    check(lib().uzkge_cuda_ipc_open(handle, C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(d_ptr: int) -> None:
+    check(lib().uzkge_cuda_ipc_close(d_ptr))
 
 
 def poly_eval_fr(coefs, x) -> np.ndarray:
