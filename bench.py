@@ -180,11 +180,16 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
 
     tau = plonk.mont(0x1234567890ABCDEF1234567890ABCDEF)
     out = {"metric": "turboplonk_synthetic_proofs_per_s", "unit": "proofs/s", "sizes": []}
-    for lg in [int(x) for x in args.plonk_logs.split(",") if x]:
+    logs = [int(x) for x in args.plonk_logs.split(",") if x]
+    runs = [(lg, "uniform") for lg in logs]
+    if world == 1 and logs and logs[-1] >= 20:
+        runs.append((logs[-1], "bits"))    # the same circuit shape over a witness of bits / small integers
+    for lg, witness in runs:
         n = 1 << lg
         split = world > 1 and lg > 18
         steps = K if lg <= 18 else max(2, min(K, 5))
         t0 = time.perf_counter()
+        lagrange = None
         if split:
             bases = ffi.srs_generate(tau, n + 3)
             pcs = udist.SplitCommitter(bases, rank, world, device=dev)
@@ -197,14 +202,17 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
                 continue
         else:
             pcs = KZGCommitmentSchemeBN254.new(n + 2, tau)
-        cs = plonk.TurboCS.synthetic(lg, seed=0xB2000004 + (0 if split else rank))
+            lagrange = KZGCommitmentSchemeBN254.new_lagrange(n, tau)   # prover_with_lagrange: what zshuffle / zmatchmaking call
+        cs = plonk.TurboCS.synthetic(lg, seed=0xB2000004 + (0 if split else rank), witness=witness)
         params = plonk.indexer(cs, pcs)
         torch.cuda.synchronize()
         setup_s = time.perf_counter() - t0
-        wit_host = cs.get_witness_array()
+        wit_pinned = ffi.PinnedArray(cs.get_witness_array().shape)     # the caller's witness, page-locked (uzkge_cuda_host_alloc)
+        wit_pinned.array[:] = cs.get_witness_array()
+        wit_host = wit_pinned.array
         wit = plonk.DevVec.from_numpy(wit_host, dev)
         for _ in range(min(W, 3)):
-            proof = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit)
+            proof = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit, lagrange_pcs=lagrange)
         torch.cuda.synchronize()
         if not split and barrier:
             barrier()
@@ -212,7 +220,7 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
         l0 = ffi.launch_count()
         t0 = time.perf_counter()
         for _ in range(steps):
-            plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit, timings=timings)
+            plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit, timings=timings, lagrange_pcs=lagrange)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / steps
         launches = (ffi.launch_count() - l0) // steps
@@ -220,7 +228,7 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
             barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            proof2 = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit_host)
+            proof2 = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit_host, lagrange_pcs=lagrange)
         torch.cuda.synchronize()
         dt_e2e = (time.perf_counter() - t0) / steps
         same = all(a == b for a, b in zip(proof.cm_t_vec + [proof.opening_witness_zeta], proof2.cm_t_vec + [proof2.opening_witness_zeta]))
@@ -235,6 +243,7 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
                 dt, dt_e2e = max_over_ranks(dt), max_over_ranks(dt_e2e)
         out["sizes"].append({
             "log_n": lg, "n_gpus": world, "mode": "msm_split" if split else ("replicas" if world > 1 else "single"),
+            "witness": witness, "lagrange_commitments": lagrange is not None,
             "prove_ms": dt * 1e3, "proofs_per_s": proofs_in_flight / dt, "e2e_prove_ms": dt_e2e * 1e3,
             "e2e_proofs_per_s": proofs_in_flight / dt_e2e,
             "h2d_bytes_per_step": int(wit_host.nbytes), "d2h_bytes_per_step": 13 * 96 + 16 * 32, "steps": steps,
@@ -244,7 +253,11 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
             "window_bits": window_bits, "hbm_peak_gib": torch.cuda.max_memory_allocated() / 2**30,
         })
         pcs.close()
-        del params, wit, cs, pcs
+        if lagrange is not None:
+            lagrange.close()
+        del wit_host
+        wit_pinned.free()
+        del params, wit, cs, pcs, lagrange
         torch.cuda.empty_cache()
         if split:
             barrier()

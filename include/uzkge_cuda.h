@@ -63,6 +63,12 @@ UZKGE_API int32_t uzkge_cuda_srs_free(uint64_t handle);
  * (kzg_poly_commitment.rs:183-204: n sequential scalar multiplications on the CPU).  tau: Montgomery Fr. */
 UZKGE_API int32_t uzkge_cuda_srs_generate(const uint64_t tau[4], size_t n, uint64_t* out_affine_xy);
 
+/* Setup path, Lagrange basis: out[i] = L_i(tau) * G for the size-n domain (n = 2^k), i.e. the SRS `lagrange-srs-*.bin` holds for the
+ * bundled circuits (uzkge/src/gen_params/mod.rs:42-65) and that prover_with_lagrange commits evaluation vectors against
+ * (plonk/prover.rs:119-146).  The scalars L_i(tau) = iNTT(tau^0 .. tau^(n-1))_i are formed on the device.  A deployment without the
+ * trapdoor derives the same points from the monomial SRS with a G1 inverse transform (not built). */
+UZKGE_API int32_t uzkge_cuda_srs_generate_lagrange(const uint64_t tau[4], size_t n, uint64_t* out_affine_xy);
+
 /* ---- MSM ------------------------------------------------------------------------------------------
  * out = sum_{i < n} scalars[i] * srs[base_offset + i].  Replaces `G1Projective::msm(&points_raw, &coefs)`
  * (kzg_poly_commitment.rs:290) for KZGCommitmentSchemeBN254::commit (:278-293).
@@ -72,6 +78,11 @@ UZKGE_API int32_t uzkge_cuda_msm_g1(uint64_t handle, size_t base_offset, const u
 /* k independent MSMs over the same SRS prefix (the round-1 wire commitments, the split quotient, ...:
  * uzkge/src/plonk/prover.rs:132-192, helpers.rs:1323-1408).  out_jac holds k * 12 words. */
 UZKGE_API int32_t uzkge_cuda_msm_g1_batch(uint64_t handle, const uint64_t* const* scalars, const size_t* n, size_t k, uint64_t* out_jac);
+
+/* *d_out_jac (+)= sum_{j < k} scalars[j] * srs[idx[j]], k <= 32, scalars on the host: PolyComScheme::apply_blind_factors
+ * (kzg_poly_commitment.rs:299-313) folded onto a device-resident commitment (accumulate = 1). */
+UZKGE_API int32_t uzkge_cuda_msm_g1_small_device(uint64_t handle, const size_t* idx, const uint64_t* scalars_host, size_t k, int32_t accumulate,
+                                                 void* d_out_jac, void* stream);
 
 /* ---- NTT ------------------------------------------------------------------------------------------
  * In-place transform of `inout` (capacity domain_size elements; the first len_in are the input, the rest

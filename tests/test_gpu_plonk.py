@@ -126,3 +126,48 @@ def test_synthetic_circuit_proof_verifies(gpu, bn, oc, log_size):
     got["w_polys_eval_zeta"][2] = (got["w_polys_eval_zeta"][2] + 1) % FR
     assert not pp.verifier(pp.Transcript(b"synthetic"), Trapdoor, ovp, [], got)
     pcs.close()
+
+
+def test_lagrange_srs_known_answers(gpu, oc, bn):
+    """uzkge_cuda_srs_generate_lagrange: sum_i w^(i j) L_i(tau) G = tau^j G -- the circuit-free known answer the reference's bundled
+    lagrange-srs files satisfy against srs-padding.bin (tests/test_oracle_golden.py), here for a synthetic trapdoor."""
+    from uzkge_b200 import plonk
+
+    n = 512
+    tau_m = plonk.mont(TAU)
+    lag = gpu.srs_generate_lagrange(tau_m, n)
+    mono = gpu.srs_generate(tau_m, 8)
+    assert all(oc.g1_on_curve(p) for p in lag[:16])
+    w = bn.root_of_unity(n)
+    h = gpu.srs_upload(lag)
+    try:
+        for j in (0, 1, 2, 5):
+            sc = bn.ints_to_array([pow(w, i * j, bn.FR) for i in range(n)], bn.FR)
+            got = gpu.g1_to_affine(gpu.msm_g1(h, sc))
+            assert np.array_equal(got, mono[j]), j
+    finally:
+        gpu.srs_free(h)
+
+
+@pytest.mark.parametrize("n_gates", [25, 200])
+def test_prover_with_lagrange_gives_the_same_proof(gpu, bn, n_gates):
+    """prover_with_lagrange (prover.rs:88-146): committing the evaluation vectors against the Lagrange SRS and folding the blind
+    factors in (apply_blind_factors, kzg_poly_commitment.rs:299-313) yields the same commitments as the coefficient path."""
+    from uzkge_b200 import KZGCommitmentSchemeBN254, plonk
+    from uzkge_b200.rng import ChaChaRng
+    from uzkge_b200.transcript import Transcript
+
+    cs = build_circuit(plonk.TurboCS(), n_gates, 3, 2, 1)
+    pcs = KZGCommitmentSchemeBN254.new(cs.size + 2, plonk.mont(TAU))
+    lagrange_pcs = KZGCommitmentSchemeBN254.new_lagrange(cs.size, plonk.mont(TAU))
+    params = plonk.indexer(cs, pcs)
+    wit = cs.get_witness_array()
+    a = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"test"), pcs, cs, params, wit)
+    b = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"test"), pcs, cs, params, wit, lagrange_pcs=lagrange_pcs)
+    assert _proof_as_oracle_dict(bn, a) == _proof_as_oracle_dict(bn, b)
+    # a Lagrange SRS of another size is ignored, as in the reference (prover.rs:119-124)
+    other = KZGCommitmentSchemeBN254.new_lagrange(2 * cs.size, plonk.mont(TAU))
+    c = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"test"), pcs, cs, params, wit, lagrange_pcs=other)
+    assert _proof_as_oracle_dict(bn, a) == _proof_as_oracle_dict(bn, c)
+    for p in (pcs, lagrange_pcs, other):
+        p.close()

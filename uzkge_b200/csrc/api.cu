@@ -619,6 +619,36 @@ UZKGE_API int32_t uzkge_cuda_srs_generate(const uint64_t tau[4], size_t n, uint6
     return UZKGE_OK;
 }
 
+UZKGE_API int32_t uzkge_cuda_srs_generate_lagrange(const uint64_t tau[4], size_t n, uint64_t* out_affine_xy) {
+    if (!tau || !out_affine_xy) return fail(UZKGE_ERR_ARG, "srs_generate_lagrange: null pointer");
+    if (n == 0 || (n & (n - 1)) || n > (1ull << 26)) return fail(UZKGE_ERR_SIZE, "srs_generate_lagrange: n must be a power of two <= 2^26");
+    API_ENTER(-1);
+    CUDA_OR_FAIL(g.data.reserve(n * sizeof(affine) + 64), "srs_generate_lagrange: buffer");
+    CUDA_OR_FAIL(g.scratch.reserve(2 * n * sizeof(fe) + 64), "srs_generate_lagrange: buffer");
+    fe* pw = (fe*)g.scratch.p;
+    fe* tmp = pw + n;
+    int rc = fr_powers_run(tau, nullptr, n, pw, g.stream);
+    if (rc != UZKGE_OK) return engine_fail(rc, "srs_generate_lagrange: powers");
+    rc = g.ntt->run(pw, pw, tmp, n, n, true, nullptr, g.stream);
+    if (rc != UZKGE_OK) return engine_fail(rc, "srs_generate_lagrange: transform");
+    rc = g.msm->fixed_base_mul(pw, (uint32_t)n, (affine*)g.data.p, g.stream);
+    if (rc != UZKGE_OK) return engine_fail(rc, "srs_generate_lagrange: launch");
+    CUDA_OR_FAIL(cudaMemcpyAsync(out_affine_xy, g.data.p, n * sizeof(affine), cudaMemcpyDeviceToHost, g.stream), "srs_generate_lagrange: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "srs_generate_lagrange: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_msm_g1_small_device(uint64_t handle, const size_t* idx, const uint64_t* scalars_host, size_t k, int32_t accumulate,
+                                                 void* d_out_jac, void* stream) {
+    if (!d_out_jac || (k && (!idx || !scalars_host))) return fail(UZKGE_ERR_ARG, "msm_g1_small_device: null pointer");
+    API_ENTER(-1);
+    auto it = g.srs.find(handle);
+    if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1_small_device: unknown handle");
+    int rc = g.msm->small_msm(&it->second, idx, scalars_host, (uint32_t)k, accumulate != 0, (jacobian*)d_out_jac, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "msm_g1_small_device: k <= 32, indices inside the SRS");
+    return engine_fail(rc, "msm_g1_small_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_host_alloc(size_t bytes, void** out) {
     if (!out) return fail(UZKGE_ERR_ARG, "host_alloc: null pointer");
     API_ENTER(-1);

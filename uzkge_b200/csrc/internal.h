@@ -189,6 +189,9 @@ public:
     int g1_add(const jacobian* d_a, const jacobian* d_b, jacobian* d_out, cudaStream_t st);
     int g1_to_affine(const jacobian* d_in, affine* d_out, cudaStream_t st);
     int powers_of_tau(const fe& tau, uint64_t first, uint32_t count, affine* d_out, cudaStream_t st);
+    int fixed_base_mul(const fe* d_scalars, uint32_t count, affine* d_out, cudaStream_t st);
+    // *d_out (+)= sum_j scalars[j] * srs[idx[j]], k <= 32 (host scalars, Montgomery)
+    int small_msm(const MsmSrs* s, const size_t* idx, const uint64_t* scalars, uint32_t k, bool accumulate, jacobian* d_out, cudaStream_t st);
     void force_lanes(uint32_t g) { force_lanes_ = g; }  // tuning knob (0 = automatic)
 
 

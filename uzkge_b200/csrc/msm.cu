@@ -307,6 +307,61 @@ __global__ void g1_to_affine_kernel(const jacobian* in, affine* out) {
     st_affine(out, r);
 }
 
+// out[i] = scalars[i] * G (affine): the Lagrange-basis SRS of a synthetic setup, L_i(tau) * G with the scalars L_i(tau) coming from
+// an inverse transform of the powers of tau (api.cu: uzkge_cuda_srs_generate_lagrange).
+__global__ void __launch_bounds__(128) g1_fixed_base_mul_kernel(const fe* __restrict__ scalars, affine g, uint32_t count, affine* out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const fe s = fe_from_mont<FrP>(ld_fe(scalars + t));
+    xyzz acc = xyzz_identity();
+#pragma unroll 1
+    for (int bit = 253; bit >= 0; bit--) {
+        acc = xyzz_dbl(acc);
+        if ((s.l[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, g);
+    }
+    st_affine(out + t, xyzz_to_affine(acc));
+}
+
+// *out (+)= sum_{j < k} scalars[j] * bases[idx[j]], k <= 32: one lane per term (double-and-add), warp-shuffle sum.  The blind
+// factors of a commitment, apply_blind_factors (kzg_poly_commitment.rs:299-313): C += sum_i b_i * (SRS[i] - SRS[n + i]).
+struct SmallMsmArgs {
+    const affine* bases;
+    uint32_t idx[32];
+    fe scalars[32];   // Montgomery
+    uint32_t k;
+    uint32_t accumulate;
+    jacobian* out;
+};
+__global__ void __launch_bounds__(32) g1_small_msm_kernel(const __grid_constant__ SmallMsmArgs a) {
+    const uint32_t lane = threadIdx.x;
+    xyzz acc = xyzz_identity();
+    if (lane < a.k) {
+        const affine p = ld_affine(a.bases + a.idx[lane]);
+        const fe s = fe_from_mont<FrP>(a.scalars[lane]);
+        if (!affine_is_identity(p)) {
+#pragma unroll 1
+            for (int bit = 253; bit >= 0; bit--) {
+                acc = xyzz_dbl(acc);
+                if ((s.l[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, p);
+            }
+        }
+    }
+    for (int d = 16; d; d >>= 1) {
+        const xyzz o = shfl_down_xyzz(acc, d);
+        xyzz_add(acc, o);
+    }
+    if (lane == 0) {
+        if (a.accumulate) {
+            const xyzz prev = jacobian_to_xyzz(ld_jacobian(a.out));
+            xyzz_add(acc, prev);
+        }
+        const jacobian r = xyzz_to_jacobian(acc);
+        st_fe(&a.out->x, r.x);
+        st_fe(&a.out->y, r.y);
+        st_fe(&a.out->z, r.z);
+    }
+}
+
 // ------------------------------------------------------------------ SRS generation (setup path)
 // out[i] = tau^i * G, i < n, affine: the G1 half of KZGCommitmentScheme::new
 // (/root/reference/uzkge/src/poly_commit/kzg_poly_commitment.rs:183-204, n sequential scalar multiplications
@@ -800,6 +855,36 @@ int MsmEngine::powers_of_tau(const fe& tau, uint64_t first, uint32_t count, affi
     g.x = fe_one<FqP>();
     g.y = fe_dbl<FqP>(g.x);
     g1_powers_of_tau_kernel<<<(count + 127) / 128, 128, 0, st>>>(tau, g, first, count, d_out);
+    UZ_COUNT_LAUNCH(1);
+    UZ_CUDA_TRY(cudaGetLastError());
+    return UZKGE_OK;
+}
+
+int MsmEngine::fixed_base_mul(const fe* d_scalars, uint32_t count, affine* d_out, cudaStream_t st) {
+    affine g;
+    g.x = fe_one<FqP>();
+    g.y = fe_dbl<FqP>(g.x);
+    g1_fixed_base_mul_kernel<<<(count + 127) / 128, 128, 0, st>>>(d_scalars, g, count, d_out);
+    UZ_COUNT_LAUNCH(1);
+    UZ_CUDA_TRY(cudaGetLastError());
+    return UZKGE_OK;
+}
+
+int MsmEngine::small_msm(const MsmSrs* s, const size_t* idx, const uint64_t* scalars, uint32_t k, bool accumulate, jacobian* d_out,
+                         cudaStream_t st) {
+    if (k > 32) return UZKGE_ERR_SIZE;
+    SmallMsmArgs a;
+    memset(&a, 0, sizeof(a));
+    for (uint32_t j = 0; j < k; j++) {
+        if (idx[j] >= s->n) return UZKGE_ERR_SIZE;
+        a.idx[j] = (uint32_t)idx[j];
+        memcpy(&a.scalars[j], scalars + 4 * j, sizeof(fe));
+    }
+    a.bases = s->tables;   // table 0 = the bases themselves
+    a.k = k;
+    a.accumulate = accumulate ? 1 : 0;
+    a.out = d_out;
+    g1_small_msm_kernel<<<1, 32, 0, st>>>(a);
     UZ_COUNT_LAUNCH(1);
     UZ_CUDA_TRY(cudaGetLastError());
     return UZKGE_OK;

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "uzkge_cuda_version": (C.c_char_p, []),
     "uzkge_cuda_srs_upload": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, u64p]),
     "uzkge_cuda_srs_generate": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uzkge_cuda_srs_generate_lagrange": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uzkge_cuda_msm_g1_small_device": (C.c_int32, [C.c_uint64, C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_srs_free": (C.c_int32, [C.c_uint64]),
     "uzkge_cuda_msm_g1": (C.c_int32, [C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_msm_g1_batch": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p]),
@@ -236,6 +238,23 @@ def srs_generate(tau, n: int) -> np.ndarray:
     out = np.zeros((n, 8), dtype=np.uint64)
     check(lib().uzkge_cuda_srs_generate(ptr(t), n, ptr(out)), CommitmentError)
     return out
+
+
+def srs_generate_lagrange(tau, n: int) -> np.ndarray:
+    """L_i(tau) * G, i < n (n a power of two), affine Montgomery limbs, built on the GPU."""
+    t = as_u64(tau).reshape(4)
+    out = np.zeros((n, 8), dtype=np.uint64)
+    check(lib().uzkge_cuda_srs_generate_lagrange(ptr(t), n, ptr(out)))
+    return out
+
+
+def msm_g1_small_device(handle: int, idx, scalars, d_out: int, accumulate: bool = False, stream: int = 0) -> None:
+    """*d_out (+)= sum_j scalars[j] * srs[idx[j]] for a handful of terms (blind factors)."""
+    k = len(idx)
+    s = as_u64(scalars, 4)
+    assert s.shape[0] == k
+    ii = (C.c_size_t * k)(*[int(x) for x in idx])
+    check(lib().uzkge_cuda_msm_g1_small_device(handle, ii, ptr(s), k, 1 if accumulate else 0, d_out, stream), CommitmentError)
 
 
 def srs_free(handle: int) -> None:

@@ -255,10 +255,13 @@ class TurboCS:
         return perm
 
     @classmethod
-    def synthetic(cls, log_size: int, seed: int = 0xB2000004, layers: int = 8) -> "TurboCS":
+    def synthetic(cls, log_size: int, seed: int = 0xB2000004, layers: int = 8, witness: str = "uniform") -> "TurboCS":
         """a satisfied circuit of 2^log_size gates made of insert_add_gate / insert_mul_gate (turbo/mod.rs:481-522) in
         `layers` layers, every gate reading two outputs of the previous layer (so the copy constraints are not trivial).  The
-        witness is evaluated layer by layer on the GPU (gather, pointwise product, sum).  No public inputs."""
+        witness is evaluated layer by layer on the GPU (gather, pointwise product, sum).  No public inputs.
+        witness = "uniform": the free inputs are uniform field elements (every wire value is full width: the worst case for the
+        commitments); "bits": the inputs are bits, so all values stay below 2^layers -- the zeros / bits / small integers that
+        dominate real circuits' wire vectors."""
         n = 1 << log_size
         cs = cls()
         rng = np.random.default_rng(seed)
@@ -266,7 +269,12 @@ class TurboCS:
         per = [g // layers + (1 if i < g % layers else 0) for i in range(layers)]
         dev = _dev()
         n_inputs = max(per[0], 2)
-        inputs = _random_fr(n_inputs, seed ^ 0x5EED)
+        if witness == "bits":
+            inputs = np.stack([_ZERO, _ONE])[rng.integers(0, 2, n_inputs)]
+        elif witness == "uniform":
+            inputs = _random_fr(n_inputs, seed ^ 0x5EED)
+        else:
+            raise ParameterError("witness must be 'uniform' or 'bits'")
         n_vars = 2 + n_inputs + g
         wit = DevVec(n_vars, dev)
         head = np.concatenate([np.stack([_ZERO, _ONE]), inputs])
@@ -413,6 +421,39 @@ def _commit_dev(pcs, vecs) -> list:
             ffi.msm_g1_device(pcs.handle, v.ptr, v.len, out.data_ptr() + 96 * i)
     jac = out.cpu().numpy().view(np.uint64).reshape(len(vecs), 12)
     return [KZGCommitment(jac[i].copy()) for i in range(len(vecs))]
+
+
+N_BLIND_SLOTS = 3   # the largest hiding degree (TurboCS::get_hiding_degree, z_poly)
+
+
+class _View:
+    """A (pointer, length) window into a DevVec, accepted wherever a coefficient vector is committed."""
+
+    def __init__(self, base: DevVec, first: int, length: int):
+        self.t, self.ptr, self.len = base.t, base.at(first), length
+
+
+def _lagrange_commit_scheme(pcs, lagrange_pcs, n: int, ws: dict):
+    """The SRS the `commit` closure of prover_with_lagrange needs (plonk/prover.rs:131-146), as ONE base vector:
+    [L_0(tau) G .. L_{n-1}(tau) G | SRS[0..3) | SRS[n..n+3)].  lagrange_pcs.commit(evals) + pcs.apply_blind_factors(cm, blinds, n)
+    = C + sum_i b_i (SRS[i] - SRS[n + i]) (kzg_poly_commitment.rs:299-313) is then a single MSM over the scalars
+    [evals | b_0 b_1 b_2 | -b_0 -b_1 -b_2] -- no separate scalar multiplications for the blinds."""
+    cached = ws.get("lagrange_scheme")
+    if cached is not None and cached[0] is lagrange_pcs:
+        return cached[1]
+    mono = pcs.public_parameter_group_1
+    idx = list(range(N_BLIND_SLOTS)) + [n + i for i in range(N_BLIND_SLOTS)]
+    pts = np.concatenate([lagrange_pcs.public_parameter_group_1[:n], mono[idx]])
+    scheme = KZGCommitmentSchemeBN254(pts)
+    ws["lagrange_scheme"] = (lagrange_pcs, scheme)
+    return scheme
+
+
+def _set_blind_slots(buf: DevVec, first: int, blinds) -> None:
+    """Slots [first, first + 6) <- [b_0 b_1 b_2 | -b_0 -b_1 -b_2] (missing blinds are zero)."""
+    b = list(blinds) + [0] * (N_BLIND_SLOTS - len(blinds))
+    rows = mont_rows(b + [-x for x in b])
+    buf.t[4 * first: 4 * (first + 2 * N_BLIND_SLOTS)].copy_(torch.from_numpy(rows.view(np.int64).reshape(-1)))
 
 
 def _evals(polys_points, dev) -> list[int]:
@@ -581,8 +622,12 @@ def batch_prove(pcs, transcript: Transcript, polys, evals, point: int, max_degre
 
 
 def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkProverParams, w,
-           timings: dict | None = None) -> PlonkProof:
-    """plonk/prover.rs:76-394.  `w`: the witness, (num_vars, 4) Montgomery limbs (numpy) or a DevVec already in HBM."""
+           timings: dict | None = None, lagrange_pcs=None) -> PlonkProof:
+    """plonk/prover.rs:76-394 (`prover` = `prover_with_lagrange` with lagrange_pcs = None).  `w`: the witness, (num_vars, 4)
+    Montgomery limbs (numpy) or a DevVec already in HBM.  With a `lagrange_pcs` whose size matches the circuit
+    (prover.rs:119-124) the wire and z commitments are MSMs of the EVALUATION vectors against the Lagrange SRS with the blind
+    terms as six extra bases (prover.rs:131-146, `_lagrange_commit_scheme`); the quotient pieces and opening proofs are committed in coefficient form -- the same group
+    elements as the reference's Lagrange branch (helpers.rs:1363-1391, pcs.rs:139-163), without its extra transforms."""
     if cs.is_verifier_only():
         raise UzkgeError("FuncParamsError")
     P = prover_params
@@ -594,6 +639,8 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     k1, k1_inv = mont(k[1]), mont(pow(k[1], -1, FR_MODULUS))
     cap = n + 8
     marks = []
+    if lagrange_pcs is not None and (lagrange_pcs.max_degree() + 1 != n or hasattr(pcs, "commit_device")):
+        lagrange_pcs = None
 
     def mark(name):
         if timings is not None:
@@ -621,16 +668,23 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         _ifft(pi.ptr, n, pi, scratch)
 
     # 2. witness polynomials: extend, interpolate, hide, commit
-    ext = ws.get("ext") or DevVec(N_WIRES_PER_GATE * n, dev, zero=False)
+    stride = n + 8          # every evaluation vector is followed by the 6 blind slots of the Lagrange commitment
+    ext = ws.get("ext") or DevVec(N_WIRES_PER_GATE * stride, dev)
     ws["ext"] = ext
-    ffi.fr_gather_device(wit.ptr, P.wiring.data_ptr(), N_WIRES_PER_GATE * n, ext.ptr)
-    w_polys = []
+    w_polys, w_blinds = [], []
     for i in range(N_WIRES_PER_GATE):
+        ffi.fr_gather_device(wit.ptr, P.wiring.data_ptr() + 4 * i * n, n, ext.at(i * stride))
         f = DevVec(cap, dev, length=n)
-        _ifft(ext.at(i * n), n, f, scratch)
-        hide_polynomial(prng, f, cs.get_hiding_degree(i), n)
+        _ifft(ext.at(i * stride), n, f, scratch)
+        w_blinds.append(hide_polynomial(prng, f, cs.get_hiding_degree(i), n))
         w_polys.append(f)
-    cm_w_vec = _commit_many(pcs, w_polys)
+    if lagrange_pcs is not None:
+        lag = _lagrange_commit_scheme(pcs, lagrange_pcs, n, ws)
+        for i in range(N_WIRES_PER_GATE):
+            _set_blind_slots(ext, i * stride + n, w_blinds[i])
+        cm_w_vec = _commit_dev(lag, [_View(ext, i * stride, n + 2 * N_BLIND_SLOTS) for i in range(N_WIRES_PER_GATE)])
+    else:
+        cm_w_vec = _commit_many(pcs, w_polys)
     for cm in cm_w_vec:
         transcript.append_commitment(cm)
     mark("round1_wires")
@@ -644,12 +698,16 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     z_poly = DevVec(cap, dev, length=n)
     tmp = ws.get("ztmp") or DevVec(4 * n, dev, zero=False)
     ws["ztmp"] = tmp
-    z_ev = DevVec(n, dev, zero=False)
-    ffi.plonk_z_evals_fr_device([ext.at(i * n) for i in range(N_WIRES_PER_GATE)], [P.sigma_evals.at(i * n) for i in range(N_WIRES_PER_GATE)],
+    z_ev = DevVec(stride, dev, zero=False)
+    ffi.plonk_z_evals_fr_device([ext.at(i * stride) for i in range(N_WIRES_PER_GATE)], [P.sigma_evals.at(i * n) for i in range(N_WIRES_PER_GATE)],
                                 P.group.ptr, mont_rows(k), mont(beta), mont(gamma), n, z_ev.ptr, tmp.ptr)
     _ifft(z_ev.ptr, n, z_poly, scratch)
-    hide_polynomial(prng, z_poly, 3, n)
-    cm_z = _commit_dev(pcs, [z_poly])[0]
+    z_blinds = hide_polynomial(prng, z_poly, 3, n)
+    if lagrange_pcs is not None:
+        _set_blind_slots(z_ev, n, z_blinds)
+        cm_z = _commit_dev(lag, [_View(z_ev, 0, n + 2 * N_BLIND_SLOTS)])[0]
+    else:
+        cm_z = _commit_dev(pcs, [z_poly])[0]
     transcript.append_commitment(cm_z)
     mark("round2_z")
 

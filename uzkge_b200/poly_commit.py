@@ -232,6 +232,12 @@ class KZGCommitmentSchemeBN254:
         (the reference draws it from the caller's RNG): public_parameter_group_1[i] = tau^i * G, built on the GPU."""
         return cls(ffi.srs_generate(tau, max_degree + 1), window_bits)
 
+    @classmethod
+    def new_lagrange(cls, n: int, tau, window_bits: int = 0) -> "KZGCommitmentSchemeBN254":
+        """The Lagrange-basis scheme of the same trapdoor: public_parameter_group_1[i] = L_i(tau) * G over the size-n domain -- what
+        `lagrange-srs-*.bin` holds (gen_params/mod.rs:42-65) and prover_with_lagrange commits evaluation vectors against."""
+        return cls(ffi.srs_generate_lagrange(tau, n), window_bits)
+
     def close(self) -> None:
         if self._handle:
             ffi.srs_free(self._handle)
