@@ -90,7 +90,7 @@ def test_prover_rejects_an_unsatisfied_witness(gpu, bn):
     pcs.close()
 
 
-@pytest.mark.parametrize("log_size", [10, 14])
+@pytest.mark.parametrize("log_size", [10, 14, 20])
 def test_synthetic_circuit_proof_verifies(gpu, bn, oc, log_size):
     """BASELINE configs[4] at test size: a synthetic circuit of add / mul gates built in bulk, proved on the GPU, checked by the
     restated verifier under the SRS trapdoor (O(1) group operations, independent of n); the witness satisfies every gate."""
@@ -112,7 +112,8 @@ def test_synthetic_circuit_proof_verifies(gpu, bn, oc, log_size):
                 + q[7] * w[0] * w[1] * w[2] * w[3] * w[4] - q[8] * w[4]) % FR == 0
     pcs = KZGCommitmentSchemeBN254.new(n + 2, plonk.mont(TAU))
     params = plonk.indexer(cs, pcs)
-    proof = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"synthetic"), pcs, cs, params, wit)
+    lagrange = KZGCommitmentSchemeBN254.new_lagrange(n, plonk.mont(TAU)) if log_size == 14 else None   # one size through prover_with_lagrange
+    proof = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"synthetic"), pcs, cs, params, wit, lagrange_pcs=lagrange)
     vp = params.verifier_params
 
     class Trapdoor:
