@@ -81,4 +81,6 @@ def gpu():
     from uzkge_b200 import ffi
 
     ffi.init(0)
+    if os.environ.get("UZKGE_MSM_AFFINE"):      # run the same suite over the batched-affine accumulation (2 = forced at every size)
+        ffi.configure("msm_affine", int(os.environ["UZKGE_MSM_AFFINE"]))
     return ffi

@@ -736,6 +736,12 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
         }
         return UZKGE_OK;
     }
+    if (k == "msm_affine") {
+        int rc = ensure_init(-1);
+        if (rc != UZKGE_OK) return rc;
+        g.msm->set_affine((uint32_t)value);
+        return UZKGE_OK;
+    }
     if (k == "quotient_min_blocks") {
         g_quotient_min_blocks = (int)value;
         return UZKGE_OK;

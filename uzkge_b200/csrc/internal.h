@@ -146,6 +146,8 @@ struct MsmWork {
     xyzz* buckets = nullptr;          // slots * nbuckets
     ReducePlan* reduce[16] = {};      // launch plan of the bucket reduction of every slot (msm_reduce.cu)
     void* cub_temp = nullptr;
+    void* aff_ws = nullptr;           // point arrays + prefix products of the batched-affine accumulation (msm_affine.cu), on demand
+    size_t aff_ws_bytes = 0;
     cudaEvent_t sorted = nullptr, accumulated = nullptr, reduced = nullptr;  // pipeline hand-offs
 };
 struct MsmSrs {
@@ -162,6 +164,12 @@ struct MsmSrs {
     MsmWork work[2];
     size_t cub_temp_bytes = 0;
 };
+
+// batched-affine bucket accumulation (msm_affine.cu)
+size_t msm_affine_workspace_bytes(uint64_t m, uint32_t nb);
+uint32_t msm_affine_rounds(double mean_load);
+int msm_affine_accumulate(const MsmSrs* s, const MsmWork& w, void* aff_ws, uint64_t m, uint32_t nb, const uint32_t* order, uint32_t thr,
+                          uint32_t rounds, cudaStream_t st, cudaStream_t st2, cudaEvent_t fork, cudaEvent_t join);
 
 // bucket reduction (msm_reduce.cu): workspace size for window size c, plan over fixed buffers, run
 size_t msm_reduce_workspace_bytes(uint32_t c, uint32_t sm_count);
@@ -193,6 +201,7 @@ public:
     // *d_out (+)= sum_j scalars[j] * srs[idx[j]], k <= 32 (host scalars, Montgomery)
     int small_msm(const MsmSrs* s, const size_t* idx, const uint64_t* scalars, uint32_t k, bool accumulate, jacobian* d_out, cudaStream_t st);
     void force_lanes(uint32_t g) { force_lanes_ = g; }  // tuning knob (0 = automatic)
+    void set_affine(uint32_t mode) { affine_mode_ = mode; }  // 0 = XYZZ accumulation only, 1 = batched-affine tree where it pays
 
 
 private:
@@ -204,7 +213,10 @@ private:
     int sm_count_;
     cudaStream_t s_sort_ = nullptr, s_acc_ = nullptr, s_red_ = nullptr;  // the pipeline's streams
     cudaEvent_t start_ = nullptr;
+    cudaStream_t aff_stream_ = nullptr;   // second stream of the batched-affine accumulation
+    cudaEvent_t aff_fork_ = nullptr, aff_join_ = nullptr;
     uint32_t force_lanes_ = 0;
+    uint32_t affine_mode_ = 0;
     std::vector<cudaStream_t> aux_;   // auxiliary streams for the concurrent reductions of a batch
     std::vector<cudaEvent_t> join_;
     cudaEvent_t fork_ = nullptr;

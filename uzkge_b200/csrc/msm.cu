@@ -587,6 +587,7 @@ void MsmEngine::release(MsmSrs* s) {
     for (MsmWork& w : s->work) {
         for (uint32_t j = 0; j < MSM_MAX_BATCH; j++)
             if (w.reduce[j]) msm_reduce_plan_destroy(w.reduce[j]);
+        if (w.aff_ws) cudaFree(w.aff_ws);
         if (w.sorted) cudaEventDestroy(w.sorted);
         if (w.accumulated) cudaEventDestroy(w.accumulated);
         if (w.reduced) cudaEventDestroy(w.reduced);
@@ -600,6 +601,9 @@ MsmEngine::~MsmEngine() {
     for (cudaStream_t a : {s_sort_, s_acc_, s_red_})
         if (a) cudaStreamDestroy(a);
     if (start_) cudaEventDestroy(start_);
+    if (aff_stream_) cudaStreamDestroy(aff_stream_);
+    if (aff_fork_) cudaEventDestroy(aff_fork_);
+    if (aff_join_) cudaEventDestroy(aff_join_);
     if (fork_) cudaEventDestroy(fork_);
     for (cudaEvent_t e : join_) cudaEventDestroy(e);
 }
@@ -620,6 +624,8 @@ int MsmEngine::run(MsmSrs* s, size_t base_offset, const fe* d_scalars, size_t n,
 
 struct MsmEngine::GroupPlan {
     uint32_t k = 0, nb_all = 0, lanes = 1, thr = 0;
+    uint64_t m = 0;        // sorted entries of the group
+    double mean = 0;       // mean bucket load
     const uint32_t* order = nullptr;
     bool empty = false;
 };
@@ -685,6 +691,8 @@ int MsmEngine::stage_sort(MsmSrs* s, MsmWork& w, size_t base_offset, const fe* c
     UZ_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_temp, temp, ok, ov, (int)nb_all, 0, (int)cap_bits, st));
     g_prof.mark(prof, MSM_PH_OFFSETS, st);
     plan->nb_all = nb_all;
+    plan->m = m;
+    plan->mean = mean;
     plan->lanes = g;
     plan->thr = thr;
     plan->order = ov.Current();
@@ -694,6 +702,34 @@ int MsmEngine::stage_sort(MsmSrs* s, MsmWork& w, size_t base_offset, const fe* c
 
 int MsmEngine::stage_accumulate(MsmSrs* s, MsmWork& w, const GroupPlan& plan, cudaStream_t st, int prof) {
     if (plan.empty) return UZKGE_OK;
+    // large single MSMs: pairwise affine tree with shared inversions (6 products per addition instead of 10), then the XYZZ tail
+    // (mode 2 forces it for any single MSM -- the test-suite's edge cases run at small sizes)
+    const bool aff_ok = plan.k == 1 && (affine_mode_ == 2 || (affine_mode_ == 1 && plan.nb_all >= (1u << 16)));
+    const uint32_t aff_rounds = aff_ok ? msm_affine_rounds(plan.mean) : 0;
+    bool affine_done = false;
+    if (aff_rounds >= (affine_mode_ == 2 ? 1u : 2u)) {
+        const size_t need = msm_affine_workspace_bytes((uint64_t)s->windows * s->n, s->nbuckets);
+        if (w.aff_ws_bytes < need) {
+            if (w.aff_ws) cudaFree(w.aff_ws);
+            w.aff_ws = nullptr;
+            w.aff_ws_bytes = 0;
+            if (cudaMalloc(&w.aff_ws, need) == cudaSuccess)
+                w.aff_ws_bytes = need;
+            else
+                cudaGetLastError();   // no room for the affine arrays: the XYZZ kernel below does the work
+        }
+        if (w.aff_ws) {
+            if (!aff_stream_) {
+                UZ_CUDA_TRY(cudaStreamCreateWithFlags(&aff_stream_, cudaStreamNonBlocking));
+                UZ_CUDA_TRY(cudaEventCreateWithFlags(&aff_fork_, cudaEventDisableTiming));
+                UZ_CUDA_TRY(cudaEventCreateWithFlags(&aff_join_, cudaEventDisableTiming));
+            }
+            const int rc = msm_affine_accumulate(s, w, w.aff_ws, plan.m, plan.nb_all, plan.order, plan.thr, aff_rounds, st, aff_stream_,
+                                                 aff_fork_, aff_join_);
+            if (rc != UZKGE_OK) return rc;
+            affine_done = true;
+        }
+    }
     AccArgs aa;
     aa.tables = s->tables;
     aa.vals = w.vals;
@@ -704,14 +740,16 @@ int MsmEngine::stage_accumulate(MsmSrs* s, MsmWork& w, const GroupPlan& plan, cu
     aa.large_threshold = plan.thr;
     aa.large_list = w.large_list;
     aa.large_cap = s->large_cap;
-    cudaError_t e;
-    switch (plan.lanes) {
-        case 1: e = launch_accumulate<1>(aa, st); break;
-        case 2: e = launch_accumulate<2>(aa, st); break;
-        case 4: e = launch_accumulate<4>(aa, st); break;
-        case 8: e = launch_accumulate<8>(aa, st); break;
-        case 16: e = launch_accumulate<16>(aa, st); break;
-        default: e = launch_accumulate<32>(aa, st); break;
+    cudaError_t e = cudaSuccess;
+    if (!affine_done) {
+        switch (plan.lanes) {
+            case 1: e = launch_accumulate<1>(aa, st); break;
+            case 2: e = launch_accumulate<2>(aa, st); break;
+            case 4: e = launch_accumulate<4>(aa, st); break;
+            case 8: e = launch_accumulate<8>(aa, st); break;
+            case 16: e = launch_accumulate<16>(aa, st); break;
+            default: e = launch_accumulate<32>(aa, st); break;
+        }
     }
     UZ_CUDA_TRY(e);
     g_prof.mark(prof, MSM_PH_ACCUMULATE, st);
