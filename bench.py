@@ -520,21 +520,31 @@ def main() -> int:
             barrier()
             out_dn[name] = max_over_ranks(e0.elapsed_time(e1) / reps)
         # both exchanges fused into the cross-rank kernel over peer memory (cudaIpc mappings, NVLink P2P loads / stores)
-        peer = udist.PeerNtt(nt, rank, world, dev)
-        peer.x_view.copy_(mine)
-        yp = peer.transform()
-        rt_ok = rt_ok and bool(torch.equal(yp, udist.ntt_fr_distributed(mine, nt, rank, world, natural_output=False)))
-        for _ in range(2):
-            peer.transform()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            peer.transform()
-        e1.record(stream)
-        barrier()
-        out_dn["peer"] = max_over_ranks(e0.elapsed_time(e1) / reps)
-        peer.close()
+        peer_err = None
+        try:
+            peer = udist.PeerNtt(nt, rank, world, dev)
+        except Exception as e:  # no peer mappings on this box: the NCCL figures stand (every rank must agree before going on)
+            peer, peer_err = None, f"{type(e).__name__}: {e}"
+        ok_all = torch.tensor([0.0 if peer is None else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        if ok_all.item() == 1.0:
+            peer.x_view.copy_(mine)
+            yp = peer.transform()
+            rt_ok = rt_ok and bool(torch.equal(yp, udist.ntt_fr_distributed(mine, nt, rank, world, natural_output=False)))
+            for _ in range(2):
+                peer.transform()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                peer.transform()
+            e1.record(stream)
+            barrier()
+            out_dn["peer"] = max_over_ranks(e0.elapsed_time(e1) / reps)
+            peer.close()
+        else:
+            out_dn["peer"] = out_dn["cyclic"]
+            peer_err = peer_err or "peer mapping failed on another rank"
         flag = torch.tensor([1.0 if rt_ok else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         results["ntt_distributed"] = {
@@ -546,7 +556,7 @@ def main() -> int:
                     "stores into the owners' buffers, local 2^24/N transform; cyclic output layout).  nccl_*: the same steps with "
                     "NCCL all-to-alls (cyclic = same output layout; natural = one more exchange back to contiguous slices); "
                     "parity_ok: inverse(forward) round trip and fused == NCCL, on every rank",
-            "single_gpu_ms_reference": "profiles/r1d_sweep.json: 3.83 ms on one GPU",
+            "single_gpu_ms_reference": "profiles/r1d_sweep.json: 3.83 ms on one GPU", "peer_memory_error": peer_err,
         }
         del mine, y, back
         torch.cuda.empty_cache()

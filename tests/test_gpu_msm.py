@@ -197,6 +197,32 @@ def test_pipelined_batch_matches_one_by_one(gpu, oc, bn):
         gpu.srs_free(h)
 
 
+def test_batched_affine_accumulation_matches_oracle(gpu, oc, bn):
+    """The pairwise affine tree with shared inversions (csrc/msm_affine.cu; off by default, `msm_affine` = 2 forces it at every
+    size): uniform and skewed scalars, duplicated points (P + P inside a bucket), P and -P (cancellation to the identity),
+    identity bases, and a size where the tree runs several rounds."""
+    try:
+        gpu.configure("msm_affine", 2)
+        for n, seed in ((64, 1), (1000, 2), (1 << 15, 3)):
+            pts = oc.g1_random_points(n, 50 + seed)
+            pts[n // 2] = pts[0]                      # duplicate base: equal digits meet as P + P
+            pts[n // 3] = 0                           # identity base
+            neg = pts[1].copy()
+            neg[4:] = bn.ints_to_array([(bn.FQ - v) % bn.FQ for v in bn.array_to_ints(pts[1][4:].reshape(1, 4), bn.FQ)], bn.FQ)[0]
+            pts[n // 4] = neg                         # -P_1
+            sc = oc.random_fr(n, 60 + seed)
+            sc[n // 2] = sc[0]
+            sc[n // 4] = sc[1]                        # s * P_1 + s * (-P_1) = identity
+            h = gpu.srs_upload(pts)
+            try:
+                for vec in (sc, witness_like(oc, bn, n, 70 + seed)):
+                    assert same_point(oc, gpu.msm_g1(h, vec), oc.msm_g1(pts, vec)), (n, seed)
+            finally:
+                gpu.srs_free(h)
+    finally:
+        gpu.configure("msm_affine", 0)
+
+
 def test_group_helpers(gpu, oc):
     pts = oc.g1_random_points(4, 3)
     a = oc.g1_mul(pts[0], oc.random_fr(1, 1)[0])
