@@ -170,7 +170,8 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
     quotient map, openings) -- wall clock around a synchronised call, because the Fiat-Shamir transcript puts the host in the loop.
     `proofs_per_s`: witness resident in HBM; `e2e_proofs_per_s`: witness in host memory, uploaded inside the timed region.
     N > 1 GPUs: circuits up to 2^18 gates run as N independent provers (replicas; proofs are latency-bound there); larger ones
-    as ONE proof whose 13 + 16 commitments are point-split over the N GPUs (dist.SplitCommitter), driven by rank 0."""
+    as ONE proof driven by rank 0 (dist.SplitCommitter): every commitment's points are split over the N GPUs and the six
+    independent 6n transforms of the quotient round run one per GPU."""
     import torch
 
     from uzkge_b200 import KZGCommitmentSchemeBN254, ffi, plonk
@@ -295,6 +296,7 @@ def main() -> int:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
         dist.init_process_group("nccl", device_id=dev)
     ffi.init(local_rank)
     stream = torch.cuda.current_stream(dev)

@@ -176,3 +176,60 @@ def test_split_committer_world2():
         p.join(60)
         assert p.exitcode == 0
     assert all(r[1] for r in res), res
+
+
+def _transform_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch
+
+        from oracle import cpu as oc
+        from uzkge_b200 import dist as udist
+
+        def ntt_fn(t_in, len_in, dom, inverse, shift, t_out, t_scr):
+            a = t_in.numpy().view(np.uint64).reshape(-1, 4)[:len_in]
+            y = oc.ntt_fr(a, dom, inverse=inverse, coset=shift)
+            t_out[: 4 * dom].copy_(torch.from_numpy(y.view(np.int64).reshape(-1)))
+            return t_out
+
+        pts = oc.g1_random_points(8, 3)
+        sc = udist.SplitCommitter(pts, rank, world, upload=lambda p: 1, msm_fn=lambda h, t, k: torch.zeros(12, dtype=torch.int64),
+                                  add_fn=oc.g1_add_jac, ntt_fn=ntt_fn)
+        if rank != 0:
+            sc.serve()
+            q.put((rank, True))
+            return
+        len_in, dom = 19, 96                      # n + 3 coefficients on the 6 n domain, like the quotient round
+        k = oc.random_fr(1, 5)[0]
+        polys = [oc.random_fr(len_in, 30 + i) for i in range(5)]
+        jobs = [(torch.from_numpy(p.view(np.int64).reshape(-1).copy()), torch.zeros(4 * dom, dtype=torch.int64)) for p in polys]
+        sc.transform_many(jobs, len_in, dom, False, k)
+        ok = all(np.array_equal(j[1].numpy().view(np.uint64).reshape(dom, 4), oc.ntt_fr(p, dom, coset=k)) for j, p in zip(jobs, polys))
+        jobs2 = [(j[1], torch.zeros(4 * dom, dtype=torch.int64)) for j in jobs[:3]]
+        sc.transform_many(jobs2, dom, dom, True, None)          # plain inverse transforms, no shift
+        ok = ok and all(np.array_equal(j[1].numpy().view(np.uint64).reshape(dom, 4), oc.ntt_fr(jobs[i][1].numpy().view(np.uint64).reshape(dom, 4), dom, inverse=True))
+                        for i, j in enumerate(jobs2))
+        sc.shutdown()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_split_committer_distributes_transforms_world2():
+    """dist.SplitCommitter.transform_many: one polynomial per rank and round, coefficients out / evaluations back, with the oracle's
+    transform injected -- more polynomials than ranks, with and without the coset shift, forward and inverse."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    port = free_port()
+    procs = [ctx.Process(target=_transform_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res

@@ -255,10 +255,10 @@ class SplitCommitter:
     checker to exercise the protocol without a GPU.
     """
 
-    OP_EXIT, OP_COMMIT = 0, 1
+    OP_EXIT, OP_COMMIT, OP_TRANSFORM = 0, 1, 2
 
     def __init__(self, affine_xy: np.ndarray, rank: int, world: int, device=None, group=None, window_bits: int = 0,
-                 upload: Callable = None, msm_fn: Callable = None, add_fn: Callable = None):
+                 upload: Callable = None, msm_fn: Callable = None, add_fn: Callable = None, ntt_fn: Callable = None):
         import torch
 
         pts = ffi.as_u64(affine_xy, 8)
@@ -274,7 +274,9 @@ class SplitCommitter:
         self._add = add_fn or ffi.g1_add
         self._recv = torch.zeros(4 * self.chunk, dtype=torch.int64, device=self.device)
         self._pad = torch.zeros(4 * self.chunk * world, dtype=torch.int64, device=self.device) if rank == 0 else None
-        self._hdr = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._hdr = torch.zeros(8, dtype=torch.int64, device=self.device)   # op, a, b, c, 4 limbs of a coset shift
+        self._ntt = ntt_fn or self._ntt_cuda
+        self._tbuf = {}
         self._part = torch.zeros(12, dtype=torch.int64, device=self.device)
         self._parts = [torch.zeros(12, dtype=torch.int64, device=self.device) for _ in range(world)] if rank == 0 else None
         self.commits = 0
@@ -327,17 +329,86 @@ class SplitCommitter:
             self.commits += 1
         return out
 
+    # ---- independent transforms of one prover round, one polynomial per rank ("replicas": each fits one GPU)
+    def _ntt_cuda(self, t_in, len_in: int, domain_size: int, inverse: bool, shift, t_out, t_scratch):
+        ffi.ntt_fr_device(t_in.data_ptr(), t_out.data_ptr(), t_scratch.data_ptr(), len_in, domain_size, inverse, shift)
+        return t_out
+
+    def _buffers(self, len_in: int, domain_size: int):
+        import torch
+
+        key = (len_in, domain_size)
+        if key not in self._tbuf:
+            mk = lambda n: torch.zeros(4 * n, dtype=torch.int64, device=self.device)
+            self._tbuf = {key: (mk(len_in), mk(domain_size), mk(domain_size))}    # one size at a time: the 6n vectors are large
+        return self._tbuf[key]
+
+    def _transform_step(self, count: int, len_in: int, domain_size: int, inverse: bool, shift, jobs=None):
+        """Collective.  Polynomial i is transformed on rank i % world; rank 0 sends the coefficients and receives the values."""
+        import torch.distributed as dist
+
+        if self.rank == 0:
+            # rounds of `world` polynomials: at most one per rank and round, so every rank's send / recv sequence pairs up in
+            # order with rank 0's (no rank waits on a send whose receive is queued behind another send)
+            scratch = self._buffers(len_in, domain_size)[2]
+            for base in range(0, count, self.world):
+                batch = list(range(base, min(count, base + self.world)))
+                pending = [dist.isend(jobs[i][0][: 4 * len_in].contiguous(), i % self.world, group=self.group) for i in batch if i % self.world]
+                for i in batch:
+                    if i % self.world == 0:
+                        self._ntt(jobs[i][0], len_in, domain_size, inverse, shift, jobs[i][1], scratch)
+                for w_ in pending:
+                    w_.wait()
+                for i in batch:
+                    if i % self.world:
+                        dist.recv(jobs[i][1][: 4 * domain_size], i % self.world, group=self.group)
+            return
+        mine = [i for i in range(count) if i % self.world == self.rank]
+        if not mine:
+            return
+        t_in, t_out, t_scr = self._buffers(len_in, domain_size)
+        for _ in mine:
+            dist.recv(t_in, 0, group=self.group)
+            out = self._ntt(t_in, len_in, domain_size, inverse, shift, t_out, t_scr)
+            dist.send(out[: 4 * domain_size], 0, group=self.group)
+
+    def transform_many(self, jobs, len_in: int, domain_size: int, inverse: bool = False, coset_shift=None) -> None:
+        """Rank 0: `jobs` = [(src tensor holding >= len_in elements, dst tensor holding domain_size elements)]: dst = the
+        (coset) transform of src, natural order -- FpPolynomial::coset_fft_with_domain for the wire and z polynomials of the
+        quotient round (plonk/helpers.rs:256-266), one polynomial per GPU."""
+        import torch.distributed as dist
+
+        assert self.rank == 0
+        self._hdr.zero_()
+        self._hdr[0], self._hdr[1], self._hdr[2], self._hdr[3] = self.OP_TRANSFORM, len(jobs), len_in, domain_size
+        shift = None
+        if coset_shift is not None:
+            shift = np.ascontiguousarray(coset_shift, dtype=np.uint64).reshape(4)
+            self._hdr[4:8] = self._hdr.new_tensor(shift.view(np.int64).tolist())
+            self._hdr[3] = domain_size | (1 << 62)
+        if inverse:
+            self._hdr[2] = len_in | (1 << 62)
+        dist.broadcast(self._hdr, src=0, group=self.group)
+        self._transform_step(len(jobs), len_in, domain_size, inverse, shift, jobs)
+
     def serve(self) -> int:
-        """Ranks > 0: answer rank 0's commitments until it shuts the service down.  Returns the number served."""
+        """Ranks > 0: answer rank 0's commitments and transforms until it shuts the service down.  Returns the number served."""
         import torch.distributed as dist
 
         assert self.rank != 0
         while True:
             dist.broadcast(self._hdr, src=0, group=self.group)
-            op, length = (int(x) for x in self._hdr.cpu())
+            h = [int(x) for x in self._hdr.cpu()]
+            op = h[0]
             if op == self.OP_EXIT:
                 return self.commits
-            self._step(length)
+            if op == self.OP_TRANSFORM:
+                count, len_in, dom = h[1], h[2] & ((1 << 62) - 1), h[3] & ((1 << 62) - 1)
+                inverse, has_shift = bool(h[2] >> 62), bool(h[3] >> 62)
+                shift = np.array(h[4:8], dtype=np.int64).view(np.uint64) if has_shift else None
+                self._transform_step(count, len_in, dom, inverse, shift)
+                continue
+            self._step(h[1])
             self.commits += 1
 
     def shutdown(self) -> None:

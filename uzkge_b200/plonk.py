@@ -717,13 +717,19 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     if coset is None:
         coset = ws["coset"] = [DevVec(m, dev, zero=False) for _ in range(N_WIRES_PER_GATE + 3)]
     w_coset, pi_coset, z_coset, t_buf = coset[:5], coset[5], coset[6], coset[7]
-    for p, c in zip(w_polys, w_coset):
-        _coset_fft(p, m, k1, c, scratch)
+    if hasattr(pcs, "transform_many"):
+        # several GPUs: the six independent 6n transforms of this round go one per rank (dist.SplitCommitter)
+        for p in w_polys + [z_poly]:
+            p.t[4 * p.len: 4 * (n + 3)].zero_()
+        pcs.transform_many([(p.t, c.t) for p, c in zip(w_polys + [z_poly], w_coset + [z_coset])], n + 3, m, False, k1)
+    else:
+        for p, c in zip(w_polys, w_coset):
+            _coset_fft(p, m, k1, c, scratch)
+        _coset_fft(z_poly, m, k1, z_coset, scratch)
     if online_values:
         _coset_fft(pi, m, k1, pi_coset, scratch)
     else:
         pi_coset.t.zero_()
-    _coset_fft(z_poly, m, k1, z_coset, scratch)
     ffi.plonk_quotient_fr_device(
         [c.ptr for c in w_coset], [c.ptr for c in P.q_coset_evals], pi_coset.ptr, z_coset.ptr, [c.ptr for c in P.s_coset_evals],
         P.coset_quotient.ptr, P.l1_coset_evals.ptr, P.qb_coset_eval.ptr, [c.ptr for c in P.q_prk_coset_evals], mont_rows(k),
