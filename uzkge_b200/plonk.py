@@ -403,15 +403,19 @@ def _coset_fft(poly: DevVec, m: int, k1: np.ndarray, out: DevVec, scratch: DevVe
     ffi.ntt_fr_device(poly.ptr, out.ptr, scratch.ptr, poly.len, m, False, k1)
 
 
-def _commit_dev(pcs, vecs) -> list:
+def _commit_dev(pcs, vecs, overlap=None) -> list:
     """PolyComScheme::commit for device-resident coefficient vectors; independent commitments share one pass when they fit.
     `pcs` is a KZGCommitmentSchemeBN254 (bases on this GPU) or anything with `commit_device` (dist.SplitCommitter: bases split
-    over the GPUs of the box)."""
+    over the GPUs of the box).  `overlap`: a callable that enqueues device work NOT depending on these commitments; it is issued
+    after the MSMs and before the host waits for them, so the GPU keeps working while the host hashes the transcript."""
     for v in vecs:
         if v.len > pcs.max_degree() + 1:
             raise DegreeError("DegreeError")
     if hasattr(pcs, "commit_device"):
-        return pcs.commit_device(vecs)
+        out = pcs.commit_device(vecs)
+        if overlap:
+            overlap()
+        return out
     dev = vecs[0].t.device
     out = torch.zeros(12 * len(vecs), dtype=torch.int64, device=dev)
     if len(vecs) > 1:   # one call: the engine batches what fits one pass and pipelines the rest
@@ -419,8 +423,30 @@ def _commit_dev(pcs, vecs) -> list:
     else:
         for i, v in enumerate(vecs):
             ffi.msm_g1_device(pcs.handle, v.ptr, v.len, out.data_ptr() + 96 * i)
-    jac = out.cpu().numpy().view(np.uint64).reshape(len(vecs), 12)
+    if overlap:
+        # read the results back on a side stream that waits for the MSMs only, not for the overlapped work behind them
+        done = torch.cuda.Event()
+        done.record()
+        overlap()
+        side = _side_stream(dev)
+        side.wait_event(done)
+        out.record_stream(side)
+        with torch.cuda.stream(side):
+            host = out.cpu()
+    else:
+        host = out.cpu()
+    jac = host.numpy().view(np.uint64).reshape(len(vecs), 12)
     return [KZGCommitment(jac[i].copy()) for i in range(len(vecs))]
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
 
 
 N_BLIND_SLOTS = 3   # the largest hiding degree (TurboCS::get_hiding_degree, z_poly)
@@ -667,6 +693,12 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
             ffi.fr_add_sparse_device(pi.ptr, idx[i:i + ffi.SPARSE_MAX], mont_rows(online_values[i:i + ffi.SPARSE_MAX]))
         _ifft(pi.ptr, n, pi, scratch)
 
+    coset = ws.get("coset")
+    if coset is None:
+        coset = ws["coset"] = [DevVec(m, dev, zero=False) for _ in range(N_WIRES_PER_GATE + 3)]
+    w_coset, pi_coset, z_coset, t_buf = coset[:5], coset[5], coset[6], coset[7]
+    multi_gpu = hasattr(pcs, "transform_many")
+
     # 2. witness polynomials: extend, interpolate, hide, commit
     stride = n + 8          # every evaluation vector is followed by the 6 blind slots of the Lagrange commitment
     ext = ws.get("ext") or DevVec(N_WIRES_PER_GATE * stride, dev)
@@ -678,13 +710,21 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         _ifft(ext.at(i * stride), n, f, scratch)
         w_blinds.append(hide_polynomial(prng, f, cs.get_hiding_degree(i), n))
         w_polys.append(f)
+    # the quotient round's coset evaluations of the wire polynomials depend on no challenge: they are enqueued behind the MSMs,
+    # so the GPU computes them while the host waits for the commitments and hashes the transcript
+
+    def wire_cosets():
+        if not multi_gpu:
+            for p, c in zip(w_polys, w_coset):
+                _coset_fft(p, m, k1, c, scratch)
+
     if lagrange_pcs is not None:
         lag = _lagrange_commit_scheme(pcs, lagrange_pcs, n, ws)
         for i in range(N_WIRES_PER_GATE):
             _set_blind_slots(ext, i * stride + n, w_blinds[i])
-        cm_w_vec = _commit_dev(lag, [_View(ext, i * stride, n + 2 * N_BLIND_SLOTS) for i in range(N_WIRES_PER_GATE)])
+        cm_w_vec = _commit_dev(lag, [_View(ext, i * stride, n + 2 * N_BLIND_SLOTS) for i in range(N_WIRES_PER_GATE)], overlap=wire_cosets)
     else:
-        cm_w_vec = _commit_many(pcs, w_polys)
+        cm_w_vec = _commit_dev(pcs, w_polys, overlap=wire_cosets)
     for cm in cm_w_vec:
         transcript.append_commitment(cm)
     mark("round1_wires")
@@ -703,29 +743,25 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
                                 P.group.ptr, mont_rows(k), mont(beta), mont(gamma), n, z_ev.ptr, tmp.ptr)
     _ifft(z_ev.ptr, n, z_poly, scratch)
     z_blinds = hide_polynomial(prng, z_poly, 3, n)
+    def z_coset_eval():
+        if not multi_gpu:
+            _coset_fft(z_poly, m, k1, z_coset, scratch)
+
     if lagrange_pcs is not None:
         _set_blind_slots(z_ev, n, z_blinds)
-        cm_z = _commit_dev(lag, [_View(z_ev, 0, n + 2 * N_BLIND_SLOTS)])[0]
+        cm_z = _commit_dev(lag, [_View(z_ev, 0, n + 2 * N_BLIND_SLOTS)], overlap=z_coset_eval)[0]
     else:
-        cm_z = _commit_dev(pcs, [z_poly])[0]
+        cm_z = _commit_dev(pcs, [z_poly], overlap=z_coset_eval)[0]
     transcript.append_commitment(cm_z)
     mark("round2_z")
 
     # 6. alpha;  7. t = numerator / Z_H on the coset k[1] <w_m>, split, commit (helpers.rs:223-678, 1323-1408)
     alpha = transcript.get_challenge_field_elem()
-    coset = ws.get("coset")
-    if coset is None:
-        coset = ws["coset"] = [DevVec(m, dev, zero=False) for _ in range(N_WIRES_PER_GATE + 3)]
-    w_coset, pi_coset, z_coset, t_buf = coset[:5], coset[5], coset[6], coset[7]
-    if hasattr(pcs, "transform_many"):
+    if multi_gpu:
         # several GPUs: the six independent 6n transforms of this round go one per rank (dist.SplitCommitter)
         for p in w_polys + [z_poly]:
             p.t[4 * p.len: 4 * (n + 3)].zero_()
         pcs.transform_many([(p.t, c.t) for p, c in zip(w_polys + [z_poly], w_coset + [z_coset])], n + 3, m, False, k1)
-    else:
-        for p, c in zip(w_polys, w_coset):
-            _coset_fft(p, m, k1, c, scratch)
-        _coset_fft(z_poly, m, k1, z_coset, scratch)
     if online_values:
         _coset_fft(pi, m, k1, pi_coset, scratch)
     else:
