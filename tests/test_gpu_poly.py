@@ -144,3 +144,112 @@ def test_eval_batch_matches_oracle(gpu, oc):
     gpu.poly_eval_batch_fr_device([d[3].data_ptr(), d[8].data_ptr()], [lens[3], lens[8]], [0, 0], pts[:1], vals.data_ptr())
     got = vals.cpu().numpy().view(np.uint64).reshape(2, 4)
     assert np.array_equal(got[0], oc.fr_eval(polys[3], pts[0])) and np.array_equal(got[1], oc.fr_eval(polys[8], pts[0]))
+
+
+# ---------------------------------------------------------------- the prover's elementwise glue (csrc/plonk_glue.cu), kernel by kernel
+def _dev(a):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64).reshape(-1)).cuda()
+
+
+def _host(t, n):
+    return t.cpu().numpy().view(np.uint64).reshape(-1, 4)[:n]
+
+
+def test_fr_lincomb_matches_bigint(gpu, oc, bn):
+    """out = sum_j c_j p_j with ragged lengths (r_poly_or_comm, batch_prove), including aliasing of the output with an input."""
+    import torch
+
+    lens = [1, 5, 1000, 1027, 4096, 3]
+    polys = [oc.random_fr(n, 800 + i) for i, n in enumerate(lens)]
+    coefs = oc.random_fr(len(lens), 9)
+    out_len = 4200
+    d = [_dev(p) for p in polys]
+    out = torch.zeros(4 * out_len, dtype=torch.int64, device="cuda")
+    gpu.fr_lincomb_device([t.data_ptr() for t in d], lens, coefs, out.data_ptr(), out_len)
+    pi, ci = [ints(bn, p) for p in polys], ints(bn, coefs)
+    want = [sum(ci[j] * pi[j][i] for j in range(len(lens)) if i < lens[j]) % bn.FR for i in range(out_len)]
+    assert ints(bn, _host(out, out_len)) == want
+    # in place: p_4 <- 2 p_4 + p_2
+    two_one = fr(bn, [2, 1])
+    gpu.fr_lincomb_device([d[4].data_ptr(), d[2].data_ptr()], [4096, 1000], two_one, d[4].data_ptr(), 4096)
+    want = [(2 * pi[4][i] + (pi[2][i] if i < 1000 else 0)) % bn.FR for i in range(4096)]
+    assert ints(bn, _host(d[4], 4096)) == want
+
+
+def test_fr_sparse_add_powers_gather_mul_trim(gpu, oc, bn):
+    import torch
+
+    n = 5000
+    a = oc.random_fr(n, 31)
+    ai = ints(bn, a)
+    # add_coef_assign on a few coefficients, a repeated index included (applied in order)
+    t = _dev(a)
+    gpu.fr_add_sparse_device(t.data_ptr(), [0, 4999, 7, 7], fr(bn, [5, -1, 11, 13]))
+    got = ints(bn, _host(t, n))
+    want = list(ai)
+    want[0] = (want[0] + 5) % bn.FR
+    want[4999] = (want[4999] - 1) % bn.FR
+    want[7] = (want[7] + 24) % bn.FR
+    assert got == want
+    # powers: scale * base^i (domain.elements(), coset_quotient)
+    base, scale = oc.random_fr(2, 5)
+    out = torch.zeros(4 * n, dtype=torch.int64, device="cuda")
+    gpu.fr_powers_device(base, n, out.data_ptr(), scale=scale)
+    b, s = ints(bn, base)[0], ints(bn, scale)[0]
+    assert ints(bn, _host(out, n)) == [s * pow(b, i, bn.FR) % bn.FR for i in range(n)]
+    gpu.fr_powers_device(base, 7, out.data_ptr())
+    assert ints(bn, _host(out, 7)) == [pow(b, i, bn.FR) for i in range(7)]
+    # gather (extend_witness) and pointwise product
+    idx = np.random.default_rng(1).integers(0, n, 3 * n).astype(np.uint32)
+    d_idx = torch.from_numpy(idx.view(np.int32)).cuda()
+    g = torch.zeros(4 * 3 * n, dtype=torch.int64, device="cuda")
+    da = _dev(a)                 # keep the tensors alive: a temporary's memory is recycled as soon as its pointer is taken
+    gpu.fr_gather_device(da.data_ptr(), d_idx.data_ptr(), 3 * n, g.data_ptr())
+    assert np.array_equal(_host(g, 3 * n), a[idx])
+    bvec = oc.random_fr(n, 32)
+    db = _dev(bvec)
+    prod = torch.zeros(4 * n, dtype=torch.int64, device="cuda")
+    gpu.fr_mul_device(da.data_ptr(), db.data_ptr(), n, prod.data_ptr())
+    assert np.array_equal(_host(prod, n), oc.fr_mul(a, bvec))
+    # trailing-zero trim
+    z = a.copy()
+    z[3000:] = 0
+    dz = _dev(z)
+    assert gpu.fr_trimmed_len_device(dz.data_ptr(), n) == 3000
+    z[:] = 0
+    dz = _dev(z)
+    assert gpu.fr_trimmed_len_device(dz.data_ptr(), n) == 0
+    z[n - 1, 2] = 1
+    dz = _dev(z)
+    assert gpu.fr_trimmed_len_device(dz.data_ptr(), n) == n
+
+
+@pytest.mark.parametrize("n", [2, 8, 1000, 4097])
+def test_z_evals_match_restated_z_poly(gpu, oc, bn, n):
+    """uzkge_cuda_plonk_z_evals_fr_device against z_poly's loop (plonk/helpers.rs:160-220) in big integers: random wires, a random
+    encoded permutation, device-resident grand product."""
+    import torch
+
+    F = bn.FR
+    w = [oc.random_fr(n, 40 + j) for j in range(5)]
+    sig = [oc.random_fr(n, 50 + j) for j in range(5)]
+    group = oc.random_fr(n, 60)
+    k = oc.random_fr(5, 61)
+    beta, gamma = oc.random_fr(2, 62)
+    dw, ds, dg = [_dev(x) for x in w], [_dev(x) for x in sig], _dev(group)
+    z = torch.zeros(4 * n, dtype=torch.int64, device="cuda")
+    tmp = torch.zeros(4 * 4 * n, dtype=torch.int64, device="cuda")
+    gpu.plonk_z_evals_fr_device([t.data_ptr() for t in dw], [t.data_ptr() for t in ds], dg.data_ptr(), k, beta, gamma, n, z.data_ptr(), tmp.data_ptr())
+    wi, si, gi, ki = [ints(bn, x) for x in w], [ints(bn, x) for x in sig], ints(bn, group), ints(bn, k)
+    b, g_ = ints(bn, beta)[0], ints(bn, gamma)[0]
+    want, prev = [1], 1
+    for i in range(n - 1):
+        num = den = 1
+        for j in range(5):
+            num = num * (wi[j][i] + g_ + b * ki[j] * gi[i]) % F
+            den = den * (wi[j][i] + g_ + b * si[j][i]) % F
+        prev = prev * num % F * pow(den, -1, F) % F
+        want.append(prev)
+    assert ints(bn, _host(z, n)) == want
