@@ -69,6 +69,11 @@ UZKGE_API int32_t uzkge_cuda_srs_generate(const uint64_t tau[4], size_t n, uint6
  * trapdoor derives the same points from the monomial SRS with a G1 inverse transform (not built). */
 UZKGE_API int32_t uzkge_cuda_srs_generate_lagrange(const uint64_t tau[4], size_t n, uint64_t* out_affine_xy);
 
+/* The same SRS WITHOUT the trapdoor: out[i] = (1 / n) sum_j w^(-i j) monomial[j], an inverse transform over G1 points ("iNTT in the
+ * exponent") of the first n = 2^k points of a monomial SRS (identity points allowed).  (n / 2) log2 n scalar
+ * multiplications: milliseconds at the bundled circuit sizes, seconds at 2^22; run once per SRS. */
+UZKGE_API int32_t uzkge_cuda_srs_lagrange_from_monomial(const uint64_t* monomial_affine_xy, size_t n, uint64_t* out_affine_xy);
+
 /* ---- MSM ------------------------------------------------------------------------------------------
  * out = sum_{i < n} scalars[i] * srs[base_offset + i].  Replaces `G1Projective::msm(&points_raw, &coefs)`
  * (kzg_poly_commitment.rs:290) for KZGCommitmentSchemeBN254::commit (:278-293).

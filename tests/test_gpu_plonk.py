@@ -172,3 +172,25 @@ def test_prover_with_lagrange_gives_the_same_proof(gpu, bn, n_gates):
     assert _proof_as_oracle_dict(bn, a) == _proof_as_oracle_dict(bn, c)
     for p in (pcs, lagrange_pcs, other):
         p.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 256, 4096])
+def test_lagrange_srs_from_monomial_without_trapdoor(gpu, oc, bn, n):
+    """uzkge_cuda_srs_lagrange_from_monomial (the inverse transform over G1 points) must give exactly the points
+    L_i(tau) * G that the trapdoor route gives; for n = 8 also against the definition (1 / n) sum_j w^(-i j) P_j in big integers,
+    with an identity point among the inputs."""
+    from uzkge_b200 import plonk
+
+    tau_m = plonk.mont(TAU)
+    mono = gpu.srs_generate(tau_m, n)
+    got = gpu.srs_lagrange_from_monomial(mono, n)
+    assert np.array_equal(got, gpu.srs_generate_lagrange(tau_m, n))
+    if n == 8:
+        pts = mono.copy()
+        pts[5] = 0                                                   # identity (the padded SRS holds such entries)
+        got = gpu.srs_lagrange_from_monomial(pts, n)
+        P = bn.array_to_affine(pts)
+        w_inv, n_inv = pow(bn.root_of_unity(n), -1, bn.FR), pow(n, -1, bn.FR)
+        for i in range(n):
+            want = bn.msm_naive(P, [n_inv * pow(w_inv, i * j, bn.FR) % bn.FR for j in range(n)])
+            assert bn.array_to_affine(got[i].reshape(1, 8))[0] == want, i

@@ -638,6 +638,34 @@ UZKGE_API int32_t uzkge_cuda_srs_generate_lagrange(const uint64_t tau[4], size_t
     return UZKGE_OK;
 }
 
+UZKGE_API int32_t uzkge_cuda_srs_lagrange_from_monomial(const uint64_t* monomial_affine_xy, size_t n, uint64_t* out_affine_xy) {
+    if (!monomial_affine_xy || !out_affine_xy) return fail(UZKGE_ERR_ARG, "srs_lagrange_from_monomial: null pointer");
+    if (n == 0 || (n & (n - 1)) || n > (1ull << 24)) return fail(UZKGE_ERR_SIZE, "srs_lagrange_from_monomial: n must be a power of two <= 2^24");
+    API_ENTER(-1);
+    uint32_t log_n = 0;
+    while ((1ull << log_n) < n) log_n++;
+    bool ok = false;
+    const fe w = ntt_root_of_unity(n, &ok);
+    if (!ok) return fail(UZKGE_ERR_SIZE, "srs_lagrange_from_monomial: no domain of this size");
+    const fe w_inv = fe_inv<FrP>(w);
+    fe nf = fe_zero();
+    nf.l[0] = (uint32_t)n;
+    const fe n_inv = fe_from_mont<FrP>(fe_inv<FrP>(fe_to_mont<FrP>(nf)));   // canonical bits for the double-and-add
+    CUDA_OR_FAIL(g.data.reserve(n * sizeof(affine) + 64), "srs_lagrange_from_monomial: buffer");
+    CUDA_OR_FAIL(g.scratch.reserve(n * sizeof(xyzz) + (n / 2 + 1) * sizeof(fe) + 64), "srs_lagrange_from_monomial: buffer");
+    affine* d_pts = (affine*)g.data.p;
+    xyzz* d_work = (xyzz*)g.scratch.p;
+    fe* d_tw = (fe*)(d_work + n);
+    CUDA_OR_FAIL(cudaMemcpyAsync(d_pts, monomial_affine_xy, n * sizeof(affine), cudaMemcpyHostToDevice, g.stream), "srs_lagrange_from_monomial: H2D");
+    int rc = fr_powers_run((const uint64_t*)&w_inv, nullptr, n / 2 ? n / 2 : 1, d_tw, g.stream);
+    if (rc != UZKGE_OK) return engine_fail(rc, "srs_lagrange_from_monomial: twiddles");
+    rc = ec_intt_run(d_pts, (uint32_t)n, log_n, d_tw, n_inv, d_work, d_pts, g.stream);
+    if (rc != UZKGE_OK) return engine_fail(rc, "srs_lagrange_from_monomial: launch");
+    CUDA_OR_FAIL(cudaMemcpyAsync(out_affine_xy, d_pts, n * sizeof(affine), cudaMemcpyDeviceToHost, g.stream), "srs_lagrange_from_monomial: D2H");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "srs_lagrange_from_monomial: execution");
+    return UZKGE_OK;
+}
+
 UZKGE_API int32_t uzkge_cuda_msm_g1_small_device(uint64_t handle, const size_t* idx, const uint64_t* scalars_host, size_t k, int32_t accumulate,
                                                  void* d_out_jac, void* stream) {
     if (!d_out_jac || (k && (!idx || !scalars_host))) return fail(UZKGE_ERR_ARG, "msm_g1_small_device: null pointer");

@@ -165,6 +165,10 @@ struct MsmSrs {
     size_t cub_temp_bytes = 0;
 };
 
+// inverse transform over G1 points: Lagrange SRS from the monomial SRS (ec_ntt.cu)
+int ec_intt_run(const affine* d_points, uint32_t n, uint32_t log_n, const fe* d_tw, const fe& n_inv_canonical, xyzz* d_work, affine* d_out,
+                cudaStream_t st);
+
 // batched-affine bucket accumulation (msm_affine.cu)
 size_t msm_affine_workspace_bytes(uint64_t m, uint32_t nb);
 uint32_t msm_affine_rounds(double mean_load);

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "uzkge_cuda_srs_generate": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_srs_generate_lagrange": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_msm_g1_small_device": (C.c_int32, [C.c_uint64, C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_srs_lagrange_from_monomial": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_srs_free": (C.c_int32, [C.c_uint64]),
     "uzkge_cuda_msm_g1": (C.c_int32, [C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_msm_g1_batch": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p]),
@@ -245,6 +246,16 @@ def srs_generate_lagrange(tau, n: int) -> np.ndarray:
     t = as_u64(tau).reshape(4)
     out = np.zeros((n, 8), dtype=np.uint64)
     check(lib().uzkge_cuda_srs_generate_lagrange(ptr(t), n, ptr(out)))
+    return out
+
+
+def srs_lagrange_from_monomial(monomial_affine_xy, n: int) -> np.ndarray:
+    """(1 / n) sum_j w^(-i j) monomial[j]: the Lagrange SRS of the size-n domain from the first n monomial points, no trapdoor."""
+    pts = as_u64(monomial_affine_xy, 8)
+    assert pts.shape[0] >= n
+    src = np.ascontiguousarray(pts[:n])
+    out = np.zeros((n, 8), dtype=np.uint64)
+    check(lib().uzkge_cuda_srs_lagrange_from_monomial(ptr(src), n, ptr(out)))
     return out
 
 

@@ -238,6 +238,13 @@ class KZGCommitmentSchemeBN254:
         `lagrange-srs-*.bin` holds (gen_params/mod.rs:42-65) and prover_with_lagrange commits evaluation vectors against."""
         return cls(ffi.srs_generate_lagrange(tau, n), window_bits)
 
+    def derive_lagrange(self, n: int, window_bits: int = 0) -> "KZGCommitmentSchemeBN254":
+        """The Lagrange-basis scheme of THIS SRS for the size-n domain, derived without the trapdoor by an inverse transform over
+        the first n G1 points (uzkge_cuda_srs_lagrange_from_monomial)."""
+        if n > self.public_parameter_group_1.shape[0]:
+            raise ParameterError("the monomial SRS is shorter than the domain")
+        return KZGCommitmentSchemeBN254(ffi.srs_lagrange_from_monomial(self.public_parameter_group_1, n), window_bits)
+
     def close(self) -> None:
         if self._handle:
             ffi.srs_free(self._handle)
