@@ -785,11 +785,12 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
             tp.t[: 4 * take].copy_(t_buf.t[4 * start: 4 * (start + take)])
         rand = fr_rand(prng)
         if i != N_WIRES_PER_GATE - 1:
+            # coefs.resize(n + 1, zero); coefs[n] += rand; coefs[0] -= prev_coef   (helpers.rs:1351-1354)
             _add_coefs(tp, [piece, 0], [rand, -prev])
             tp.len = piece + 1
-        elif take == 0:
-            _add_coefs(tp, [0], [-prev])
         else:
+            # the last piece: [-prev_coef] when it is empty, else coefs[0] -= prev_coef   (helpers.rs:1355-1361); the buffer is
+            # zero-initialised, so both cases are one add at index 0
             _add_coefs(tp, [0], [-prev])
         prev = rand
         t_polys.append(tp)
