@@ -178,6 +178,19 @@ typedef struct {
     size_t m, factor;
 } uzkge_quotient_args;
 UZKGE_API int32_t uzkge_cuda_plonk_quotient_fr_device(const uzkge_quotient_args* args, void* d_out, void* stream);
+/* The same map for the `shuffle` feature set (what zshuffle is built with): terms 12-18 of t_poly (plonk/helpers.rs:416-640) on top of
+ * terms 1-11 -- the remark gates' elliptic-curve additions selected by the witness selectors, and the selector constraints.  Device
+ * arrays of m elements: the coset evaluations of the 3 witness-selector polynomials (prover.rs:148-165), of q_ecc and of the 12 + 12
+ * shuffle public-key / generator selector polynomials (indexer.rs:447-501; order x_00..x_11, y_00..y_11, dxy_00..dxy_11). */
+typedef struct {
+    const void* w_sel[3];
+    const void* q_ecc;
+    const void* pk[12];
+    const void* gen[12];
+    uint64_t edwards_a[4];
+} uzkge_quotient_shuffle_args;
+UZKGE_API int32_t uzkge_cuda_plonk_quotient_shuffle_fr_device(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* shuffle,
+                                                              void* d_out, void* stream);
 
 /* ---- elementwise glue of a device-resident prover; DEVICE pointers, caller's stream, no copies, no sync ------
  * out[i] = sum_{j < k} coefs[j] * polys[j][i] for i < out_len, where polys[j][i] = 0 for i >= lens[j]; coefs: k Montgomery Fr on

@@ -27,8 +27,27 @@ def z_h_inv_coset_evals(k1: int, group_gen_m: int, n: int, factor: int):
     return out
 
 
-def quotient_coset_evals(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, alpha, beta, gamma, g, g_inv, z_h_inv, factor):
-    """helpers.rs:284-669.  w: 5 lists of m values, q: 9, s: 5, q_prk: 4; the rest lists of m values or scalars."""
+def shuffle_terms(wv, w0n, w1n, w2n, ws, q_ecc, pk, gen, edwards_a, alpha):
+    """Terms 12-18 of t_poly's numerator (helpers.rs:416-640, `shuffle` feature) at one point.  ws: the 3 witness-selector values,
+    pk / gen: the 12 public-key / generator selector values (x_00..x_11, y_00..y_11, dxy_00..dxy_11)."""
+    a = [pow(alpha, i, FR) for i in range(17)]
+    sel = [((1 - ws[0]) * (1 - ws[1]) + q_ecc - 1) % FR, ws[0] * (1 - ws[1]) % FR, (1 - ws[0]) * ws[1] % FR, ws[0] * ws[1] % FR]
+    t12 = t13 = t14 = t15 = 0
+    for c in range(4):
+        t12 += sel[c] * (ws[2] * w0n - ws[2] * wv[0] * pk[4 + c] - wv[1] * pk[c] + wv[0] * wv[1] * w0n * pk[8 + c])
+        t13 += sel[c] * (ws[2] * w1n + wv[0] * edwards_a * pk[c] - ws[2] * wv[1] * pk[4 + c] - wv[0] * wv[1] * w1n * pk[8 + c])
+        t14 += sel[c] * (ws[2] * w2n - ws[2] * wv[2] * gen[4 + c] - wv[3] * gen[c] + wv[2] * wv[3] * w2n * gen[8 + c])
+        t15 += sel[c] * (ws[2] * wv[4] + wv[2] * edwards_a * gen[c] - ws[2] * wv[3] * gen[4 + c] - wv[2] * wv[3] * wv[4] * gen[8 + c])
+    t16 = q_ecc * ws[0] * (1 - ws[0]) + (1 - q_ecc) * ws[0]
+    t17 = q_ecc * ws[1] * (1 - ws[1]) + (1 - q_ecc) * ws[1]
+    t18 = q_ecc * (1 + ws[2]) * (1 - ws[2])
+    return (a[10] * t12 + a[11] * t13 + a[12] * t14 + a[13] * t15 + a[14] * t16 + a[15] * t17 + a[16] * t18) % FR
+
+
+def quotient_coset_evals(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, alpha, beta, gamma, g, g_inv, z_h_inv, factor, shuffle=None):
+    """helpers.rs:284-669.  w: 5 lists of m values, q: 9, s: 5, q_prk: 4; the rest lists of m values or scalars.
+    shuffle: None (default feature set, terms 1-11) or a dict {w_sel: 3 lists, q_ecc: list, pk: 12 lists, gen: 12 lists,
+    edwards_a: scalar} adding terms 12-18."""
     m = len(z)
     a = [pow(alpha, i, FR) for i in range(10)]
     g2p1 = (g * g + 1) % FR
@@ -57,5 +76,9 @@ def quotient_coset_evals(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, alpha
         term9 = a[7] * prk3 * (pow(tmp - wv[4], 5, FR) + g * tmp * tmp - (g * w320 + g2p1 * w221 + prk2))
         term11 = a[9] * prk3 * (pow(tmp - wv[4], 5, FR) + g * wv[4] * wv[4] + g_inv - w1n)
         num = term1 + term2 + (term4 - term3) + term5 + term6 + term7 - term8 - term9 - term10 - term11
+        if shuffle is not None:
+            sh = shuffle
+            num += shuffle_terms(wv, w0n, w1n, w2n, [sh["w_sel"][j][p] for j in range(3)], sh["q_ecc"][p], [sh["pk"][j][p] for j in range(12)],
+                                 [sh["gen"][j][p] for j in range(12)], sh["edwards_a"], alpha)
         out.append(num % FR * z_h_inv[p % factor] % FR)
     return out

@@ -202,6 +202,7 @@ class TurboCS:
         self.public_vars_constraint_indices = []
         self.public_vars_witness_indices = []
         self.boolean_constraint_indices = []
+        self.edwards_a = 0
         self.insert_constant_gate(0, 0)
         self.insert_constant_gate(1, 1)
 
@@ -333,7 +334,9 @@ def _g1_lin(terms):
 
 
 # ---------------------------------------------------------------- indexer (plonk/indexer.rs:248-536)
-def indexer(cs: TurboCS, pcs: Kzg):
+def indexer(cs: TurboCS, pcs: Kzg, shuffle: bool = False):
+    """shuffle = True adds what the `shuffle` feature adds (indexer.rs:447-501): q_ecc and the 12 + 12 shuffle selector polynomials
+    (all zero for circuits without remark gates -- the only circuits this restatement builds)."""
     n, m = cs.size, cs.quot_eval_dom_size()
     factor = m // n
     root = bn.root_of_unity(n)
@@ -371,6 +374,14 @@ def indexer(cs: TurboCS, pcs: Kzg):
         "anemoi_generator": 0, "anemoi_generator_inv": 0, "k": k, "cs_size": n,
         "public_vars_constraint_indices": list(cs.public_vars_constraint_indices), "lagrange_constants": lagrange_constants,
     }
+    P["shuffle"] = shuffle
+    if shuffle:
+        P["q_ecc_poly"], P["q_ecc_coset"] = pre([0] * n)
+        P["q_gen_polys"], P["q_gen_coset"] = zip(*[pre([0] * n) for _ in range(12)])
+        P["q_pk_polys"], P["q_pk_coset"] = P["q_gen_polys"], P["q_gen_coset"]          # indexer.rs:493-496
+        P["vp"].update({"cm_q_ecc": pcs.commit(P["q_ecc_poly"]), "cm_shuffle_generator_vec": [pcs.commit(p) for p in P["q_gen_polys"]],
+                        "cm_shuffle_public_key_vec": [pcs.commit(p) for p in P["q_pk_polys"]], "edwards_a": cs.edwards_a, "root": root,
+                        "pi_points": [pow(root, ci, FR) for ci in cs.public_vars_constraint_indices], "pi_lagrange": lagrange_constants})
     return P
 
 
@@ -400,12 +411,17 @@ def z_evals(P, w_ext, beta, gamma):
     return out
 
 
-def t_poly(P, w_polys, z_poly, alpha, beta, gamma, pi_poly):
+def t_poly(P, w_polys, z_poly, alpha, beta, gamma, pi_poly, w_sel_polys=None):
     m, k = P["m"], P["vp"]["k"]
     co = lambda c: bn.coset_fft(c, m, k[1])
+    sh = None
+    if w_sel_polys is not None:
+        sh = {"w_sel": [co(p) for p in w_sel_polys], "q_ecc": P["q_ecc_coset"], "pk": P["q_pk_coset"], "gen": P["q_gen_coset"],
+              "edwards_a": P["vp"]["edwards_a"]}
     evals = qmap.quotient_coset_evals(
         [co(p) for p in w_polys], P["q_coset"], co(pi_poly), co(z_poly), P["s_coset"], P["coset_quotient"], P["l1_coset"], P["qb_coset"],
-        P["q_prk_coset"], k, alpha, beta, gamma, P["vp"]["anemoi_generator"], P["vp"]["anemoi_generator_inv"], P["z_h_inv"], P["factor"])
+        P["q_prk_coset"], k, alpha, beta, gamma, P["vp"]["anemoi_generator"], P["vp"]["anemoi_generator_inv"], P["z_h_inv"], P["factor"],
+        shuffle=sh)
     return bn.trim(bn.coset_ifft(evals, m, inv_mod(k[1], FR)))
 
 
@@ -484,8 +500,11 @@ def batch_prove(tr, pcs, polys, point, max_degree):
 
 
 def prover(rng, tr, pcs, cs, P, witness):
+    """prover.rs:88-394, lagrange_pcs = None.  With P["shuffle"] (indexer(..., shuffle=True)) the `shuffle` feature set: witness-selector
+    polynomials committed after the wires, quotient terms 12-18, q_ecc / w_sel openings, linearisation parts 6-9."""
     n, vp = P["n"], P["vp"]
     k, root = vp["k"], P["root"]
+    shuffle = P.get("shuffle", False)
     online = [witness[i] for i in cs.public_vars_witness_indices]
     transcript_init_plonk(tr, vp, online, root)
     pi_evals = [0] * n
@@ -501,6 +520,15 @@ def prover(rng, tr, pcs, cs, P, witness):
         tr.point(cm)
         w_polys.append(f)
         cm_w.append(cm)
+    w_sel_polys, cm_w_sel = [], []
+    if shuffle:
+        for _ in range(3):                      # compute_witness_selectors: all zero without remark gates (turbo/mod.rs:148-163)
+            f = bn.trim(bn.ifft([0] * n, n))
+            hide_polynomial(rng, f, 2, n)
+            cm = pcs.commit(f)
+            tr.point(cm)
+            w_sel_polys.append(f)
+            cm_w_sel.append(cm)
     beta = tr.challenge()
     tr.byte(0x01)
     gamma = tr.challenge()
@@ -509,7 +537,7 @@ def prover(rng, tr, pcs, cs, P, witness):
     cm_z = pcs.commit(z)
     tr.point(cm_z)
     alpha = tr.challenge()
-    t = t_poly(P, w_polys, z, alpha, beta, gamma, pi)
+    t = t_poly(P, w_polys, z, alpha, beta, gamma, pi, w_sel_polys if shuffle else None)
     t_polys = split_t(rng, t, N_WIRES, n + 2)
     cm_t = [pcs.commit(p) for p in t_polys]
     for c in cm_t:
@@ -521,26 +549,56 @@ def prover(rng, tr, pcs, cs, P, witness):
     zeta_omega = root * zeta % FR
     z_ev_omega = p_eval(z, zeta_omega)
     w_ev_omega = [p_eval(p, zeta_omega) for p in w_polys[:3]]
-    for v in w_ev + s_ev:
+    q_ecc_ev = p_eval(P["q_ecc_poly"], zeta) if shuffle else 0
+    w_sel_ev = [p_eval(p, zeta) for p in w_sel_polys]
+    for v in w_ev + s_ev + w_sel_ev:
         tr.fr(v)
     tr.fr(prk3)
     tr.fr(prk4)
     tr.fr(z_ev_omega)
+    if shuffle:
+        tr.fr(q_ecc_ev)
     for v in w_ev_omega:
         tr.fr(v)
     u = tr.challenge()
     z_h_ev, l1_ev = first_lagrange(zeta, n)
     src = {"q": P["q_polys"], "z": [z], "s_last": [P["s_polys"][N_WIRES - 1]], "qb": [P["qb_poly"]], "prk": P["q_prk_polys"], "t": t_polys}
-    r = _lin_polys([(s, src[name][i]) for s, (name, i) in r_scalars(k, w_ev, s_ev, prk3, z_ev_omega, alpha, beta, gamma, zeta, l1_ev,
-                                                                     z_h_ev, n + 2)])
-    open_zeta = w_polys + list(P["s_polys"][:N_WIRES - 1]) + [P["q_prk_polys"][2], P["q_prk_polys"][3], r]
-    wit_zeta = batch_prove(tr, pcs, open_zeta, zeta, n + 2)
-    wit_zeta_omega = batch_prove(tr, pcs, [z, w_polys[0], w_polys[1], w_polys[2]], zeta_omega, n + 2)
-    return {
+    proof = {
         "cm_w_vec": cm_w, "cm_t_vec": cm_t, "cm_z": cm_z, "prk_3_poly_eval_zeta": prk3, "prk_4_poly_eval_zeta": prk4,
         "w_polys_eval_zeta": w_ev, "w_polys_eval_zeta_omega": w_ev_omega, "z_eval_zeta_omega": z_ev_omega, "s_polys_eval_zeta": s_ev,
-        "opening_witness_zeta": wit_zeta, "opening_witness_zeta_omega": wit_zeta_omega, "_u": u,
     }
+    if shuffle:
+        from .plonk_verifier_shuffle import r_terms      # the term list the golden-pinned verifier sums over commitments
+
+        proof.update({"cm_w_sel_vec": cm_w_sel, "q_ecc_poly_eval_zeta": q_ecc_ev, "w_sel_polys_eval_zeta": w_sel_ev})
+        src.update({"pk": P["q_pk_polys"], "gen": P["q_gen_polys"]})
+        terms = r_terms(k, vp["edwards_a"], proof, alpha, beta, gamma, zeta, l1_ev, z_h_ev, n + 2)
+    else:
+        terms = r_scalars(k, w_ev, s_ev, prk3, z_ev_omega, alpha, beta, gamma, zeta, l1_ev, z_h_ev, n + 2)
+    r = _lin_polys([(s_, src[name][i]) for s_, (name, i) in terms])
+    open_zeta = w_polys + list(P["s_polys"][:N_WIRES - 1]) + [P["q_prk_polys"][2], P["q_prk_polys"][3]]
+    if shuffle:
+        open_zeta += [P["q_ecc_poly"]] + w_sel_polys
+    open_zeta.append(r)
+    proof["opening_witness_zeta"] = batch_prove(tr, pcs, open_zeta, zeta, n + 2)
+    proof["opening_witness_zeta_omega"] = batch_prove(tr, pcs, [z, w_polys[0], w_polys[1], w_polys[2]], zeta_omega, n + 2)
+    proof["_u"] = u
+    return proof
+
+
+def proof_to_bytes_be(proof) -> bytes:
+    """PlonkProof::to_bytes_be (indexer.rs:538-590), either feature set."""
+    pt = lambda P_: bytes(64) if P_ is None else P_[0].to_bytes(32, "big") + P_[1].to_bytes(32, "big")
+    sc = lambda v: v.to_bytes(32, "big")
+    out = b"".join(pt(c) for c in proof["cm_w_vec"])
+    out += b"".join(pt(c) for c in proof.get("cm_w_sel_vec", []))
+    out += b"".join(pt(c) for c in proof["cm_t_vec"]) + pt(proof["cm_z"])
+    out += sc(proof["prk_3_poly_eval_zeta"]) + sc(proof["prk_4_poly_eval_zeta"])
+    out += b"".join(sc(v) for v in proof["w_polys_eval_zeta"] + proof["w_polys_eval_zeta_omega"]) + sc(proof["z_eval_zeta_omega"])
+    out += b"".join(sc(v) for v in proof["s_polys_eval_zeta"])
+    if "q_ecc_poly_eval_zeta" in proof:
+        out += sc(proof["q_ecc_poly_eval_zeta"]) + b"".join(sc(v) for v in proof["w_sel_polys_eval_zeta"])
+    return out + pt(proof["opening_witness_zeta"]) + pt(proof["opening_witness_zeta_omega"])
 
 
 # ---------------------------------------------------------------- verifier (plonk/verifier.rs:17-164) under a known trapdoor

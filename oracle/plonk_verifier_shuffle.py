@@ -120,46 +120,53 @@ def r_eval_zeta(p, alpha, beta, gamma, pi_ev, l1_ev, g, g_inv):
     return (term1 + term2 - pi_ev + term3 + term4 + term5 + term6 - term7 - term8 - term9 - term10) % FR
 
 
-def r_commitment(vp, p, alpha, beta, gamma, zeta, l1_ev, z_h_ev, n_t_polys):
-    """r_poly_or_comm over commitments (helpers.rs:681-999), as (scalar, point) terms summed in G1."""
+def r_terms(k, ed_a, p, alpha, beta, gamma, zeta, l1_ev, z_h_ev, n_t_polys):
+    """r_poly_or_comm (helpers.rs:681-999, `shuffle` feature) as (scalar, (family, index)) terms over the families
+    q[0..9), z, s_last, qb, prk[0..2), pk[0..12), gen[0..12), t[0..5): the verifier sums commitments, the prover polynomials."""
     a = [pow(alpha, i, FR) for i in range(14)]
     w, wo, s, ws = p["w_polys_eval_zeta"], p["w_polys_eval_zeta_omega"], p["s_polys_eval_zeta"], p["w_sel_polys_eval_zeta"]
-    prk3, q_ecc, k, ed_a = p["prk_3_poly_eval_zeta"], p["q_ecc_poly_eval_zeta"], vp["k"], vp["edwards_a"]
+    prk3, q_ecc = p["prk_3_poly_eval_zeta"], p["q_ecc_poly_eval_zeta"]
     sel_mult = [w[0], w[1], w[2], w[3], w[0] * w[1], w[2] * w[3], 1, w[0] * w[1] * w[2] * w[3] * w[4], -w[4]]
-    terms = [(sel_mult[i], vp["cm_q_vec"][i]) for i in range(9)]
+    terms = [(sel_mult[i], ("q", i)) for i in range(9)]
     z_scalar = alpha
     for i in range(N_WIRES):
         z_scalar = z_scalar * (w[i] + k[i] * beta % FR * zeta + gamma) % FR
     z_scalar += l1_ev * a[2]
-    terms.append((z_scalar, p["cm_z"]))
+    terms.append((z_scalar, ("z", 0)))
     s_last = alpha * p["z_eval_zeta_omega"] % FR * beta % FR
     for i in range(N_WIRES - 1):
         s_last = s_last * (w[i] + beta * s[i] + gamma) % FR
-    terms.append((-s_last, vp["cm_s_vec"][4]))
-    terms.append((w[1] * (w[1] - 1) * a[3] + w[2] * (w[2] - 1) * a[4] + w[3] * (w[3] - 1) * a[5], vp["cm_qb"]))
-    terms.append((prk3 * a[6], vp["cm_prk_vec"][0]))
-    terms.append((prk3 * a[7], vp["cm_prk_vec"][1]))
+    terms.append((-s_last, ("s_last", 0)))
+    terms.append((w[1] * (w[1] - 1) * a[3] + w[2] * (w[2] - 1) * a[4] + w[3] * (w[3] - 1) * a[5], ("qb", 0)))
+    terms.append((prk3 * a[6], ("prk", 0)))
+    terms.append((prk3 * a[7], ("prk", 1)))
     sel = [((1 - ws[0]) * (1 - ws[1]) + q_ecc - 1) % FR, ws[0] * (1 - ws[1]) % FR, (1 - ws[0]) * ws[1] % FR, ws[0] * ws[1] % FR]
-    pk, gen = vp["cm_shuffle_public_key_vec"], vp["cm_shuffle_generator_vec"]   # x: 0..3, y: 4..7, dxy: 8..11
-    for c in range(4):
+    for c in range(4):                                          # x: 0..3, y: 4..7, dxy: 8..11
         # 6. alpha^10: dxy * w0 w1 w0' - y * wsel2 w0 - x * w1                (public key)
-        terms += [(a[10] * sel[c] % FR * (w[0] * w[1] % FR * wo[0]) % FR, pk[8 + c]),
-                  (-a[10] * sel[c] % FR * (ws[2] * w[0]) % FR, pk[4 + c]), (-a[10] * sel[c] % FR * w[1] % FR, pk[c])]
+        terms += [(a[10] * sel[c] % FR * (w[0] * w[1] % FR * wo[0]) % FR, ("pk", 8 + c)),
+                  (-a[10] * sel[c] % FR * (ws[2] * w[0]) % FR, ("pk", 4 + c)), (-a[10] * sel[c] % FR * w[1] % FR, ("pk", c))]
         # 7. alpha^11: -dxy * w0 w1 w1' + x * a w0 - y * wsel2 w1
-        terms += [(-a[11] * sel[c] % FR * (w[0] * w[1] % FR * wo[1]) % FR, pk[8 + c]),
-                  (a[11] * sel[c] % FR * (w[0] * ed_a) % FR, pk[c]), (-a[11] * sel[c] % FR * (ws[2] * w[1]) % FR, pk[4 + c])]
+        terms += [(-a[11] * sel[c] % FR * (w[0] * w[1] % FR * wo[1]) % FR, ("pk", 8 + c)),
+                  (a[11] * sel[c] % FR * (w[0] * ed_a) % FR, ("pk", c)), (-a[11] * sel[c] % FR * (ws[2] * w[1]) % FR, ("pk", 4 + c))]
         # 8. alpha^12: dxy * w2 w3 w2' - y * wsel2 w2 - x * w3                (generator)
-        terms += [(a[12] * sel[c] % FR * (w[2] * w[3] % FR * wo[2]) % FR, gen[8 + c]),
-                  (-a[12] * sel[c] % FR * (ws[2] * w[2]) % FR, gen[4 + c]), (-a[12] * sel[c] % FR * w[3] % FR, gen[c])]
+        terms += [(a[12] * sel[c] % FR * (w[2] * w[3] % FR * wo[2]) % FR, ("gen", 8 + c)),
+                  (-a[12] * sel[c] % FR * (ws[2] * w[2]) % FR, ("gen", 4 + c)), (-a[12] * sel[c] % FR * w[3] % FR, ("gen", c))]
         # 9. alpha^13: -dxy * w2 w3 w4 + x * a w2 - y * wsel2 w3
-        terms += [(-a[13] * sel[c] % FR * (w[2] * w[3] % FR * w[4]) % FR, gen[8 + c]),
-                  (a[13] * sel[c] % FR * (w[2] * ed_a) % FR, gen[c]), (-a[13] * sel[c] % FR * (ws[2] * w[3]) % FR, gen[4 + c])]
+        terms += [(-a[13] * sel[c] % FR * (w[2] * w[3] % FR * w[4]) % FR, ("gen", 8 + c)),
+                  (a[13] * sel[c] % FR * (w[2] * ed_a) % FR, ("gen", c)), (-a[13] * sel[c] % FR * (ws[2] * w[3]) % FR, ("gen", 4 + c))]
     f = pow(zeta, n_t_polys, FR)
     e = z_h_ev
-    for t in p["cm_t_vec"]:
-        terms.append((-e, t))
+    for i in range(N_WIRES):
+        terms.append((-e, ("t", i)))
         e = e * f % FR
-    return _g1_lin([(sc % FR, P) for sc, P in terms])
+    return [(sc % FR, ref) for sc, ref in terms]
+
+
+def r_commitment(vp, p, alpha, beta, gamma, zeta, l1_ev, z_h_ev, n_t_polys):
+    fam = {"q": vp["cm_q_vec"], "z": [p["cm_z"]], "s_last": [vp["cm_s_vec"][4]], "qb": [vp["cm_qb"]], "prk": vp["cm_prk_vec"],
+           "pk": vp["cm_shuffle_public_key_vec"], "gen": vp["cm_shuffle_generator_vec"], "t": p["cm_t_vec"]}
+    return _g1_lin([(sc, fam[name][i]) for sc, (name, i) in r_terms(vp["k"], vp["edwards_a"], p, alpha, beta, gamma, zeta, l1_ev, z_h_ev,
+                                                                      n_t_polys)])
 
 
 def _batch(tr, cms, max_degree, point, evals):
@@ -180,9 +187,15 @@ def verify_shuffle_proof(fixture: dict, pi_points, pi_lagrange, tamper=None) -> 
     if tamper:
         tamper(p, pi)
     vp = parse_vk(fixture["vk_words"], fixture["public_key_commitments"], pi_points, pi_lagrange)
-    n, root = vp["cs_size"], vp["root"]
     tr = Transcript(b"Plonk shuffle Proof")
     tr.u64(fixture["n_cards"])
+    return verifier(tr, vp, pi, p, g2=(_g2(fixture["g2_tau_h_eip197"]), _g2(fixture["g2_h_eip197"])))
+
+
+def verifier(tr, vp, pi, p, g2=None, trapdoor=None) -> bool:
+    """plonk/verifier.rs:17-164 with the `shuffle` feature.  The final check is the pairing (g2 = (tau H, H)) or, for a synthetic SRS
+    with a known trapdoor, its G1 equivalent  sum u^i W_i * tau == right-hand side."""
+    n, root = vp["cs_size"], vp["root"]
     transcript_init_plonk(tr, vp, pi, root)
     for c in p["cm_w_vec"] + p["cm_w_sel_vec"]:
         tr.point(c)
@@ -221,4 +234,6 @@ def verify_shuffle_proof(fixture: dict, pi_points, pi_lagrange, tamper=None) -> 
     W, Wo = p["opening_witness_zeta"], p["opening_witness_zeta_omega"]
     left = _g1_lin([(1, W), (u, Wo)])
     right = _g1_lin([(zeta, W), (u * zeta_omega, Wo), (-(val + u * val_o), (1, 2)), (1, comm), (u, comm_o)])
-    return pairing.multi_pairing_is_one([(left, _g2(fixture["g2_tau_h_eip197"])), (bn.g1_neg(right), _g2(fixture["g2_h_eip197"]))])
+    if trapdoor is not None:
+        return _g1_lin([(trapdoor, left)]) == right
+    return pairing.multi_pairing_is_one([(left, g2[0]), (bn.g1_neg(right), g2[1])])

@@ -194,3 +194,81 @@ def test_lagrange_srs_from_monomial_without_trapdoor(gpu, oc, bn, n):
         for i in range(n):
             want = bn.msm_naive(P, [n_inv * pow(w_inv, i * j, bn.FR) % bn.FR for j in range(n)])
             assert bn.array_to_affine(got[i].reshape(1, 8))[0] == want, i
+
+
+@pytest.mark.parametrize("n_gates,n_public", [(2, 1), (60, 2)])
+def test_shuffle_feature_prover_matches_restatement_and_golden_pinned_verifier(gpu, bn, n_gates, n_public):
+    """The `shuffle` feature set (what zshuffle is compiled with): witness-selector polynomials, quotient terms 12-18, q_ecc / w_sel
+    openings, linearisation parts 6-9.  The GPU proof must equal the restatement's byte for byte (PlonkProof::to_bytes_be) and be
+    accepted by oracle/plonk_verifier_shuffle.py -- the verifier restatement that accepts the reference's own golden proofs
+    (tests/test_oracle_golden_proof.py) -- under the synthetic SRS's trapdoor."""
+    from oracle import plonk_prover as pp
+    from oracle import plonk_verifier_shuffle as vs
+    from uzkge_b200 import KZGCommitmentSchemeBN254, plonk
+    from uzkge_b200.rng import ChaChaRng
+    from uzkge_b200.transcript import Transcript
+
+    cs = build_circuit(plonk.TurboCS(), n_gates, 21, n_public, 1)
+    ocs = build_circuit(pp.TurboCS(), n_gates, 21, n_public, 1)
+    pcs, opcs = KZGCommitmentSchemeBN254.new(cs.size + 2, plonk.mont(TAU)), pp.Kzg(cs.size + 2, TAU)
+    params, oparams = plonk.indexer(cs, pcs, shuffle=True), pp.indexer(ocs, opcs, shuffle=True)
+    proof = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"Plonk shuffle Proof"), pcs, cs, params, cs.get_witness_array())
+    want = pp.prover(pp.ChaCha(bytes(32)), pp.Transcript(b"Plonk shuffle Proof"), opcs, ocs, oparams, ocs.witness)
+    raw = proof.to_bytes_be()
+    assert len(raw) == 1632 and raw == pp.proof_to_bytes_be(want)
+    pi = [ocs.witness[i] for i in ocs.public_vars_witness_indices]
+    assert vs.verifier(pp.Transcript(b"Plonk shuffle Proof"), oparams["vp"], pi, vs.parse_proof(raw), trapdoor=TAU)
+    bad = bytearray(raw)
+    bad[900] ^= 1                          # inside prk_3 / a wire evaluation
+    try:
+        rejected = not vs.verifier(pp.Transcript(b"Plonk shuffle Proof"), oparams["vp"], pi, vs.parse_proof(bytes(bad)), trapdoor=TAU)
+    except AssertionError:                 # not a field element any more
+        rejected = True
+    assert rejected
+    pcs.close()
+
+
+def test_shuffle_quotient_terms_match_restatement(gpu, oc, bn):
+    """uzkge_cuda_plonk_quotient_shuffle_fr_device on random coset evaluations (every selector non-zero) against t_poly's loop body with
+    terms 1-18 in big integers (oracle/plonk.py)."""
+    import torch
+
+    from oracle import plonk
+
+    n, factor = 32, 6
+    m = n * factor
+    K5 = [1, 0x2F8DD1F1A7583C42C4E12A44E110404C73CA6C94813F85835DA4FB7BB1301D4A, 3, 5, 7]
+    rnd = lambda seed: oc.random_fr(m, seed)
+    groups = {"w": 5, "q": 9, "s": 5, "q_prk": 4, "w_sel": 3, "pk": 12, "gen": 12}
+    arrays, seed = {}, 500
+    for name, cnt in groups.items():
+        arrays[name] = [rnd(seed + i) for i in range(cnt)]
+        seed += cnt
+    for name in ("pi", "z", "coset_quotient", "l1", "qb", "q_ecc"):
+        arrays[name] = rnd(seed)
+        seed += 1
+    sc = oc.random_fr(6, 77)
+    alpha, beta, gamma, g, ed_a = sc[0], sc[1], sc[2], sc[3], sc[4]
+    g_inv = oc.fr_inv(g)
+    zh = oc.random_fr(factor, 78)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64).reshape(-1)).cuda()
+    keep = {nm: ([dev(a) for a in v] if isinstance(v, list) else dev(v)) for nm, v in arrays.items()}
+    out = torch.empty(4 * m, dtype=torch.int64, device="cuda")
+    P_ = lambda t: t.data_ptr()
+    gpu.plonk_quotient_fr_device(
+        [P_(t) for t in keep["w"]], [P_(t) for t in keep["q"]], P_(keep["pi"]), P_(keep["z"]), [P_(t) for t in keep["s"]],
+        P_(keep["coset_quotient"]), P_(keep["l1"]), P_(keep["qb"]), [P_(t) for t in keep["q_prk"]], bn.ints_to_array(K5, bn.FR),
+        alpha, beta, gamma, g, g_inv, zh, m, factor, out.data_ptr(),
+        shuffle={"w_sel": [P_(t) for t in keep["w_sel"]], "q_ecc": P_(keep["q_ecc"]), "pk": [P_(t) for t in keep["pk"]],
+                 "gen": [P_(t) for t in keep["gen"]], "edwards_a": ed_a})
+    torch.cuda.synchronize()
+    got = bn.array_to_ints(out.cpu().numpy().view(np.uint64).reshape(m, 4), bn.FR)
+    I = lambda a: bn.array_to_ints(a, bn.FR)
+    S = lambda a: I(a.reshape(1, 4))[0]
+    want = plonk.quotient_coset_evals(
+        [I(a) for a in arrays["w"]], [I(a) for a in arrays["q"]], I(arrays["pi"]), I(arrays["z"]), [I(a) for a in arrays["s"]],
+        I(arrays["coset_quotient"]), I(arrays["l1"]), I(arrays["qb"]), [I(a) for a in arrays["q_prk"]], K5, S(alpha), S(beta), S(gamma),
+        S(g), S(g_inv), I(zh), factor,
+        shuffle={"w_sel": [I(a) for a in arrays["w_sel"]], "q_ecc": I(arrays["q_ecc"]), "pk": [I(a) for a in arrays["pk"]],
+                 "gen": [I(a) for a in arrays["gen"]], "edwards_a": S(ed_a)})
+    assert got == want

@@ -73,3 +73,31 @@ def test_modified_golden_proofs_are_rejected(domain_kat):
         assert not vs.verify_shuffle_proof(fx, pts, lag, tamper=tamper)
     wrong_cards = dict(fx, n_cards=21)       # the transcript prefix binds the number of cards (build_cs.rs:108-109)
     assert not vs.verify_shuffle_proof(wrong_cards, pts, lag)
+
+
+@pytest.mark.parametrize("n_gates", [3, 25])
+def test_restated_shuffle_prover_is_accepted_by_the_golden_pinned_verifier(n_gates):
+    """The prover restatement for the `shuffle` feature set (witness selectors, quotient terms 12-18, linearisation parts 6-9) emits
+    1632-byte proofs that the verifier above -- the one that accepts the reference's golden proofs -- accepts under the synthetic SRS's
+    trapdoor, and rejects after a change.  The GPU prover is compared byte for byte with this restatement (tests/test_gpu_plonk.py)."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from plonk_circuits import FR, build_circuit
+
+    from oracle import plonk_prover as pp
+    from oracle import plonk_verifier_shuffle as vs
+
+    tau = 0x1234567890ABCDEF1234567890ABCDEF
+    cs = build_circuit(pp.TurboCS(), n_gates, 7, n_public=2)
+    pcs = pp.Kzg(cs.size + 2, tau)
+    params = pp.indexer(cs, pcs, shuffle=True)
+    proof = pp.prover(pp.ChaCha(bytes(32)), pp.Transcript(b"Plonk shuffle Proof"), pcs, cs, params, cs.witness)
+    raw = pp.proof_to_bytes_be(proof)
+    assert len(raw) == 1632
+    pi = [cs.witness[i] for i in cs.public_vars_witness_indices]
+    parsed = vs.parse_proof(raw)
+    assert vs.verifier(pp.Transcript(b"Plonk shuffle Proof"), params["vp"], pi, parsed, trapdoor=tau)
+    bad = dict(parsed, w_sel_polys_eval_zeta=[(parsed["w_sel_polys_eval_zeta"][0] + 1) % FR] + parsed["w_sel_polys_eval_zeta"][1:])
+    assert not vs.verifier(pp.Transcript(b"Plonk shuffle Proof"), params["vp"], pi, bad, trapdoor=tau)
+    assert not vs.verifier(pp.Transcript(b"Plonk shuffle Proof"), params["vp"], [(pi[0] + 1) % FR] + pi[1:], parsed, trapdoor=tau)

@@ -494,10 +494,20 @@ UZKGE_API int32_t uzkge_cuda_grand_product_fr(const uint64_t* num, const uint64_
 
 UZKGE_API int32_t uzkge_cuda_plonk_quotient_fr_device(const uzkge_quotient_args* args, void* d_out, void* stream) {
     API_ENTER(-1);
-    int rc = plonk_quotient_run(args, d_out, (cudaStream_t)stream);
+    int rc = plonk_quotient_run(args, nullptr, d_out, (cudaStream_t)stream);
     if (rc == UZKGE_ERR_ARG) return fail(rc, "plonk_quotient_fr_device: null pointer");
     if (rc == UZKGE_ERR_SIZE) return fail(rc, "plonk_quotient_fr_device: m must be a multiple of factor, 1 <= factor <= 16");
     return engine_fail(rc, "plonk_quotient_fr_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_plonk_quotient_shuffle_fr_device(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* shuffle,
+                                                              void* d_out, void* stream) {
+    if (!shuffle) return fail(UZKGE_ERR_ARG, "plonk_quotient_shuffle_fr_device: null pointer");
+    API_ENTER(-1);
+    int rc = plonk_quotient_run(args, shuffle, d_out, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "plonk_quotient_shuffle_fr_device: null pointer");
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "plonk_quotient_shuffle_fr_device: m must be a multiple of factor, 1 <= factor <= 16");
+    return engine_fail(rc, "plonk_quotient_shuffle_fr_device");
 }
 
 UZKGE_API int32_t uzkge_cuda_fr_lincomb_device(const void* const* d_polys, const size_t* lens, const uint64_t* coefs_host, size_t k,

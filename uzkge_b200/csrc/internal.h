@@ -244,7 +244,7 @@ private:
 };
 
 // ---------------------------------------------------------------- PlonK quotient map (quotient.cu)
-int plonk_quotient_run(const uzkge_quotient_args* args, void* d_out, cudaStream_t st);
+int plonk_quotient_run(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* shuffle, void* d_out, cudaStream_t st);
 
 // ---------------------------------------------------------------- elementwise prover glue (plonk_glue.cu)
 int fr_lincomb_run(const void* const* d_polys, const size_t* lens, const uint64_t* coefs, size_t k, void* d_out, size_t out_len, cudaStream_t st);

@@ -58,6 +58,17 @@ class QuotientArgs(C.Structure):
     ]
 
 
+class QuotientShuffleArgs(C.Structure):
+    """uzkge_quotient_shuffle_args (include/uzkge_cuda.h)."""
+    _fields_ = [
+        ("w_sel", C.c_void_p * 3),
+        ("q_ecc", C.c_void_p),
+        ("pk", C.c_void_p * 12),
+        ("gen", C.c_void_p * 12),
+        ("edwards_a", C.c_uint64 * 4),
+    ]
+
+
 _SIGNATURES = {
     "uzkge_cuda_init": (C.c_int32, [C.c_int32]),
     "uzkge_cuda_device_count": (C.c_int32, []),
@@ -104,6 +115,7 @@ _SIGNATURES = {
     ),
     "uzkge_cuda_grand_product_fr": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_plonk_quotient_fr_device": (C.c_int32, [C.POINTER(QuotientArgs), C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_plonk_quotient_shuffle_fr_device": (C.c_int32, [C.POINTER(QuotientArgs), C.POINTER(QuotientShuffleArgs), C.c_void_p, C.c_void_p]),
     "uzkge_cuda_fr_lincomb_device": (
         C.c_int32,
         [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p],
@@ -432,8 +444,10 @@ def grand_product_fr(num, den) -> np.ndarray:
 
 
 def plonk_quotient_fr_device(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, alpha, beta, gamma, anemoi_g, anemoi_g_inv,
-                             z_h_inv, m: int, factor: int, d_out: int, stream: int = 0) -> None:
-    """Device pointers (ints) for the arrays, numpy Montgomery limbs for the scalars; see uzkge_quotient_args."""
+                             z_h_inv, m: int, factor: int, d_out: int, stream: int = 0, shuffle=None) -> None:
+    """Device pointers (ints) for the arrays, numpy Montgomery limbs for the scalars; see uzkge_quotient_args.
+    shuffle: None, or a dict {w_sel: 3 pointers, q_ecc: pointer, pk: 12 pointers, gen: 12 pointers, edwards_a: limbs} for the
+    `shuffle` feature set (uzkge_cuda_plonk_quotient_shuffle_fr_device)."""
     a = QuotientArgs()
     for j in range(5):
         a.w[j], a.s[j] = w[j], s[j]
@@ -450,7 +464,17 @@ def plonk_quotient_fr_device(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, a
     for i in range(zh.shape[0]):
         a.z_h_inv[i][:] = [int(x) for x in zh[i]]
     a.m, a.factor = m, factor
-    check(lib().uzkge_cuda_plonk_quotient_fr_device(C.byref(a), d_out, stream))
+    if shuffle is None:
+        check(lib().uzkge_cuda_plonk_quotient_fr_device(C.byref(a), d_out, stream))
+        return
+    b = QuotientShuffleArgs()
+    for j in range(3):
+        b.w_sel[j] = shuffle["w_sel"][j]
+    b.q_ecc = shuffle["q_ecc"]
+    for j in range(12):
+        b.pk[j], b.gen[j] = shuffle["pk"][j], shuffle["gen"][j]
+    b.edwards_a[:] = [int(x) for x in as_u64(shuffle["edwards_a"]).reshape(4)]
+    check(lib().uzkge_cuda_plonk_quotient_shuffle_fr_device(C.byref(a), C.byref(b), d_out, stream))
 
 
 LINCOMB_MAX = 24

@@ -343,6 +343,11 @@ class PlonkVerifierParams:
     cs_size: int
     public_vars_constraint_indices: list
     lagrange_constants: list
+    # `shuffle` feature set (plonk/indexer.rs:163-176)
+    cm_q_ecc: KZGCommitment | None = None
+    cm_shuffle_generator_vec: list | None = None
+    cm_shuffle_public_key_vec: list | None = None
+    edwards_a: int = 0
 
 
 @dataclass
@@ -369,6 +374,13 @@ class PlonkProverParams:
     root: int = 0
     root_m: int = 0
     workspace: dict = field(default_factory=dict)
+    # `shuffle` feature set (plonk/indexer.rs:100-139): None when the parameters were built for the default features
+    q_ecc_poly: DevVec | None = None
+    q_ecc_coset_eval: DevVec | None = None
+    q_shuffle_generator_polys: list | None = None
+    q_shuffle_generator_coset_evals: list | None = None
+    q_shuffle_public_key_polys: list | None = None
+    q_shuffle_public_key_coset_evals: list | None = None
 
     def get_verifier_params_ref(self) -> PlonkVerifierParams:
         return self.verifier_params
@@ -388,6 +400,22 @@ class PlonkProof:
     s_polys_eval_zeta: list
     opening_witness_zeta: KZGCommitment
     opening_witness_zeta_omega: KZGCommitment
+    # `shuffle` feature set
+    cm_w_sel_vec: list | None = None
+    q_ecc_poly_eval_zeta: int | None = None
+    w_sel_polys_eval_zeta: list | None = None
+
+    def to_bytes_be(self) -> bytes:
+        """PlonkProof::to_bytes_be (plonk/indexer.rs:538-590): what the Solidity verifier of the reference consumes."""
+        sc = lambda v: int(v).to_bytes(32, "big")
+        pts = lambda cms: b"".join(c.to_transcript_bytes() for c in cms)
+        out = pts(self.cm_w_vec) + pts(self.cm_w_sel_vec or []) + pts(self.cm_t_vec) + pts([self.cm_z])
+        out += sc(self.prk_3_poly_eval_zeta) + sc(self.prk_4_poly_eval_zeta)
+        out += b"".join(sc(v) for v in self.w_polys_eval_zeta + self.w_polys_eval_zeta_omega) + sc(self.z_eval_zeta_omega)
+        out += b"".join(sc(v) for v in self.s_polys_eval_zeta)
+        if self.cm_w_sel_vec is not None:
+            out += sc(self.q_ecc_poly_eval_zeta) + b"".join(sc(v) for v in self.w_sel_polys_eval_zeta)
+        return out + pts([self.opening_witness_zeta, self.opening_witness_zeta_omega])
 
 
 # ---------------------------------------------------------------------------------------------- device helpers
@@ -508,8 +536,12 @@ def _add_coefs(poly: DevVec, idx, vals) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- indexer
-def indexer(cs: TurboCS, pcs) -> PlonkProverParams:
-    """plonk/indexer.rs:240-536 with lagrange_pcs = None, permutation = None, verifier_params = None."""
+def indexer(cs: TurboCS, pcs, shuffle: bool = False) -> PlonkProverParams:
+    """plonk/indexer.rs:240-536 with lagrange_pcs = None, permutation = None, verifier_params = None.  shuffle = True builds the
+    parameters of the `shuffle` feature set (what zshuffle is compiled with): q_ecc and the 12 + 12 shuffle selector polynomials
+    (indexer.rs:447-501) -- all zero here, because the supported gate set has no remark gates; the prover then also commits the
+    witness-selector polynomials, evaluates terms 12-18 of the quotient and opens q_ecc / w_sel, i.e. produces the proof format of
+    the reference's deployed verifier."""
     if cs.selectors is None:
         raise UzkgeError("call cs.pad() before indexing")
     n, m = cs.size, cs.quot_eval_dom_size()
@@ -589,11 +621,18 @@ def indexer(cs: TurboCS, pcs) -> PlonkProverParams:
         public_vars_constraint_indices=list(cs.public_vars_constraint_indices), lagrange_constants=lagrange_constants)
     d_wiring = torch.from_numpy(cs.wiring.reshape(-1).view(np.int32)).to(dev)
     torch.cuda.synchronize()
-    return PlonkProverParams(
+    extra = {}
+    if shuffle:
+        vp.cm_q_ecc, vp.cm_shuffle_generator_vec, vp.cm_shuffle_public_key_vec = identity, [identity] * 12, [identity] * 12
+        vp.edwards_a = 0
+        extra = dict(q_ecc_poly=zero_poly, q_ecc_coset_eval=zero_coset, q_shuffle_generator_polys=[zero_poly] * 12,
+                     q_shuffle_generator_coset_evals=[zero_coset] * 12, q_shuffle_public_key_polys=[zero_poly] * 12,
+                     q_shuffle_public_key_coset_evals=[zero_coset] * 12)
+    return PlonkProverParams(**extra, **dict(
         q_polys=q_polys, s_polys=s_polys, qb_poly=qb_poly, q_prk_polys=q_prk_polys, verifier_params=vp, group=group,
         coset_quotient=coset_quotient, l1_coset_evals=l1_coset, z_h_inv_coset_evals=mont_rows(z_h_inv), q_coset_evals=q_coset,
         s_coset_evals=s_coset, qb_coset_eval=qb_coset, q_prk_coset_evals=q_prk_coset, sigma_evals=sigma, wiring=d_wiring,
-        n=n, m=m, factor=factor, root=root, root_m=root_m, workspace={"scratch": scratch})
+        n=n, m=m, factor=factor, root=root, root_m=root_m, workspace={"scratch": scratch}))
 
 
 def _commit_many(pcs, vecs) -> list:
@@ -727,6 +766,18 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         cm_w_vec = _commit_dev(pcs, w_polys, overlap=wire_cosets)
     for cm in cm_w_vec:
         transcript.append_commitment(cm)
+    # 3. (`shuffle` feature set) witness-selector polynomials (prover.rs:148-165): zero on H here (compute_witness_selectors
+    # without remark gates, turbo/mod.rs:148-163), hidden with 2 blinds each, committed
+    shuffle = P.q_ecc_poly is not None
+    w_sel_polys, cm_w_sel_vec = [], None
+    if shuffle:
+        for _ in range(3):
+            f = DevVec(cap, dev, length=1)
+            hide_polynomial(prng, f, 2, n)
+            w_sel_polys.append(f)
+        cm_w_sel_vec = _commit_dev(pcs, w_sel_polys)
+        for cm in cm_w_sel_vec:
+            transcript.append_commitment(cm)
     mark("round1_wires")
 
     # 4. beta, gamma
@@ -766,11 +817,21 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         _coset_fft(pi, m, k1, pi_coset, scratch)
     else:
         pi_coset.t.zero_()
+    shuffle_args = None
+    if shuffle:
+        w_sel_coset = ws.get("w_sel_coset")
+        if w_sel_coset is None:
+            w_sel_coset = ws["w_sel_coset"] = [DevVec(m, dev, zero=False) for _ in range(3)]
+        for p, c in zip(w_sel_polys, w_sel_coset):
+            _coset_fft(p, m, k1, c, scratch)
+        shuffle_args = {"w_sel": [c.ptr for c in w_sel_coset], "q_ecc": P.q_ecc_coset_eval.ptr,
+                        "pk": [c.ptr for c in P.q_shuffle_public_key_coset_evals], "gen": [c.ptr for c in P.q_shuffle_generator_coset_evals],
+                        "edwards_a": mont(vp.edwards_a)}
     ffi.plonk_quotient_fr_device(
         [c.ptr for c in w_coset], [c.ptr for c in P.q_coset_evals], pi_coset.ptr, z_coset.ptr, [c.ptr for c in P.s_coset_evals],
         P.coset_quotient.ptr, P.l1_coset_evals.ptr, P.qb_coset_eval.ptr, [c.ptr for c in P.q_prk_coset_evals], mont_rows(k),
         mont(alpha), mont(beta), mont(gamma), mont(vp.anemoi_generator), mont(vp.anemoi_generator_inv), P.z_h_inv_coset_evals,
-        m, P.factor, t_buf.ptr)
+        m, P.factor, t_buf.ptr, shuffle=shuffle_args)
     ffi.ntt_fr_device(t_buf.ptr, t_buf.ptr, scratch.ptr, m, m, True, k1_inv)
     coefs_len = ffi.fr_trimmed_len_device(t_buf.ptr, m)
     mark("round3_quotient")
@@ -805,15 +866,20 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     s_open = P.s_polys[: N_WIRES_PER_GATE - 1]
     pts = ([(p, zeta) for p in w_polys] + [(p, zeta) for p in s_open] + [(P.q_prk_polys[2], zeta), (P.q_prk_polys[3], zeta)]
            + [(z_poly, zeta_omega)] + [(p, zeta_omega) for p in w_polys[:3]])
+    if shuffle:
+        pts += [(P.q_ecc_poly, zeta)] + [(p, zeta) for p in w_sel_polys]
     ev = _evals(pts, dev)
     w_polys_eval_zeta, s_polys_eval_zeta = ev[0:5], ev[5:9]
     prk_3_poly_eval_zeta, prk_4_poly_eval_zeta, z_eval_zeta_omega = ev[9], ev[10], ev[11]
     w_polys_eval_zeta_omega = ev[12:15]
-    for v in w_polys_eval_zeta + s_polys_eval_zeta:
+    q_ecc_poly_eval_zeta, w_sel_polys_eval_zeta = (ev[15], ev[16:19]) if shuffle else (None, None)
+    for v in w_polys_eval_zeta + s_polys_eval_zeta + (w_sel_polys_eval_zeta or []):
         transcript.append_challenge(v)
     transcript.append_challenge(prk_3_poly_eval_zeta)
     transcript.append_challenge(prk_4_poly_eval_zeta)
     transcript.append_challenge(z_eval_zeta_omega)
+    if shuffle:
+        transcript.append_challenge(q_ecc_poly_eval_zeta)
     for v in w_polys_eval_zeta_omega:
         transcript.append_challenge(v)
     # 10. u
@@ -838,19 +904,53 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     terms.append((we[1] * (we[1] - 1) * a[3] + we[2] * (we[2] - 1) * a[4] + we[3] * (we[3] - 1) * a[5], P.qb_poly))
     terms.append((prk_3_poly_eval_zeta * a[6], P.q_prk_polys[0]))
     terms.append((prk_3_poly_eval_zeta * a[7], P.q_prk_polys[1]))
+    if shuffle:
+        # 6.-9. the remark-gate parts (helpers.rs:747-983): per selector combination c, over the public-key / generator selector
+        # polynomials x_c, y_c, dxy_c
+        ws, wo, ed_a = w_sel_polys_eval_zeta, w_polys_eval_zeta_omega, vp.edwards_a
+        ah = [pow(alpha, i, FR_MODULUS) for i in range(14)]
+        sel = [((1 - ws[0]) * (1 - ws[1]) + q_ecc_poly_eval_zeta - 1) % FR_MODULUS, ws[0] * (1 - ws[1]) % FR_MODULUS,
+               (1 - ws[0]) * ws[1] % FR_MODULUS, ws[0] * ws[1] % FR_MODULUS]
+        pk, gen = P.q_shuffle_public_key_polys, P.q_shuffle_generator_polys
+        for c in range(4):
+            terms += [(ah[10] * sel[c] * we[0] * we[1] * wo[0], pk[8 + c]), (-ah[10] * sel[c] * ws[2] * we[0], pk[4 + c]),
+                      (-ah[10] * sel[c] * we[1], pk[c]),
+                      (-ah[11] * sel[c] * we[0] * we[1] * wo[1], pk[8 + c]), (ah[11] * sel[c] * we[0] * ed_a, pk[c]),
+                      (-ah[11] * sel[c] * ws[2] * we[1], pk[4 + c]),
+                      (ah[12] * sel[c] * we[2] * we[3] * wo[2], gen[8 + c]), (-ah[12] * sel[c] * ws[2] * we[2], gen[4 + c]),
+                      (-ah[12] * sel[c] * we[3], gen[c]),
+                      (-ah[13] * sel[c] * we[2] * we[3] * we[4], gen[8 + c]), (ah[13] * sel[c] * we[2] * ed_a, gen[c]),
+                      (-ah[13] * sel[c] * ws[2] * we[3], gen[4 + c])]
     zfactor = pow(zeta, piece, FR_MODULUS)
     exponent = z_h_eval_zeta
     for tp in t_polys:
         terms.append((-exponent, tp))
         exponent = exponent * zfactor % FR_MODULUS
+    merged: dict = {}            # the same polynomial may appear in several terms (the shared zero selector, the 3 uses of x_c ...)
+    for sc_, p_ in terms:
+        key = p_.ptr
+        merged[key] = ((merged[key][0] + sc_) % FR_MODULUS, p_) if key in merged else (sc_ % FR_MODULUS, p_)
+    terms = list(merged.values())
     rlen = max(p.len for _, p in terms)
     r_poly = DevVec(max(cap, rlen), dev, zero=False, length=rlen)
-    ffi.fr_lincomb_device([p.ptr for _, p in terms], [p.len for _, p in terms], mont_rows([s for s, _ in terms]), r_poly.ptr, rlen)
+    first = True
+    for i in range(0, len(terms), ffi.LINCOMB_MAX - 1):
+        chunk = terms[i:i + ffi.LINCOMB_MAX - 1]
+        ptrs, lens, scs = [p.ptr for _, p in chunk], [p.len for _, p in chunk], [s_ for s_, _ in chunk]
+        if not first:            # accumulate onto the partial sum
+            ptrs, lens, scs = ptrs + [r_poly.ptr], lens + [rlen], scs + [1]
+        ffi.fr_lincomb_device(ptrs, lens, mont_rows(scs), r_poly.ptr, rlen)
+        first = False
     r_eval_zeta = _evals([(r_poly, zeta)], dev)[0]
     mark("round4_evals_r")
 
-    polys_to_open = w_polys + s_open + [P.q_prk_polys[2], P.q_prk_polys[3], r_poly]
-    evals_to_open = w_polys_eval_zeta + s_polys_eval_zeta + [prk_3_poly_eval_zeta, prk_4_poly_eval_zeta, r_eval_zeta]
+    polys_to_open = w_polys + s_open + [P.q_prk_polys[2], P.q_prk_polys[3]]
+    evals_to_open = w_polys_eval_zeta + s_polys_eval_zeta + [prk_3_poly_eval_zeta, prk_4_poly_eval_zeta]
+    if shuffle:
+        polys_to_open += [P.q_ecc_poly] + w_sel_polys
+        evals_to_open += [q_ecc_poly_eval_zeta] + w_sel_polys_eval_zeta
+    polys_to_open.append(r_poly)
+    evals_to_open.append(r_eval_zeta)
     # the first opening proof does not enter the transcript before the second is built (prover.rs:359-381), so the two
     # quotients are committed in one batch
     hmax = max(p.len for p in polys_to_open + [z_poly])
@@ -869,4 +969,5 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         cm_w_vec=cm_w_vec, cm_t_vec=cm_t_vec, cm_z=cm_z, prk_3_poly_eval_zeta=prk_3_poly_eval_zeta,
         prk_4_poly_eval_zeta=prk_4_poly_eval_zeta, w_polys_eval_zeta=w_polys_eval_zeta, w_polys_eval_zeta_omega=w_polys_eval_zeta_omega,
         z_eval_zeta_omega=z_eval_zeta_omega, s_polys_eval_zeta=s_polys_eval_zeta, opening_witness_zeta=opening_witness_zeta,
-        opening_witness_zeta_omega=opening_witness_zeta_omega)
+        opening_witness_zeta_omega=opening_witness_zeta_omega, cm_w_sel_vec=cm_w_sel_vec, q_ecc_poly_eval_zeta=q_ecc_poly_eval_zeta,
+        w_sel_polys_eval_zeta=w_sel_polys_eval_zeta)
