@@ -182,10 +182,12 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
     tau = plonk.mont(0x1234567890ABCDEF1234567890ABCDEF)
     out = {"metric": "turboplonk_synthetic_proofs_per_s", "unit": "proofs/s", "sizes": []}
     logs = [int(x) for x in args.plonk_logs.split(",") if x]
-    runs = [(lg, "uniform") for lg in logs]
-    if world == 1 and logs and logs[-1] >= 20:
-        runs.append((logs[-1], "bits"))    # the same circuit shape over a witness of bits / small integers
-    for lg, witness in runs:
+    runs = [(lg, "uniform", False) for lg in logs]
+    if world == 1 and logs:
+        if logs[-1] >= 20:
+            runs.append((logs[-1], "bits", False))    # the same circuit shape over a witness of bits / small integers
+        runs.append((logs[0], "uniform", True))       # the `shuffle` feature set: the 1632-byte proof format of zshuffle's verifier
+    for lg, witness, shuffle_features in runs:
         n = 1 << lg
         split = world > 1 and lg > 18
         steps = K if lg <= 18 else max(2, min(K, 5))
@@ -205,7 +207,7 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
             pcs = KZGCommitmentSchemeBN254.new(n + 2, tau)
             lagrange = KZGCommitmentSchemeBN254.new_lagrange(n, tau)   # prover_with_lagrange: what zshuffle / zmatchmaking call
         cs = plonk.TurboCS.synthetic(lg, seed=0xB2000004 + (0 if split else rank), witness=witness)
-        params = plonk.indexer(cs, pcs)
+        params = plonk.indexer(cs, pcs, shuffle=shuffle_features)
         torch.cuda.synchronize()
         setup_s = time.perf_counter() - t0
         wit_pinned = ffi.PinnedArray(cs.get_witness_array().shape)     # the caller's witness, page-locked (uzkge_cuda_host_alloc)
@@ -245,6 +247,7 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
         out["sizes"].append({
             "log_n": lg, "n_gpus": world, "mode": "msm_split" if split else ("replicas" if world > 1 else "single"),
             "witness": witness, "lagrange_commitments": lagrange is not None,
+            "feature_set": "shuffle" if shuffle_features else "default", "proof_bytes": len(proof.to_bytes_be()),
             "prove_ms": dt * 1e3, "proofs_per_s": proofs_in_flight / dt, "e2e_prove_ms": dt_e2e * 1e3,
             "e2e_proofs_per_s": proofs_in_flight / dt_e2e,
             "h2d_bytes_per_step": int(wit_host.nbytes), "d2h_bytes_per_step": 13 * 96 + 16 * 32, "steps": steps,
