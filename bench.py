@@ -182,14 +182,16 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
     tau = plonk.mont(0x1234567890ABCDEF1234567890ABCDEF)
     out = {"metric": "turboplonk_synthetic_proofs_per_s", "unit": "proofs/s", "sizes": []}
     logs = [int(x) for x in args.plonk_logs.split(",") if x]
-    runs = [(lg, "uniform", False) for lg in logs]
-    if world == 1 and logs:
+    # (log size, witness, shuffle feature set, one proof split over the GPUs)
+    runs = [(lg, "uniform", False, world > 1 and lg > 18) for lg in logs]
+    if logs and world == 1:
         if logs[-1] >= 20:
-            runs.append((logs[-1], "bits", False))    # the same circuit shape over a witness of bits / small integers
-        runs.append((logs[0], "uniform", True))       # the `shuffle` feature set: the 1632-byte proof format of zshuffle's verifier
-    for lg, witness, shuffle_features in runs:
+            runs.append((logs[-1], "bits", False, False))    # the same circuit shape over a witness of bits / small integers
+        runs.append((logs[0], "uniform", True, False))       # the `shuffle` feature set: the 1632-byte proof format of zshuffle's verifier
+    if logs and world > 1 and logs[-1] > 18:
+        runs.append((logs[-1], "uniform", False, False))     # throughput: N independent provers of the large circuit (25 GiB each)
+    for lg, witness, shuffle_features, split in runs:
         n = 1 << lg
-        split = world > 1 and lg > 18
         steps = K if lg <= 18 else max(2, min(K, 5))
         t0 = time.perf_counter()
         lagrange = None
