@@ -272,3 +272,22 @@ def test_shuffle_quotient_terms_match_restatement(gpu, oc, bn):
         shuffle={"w_sel": [I(a) for a in arrays["w_sel"]], "q_ecc": I(arrays["q_ecc"]), "pk": [I(a) for a in arrays["pk"]],
                  "gen": [I(a) for a in arrays["gen"]], "edwards_a": S(ed_a)})
     assert got == want
+
+
+@pytest.mark.parametrize("n_gates,n_public", [(25, 2), (300, 0)])
+def test_quotient_round_by_cosets_gives_the_same_proof(gpu, bn, n_gates, n_public):
+    """The quotient round evaluated coset by coset (six size-n coset transforms per polynomial on the folded coefficients, the
+    pointwise map per coset with factor 1, interleave, one 6n inverse transform) -- the decomposition dist.SplitCommitter deals to the
+    GPUs of a box -- must give the proof of the natural 6n path."""
+    from uzkge_b200 import KZGCommitmentSchemeBN254, plonk
+    from uzkge_b200.rng import ChaChaRng
+    from uzkge_b200.transcript import Transcript
+
+    cs = build_circuit(plonk.TurboCS(), n_gates, 9, n_public, 1)
+    pcs = KZGCommitmentSchemeBN254.new(cs.size + 2, plonk.mont(TAU))
+    params = plonk.indexer(cs, pcs)
+    wit = cs.get_witness_array()
+    a = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"test"), pcs, cs, params, wit)
+    b = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"test"), pcs, cs, params, wit, quotient_by_cosets=True)
+    assert a.to_bytes_be() == b.to_bytes_be()
+    pcs.close()

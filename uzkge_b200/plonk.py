@@ -639,6 +639,83 @@ def _commit_many(pcs, vecs) -> list:
     return _commit_dev(pcs, vecs)
 
 
+# ---------------------------------------------------------------------------------------------- the quotient round, coset by coset
+# The 6 n points k[1] w_m^p of the quotient domain are the 6 cosets g_j <w_n>, g_j = k[1] w_m^j (p = 6 i + j).  On one coset a
+# polynomial of n + 3 coefficients is a size-n coset transform of its folded coefficients (X^n = g_j^n there), the w-shifted point
+# of p is the next point of the same coset, and Z_H is the constant g_j^n - 1: the quotient map of a coset needs nothing from the
+# other cosets, so the round splits over GPUs by coset (dist.SplitCommitter.quotient_*).
+class CosetParams:
+    """Everything the quotient map needs on coset j, built from the COEFFICIENT forms of the preprocessed polynomials."""
+
+    def __init__(self, q_polys, s_polys, qb_poly, q_prk_polys, k, n: int, j: int, dev):
+        m = 6 * n
+        root_m, root_n = _root(m), _root(n)
+        self.n, self.j = n, j
+        self.g = k[1] * pow(root_m, j, FR_MODULUS) % FR_MODULUS
+        self.g_n = pow(self.g, n, FR_MODULUS)
+        self.z_h_inv = pow((self.g_n - 1) % FR_MODULUS, -1, FR_MODULUS)
+        self.scratch = DevVec(n, dev, zero=False)
+        g_m = mont(self.g)
+
+        def ev(poly):
+            out = DevVec(n, dev, zero=False)
+            ffi.ntt_fr_device(poly.ptr, out.ptr, self.scratch.ptr, min(poly.len, n), n, False, g_m)
+            return out
+
+        cache = {}
+
+        def ev_shared(poly):            # the zero selectors share one buffer in the parameters: keep sharing their evaluations
+            if poly.ptr not in cache:
+                cache[poly.ptr] = ev(poly)
+            return cache[poly.ptr]
+
+        self.q = [ev_shared(p) for p in q_polys]
+        self.s = [ev_shared(p) for p in s_polys]
+        self.qb = ev_shared(qb_poly)
+        self.q_prk = [ev_shared(p) for p in q_prk_polys]
+        ones = DevVec(n, dev, zero=False)                       # l1_coefs = 1 + X + ... + X^(n-1)  (indexer.rs:343-346)
+        ffi.fr_powers_device(mont(1), n, ones.ptr)
+        self.l1 = ev(ones)
+        self.coset_quotient = DevVec(n, dev, zero=False)        # g_j w_n^i
+        ffi.fr_powers_device(mont(root_n), n, self.coset_quotient.ptr, scale=g_m)
+        self.evals = [DevVec(n, dev, zero=(i == 6)) for i in range(7)]   # w0..w4, z, pi on this coset (pi stays zero if never given)
+        self.head = DevVec(4, dev, zero=False)
+
+    def eval_folded(self, poly_t, length: int, out: DevVec) -> None:
+        """out = the polynomial (`length` <= n + 3 coefficients in `poly_t`) on this coset: fold X^(n + l) = g^n X^l into the head
+        coefficients (restored afterwards), then one size-n coset transform."""
+        n = self.n
+        extra = max(0, length - n)
+        ptr = poly_t.data_ptr()
+        if extra:
+            self.head.t[: 4 * extra].copy_(poly_t[: 4 * extra])
+            ffi.fr_lincomb_device([ptr, ptr + 32 * n], [extra, extra], mont_rows([1, self.g_n]), ptr, extra)
+        ffi.ntt_fr_device(ptr, out.ptr, self.scratch.ptr, min(length, n), n, False, mont(self.g))
+        if extra:
+            poly_t[: 4 * extra].copy_(self.head.t[: 4 * extra])
+
+    def quotient(self, polys, k, alpha: int, beta: int, gamma: int, out: DevVec) -> None:
+        """polys: [(tensor, length)] for w0..w4, z and pi (pi may be None = zero).  out: t on this coset (n values)."""
+        for (t_, ln), e in zip(polys[:6], self.evals[:6]):
+            self.eval_folded(t_, ln, e)
+        if polys[6] is not None:
+            self.eval_folded(polys[6][0], polys[6][1], self.evals[6])
+        ffi.plonk_quotient_fr_device(
+            [e.ptr for e in self.evals[:5]], [c.ptr for c in self.q], self.evals[6].ptr, self.evals[5].ptr, [c.ptr for c in self.s],
+            self.coset_quotient.ptr, self.l1.ptr, self.qb.ptr, [c.ptr for c in self.q_prk], mont_rows(k), mont(alpha), mont(beta),
+            mont(gamma), mont(0), mont(0), mont_rows([self.z_h_inv]), self.n, 1, out.ptr)
+
+
+def interleave_cosets(t_cosets: DevVec, n: int, out: DevVec, idx_cache: dict) -> None:
+    """out[6 i + j] = t_cosets[j * n + i]: the natural order the 6n coset iFFT expects."""
+    dev = out.t.device
+    if idx_cache.get("n") != n:
+        p = torch.arange(6 * n, device=dev, dtype=torch.int64)
+        idx_cache["idx"] = ((p % 6) * n + p // 6).to(torch.int32)
+        idx_cache["n"] = n
+    ffi.fr_gather_device(t_cosets.ptr, idx_cache["idx"].data_ptr(), 6 * n, out.ptr)
+
+
 # ---------------------------------------------------------------------------------------------- prover
 def hide_polynomial(prng, polynomial: DevVec, hiding_degree: int, zeroing_degree: int) -> list[int]:
     """helpers.rs:139-154: add (b_0 + b_1 X + ...) (X^zeroing_degree - 1)."""
@@ -687,12 +764,14 @@ def batch_prove(pcs, transcript: Transcript, polys, evals, point: int, max_degre
 
 
 def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkProverParams, w,
-           timings: dict | None = None, lagrange_pcs=None) -> PlonkProof:
+           timings: dict | None = None, lagrange_pcs=None, quotient_by_cosets: bool = False) -> PlonkProof:
     """plonk/prover.rs:76-394 (`prover` = `prover_with_lagrange` with lagrange_pcs = None).  `w`: the witness, (num_vars, 4)
     Montgomery limbs (numpy) or a DevVec already in HBM.  With a `lagrange_pcs` whose size matches the circuit
     (prover.rs:119-124) the wire and z commitments are MSMs of the EVALUATION vectors against the Lagrange SRS with the blind
     terms as six extra bases (prover.rs:131-146, `_lagrange_commit_scheme`); the quotient pieces and opening proofs are committed in coefficient form -- the same group
-    elements as the reference's Lagrange branch (helpers.rs:1363-1391, pcs.rs:139-163), without its extra transforms."""
+    elements as the reference's Lagrange branch (helpers.rs:1363-1391, pcs.rs:139-163), without its extra transforms.
+    quotient_by_cosets: evaluate the quotient round coset by coset (CosetParams) on this GPU -- the single-GPU form of what
+    dist.SplitCommitter distributes; the proof is the same."""
     if cs.is_verifier_only():
         raise UzkgeError("FuncParamsError")
     P = prover_params
@@ -753,7 +832,7 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     # so the GPU computes them while the host waits for the commitments and hashes the transcript
 
     def wire_cosets():
-        if not multi_gpu:
+        if not multi_gpu and not quotient_by_cosets:
             for p, c in zip(w_polys, w_coset):
                 _coset_fft(p, m, k1, c, scratch)
 
@@ -795,7 +874,7 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     _ifft(z_ev.ptr, n, z_poly, scratch)
     z_blinds = hide_polynomial(prng, z_poly, 3, n)
     def z_coset_eval():
-        if not multi_gpu:
+        if not multi_gpu and not quotient_by_cosets:
             _coset_fft(z_poly, m, k1, z_coset, scratch)
 
     if lagrange_pcs is not None:
@@ -808,12 +887,30 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
 
     # 6. alpha;  7. t = numerator / Z_H on the coset k[1] <w_m>, split, commit (helpers.rs:223-678, 1323-1408)
     alpha = transcript.get_challenge_field_elem()
-    if multi_gpu:
+    by_cosets = (quotient_by_cosets or hasattr(pcs, "quotient_by_cosets")) and P.factor == 6 and P.q_ecc_poly is None
+    if by_cosets:
+        for p in w_polys + [z_poly]:
+            p.t[4 * p.len: 4 * (n + 3)].zero_()
+        polys = [(p.t, n + 3) for p in w_polys + [z_poly]] + [(pi.t, n) if online_values else None]
+        t_cosets = ws.get("t_cosets") or DevVec(m, dev, zero=False)
+        ws["t_cosets"] = t_cosets
+        if hasattr(pcs, "quotient_by_cosets"):
+            pcs.quotient_by_cosets(P, polys, k, alpha, beta, gamma, t_cosets)        # the cosets are dealt to the GPUs of the box
+        else:
+            cps = ws.get("coset_params")
+            if cps is None:
+                cps = ws["coset_params"] = [CosetParams(P.q_polys, P.s_polys, P.qb_poly, P.q_prk_polys, k, n, j, dev) for j in range(6)]
+            for j, cp in enumerate(cps):
+                cp.quotient(polys, k, alpha, beta, gamma, _View(t_cosets, j * n, n))
+        interleave_cosets(t_cosets, n, t_buf, ws.setdefault("interleave", {}))
+    elif multi_gpu:
         # several GPUs: the six independent 6n transforms of this round go one per rank (dist.SplitCommitter)
         for p in w_polys + [z_poly]:
             p.t[4 * p.len: 4 * (n + 3)].zero_()
         pcs.transform_many([(p.t, c.t) for p, c in zip(w_polys + [z_poly], w_coset + [z_coset])], n + 3, m, False, k1)
-    if online_values:
+    if by_cosets:
+        pass
+    elif online_values:
         _coset_fft(pi, m, k1, pi_coset, scratch)
     else:
         pi_coset.t.zero_()
@@ -827,11 +924,12 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         shuffle_args = {"w_sel": [c.ptr for c in w_sel_coset], "q_ecc": P.q_ecc_coset_eval.ptr,
                         "pk": [c.ptr for c in P.q_shuffle_public_key_coset_evals], "gen": [c.ptr for c in P.q_shuffle_generator_coset_evals],
                         "edwards_a": mont(vp.edwards_a)}
-    ffi.plonk_quotient_fr_device(
-        [c.ptr for c in w_coset], [c.ptr for c in P.q_coset_evals], pi_coset.ptr, z_coset.ptr, [c.ptr for c in P.s_coset_evals],
-        P.coset_quotient.ptr, P.l1_coset_evals.ptr, P.qb_coset_eval.ptr, [c.ptr for c in P.q_prk_coset_evals], mont_rows(k),
-        mont(alpha), mont(beta), mont(gamma), mont(vp.anemoi_generator), mont(vp.anemoi_generator_inv), P.z_h_inv_coset_evals,
-        m, P.factor, t_buf.ptr, shuffle=shuffle_args)
+    if not by_cosets:
+        ffi.plonk_quotient_fr_device(
+            [c.ptr for c in w_coset], [c.ptr for c in P.q_coset_evals], pi_coset.ptr, z_coset.ptr, [c.ptr for c in P.s_coset_evals],
+            P.coset_quotient.ptr, P.l1_coset_evals.ptr, P.qb_coset_eval.ptr, [c.ptr for c in P.q_prk_coset_evals], mont_rows(k),
+            mont(alpha), mont(beta), mont(gamma), mont(vp.anemoi_generator), mont(vp.anemoi_generator_inv), P.z_h_inv_coset_evals,
+            m, P.factor, t_buf.ptr, shuffle=shuffle_args)
     ffi.ntt_fr_device(t_buf.ptr, t_buf.ptr, scratch.ptr, m, m, True, k1_inv)
     coefs_len = ffi.fr_trimmed_len_device(t_buf.ptr, m)
     mark("round3_quotient")
