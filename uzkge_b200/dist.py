@@ -242,6 +242,13 @@ class PeerNtt:
 
 
 # ------------------------------------------------------------------------------------------------ point-split commitments for the prover
+class _Slice:
+    """Window into a DevVec-like object (`.t`, element offset): what CosetParams.quotient writes a coset's values to."""
+
+    def __init__(self, base, first: int):
+        self.t, self.ptr = base.t, base.t.data_ptr() + 32 * first
+
+
 class SplitCommitter:
     """KZG commitments of DEVICE-RESIDENT coefficient vectors with the SRS points split over the ranks (SURVEY 8e, row "MSM"),
     driven by rank 0 -- the rank that runs the prover (uzkge_b200/plonk.py) and owns the polynomials.
@@ -255,7 +262,7 @@ class SplitCommitter:
     checker to exercise the protocol without a GPU.
     """
 
-    OP_EXIT, OP_COMMIT, OP_TRANSFORM = 0, 1, 2
+    OP_EXIT, OP_COMMIT, OP_TRANSFORM, OP_QSETUP, OP_QUOTIENT = 0, 1, 2, 3, 4
 
     def __init__(self, affine_xy: np.ndarray, rank: int, world: int, device=None, group=None, window_bits: int = 0,
                  upload: Callable = None, msm_fn: Callable = None, add_fn: Callable = None, ntt_fn: Callable = None):
@@ -391,6 +398,91 @@ class SplitCommitter:
         dist.broadcast(self._hdr, src=0, group=self.group)
         self._transform_step(len(jobs), len_in, domain_size, inverse, shift, jobs)
 
+    # ---- the quotient round, one coset (or a few) of the 6n domain per rank (plonk.CosetParams)
+    def _my_cosets(self):
+        return [j for j in range(6) if j % self.world == self.rank]
+
+    def _quotient_setup_step(self, n: int, k_t, poly_ts) -> None:
+        """Collective.  k_t: 20 int64 (k[0..5) limbs), poly_ts: the 19 coefficient vectors q[9], s[5], qb, q_prk[4] (n elements each;
+        filled on rank 0, receive buffers elsewhere)."""
+        import torch
+        import torch.distributed as dist
+
+        from . import plonk
+
+        dist.broadcast(k_t, src=0, group=self.group)
+        for t in poly_ts:
+            dist.broadcast(t, src=0, group=self.group)
+        k = [plonk.unmont(row) for row in k_t.cpu().numpy().view(np.uint64).reshape(5, 4)]
+
+        class _Vec:                               # (pointer, length) view of a received tensor
+            def __init__(self, t):
+                self.t, self.ptr, self.len = t, t.data_ptr(), n
+
+        vecs = [_Vec(t) for t in poly_ts]
+        self._q = {"n": n, "k": k, "params": {j: plonk.CosetParams(vecs[0:9], vecs[9:14], vecs[14], vecs[15:19], k, n, j, self.device)
+                                              for j in self._my_cosets()},
+                   "polys": [torch.zeros(4 * (n + 4), dtype=torch.int64, device=self.device) for _ in range(7)],
+                   "scal": torch.zeros(12, dtype=torch.int64, device=self.device),
+                   "out": plonk.DevVec(n, self.device, zero=False)}
+
+    def _quotient_step(self, n: int, has_pi: bool, t_cosets=None) -> None:
+        """Collective.  The polynomials (w0..w4, z of n + 3 coefficients, pi of n) and alpha, beta, gamma are already in
+        self._q["polys"] / ["scal"] on rank 0."""
+        import torch.distributed as dist
+
+        from . import plonk
+
+        q = self._q
+        dist.broadcast(q["scal"], src=0, group=self.group)
+        for i in range(7 if has_pi else 6):
+            dist.broadcast(q["polys"][i], src=0, group=self.group)
+        alpha, beta, gamma = (plonk.unmont(row) for row in q["scal"].cpu().numpy().view(np.uint64).reshape(3, 4))
+        polys = [(q["polys"][i], n + 3) for i in range(6)] + [(q["polys"][6], n) if has_pi else None]
+        if self.rank == 0:
+            for j in self._my_cosets():
+                q["params"][j].quotient(polys, q["k"], alpha, beta, gamma, _Slice(t_cosets, j * n))
+            for j in range(6):
+                if j % self.world:
+                    dist.recv(t_cosets.t[4 * j * n: 4 * (j + 1) * n], j % self.world, group=self.group)
+        else:
+            for j in self._my_cosets():
+                q["params"][j].quotient(polys, q["k"], alpha, beta, gamma, q["out"])
+                dist.send(q["out"].t[: 4 * n], 0, group=self.group)
+
+    def quotient_by_cosets(self, P, polys, k, alpha: int, beta: int, gamma: int, t_cosets) -> None:
+        """Rank 0 (called by plonk.prover): t on the six cosets of the quotient domain into t_cosets[j * n + i], the cosets dealt to
+        the ranks.  The preprocessed polynomials travel once (first call), the round's seven polynomials every proof."""
+        import torch
+        import torch.distributed as dist
+
+        from . import plonk
+
+        assert self.rank == 0
+        n = P.n
+        if getattr(self, "_q", None) is None or self._q["n"] != n or self._q.get("owner") is not P:
+            self._hdr.zero_()
+            self._hdr[0], self._hdr[1] = self.OP_QSETUP, n
+            dist.broadcast(self._hdr, src=0, group=self.group)
+            k_t = torch.from_numpy(plonk.mont_rows(k).view(np.int64).reshape(-1).copy()).to(self.device)
+            poly_ts = []
+            for v in list(P.q_polys) + list(P.s_polys) + [P.qb_poly] + list(P.q_prk_polys):
+                t = torch.zeros(4 * n, dtype=torch.int64, device=self.device)
+                t[: 4 * min(v.len, n)].copy_(v.t[: 4 * min(v.len, n)])
+                poly_ts.append(t)
+            self._quotient_setup_step(n, k_t, poly_ts)
+            self._q["owner"] = P
+        q = self._q
+        q["scal"].copy_(torch.from_numpy(plonk.mont_rows([alpha, beta, gamma]).view(np.int64).reshape(-1).copy()))
+        has_pi = polys[6] is not None
+        for i, pl in enumerate(polys):
+            if pl is not None:
+                q["polys"][i][: 4 * pl[1]].copy_(pl[0][: 4 * pl[1]])
+        self._hdr.zero_()
+        self._hdr[0], self._hdr[1], self._hdr[2] = self.OP_QUOTIENT, n, 1 if has_pi else 0
+        dist.broadcast(self._hdr, src=0, group=self.group)
+        self._quotient_step(n, has_pi, t_cosets)
+
     def serve(self) -> int:
         """Ranks > 0: answer rank 0's commitments and transforms until it shuts the service down.  Returns the number served."""
         import torch.distributed as dist
@@ -402,6 +494,17 @@ class SplitCommitter:
             op = h[0]
             if op == self.OP_EXIT:
                 return self.commits
+            if op == self.OP_QSETUP:
+                import torch
+
+                n = h[1]
+                k_t = torch.zeros(20, dtype=torch.int64, device=self.device)
+                poly_ts = [torch.zeros(4 * n, dtype=torch.int64, device=self.device) for _ in range(19)]
+                self._quotient_setup_step(n, k_t, poly_ts)
+                continue
+            if op == self.OP_QUOTIENT:
+                self._quotient_step(h[1], bool(h[2]))
+                continue
             if op == self.OP_TRANSFORM:
                 count, len_in, dom = h[1], h[2] & ((1 << 62) - 1), h[3] & ((1 << 62) - 1)
                 inverse, has_shift = bool(h[2] >> 62), bool(h[3] >> 62)
