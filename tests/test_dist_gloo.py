@@ -233,3 +233,22 @@ def test_split_committer_distributes_transforms_world2():
         p.join(60)
         assert p.exitcode == 0
     assert all(r[1] for r in res), res
+
+
+def test_host_jacobian_add_matches_oracle(oc):
+    """dist._jac_add_host (the world - 1 combinations of a split commitment, on the host): addition, doubling, identity operands,
+    P + (-P), against the oracle's group law."""
+    from uzkge_b200.dist import _jac_add_host
+
+    FQ = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    pts = oc.g1_random_points(4, 3)
+    a = oc.g1_mul(pts[0], oc.random_fr(1, 1)[0])
+    b = oc.g1_mul(pts[1], oc.random_fr(1, 2)[0])
+    ident = np.zeros(12, dtype=np.uint64)
+    for x, y in ((a, b), (a, a), (a, ident), (ident, b), (ident, ident)):
+        assert np.array_equal(oc.g1_to_affine(_jac_add_host(x, y)), oc.g1_to_affine(oc.g1_add_jac(x, y)))
+    neg = a.copy()
+    yv = sum(int(a[4 + j]) << (64 * j) for j in range(4))
+    for j in range(4):
+        neg[4 + j] = (((FQ - yv) % FQ) >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    assert not oc.g1_to_affine(_jac_add_host(a, neg)).any()

@@ -242,6 +242,51 @@ class PeerNtt:
 
 
 # ------------------------------------------------------------------------------------------------ point-split commitments for the prover
+_FQ = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+_FQ_R = (1 << 256) % _FQ
+_FQ_R_INV = pow(_FQ_R, -1, _FQ)
+
+
+def _jac_add_host(a, b) -> np.ndarray:
+    """a + b on Jacobian points given as 12 Montgomery limbs each: the world - 1 combinations of a split commitment, O(1) group
+    operations on the host (a device round trip per addition costs ten times the arithmetic).  add-2007-bl / dbl-2009-l, a = 0."""
+    def load(v):
+        v = np.asarray(v, dtype=np.uint64).reshape(12)
+        return [(int(v[4 * i]) | int(v[4 * i + 1]) << 64 | int(v[4 * i + 2]) << 128 | int(v[4 * i + 3]) << 192) * _FQ_R_INV % _FQ for i in range(3)]
+
+    def store(x, y, z):
+        out = np.zeros(12, dtype=np.uint64)
+        for i, c in enumerate((x, y, z)):
+            m = c % _FQ * _FQ_R % _FQ
+            for j in range(4):
+                out[4 * i + j] = (m >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+        return out
+
+    x1, y1, z1 = load(a)
+    x2, y2, z2 = load(b)
+    if z1 == 0:
+        return store(x2, y2, z2) if z2 else store(1, 1, 0)
+    if z2 == 0:
+        return store(x1, y1, z1)
+    z1z1, z2z2 = z1 * z1 % _FQ, z2 * z2 % _FQ
+    u1, u2 = x1 * z2z2 % _FQ, x2 * z1z1 % _FQ
+    s1, s2 = y1 * z2 * z2z2 % _FQ, y2 * z1 * z1z1 % _FQ
+    if u1 == u2:
+        if s1 != s2:
+            return store(1, 1, 0)
+        a_, b_ = x1 * x1 % _FQ, y1 * y1 % _FQ
+        c_ = b_ * b_ % _FQ
+        d_ = 2 * ((x1 + b_) * (x1 + b_) - a_ - c_) % _FQ
+        e_ = 3 * a_ % _FQ
+        x3 = (e_ * e_ - 2 * d_) % _FQ
+        return store(x3, e_ * (d_ - x3) - 8 * c_, 2 * y1 * z1)
+    h, r = (u2 - u1) % _FQ, (s2 - s1) % _FQ
+    hh = h * h % _FQ
+    hhh, v = h * hh % _FQ, u1 * hh % _FQ
+    x3 = (r * r - hhh - 2 * v) % _FQ
+    return store(x3, r * (v - x3) - s1 * hhh, z1 * z2 * h)
+
+
 class _Slice:
     """Window into a DevVec-like object (`.t`, element offset): what CosetParams.quotient writes a coset's values to."""
 
@@ -278,7 +323,7 @@ class SplitCommitter:
         upload = upload or (lambda p: ffi.srs_upload(p, window_bits))
         self.handle = upload(pts[self.lo: self.hi]) if self.hi > self.lo else None
         self._msm = msm_fn or self._msm_cuda
-        self._add = add_fn or ffi.g1_add
+        self._add = add_fn or _jac_add_host
         self._recv = torch.zeros(4 * self.chunk, dtype=torch.int64, device=self.device)
         self._pad = torch.zeros(4 * self.chunk * world, dtype=torch.int64, device=self.device) if rank == 0 else None
         self._hdr = torch.zeros(8, dtype=torch.int64, device=self.device)   # op, a, b, c, 4 limbs of a coset shift
