@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- BN254 G1 MSM 2^20 points/s (headline, BASELINE.json configs[1]) and Fr NTT 2^22 elements/s
-(configs[2]) on N B200s, one process per GPU, next to the CPU restatement of the reference's arkworks path.
+"""bench.py -- BN254 G1 MSM 2^20 points/s (headline, BASELINE.json configs[1]), Fr NTT 2^22 elements/s (configs[2]) and
+TurboPlonK proofs/s on synthetic circuits (configs[4]) on N B200s, one process per GPU, next to the CPU restatement of the
+reference's arkworks path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload both|msm|ntt]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|both|msm|ntt|plonk]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 A step = one pass of the hot path over one batch of synthetic input:
-  msm : one variable-base MSM over 2^20 resident KZG bases (powers-of-tau SRS) with fresh uniform Fr scalars.
+  msm : one variable-base MSM over 2^20 resident KZG bases (powers-of-tau SRS) with fresh uniform Fr scalars.  The K timed
+        steps travel in ONE batch call, which the engine software-pipelines (`detail.single_call_ms`: one MSM per call).
         N > 1: the job is ONE MSM over N * 2^20 points; rank r owns slice r (bases resident on its GPU) and the
         N partial sums (96 B each) are all-gathered and added -- weak scaling, no other collective.
-  ntt : one forward 2^22 Fr NTT, natural order in and out (replicas only at N > 1: it fits one GPU).
-`value` is device-resident throughput (CUDA events on the launching stream, max over ranks); `e2e` goes through the
-host-pointer C ABI call a Rust caller makes (pinned host buffers, H2D + D2H inside the timed region).
-Inputs rotate over more distinct buffers than fit in the 126 MB L2 (`config.l2`).
+  ntt : one forward 2^22 Fr NTT, natural order in and out (block "ntt"; replicas at N > 1: it fits one GPU), and at N > 1 ONE
+        2^24 four-step transform over the N GPUs (block "ntt_distributed": exchanges fused into the kernel over peer memory,
+        next to the NCCL all-to-all version).
+  plonk : one complete proof of a synthetic TurboPlonK circuit (block "plonk": 2^14 and 2^22 gates, default and shuffle feature
+        sets, uniform and bits witnesses; N > 1: replicas for throughput, one proof split over the GPUs for latency).
+The JSON line's top level is the MSM (`value` device-resident with CUDA events on the launching stream, max over ranks; `e2e`
+through the host-pointer C ABI a Rust caller uses: pinned host buffers, H2D + D2H inside the timed region; `roofline`,
+`int_roofline`, `cpu_baseline`, `clocks`, `gpu_launches`).  Inputs rotate over more distinct buffers than fit in the 126 MB L2
+(`config.l2`).
 """
 from __future__ import annotations
 
