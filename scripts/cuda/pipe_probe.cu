@@ -1,0 +1,73 @@
+// pipe_probe.cu -- how much multiplier throughput does a B200 SM have besides the IMAD ("fmaheavy") pipe that the 256-bit
+// Montgomery product lives on?  Three kernels over the whole GPU, timed with CUDA events:
+//   imad : dependent IMAD.WIDE chains (what ff.cuh issues: 32 x 32 -> 64 bit, 4 cycles per warp instruction and sub-partition)
+//   dfma : dependent DFMA chains (the FP64 pipe: a 52-bit-limb Montgomery product would run there)
+//   both : the two interleaved in one warp (do the pipes overlap?)
+// Build + run (development aid, not part of the library):  nvcc -gencode arch=compute_100a,code=sm_100a -O3 pipe_probe.cu -o pipe_probe
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int MODE>
+__global__ void __launch_bounds__(256) probe(unsigned long long* sink, double* dsink, int iters) {
+    unsigned long long a[8];
+    double d[8];
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = t * 8 + i + 1;
+        d[i] = 1.0 + 1e-9 * (t + i);
+    }
+    const unsigned m = 0x9E3779B1u + t;
+    const double dm = 1.0000001;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (MODE != 1) a[i] = (unsigned long long)(unsigned)a[i] * m + a[i];   // IMAD.WIDE
+            if (MODE != 0) d[i] = fma(d[i], dm, 1e-12);                             // DFMA
+        }
+    }
+    unsigned long long s = 0;
+    double ds = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        s += a[i];
+        ds += d[i];
+    }
+    if (s == 0x1234567ull) sink[t] = s;
+    if (ds == 1.2345) dsink[t] = ds;
+}
+
+template <int MODE>
+static double run(int iters) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned long long* sink;
+    double* dsink;
+    const int blocks = sms * 8, threads = 256;
+    cudaMalloc(&sink, sizeof(unsigned long long) * blocks * threads);
+    cudaMalloc(&dsink, sizeof(double) * blocks * threads);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    probe<MODE><<<blocks, threads>>>(sink, dsink, iters);
+    cudaEventRecord(e0);
+    probe<MODE><<<blocks, threads>>>(sink, dsink, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaFree(sink);
+    cudaFree(dsink);
+    return (double)blocks * threads * 8.0 * iters / (ms * 1e-3);   // operations of EACH kind per second
+}
+
+int main() {
+    const int iters = 20000;
+    const double imad = run<0>(iters), dfma = run<1>(iters), both = run<2>(iters);
+    printf("IMAD.WIDE alone : %8.2f T/s\n", imad / 1e12);
+    printf("DFMA alone      : %8.2f T/s\n", dfma / 1e12);
+    printf("interleaved     : %8.2f T/s of each (IMAD.WIDE + DFMA issued by the same warps)\n", both / 1e12);
+    return 0;
+}
