@@ -99,6 +99,12 @@ UZKGE_API int32_t uzkge_cuda_msm_g1_small_device(uint64_t handle, const size_t* 
  *                                     trailing-zero trim stays in Rust (`from_coefs`)
  *   inverse = 1, coset_shift = k^-1 : coset_ifft_with_domain               (:601-607)  ifft, then c_j * (k^-1)^j */
 UZKGE_API int32_t uzkge_cuda_ntt_fr(uint64_t* inout, size_t len_in, size_t domain_size, int32_t inverse, const uint64_t* coset_shift);
+/* k transforms over the same domain in one call (the 5 wire iFFTs of a prover round, the 7 coset FFTs of t_poly, the ~33 of the
+ * indexer: plonk/prover.rs:155-170, helpers.rs:256-266, indexer.rs:296-470), software-pipelined over three device buffers and three
+ * streams: the H2D copy of vector j + 1 and the D2H copy of vector j - 1 run under transform j.  inouts[j] holds domain_size elements,
+ * the first len_in[j] are the input. */
+UZKGE_API int32_t uzkge_cuda_ntt_fr_batch(uint64_t* const* inouts, const size_t* len_in, size_t k, size_t domain_size, int32_t inverse,
+                                          const uint64_t* coset_shift);
 /* generator of the size-n domain (Montgomery), for the Rust side's consistency assert against
  * `domain.group_gen`; UZKGE_ERR_SIZE if n is not 3^a 2^b with a <= 2, b <= 28. */
 UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]);

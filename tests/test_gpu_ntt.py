@@ -135,3 +135,23 @@ def test_full_size_properties(gpu, oc, bn, n):
     cev = gpu.ntt_fr(x[: n // 2], n, coset_shift=k)
     back = gpu.ntt_fr(cev, n, inverse=True, coset_shift=kinv)
     assert np.array_equal(back[: n // 2], x[: n // 2]) and not back[n // 2 :].any()
+
+
+@pytest.mark.parametrize("n", [64, 1 << 14, 3 << 12])
+def test_batch_host_transforms_match_single_calls(gpu, oc, n):
+    """uzkge_cuda_ntt_fr_batch: k host vectors through the three-buffer copy / transform / copy pipeline (more vectors than buffers,
+    ragged inputs, forward, inverse and coset) against the oracle."""
+    k = 7
+    shift = oc.random_fr(1, 5)[0]
+    lens = [n, n // 2 + 1, 1, n, 3, n - 1, n]
+    for inverse, cs in ((False, None), (True, None), (False, shift), (True, shift)):
+        src = [oc.random_fr(n, 300 + j) for j in range(k)]
+        bufs = []
+        for j in range(k):
+            b = np.zeros((n, 4), dtype=np.uint64)
+            b[: lens[j]] = src[j][: lens[j]]
+            bufs.append(b)
+        want = [oc.ntt_fr(src[j][: lens[j]], n, inverse=inverse, coset=cs) for j in range(k)]
+        gpu.ntt_fr_batch_inplace(bufs, lens, n, inverse=inverse, coset_shift=cs)
+        for j in range(k):
+            assert np.array_equal(bufs[j], want[j]), (inverse, cs is not None, j)

@@ -63,7 +63,7 @@ struct State {
     std::map<uint64_t, MsmSrs> srs;
     uint64_t next_handle = 1;
     DevBuf data, scratch, scalars, small;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, out_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
     uint32_t ntt_log_tile = 10, ntt_max_log_r = 10, ntt_two_pass_max = 18;  // measured best on B200 (scripts/gpu_ntt_cfg.py)
 };
@@ -337,6 +337,59 @@ UZKGE_API int32_t uzkge_cuda_ntt_fr(uint64_t* inout, size_t len_in, size_t domai
     }
     CUDA_OR_FAIL(cudaMemcpyAsync(inout, g.data.p, domain_size * sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "ntt_fr: D2H");
     CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "ntt_fr: execution");
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_ntt_fr_batch(uint64_t* const* inouts, const size_t* len_in, size_t k, size_t domain_size, int32_t inverse,
+                                          const uint64_t* coset_shift) {
+    if (k && (!inouts || !len_in)) return fail(UZKGE_ERR_ARG, "ntt_fr_batch: null pointer");
+    if (inverse != 0 && inverse != 1) return fail(UZKGE_ERR_ARG, "ntt_fr_batch: inverse must be 0 or 1");
+    API_ENTER(-1);
+    if (k == 0) return UZKGE_OK;
+    bool ok = false;
+    ntt_root_of_unity(domain_size, &ok);
+    if (!ok || domain_size % 9 == 0) return fail(UZKGE_ERR_SIZE, "ntt_fr_batch: domain size must be 2^k or 3 * 2^k, k <= 28");
+    for (size_t j = 0; j < k; j++) {
+        if (!inouts[j]) return fail(UZKGE_ERR_ARG, "ntt_fr_batch: null vector");
+        if (len_in[j] > domain_size) return fail(UZKGE_ERR_SIZE, "ntt_fr_batch: input longer than the domain");
+    }
+    // Three stages on three streams over three device buffers: while transform j runs, vector j + 1 is on its way in and
+    // vector j - 1 on its way out (PCIe is full duplex), so a batch costs max(H2D, D2H, compute) per vector instead of their sum.
+    const size_t bytes = domain_size * sizeof(fe);
+    CUDA_OR_FAIL(g.data.reserve(3 * bytes), "ntt_fr_batch: data buffers");
+    CUDA_OR_FAIL(g.scratch.reserve(bytes), "ntt_fr_batch: scratch buffer");
+    if (!g.copy_stream) CUDA_OR_FAIL(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking), "ntt_fr_batch: stream");
+    if (!g.out_stream) CUDA_OR_FAIL(cudaStreamCreateWithFlags(&g.out_stream, cudaStreamNonBlocking), "ntt_fr_batch: stream");
+    while (g.copy_events.size() < 9) {
+        cudaEvent_t ev;
+        CUDA_OR_FAIL(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "ntt_fr_batch: event");
+        g.copy_events.push_back(ev);
+    }
+    cudaEvent_t* in_done = g.copy_events.data();        // [3]: vector landed in buffer b
+    cudaEvent_t* run_done = g.copy_events.data() + 3;   // [3]: transform finished in buffer b
+    cudaEvent_t* out_done = g.copy_events.data() + 6;   // [3]: buffer b copied back, free again
+    fe shift;
+    if (coset_shift) memcpy(&shift, coset_shift, sizeof(fe));
+    for (size_t j = 0; j < k; j++) {
+        const size_t b = j % 3;
+        fe* buf = (fe*)((char*)g.data.p + b * bytes);
+        if (j >= 3) CUDA_OR_FAIL(cudaStreamWaitEvent(g.copy_stream, out_done[b], 0), "ntt_fr_batch: wait");
+        if (len_in[j])
+            CUDA_OR_FAIL(cudaMemcpyAsync(buf, inouts[j], len_in[j] * sizeof(fe), cudaMemcpyHostToDevice, g.copy_stream), "ntt_fr_batch: H2D");
+        CUDA_OR_FAIL(cudaEventRecord(in_done[b], g.copy_stream), "ntt_fr_batch: event");
+        CUDA_OR_FAIL(cudaStreamWaitEvent(g.stream, in_done[b], 0), "ntt_fr_batch: wait");
+        int rc = g.ntt->run(buf, buf, (fe*)g.scratch.p, len_in[j], domain_size, inverse != 0, coset_shift ? &shift : nullptr, g.stream);
+        if (rc != UZKGE_OK) {
+            cudaDeviceSynchronize();
+            return engine_fail(rc, "ntt_fr_batch: launch");
+        }
+        CUDA_OR_FAIL(cudaEventRecord(run_done[b], g.stream), "ntt_fr_batch: event");
+        CUDA_OR_FAIL(cudaStreamWaitEvent(g.out_stream, run_done[b], 0), "ntt_fr_batch: wait");
+        CUDA_OR_FAIL(cudaMemcpyAsync(inouts[j], buf, bytes, cudaMemcpyDeviceToHost, g.out_stream), "ntt_fr_batch: D2H");
+        CUDA_OR_FAIL(cudaEventRecord(out_done[b], g.out_stream), "ntt_fr_batch: event");
+    }
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.out_stream), "ntt_fr_batch: execution");
+    CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "ntt_fr_batch: execution");
     return UZKGE_OK;
 }
 

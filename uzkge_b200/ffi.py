@@ -83,6 +83,7 @@ _SIGNATURES = {
     "uzkge_cuda_msm_g1": (C.c_int32, [C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_msm_g1_batch": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p]),
     "uzkge_cuda_ntt_fr": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p]),
+    "uzkge_cuda_ntt_fr_batch": (C.c_int32, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p]),
     "uzkge_cuda_fr_root_of_unity": (C.c_int32, [C.c_size_t, C.c_void_p]),
     "uzkge_cuda_msm_g1_device": (C.c_int32, [C.c_uint64, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_msm_g1_batch_device": (
@@ -333,6 +334,17 @@ def ntt_fr_inplace(buf: np.ndarray, len_in: int, domain_size: int, inverse: bool
         lib().uzkge_cuda_ntt_fr(ptr(buf), len_in, domain_size, 1 if inverse else 0, ptr(shift) if shift is not None else None),
         FFTError,
     )
+
+
+def ntt_fr_batch_inplace(bufs, lens_in, domain_size: int, inverse: bool = False, coset_shift=None) -> None:
+    """In-place transforms of k host buffers (each (domain_size, 4) uint64, C-contiguous, ideally pinned) in one pipelined call."""
+    k = len(bufs)
+    for b in bufs:
+        assert b.dtype == np.uint64 and b.flags["C_CONTIGUOUS"] and b.size == 4 * domain_size
+    pp = (C.c_void_p * k)(*[b.ctypes.data for b in bufs])
+    ll = (C.c_size_t * k)(*[int(x) for x in lens_in])
+    shift = as_u64(coset_shift, 4) if coset_shift is not None else None
+    check(lib().uzkge_cuda_ntt_fr_batch(pp, ll, k, domain_size, 1 if inverse else 0, ptr(shift) if shift is not None else None), FFTError)
 
 
 def fr_root_of_unity(n: int) -> np.ndarray:
