@@ -203,6 +203,9 @@ class TurboCS:
         self.public_vars_witness_indices = []
         self.boolean_constraint_indices = []
         self.edwards_a = 0
+        self.rounds = 0                 # n_iteration_shuffle_scalar_mul
+        self.pk_table = self.gen_table = None      # [round][4] -> (x, y, dxy)
+        self.remark = []                # shuffle_remark_constraint_indices: (first row, [s1 column, s2 column, s3 column])
         self.insert_constant_gate(0, 0)
         self.insert_constant_gate(1, 1)
 
@@ -258,6 +261,135 @@ class TurboCS:
         o = self.new_variable(self.witness[l] * self.witness[r])
         self.insert_mul_gate(l, r, o)
         return o
+
+    # ---- the shuffle gadgets
+    def equal(self, l, r):
+        self.insert_sub_gate(l, r, 0)
+
+    def linear_combine(self, wires_in, q1, q2, q3, q4):
+        """turbo/mod.rs:639-662."""
+        w = self.witness
+        o = self.new_variable(w[wires_in[0]] * q1 + w[wires_in[1]] * q2 + w[wires_in[2]] * q3 + w[wires_in[3]] * q4)
+        self.insert_lc_gate(wires_in, o, q1, q2, q3, q4)
+        return o
+
+    def load_shuffle_remark_parameters(self, pk):
+        """turbo/mod.rs:926-966 with BabyJubjubShuffle's constants."""
+        from . import babyjubjub as bj
+
+        tab = lambda segs: [[(x, y, bj.D * x * y % FR) for x, y in seg] for seg in segs]
+        self.pk_table, self.gen_table = tab(bj.segments(pk)), tab(bj.segments(bj.GEN))
+        self.edwards_a, self.rounds = bj.A, bj.NUM_ITERATIONS
+
+    def new_card_variable(self, card):
+        """constraint_system/shuffle/mod.rs:64-78: card = (e1, e2); variables created first.x, first.y, second.x, second.y and
+        returned as [second.x, second.y, first.x, first.y]."""
+        (fx, fy), (sx, sy) = card
+        a, b, c, d = self.new_variable(fx), self.new_variable(fy), self.new_variable(sx), self.new_variable(sy)
+        return [c, d, a, b]
+
+    def prepare_pi_card_variable(self, cv):
+        for v in cv:
+            self.prepare_pi_variable(v)
+
+    def eval_card_remark(self, field_bits, intermediate_values, input_var):
+        """constraint_system/shuffle/remark.rs:11-94: rounds + 1 gates with all-zero selectors; row r holds the running pair of
+        points in wires 0..3 and the next round's g.y in the output wire (0 in the last row)."""
+        assert len(field_bits) == len(intermediate_values) == self.rounds
+        self.remark.append((self.size, [[b[i] for b in field_bits] for i in range(3)]))
+        iv = [[self.new_variable(x) for x in vals] for vals in intermediate_values]
+        z4 = (0, 0, 0, 0)
+        self._push(z4, (0, 0), 0, 0, 0, list(input_var) + [iv[0][3]])
+        for r in range(self.rounds - 1):
+            self._push(z4, (0, 0), 0, 0, 0, iv[r] + [iv[r + 1][3]])
+        self._push(z4, (0, 0), 0, 0, 0, iv[-1] + [0])
+        return list(iv[-1])
+
+    def _sum3(self, vs, boolean=False):
+        s = 0
+        for i in range(0, len(vs), 3):
+            c = list(vs[i:i + 3])
+            q = [1] * len(c) + [0] * (3 - len(c))
+            s = self.linear_combine([s] + c + [0] * (3 - len(c)), 1, q[0], q[1], q[2])
+            if boolean:
+                self.attach_boolean_constraint_to_gate()
+        return s
+
+    def shuffle_card(self, card_vars, matrix):
+        """constraint_system/shuffle/permutation.rs:8-216."""
+        n = len(matrix)
+        pm = [[self.new_variable(y) for y in row] for row in matrix]
+        for row in pm:
+            self.equal(self._sum3(row, True), 1)
+        for j in range(n):
+            self.equal(self._sum3([pm[i][j] for i in range(n)]), 1)
+        w, out = self.witness, []
+        for row in pm:
+            permuted = []
+            for i in range(4):
+                coord = [cv[i] for cv in card_vars]
+                rv = []
+                for c in range(0, n, 2):
+                    if c + 1 < n:
+                        r = self.new_variable(w[row[c]] * w[coord[c]] + w[row[c + 1]] * w[coord[c + 1]])
+                        self._push((0, 0, 0, 0), (1, 1), 0, 0, 1, [row[c], coord[c], row[c + 1], coord[c + 1], r])
+                    else:
+                        r = self.new_variable(w[row[c]] * w[coord[c]])
+                        self._push((0, 0, 0, 0), (1, 1), 0, 0, 1, [row[c], coord[c], 0, 0, r])
+                    rv.append(r)
+                permuted.append(self._sum3(rv))
+            out.append(permuted)
+        return out
+
+    def _remark_rows(self):
+        for first, sel in self.remark:
+            for j in range(self.rounds):
+                yield first + j, j, sel
+
+    def compute_witness_selectors(self):
+        """turbo/mod.rs:171-191."""
+        polys = [[0] * self.size for _ in range(3)]
+        for row, j, sel in self._remark_rows():
+            for t in range(3):
+                polys[t][row] = sel[t][j]
+        return polys
+
+    def table_selectors(self, table):
+        """turbo/mod.rs:310-364: x_00..x_11, y_00..y_11, dxy_00..dxy_11 on the remark rows."""
+        polys = [[0] * self.size for _ in range(12)]
+        for row, j, _ in self._remark_rows():
+            for c in range(3):
+                for t in range(4):
+                    polys[4 * c + t][row] = table[j][t][c]
+        return polys
+
+    def q_ecc(self):
+        """plonk/indexer.rs:417-424."""
+        q = [0] * self.size
+        for row, _, _ in self._remark_rows():
+            q[row] = 1
+        return q
+
+    def check_remark_equations(self, witness):
+        """The four remark equations of verify_witness (turbo/mod.rs:1100-1330) on every remark row: the twisted Edwards addition
+        of +-(the selected multiple of pk / G) to the running pair of points, written without divisions."""
+        w_of = lambda j, row: witness[self.wiring[j][row]]
+        for row, r, sel in self._remark_rows():
+            a, b, c, d, o = (w_of(j, row) for j in range(5))
+            an, bn_, cn = (w_of(j, row + 1) for j in range(3))
+            s1, s2, s3 = sel[0][r], sel[1][r], sel[2][r]
+            pick = [(1 - s1) * (1 - s2), s1 * (1 - s2), (1 - s1) * s2, s1 * s2]
+            e = [0, 0, 0, 0]
+            for t in range(4):
+                px, py, pd = self.pk_table[r][t]
+                gx, gy, gd = self.gen_table[r][t]
+                e[0] += pick[t] * (s3 * an - s3 * a * py - b * px + a * b * an * pd)
+                e[1] += pick[t] * (s3 * bn_ + self.edwards_a * a * px - s3 * b * py - a * b * bn_ * pd)
+                e[2] += pick[t] * (s3 * cn - s3 * c * gy - d * gx + c * d * cn * gd)
+                e[3] += pick[t] * (s3 * o + self.edwards_a * c * gx - s3 * d * gy - c * d * o * gd)
+            if any(v % FR for v in e):
+                return False
+        return True
 
     def pad(self):
         n = 1
@@ -335,8 +467,8 @@ def _g1_lin(terms):
 
 # ---------------------------------------------------------------- indexer (plonk/indexer.rs:248-536)
 def indexer(cs: TurboCS, pcs: Kzg, shuffle: bool = False):
-    """shuffle = True adds what the `shuffle` feature adds (indexer.rs:447-501): q_ecc and the 12 + 12 shuffle selector polynomials
-    (all zero for circuits without remark gates -- the only circuits this restatement builds)."""
+    """shuffle = True adds what the `shuffle` feature adds (indexer.rs:414-476): q_ecc and the 12 + 12 shuffle selector polynomials
+    (all zero for circuits without remark gates)."""
     n, m = cs.size, cs.quot_eval_dom_size()
     factor = m // n
     root = bn.root_of_unity(n)
@@ -376,13 +508,30 @@ def indexer(cs: TurboCS, pcs: Kzg, shuffle: bool = False):
     }
     P["shuffle"] = shuffle
     if shuffle:
-        P["q_ecc_poly"], P["q_ecc_coset"] = pre([0] * n)
-        P["q_gen_polys"], P["q_gen_coset"] = zip(*[pre([0] * n) for _ in range(12)])
-        P["q_pk_polys"], P["q_pk_coset"] = P["q_gen_polys"], P["q_gen_coset"]          # indexer.rs:493-496
+        # indexer.rs:414-476: q_ecc, the generator selectors, and the public-key selectors as a copy of them
+        P["q_ecc_poly"], P["q_ecc_coset"] = pre(cs.q_ecc())
+        gen_evals = cs.table_selectors(cs.gen_table) if cs.remark else [[0] * n for _ in range(12)]
+        P["q_gen_polys"], P["q_gen_coset"] = zip(*[pre(e) for e in gen_evals])
+        P["q_pk_polys"], P["q_pk_coset"] = P["q_gen_polys"], P["q_gen_coset"]
         P["vp"].update({"cm_q_ecc": pcs.commit(P["q_ecc_poly"]), "cm_shuffle_generator_vec": [pcs.commit(p) for p in P["q_gen_polys"]],
                         "cm_shuffle_public_key_vec": [pcs.commit(p) for p in P["q_pk_polys"]], "edwards_a": cs.edwards_a, "root": root,
                         "pi_points": [pow(root, ci, FR) for ci in cs.public_vars_constraint_indices], "pi_lagrange": lagrange_constants})
     return P
+
+
+def refresh_public_key(P, cs, pcs, pk):
+    """shuffle/src/gen_params/params.rs:57-129 (monomial branch): reload the key, rebuild the 12 public-key selector polynomials,
+    their coset evaluations and commitments."""
+    cs.load_shuffle_remark_parameters(pk)
+    n, m, k = P["n"], P["m"], P["vp"]["k"]
+    polys, cosets = [], []
+    for e in cs.table_selectors(cs.pk_table):
+        c = bn.trim(bn.ifft(e, n))
+        polys.append(c)
+        cosets.append(bn.coset_fft(c, m, k[1]))
+    P["q_pk_polys"], P["q_pk_coset"] = polys, cosets
+    P["vp"]["cm_shuffle_public_key_vec"] = [pcs.commit(p) for p in polys]
+    return P["vp"]["cm_shuffle_public_key_vec"]
 
 
 # ---------------------------------------------------------------- prover (plonk/prover.rs:88-394, lagrange_pcs = None)
@@ -522,8 +671,8 @@ def prover(rng, tr, pcs, cs, P, witness):
         cm_w.append(cm)
     w_sel_polys, cm_w_sel = [], []
     if shuffle:
-        for _ in range(3):                      # compute_witness_selectors: all zero without remark gates (turbo/mod.rs:148-163)
-            f = bn.trim(bn.ifft([0] * n, n))
+        for sel_evals in cs.compute_witness_selectors():      # prover.rs:177-191
+            f = bn.trim(bn.ifft(sel_evals, n))
             hide_polynomial(rng, f, 2, n)
             cm = pcs.commit(f)
             tr.point(cm)

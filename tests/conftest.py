@@ -76,6 +76,12 @@ def srs_padding_head(oc):
 
 
 @pytest.fixture(scope="session")
+def srs_padding_tail(oc):
+    """tau^n, tau^(n+1), tau^(n+2) for n = 4096, 8192, 16384 (rows 0-2, 3-5, 6-8): srs-padding.bin[2051..2060)."""
+    return _load_points_mont("srs_padding_tail.npy", oc)
+
+
+@pytest.fixture(scope="session")
 def gpu():
     """The CUDA backend through its C ABI; fails loudly (no skip, no fallback) if it cannot start on a GPU box."""
     from uzkge_b200 import ffi

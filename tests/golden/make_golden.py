@@ -48,6 +48,9 @@ def main():
     assert all(o.g1_is_on_curve(P) for P in pts)
     assert pts[0] == o.G1_GEN
     np.save(os.path.join(HERE, "srs_padding_head.npy"), limbs(pts[:64]))
+    # tau^n .. tau^(n+2) for n = 4096, 8192, 16384: what load_srs_params puts at [n, n + 3) (uzkge/src/gen_params/mod.rs:147-171)
+    assert len(pts) == 2060
+    np.save(os.path.join(HERE, "srs_padding_tail.npy"), limbs(pts[2051:2060]))
 
     # ---- domain KATs from the generated Solidity verifier keys
     kat = {}

@@ -23,3 +23,54 @@ def build_circuit(cs, n_gates: int, seed: int, n_public: int = 1, n_boolean: int
         cs.attach_boolean_constraint_to_gate()
     cs.pad()
     return cs
+
+
+def shuffle_inputs(n_cards: int, seed: int):
+    """Deterministic inputs of a zshuffle circuit (shuffle/src/build_cs.rs:26-56): joint public key, input deck, remark bits and the
+    permutation, as plain integers / tuples, drawn with Python's generator and the oracle's curve arithmetic."""
+    from oracle import babyjubjub as bj
+
+    rnd = random.Random(seed)
+    sk = rnd.randrange(1, bj.ORDER)
+    pk = bj.mul(sk, bj.GEN)
+    cards, messages = [], []
+    for _ in range(n_cards):
+        msg = bj.mul(rnd.randrange(1, bj.ORDER), bj.GEN)
+        cards.append(bj.encrypt(rnd.randrange(1, bj.ORDER), msg, pk))
+        messages.append(msg)
+    bits = [[[rnd.random() < 0.5 for _ in range(3)] for _ in range(bj.NUM_ITERATIONS)] for _ in range(n_cards)]
+    perm = list(range(n_cards))
+    rnd.shuffle(perm)
+    return {"sk": sk, "pk": pk, "cards": cards, "messages": messages, "bits": bits, "perm": perm}
+
+
+def build_shuffle_circuit(cs, inp):
+    """build_cs (shuffle/src/build_cs.rs:26-56) on the product's TurboCS or on the oracle's, from the same inputs.  Returns
+    (cs, output card variables)."""
+    n = len(inp["cards"])
+    matrix = [[1 if inp["perm"][i] == j else 0 for j in range(n)] for i in range(n)]
+    cs.load_shuffle_remark_parameters(inp["pk"])
+    remarked = []
+    if hasattr(cs, "_init_shuffle"):         # the product's host mirror
+        from uzkge_b200 import shuffle as sh
+
+        for card, bits in zip(inp["cards"], inp["bits"]):
+            c = sh.Ciphertext(card[0], card[1])
+            trace = sh.BabyJubjubShuffle.eval_remark_with_trace(c, bits, inp["pk"])
+            var = cs.new_card_variable(c)
+            cs.prepare_pi_card_variable(var)
+            remarked.append(cs.eval_card_remark(trace, var))
+        out = cs.shuffle_card(remarked, sh.Permutation(matrix))
+    else:
+        from oracle import babyjubjub as bj
+
+        for card, bits in zip(inp["cards"], inp["bits"]):
+            fb, iv = bj.remark_trace(card, bits, inp["pk"])
+            var = cs.new_card_variable(card)
+            cs.prepare_pi_card_variable(var)
+            remarked.append(cs.eval_card_remark(fb, iv, var))
+        out = cs.shuffle_card(remarked, matrix)
+    for cv in out:
+        cs.prepare_pi_card_variable(cv)
+    cs.pad()
+    return cs, out

@@ -5,7 +5,8 @@ Python with the reference's names and order of operations (the RNG draws and tra
 
   TurboCS (the gates a synthetic circuit needs)  /root/reference/uzkge/src/plonk/constraint_system/turbo/mod.rs:395-537, 853-891, 968-977
   compute_permutation / extend_witness           /root/reference/uzkge/src/plonk/constraint_system/mod.rs:54-84, 103-111
-  indexer                                        /root/reference/uzkge/src/plonk/indexer.rs:248-536   (default features: no `shuffle`)
+  indexer                                        /root/reference/uzkge/src/plonk/indexer.rs:248-536   (both feature sets)
+  refresh_prover_params_public_key               /root/reference/shuffle/src/gen_params/params.rs:57-129
   prover                                         /root/reference/uzkge/src/plonk/prover.rs:76-394     (lagrange_pcs = None)
   pi_poly, hide_polynomial, z_poly, t_poly,
   r_poly, split_t_and_commit, first_lagrange_poly /root/reference/uzkge/src/plonk/helpers.rs:111-131, 139-154, 160-220, 223-678, 681-999,
@@ -28,6 +29,7 @@ from . import ffi
 from .errors import DegreeError, ParameterError, UzkgeError
 from .poly_commit import FR_MODULUS, KZGCommitment, KZGCommitmentSchemeBN254
 from .rng import ChaChaRng, choose_ks, fr_rand
+from .shuffle import ShuffleGates
 from .transcript import Transcript, init_pcs_batch_eval_transcript, transcript_init_plonk
 
 N_WIRES_PER_GATE = 5
@@ -91,9 +93,10 @@ def _dev():
 
 
 # ---------------------------------------------------------------------------------------------- TurboCS
-class TurboCS:
+class TurboCS(ShuffleGates):
     """constraint_system/turbo/mod.rs.  Gates are appended one by one (Python lists) or in bulk (`synthetic`); `pad()` freezes
-    the circuit into numpy arrays: selectors (9, n, 4) Montgomery limbs, wiring (5, n) uint32."""
+    the circuit into numpy arrays: selectors (9, n, 4) Montgomery limbs, wiring (5, n) uint32.  The shuffle gadgets
+    (constraint_system/shuffle/*.rs) come from shuffle.ShuffleGates."""
 
     def __init__(self):
         self._sel = [[] for _ in range(N_SELECTORS)]     # small codes: index into _sel_values
@@ -110,6 +113,7 @@ class TurboCS:
         self.selectors: np.ndarray | None = None
         self.wiring: np.ndarray | None = None
         self.verifier_only = False
+        self._init_shuffle()
         self.insert_constant_gate(self.zero_var(), 0)
         self.insert_constant_gate(self.one_var(), 1)
 
@@ -229,6 +233,86 @@ class TurboCS:
         self.wiring = wir
         self.size = n
         self._sel = self._wir = None
+        self._sel_codes, self._sel_table = sel, self._sel_values + [0]       # kept for verify_witness
+
+    # ---- `shuffle` feature set: selector tables as Montgomery arrays (turbo/mod.rs:171-191, 310-364; plonk/indexer.rs:417-424)
+    def _scatter_rows(self, per_round_values, count: int) -> np.ndarray:
+        """(count, n, 4) arrays, zero except on the rows of the remark gates: row first + j holds per_round_values[t][j]."""
+        out = np.zeros((count, self.size, 4), dtype=np.uint64)
+        firsts = np.asarray(self.shuffle_remark_constraint_indices(), dtype=np.int64)
+        rounds = self.n_iteration_shuffle_scalar_mul
+        if len(firsts) and rounds:
+            rows = (firsts[:, None] + np.arange(rounds)[None, :]).reshape(-1)
+            for t in range(count):
+                vals = per_round_values(t)              # (cards, rounds, 4) or (rounds, 4) Montgomery limbs
+                out[t, rows] = np.broadcast_to(vals, (len(firsts), rounds, 4)).reshape(-1, 4)
+        return out
+
+    def compute_witness_selectors(self) -> np.ndarray:
+        cons = self.shuffle_remark_constraints
+        return self._scatter_rows(lambda t: np.stack([mont_rows(sel[t]) for _, sel in cons]), 3)
+
+    def _table_selectors(self, table) -> np.ndarray:
+        if not self.shuffle_remark_constraints:
+            return np.zeros((12, self.size, 4), dtype=np.uint64)
+        return self._scatter_rows(lambda t: mont_rows([table[j][t % 4][t // 4] for j in range(self.n_iteration_shuffle_scalar_mul)]), 12)
+
+    def compute_shuffle_generator_selectors(self) -> np.ndarray:
+        return self._table_selectors(self.shuffle_generators)
+
+    def compute_shuffle_public_key_selectors(self) -> np.ndarray:
+        return self._table_selectors(self.shuffle_public_keys)
+
+    def compute_q_ecc(self) -> np.ndarray:
+        return self._scatter_rows(lambda t: mont_rows([1] * self.n_iteration_shuffle_scalar_mul), 1)[0]
+
+    def verify_witness(self, witness, online_vars) -> None:
+        """turbo/mod.rs:1041-1396 for the supported gate set (no Anemoi gates): the remark equations, the gate equation with the
+        public inputs, the boolean rows.  Raises UzkgeError naming the first failing row.  Host-side check, Python integers."""
+        if self.selectors is None:
+            raise UzkgeError("call cs.pad() before verify_witness")
+        if len(witness) != self.num_vars:
+            raise UzkgeError(f"witness len = {len(witness)}, num_vars = {self.num_vars}")
+        if not (len(online_vars) == len(self.public_vars_witness_indices) == len(self.public_vars_constraint_indices)):
+            raise UzkgeError("wrong number of online variables")
+        R, wir = FR_MODULUS, self.wiring
+        a_ed = self.edwards_a
+        for first, sel in self.shuffle_remark_constraints:
+            for r in range(self.n_iteration_shuffle_scalar_mul):
+                row = first + r
+                a, b, c, d, o = (witness[int(wir[j, row])] for j in range(5))
+                an, bn, cn = (witness[int(wir[j, row + 1])] for j in range(3))
+                s1, s2, s3 = sel[0][r], sel[1][r], sel[2][r]
+                if s1 not in (0, 1) or s2 not in (0, 1) or s3 not in (1, R - 1):
+                    raise UzkgeError(f"cs index {first} round {r}: wire selectors out of range")
+                w4 = [(1 - s1) * (1 - s2), s1 * (1 - s2), (1 - s1) * s2, s1 * s2]
+                e = [0, 0, 0, 0]
+                for t in range(4):
+                    px, py, pd = self.shuffle_public_keys[r][t]
+                    gx, gy, gd = self.shuffle_generators[r][t]
+                    e[0] += w4[t] * (s3 * an - s3 * a * py - b * px + a * b * an * pd)
+                    e[1] += w4[t] * (s3 * bn + a_ed * a * px - s3 * b * py - a * b * bn * pd)
+                    e[2] += w4[t] * (s3 * cn - s3 * c * gy - d * gx + c * d * cn * gd)
+                    e[3] += w4[t] * (s3 * o + a_ed * c * gx - s3 * d * gy - c * d * o * gd)
+                for t in range(4):
+                    if e[t] % R:
+                        raise UzkgeError(f"cs index {first} round {r}: equation {t + 1} of shuffle does not hold")
+        pub = {}
+        for c_i, w_i, v in zip(self.public_vars_constraint_indices, self.public_vars_witness_indices, online_vars):
+            if witness[w_i] != v % R:
+                raise UzkgeError(f"cs index {c_i}: online var does not match witness")
+            pub[c_i] = v % R
+        booleans = set(self.boolean_constraint_indices)
+        tab = self._sel_table
+        for row in range(self.size):
+            w = [witness[int(wir[j, row])] for j in range(5)]
+            q = [tab[int(self._sel_codes[j, row])] for j in range(N_SELECTORS)]
+            g = (q[0] * w[0] + q[1] * w[1] + q[2] * w[2] + q[3] * w[3] + q[4] * w[0] * w[1] + q[5] * w[2] * w[3] + q[6] + pub.get(row, 0)
+                 + q[7] * w[0] * w[1] * w[2] * w[3] * w[4] - q[8] * w[4])
+            if g % R:
+                raise UzkgeError(f"cs index {row}: gate equation does not hold")
+            if row in booleans and any(w[j] not in (0, 1) for j in (1, 2, 3)):
+                raise UzkgeError(f"cs index {row}: a boolean-constrained wire is not one or zero")
 
     def get_witness_array(self) -> np.ndarray:
         """The witness as (num_vars, 4) Montgomery limbs."""
@@ -503,6 +587,26 @@ def _lagrange_commit_scheme(pcs, lagrange_pcs, n: int, ws: dict):
     return scheme
 
 
+def _commit_coefs_lagrange(lag, polys, n: int, scratch: DevVec) -> list:
+    """Commit COEFFICIENT vectors of up to n + 3 entries over the Lagrange SRS (helpers.rs:1363-1391, pcs.rs:139-163): with
+    f = f_lo + X^n f_hi, f(tau) G = MSM(L_i(tau) G, f_lo on H) + sum_i f_hi[i] SRS[n + i], i.e. one size-n forward transform and
+    one MSM over `_lagrange_commit_scheme`'s bases with the scalars [f_lo on H | 0 0 0 | f_hi].  (The reference folds f_hi into
+    f_lo and cancels it again through apply_blind_factors; the group element is the same.)"""
+    dev = polys[0].t.device
+    stride = n + 8
+    buf = DevVec(len(polys) * stride, dev)
+    for i, p in enumerate(polys):
+        if p.len > n + N_BLIND_SLOTS:
+            raise DegreeError("DegreeError")
+        if p.len == 0:
+            continue
+        ffi.ntt_fr_device(p.ptr, buf.at(i * stride), scratch.ptr, min(p.len, n), n, False, None)
+        hi = p.len - n
+        if hi > 0:
+            buf.t[4 * (i * stride + n + N_BLIND_SLOTS): 4 * (i * stride + n + N_BLIND_SLOTS + hi)].copy_(p.t[4 * n: 4 * (n + hi)])
+    return _commit_dev(lag, [_View(buf, i * stride, n + 2 * N_BLIND_SLOTS) for i in range(len(polys))])
+
+
 def _set_blind_slots(buf: DevVec, first: int, blinds) -> None:
     """Slots [first, first + 6) <- [b_0 b_1 b_2 | -b_0 -b_1 -b_2] (missing blinds are zero)."""
     b = list(blinds) + [0] * (N_BLIND_SLOTS - len(blinds))
@@ -536,12 +640,14 @@ def _add_coefs(poly: DevVec, idx, vals) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- indexer
-def indexer(cs: TurboCS, pcs, shuffle: bool = False) -> PlonkProverParams:
-    """plonk/indexer.rs:240-536 with lagrange_pcs = None, permutation = None, verifier_params = None.  shuffle = True builds the
-    parameters of the `shuffle` feature set (what zshuffle is compiled with): q_ecc and the 12 + 12 shuffle selector polynomials
-    (indexer.rs:447-501) -- all zero here, because the supported gate set has no remark gates; the prover then also commits the
-    witness-selector polynomials, evaluates terms 12-18 of the quotient and opens q_ecc / w_sel, i.e. produces the proof format of
-    the reference's deployed verifier."""
+def indexer(cs: TurboCS, pcs, shuffle: bool = False, lagrange_pcs=None) -> PlonkProverParams:
+    """plonk/indexer.rs:240-536 with permutation = None, verifier_params = None.  shuffle = True builds the parameters of the
+    `shuffle` feature set (what zshuffle is compiled with): q_ecc and the 12 + 12 shuffle selector polynomials
+    (indexer.rs:414-476) from the circuit's remark gates (zero polynomials when it has none); the public-key selectors start as a
+    copy of the generator selectors (indexer.rs:471-476) until refresh_prover_params_public_key loads a key.  The prover then
+    also commits the witness-selector polynomials, evaluates terms 12-18 of the quotient and opens q_ecc / w_sel, i.e. produces the
+    proof format of the reference's deployed verifier.  lagrange_pcs: when given (and of the circuit's size) every commitment
+    is the MSM of the EVALUATIONS over the Lagrange SRS (indexer.rs:284-301, `commit` closure) instead of the coefficients'."""
     if cs.selectors is None:
         raise UzkgeError("call cs.pad() before indexing")
     n, m = cs.size, cs.quot_eval_dom_size()
@@ -568,29 +674,39 @@ def indexer(cs: TurboCS, pcs, shuffle: bool = False) -> PlonkProverParams:
     ffi.fr_gather_device(table.ptr, d_perm.data_ptr(), N_WIRES_PER_GATE * n, sigma.ptr)
     del table
 
-    def preprocess(evals_ptr: int):
+    if lagrange_pcs is not None and lagrange_pcs.max_degree() + 1 != n:
+        lagrange_pcs = None                                                # indexer.rs:262-267
+    commit_src = {}      # id(coefficient vector) -> what is committed for it: the evaluations on the Lagrange path
+
+    def preprocess(evals):
+        """evals: a DevVec or _View of n values on H -> (coefficients, coset evaluations)."""
         coefs = DevVec(n, dev, zero=False)
-        _ifft(evals_ptr, n, coefs, scratch)
+        _ifft(evals.ptr, n, coefs, scratch)
         coset = DevVec(m, dev, zero=False)
         _coset_fft(coefs, m, k1, coset, scratch)
+        commit_src[id(coefs)] = evals if lagrange_pcs is not None else coefs
         return coefs, coset
+
+    def commit_all(polys):
+        if lagrange_pcs is not None:
+            return _commit_many(lagrange_pcs, [commit_src[id(p)] for p in polys])
+        return _commit_many(pcs, polys)
 
     s_polys, s_coset = [], []
     for i in range(N_WIRES_PER_GATE):
-        c, e = preprocess(sigma.at(i * n))
+        c, e = preprocess(_View(sigma, i * n, n))
         s_polys.append(c)
         s_coset.append(e)
     # Step 2: selector polynomials
     q_polys, q_coset = [], []
     for i in range(N_SELECTORS):
-        ev = DevVec.from_numpy(cs.selectors[i], dev)
-        c, e = preprocess(ev.ptr)
+        c, e = preprocess(DevVec.from_numpy(cs.selectors[i], dev))
         q_polys.append(c)
         q_coset.append(e)
     # Step 3: L1 and Z_H
     l1 = DevVec(n, dev)
     ffi.fr_add_sparse_device(l1.ptr, [0], mont_rows([n]))
-    _l1_coefs, l1_coset = preprocess(l1.ptr)
+    _l1_coefs, l1_coset = preprocess(l1)
     z_h_inv = []
     mult, step = pow(k[1], n, FR_MODULUS), pow(root_m, n, FR_MODULUS)
     for _ in range(factor):
@@ -608,26 +724,39 @@ def indexer(cs: TurboCS, pcs, shuffle: bool = False) -> PlonkProverParams:
         idx = list(cs.boolean_constraint_indices)
         for i in range(0, len(idx), ffi.SPARSE_MAX):
             ffi.fr_add_sparse_device(qb.ptr, idx[i:i + ffi.SPARSE_MAX], mont_rows([1] * len(idx[i:i + ffi.SPARSE_MAX])))
-        qb_poly, qb_coset = preprocess(qb.ptr)
+        qb_poly, qb_coset = preprocess(qb)
     else:
         qb_poly, qb_coset = zero_poly, zero_coset
     q_prk_polys, q_prk_coset = [zero_poly] * 4, [zero_coset] * 4
 
-    cms = _commit_many(pcs, q_polys + s_polys + [qb_poly, zero_poly])
+    commit_src[id(zero_poly)] = zero_poly
+    cms = commit_all(q_polys + s_polys + [qb_poly, zero_poly])
     identity = cms[-1]
     vp = PlonkVerifierParams(
         cm_q_vec=cms[:N_SELECTORS], cm_s_vec=cms[N_SELECTORS:N_SELECTORS + N_WIRES_PER_GATE], cm_qb=cms[-2], cm_prk_vec=[identity] * 4,
         anemoi_generator=0, anemoi_generator_inv=0, k=k, cs_size=n,
         public_vars_constraint_indices=list(cs.public_vars_constraint_indices), lagrange_constants=lagrange_constants)
     d_wiring = torch.from_numpy(cs.wiring.reshape(-1).view(np.int32)).to(dev)
-    torch.cuda.synchronize()
     extra = {}
     if shuffle:
-        vp.cm_q_ecc, vp.cm_shuffle_generator_vec, vp.cm_shuffle_public_key_vec = identity, [identity] * 12, [identity] * 12
-        vp.edwards_a = 0
-        extra = dict(q_ecc_poly=zero_poly, q_ecc_coset_eval=zero_coset, q_shuffle_generator_polys=[zero_poly] * 12,
-                     q_shuffle_generator_coset_evals=[zero_coset] * 12, q_shuffle_public_key_polys=[zero_poly] * 12,
-                     q_shuffle_public_key_coset_evals=[zero_coset] * 12)
+        # Steps 7-9 (indexer.rs:414-476): q_ecc = 1 on the rows of the remark gates, the 12 generator selectors, and the
+        # public-key selectors as a copy of them
+        if cs.shuffle_remark_constraints:
+            q_ecc_poly, q_ecc_coset = preprocess(DevVec.from_numpy(cs.compute_q_ecc(), dev))
+            gen_evals = cs.compute_shuffle_generator_selectors()
+            gen = [preprocess(DevVec.from_numpy(gen_evals[i], dev)) for i in range(12)]
+            gen_polys, gen_coset = [g[0] for g in gen], [g[1] for g in gen]
+            cms2 = commit_all([q_ecc_poly] + gen_polys)
+            vp.cm_q_ecc, vp.cm_shuffle_generator_vec = cms2[0], cms2[1:]
+        else:
+            q_ecc_poly, q_ecc_coset, gen_polys, gen_coset = zero_poly, zero_coset, [zero_poly] * 12, [zero_coset] * 12
+            vp.cm_q_ecc, vp.cm_shuffle_generator_vec = identity, [identity] * 12
+        vp.cm_shuffle_public_key_vec = list(vp.cm_shuffle_generator_vec)
+        vp.edwards_a = cs.edwards_a
+        extra = dict(q_ecc_poly=q_ecc_poly, q_ecc_coset_eval=q_ecc_coset, q_shuffle_generator_polys=gen_polys,
+                     q_shuffle_generator_coset_evals=gen_coset, q_shuffle_public_key_polys=list(gen_polys),
+                     q_shuffle_public_key_coset_evals=list(gen_coset))
+    torch.cuda.synchronize()
     return PlonkProverParams(**extra, **dict(
         q_polys=q_polys, s_polys=s_polys, qb_poly=qb_poly, q_prk_polys=q_prk_polys, verifier_params=vp, group=group,
         coset_quotient=coset_quotient, l1_coset_evals=l1_coset, z_h_inv_coset_evals=mont_rows(z_h_inv), q_coset_evals=q_coset,
@@ -637,6 +766,42 @@ def indexer(cs: TurboCS, pcs, shuffle: bool = False) -> PlonkProverParams:
 
 def _commit_many(pcs, vecs) -> list:
     return _commit_dev(pcs, vecs)
+
+
+def refresh_prover_params_public_key(cs: TurboCS, prover_params: PlonkProverParams, pcs, shuffle_pk, lagrange_pcs=None) -> list:
+    """shuffle/src/gen_params/params.rs:57-129: load a new joint public key into the circuit and rebuild what depends on it -- the
+    12 public-key selector polynomials (ifft over H), their evaluations on the quotient coset (coset fft over 6n points) and
+    their commitments (over the Lagrange SRS when one of the circuit's size is given, else over the monomial SRS).  Updates
+    `prover_params` in place and returns the 12 commitments.  (The reference reloads both SRS files here; the caller passes the
+    resident ones.)"""
+    P = prover_params
+    if P.q_shuffle_public_key_polys is None:
+        raise ParameterError("the parameters were built without the shuffle feature set")
+    cs.load_shuffle_remark_parameters(shuffle_pk)
+    n, m = cs.size, cs.quot_eval_dom_size()
+    if m % n != 0 or n != P.n:
+        raise ParameterError("ParameterError")
+    if lagrange_pcs is not None and lagrange_pcs.max_degree() + 1 != n:
+        lagrange_pcs = None
+    dev = _dev()
+    scratch = P.workspace.get("scratch") or DevVec(m, dev, zero=False)
+    k1 = mont(P.verifier_params.k[1])
+    evals = cs.compute_shuffle_public_key_selectors()
+    d_evals, polys, cosets = [], [], []
+    for i in range(12):
+        ev = DevVec.from_numpy(evals[i], dev)
+        coefs, coset = DevVec(n, dev, zero=False), DevVec(m, dev, zero=False)
+        _ifft(ev.ptr, n, coefs, scratch)
+        _coset_fft(coefs, m, k1, coset, scratch)
+        d_evals.append(ev)
+        polys.append(coefs)
+        cosets.append(coset)
+    cms = _commit_many(lagrange_pcs, d_evals) if lagrange_pcs is not None else _commit_many(pcs, polys)
+    torch.cuda.synchronize()
+    P.q_shuffle_public_key_polys, P.q_shuffle_public_key_coset_evals = polys, cosets
+    P.verifier_params.cm_shuffle_public_key_vec = cms
+    P.workspace.pop("coset_params", None)
+    return cms
 
 
 # ---------------------------------------------------------------------------------------------- the quotient round, coset by coset
@@ -764,12 +929,16 @@ def batch_prove(pcs, transcript: Transcript, polys, evals, point: int, max_degre
 
 
 def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkProverParams, w,
-           timings: dict | None = None, lagrange_pcs=None, quotient_by_cosets: bool = False) -> PlonkProof:
+           timings: dict | None = None, lagrange_pcs=None, quotient_by_cosets: bool = False, lagrange_all: bool | None = None) -> PlonkProof:
     """plonk/prover.rs:76-394 (`prover` = `prover_with_lagrange` with lagrange_pcs = None).  `w`: the witness, (num_vars, 4)
     Montgomery limbs (numpy) or a DevVec already in HBM.  With a `lagrange_pcs` whose size matches the circuit
     (prover.rs:119-124) the wire and z commitments are MSMs of the EVALUATION vectors against the Lagrange SRS with the blind
     terms as six extra bases (prover.rs:131-146, `_lagrange_commit_scheme`); the quotient pieces and opening proofs are committed in coefficient form -- the same group
     elements as the reference's Lagrange branch (helpers.rs:1363-1391, pcs.rs:139-163), without its extra transforms.
+    lagrange_all: also commit the witness-selector polynomials, the quotient pieces and the two opening quotients over the Lagrange
+    SRS (one forward transform each, `_commit_coefs_lagrange`) -- what the reference's Lagrange branch does, and the only
+    possibility with the bundled production parameters, whose monomial SRS holds tau^i only for i < 2051 and i in [n, n + 3)
+    (gen_params/mod.rs:147-171).  None = decide from the SRS: on when bases below n are missing.
     quotient_by_cosets: evaluate the quotient round coset by coset (CosetParams) on this GPU -- the single-GPU form of what
     dist.SplitCommitter distributes; the proof is the same."""
     if cs.is_verifier_only():
@@ -785,6 +954,12 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     marks = []
     if lagrange_pcs is not None and (lagrange_pcs.max_degree() + 1 != n or hasattr(pcs, "commit_device")):
         lagrange_pcs = None
+    if lagrange_pcs is None:
+        lagrange_all = False
+    elif lagrange_all is None:
+        if "srs_truncated" not in ws:
+            ws["srs_truncated"] = not bool(np.asarray(pcs.public_parameter_group_1[:n]).any(axis=1).all())
+        lagrange_all = ws["srs_truncated"]
 
     def mark(name):
         if timings is not None:
@@ -845,16 +1020,32 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         cm_w_vec = _commit_dev(pcs, w_polys, overlap=wire_cosets)
     for cm in cm_w_vec:
         transcript.append_commitment(cm)
-    # 3. (`shuffle` feature set) witness-selector polynomials (prover.rs:148-165): zero on H here (compute_witness_selectors
-    # without remark gates, turbo/mod.rs:148-163), hidden with 2 blinds each, committed
+    # 3. (`shuffle` feature set) witness-selector polynomials (prover.rs:177-191): the remark gates' bit / sign columns
+    # (compute_witness_selectors, turbo/mod.rs:171-191; zero on H without remark gates), hidden with 2 blinds each, committed
     shuffle = P.q_ecc_poly is not None
     w_sel_polys, cm_w_sel_vec = [], None
     if shuffle:
-        for _ in range(3):
-            f = DevVec(cap, dev, length=1)
-            hide_polynomial(prng, f, 2, n)
+        has_remark = bool(cs.shuffle_remark_constraints)
+        w_sel_blinds = []
+        sel_ev = DevVec(3 * stride, dev)
+        if has_remark:
+            sel_host = cs.compute_witness_selectors()
+            for i in range(3):
+                sel_ev.t[4 * i * stride: 4 * (i * stride + n)].copy_(torch.from_numpy(sel_host[i].view(np.int64).reshape(-1)))
+        for i in range(3):
+            if has_remark:
+                f = DevVec(cap, dev, length=n)
+                _ifft(sel_ev.at(i * stride), n, f, scratch)
+            else:
+                f = DevVec(cap, dev, length=1)
+            w_sel_blinds.append(hide_polynomial(prng, f, 2, n))
             w_sel_polys.append(f)
-        cm_w_sel_vec = _commit_dev(pcs, w_sel_polys)
+        if lagrange_all:
+            for i in range(3):
+                _set_blind_slots(sel_ev, i * stride + n, w_sel_blinds[i])
+            cm_w_sel_vec = _commit_dev(lag, [_View(sel_ev, i * stride, n + 2 * N_BLIND_SLOTS) for i in range(3)])
+        else:
+            cm_w_sel_vec = _commit_dev(pcs, w_sel_polys)
         for cm in cm_w_sel_vec:
             transcript.append_commitment(cm)
     mark("round1_wires")
@@ -956,7 +1147,7 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
             _add_coefs(tp, [0], [-prev])
         prev = rand
         t_polys.append(tp)
-    cm_t_vec = _commit_many(pcs, t_polys)
+    cm_t_vec = _commit_coefs_lagrange(lag, t_polys, n, scratch) if lagrange_all else _commit_many(pcs, t_polys)
     for cm in cm_t_vec:
         transcript.append_commitment(cm)
     mark("round3_commit_t")
@@ -1008,20 +1199,20 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     if shuffle:
         # 6.-9. the remark-gate parts (helpers.rs:747-983): per selector combination c, over the public-key / generator selector
         # polynomials x_c, y_c, dxy_c
-        ws, wo, ed_a = w_sel_polys_eval_zeta, w_polys_eval_zeta_omega, vp.edwards_a
+        wsl, wo, ed_a = w_sel_polys_eval_zeta, w_polys_eval_zeta_omega, vp.edwards_a
         ah = [pow(alpha, i, FR_MODULUS) for i in range(14)]
-        sel = [((1 - ws[0]) * (1 - ws[1]) + q_ecc_poly_eval_zeta - 1) % FR_MODULUS, ws[0] * (1 - ws[1]) % FR_MODULUS,
-               (1 - ws[0]) * ws[1] % FR_MODULUS, ws[0] * ws[1] % FR_MODULUS]
+        sel = [((1 - wsl[0]) * (1 - wsl[1]) + q_ecc_poly_eval_zeta - 1) % FR_MODULUS, wsl[0] * (1 - wsl[1]) % FR_MODULUS,
+               (1 - wsl[0]) * wsl[1] % FR_MODULUS, wsl[0] * wsl[1] % FR_MODULUS]
         pk, gen = P.q_shuffle_public_key_polys, P.q_shuffle_generator_polys
         for c in range(4):
-            terms += [(ah[10] * sel[c] * we[0] * we[1] * wo[0], pk[8 + c]), (-ah[10] * sel[c] * ws[2] * we[0], pk[4 + c]),
+            terms += [(ah[10] * sel[c] * we[0] * we[1] * wo[0], pk[8 + c]), (-ah[10] * sel[c] * wsl[2] * we[0], pk[4 + c]),
                       (-ah[10] * sel[c] * we[1], pk[c]),
                       (-ah[11] * sel[c] * we[0] * we[1] * wo[1], pk[8 + c]), (ah[11] * sel[c] * we[0] * ed_a, pk[c]),
-                      (-ah[11] * sel[c] * ws[2] * we[1], pk[4 + c]),
-                      (ah[12] * sel[c] * we[2] * we[3] * wo[2], gen[8 + c]), (-ah[12] * sel[c] * ws[2] * we[2], gen[4 + c]),
+                      (-ah[11] * sel[c] * wsl[2] * we[1], pk[4 + c]),
+                      (ah[12] * sel[c] * we[2] * we[3] * wo[2], gen[8 + c]), (-ah[12] * sel[c] * wsl[2] * we[2], gen[4 + c]),
                       (-ah[12] * sel[c] * we[3], gen[c]),
                       (-ah[13] * sel[c] * we[2] * we[3] * we[4], gen[8 + c]), (ah[13] * sel[c] * we[2] * ed_a, gen[c]),
-                      (-ah[13] * sel[c] * ws[2] * we[3], gen[4 + c])]
+                      (-ah[13] * sel[c] * wsl[2] * we[3], gen[4 + c])]
     zfactor = pow(zeta, piece, FR_MODULUS)
     exponent = z_h_eval_zeta
     for tp in t_polys:
@@ -1058,7 +1249,10 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     sh, q1, q2 = DevVec(hmax, dev, zero=False), DevVec(hmax, dev, zero=False), DevVec(hmax, dev, zero=False)
     rem1 = batch_prove_quotient(transcript, polys_to_open, evals_to_open, zeta, n + 2, sh, q1)
     rem2 = batch_prove_quotient(transcript, [z_poly] + w_polys[:3], [z_eval_zeta_omega] + w_polys_eval_zeta_omega, zeta_omega, n + 2, sh, q2)
-    opening_witness_zeta, opening_witness_zeta_omega = _commit_dev(pcs, [q1, q2])
+    if lagrange_all:
+        opening_witness_zeta, opening_witness_zeta_omega = _commit_coefs_lagrange(lag, [q1, q2], n, scratch)
+    else:
+        opening_witness_zeta, opening_witness_zeta_omega = _commit_dev(pcs, [q1, q2])
     if torch.cat([rem1, rem2]).cpu().numpy().any():
         raise UzkgeError("PCSProveEvalError")
     mark("round5_openings")
