@@ -277,6 +277,78 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
     return out
 
 
+def zshuffle_proofs(dev, K: int, W: int, cards: int = 52) -> dict:
+    """BASELINE.json configs[0]: the zshuffle circuit itself (shuffle/src/build_cs.rs:26-56: `cards` remark gadgets + the permutation
+    gadget, 2^14 gates for 52 cards) built by the host mirror (uzkge_b200/shuffle.py), indexed with the `shuffle` feature set, a joint
+    key loaded with refresh_prover_params_public_key, and proved the way the reference's production path does: every commitment
+    over the Lagrange SRS (lagrange_all).  The SRS is synthetic (known tau) -- the parity tests use the bundled production
+    parameters.  A step = one `prover` call; building the circuit (host, Python integers) is reported beside it, not inside."""
+    import torch
+
+    from uzkge_b200 import KZGCommitmentSchemeBN254, ffi, plonk
+    from uzkge_b200 import shuffle as sh
+    from uzkge_b200.rng import ChaChaRng
+    from uzkge_b200.transcript import Transcript
+
+    tau = plonk.mont(0x1234567890ABCDEF1234567890ABCDEF)
+    prng = ChaChaRng.from_seed(bytes(32))
+    t0 = time.perf_counter()
+    apk = sh.rand_point(prng)
+    deck = [sh.Ciphertext.rand(prng) for _ in range(cards)]
+    cs, _ = sh.build_cs(plonk.TurboCS(), prng, apk, deck)
+    build_s = time.perf_counter() - t0
+    n = cs.size
+    t0 = time.perf_counter()
+    pcs, lagrange = KZGCommitmentSchemeBN254.new(n + 2, tau), KZGCommitmentSchemeBN254.new_lagrange(n, tau)
+    params = plonk.indexer(cs, pcs, shuffle=True, lagrange_pcs=lagrange)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    plonk.refresh_prover_params_public_key(cs, params, pcs, apk, lagrange_pcs=lagrange)
+    refresh_ms = (time.perf_counter() - t0) * 1e3
+    wit_pinned = ffi.PinnedArray(cs.get_witness_array().shape)
+    wit_pinned.array[:] = cs.get_witness_array()
+    wit_host = wit_pinned.array
+
+    def prove(w, timings=None):
+        tr = Transcript(b"Plonk shuffle Proof")
+        tr.append_u64(cards)
+        return plonk.prover(ChaChaRng.from_seed(bytes(32)), tr, pcs, cs, params, w, timings=timings, lagrange_pcs=lagrange, lagrange_all=True)
+
+    wit = plonk.DevVec.from_numpy(wit_host, dev)
+    for _ in range(max(W, 3)):
+        proof = prove(wit)
+    torch.cuda.synchronize()
+    timings = {}
+    l0 = ffi.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        prove(wit, timings)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / K
+    launches = (ffi.launch_count() - l0) // K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        proof2 = prove(wit_host)
+    torch.cuda.synchronize()
+    dt_e2e = (time.perf_counter() - t0) / K
+    res = {
+        "circuit": f"zshuffle-{cards}", "log_n": n.bit_length() - 1, "n_gpus": 1, "mode": "single", "witness": "remark + permutation gadgets",
+        "lagrange_commitments": True, "lagrange_all": True, "feature_set": "shuffle", "proof_bytes": len(proof.to_bytes_be()),
+        "prove_ms": dt * 1e3, "proofs_per_s": 1 / dt, "e2e_prove_ms": dt_e2e * 1e3, "e2e_proofs_per_s": 1 / dt_e2e,
+        "h2d_bytes_per_step": int(wit_host.nbytes) + 3 * n * 32, "d2h_bytes_per_step": 16 * 96 + 20 * 32, "steps": K,
+        "launches_per_proof": int(launches), "rounds_ms": {k: v / K for k, v in timings.items()},
+        "ops_per_proof": {"msm": 16, "ifft_n": 9, "fft_n": 7, "coset_fft_6n": 9, "coset_ifft_6n": 1, "quotient_points": int(params.m), "evals": 20},
+        "build_cs_host_s": build_s, "setup_s": setup_s, "refresh_public_key_ms": refresh_ms,
+        "deterministic": proof.to_bytes_be() == proof2.to_bytes_be(),
+    }
+    pcs.close()
+    lagrange.close()
+    del wit_host
+    wit_pinned.free()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main() -> int:
     ap = argparse.ArgumentParser()
@@ -286,6 +358,7 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="all", choices=["all", "both", "msm", "ntt", "plonk"])
     ap.add_argument("--plonk-logs", default="14,22", help="log2 circuit sizes of the synthetic TurboPlonK proofs")
+    ap.add_argument("--no-zshuffle", action="store_true", help="skip the zshuffle-52 circuit of the PlonK block")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -596,6 +669,8 @@ def main() -> int:
     # -------------------------------------------------------------------------------------------- PlonK (rank 0, N = 1)
     if args.workload in ("all", "plonk"):
         results["plonk"] = plonk_proofs(args, dev, K, W, rank, world, barrier, max_over_ranks)
+        if world == 1 and not args.no_zshuffle:
+            results["plonk"]["sizes"].append(zshuffle_proofs(dev, K, W))
 
     t_region1 = time.time()
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
@@ -720,7 +795,7 @@ def main() -> int:
             "metric": "turboplonk_synthetic_proofs_per_s", "value": first["proofs_per_s"], "unit": "proofs/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": first["prove_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (256-bit Montgomery, IMAD carry chains)", "data": "synthetic",
-            "config": {"workload": f"synthetic TurboPlonK circuit, 2^{first['log_n']} gates, full prove, witness resident in HBM"},
+            "config": {"workload": f"{first.get('circuit', 'synthetic TurboPlonK circuit')}, 2^{first['log_n']} gates, full prove, witness resident in HBM"},
             "e2e": {"value": first["e2e_proofs_per_s"], "unit": "proofs/s", "h2d_bytes_per_step": first["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": first["d2h_bytes_per_step"]},
             "gpu_launches": int(launches), "clocks": clocks, "plonk": pl,

@@ -54,9 +54,10 @@ def build_shuffle_circuit(cs, inp):
     if hasattr(cs, "_init_shuffle"):         # the product's host mirror
         from uzkge_b200 import shuffle as sh
 
+        pks = sh.BabyJubjubShuffle.crate_public_keys(inp["pk"])
         for card, bits in zip(inp["cards"], inp["bits"]):
             c = sh.Ciphertext(card[0], card[1])
-            trace = sh.BabyJubjubShuffle.eval_remark_with_trace(c, bits, inp["pk"])
+            trace = sh.BabyJubjubShuffle.eval_remark_with_trace(c, bits, inp["pk"], pks)
             var = cs.new_card_variable(c)
             cs.prepare_pi_card_variable(var)
             remarked.append(cs.eval_card_remark(trace, var))

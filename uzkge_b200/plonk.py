@@ -249,7 +249,11 @@ class TurboCS(ShuffleGates):
         return out
 
     def compute_witness_selectors(self) -> np.ndarray:
-        cons = self.shuffle_remark_constraints
+        cons, codes = self.shuffle_remark_constraints, self._remark_sel_codes
+        if cons and all(c is not None for c in codes):            # remark traces: bits and signs only -> table lookup
+            table = np.stack([_ZERO, _ONE, mont(-1)])
+            arr = np.asarray(codes, dtype=np.int64)               # (cards, 3, rounds)
+            return self._scatter_rows(lambda t: table[arr[:, t, :]], 3)
         return self._scatter_rows(lambda t: np.stack([mont_rows(sel[t]) for _, sel in cons]), 3)
 
     def _table_selectors(self, table) -> np.ndarray:

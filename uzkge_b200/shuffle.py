@@ -43,19 +43,51 @@ def ed_add(p, q):
     return (x3, y3)
 
 
+def _ext(p):
+    return (p[0], p[1], 1, p[0] * p[1] % FQ)
+
+
+def _ext_add(p, q):
+    """The same law in extended coordinates (X : Y : Z : T), T = XY / Z: no inversion per addition."""
+    x1, y1, z1, t1 = p
+    x2, y2, z2, t2 = q
+    a = x1 * x2 % FQ
+    b = y1 * y2 % FQ
+    c = COEFF_D * t1 % FQ * t2 % FQ
+    d = z1 * z2 % FQ
+    e = ((x1 + y1) * (x2 + y2) - a - b) % FQ
+    f, g, h = (d - c) % FQ, (d + c) % FQ, (b - COEFF_A * a) % FQ
+    return (e * f % FQ, g * h % FQ, f * g % FQ, e * h % FQ)
+
+
+def _batch_affine(points):
+    """Extended -> affine for a list of points with ONE modular inversion (prefix products)."""
+    prefix, acc = [], 1
+    for p in points:
+        prefix.append(acc)
+        acc = acc * p[2] % FQ
+    inv = pow(acc, -1, FQ)
+    out = [None] * len(points)
+    for i in range(len(points) - 1, -1, -1):
+        zi = inv * prefix[i] % FQ
+        inv = inv * points[i][2] % FQ
+        out[i] = (points[i][0] * zi % FQ, points[i][1] * zi % FQ)
+    return out
+
+
 def ed_neg(p):
     return ((-p[0]) % FQ, p[1])
 
 
 def ed_mul(k: int, p):
-    acc, base = IDENTITY, p
+    acc, base = (0, 1, 1, 0), _ext(p)
     k %= SUBGROUP_ORDER
     while k:
         if k & 1:
-            acc = ed_add(acc, base)
-        base = ed_add(base, base)
+            acc = _ext_add(acc, base)
+        base = _ext_add(base, base)
         k >>= 1
-    return acc
+    return _batch_affine([acc])[0]
 
 
 def ed_is_on_curve(p) -> bool:
@@ -135,16 +167,16 @@ class BabyJubjubShuffle:
 
     @classmethod
     def _segments(cls, base) -> list:
-        out, g = [], base
+        flat, g = [], _ext(base)
         for _ in range(cls.NUM_ITERATIONS):
-            seg, cur = [], g
+            cur = g
             for _ in range(N_SELECT_BITS):
-                seg.append(cur)
-                cur = ed_add(cur, g)
+                flat.append(cur)
+                cur = _ext_add(cur, g)
             for _ in range(N_SELECT_BITS):
-                g = ed_add(g, g)
-            out.append(seg)
-        return out
+                g = _ext_add(g, g)
+        aff = _batch_affine(flat)
+        return [aff[i:i + N_SELECT_BITS] for i in range(0, len(aff), N_SELECT_BITS)]
 
     @classmethod
     def crate_generators(cls) -> list:
@@ -177,16 +209,18 @@ class BabyJubjubShuffle:
             raise ValueError("r_bits must hold NUM_ITERATIONS entries")
         gens = cls.crate_generators()
         pks = pks if pks is not None else cls.crate_public_keys(pk)
-        c1, c2 = card.get_first(), card.get_second()
+        c1, c2 = _ext(card.get_first()), _ext(card.get_second())
         trace = RemarkTrace(n_round=cls.NUM_ITERATIONS)
+        chain = []
         for bits, gen, pkseg in zip(r_bits, gens, pks):
             j = int(bool(bits[0])) + 2 * int(bool(bits[1]))
-            if bits[2]:
-                c1, c2 = ed_add(c1, gen[j]), ed_add(c2, pkseg[j])
-            else:
-                c1, c2 = ed_add(c1, ed_neg(gen[j])), ed_add(c2, ed_neg(pkseg[j]))
+            g_, p_ = (gen[j], pkseg[j]) if bits[2] else (ed_neg(gen[j]), ed_neg(pkseg[j]))
+            c1, c2 = _ext_add(c1, _ext(g_)), _ext_add(c2, _ext(p_))
             trace.bits.append([int(bool(bits[0])), int(bool(bits[1])), 1 if bits[2] else FQ - 1])
-            trace.intermediate_values.append([c2[0], c2[1], c1[0], c1[1]])
+            chain += [c2, c1]
+        aff = _batch_affine(chain)
+        for i in range(0, len(aff), 2):
+            trace.intermediate_values.append([aff[i][0], aff[i][1], aff[i + 1][0], aff[i + 1][1]])
         trace.output = list(trace.intermediate_values[-1])
         return trace
 
@@ -239,6 +273,9 @@ class Permutation:
         assert all(sum(self.matrix[i][j] for i in range(n)) == 1 for j in range(n))
 
 
+_SEL_CODES = {0: 0, 1: 1, FQ - 1: 2}
+
+
 class CardVar(list):
     """constraint_system/shuffle/mod.rs:13-62: the 4 variable indices of a card, [second.x, second.y, first.x, first.y]."""
 
@@ -268,6 +305,7 @@ class ShuffleGates:
         self.shuffle_public_keys = None       # [round][4] -> (x, y, dxy)
         self.shuffle_generators = None
         self.shuffle_remark_constraints: list = []     # (first gate, [s1 list, s2 list, s3 list])
+        self._remark_sel_codes: list = []              # the same columns as indices into (0, 1, -1), or None for other values
 
     # ---- turbo/mod.rs:639-662
     def linear_combine(self, wires_in, q1: int, q2: int, q3: int, q4: int) -> int:
@@ -302,6 +340,8 @@ class ShuffleGates:
         if len(wiring_selectors) != N_WIRE_SELECTORS or any(len(x) != self.n_iteration_shuffle_scalar_mul for x in wiring_selectors):
             raise ValueError("one value per iteration and wire selector expected")
         self.shuffle_remark_constraints.append((self.size, [list(x) for x in wiring_selectors]))
+        codes = [[_SEL_CODES.get(v % FQ, -1) for v in x] for x in wiring_selectors]
+        self._remark_sel_codes.append(None if any(c < 0 for x in codes for c in x) else codes)
 
     def shuffle_remark_constraint_indices(self) -> list:
         return [i for i, _ in self.shuffle_remark_constraints]
