@@ -252,9 +252,24 @@ class TurboCS(ShuffleGates):
         cons, codes = self.shuffle_remark_constraints, self._remark_sel_codes
         if cons and all(c is not None for c in codes):            # remark traces: bits and signs only -> table lookup
             table = np.stack([_ZERO, _ONE, mont(-1)])
-            arr = np.asarray(codes, dtype=np.int64)               # (cards, 3, rounds)
+            arr = np.stack(codes)                                 # (cards, 3, rounds)
             return self._scatter_rows(lambda t: table[arr[:, t, :]], 3)
         return self._scatter_rows(lambda t: np.stack([mont_rows(sel[t]) for _, sel in cons]), 3)
+
+    def witness_selector_codes(self):
+        """The witness selectors as (3, n) int32 indices into the table (0, 1, -1), or None when some remark gate carries other
+        values: what the prover uploads instead of 3 n field elements."""
+        codes = self._remark_sel_codes
+        if not self.shuffle_remark_constraints or any(c is None for c in codes):
+            return None
+        firsts = np.asarray(self.shuffle_remark_constraint_indices(), dtype=np.int64)
+        rounds = self.n_iteration_shuffle_scalar_mul
+        rows = (firsts[:, None] + np.arange(rounds)[None, :]).reshape(-1)
+        arr = np.stack(codes)                                     # (cards, 3, rounds) int32
+        out = np.zeros((3, self.size), dtype=np.int32)
+        for t in range(3):
+            out[t, rows] = arr[:, t, :].reshape(-1)
+        return out
 
     def _table_selectors(self, table) -> np.ndarray:
         if not self.shuffle_remark_constraints:
@@ -976,8 +991,8 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     if wit.len != cs.num_vars:
         raise ParameterError("witness length != num_vars")
     if cs.public_vars_witness_indices:
-        rows = wit.t.view(-1, 4)[torch.tensor(cs.public_vars_witness_indices, device=dev)].cpu().numpy().view(np.uint64)
-        online_values = [unmont(r) for r in rows]
+        d_online = wit.t.view(-1, 4)[torch.tensor(cs.public_vars_witness_indices, device=dev)]
+        online_values = [unmont(r) for r in d_online.cpu().numpy().view(np.uint64)]
     else:
         online_values = []
     transcript_init_plonk(transcript, vp, online_values, P.root)
@@ -985,9 +1000,12 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     # 1. the PI polynomial (helpers.rs:111-131)
     pi = DevVec(n, dev)
     if online_values:
-        idx = list(cs.public_vars_constraint_indices)
-        for i in range(0, len(idx), ffi.SPARSE_MAX):
-            ffi.fr_add_sparse_device(pi.ptr, idx[i:i + ffi.SPARSE_MAX], mont_rows(online_values[i:i + ffi.SPARSE_MAX]))
+        # evals[row] = the public input constrained at that row (rows are distinct: one constant gate per prepare_pi_variable);
+        # the values never leave the device: a row scatter of the witness entries read above
+        rows_idx = ws.get("pi_rows")
+        if rows_idx is None or rows_idx.numel() != len(online_values):
+            rows_idx = ws["pi_rows"] = torch.tensor(list(vp.public_vars_constraint_indices), device=dev)
+        pi.t.view(-1, 4)[rows_idx] = d_online
         _ifft(pi.ptr, n, pi, scratch)
 
     coset = ws.get("coset")
@@ -1010,32 +1028,41 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     # the quotient round's coset evaluations of the wire polynomials depend on no challenge: they are enqueued behind the MSMs,
     # so the GPU computes them while the host waits for the commitments and hashes the transcript
 
+    def w_sel_coset_bufs():
+        if "w_sel_coset" not in ws:
+            ws["w_sel_coset"] = [DevVec(m, dev, zero=False) for _ in range(3)]
+        return ws["w_sel_coset"]
+
     def wire_cosets():
         if not multi_gpu and not quotient_by_cosets:
             for p, c in zip(w_polys, w_coset):
                 _coset_fft(p, m, k1, c, scratch)
+        if w_sel_polys:                                          # the witness selectors' too (`shuffle` feature set)
+            for p, c in zip(w_sel_polys, w_sel_coset_bufs()):
+                _coset_fft(p, m, k1, c, scratch)
 
-    if lagrange_pcs is not None:
-        lag = _lagrange_commit_scheme(pcs, lagrange_pcs, n, ws)
-        for i in range(N_WIRES_PER_GATE):
-            _set_blind_slots(ext, i * stride + n, w_blinds[i])
-        cm_w_vec = _commit_dev(lag, [_View(ext, i * stride, n + 2 * N_BLIND_SLOTS) for i in range(N_WIRES_PER_GATE)], overlap=wire_cosets)
-    else:
-        cm_w_vec = _commit_dev(pcs, w_polys, overlap=wire_cosets)
-    for cm in cm_w_vec:
-        transcript.append_commitment(cm)
     # 3. (`shuffle` feature set) witness-selector polynomials (prover.rs:177-191): the remark gates' bit / sign columns
-    # (compute_witness_selectors, turbo/mod.rs:171-191; zero on H without remark gates), hidden with 2 blinds each, committed
+    # (compute_witness_selectors, turbo/mod.rs:171-191; zero on H without remark gates), hidden with 2 blinds each.  They depend on
+    # no challenge and the RNG draws keep the reference's order (wires, then selectors), so they are committed in the same batch
+    # as the wires when both go to the same SRS.
     shuffle = P.q_ecc_poly is not None
-    w_sel_polys, cm_w_sel_vec = [], None
+    w_sel_polys, w_sel_blinds, cm_w_sel_vec = [], [], None
     if shuffle:
         has_remark = bool(cs.shuffle_remark_constraints)
-        w_sel_blinds = []
         sel_ev = DevVec(3 * stride, dev)
         if has_remark:
-            sel_host = cs.compute_witness_selectors()
-            for i in range(3):
-                sel_ev.t[4 * i * stride: 4 * (i * stride + n)].copy_(torch.from_numpy(sel_host[i].view(np.int64).reshape(-1)))
+            codes = cs.witness_selector_codes()
+            if codes is not None:          # bits and signs: upload 3 n small indices, expand against (0, 1, -1) on the device
+                table = ws.get("w_sel_table")
+                if table is None:
+                    table = ws["w_sel_table"] = DevVec.from_numpy(np.stack([_ZERO, _ONE, mont(-1)]), dev)
+                d_codes = torch.from_numpy(codes).to(dev)
+                for i in range(3):
+                    ffi.fr_gather_device(table.ptr, d_codes.data_ptr() + 4 * i * n, n, sel_ev.at(i * stride))
+            else:
+                sel_host = cs.compute_witness_selectors()
+                for i in range(3):
+                    sel_ev.t[4 * i * stride: 4 * (i * stride + n)].copy_(torch.from_numpy(sel_host[i].view(np.int64).reshape(-1)))
         for i in range(3):
             if has_remark:
                 f = DevVec(cap, dev, length=n)
@@ -1044,14 +1071,27 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
                 f = DevVec(cap, dev, length=1)
             w_sel_blinds.append(hide_polynomial(prng, f, 2, n))
             w_sel_polys.append(f)
-        if lagrange_all:
-            for i in range(3):
-                _set_blind_slots(sel_ev, i * stride + n, w_sel_blinds[i])
-            cm_w_sel_vec = _commit_dev(lag, [_View(sel_ev, i * stride, n + 2 * N_BLIND_SLOTS) for i in range(3)])
-        else:
-            cm_w_sel_vec = _commit_dev(pcs, w_sel_polys)
-        for cm in cm_w_sel_vec:
-            transcript.append_commitment(cm)
+    if lagrange_pcs is not None:
+        lag = _lagrange_commit_scheme(pcs, lagrange_pcs, n, ws)
+        for i in range(N_WIRES_PER_GATE):
+            _set_blind_slots(ext, i * stride + n, w_blinds[i])
+        wire_vecs, wire_scheme = [_View(ext, i * stride, n + 2 * N_BLIND_SLOTS) for i in range(N_WIRES_PER_GATE)], lag
+    else:
+        wire_vecs, wire_scheme = w_polys, pcs
+    sel_vecs, sel_scheme = w_sel_polys, pcs
+    if shuffle and lagrange_all:
+        for i in range(3):
+            _set_blind_slots(sel_ev, i * stride + n, w_sel_blinds[i])
+        sel_vecs, sel_scheme = [_View(sel_ev, i * stride, n + 2 * N_BLIND_SLOTS) for i in range(3)], lag
+    if shuffle and sel_scheme is wire_scheme:
+        cms = _commit_dev(wire_scheme, wire_vecs + sel_vecs, overlap=wire_cosets)
+        cm_w_vec, cm_w_sel_vec = cms[:N_WIRES_PER_GATE], cms[N_WIRES_PER_GATE:]
+    else:
+        cm_w_vec = _commit_dev(wire_scheme, wire_vecs, overlap=wire_cosets)
+        if shuffle:
+            cm_w_sel_vec = _commit_dev(sel_scheme, sel_vecs)
+    for cm in cm_w_vec + (cm_w_sel_vec or []):
+        transcript.append_commitment(cm)
     mark("round1_wires")
 
     # 4. beta, gamma
@@ -1114,11 +1154,7 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         pi_coset.t.zero_()
     shuffle_args = None
     if shuffle:
-        w_sel_coset = ws.get("w_sel_coset")
-        if w_sel_coset is None:
-            w_sel_coset = ws["w_sel_coset"] = [DevVec(m, dev, zero=False) for _ in range(3)]
-        for p, c in zip(w_sel_polys, w_sel_coset):
-            _coset_fft(p, m, k1, c, scratch)
+        w_sel_coset = w_sel_coset_bufs()          # filled behind the round-1 commitments (wire_cosets)
         shuffle_args = {"w_sel": [c.ptr for c in w_sel_coset], "q_ecc": P.q_ecc_coset_eval.ptr,
                         "pk": [c.ptr for c in P.q_shuffle_public_key_coset_evals], "gen": [c.ptr for c in P.q_shuffle_generator_coset_evals],
                         "edwards_a": mont(vp.edwards_a)}

@@ -20,6 +20,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+import numpy as np
+
 from .rng import FR_MODULUS as FQ      # the base field of Baby Jubjub is BN254's Fr
 
 COEFF_A = 1
@@ -341,7 +343,7 @@ class ShuffleGates:
             raise ValueError("one value per iteration and wire selector expected")
         self.shuffle_remark_constraints.append((self.size, [list(x) for x in wiring_selectors]))
         codes = [[_SEL_CODES.get(v % FQ, -1) for v in x] for x in wiring_selectors]
-        self._remark_sel_codes.append(None if any(c < 0 for x in codes for c in x) else codes)
+        self._remark_sel_codes.append(None if any(c < 0 for x in codes for c in x) else np.asarray(codes, dtype=np.int32))
 
     def shuffle_remark_constraint_indices(self) -> list:
         return [i for i, _ in self.shuffle_remark_constraints]
