@@ -1,0 +1,65 @@
+"""One zshuffle-52 proof (production route: everything over the Lagrange SRS) for a kernel launch list and a host profile.
+
+    python scripts/gpu_zshuffle_profile.py host      # cProfile of 10 proofs (where does the host spend the proof's wall time?)
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file launches.csv \
+        python scripts/gpu_zshuffle_profile.py ncu   # per-kernel durations of ONE proof (cudaProfilerStart/Stop around it)
+"""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+
+from uzkge_b200 import KZGCommitmentSchemeBN254, ffi, plonk
+from uzkge_b200 import shuffle as sh
+from uzkge_b200.rng import ChaChaRng
+from uzkge_b200.transcript import Transcript
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "host"
+ffi.init(0)
+if os.environ.get("MSM_LANES"):
+    ffi.configure("msm_lanes", int(os.environ["MSM_LANES"]))
+dev = torch.device("cuda", 0)
+tau = plonk.mont(0x1234567890ABCDEF1234567890ABCDEF)
+prng = ChaChaRng.from_seed(bytes(32))
+apk = sh.rand_point(prng)
+cs, _ = sh.build_cs(plonk.TurboCS(), prng, apk, [sh.Ciphertext.rand(prng) for _ in range(52)])
+n = cs.size
+pcs, lagrange = KZGCommitmentSchemeBN254.new(n + 2, tau), KZGCommitmentSchemeBN254.new_lagrange(n, tau)
+params = plonk.indexer(cs, pcs, shuffle=True, lagrange_pcs=lagrange)
+plonk.refresh_prover_params_public_key(cs, params, pcs, apk, lagrange_pcs=lagrange)
+wit = plonk.DevVec.from_numpy(cs.get_witness_array(), dev)
+
+
+def prove():
+    tr = Transcript(b"Plonk shuffle Proof")
+    tr.append_u64(52)
+    return plonk.prover(ChaChaRng.from_seed(bytes(32)), tr, pcs, cs, params, wit, lagrange_pcs=lagrange, lagrange_all=True)
+
+
+for _ in range(3):
+    prove()
+torch.cuda.synchronize()
+if mode == "ncu":
+    torch.cuda.cudart().cudaProfilerStart()
+    prove()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+else:
+    t0 = time.perf_counter()
+    for _ in range(10):
+        prove()
+    torch.cuda.synchronize()
+    print("ms per proof", (time.perf_counter() - t0) * 100)
+    if mode == "time":
+        sys.exit(0)
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(10):
+        prove()
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(30)

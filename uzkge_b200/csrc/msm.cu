@@ -668,11 +668,14 @@ int MsmEngine::stage_sort(MsmSrs* s, MsmWork& w, size_t base_offset, const fe* c
     UZ_CUDA_TRY(cudaMemsetAsync(w.large_list, 0, 4, st));
     g_prof.mark(prof, MSM_PH_SORT, st);
 
-    // lanes per bucket: ~48 entries per lane, but at least enough groups to fill every SM
+    // lanes per bucket: at most ~80 entries per lane; and for small problems (the prover's batches of 2^12..2^18-point MSMs), where
+    // one wave of long per-lane chains is latency-bound, more lanes until about 2.75 x the resident threads are in flight,
+    // keeping >= 5 entries per lane.  Measured with scripts/gpu_msm_lanes.py: 5 x 2^14: 1224 -> 623 us, 8 x 2^14: 1326 -> 846 us,
+    // 2^18: 1184 -> 1034 us; 2^20 and up keep their lane count.
     const double mean = (double)m / (double)(nb_all - k);
     uint32_t g = 1;
     while (g < 32 && mean / (g * 2) >= 40.0) g *= 2;
-    while (g < 32 && (uint64_t)nb_all * g * 2 <= (uint64_t)sm_count_ * 512) g *= 2;
+    while (g < 32 && (uint64_t)nb_all * g * 2 <= (uint64_t)sm_count_ * 1408 && mean / (g * 2) >= 5.0) g *= 2;
     if (force_lanes_) g = force_lanes_;
     // segments above the threshold are split into warp slices (msm_large_*)
     uint32_t thr = (uint32_t)(mean * 8.0);
