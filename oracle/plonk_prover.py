@@ -206,6 +206,9 @@ class TurboCS:
         self.rounds = 0                 # n_iteration_shuffle_scalar_mul
         self.pk_table = self.gen_table = None      # [round][4] -> (x, y, dxy)
         self.remark = []                # shuffle_remark_constraint_indices: (first row, [s1 column, s2 column, s3 column])
+        self.anemoi_constraints_indices = []          # first rows of the 14-row Anemoi permutations
+        self.anemoi_generator = self.anemoi_generator_inv = 0
+        self.anemoi_prk = None          # (x[14][2], y[14][2]): the preprocessed round keys
         self.insert_constant_gate(0, 0)
         self.insert_constant_gate(1, 1)
 
@@ -370,6 +373,15 @@ class TurboCS:
             q[row] = 1
         return q
 
+    def compute_anemoi_jive_selectors(self):
+        """turbo/mod.rs:285-304."""
+        polys = [[0] * self.size for _ in range(4)]
+        for first in self.anemoi_constraints_indices:
+            for j in range(14):
+                polys[0][first + j], polys[1][first + j] = self.anemoi_prk[0][j]
+                polys[2][first + j], polys[3][first + j] = self.anemoi_prk[1][j]
+        return polys
+
     def check_remark_equations(self, witness):
         """The four remark equations of verify_witness (turbo/mod.rs:1100-1330) on every remark row: the twisted Edwards addition
         of +-(the selected multiple of pk / G) to the running pair of points, written without divisions."""
@@ -492,7 +504,7 @@ def indexer(cs: TurboCS, pcs: Kzg, shuffle: bool = False):
     for i in cs.boolean_constraint_indices:
         qb[i] = 1
     P["qb_poly"], P["qb_coset"] = pre(qb)
-    P["q_prk_polys"], P["q_prk_coset"] = zip(*[pre([0] * n) for _ in range(4)])   # no Anemoi gates in the synthetic circuits
+    P["q_prk_polys"], P["q_prk_coset"] = zip(*[pre(e) for e in cs.compute_anemoi_jive_selectors()])      # indexer.rs:385-412
     lagrange_constants = []
     for ci in cs.public_vars_constraint_indices:
         inv = 1
@@ -503,7 +515,7 @@ def indexer(cs: TurboCS, pcs: Kzg, shuffle: bool = False):
     P["vp"] = {
         "cm_q_vec": [pcs.commit(p) for p in P["q_polys"]], "cm_s_vec": [pcs.commit(p) for p in P["s_polys"]],
         "cm_qb": pcs.commit(P["qb_poly"]), "cm_prk_vec": [pcs.commit(p) for p in P["q_prk_polys"]],
-        "anemoi_generator": 0, "anemoi_generator_inv": 0, "k": k, "cs_size": n,
+        "anemoi_generator": cs.anemoi_generator, "anemoi_generator_inv": cs.anemoi_generator_inv, "k": k, "cs_size": n,
         "public_vars_constraint_indices": list(cs.public_vars_constraint_indices), "lagrange_constants": lagrange_constants,
     }
     P["shuffle"] = shuffle

@@ -28,7 +28,8 @@ prng = ChaChaRng.from_seed(bytes(32))
 apk = sh.rand_point(prng)
 cs, _ = sh.build_cs(plonk.TurboCS(), prng, apk, [sh.Ciphertext.rand(prng) for _ in range(52)])
 n = cs.size
-pcs, lagrange = KZGCommitmentSchemeBN254.new(n + 2, tau), KZGCommitmentSchemeBN254.new_lagrange(n, tau)
+wb = int(os.environ.get("WINDOW_BITS", "0"))
+pcs, lagrange = KZGCommitmentSchemeBN254.new(n + 2, tau, wb), KZGCommitmentSchemeBN254.new_lagrange(n, tau, wb)
 params = plonk.indexer(cs, pcs, shuffle=True, lagrange_pcs=lagrange)
 plonk.refresh_prover_params_public_key(cs, params, pcs, apk, lagrange_pcs=lagrange)
 wit = plonk.DevVec.from_numpy(cs.get_witness_array(), dev)

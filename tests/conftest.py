@@ -76,6 +76,11 @@ def srs_padding_head(oc):
 
 
 @pytest.fixture(scope="session")
+def lagrange_srs_8192(oc):
+    return _load_points_mont("lagrange_srs_8192.npy", oc)
+
+
+@pytest.fixture(scope="session")
 def srs_padding_tail(oc):
     """tau^n, tau^(n+1), tau^(n+2) for n = 4096, 8192, 16384 (rows 0-2, 3-5, 6-8): srs-padding.bin[2051..2060)."""
     return _load_points_mont("srs_padding_tail.npy", oc)

@@ -75,3 +75,25 @@ def build_shuffle_circuit(cs, inp):
         cs.prepare_pi_card_variable(cv)
     cs.pad()
     return cs, out
+
+
+def transplant(cs):
+    """A frozen circuit of the product's TurboCS (uzkge_b200/plonk.py) as the restatement's TurboCS (oracle/plonk_prover.py): same
+    selectors, wiring, witness and gate annotations.  Used where the circuit builder is pinned by reference data (the bundled
+    verifier keys) rather than by a second implementation."""
+    from oracle import plonk_prover as pp
+
+    o = pp.TurboCS()
+    n = cs.size
+    tab = cs._sel_table
+    o.selectors = [[tab[int(c)] for c in cs._sel_codes[j]] for j in range(9)]
+    o.wiring = [[int(v) for v in cs.wiring[j]] for j in range(5)]
+    o.size, o.num_vars, o.witness = n, cs.num_vars, list(cs.witness)
+    o.public_vars_constraint_indices = list(cs.public_vars_constraint_indices)
+    o.public_vars_witness_indices = list(cs.public_vars_witness_indices)
+    o.boolean_constraint_indices = list(cs.boolean_constraint_indices)
+    o.anemoi_constraints_indices = list(cs.anemoi_constraints_indices)
+    o.anemoi_generator, o.anemoi_generator_inv = cs.anemoi_generator, cs.anemoi_generator_inv
+    if cs.anemoi_preprocessed_round_keys_x is not None:
+        o.anemoi_prk = (cs.anemoi_preprocessed_round_keys_x, cs.anemoi_preprocessed_round_keys_y)
+    return o

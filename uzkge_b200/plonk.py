@@ -29,6 +29,7 @@ from . import ffi
 from .errors import DegreeError, ParameterError, UzkgeError
 from .poly_commit import FR_MODULUS, KZGCommitment, KZGCommitmentSchemeBN254
 from .rng import ChaChaRng, choose_ks, fr_rand
+from .anemoi import N_ANEMOI_ROUNDS, AnemoiGates
 from .shuffle import ShuffleGates
 from .transcript import Transcript, init_pcs_batch_eval_transcript, transcript_init_plonk
 
@@ -93,10 +94,11 @@ def _dev():
 
 
 # ---------------------------------------------------------------------------------------------- TurboCS
-class TurboCS(ShuffleGates):
+class TurboCS(ShuffleGates, AnemoiGates):
     """constraint_system/turbo/mod.rs.  Gates are appended one by one (Python lists) or in bulk (`synthetic`); `pad()` freezes
     the circuit into numpy arrays: selectors (9, n, 4) Montgomery limbs, wiring (5, n) uint32.  The shuffle gadgets
-    (constraint_system/shuffle/*.rs) come from shuffle.ShuffleGates."""
+    (constraint_system/shuffle/*.rs) come from shuffle.ShuffleGates, the Anemoi ones (constraint_system/anemoi/mod.rs) from
+    anemoi.AnemoiGates."""
 
     def __init__(self):
         self._sel = [[] for _ in range(N_SELECTORS)]     # small codes: index into _sel_values
@@ -114,6 +116,7 @@ class TurboCS(ShuffleGates):
         self.wiring: np.ndarray | None = None
         self.verifier_only = False
         self._init_shuffle()
+        self._init_anemoi()
         self.insert_constant_gate(self.zero_var(), 0)
         self.insert_constant_gate(self.one_var(), 1)
 
@@ -213,6 +216,12 @@ class TurboCS(ShuffleGates):
         self.insert_mul_gate(left_var, right_var, out)
         return out
 
+    def select(self, var0: int, var1: int, bit: int) -> int:
+        """turbo/mod.rs:767-796: var_bit = (1 - bit) var0 + bit var1; wires (bit, var0, bit, var1), q2 = qm2 = qo = 1, qm1 = -1."""
+        out = self.new_variable(self.witness[var0] if self.witness[bit] == 0 else self.witness[var1])
+        self._push_gate((0, 1, 0, 0), (-1, 1), 0, 0, 1, [bit, var0, bit, var1, out])
+        return out
+
     def equal(self, left_var: int, right_var: int) -> None:
         self.insert_sub_gate(left_var, right_var, self.zero_var())
 
@@ -256,6 +265,17 @@ class TurboCS(ShuffleGates):
             return self._scatter_rows(lambda t: table[arr[:, t, :]], 3)
         return self._scatter_rows(lambda t: np.stack([mont_rows(sel[t]) for _, sel in cons]), 3)
 
+    def compute_anemoi_jive_selectors(self) -> np.ndarray:
+        """turbo/mod.rs:285-304 as (4, n, 4) Montgomery limbs."""
+        out = np.zeros((4, self.size, 4), dtype=np.uint64)
+        firsts = np.asarray(self.anemoi_constraints_indices, dtype=np.int64)
+        if len(firsts):
+            rows = (firsts[:, None] + np.arange(N_ANEMOI_ROUNDS)[None, :]).reshape(-1)
+            kx, ky = self.anemoi_preprocessed_round_keys_x, self.anemoi_preprocessed_round_keys_y
+            for t, col in enumerate(([k[0] for k in kx], [k[1] for k in kx], [k[0] for k in ky], [k[1] for k in ky])):
+                out[t, rows] = np.broadcast_to(mont_rows(col), (len(firsts), N_ANEMOI_ROUNDS, 4)).reshape(-1, 4)
+        return out
+
     def witness_selector_codes(self):
         """The witness selectors as (3, n) int32 indices into the table (0, 1, -1), or None when some remark gate carries other
         values: what the prover uploads instead of 3 n field elements."""
@@ -286,8 +306,7 @@ class TurboCS(ShuffleGates):
         return self._scatter_rows(lambda t: mont_rows([1] * self.n_iteration_shuffle_scalar_mul), 1)[0]
 
     def verify_witness(self, witness, online_vars) -> None:
-        """turbo/mod.rs:1041-1396 for the supported gate set (no Anemoi gates): the remark equations, the gate equation with the
-        public inputs, the boolean rows.  Raises UzkgeError naming the first failing row.  Host-side check, Python integers."""
+        """turbo/mod.rs:1041-1396: the Anemoi and remark equations, the gate equation with the public inputs, the boolean rows.  Raises UzkgeError naming the first failing row.  Host-side check, Python integers."""
         if self.selectors is None:
             raise UzkgeError("call cs.pad() before verify_witness")
         if len(witness) != self.num_vars:
@@ -295,6 +314,9 @@ class TurboCS(ShuffleGates):
         if not (len(online_vars) == len(self.public_vars_witness_indices) == len(self.public_vars_constraint_indices)):
             raise UzkgeError("wrong number of online variables")
         R, wir = FR_MODULUS, self.wiring
+        err = self.check_anemoi_rows(witness, lambda j, row: int(wir[j, row]))
+        if err:
+            raise UzkgeError(err)
         a_ed = self.edwards_a
         for first, sel in self.shuffle_remark_constraints:
             for r in range(self.n_iteration_shuffle_scalar_mul):
@@ -601,7 +623,7 @@ def _lagrange_commit_scheme(pcs, lagrange_pcs, n: int, ws: dict):
     mono = pcs.public_parameter_group_1
     idx = list(range(N_BLIND_SLOTS)) + [n + i for i in range(N_BLIND_SLOTS)]
     pts = np.concatenate([lagrange_pcs.public_parameter_group_1[:n], mono[idx]])
-    scheme = KZGCommitmentSchemeBN254(pts)
+    scheme = KZGCommitmentSchemeBN254(pts, getattr(lagrange_pcs, "window_bits", 0))
     ws["lagrange_scheme"] = (lagrange_pcs, scheme)
     return scheme
 
@@ -736,7 +758,7 @@ def indexer(cs: TurboCS, pcs, shuffle: bool = False, lagrange_pcs=None) -> Plonk
     for ci in cs.public_vars_constraint_indices:
         # prod_{i != j} (w^j - w^i) = n * w^{-j}  (derivative of X^n - 1 at w^j)
         lagrange_constants.append(pow(n * pow(root, -ci, FR_MODULUS) % FR_MODULUS, -1, FR_MODULUS))
-    # Step 5: boolean constraints; Step 6: Anemoi round keys (none in the supported gate set: zero polynomials)
+    # Step 5: boolean constraints; Step 6: Anemoi round keys (zero polynomials without Anemoi gates)
     zero_poly, zero_coset = DevVec(n, dev), DevVec(m, dev)
     if cs.boolean_constraint_indices:
         qb = DevVec(n, dev)
@@ -746,14 +768,21 @@ def indexer(cs: TurboCS, pcs, shuffle: bool = False, lagrange_pcs=None) -> Plonk
         qb_poly, qb_coset = preprocess(qb)
     else:
         qb_poly, qb_coset = zero_poly, zero_coset
-    q_prk_polys, q_prk_coset = [zero_poly] * 4, [zero_coset] * 4
+    if cs.anemoi_constraints_indices:      # indexer.rs:385-412: the preprocessed round keys on the rows of the Anemoi gates
+        prk_evals = cs.compute_anemoi_jive_selectors()
+        prk = [preprocess(DevVec.from_numpy(prk_evals[i], dev)) for i in range(4)]
+        q_prk_polys, q_prk_coset = [c for c, _ in prk], [e for _, e in prk]
+    else:
+        q_prk_polys, q_prk_coset = [zero_poly] * 4, [zero_coset] * 4
 
     commit_src[id(zero_poly)] = zero_poly
-    cms = commit_all(q_polys + s_polys + [qb_poly, zero_poly])
-    identity = cms[-1]
+    n_fixed = N_SELECTORS + N_WIRES_PER_GATE
+    cms = commit_all(q_polys + s_polys + [qb_poly, zero_poly] + (q_prk_polys if cs.anemoi_constraints_indices else []))
+    identity = cms[n_fixed + 1]
     vp = PlonkVerifierParams(
-        cm_q_vec=cms[:N_SELECTORS], cm_s_vec=cms[N_SELECTORS:N_SELECTORS + N_WIRES_PER_GATE], cm_qb=cms[-2], cm_prk_vec=[identity] * 4,
-        anemoi_generator=0, anemoi_generator_inv=0, k=k, cs_size=n,
+        cm_q_vec=cms[:N_SELECTORS], cm_s_vec=cms[N_SELECTORS:n_fixed], cm_qb=cms[n_fixed],
+        cm_prk_vec=cms[n_fixed + 2:] if cs.anemoi_constraints_indices else [identity] * 4,
+        anemoi_generator=cs.anemoi_generator, anemoi_generator_inv=cs.anemoi_generator_inv, k=k, cs_size=n,
         public_vars_constraint_indices=list(cs.public_vars_constraint_indices), lagrange_constants=lagrange_constants)
     d_wiring = torch.from_numpy(cs.wiring.reshape(-1).view(np.int32)).to(dev)
     extra = {}

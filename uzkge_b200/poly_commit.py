@@ -224,6 +224,7 @@ class KZGCommitmentSchemeBN254:
 
     def __init__(self, public_parameter_group_1, window_bits: int = 0):
         self.public_parameter_group_1 = ffi.as_u64(public_parameter_group_1, 8)
+        self.window_bits = window_bits          # as requested (0 = the engine's rule); info() reports the one in use
         self._handle = ffi.srs_upload(self.public_parameter_group_1, window_bits)
 
     @classmethod
