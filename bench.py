@@ -277,42 +277,35 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
     return out
 
 
-def zshuffle_proofs(dev, K: int, W: int, cards: int = 52) -> dict:
-    """BASELINE.json configs[0]: the zshuffle circuit itself (shuffle/src/build_cs.rs:26-56: `cards` remark gadgets + the permutation
-    gadget, 2^14 gates for 52 cards) built by the host mirror (uzkge_b200/shuffle.py), indexed with the `shuffle` feature set, a joint
-    key loaded with refresh_prover_params_public_key, and proved the way the reference's production path does: every commitment
-    over the Lagrange SRS (lagrange_all).  The SRS is synthetic (known tau) -- the parity tests use the bundled production
-    parameters.  A step = one `prover` call; building the circuit (host, Python integers) is reported beside it, not inside."""
+def _app_circuit_proofs(dev, K: int, W: int, name: str, cs, build_s: float, shuffle: bool, label: bytes, count: int, apk=None) -> dict:
+    """One of the reference's application circuits through indexer_with_lagrange / prover_with_lagrange the way the production path
+    does: every commitment over the Lagrange SRS (lagrange_all).  The SRS is synthetic (known tau) -- the parity tests use the
+    bundled production parameters.  A step = one `prover` call; building the circuit (host, Python integers) is reported beside it."""
     import torch
 
     from uzkge_b200 import KZGCommitmentSchemeBN254, ffi, plonk
-    from uzkge_b200 import shuffle as sh
     from uzkge_b200.rng import ChaChaRng
     from uzkge_b200.transcript import Transcript
 
     tau = plonk.mont(0x1234567890ABCDEF1234567890ABCDEF)
-    prng = ChaChaRng.from_seed(bytes(32))
-    t0 = time.perf_counter()
-    apk = sh.rand_point(prng)
-    deck = [sh.Ciphertext.rand(prng) for _ in range(cards)]
-    cs, _ = sh.build_cs(plonk.TurboCS(), prng, apk, deck)
-    build_s = time.perf_counter() - t0
     n = cs.size
     t0 = time.perf_counter()
     pcs, lagrange = KZGCommitmentSchemeBN254.new(n + 2, tau), KZGCommitmentSchemeBN254.new_lagrange(n, tau)
-    params = plonk.indexer(cs, pcs, shuffle=True, lagrange_pcs=lagrange)
+    params = plonk.indexer(cs, pcs, shuffle=shuffle, lagrange_pcs=lagrange)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    plonk.refresh_prover_params_public_key(cs, params, pcs, apk, lagrange_pcs=lagrange)
-    refresh_ms = (time.perf_counter() - t0) * 1e3
+    refresh_ms = None
+    if apk is not None:
+        t0 = time.perf_counter()
+        plonk.refresh_prover_params_public_key(cs, params, pcs, apk, lagrange_pcs=lagrange)
+        refresh_ms = (time.perf_counter() - t0) * 1e3
     wit_pinned = ffi.PinnedArray(cs.get_witness_array().shape)
     wit_pinned.array[:] = cs.get_witness_array()
     wit_host = wit_pinned.array
 
     def prove(w, timings=None):
-        tr = Transcript(b"Plonk shuffle Proof")
-        tr.append_u64(cards)
+        tr = Transcript(label)
+        tr.append_u64(count)
         return plonk.prover(ChaChaRng.from_seed(bytes(32)), tr, pcs, cs, params, w, timings=timings, lagrange_pcs=lagrange, lagrange_all=True)
 
     wit = plonk.DevVec.from_numpy(wit_host, dev)
@@ -332,13 +325,16 @@ def zshuffle_proofs(dev, K: int, W: int, cards: int = 52) -> dict:
         proof2 = prove(wit_host)
     torch.cuda.synchronize()
     dt_e2e = (time.perf_counter() - t0) / K
+    n_msm, n_sel = (16, 3) if shuffle else (13, 0)
     res = {
-        "circuit": f"zshuffle-{cards}", "log_n": n.bit_length() - 1, "n_gpus": 1, "mode": "single", "witness": "remark + permutation gadgets",
-        "lagrange_commitments": True, "lagrange_all": True, "feature_set": "shuffle", "proof_bytes": len(proof.to_bytes_be()),
+        "circuit": name, "log_n": n.bit_length() - 1, "n_gpus": 1, "mode": "single", "witness": "the application's gadgets",
+        "lagrange_commitments": True, "lagrange_all": True, "feature_set": "shuffle" if shuffle else "default",
+        "proof_bytes": len(proof.to_bytes_be()), "public_inputs": len(cs.public_vars_constraint_indices),
         "prove_ms": dt * 1e3, "proofs_per_s": 1 / dt, "e2e_prove_ms": dt_e2e * 1e3, "e2e_proofs_per_s": 1 / dt_e2e,
-        "h2d_bytes_per_step": int(wit_host.nbytes) + 3 * n * 32, "d2h_bytes_per_step": 16 * 96 + 20 * 32, "steps": K,
+        "h2d_bytes_per_step": int(wit_host.nbytes) + n_sel * n * 4, "d2h_bytes_per_step": n_msm * 96 + (20 if shuffle else 16) * 32, "steps": K,
         "launches_per_proof": int(launches), "rounds_ms": {k: v / K for k, v in timings.items()},
-        "ops_per_proof": {"msm": 16, "ifft_n": 9, "fft_n": 7, "coset_fft_6n": 9, "coset_ifft_6n": 1, "quotient_points": int(params.m), "evals": 20},
+        "ops_per_proof": {"msm": n_msm, "ifft_n": 6 + n_sel, "fft_n": 7, "coset_fft_6n": 6 + n_sel, "coset_ifft_6n": 1,
+                          "quotient_points": int(params.m), "evals": 20 if shuffle else 16},
         "build_cs_host_s": build_s, "setup_s": setup_s, "refresh_public_key_ms": refresh_ms,
         "deterministic": proof.to_bytes_be() == proof2.to_bytes_be(),
     }
@@ -347,6 +343,35 @@ def zshuffle_proofs(dev, K: int, W: int, cards: int = 52) -> dict:
     del wit_host
     wit_pinned.free()
     return res
+
+
+def zshuffle_proofs(dev, K: int, W: int, cards: int = 52) -> dict:
+    """BASELINE.json configs[0]: the zshuffle circuit itself (shuffle/src/build_cs.rs:26-56: `cards` remark gadgets + the permutation
+    gadget, 2^14 gates for 52 cards) built by the host mirror (uzkge_b200/shuffle.py), `shuffle` feature set, a joint key loaded
+    with refresh_prover_params_public_key."""
+    from uzkge_b200 import plonk
+    from uzkge_b200 import shuffle as sh
+    from uzkge_b200.rng import ChaChaRng
+
+    prng = ChaChaRng.from_seed(bytes(32))
+    t0 = time.perf_counter()
+    apk = sh.rand_point(prng)
+    deck = [sh.Ciphertext.rand(prng) for _ in range(cards)]
+    cs, _ = sh.build_cs(plonk.TurboCS(), prng, apk, deck)
+    return _app_circuit_proofs(dev, K, W, f"zshuffle-{cards}", cs, time.perf_counter() - t0, True, b"Plonk shuffle Proof", cards, apk)
+
+
+def zmatchmaking_proofs(dev, K: int, W: int) -> dict:
+    """BASELINE.json's zmatchmaking circuit (matchmaking/src/build_cs.rs:26-67: N = 50 inputs, 18 Anemoi permutations, 2^13 gates)
+    built by uzkge_b200/matchmaking.py, default feature set (the crate's own Cargo.toml does not enable `shuffle`)."""
+    from uzkge_b200 import matchmaking as mm
+    from uzkge_b200 import plonk
+    from uzkge_b200.rng import ChaChaRng, fr_rand
+
+    prng = ChaChaRng.from_seed(bytes(32))
+    t0 = time.perf_counter()
+    cs, _ = mm.build_cs(plonk.TurboCS(), list(range(1, mm.N + 1)), fr_rand(prng), fr_rand(prng))
+    return _app_circuit_proofs(dev, K, W, "zmatchmaking", cs, time.perf_counter() - t0, False, mm.PLONK_PROOF_TRANSCRIPT, mm.N)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -358,7 +383,7 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="all", choices=["all", "both", "msm", "ntt", "plonk"])
     ap.add_argument("--plonk-logs", default="14,22", help="log2 circuit sizes of the synthetic TurboPlonK proofs")
-    ap.add_argument("--no-zshuffle", action="store_true", help="skip the zshuffle-52 circuit of the PlonK block")
+    ap.add_argument("--no-zshuffle", action="store_true", help="skip the application circuits (zmatchmaking, zshuffle-52) of the PlonK block")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -670,6 +695,7 @@ def main() -> int:
     if args.workload in ("all", "plonk"):
         results["plonk"] = plonk_proofs(args, dev, K, W, rank, world, barrier, max_over_ranks)
         if world == 1 and not args.no_zshuffle:
+            results["plonk"]["sizes"].append(zmatchmaking_proofs(dev, K, W))
             results["plonk"]["sizes"].append(zshuffle_proofs(dev, K, W))
 
     t_region1 = time.time()

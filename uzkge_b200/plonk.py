@@ -860,8 +860,9 @@ def refresh_prover_params_public_key(cs: TurboCS, prover_params: PlonkProverPara
 class CosetParams:
     """Everything the quotient map needs on coset j, built from the COEFFICIENT forms of the preprocessed polynomials."""
 
-    def __init__(self, q_polys, s_polys, qb_poly, q_prk_polys, k, n: int, j: int, dev):
+    def __init__(self, q_polys, s_polys, qb_poly, q_prk_polys, k, n: int, j: int, dev, anemoi=(0, 0)):
         m = 6 * n
+        self.anemoi = (mont(anemoi[0]), mont(anemoi[1]))      # generator and its inverse (quotient terms 8-11)
         root_m, root_n = _root(m), _root(n)
         self.n, self.j = n, j
         self.g = k[1] * pow(root_m, j, FR_MODULUS) % FR_MODULUS
@@ -916,7 +917,7 @@ class CosetParams:
         ffi.plonk_quotient_fr_device(
             [e.ptr for e in self.evals[:5]], [c.ptr for c in self.q], self.evals[6].ptr, self.evals[5].ptr, [c.ptr for c in self.s],
             self.coset_quotient.ptr, self.l1.ptr, self.qb.ptr, [c.ptr for c in self.q_prk], mont_rows(k), mont(alpha), mont(beta),
-            mont(gamma), mont(0), mont(0), mont_rows([self.z_h_inv]), self.n, 1, out.ptr)
+            mont(gamma), self.anemoi[0], self.anemoi[1], mont_rows([self.z_h_inv]), self.n, 1, out.ptr)
 
 
 def interleave_cosets(t_cosets: DevVec, n: int, out: DevVec, idx_cache: dict) -> None:
@@ -1154,6 +1155,7 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     # over GPUs: by coset from 3 GPUs on (measured at 2^22: 2 GPUs 142 ms by coset vs 137 ms with only the six transforms
     # distributed; 8 GPUs 70 ms vs 87 ms)
     dist_cosets = hasattr(pcs, "quotient_by_cosets") and getattr(pcs, "world", 1) >= 3
+    dist_cosets = dist_cosets and not vp.anemoi_generator      # the distributed setup does not carry the Anemoi constants
     by_cosets = (quotient_by_cosets or dist_cosets) and P.factor == 6 and P.q_ecc_poly is None
     if by_cosets:
         for p in w_polys + [z_poly]:
@@ -1166,7 +1168,8 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         else:
             cps = ws.get("coset_params")
             if cps is None:
-                cps = ws["coset_params"] = [CosetParams(P.q_polys, P.s_polys, P.qb_poly, P.q_prk_polys, k, n, j, dev) for j in range(6)]
+                cps = ws["coset_params"] = [CosetParams(P.q_polys, P.s_polys, P.qb_poly, P.q_prk_polys, k, n, j, dev,
+                                                       (vp.anemoi_generator, vp.anemoi_generator_inv)) for j in range(6)]
             for j, cp in enumerate(cps):
                 cp.quotient(polys, k, alpha, beta, gamma, _View(t_cosets, j * n, n))
         interleave_cosets(t_cosets, n, t_buf, ws.setdefault("interleave", {}))
