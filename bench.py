@@ -333,7 +333,7 @@ def _app_circuit_proofs(dev, K: int, W: int, name: str, cs, build_s: float, shuf
         "prove_ms": dt * 1e3, "proofs_per_s": 1 / dt, "e2e_prove_ms": dt_e2e * 1e3, "e2e_proofs_per_s": 1 / dt_e2e,
         "h2d_bytes_per_step": int(wit_host.nbytes) + n_sel * n * 4, "d2h_bytes_per_step": n_msm * 96 + (20 if shuffle else 16) * 32, "steps": K,
         "launches_per_proof": int(launches), "rounds_ms": {k: v / K for k, v in timings.items()},
-        "ops_per_proof": {"msm": n_msm, "ifft_n": 6 + n_sel, "fft_n": 7, "coset_fft_6n": 6 + n_sel, "coset_ifft_6n": 1,
+        "ops_per_proof": {"msm": n_msm, "ifft_n": 7 + n_sel, "fft_n": 7, "coset_fft_6n": 7 + n_sel, "coset_ifft_6n": 1,
                           "quotient_points": int(params.m), "evals": 20 if shuffle else 16},
         "build_cs_host_s": build_s, "setup_s": setup_s, "refresh_public_key_ms": refresh_ms,
         "deterministic": proof.to_bytes_be() == proof2.to_bytes_be(),
