@@ -695,8 +695,11 @@ def main() -> int:
     if args.workload in ("all", "plonk"):
         results["plonk"] = plonk_proofs(args, dev, K, W, rank, world, barrier, max_over_ranks)
         if world == 1 and not args.no_zshuffle:
-            results["plonk"]["sizes"].append(zmatchmaking_proofs(dev, K, W))
-            results["plonk"]["sizes"].append(zshuffle_proofs(dev, K, W))
+            for app in (zmatchmaking_proofs, zshuffle_proofs):
+                try:
+                    results["plonk"]["sizes"].append(app(dev, K, W))
+                except Exception as exc:       # reported in the JSON line, never silently: the synthetic sizes above still stand
+                    results["plonk"].setdefault("app_errors", []).append(f"{app.__name__}: {exc!r}")
 
     t_region1 = time.time()
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
