@@ -1020,20 +1020,26 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     wit = w if isinstance(w, DevVec) else DevVec.from_numpy(w, dev)
     if wit.len != cs.num_vars:
         raise ParameterError("witness length != num_vars")
-    if cs.public_vars_witness_indices:
+    n_online = len(cs.public_vars_witness_indices)
+    online_rows = None
+    if n_online:
         d_online = wit.t.view(-1, 4)[torch.tensor(cs.public_vars_witness_indices, device=dev)]
-        online_values = [unmont(r) for r in d_online.cpu().numpy().view(np.uint64)]
-    else:
-        online_values = []
-    transcript_init_plonk(transcript, vp, online_values, P.root)
+        online_rows = d_online.cpu().numpy().view(np.uint64)
+
+    def init_transcript():
+        """transcript_init_plonk (plonk/transcript.rs:8-31).  Host-only work (hundreds of big-integer conversions and appends for
+        the application circuits): deferred until round 1's kernels are enqueued, so the GPU is already busy; it must only precede
+        the first commitment appended."""
+        online_values = [unmont(r) for r in online_rows] if n_online else []
+        transcript_init_plonk(transcript, vp, online_values, P.root)
 
     # 1. the PI polynomial (helpers.rs:111-131)
     pi = DevVec(n, dev)
-    if online_values:
+    if n_online:
         # evals[row] = the public input constrained at that row (rows are distinct: one constant gate per prepare_pi_variable);
         # the values never leave the device: a row scatter of the witness entries read above
         rows_idx = ws.get("pi_rows")
-        if rows_idx is None or rows_idx.numel() != len(online_values):
+        if rows_idx is None or rows_idx.numel() != n_online:
             rows_idx = ws["pi_rows"] = torch.tensor(list(vp.public_vars_constraint_indices), device=dev)
         pi.t.view(-1, 4)[rows_idx] = d_online
         _ifft(pi.ptr, n, pi, scratch)
@@ -1070,6 +1076,7 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         if w_sel_polys:                                          # the witness selectors' too (`shuffle` feature set)
             for p, c in zip(w_sel_polys, w_sel_coset_bufs()):
                 _coset_fft(p, m, k1, c, scratch)
+        init_transcript()                                        # host work, with the GPU busy on the above
 
     # 3. (`shuffle` feature set) witness-selector polynomials (prover.rs:177-191): the remark gates' bit / sign columns
     # (compute_witness_selectors, turbo/mod.rs:171-191; zero on H without remark gates), hidden with 2 blinds each.  They depend on
@@ -1160,7 +1167,7 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
     if by_cosets:
         for p in w_polys + [z_poly]:
             p.t[4 * p.len: 4 * (n + 3)].zero_()
-        polys = [(p.t, n + 3) for p in w_polys + [z_poly]] + [(pi.t, n) if online_values else None]
+        polys = [(p.t, n + 3) for p in w_polys + [z_poly]] + [(pi.t, n) if n_online else None]
         t_cosets = ws.get("t_cosets") or DevVec(m, dev, zero=False)
         ws["t_cosets"] = t_cosets
         if dist_cosets:
@@ -1180,7 +1187,7 @@ def prover(prng, transcript: Transcript, pcs, cs: TurboCS, prover_params: PlonkP
         pcs.transform_many([(p.t, c.t) for p, c in zip(w_polys + [z_poly], w_coset + [z_coset])], n + 3, m, False, k1)
     if by_cosets:
         pass
-    elif online_values:
+    elif n_online:
         _coset_fft(pi, m, k1, pi_coset, scratch)
     else:
         pi_coset.t.zero_()
