@@ -1,4 +1,5 @@
-"""One zshuffle-52 proof (production route: everything over the Lagrange SRS) for a kernel launch list and a host profile.
+"""One zshuffle-52 (or, with APP=zmatchmaking, zmatchmaking) proof (production route: everything over the Lagrange SRS) for a kernel
+launch list and a host profile.  WINDOW_BITS / MSM_LANES override the engine's choices.
 
     python scripts/gpu_zshuffle_profile.py host      # cProfile of 10 proofs (where does the host spend the proof's wall time?)
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file launches.csv \
@@ -25,19 +26,28 @@ if os.environ.get("MSM_LANES"):
 dev = torch.device("cuda", 0)
 tau = plonk.mont(0x1234567890ABCDEF1234567890ABCDEF)
 prng = ChaChaRng.from_seed(bytes(32))
-apk = sh.rand_point(prng)
-cs, _ = sh.build_cs(plonk.TurboCS(), prng, apk, [sh.Ciphertext.rand(prng) for _ in range(52)])
+app = os.environ.get("APP", "zshuffle")          # or "zmatchmaking"
+if app == "zshuffle":
+    apk = sh.rand_point(prng)
+    cs, _ = sh.build_cs(plonk.TurboCS(), prng, apk, [sh.Ciphertext.rand(prng) for _ in range(52)])
+    label, count = b"Plonk shuffle Proof", 52
+else:
+    from uzkge_b200 import matchmaking as mm
+
+    cs, _ = mm.build_cs(plonk.TurboCS(), list(range(1, mm.N + 1)), 12345, 67890)
+    apk, label, count = None, mm.PLONK_PROOF_TRANSCRIPT, mm.N
 n = cs.size
 wb = int(os.environ.get("WINDOW_BITS", "0"))
 pcs, lagrange = KZGCommitmentSchemeBN254.new(n + 2, tau, wb), KZGCommitmentSchemeBN254.new_lagrange(n, tau, wb)
-params = plonk.indexer(cs, pcs, shuffle=True, lagrange_pcs=lagrange)
-plonk.refresh_prover_params_public_key(cs, params, pcs, apk, lagrange_pcs=lagrange)
+params = plonk.indexer(cs, pcs, shuffle=app == "zshuffle", lagrange_pcs=lagrange)
+if apk is not None:
+    plonk.refresh_prover_params_public_key(cs, params, pcs, apk, lagrange_pcs=lagrange)
 wit = plonk.DevVec.from_numpy(cs.get_witness_array(), dev)
 
 
 def prove():
-    tr = Transcript(b"Plonk shuffle Proof")
-    tr.append_u64(52)
+    tr = Transcript(label)
+    tr.append_u64(count)
     return plonk.prover(ChaChaRng.from_seed(bytes(32)), tr, pcs, cs, params, wit, lagrange_pcs=lagrange, lagrange_all=True)
 
 
