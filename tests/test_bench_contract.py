@@ -1,0 +1,55 @@
+"""CPU: the JSON line of `bench.py` as committed under profiles/ (the last run on a B200 of this round) carries every key the
+driver's contract names, with consistent values -- a guard against edits to bench.py that drop a field.  The reference arm is run
+here for real (it is the CPU arm) on a tiny sample."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+
+
+def _load(name):
+    return json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+
+
+def _check_line(d, n_gpus):
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "roofline", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["n_gpus"] == n_gpus and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["warmup"] >= 3 and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
+    assert d["metric"] == "bn254_g1_msm_2^20_points_per_s" and d["unit"] == "points/s"
+    assert abs(d["value"] - n_gpus * (1 << 20) / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 32 << 20 and e["d2h_bytes_per_step"] == 96 and 0 < e["value"] <= d["value"] * 1.05
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert "traffic" in r
+    assert d["gpu_launches"] > 0
+    c = d["clocks"]
+    assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_committed_bench_line_follows_the_contract():
+    d = _load("r1k_bench.json")
+    _check_line(d, 1)
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "points/s" and cb["sample"]
+    assert d["int_roofline"]["frac"] > 0.85                       # the accumulate kernel against the measured multiplier roof
+    circuits = {s.get("circuit", f"synthetic-{s['log_n']}-{s['witness']}-{s['feature_set']}"): s for s in d["plonk"]["sizes"]}
+    assert {"zshuffle-52", "zmatchmaking"} <= set(circuits) and "app_errors" not in d["plonk"]
+    for s in circuits.values():
+        assert s["deterministic"] and s["proof_bytes"] == (1632 if s["feature_set"] == "shuffle" else 1312)
+    for name, n in (("r1k_bench_2gpu.json", 2), ("r1k_bench_4gpu.json", 4)):
+        _check_line(_load(name), n)
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--workload", "ntt"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-400:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and "unavailable" not in d
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
