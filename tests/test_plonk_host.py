@@ -117,3 +117,47 @@ def test_restated_prover_is_accepted_by_restated_verifier(n_gates):
     assert not pp.verifier(pp.Transcript(b"other"), pcs, params["vp"], pi, proof)
     # commitments through the trapdoor equal commitments through the SRS (the MSM definition)
     assert pcs.commit(params["q_polys"][0]) == pcs.commit_msm(params["q_polys"][0])
+
+
+def test_turbo_cs_helper_gadgets():
+    """range_check, select, is_equal / is_not_equal (turbo/mod.rs:703-836) on the host mirror: the honest witness satisfies every gate
+    (verify_witness), a value outside the range or a flipped flag does not, and the restated prover / verifier accept the circuit."""
+    from plonk_circuits import transplant
+
+    from oracle import plonk_prover as pp
+    from uzkge_b200 import plonk
+    from uzkge_b200.errors import UzkgeError
+
+    def build(x_value, n_bits):
+        cs = plonk.TurboCS()
+        x, y, z = cs.new_variable(x_value), cs.new_variable(77), cs.new_variable(77)
+        bits = cs.range_check(x, n_bits)
+        eq, ne = cs.is_equal_or_not_equal(y, z)
+        ne2 = cs.is_not_equal(x, y)
+        picked = cs.select(x, y, cs.is_equal(x, x))
+        cs.prepare_pi_variable(picked)
+        cs.pad()
+        return cs, bits, (eq, ne, ne2, picked)
+
+    for n_bits in (2, 3, 4, 5, 8, 13):
+        value = (1 << n_bits) - 3 if n_bits > 2 else 2
+        cs, bits, (eq, ne, ne2, picked) = build(value, n_bits)
+        w = cs.witness
+        assert sum(w[b] << i for i, b in enumerate(bits)) == value and len(bits) == n_bits
+        assert (w[eq], w[ne], w[ne2], w[picked]) == (1, 0, 1, 77)
+        cs.verify_witness(w, [77])
+    cs, bits, _ = build(1 << 9, 8)                                   # 512 does not fit 8 bits
+    with pytest.raises(UzkgeError):
+        cs.verify_witness(cs.witness, [77])
+    cs, bits, (eq, ne, ne2, picked) = build(200, 8)
+    bad = list(cs.witness)
+    bad[eq] = 0
+    with pytest.raises(UzkgeError):
+        cs.verify_witness(bad, [77])
+    ocs = transplant(cs)
+    tau = 0x1234567890ABCDEF1234567890ABCDEF
+    pcs = pp.Kzg(cs.size + 2, tau)
+    P = pp.indexer(ocs, pcs)
+    proof = pp.prover(pp.ChaCha(bytes(32)), pp.Transcript(b"gadgets"), pcs, ocs, P, ocs.witness)
+    assert pp.verifier(pp.Transcript(b"gadgets"), pcs, P["vp"], [77], proof)
+    assert not pp.verifier(pp.Transcript(b"gadgets"), pcs, P["vp"], [78], proof)

@@ -222,6 +222,45 @@ class TurboCS(ShuffleGates, AnemoiGates):
         self._push_gate((0, 1, 0, 0), (-1, 1), 0, 0, 1, [bit, var0, bit, var1, out])
         return out
 
+    def range_check(self, var: int, n_bits: int) -> list:
+        """turbo/mod.rs:703-763: constrain 0 <= witness[var] < 2^n_bits; returns the bit variables, little endian.  The bits are
+        boolean-constrained through the qb selector of the accumulation gates (wires 2-4) and one boolean gate for the top bit."""
+        if n_bits < 2:
+            raise ParameterError("the number of bits is less than two")
+        value = self.witness[var]
+        b = [self.new_variable((value >> i) & 1) for i in range(n_bits)]
+        acc = b[n_bits - 1]
+        self.insert_boolean_gate(b[n_bits - 1])
+        m = (n_bits - 2) // 3
+        for i in range(m):
+            acc = self.linear_combine([acc, b[n_bits - 1 - i * 3 - 1], b[n_bits - 1 - i * 3 - 2], b[n_bits - 1 - i * 3 - 3]], 8, 4, 2, 1)
+            self.attach_boolean_constraint_to_gate()
+        rest = (n_bits - 1) - 3 * m
+        if rest == 1:
+            self.insert_lc_gate([acc, b[0], 0, 0], var, 2, 1, 0, 0)
+        elif rest == 2:
+            self.insert_lc_gate([acc, b[1], b[0], 0], var, 4, 2, 1, 0)
+        else:
+            self.insert_lc_gate([acc, b[2], b[1], b[0]], var, 8, 4, 2, 1)
+        self.attach_boolean_constraint_to_gate()
+        return b
+
+    def is_equal_or_not_equal(self, left_var: int, right_var: int) -> tuple:
+        """turbo/mod.rs:814-836: two boolean variables, (1, 0) iff the values are equal, (0, 1) otherwise."""
+        diff = self.sub(left_var, right_var)
+        d = self.witness[diff]
+        inv_diff = self.new_variable(pow(d, -1, FR_MODULUS) if d else 0)
+        mul_var = self.mul(diff, inv_diff)
+        diff_is_zero = self.sub(self.one_var(), mul_var)
+        self.insert_mul_gate(diff, diff_is_zero, self.zero_var())
+        return diff_is_zero, mul_var
+
+    def is_equal(self, left_var: int, right_var: int) -> int:
+        return self.is_equal_or_not_equal(left_var, right_var)[0]
+
+    def is_not_equal(self, left_var: int, right_var: int) -> int:
+        return self.is_equal_or_not_equal(left_var, right_var)[1]
+
     def equal(self, left_var: int, right_var: int) -> None:
         self.insert_sub_gate(left_var, right_var, self.zero_var())
 
