@@ -1,5 +1,6 @@
-"""CPU restatement (Python big integers) of the reference's TurboPlonK prover and verifier for the default feature set
-(no `shuffle`).  TEST INFRASTRUCTURE ONLY: imported by tests/ alone, never by the product package.
+"""CPU restatement (Python big integers) of the reference's TurboPlonK indexer, prover and verifier: the default feature set, and
+(indexer / prover; the verifier for it is oracle/plonk_verifier_shuffle.py) the `shuffle` feature set with the remark and permutation
+gadgets of zshuffle's circuit.  TEST INFRASTRUCTURE ONLY: imported by tests/ alone, never by the product package.
 
 Follows, function by function:
   TurboCS (subset)            /root/reference/uzkge/src/plonk/constraint_system/turbo/mod.rs:395-537, 853-891, 968-977
@@ -18,8 +19,10 @@ The pairing check of batch_verify_diff_points (kzg_poly_commitment.rs:407-460) i
 trapdoor tau (the SRS here is synthetic): e(A, H) = e(B, tau H)  <=>  A = tau * B.
 
 Everything is a canonical integer mod r; G1 points are affine (x, y) tuples or None; MSMs go through oracle.bn254.
-Parity status: the Rust prover cannot run here (no toolchain), so a proof is pinned by (1) this restatement's own verifier
-accepting it, (2) the golden RNG / domain values, (3) bit-equality with the GPU pipeline on the same seed.
+Parity status: the Rust prover cannot run here (no toolchain), so a proof is pinned by (1) this restatement's own verifier and
+oracle/plonk_verifier_shuffle.py -- the verifier that accepts the reference's golden proofs -- accepting it, (2) the golden RNG /
+domain values, (3) the circuits' preprocessed commitments reproducing the reference's deployed / bundled verifier keys
+(tests/test_shuffle_host.py, tests/test_matchmaking_host.py), (4) bit-equality with the GPU pipeline on the same seed.
 """
 from __future__ import annotations
 

@@ -3,7 +3,8 @@
 No Rust toolchain exists in this image, so what in production is the patched body of `prover_with_lagrange` is restated here in
 Python with the reference's names and order of operations (the RNG draws and transcript appends are order-sensitive):
 
-  TurboCS (the gates a synthetic circuit needs)  /root/reference/uzkge/src/plonk/constraint_system/turbo/mod.rs:395-537, 853-891, 968-977
+  TurboCS (gates, helper gadgets, verify_witness) /root/reference/uzkge/src/plonk/constraint_system/turbo/mod.rs:395-1396; the shuffle
+                                                 and Anemoi gadgets are mixed in from shuffle.py / anemoi.py
   compute_permutation / extend_witness           /root/reference/uzkge/src/plonk/constraint_system/mod.rs:54-84, 103-111
   indexer                                        /root/reference/uzkge/src/plonk/indexer.rs:248-536   (both feature sets)
   refresh_prover_params_public_key               /root/reference/shuffle/src/gen_params/params.rs:57-129
