@@ -1,0 +1,201 @@
+// The reference's unit tests for the hot-path boundary, restated against the C++ host layer (include/uzkge_host.hpp):
+//   test_fft / check_fft                      /root/reference/uzkge/src/poly_commit/field_polynomial.rs:632-719
+//   test_commit, test_homomorphic_poly_com_elem  /root/reference/uzkge/src/poly_commit/kzg_poly_commitment.rs:483-548
+//   test_pcs_eval                              /root/reference/uzkge/src/poly_commit/pcs.rs:260-290
+// Expected values come from the CPU oracle (oracle/oracle.c) -- this is a TEST program; the product never links the oracle.
+//   host_api_test nodevice   (no GPU visible: every device call must fail loudly with the mapped UzkgeError; host logic is checked)
+//   host_api_test gpu        (parity with the oracle through the C++ layer)
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "uzkge_host.hpp"
+
+extern "C" {
+void oracle_init(void);
+void oracle_fr_to_mont(const uint64_t* a, uint64_t* o, size_t n);
+int oracle_msm_g1(const uint64_t* bases, const uint64_t* scalars, size_t n, uint64_t* out_jac);
+void oracle_g1_mul(const uint64_t* base_aff, const uint64_t* scalar_mont, uint64_t* out_jac);
+void oracle_g1_add_jac(const uint64_t* a, const uint64_t* b, uint64_t* out_jac);
+void oracle_g1_to_affine(const uint64_t* in_jac, uint64_t* out_aff);
+int oracle_ntt_fr(uint64_t* data, size_t len_in, size_t n, int inverse, const uint64_t* coset);
+void oracle_fr_eval(const uint64_t* coefs, size_t n, const uint64_t* x_mont, uint64_t* out_mont);
+void oracle_fr_inv(const uint64_t* a_mont, uint64_t* out_mont);
+}
+
+using namespace uzkge;
+
+static int failures = 0;
+#define CHECK(cond)                                                        \
+    do {                                                                   \
+        if (!(cond)) {                                                     \
+            std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);    \
+            failures++;                                                    \
+        }                                                                  \
+    } while (0)
+
+template <class F>
+static bool throws(UzkgeError kind, F&& f) {
+    try {
+        f();
+    } catch (const Error& e) {
+        return e.kind == kind;
+    }
+    return false;
+}
+
+static Fr mont(uint64_t v) {   // a small integer in Montgomery form
+    Fr c = {v, 0, 0, 0}, m{};
+    oracle_fr_to_mont(c.data(), m.data(), 1);
+    return m;
+}
+static std::vector<Fr> pseudo_random(size_t n, uint64_t seed) {   // Montgomery images of 62-bit values: valid field elements
+    std::vector<Fr> out(n);
+    uint64_t s = seed;
+    for (auto& x : out) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        x = mont(s >> 2);
+    }
+    return out;
+}
+static std::array<uint64_t, 8> oracle_affine(const std::array<uint64_t, 12>& jac) {
+    std::array<uint64_t, 8> a{};
+    oracle_g1_to_affine(jac.data(), a.data());
+    return a;
+}
+
+static void host_logic() {
+    // from_coefs trims trailing zeros, keeps one coefficient (field_polynomial.rs:154-159)
+    auto p = FpPolynomial::from_coefs({mont(1), mont(2), Fr{}, Fr{}});
+    CHECK(p.degree() == 1 && p.coefs.size() == 2);
+    CHECK(FpPolynomial::from_coefs({}).is_zero() && FpPolynomial::zero().degree() == 0);
+    CHECK(FpPolynomial::from_coefs({Fr{}, Fr{}}).is_zero());
+    // -x + x = 0 mod r on the limbs; -0 = 0
+    Fr one = mont(1), neg = fr_neg(one);
+    unsigned __int128 carry = 0;
+    Fr sum{};
+    for (int i = 0; i < 4; i++) {
+        carry += (unsigned __int128)one[i] + neg[i];
+        sum[i] = (uint64_t)carry;
+        carry >>= 64;
+    }
+    CHECK(sum == FR_MODULUS && fr_is_zero(fr_neg(Fr{})));
+    CHECK(throws(UzkgeError::ParameterError, [] { FpPolynomial::evaluation_domain(12); }));
+}
+
+static int run_nodevice() {
+    host_logic();
+    CHECK(uzkge_cuda_device_count() <= 0);
+    // no CPU fallback: every entry point of the layer reports the operation's error
+    CHECK(throws(UzkgeError::FFTError, [] { Radix2EvaluationDomain::new_(8).value().fft({mont(1)}); }) ||
+          throws(UzkgeError::FFTError, [] { Radix2EvaluationDomain::new_(8); }));
+    CHECK(throws(UzkgeError::CommitmentError, [] { KZGCommitmentSchemeBN254::new_(4, mont(7)); }));
+    CHECK(throws(UzkgeError::CommitmentError, [] { KZGCommitmentSchemeBN254(std::vector<uint64_t>(16, 1)); }));
+    CHECK(throws(UzkgeError::ParameterError, [] { KZGCommitmentSchemeBN254(std::vector<uint64_t>(7, 1)); }));
+    CHECK(throws(UzkgeError::Message, [] { FpPolynomial::from_coefs({mont(1), mont(2)}).eval(mont(3)); }));
+    CHECK(throws(UzkgeError::CommitmentError, [] { KZGCommitment{}.add(KZGCommitment{}); }));
+    CHECK(MixedRadixEvaluationDomain::new_(10) == std::nullopt ? true : false);
+    return failures;
+}
+
+static void test_fft() {
+    Fr k = mont(0x1234567);   // a coset shift
+    Fr k_inv{};
+    oracle_fr_inv(k.data(), k_inv.data());
+    for (size_t n : {1, 2, 8, 64, 1024, 12, 96, 3072}) {
+        const bool radix2 = (n & (n - 1)) == 0;
+        auto domain = radix2 ? FpPolynomial::evaluation_domain(n) : FpPolynomial::quotient_evaluation_domain(n);
+        CHECK(domain.has_value() && domain->size() == n);
+        for (size_t len : {n, n / 2 + 1}) {
+            auto poly = FpPolynomial::from_coefs(pseudo_random(len, 17 * n + len));
+            // check_fft (field_polynomial.rs:632-646): the transform against the oracle's, natural order, zero-padded input
+            std::vector<Fr> want(n, Fr{});
+            std::memcpy(want.data(), poly.coefs.data(), poly.coefs.size() * sizeof(Fr));
+            CHECK(oracle_ntt_fr(want[0].data(), poly.coefs.size(), n, 0, nullptr) == 0);
+            auto evals = poly.fft_with_domain(*domain);
+            CHECK(evals == want);
+            CHECK(poly.fft(n).value() == want);
+            // test_fft: ifft(fft(p)) == p, trimmed; and the coset pair with the scaling fused
+            CHECK(FpPolynomial::ifft_with_domain(*domain, evals) == poly);
+            std::vector<Fr> cwant(n, Fr{});
+            std::memcpy(cwant.data(), poly.coefs.data(), poly.coefs.size() * sizeof(Fr));
+            CHECK(oracle_ntt_fr(cwant[0].data(), poly.coefs.size(), n, 0, k.data()) == 0);
+            auto cevals = poly.coset_fft_with_domain(*domain, k);
+            CHECK(cevals == cwant);
+            CHECK(FpPolynomial::coset_ifft_with_domain(*domain, cevals, k_inv) == poly);
+        }
+    }
+    CHECK(throws(UzkgeError::FFTError, [] { Radix2EvaluationDomain::new_(4).value().fft(pseudo_random(5, 1)); }));
+    CHECK(!MixedRadixEvaluationDomain::new_(10).has_value());
+}
+
+static void test_commit_and_pcs() {
+    const size_t max_degree = 40;
+    Fr tau = mont(0xC0FFEE1234ull);
+    auto pcs = KZGCommitmentSchemeBN254::new_(max_degree, tau);
+    CHECK(pcs.max_degree() == max_degree);
+    // test_commit: the commitment is the MSM of the coefficients over the SRS
+    auto p = FpPolynomial::from_coefs(pseudo_random(max_degree + 1, 5));
+    auto cm = pcs.commit(p);
+    std::array<uint64_t, 12> want{};
+    CHECK(oracle_msm_g1(pcs.public_parameter_group_1.data(), p.coefs[0].data(), p.coefs.size(), want.data()) == 0);
+    CHECK(cm.to_affine() == oracle_affine(want));
+    CHECK(throws(UzkgeError::DegreeError, [&] { pcs.commit(FpPolynomial::from_coefs(pseudo_random(max_degree + 2, 6))); }));
+    // test_homomorphic_poly_com_elem on polynomials with disjoint supports: com(p) + com(q) == com(p + q)
+    auto a = pseudo_random(3, 9);
+    auto lo = FpPolynomial::from_coefs({a[0], a[1]});
+    auto hi = FpPolynomial::from_coefs({Fr{}, Fr{}, a[2]});
+    auto both = FpPolynomial::from_coefs({a[0], a[1], a[2]});
+    CHECK(pcs.commit(lo).add(pcs.commit(hi)) == pcs.commit(both));
+    auto batch = pcs.commit_batch({&lo, &hi, &both, &p});
+    CHECK(batch.size() == 4 && batch[0] == pcs.commit(lo) && batch[2] == pcs.commit(both) && batch[3] == cm);
+    // test_pcs_eval: eval, and prove = the commitment of (P - P(x)) / (X - x)
+    Fr x = mont(0x55AA55AA);
+    Fr ev = pcs.eval(p, x), ev_want{};
+    oracle_fr_eval(p.coefs[0].data(), p.coefs.size(), x.data(), ev_want.data());
+    CHECK(ev == ev_want);
+    auto qr = p.div_rem_linear(x);
+    CHECK(qr.second.coefs[0] == ev && qr.first.degree() == p.degree() - 1);
+    CHECK(pcs.prove(p, x, max_degree) == pcs.commit(qr.first));
+    CHECK(throws(UzkgeError::DegreeError, [&] { pcs.prove(p, x, 3); }));
+    // apply_blind_factors: C + b0 (SRS[0] - SRS[n]) + b1 (SRS[1] - SRS[n + 1])
+    const size_t n = 16;
+    auto blinds = pseudo_random(2, 11);
+    auto blinded = pcs.apply_blind_factors(cm, blinds, n);
+    std::array<uint64_t, 12> acc = cm.value, t{};
+    for (size_t i = 0; i < 2; i++) {
+        Fr nb = fr_neg(blinds[i]);
+        oracle_g1_mul(pcs.public_parameter_group_1.data() + 8 * i, blinds[i].data(), t.data());
+        oracle_g1_add_jac(acc.data(), t.data(), acc.data());
+        oracle_g1_mul(pcs.public_parameter_group_1.data() + 8 * (n + i), nb.data(), t.data());
+        oracle_g1_add_jac(acc.data(), t.data(), acc.data());
+    }
+    CHECK(blinded.to_affine() == oracle_affine(acc));
+    CHECK(throws(UzkgeError::ParameterError, [&] { pcs.apply_blind_factors(cm, blinds, max_degree); }));
+    // the Lagrange SRS of the same trapdoor commits evaluation vectors to the same group element (prover_with_lagrange)
+    auto lag = pcs.derive_lagrange(n);
+    auto small = FpPolynomial::from_coefs(pseudo_random(n, 13));
+    auto evals = small.fft_with_domain(*FpPolynomial::evaluation_domain(n));
+    CHECK(lag.commit(FpPolynomial{evals}) == pcs.commit(small));
+}
+
+int main(int argc, char** argv) {
+    const std::string mode = argc > 1 ? argv[1] : "gpu";
+    oracle_init();
+    if (mode == "nodevice") {
+        const int f = run_nodevice();
+        std::printf(f ? "FAILED (%d)\n" : "PASS nodevice\n", f);
+        return f ? 1 : 0;
+    }
+    try {
+        init(0);
+        host_logic();
+        test_fft();
+        test_commit_and_pcs();
+    } catch (const Error& e) {
+        std::printf("FAIL: uncaught uzkge::Error: %s\n", e.what());
+        return 1;
+    }
+    std::printf(failures ? "FAILED (%d)\n" : "PASS gpu\n", failures);
+    return failures ? 1 : 0;
+}
