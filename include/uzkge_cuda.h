@@ -139,6 +139,11 @@ UZKGE_API int32_t uzkge_cuda_ntt_cross_rows_fr_device(const void* const* d_in_ro
  * cudaIpcOpenMemHandle.  `handle` is 64 opaque bytes to ship through any host channel (torch.distributed all_gather_object). */
 UZKGE_API int32_t uzkge_cuda_dev_alloc(size_t bytes, void** d_ptr);
 UZKGE_API int32_t uzkge_cuda_dev_free(void* d_ptr);
+/* Synchronous host <-> device copies for callers without their own CUDA binding (the Rust crate, the C++ host layer): ordered with
+ * the *_device entry points called with stream = NULL.  What `Vec<Fr>` <-> device buffer conversions of a device-resident
+ * prover_with_lagrange (plonk/prover.rs:88-394) need at its ends. */
+UZKGE_API int32_t uzkge_cuda_dev_copy_in(void* d_dst, const void* h_src, size_t bytes);
+UZKGE_API int32_t uzkge_cuda_dev_copy_out(void* h_dst, const void* d_src, size_t bytes);
 UZKGE_API int32_t uzkge_cuda_ipc_export(const void* d_ptr, uint8_t handle[64]);
 UZKGE_API int32_t uzkge_cuda_ipc_open(const uint8_t handle[64], void** d_ptr);
 UZKGE_API int32_t uzkge_cuda_ipc_close(void* d_ptr);

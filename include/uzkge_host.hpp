@@ -289,6 +289,72 @@ class KZGCommitmentSchemeBN254 {
     uint64_t handle_ = 0;
 };
 
+// ---- device-resident vectors: what keeps the prover's polynomials in HBM between the rounds.  The *_device entry
+// points are called with stream = NULL; uzkge_cuda_dev_copy_in / _out are ordered with them.
+class DeviceVec {
+  public:
+    explicit DeviceVec(size_t n_elements) : n_(n_elements) {
+        detail::check(uzkge_cuda_dev_alloc(n_ * sizeof(Fr), &ptr_), UzkgeError::Message, "uzkge_cuda_dev_alloc");
+    }
+    explicit DeviceVec(const std::vector<Fr>& host) : DeviceVec(host.size()) { upload(host); }
+    DeviceVec(const DeviceVec&) = delete;
+    DeviceVec& operator=(const DeviceVec&) = delete;
+    DeviceVec(DeviceVec&& o) noexcept : ptr_(o.ptr_), n_(o.n_) { o.ptr_ = nullptr; }
+    ~DeviceVec() {
+        if (ptr_) uzkge_cuda_dev_free(ptr_);
+    }
+    void* ptr() const { return ptr_; }
+    size_t size() const { return n_; }
+    void upload(const std::vector<Fr>& host) {
+        if (host.size() > n_) throw Error(UzkgeError::ParameterError, "upload: vector longer than the buffer");
+        detail::check(uzkge_cuda_dev_copy_in(ptr_, host.data(), host.size() * sizeof(Fr)), UzkgeError::Message, "uzkge_cuda_dev_copy_in");
+    }
+    std::vector<Fr> download(size_t count) const {
+        if (count > n_) throw Error(UzkgeError::ParameterError, "download: more than the buffer holds");
+        std::vector<Fr> out(count);
+        detail::check(uzkge_cuda_dev_copy_out(out.data(), ptr_, count * sizeof(Fr)), UzkgeError::Message, "uzkge_cuda_dev_copy_out");
+        return out;
+    }
+
+  private:
+    void* ptr_ = nullptr;
+    size_t n_ = 0;
+};
+
+// domain.fft / ifft (and the coset variants) of a device-resident vector: out[0..size) <- transform(in[0..len_in) zero-padded)
+inline void transform_device(const EvaluationDomain& domain, const DeviceVec& in, size_t len_in, DeviceVec& out, DeviceVec& scratch, bool inverse,
+                             const Fr* coset_shift = nullptr) {
+    if (len_in > domain.size() || out.size() < domain.size() || scratch.size() < domain.size() || in.size() < len_in)
+        throw Error(UzkgeError::FFTError, "transform_device: buffer sizes");
+    detail::check(uzkge_cuda_ntt_fr_device(in.ptr(), out.ptr(), scratch.ptr(), len_in, domain.size(), inverse ? 1 : 0,
+                                           coset_shift ? coset_shift->data() : nullptr, nullptr),
+                  UzkgeError::FFTError, "uzkge_cuda_ntt_fr_device");
+}
+
+// PolyComScheme::commit for device-resident coefficient vectors: the independent commitments of a round in one pass
+inline std::vector<KZGCommitment> commit_device(const KZGCommitmentSchemeBN254& pcs, const std::vector<const DeviceVec*>& vecs,
+                                                const std::vector<size_t>& lens) {
+    if (vecs.size() != lens.size()) throw Error(UzkgeError::ParameterError, "commit_device: one length per vector");
+    std::vector<const void*> ptrs;
+    for (size_t i = 0; i < vecs.size(); i++) {
+        if (lens[i] > pcs.n_points()) throw Error(UzkgeError::DegreeError, "DegreeError");
+        if (lens[i] > vecs[i]->size()) throw Error(UzkgeError::ParameterError, "commit_device: length beyond the buffer");
+        ptrs.push_back(vecs[i]->ptr());
+    }
+    std::vector<KZGCommitment> out(vecs.size());
+    if (out.empty()) return out;
+    void* d_out = nullptr;
+    detail::check(uzkge_cuda_dev_alloc(96 * out.size(), &d_out), UzkgeError::CommitmentError, "uzkge_cuda_dev_alloc");
+    const int32_t rc = uzkge_cuda_msm_g1_batch_device(pcs.handle(), 0, ptrs.data(), lens.data(), out.size(), d_out, nullptr);
+    std::vector<uint64_t> flat(12 * out.size());
+    const int32_t rc2 = rc == UZKGE_OK ? uzkge_cuda_dev_copy_out(flat.data(), d_out, 96 * out.size()) : UZKGE_OK;
+    uzkge_cuda_dev_free(d_out);
+    detail::check(rc, UzkgeError::CommitmentError, "uzkge_cuda_msm_g1_batch_device");
+    detail::check(rc2, UzkgeError::CommitmentError, "uzkge_cuda_dev_copy_out");
+    for (size_t i = 0; i < out.size(); i++) std::memcpy(out[i].value.data(), flat.data() + 12 * i, 96);
+    return out;
+}
+
 }  // namespace uzkge
 
 #endif  // UZKGE_HOST_HPP

@@ -94,6 +94,7 @@ static int run_nodevice() {
     CHECK(throws(UzkgeError::ParameterError, [] { KZGCommitmentSchemeBN254(std::vector<uint64_t>(7, 1)); }));
     CHECK(throws(UzkgeError::Message, [] { FpPolynomial::from_coefs({mont(1), mont(2)}).eval(mont(3)); }));
     CHECK(throws(UzkgeError::CommitmentError, [] { KZGCommitment{}.add(KZGCommitment{}); }));
+    CHECK(throws(UzkgeError::Message, [] { DeviceVec v(4); }));
     CHECK(MixedRadixEvaluationDomain::new_(10) == std::nullopt ? true : false);
     return failures;
 }
@@ -179,6 +180,30 @@ static void test_commit_and_pcs() {
     CHECK(lag.commit(FpPolynomial{evals}) == pcs.commit(small));
 }
 
+// the same results with the polynomials resident in HBM (the *_device rows of the ABI): upload once, transform and commit there
+static void test_device_resident() {
+    const size_t n = 1024, m = 6 * n;
+    auto pcs = KZGCommitmentSchemeBN254::new_(n + 2, mont(0xABCDEF0123ull));
+    auto p = FpPolynomial::from_coefs(pseudo_random(n, 21)), q = FpPolynomial::from_coefs(pseudo_random(n + 3, 22));
+    DeviceVec dp(p.coefs), dq(q.coefs), evals(m), back(m), scratch(m);
+    CHECK(dp.download(n) == p.coefs);
+    auto cms = commit_device(pcs, {&dp, &dq}, {p.coefs.size(), q.coefs.size()});
+    CHECK(cms.size() == 2 && cms[0] == pcs.commit(p) && cms[1] == pcs.commit(q));
+    Fr k = mont(0x77123), k_inv{};
+    oracle_fr_inv(k.data(), k_inv.data());
+    auto dom_n = *FpPolynomial::evaluation_domain(n);
+    auto dom_m = *FpPolynomial::quotient_evaluation_domain(m);
+    transform_device(dom_n, dp, n, evals, scratch, false);
+    CHECK(evals.download(n) == p.fft_with_domain(dom_n));
+    transform_device(dom_m, dq, n + 3, evals, scratch, false, &k);                // coset_fft of n + 3 coefficients on the 6n domain
+    CHECK(evals.download(m) == q.coset_fft_with_domain(dom_m, k));
+    transform_device(dom_m, evals, m, back, scratch, true, &k_inv);               // and back
+    auto coefs = back.download(m);
+    CHECK(FpPolynomial::from_coefs(coefs) == q);
+    CHECK(throws(UzkgeError::DegreeError, [&] { commit_device(pcs, {&evals}, {m}); }));
+    CHECK(throws(UzkgeError::FFTError, [&] { transform_device(dom_m, dp, n, dp, scratch, false); }));
+}
+
 int main(int argc, char** argv) {
     const std::string mode = argc > 1 ? argv[1] : "gpu";
     oracle_init();
@@ -192,6 +217,7 @@ int main(int argc, char** argv) {
         host_logic();
         test_fft();
         test_commit_and_pcs();
+        test_device_resident();
     } catch (const Error& e) {
         std::printf("FAIL: uncaught uzkge::Error: %s\n", e.what());
         return 1;

@@ -439,6 +439,22 @@ UZKGE_API int32_t uzkge_cuda_dev_free(void* d_ptr) {
     CUDA_OR_FAIL(cudaFree(d_ptr), "dev_free");
     return UZKGE_OK;
 }
+UZKGE_API int32_t uzkge_cuda_dev_copy_in(void* d_dst, const void* h_src, size_t bytes) {
+    if (bytes && (!d_dst || !h_src)) return fail(UZKGE_ERR_ARG, "dev_copy_in: null pointer");
+    API_ENTER(-1);
+    if (bytes == 0) return UZKGE_OK;
+    // synchronous, on the legacy default stream: ordered with *_device calls made with stream = NULL
+    CUDA_OR_FAIL(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice), "dev_copy_in");
+    return UZKGE_OK;
+}
+UZKGE_API int32_t uzkge_cuda_dev_copy_out(void* h_dst, const void* d_src, size_t bytes) {
+    if (bytes && (!h_dst || !d_src)) return fail(UZKGE_ERR_ARG, "dev_copy_out: null pointer");
+    API_ENTER(-1);
+    if (bytes == 0) return UZKGE_OK;
+    // synchronous, on the legacy default stream: everything enqueued through *_device calls with stream = NULL completes first
+    CUDA_OR_FAIL(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost), "dev_copy_out");
+    return UZKGE_OK;
+}
 UZKGE_API int32_t uzkge_cuda_ipc_export(const void* d_ptr, uint8_t handle[64]) {
     if (!d_ptr || !handle) return fail(UZKGE_ERR_ARG, "ipc_export: null pointer");
     API_ENTER(-1);

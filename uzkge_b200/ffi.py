@@ -104,6 +104,8 @@ _SIGNATURES = {
     ),
     "uzkge_cuda_dev_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "uzkge_cuda_dev_free": (C.c_int32, [C.c_void_p]),
+    "uzkge_cuda_dev_copy_in": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "uzkge_cuda_dev_copy_out": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "uzkge_cuda_ipc_export": (C.c_int32, [C.c_void_p, C.c_char_p]),
     "uzkge_cuda_ipc_open": (C.c_int32, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "uzkge_cuda_ipc_close": (C.c_int32, [C.c_void_p]),
