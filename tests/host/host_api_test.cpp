@@ -10,6 +10,7 @@
 #include <string>
 
 #include "uzkge_host.hpp"
+#include "uzkge_transcript.hpp"
 
 extern "C" {
 void oracle_init(void);
@@ -21,6 +22,10 @@ void oracle_g1_to_affine(const uint64_t* in_jac, uint64_t* out_aff);
 int oracle_ntt_fr(uint64_t* data, size_t len_in, size_t n, int inverse, const uint64_t* coset);
 void oracle_fr_eval(const uint64_t* coefs, size_t n, const uint64_t* x_mont, uint64_t* out_mont);
 void oracle_fr_inv(const uint64_t* a_mont, uint64_t* out_mont);
+void oracle_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n);
+void oracle_fq_mul(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n);
+void oracle_fr_from_mont(const uint64_t* a, uint64_t* o, size_t n);
+void oracle_fq_to_mont(const uint64_t* a, uint64_t* o, size_t n);
 }
 
 using namespace uzkge;
@@ -204,9 +209,76 @@ static void test_device_resident() {
     CHECK(throws(UzkgeError::FFTError, [&] { transform_device(dom_m, dp, n, dp, scratch, false); }));
 }
 
+static Limbs parse_hex(const char* h) {           // "0x..." canonical integer -> limbs
+    Limbs out{};
+    std::string t(h);
+    if (t.rfind("0x", 0) == 0) t = t.substr(2);
+    int nib = 0;
+    for (auto it = t.rbegin(); it != t.rend(); ++it, ++nib) {
+        const char c = *it;
+        const uint64_t v = c <= '9' ? c - '0' : (c | 32) - 'a' + 10;
+        out[nib >> 4] |= v << (4 * (nib & 15));
+    }
+    return out;
+}
+static void print_hex(const char* name, const Limbs& canonical) {
+    std::printf("%s 0x%016llx%016llx%016llx%016llx\n", name, (unsigned long long)canonical[3], (unsigned long long)canonical[2],
+                (unsigned long long)canonical[1], (unsigned long long)canonical[0]);
+}
+
+// the serial host part (include/uzkge_transcript.hpp): needs no device.  argv: the golden k[1..4] of the reference's verifier keys.
+static int run_serial(int argc, char** argv) {
+    // Keccak-256 of the empty string
+    uint8_t d[32];
+    uzkge_host_keccak256(nullptr, 0, d);
+    CHECK(from_bytes_be(d) == parse_hex("0xc5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"));
+    // the host's Montgomery arithmetic against the oracle's, both fields
+    auto xs = pseudo_random(64, 3), ys = pseudo_random(64, 4);
+    for (size_t i = 0; i < xs.size(); i++) {
+        Limbs want{}, back{};
+        oracle_fr_mul(xs[i].data(), ys[i].data(), want.data(), 1);
+        CHECK(FR.mul(xs[i], ys[i]) == want);
+        oracle_fq_mul(xs[i].data(), ys[i].data(), want.data(), 1);       // any limbs below p are valid Fq elements too
+        CHECK(FQ.mul(xs[i], ys[i]) == want);
+        oracle_fr_from_mont(xs[i].data(), back.data(), 1);
+        CHECK(FR.from_mont(xs[i]) == back && FR.to_mont(back) == xs[i]);
+        CHECK(FR.mul(xs[i], FR.inverse(xs[i])) == FR.one);
+        CHECK(FR.add(xs[i], FR.neg(xs[i])) == Limbs{} && FR.neg(xs[i]) == fr_neg(xs[i]));
+    }
+    CHECK(FR.from_mont(FR.one) == Limbs({1, 0, 0, 0}) && FQ.from_mont(FQ.one) == Limbs({1, 0, 0, 0}));
+    CHECK(FR.modulus == FR_MODULUS);
+    // choose_ks with ChaChaRng::from_seed([0; 32]) (plonk/indexer.rs:258): the k written into the reference's verifier keys
+    ChaChaRng prng(std::array<uint8_t, 32>{});
+    auto k = choose_ks(prng, 5);
+    CHECK(k.size() == 5 && k[0] == FR.one && argc >= 6);
+    for (int i = 1; i < 5 && i + 1 < argc; i++) CHECK(FR.from_mont(k[i]) == parse_hex(argv[i + 1]));
+    // a fixed transcript script; the caller compares the two challenges with the Python mirror's
+    Transcript tr("Plonk shuffle Proof");
+    tr.append_u64(52);
+    tr.append_challenge(k[1]);
+    std::array<uint64_t, 8> g{};
+    const Limbs gx = FQ.to_mont({1, 0, 0, 0}), gy = FQ.to_mont({2, 0, 0, 0});
+    std::memcpy(g.data(), gx.data(), 32);
+    std::memcpy(g.data() + 4, gy.data(), 32);
+    tr.append_commitment(g);
+    tr.append_commitment(std::array<uint64_t, 8>{});      // the identity: 64 zero bytes
+    const Limbs c1 = tr.get_challenge_field_elem();
+    tr.append_single_byte(0x01);
+    tr.append_challenge(FR.mul(c1, k[2]));
+    const Limbs c2 = tr.get_challenge_field_elem();
+    print_hex("challenge1", FR.from_mont(c1));
+    print_hex("challenge2", FR.from_mont(c2));
+    return failures;
+}
+
 int main(int argc, char** argv) {
     const std::string mode = argc > 1 ? argv[1] : "gpu";
     oracle_init();
+    if (mode == "serial") {
+        const int f = run_serial(argc, argv);
+        std::printf(f ? "FAILED (%d)\n" : "PASS serial\n", f);
+        return f ? 1 : 0;
+    }
     if (mode == "nodevice") {
         const int f = run_nodevice();
         std::printf(f ? "FAILED (%d)\n" : "PASS nodevice\n", f);
