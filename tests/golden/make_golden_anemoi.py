@@ -4,8 +4,9 @@
 
 Sources: /root/reference/uzkge/src/anemoi/bn254/mod.rs:13-377 (generator, its inverse, round keys, preprocessed round keys, MDS
 matrix, alpha inverse) and /root/reference/uzkge/src/anemoi/tests.rs:10-21, 210-237 (the sponge and stream-cipher known answers
-for the input [1, 2, 3, 4]).  Output tests/golden/anemoi_bn254.json: data only.
+for the input [1, 2, 3, 4]).  Output tests/golden/anemoi_bn254.json: data only (the round-key tables as SHA-256 digests plus their first row).
 """
+import hashlib
 import json
 import os
 import re
@@ -23,9 +24,14 @@ def main():
         vals = re.findall(r'MontFp!\(\s*"(\d+)"\s*\)', body)
         return [vals[i:i + 2] for i in range(0, len(vals), 2)]
 
-    out = {name.lower(): table(name) for name in ("ROUND_KEYS_X", "ROUND_KEYS_Y", "PREPROCESSED_ROUND_KEYS_X", "PREPROCESSED_ROUND_KEYS_Y",
-                                                  "MDS_MATRIX")}
-    assert all(len(out[k]) == 14 for k in out if k != "mds_matrix") and len(out["mds_matrix"]) == 2
+    out = {}
+    for name in ("ROUND_KEYS_X", "ROUND_KEYS_Y", "PREPROCESSED_ROUND_KEYS_X", "PREPROCESSED_ROUND_KEYS_Y"):
+        t = table(name)
+        assert len(t) == 14
+        # a known answer for the 28 values of each table without carrying them: SHA-256 of "a,b;a,b;..." plus the first row
+        out[name.lower()] = {"sha256": hashlib.sha256(";".join(",".join(row) for row in t).encode()).hexdigest(), "first": t[0]}
+    out["mds_matrix"] = table("MDS_MATRIX")
+    assert len(out["mds_matrix"]) == 2
     out["generator"] = re.search(r'const GENERATOR: Fr = MontFp!\("(\d+)"\)', src).group(1)
     out["generator_inv"] = re.search(r'const GENERATOR_INV: Fr =\s*MontFp!\("(\d+)"\)', src).group(1)
     limbs = re.findall(r"(\d+)u64", src[src.index("fn get_alpha_inv"):])
