@@ -43,6 +43,17 @@ LOG_NTT = 22
 
 
 # ------------------------------------------------------------------------------------------------ inputs
+
+_JSON_OUT = None      # the process's real stdout once __main__ has redirected file descriptor 1 (see the bottom of the file)
+
+
+def emit(line: dict) -> None:
+    """Print the result line on the real stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def random_fr(n: int, seed: int) -> np.ndarray:
     """n uniform Fr elements as raw Montgomery limbs (uniform residues stay uniform under the Montgomery map)."""
     rng = np.random.default_rng(seed)
@@ -166,7 +177,7 @@ def run_reference(args, rank: int, world: int) -> int:
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -829,7 +840,7 @@ def main() -> int:
                     "d2h_bytes_per_step": first["d2h_bytes_per_step"]},
             "gpu_launches": int(launches), "clocks": clocks, "plonk": pl,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     head = "msm" if "msm" in results else "ntt"
@@ -858,11 +869,16 @@ def main() -> int:
         line["plonk"] = results["plonk"]
     if "ntt_distributed" in results:
         line["ntt_distributed"] = results["ntt_distributed"]
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line, the JSON: whatever a library writes to file descriptor 1 on the way (NCCL prints its version
+    # banner there) is sent to stderr instead
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     sys.exit(main())

@@ -49,7 +49,8 @@ def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
                           "--workload", "ntt"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-400:]
-    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert len(out.stdout.strip().splitlines()) == 1, "stdout must carry exactly the JSON line"
+    d = json.loads(out.stdout)
     assert d["impl"] == "reference" and "unavailable" not in d
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
