@@ -54,3 +54,15 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and "unavailable" not in d
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_our_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm exits non-zero, says why, and prints no result line."""
+    from uzkge_b200 import ffi
+
+    if ffi.lib().uzkge_cuda_device_count() > 0:
+        import pytest
+
+        pytest.skip("a CUDA device is visible")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode != 0 and out.stdout.strip() == "" and "no CPU path" in out.stderr
