@@ -14,8 +14,14 @@
  * Ownership: the caller owns every host buffer; the library copies in / out and owns all device memory.
  * Errors: 0 = OK, otherwise one of UZKGE_ERR_*; uzkge_cuda_last_error() gives a thread-local message.
  * There is NO CPU fallback: without a usable CUDA device every call fails with UZKGE_ERR_NO_DEVICE.
- * Threading: every entry point may be called from any thread; calls are serialised per process
- * (one process drives one GPU; multi-GPU = one process per GPU, see uzkge_b200/dist.py).
+ * Threading: every entry point may be called from any thread; calls are serialised PER DEVICE (one mutex and one internal stream per
+ * GPU), so threads working on different GPUs run concurrently.
+ * Devices: a call goes to the device of the SRS handle it names (handles carry their device), otherwise to the device the calling
+ * thread selected with uzkge_cuda_init / uzkge_cuda_set_device, otherwise to the first device initialised.  One process can drive all
+ * GPUs of the box: uzkge_cuda_init_devices + uzkge_cuda_srs_upload_multi (below); one process per GPU (uzkge_b200/dist.py) works too.
+ * Streams: the *_device entry points enqueue on the caller's stream.  Workspaces shared by all streams of a device (the MSM buffers
+ * of an SRS handle, the scan workspace of the polynomial calls, the small result buffer) are ordered internally: when consecutive
+ * calls use different streams the later stream waits (cudaStreamWaitEvent) for the earlier call's work; nothing blocks the host.
  */
 #ifndef UZKGE_CUDA_H
 #define UZKGE_CUDA_H
@@ -42,10 +48,20 @@ extern "C" {
 #define UZKGE_ERR_ARG 6         /* null pointer / bad flag                                             */
 #define UZKGE_ERR_INTERNAL 7
 
-/* Bind this process to CUDA device `device` (-1: keep the current device, e.g. the one torch selected).
- * Idempotent and thread-safe.  Must be called before any other entry point. */
+/* Initialise CUDA device `device` (-1: the calling thread's device, else the process default, else the CUDA runtime's current device,
+ * e.g. the one torch selected) and make it the calling thread's device.  Idempotent and thread-safe; the first device initialised
+ * becomes the process default.  Every entry point initialises its device on first use, so calling this is optional. */
 UZKGE_API int32_t uzkge_cuda_init(int32_t device);
+/* Route the calling thread's subsequent calls (those that do not name an SRS handle) to `device`; uzkge_cuda_get_device: the device
+ * they currently go to (-1 before anything was initialised). */
+UZKGE_API int32_t uzkge_cuda_set_device(int32_t device);
+UZKGE_API int32_t uzkge_cuda_get_device(void);
 UZKGE_API int32_t uzkge_cuda_device_count(void);
+/* One process, several GPUs (SURVEY 8b `uzkge_cuda_init(device_count)`, 8e): initialise devices 0 .. device_count - 1 (0 = all visible)
+ * as the device GROUP and enable peer access between them.  The reference is a single process (shuffle/src/sdk.rs:196-227), so this
+ * is how its Rust host reaches the other GPUs of the box. */
+UZKGE_API int32_t uzkge_cuda_init_devices(int32_t device_count);
+UZKGE_API int32_t uzkge_cuda_group_size(void);
 UZKGE_API const char* uzkge_cuda_last_error(void);
 /* "uzkge-b200 <version> sm_100a" */
 UZKGE_API const char* uzkge_cuda_version(void);
@@ -58,6 +74,17 @@ UZKGE_API const char* uzkge_cuda_version(void);
  * window_bits = 0 lets the library choose c from n. */
 UZKGE_API int32_t uzkge_cuda_srs_upload(const uint64_t* affine_xy, size_t n, uint32_t window_bits, uint64_t* handle);
 UZKGE_API int32_t uzkge_cuda_srs_free(uint64_t handle);
+/* The same SRS over the device group; the handle is accepted by uzkge_cuda_msm_g1, uzkge_cuda_msm_g1_batch, uzkge_cuda_srs_info and
+ * uzkge_cuda_srs_free (the device-pointer variants need a single-device handle).
+ *   UZKGE_MULTI_SPLIT      : device i keeps bases [i n / G, (i + 1) n / G) (tables included) -- "MSM points are split per GPU and the
+ *                            partial G1 sums are combined with one projective add each": every MSM runs on all devices at once, one
+ *                            worker thread per device, the G partial sums (96 B) are added on the host.
+ *   UZKGE_MULTI_REPLICATED : every device keeps the whole SRS -- "a PlonK round's independent polynomial commitments are distributed
+ *                            across GPUs" (plonk/prover.rs:132-192, helpers.rs:1323-1408): uzkge_cuda_msm_g1_batch deals MSM j to
+ *                            device j mod G; a single uzkge_cuda_msm_g1 runs on the first device. */
+#define UZKGE_MULTI_SPLIT 0
+#define UZKGE_MULTI_REPLICATED 1
+UZKGE_API int32_t uzkge_cuda_srs_upload_multi(const uint64_t* affine_xy, size_t n, uint32_t window_bits, int32_t mode, uint64_t* handle);
 
 /* Setup path: out[i] = tau^i * G (affine, Montgomery), i < n -- the G1 half of KZGCommitmentScheme::new
  * (kzg_poly_commitment.rs:183-204: n sequential scalar multiplications on the CPU).  tau: Montgomery Fr. */
@@ -111,8 +138,12 @@ UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]);
 
 /* ---- device-resident variants ----------------------------------------------------------------------
  * Same semantics with DEVICE pointers and a caller-provided cudaStream_t (NULL = default stream); nothing
- * is copied and nothing synchronises: this is what a device-resident prover pipeline and the
- * HBM-resident benchmark call.  d_out may equal d_in for the NTT; d_scratch holds domain_size elements. */
+ * is copied and, in the steady state, nothing synchronises: this is what a device-resident prover pipeline and the
+ * HBM-resident benchmark call.  d_out may equal d_in for the NTT; d_scratch holds domain_size elements.
+ * Exceptions (first-use set-up, hence not CUDA-graph capturable until warmed up): the FIRST transform of a domain size, and the first
+ * use of a (size, coset shift) pair, build their twiddle / coset tables (cudaMalloc + one stream synchronisation); at most 8 coset
+ * tables are kept per device, rotating more than 8 (size, shift) pairs rebuilds them (cudaFree + cudaMalloc);
+ * uzkge_cuda_grand_product_fr_device and uzkge_cuda_fr_trimmed_len_device read one value back and say so below. */
 UZKGE_API int32_t uzkge_cuda_msm_g1_device(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, void* d_out_jac, void* stream);
 /* k MSMs over srs[base_offset ..] in one pass (one sort, one accumulate launch, concurrent reductions); d_scalars is a HOST
  * array of k device pointers, d_out_jac holds k * 12 words on the device. */

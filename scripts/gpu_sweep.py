@@ -1,5 +1,8 @@
 """BASELINE.json configs[1] and configs[2] sweeps, device-resident (CUDA events): G1 MSM 2^16..2^24 and Fr NTT / iNTT /
 coset-FFT 2^16..2^24 plus the mixed-radix sizes 3*2^k the quotient domain needs.  Writes one JSON document.
+Every row is CHECKED before it is written (a timing of an unverified result is refused): MSM results against the SRS trapdoor
+(MSM(srs, f) = f(tau) G, CPU oracle: Horner + one scalar multiplication); transforms through Horner spot checks of the outputs at
+random indices on the CPU oracle, and the inverse variants through the round trip.
 
     python scripts/gpu_sweep.py [out.json] [max_log_msm]
 """
@@ -7,6 +10,7 @@ import sys, os, json
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
 from uzkge_b200 import ffi
+from oracle import cpu as oc   # checker only
 import bench as B
 
 ffi.init(0)
@@ -38,6 +42,22 @@ for lg, mixed in [(l, False) for l in range(16, 25)] + [(l, True) for l in range
     o = torch.empty_like(x)
     s = torch.empty_like(x)
     row = {"n": n, "label": ("3*2^%d" % lg) if mixed else ("2^%d" % lg)}
+    # checks first: fft / coset fft outputs at two random indices equal the polynomial's value there (Horner on the CPU oracle);
+    # ifft(fft(x)) = x and coset_ifft(coset_fft(x)) = x with the inverse shift
+    xh = x.cpu().numpy().view(np.uint64).reshape(n, 4)
+    w = ffi.fr_root_of_unity(n)
+    k_inv = oc.fr_inv(k_shift)
+    for cs_ in (None, k_shift):
+        ffi.ntt_fr_device(x.data_ptr(), o.data_ptr(), s.data_ptr(), n, n, False, cs_)
+        oh = o.cpu().numpy().view(np.uint64).reshape(n, 4)
+        for idx in (1, int(np.random.default_rng(lg).integers(2, n))):
+            point = oc.fr_pow(w, idx) if cs_ is None else oc.fr_mul(oc.fr_pow(w, idx).reshape(1, 4), cs_.reshape(1, 4))[0]
+            if not np.array_equal(oc.fr_eval(xh, point), oh[idx]):
+                raise SystemExit(f"sweep: transform {row['label']} differs from the oracle at index {idx} -- refusing to write the row")
+        ffi.ntt_fr_device(o.data_ptr(), o.data_ptr(), s.data_ptr(), n, n, True, None if cs_ is None else k_inv)
+        if not torch.equal(o, x):
+            raise SystemExit(f"sweep: inverse transform {row['label']} does not return the input -- refusing to write the row")
+    row["checked"] = "Horner spot checks (2 indices, fft and coset fft) + inverse round trips"
     for name, inv, cs in (("fft", False, None), ("ifft", True, None), ("coset_fft", False, k_shift), ("coset_ifft", True, k_shift)):
         ms = timeit(lambda: ffi.ntt_fr_device(x.data_ptr(), o.data_ptr(), s.data_ptr(), n, n, inv, cs), 10 if n < (1 << 23) else 5)
         row[name + "_us"] = round(ms * 1e3, 1)
@@ -69,6 +89,12 @@ for lg in range(16, max_log_msm + 1):
             m = (u >= 0.8) & (u < 0.9)
             sc_h[m] = SMALL[rng.integers(0, 1 << 16, int(m.sum()))]
         sc = torch.from_numpy(sc_h.view(np.int64)).to(dev)
+        ffi.msm_g1_device(h, sc.data_ptr(), n, out.data_ptr())
+        got = out.cpu().numpy().view(np.uint64)
+        want = oc.g1_mul(bases[0], oc.fr_eval(sc_h, tau))
+        if not np.array_equal(oc.g1_to_affine(got), oc.g1_to_affine(want)):
+            raise SystemExit(f"sweep: MSM 2^{lg} ({kind}) differs from f(tau) G -- refusing to write the row")
+        row["checked"] = "MSM(srs, f) == f(tau) G on the CPU oracle, uniform and witness-like scalars"
         ms = timeit(lambda: ffi.msm_g1_device(h, sc.data_ptr(), n, out.data_ptr()), 5, 2)
         row[kind + "_us"] = round(ms * 1e3, 1)
         row[kind + "_points_per_s"] = n / ms * 1e3

@@ -9,6 +9,8 @@ using namespace uz;
 extern "C" {
 void uzhost_fq_mul(const fe* a, const fe* b, fe* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fe_mul<FqP>(a[i], b[i]); }
 void uzhost_fr_mul(const fe* a, const fe* b, fe* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fe_mul<FrP>(a[i], b[i]); }
+void uzhost_fq_sqr(const fe* a, fe* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fe_sqr<FqP>(a[i]); }
+void uzhost_fr_sqr(const fe* a, fe* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fe_sqr<FrP>(a[i]); }
 void uzhost_fq_add(const fe* a, const fe* b, fe* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fe_add<FqP>(a[i], b[i]); }
 void uzhost_fq_sub(const fe* a, const fe* b, fe* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fe_sub<FqP>(a[i], b[i]); }
 void uzhost_fr_add(const fe* a, const fe* b, fe* o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = fe_add<FrP>(a[i], b[i]); }

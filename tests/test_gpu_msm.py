@@ -331,3 +331,56 @@ def test_full_size_trapdoor_property(gpu, oc, bn):
             assert same_point(oc, gpu.msm_g1(h, sc), want)
     finally:
         gpu.srs_free(h)
+
+
+def witness_like_fast(oc, n, seed):
+    """witness_like without per-element Python integers (for 2^22 and above): the small values are written as canonical limbs and
+    converted to Montgomery form by the oracle in one call."""
+    rng = np.random.default_rng(seed)
+    s = oc.random_fr(n, seed)
+    u = rng.random(n)
+    canon = np.zeros((n, 4), dtype=np.uint64)
+    canon[:, 0] = np.where(u < 0.8, rng.integers(0, 2, size=n), rng.integers(0, 1 << 16, size=n)).astype(np.uint64)
+    small = oc.fr_to_mont(canon)
+    s[u < 0.5] = 0
+    m = (u >= 0.5) & (u < 0.9)
+    s[m] = small[m]
+    return s
+
+
+@pytest.mark.parametrize("log_n", [22, 24])
+def test_top_of_the_sweep_trapdoor_property(gpu, oc, log_n):
+    """BASELINE configs[1] above 2^20 (2^22: 13 windows of c = 20; 2^24: the widest window, the largest `f n + i | sign` entry codes,
+    13 GiB of tables): the same arithmetic-progression property, uniform and witness-like scalars, plus a prefix and an offset range."""
+    n = 1 << log_n
+    two = oc.g1_random_points(2, 1000 + log_n)
+    pts = oc.g1_progression(two[0], two[1], n)
+    h = gpu.srs_upload(pts)
+
+    def want(sc, first):
+        s0, s1 = oc.fr_weighted_sums(sc)      # sum s_i (P0 + (first + i) Q) = (sum s_i) (P0 + first Q) + (sum i s_i) Q
+        return oc.g1_add_jac(oc.g1_mul(pts[first], s0), oc.g1_mul(two[1], s1))
+
+    try:
+        for sc in (oc.random_fr(n, 17 + log_n), witness_like_fast(oc, n, 18 + log_n)):
+            assert same_point(oc, gpu.msm_g1(h, sc), want(sc, 0))
+        m = n // 2 + 12345
+        assert same_point(oc, gpu.msm_g1(h, sc[:m]), want(sc[:m], 0))
+        assert same_point(oc, gpu.msm_g1(h, sc[:m], base_offset=n - m), want(sc[:m], n - m))
+    finally:
+        gpu.srs_free(h)
+
+
+def test_largest_size_against_the_trapdoor(gpu, oc):
+    """2^24 over a powers-of-tau SRS generated on the device: MSM(srs, f) = f(tau) G (SURVEY 8c golden 6) -- O(n) field work on the
+    CPU and one scalar multiplication; bases of full entropy in every coordinate (the progression above has structured bases)."""
+    n = 1 << 24
+    tau = oc.random_fr(1, 4242)[0]
+    srs = gpu.srs_generate(tau, n)
+    h = gpu.srs_upload(srs)
+    try:
+        f = oc.random_fr(n, 4243)
+        want = oc.g1_mul(srs[0], oc.fr_eval(f, tau))
+        assert same_point(oc, gpu.msm_g1(h, f), want)
+    finally:
+        gpu.srs_free(h)

@@ -90,9 +90,9 @@ def test_prover_rejects_an_unsatisfied_witness(gpu, bn):
     pcs.close()
 
 
-@pytest.mark.parametrize("log_size", [10, 14, 20])
+@pytest.mark.parametrize("log_size", [10, 14, 20, 22])
 def test_synthetic_circuit_proof_verifies(gpu, bn, oc, log_size):
-    """BASELINE configs[4] at test size: a synthetic circuit of add / mul gates built in bulk, proved on the GPU, checked by the
+    """BASELINE configs[4] up to its full size (2^22 gates): a synthetic circuit of add / mul gates built in bulk, proved on the GPU, checked by the
     restated verifier under the SRS trapdoor (O(1) group operations, independent of n); the witness satisfies every gate."""
     from oracle import plonk_prover as pp
     from uzkge_b200 import KZGCommitmentSchemeBN254, plonk

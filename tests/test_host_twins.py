@@ -52,6 +52,29 @@ def test_field_ops_match_oracle(uz, oc, bn, field):
     assert bn.array_to_ints(o, None, mont=False) == [(x - y) % mod for x, y in zip(ai, bi)]
 
 
+@pytest.mark.parametrize("field", ["fr", "fq"])
+def test_dedicated_squaring_matches_the_product(uz, oc, bn, field):
+    """fe_sqr (ff.cuh: 108 multiplier instructions, separate reduction with deferred carries) == fe_mul(a, a) == the oracle's product, on
+    edge values, on limb patterns that maximise the cross products and the carries (all-ones limbs below the modulus), and on random
+    values."""
+    mod = bn.FR if field == "fr" else bn.FQ
+    pats = []
+    for k in range(8):
+        for fill in (0xFFFFFFFF, 0x80000000, 0xFFFF0000, 1):
+            v = sum(fill << (32 * j) for j in range(k + 1))
+            pats += [v % mod, (mod - v) % mod, (v << (32 * (7 - k))) % mod]
+    pats += [mod - 1 - (1 << (32 * j)) for j in range(8)] + [(mod >> (32 * j)) << (32 * j) for j in range(1, 8)]
+    a = np.concatenate([edge_values(oc, bn, mod), np.array([bn.int_to_limbs(v) for v in pats], dtype=np.uint64), oc.random_fr(20000, 31)])
+    n = a.shape[0]
+    o = np.empty_like(a)
+    getattr(uz, f"uzhost_{field}_sqr")(p(a), p(o), C.c_size_t(n))
+    want = oc.fr_mul(a, a) if field == "fr" else oc.fq_mul(a, a)
+    assert np.array_equal(o, want)
+    o2 = np.empty_like(a)
+    getattr(uz, f"uzhost_{field}_mul")(p(a), p(a), p(o2), C.c_size_t(n))
+    assert np.array_equal(o, o2)
+
+
 def test_constants_and_inverse(uz, oc, bn):
     out = np.zeros((4, 4), dtype=np.uint64)
     uz.uzhost_consts(p(out))

@@ -7,18 +7,26 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 
 #include "devmem.cuh"
 #include "internal.h"
 
 namespace uz {
 std::atomic<uint64_t> g_launches{0};
-Profiler g_prof;
+static Profiler g_profs[UZ_MAX_DEVICES];
+Profiler& prof_for_current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return g_profs[(d >= 0 && d < UZ_MAX_DEVICES) ? d : 0];
+}
 }
 
 using namespace uz;
@@ -51,6 +59,30 @@ struct DevBuf {
     }
 };
 
+// Orders the users of a workspace that is shared by every stream of a device (the MSM buffers of an SRS handle, the scan
+// workspace of the polynomial engine, the small result buffer): the next user's stream waits for the previous user's last
+// launch when the two streams differ.  Same stream: nothing is enqueued.
+struct Fence {
+    cudaEvent_t ev = nullptr;
+    cudaStream_t last = nullptr;
+    bool used = false;
+    cudaError_t enter(cudaStream_t st) {
+        if (used && last != st) return cudaStreamWaitEvent(st, ev, 0);
+        return cudaSuccess;
+    }
+    cudaError_t leave(cudaStream_t st) {
+        if (!ev) {
+            cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        last = st;
+        used = true;
+        return cudaEventRecord(ev, st);
+    }
+};
+
+// One per CUDA device, created on first use.  Every entry point works on ONE device's state under that device's mutex: calls
+// aimed at different devices (different threads, or the workers of a multi-device call) run concurrently.
 struct State {
     std::mutex mu;
     bool ready = false;
@@ -61,13 +93,22 @@ struct State {
     std::unique_ptr<MsmEngine> msm;
     std::unique_ptr<PolyEngine> poly;
     std::map<uint64_t, MsmSrs> srs;
+    std::map<uint64_t, Fence> srs_fence;
+    Fence poly_fence, small_fence;
     uint64_t next_handle = 1;
     DevBuf data, scratch, scalars, small;
     cudaStream_t copy_stream = nullptr, out_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
-    uint32_t ntt_log_tile = 10, ntt_max_log_r = 10, ntt_two_pass_max = 18;  // measured best on B200 (scripts/gpu_ntt_cfg.py)
 };
-State g;
+struct Config {
+    uint32_t ntt_log_tile = 10, ntt_max_log_r = 10, ntt_two_pass_max = 18;  // measured best on B200 (scripts/gpu_ntt_cfg.py)
+    uint32_t ntt_big_threads = 1024, msm_lanes = 0, msm_affine = 0;
+};
+std::mutex g_reg_mu;                  // guards the registry below (never held while a device's work is enqueued)
+State* g_states[UZ_MAX_DEVICES] = {};
+Config g_cfg;
+int g_default_device = -1;            // the first device initialised: where calls of threads that never chose a device go
+thread_local int t_device = -1;       // the device this thread's calls go to (uzkge_cuda_init / uzkge_cuda_set_device)
 
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     char buf[512];
@@ -89,59 +130,92 @@ int engine_fail(int rc, const char* what) {
     return fail(rc, what);
 }
 
-// caller holds g.mu
-int ensure_init(int device) {
-    if (g.ready) {
-        cudaError_t e = cudaSetDevice(g.device);
-        if (e != cudaSuccess) return fail_cuda("cudaSetDevice", e);
-        return UZKGE_OK;
-    }
+// SRS handles carry their device: bits 48..55 = device + 1, bit 63 = multi-device handle (see the bottom of this file)
+constexpr uint64_t HANDLE_MULTI = 1ull << 63;
+inline int handle_device(uint64_t h) { return (int)((h >> 48) & 0xff) - 1; }
+
+// Which device does this call go to?  `want` >= 0: that device; -1: the calling thread's device, else the process default, else
+// the device current in the CUDA runtime (e.g. the one torch selected).  Creates and initialises the state on first use.
+int enter_state(int want, State** out) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
         cudaGetLastError();
         return fail(UZKGE_ERR_NO_DEVICE, "no CUDA device: uzkge-b200 has no CPU path");
     }
-    if (device >= 0) {
-        if (device >= count) return fail(UZKGE_ERR_NO_DEVICE, "device index out of range");
-        e = cudaSetDevice(device);
+    int dev = want >= 0 ? want : t_device;
+    if (dev < 0) dev = g_default_device;
+    if (dev < 0) {
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return fail_cuda("cudaGetDevice", e);
+    }
+    if (dev >= count || dev >= UZ_MAX_DEVICES) return fail(UZKGE_ERR_NO_DEVICE, "device index out of range");
+    std::lock_guard<std::mutex> reg(g_reg_mu);
+    State* st = g_states[dev];
+    if (!st) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) return fail_cuda("cudaGetDeviceProperties", e);
+        if (prop.major != 10) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "device %d (%.64s, sm_%d%d) is not a Blackwell sm_100 part: kernels are built for sm_100a only",
+                     dev, prop.name, prop.major, prop.minor);
+            return fail(UZKGE_ERR_NO_DEVICE, buf);
+        }
+        e = cudaSetDevice(dev);
         if (e != cudaSuccess) return fail_cuda("cudaSetDevice", e);
+        std::unique_ptr<State> fresh(new State());
+        e = cudaStreamCreateWithFlags(&fresh->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return fail_cuda("cudaStreamCreate", e);
+        fresh->device = dev;
+        fresh->sm_count = prop.multiProcessorCount;
+        fresh->ntt.reset(new NttEngine(fresh->sm_count));
+        fresh->ntt->configure(g_cfg.ntt_log_tile, g_cfg.ntt_max_log_r, g_cfg.ntt_two_pass_max);
+        fresh->ntt->set_big_threads(g_cfg.ntt_big_threads);
+        fresh->msm.reset(new MsmEngine(fresh->sm_count));
+        fresh->msm->force_lanes(g_cfg.msm_lanes);
+        fresh->msm->set_affine(g_cfg.msm_affine);
+        fresh->poly.reset(new PolyEngine());
+        fresh->ready = true;
+        st = g_states[dev] = fresh.release();
+        if (g_default_device < 0) g_default_device = dev;
     }
-    int dev = 0;
-    e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return fail_cuda("cudaGetDevice", e);
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, dev);
-    if (e != cudaSuccess) return fail_cuda("cudaGetDeviceProperties", e);
-    if (prop.major != 10) {
-        char buf[256];
-        snprintf(buf, sizeof buf, "device %d (%.64s, sm_%d%d) is not a Blackwell sm_100 part: kernels are built for sm_100a only",
-                 dev, prop.name, prop.major, prop.minor);
-        return fail(UZKGE_ERR_NO_DEVICE, buf);
-    }
-    e = cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) return fail_cuda("cudaStreamCreate", e);
-    g.device = dev;
-    g.sm_count = prop.multiProcessorCount;
-    g.ntt.reset(new NttEngine(g.sm_count));
-    g.ntt->configure(g.ntt_log_tile, g.ntt_max_log_r, g.ntt_two_pass_max);
-    g.msm.reset(new MsmEngine(g.sm_count));
-    g.poly.reset(new PolyEngine());
-    g.ready = true;
+    *out = st;
     return UZKGE_OK;
 }
 
-#define API_ENTER(dev)                           \
-    std::lock_guard<std::mutex> lock__(g.mu);    \
-    do {                                         \
-        int rc__ = ensure_init(dev);             \
-        if (rc__ != UZKGE_OK) return rc__;       \
+// st__ is the device state of this call; `g` reads like the single global it used to be
+#define g (*st__)
+#define API_ENTER(dev)                                                   \
+    State* st__ = nullptr;                                               \
+    do {                                                                 \
+        int rc__ = enter_state((dev), &st__);                            \
+        if (rc__ != UZKGE_OK) return rc__;                               \
+    } while (0);                                                         \
+    std::lock_guard<std::mutex> lock__(st__->mu);                        \
+    do {                                                                 \
+        cudaError_t e__ = cudaSetDevice(st__->device);                   \
+        if (e__ != cudaSuccess) return fail_cuda("cudaSetDevice", e__);  \
     } while (0)
+// entry points that take an SRS handle run on the handle's device, whatever device the thread selected
+#define API_ENTER_HANDLE(handle, what)                                                        \
+    if (handle_device(handle) < 0) return fail(UZKGE_ERR_HANDLE, what ": unknown handle");    \
+    API_ENTER(handle_device(handle))
 
 #define CUDA_OR_FAIL(expr, what)                         \
     do {                                                 \
         cudaError_t e__ = (expr);                        \
         if (e__ != cudaSuccess) return fail_cuda(what, e__); \
+    } while (0)
+
+// run `expr` (an engine call that enqueues work on `st` using a workspace guarded by `f`) ordered after the previous user of that
+// workspace on any other stream
+#define FENCED(f, st, what, expr)                                                   \
+    do {                                                                            \
+        CUDA_OR_FAIL((f).enter(st), what ": stream order");                         \
+        rc = (expr);                                                                \
+        cudaError_t le__ = (f).leave(st);                                           \
+        if (rc == UZKGE_OK && le__ != cudaSuccess) return fail_cuda(what ": stream order", le__); \
     } while (0)
 
 // ---- K1 test / roof kernels
@@ -177,7 +251,20 @@ extern "C" {
 
 UZKGE_API int32_t uzkge_cuda_init(int32_t device) {
     API_ENTER(device);
+    t_device = st__->device;
     return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_set_device(int32_t device) {
+    if (device < 0) return fail(UZKGE_ERR_ARG, "set_device: device index must be >= 0");
+    API_ENTER(device);
+    t_device = st__->device;
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_get_device(void) {
+    if (t_device >= 0) return t_device;
+    return g_default_device;
 }
 
 UZKGE_API int32_t uzkge_cuda_device_count(void) {
@@ -192,34 +279,40 @@ UZKGE_API int32_t uzkge_cuda_device_count(void) {
 UZKGE_API const char* uzkge_cuda_last_error(void) { return t_error.c_str(); }
 UZKGE_API const char* uzkge_cuda_version(void) { return "uzkge-b200 0.1.0 sm_100a"; }
 
-UZKGE_API int32_t uzkge_cuda_srs_upload(const uint64_t* affine_xy, size_t n, uint32_t window_bits, uint64_t* handle) {
+static int32_t srs_upload_one(int device, const uint64_t* affine_xy, size_t n, uint32_t window_bits, uint64_t* handle) {
     if (!affine_xy || !handle) return fail(UZKGE_ERR_ARG, "srs_upload: null pointer");
-    API_ENTER(-1);
+    API_ENTER(device);
     MsmSrs s;
     int rc = g.msm->upload(affine_xy, n, window_bits, &s, g.stream);
     if (rc != UZKGE_OK) {
         g.msm->release(&s);
         return engine_fail(rc, "srs_upload");
     }
-    const uint64_t h = g.next_handle++;
+    const uint64_t h = ((uint64_t)(g.device + 1) << 48) | g.next_handle++;
     g.srs[h] = s;
     *handle = h;
     return UZKGE_OK;
 }
 
-UZKGE_API int32_t uzkge_cuda_srs_free(uint64_t handle) {
-    API_ENTER(-1);
+static int32_t srs_free_one(uint64_t handle) {
+    API_ENTER_HANDLE(handle, "srs_free");
     auto it = g.srs.find(handle);
     if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "srs_free: unknown handle");
     cudaStreamSynchronize(g.stream);
+    cudaDeviceSynchronize();   // *_device calls may still be running on the caller's streams
     g.msm->release(&it->second);
     g.srs.erase(it);
+    auto fit = g.srs_fence.find(handle);
+    if (fit != g.srs_fence.end()) {
+        if (fit->second.ev) cudaEventDestroy(fit->second.ev);
+        g.srs_fence.erase(fit);
+    }
     return UZKGE_OK;
 }
 
-UZKGE_API int32_t uzkge_cuda_srs_info(uint64_t handle, uzkge_srs_info* info) {
+static int32_t srs_info_one(uint64_t handle, uzkge_srs_info* info) {
     if (!info) return fail(UZKGE_ERR_ARG, "srs_info: null pointer");
-    API_ENTER(-1);
+    API_ENTER_HANDLE(handle, "srs_info");
     auto it = g.srs.find(handle);
     if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "srs_info: unknown handle");
     info->window_bits = it->second.c;
@@ -232,9 +325,9 @@ UZKGE_API int32_t uzkge_cuda_srs_info(uint64_t handle, uzkge_srs_info* info) {
     return UZKGE_OK;
 }
 
-UZKGE_API int32_t uzkge_cuda_msm_g1_batch(uint64_t handle, const uint64_t* const* scalars, const size_t* n, size_t k, uint64_t* out_jac) {
+static int32_t msm_g1_batch_one(uint64_t handle, const uint64_t* const* scalars, const size_t* n, size_t k, uint64_t* out_jac) {
     if (k && (!scalars || !n || !out_jac)) return fail(UZKGE_ERR_ARG, "msm_g1_batch: null pointer");
-    API_ENTER(-1);
+    API_ENTER_HANDLE(handle, "msm_g1");
     auto it = g.srs.find(handle);
     if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1: unknown handle");
     if (k == 0) return UZKGE_OK;
@@ -265,20 +358,23 @@ UZKGE_API int32_t uzkge_cuda_msm_g1_batch(uint64_t handle, const uint64_t* const
         ptrs[j] = d_s + off;
         off += n[j];
     }
-    int rc = g.msm->run_pipelined(&s, 0, ptrs.data(), n, k, d_o, g.stream, g.copy_events.data());
+    int rc;
+    CUDA_OR_FAIL(g.small_fence.enter(g.stream), "msm_g1_batch: stream order");
+    FENCED(g.srs_fence[handle], g.stream, "msm_g1_batch", g.msm->run_pipelined(&s, 0, ptrs.data(), n, k, d_o, g.stream, g.copy_events.data()));
     if (rc != UZKGE_OK) {
         cudaStreamSynchronize(g.copy_stream);
         cudaStreamSynchronize(g.stream);
         return engine_fail(rc, "msm_g1_batch: launch");
     }
     CUDA_OR_FAIL(cudaMemcpyAsync(out_jac, d_o, k * sizeof(jacobian), cudaMemcpyDeviceToHost, g.stream), "msm_g1: D2H");
+    CUDA_OR_FAIL(g.small_fence.leave(g.stream), "msm_g1_batch: stream order");
     CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "msm_g1: execution");
     return UZKGE_OK;
 }
 
-UZKGE_API int32_t uzkge_cuda_msm_g1(uint64_t handle, size_t base_offset, const uint64_t* scalars, size_t n, uint64_t out_jac[12]) {
+static int32_t msm_g1_one(uint64_t handle, size_t base_offset, const uint64_t* scalars, size_t n, uint64_t out_jac[12]) {
     if (!out_jac || (n && !scalars)) return fail(UZKGE_ERR_ARG, "msm_g1: null pointer");
-    API_ENTER(-1);
+    API_ENTER_HANDLE(handle, "msm_g1");
     auto it = g.srs.find(handle);
     if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1: unknown handle");
     MsmSrs& s = it->second;
@@ -286,32 +382,39 @@ UZKGE_API int32_t uzkge_cuda_msm_g1(uint64_t handle, size_t base_offset, const u
     CUDA_OR_FAIL(g.scalars.reserve(n * sizeof(fe) + 32), "msm_g1: scalar buffer");
     CUDA_OR_FAIL(g.small.reserve(4096), "msm_g1: output buffer");
     if (n) CUDA_OR_FAIL(cudaMemcpyAsync(g.scalars.p, scalars, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "msm_g1: H2D");
-    int rc = g.msm->run(&s, base_offset, (const fe*)g.scalars.p, n, (jacobian*)g.small.p, g.stream);
+    int rc;
+    CUDA_OR_FAIL(g.small_fence.enter(g.stream), "msm_g1: stream order");
+    FENCED(g.srs_fence[handle], g.stream, "msm_g1", g.msm->run(&s, base_offset, (const fe*)g.scalars.p, n, (jacobian*)g.small.p, g.stream));
     if (rc != UZKGE_OK) {
         cudaStreamSynchronize(g.stream);
         return engine_fail(rc, "msm_g1: launch");
     }
     CUDA_OR_FAIL(cudaMemcpyAsync(out_jac, g.small.p, sizeof(jacobian), cudaMemcpyDeviceToHost, g.stream), "msm_g1: D2H");
+    CUDA_OR_FAIL(g.small_fence.leave(g.stream), "msm_g1: stream order");
     CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "msm_g1: execution");
     return UZKGE_OK;
 }
 
 UZKGE_API int32_t uzkge_cuda_msm_g1_device(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, void* d_out_jac, void* stream) {
     if (!d_out_jac || (n && !d_scalars)) return fail(UZKGE_ERR_ARG, "msm_g1_device: null pointer");
-    API_ENTER(-1);
+    API_ENTER_HANDLE(handle, "msm_g1_device");
     auto it = g.srs.find(handle);
     if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1_device: unknown handle");
-    int rc = g.msm->run(&it->second, base_offset, (const fe*)d_scalars, n, (jacobian*)d_out_jac, (cudaStream_t)stream);
+    int rc;
+    FENCED(g.srs_fence[handle], (cudaStream_t)stream, "msm_g1_device",
+           g.msm->run(&it->second, base_offset, (const fe*)d_scalars, n, (jacobian*)d_out_jac, (cudaStream_t)stream));
     return engine_fail(rc, "msm_g1_device");
 }
 
 UZKGE_API int32_t uzkge_cuda_msm_g1_batch_device(uint64_t handle, size_t base_offset, const void* const* d_scalars, const size_t* n,
                                                  size_t k, void* d_out_jac, void* stream) {
     if (k && (!d_scalars || !n || !d_out_jac)) return fail(UZKGE_ERR_ARG, "msm_g1_batch_device: null pointer");
-    API_ENTER(-1);
+    API_ENTER_HANDLE(handle, "msm_g1_batch_device");
     auto it = g.srs.find(handle);
     if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1_batch_device: unknown handle");
-    int rc = g.msm->run_pipelined(&it->second, base_offset, (const fe* const*)d_scalars, n, k, (jacobian*)d_out_jac, (cudaStream_t)stream);
+    int rc;
+    FENCED(g.srs_fence[handle], (cudaStream_t)stream, "msm_g1_batch_device",
+           g.msm->run_pipelined(&it->second, base_offset, (const fe* const*)d_scalars, n, k, (jacobian*)d_out_jac, (cudaStream_t)stream));
     if (rc == UZKGE_ERR_SIZE) return fail(rc, "msm_g1_batch_device: range outside the SRS");
     return engine_fail(rc, "msm_g1_batch_device");
 }
@@ -487,9 +590,12 @@ UZKGE_API int32_t uzkge_cuda_poly_eval_fr(const uint64_t* coefs, size_t n, const
     CUDA_OR_FAIL(cudaMemcpyAsync(g.data.p, coefs, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "poly_eval_fr: H2D");
     fe z;
     memcpy(&z, x, sizeof(fe));
-    int rc = g.poly->horner((const fe*)g.data.p, n, z, nullptr, (fe*)g.small.p, g.stream);
+    int rc;
+    CUDA_OR_FAIL(g.small_fence.enter(g.stream), "poly_eval_fr: stream order");
+    FENCED(g.poly_fence, g.stream, "poly_eval_fr", g.poly->horner((const fe*)g.data.p, n, z, nullptr, (fe*)g.small.p, g.stream));
     if (rc != UZKGE_OK) return engine_fail(rc, "poly_eval_fr");
     CUDA_OR_FAIL(cudaMemcpyAsync(out, g.small.p, sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "poly_eval_fr: D2H");
+    CUDA_OR_FAIL(g.small_fence.leave(g.stream), "poly_eval_fr: stream order");
     CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "poly_eval_fr: execution");
     return UZKGE_OK;
 }
@@ -504,10 +610,13 @@ UZKGE_API int32_t uzkge_cuda_poly_div_linear_fr(const uint64_t* coefs, size_t n,
     CUDA_OR_FAIL(cudaMemcpyAsync(g.data.p, coefs, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "poly_div_linear_fr: H2D");
     fe z;
     memcpy(&z, z_in, sizeof(fe));
-    int rc = g.poly->horner((const fe*)g.data.p, n, z, (fe*)g.scratch.p, (fe*)g.small.p, g.stream);
+    int rc;
+    CUDA_OR_FAIL(g.small_fence.enter(g.stream), "poly_div_linear_fr: stream order");
+    FENCED(g.poly_fence, g.stream, "poly_div_linear_fr", g.poly->horner((const fe*)g.data.p, n, z, (fe*)g.scratch.p, (fe*)g.small.p, g.stream));
     if (rc != UZKGE_OK) return engine_fail(rc, "poly_div_linear_fr");
     if (n > 1) CUDA_OR_FAIL(cudaMemcpyAsync(quotient, g.scratch.p, (n - 1) * sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "poly_div_linear_fr: D2H");
     CUDA_OR_FAIL(cudaMemcpyAsync(rem, g.small.p, sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "poly_div_linear_fr: D2H");
+    CUDA_OR_FAIL(g.small_fence.leave(g.stream), "poly_div_linear_fr: stream order");
     CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "poly_div_linear_fr: execution");
     return UZKGE_OK;
 }
@@ -519,7 +628,8 @@ UZKGE_API int32_t uzkge_cuda_poly_horner_fr_device(const void* d_coefs, size_t n
     API_ENTER(-1);
     fe z;
     memcpy(&z, z_host, sizeof(fe));
-    int rc = g.poly->horner((const fe*)d_coefs, n, z, (fe*)d_quotient, (fe*)d_value, (cudaStream_t)stream);
+    int rc;
+    FENCED(g.poly_fence, (cudaStream_t)stream, "poly_horner_fr_device", g.poly->horner((const fe*)d_coefs, n, z, (fe*)d_quotient, (fe*)d_value, (cudaStream_t)stream));
     return engine_fail(rc, "poly_horner_fr_device");
 }
 
@@ -532,7 +642,9 @@ UZKGE_API int32_t uzkge_cuda_poly_eval_batch_fr_device(const void* const* d_poly
     memcpy(pts, points_host, npoints * sizeof(fe));
     uint64_t n64[UZKGE_EVAL_BATCH_MAX];
     for (size_t j = 0; j < k; j++) n64[j] = lens[j];
-    int rc = g.poly->eval_batch((const fe* const*)d_polys, n64, point_index, (uint32_t)k, pts, (uint32_t)npoints, (fe*)d_values, (cudaStream_t)stream);
+    int rc;
+    FENCED(g.poly_fence, (cudaStream_t)stream, "poly_eval_batch_fr_device",
+           g.poly->eval_batch((const fe* const*)d_polys, n64, point_index, (uint32_t)k, pts, (uint32_t)npoints, (fe*)d_values, (cudaStream_t)stream));
     if (rc == UZKGE_ERR_SIZE) return fail(rc, "poly_eval_batch_fr_device: empty polynomial or bad point index");
     if (rc == UZKGE_ERR_ARG) return fail(rc, "poly_eval_batch_fr_device: null polynomial");
     return engine_fail(rc, "poly_eval_batch_fr_device");
@@ -553,7 +665,8 @@ UZKGE_API int32_t uzkge_cuda_grand_product_fr(const uint64_t* num, const uint64_
     CUDA_OR_FAIL(cudaMemcpyAsync(d_num, num, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "grand_product_fr: H2D");
     CUDA_OR_FAIL(cudaMemcpyAsync(d_den, den, n * sizeof(fe), cudaMemcpyHostToDevice, g.stream), "grand_product_fr: H2D");
     // the result (n + 1 elements) overwrites the inputs' buffer once they are consumed
-    int rc = g.poly->grand_product(d_num, d_den, n, d_num, (fe*)g.scratch.p, g.stream);
+    int rc;
+    FENCED(g.poly_fence, g.stream, "grand_product_fr", g.poly->grand_product(d_num, d_den, n, d_num, (fe*)g.scratch.p, g.stream));
     if (rc == UZKGE_ERR_ARG) return fail(rc, "grand_product_fr: a denominator is zero");
     if (rc != UZKGE_OK) return engine_fail(rc, "grand_product_fr");
     CUDA_OR_FAIL(cudaMemcpyAsync(out, d_num, (n + 1) * sizeof(fe), cudaMemcpyDeviceToHost, g.stream), "grand_product_fr: D2H");
@@ -620,7 +733,9 @@ UZKGE_API int32_t uzkge_cuda_fr_mul_device(const void* d_a, const void* d_b, siz
 UZKGE_API int32_t uzkge_cuda_fr_trimmed_len_device(const void* d_poly, size_t n, size_t* len_out, void* stream) {
     API_ENTER(-1);
     CUDA_OR_FAIL(g.small.reserve(4096), "fr_trimmed_len_device: buffer");
-    int rc = fr_trimmed_len_run(d_poly, n, (unsigned long long*)g.small.p, len_out, (cudaStream_t)stream);
+    int rc;
+    FENCED(g.small_fence, (cudaStream_t)stream, "fr_trimmed_len_device",
+           fr_trimmed_len_run(d_poly, n, (unsigned long long*)g.small.p, len_out, (cudaStream_t)stream));
     if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_trimmed_len_device: null pointer");
     return engine_fail(rc, "fr_trimmed_len_device");
 }
@@ -628,7 +743,9 @@ UZKGE_API int32_t uzkge_cuda_fr_trimmed_len_device(const void* d_poly, size_t n,
 UZKGE_API int32_t uzkge_cuda_grand_product_fr_device(const void* d_num, const void* d_den, size_t n, void* d_out, void* d_tmp, void* stream) {
     if (!d_num || !d_den || !d_out || !d_tmp) return fail(UZKGE_ERR_ARG, "grand_product_fr_device: null pointer");
     API_ENTER(-1);
-    int rc = g.poly->grand_product((const fe*)d_num, (const fe*)d_den, n, (fe*)d_out, (fe*)d_tmp, (cudaStream_t)stream);
+    int rc;
+    FENCED(g.poly_fence, (cudaStream_t)stream, "grand_product_fr_device",
+           g.poly->grand_product((const fe*)d_num, (const fe*)d_den, n, (fe*)d_out, (fe*)d_tmp, (cudaStream_t)stream));
     if (rc == UZKGE_ERR_ARG) return fail(rc, "grand_product_fr_device: a denominator is zero");
     return engine_fail(rc, "grand_product_fr_device");
 }
@@ -637,7 +754,9 @@ UZKGE_API int32_t uzkge_cuda_plonk_z_evals_fr_device(const void* const d_w[5], c
                                                      const uint64_t* k_host, const uint64_t beta_host[4], const uint64_t gamma_host[4], size_t n,
                                                      void* d_z, void* d_tmp, void* stream) {
     API_ENTER(-1);
-    int rc = plonk_z_evals_run(g.poly.get(), d_w, d_sigma, d_group, k_host, beta_host, gamma_host, n, d_z, d_tmp, (cudaStream_t)stream);
+    int rc;
+    FENCED(g.poly_fence, (cudaStream_t)stream, "plonk_z_evals_fr_device",
+           plonk_z_evals_run(g.poly.get(), d_w, d_sigma, d_group, k_host, beta_host, gamma_host, n, d_z, d_tmp, (cudaStream_t)stream));
     if (rc == UZKGE_ERR_ARG) return fail(rc, "plonk_z_evals_fr_device: null pointer or zero denominator");
     if (rc == UZKGE_ERR_SIZE) return fail(rc, "plonk_z_evals_fr_device: n >= 2");
     return engine_fail(rc, "plonk_z_evals_fr_device");
@@ -657,11 +776,13 @@ UZKGE_API int32_t uzkge_cuda_g1_add(const uint64_t a_jac[12], const uint64_t b_j
     API_ENTER(-1);
     CUDA_OR_FAIL(g.small.reserve(4096), "g1_add: buffer");
     jacobian* d = (jacobian*)g.small.p;
+    CUDA_OR_FAIL(g.small_fence.enter(g.stream), "g1_add: stream order");
     CUDA_OR_FAIL(cudaMemcpyAsync(d, a_jac, sizeof(jacobian), cudaMemcpyHostToDevice, g.stream), "g1_add: H2D");
     CUDA_OR_FAIL(cudaMemcpyAsync(d + 1, b_jac, sizeof(jacobian), cudaMemcpyHostToDevice, g.stream), "g1_add: H2D");
     int rc = g.msm->g1_add(d, d + 1, d + 2, g.stream);
     if (rc != UZKGE_OK) return engine_fail(rc, "g1_add");
     CUDA_OR_FAIL(cudaMemcpyAsync(out_jac, d + 2, sizeof(jacobian), cudaMemcpyDeviceToHost, g.stream), "g1_add: D2H");
+    CUDA_OR_FAIL(g.small_fence.leave(g.stream), "g1_add: stream order");
     CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "g1_add: execution");
     return UZKGE_OK;
 }
@@ -671,10 +792,12 @@ UZKGE_API int32_t uzkge_cuda_g1_to_affine(const uint64_t in_jac[12], uint64_t ou
     API_ENTER(-1);
     CUDA_OR_FAIL(g.small.reserve(4096), "g1_to_affine: buffer");
     jacobian* d = (jacobian*)g.small.p;
+    CUDA_OR_FAIL(g.small_fence.enter(g.stream), "g1_to_affine: stream order");
     CUDA_OR_FAIL(cudaMemcpyAsync(d, in_jac, sizeof(jacobian), cudaMemcpyHostToDevice, g.stream), "g1_to_affine: H2D");
     int rc = g.msm->g1_to_affine(d, (affine*)(d + 1), g.stream);
     if (rc != UZKGE_OK) return engine_fail(rc, "g1_to_affine");
     CUDA_OR_FAIL(cudaMemcpyAsync(out_affine, d + 1, sizeof(affine), cudaMemcpyDeviceToHost, g.stream), "g1_to_affine: D2H");
+    CUDA_OR_FAIL(g.small_fence.leave(g.stream), "g1_to_affine: stream order");
     CUDA_OR_FAIL(cudaStreamSynchronize(g.stream), "g1_to_affine: execution");
     return UZKGE_OK;
 }
@@ -748,7 +871,7 @@ UZKGE_API int32_t uzkge_cuda_srs_lagrange_from_monomial(const uint64_t* monomial
 UZKGE_API int32_t uzkge_cuda_msm_g1_small_device(uint64_t handle, const size_t* idx, const uint64_t* scalars_host, size_t k, int32_t accumulate,
                                                  void* d_out_jac, void* stream) {
     if (!d_out_jac || (k && (!idx || !scalars_host))) return fail(UZKGE_ERR_ARG, "msm_g1_small_device: null pointer");
-    API_ENTER(-1);
+    API_ENTER_HANDLE(handle, "msm_g1_small_device");
     auto it = g.srs.find(handle);
     if (it == g.srs.end()) return fail(UZKGE_ERR_HANDLE, "msm_g1_small_device: unknown handle");
     int rc = g.msm->small_msm(&it->second, idx, scalars_host, (uint32_t)k, accumulate != 0, (jacobian*)d_out_jac, (cudaStream_t)stream);
@@ -784,8 +907,9 @@ UZKGE_API int32_t uzkge_cuda_profile_enable(int32_t on) {
     CUDA_OR_FAIL(cudaDeviceSynchronize(), "profile_enable");
     double sums[Profiler::KINDS][Profiler::MAX_PHASES] = {};
     uint64_t runs[Profiler::KINDS] = {};
-    g_prof.collect(sums, runs);  // drop stale records
-    g_prof.enabled = on != 0;
+    Profiler& prof = g_profs[g.device];
+    prof.collect(sums, runs);  // drop stale records
+    prof.enabled = on != 0;
     return UZKGE_OK;
 }
 
@@ -794,15 +918,15 @@ UZKGE_API int32_t uzkge_cuda_profile_read(int32_t kind, double phase_ms[8], uint
     if (kind < 0 || kind >= Profiler::KINDS) return fail(UZKGE_ERR_ARG, "profile_read: kind must be 0 (MSM) or 1 (NTT)");
     API_ENTER(-1);
     CUDA_OR_FAIL(cudaDeviceSynchronize(), "profile_read");
-    static double sums[Profiler::KINDS][Profiler::MAX_PHASES];
-    static uint64_t runs[Profiler::KINDS];
-    g_prof.collect(sums, runs);
+    static double sums[UZ_MAX_DEVICES][Profiler::KINDS][Profiler::MAX_PHASES];
+    static uint64_t runs[UZ_MAX_DEVICES][Profiler::KINDS];
+    g_profs[g.device].collect(sums[g.device], runs[g.device]);
     for (int i = 0; i < Profiler::MAX_PHASES; i++) {
-        phase_ms[i] = sums[kind][i];
-        sums[kind][i] = 0;
+        phase_ms[i] = sums[g.device][kind][i];
+        sums[g.device][kind][i] = 0;
     }
-    *runs_out = runs[kind];
-    runs[kind] = 0;
+    *runs_out = runs[g.device][kind];
+    runs[g.device][kind] = 0;
     return UZKGE_OK;
 }
 
@@ -810,50 +934,57 @@ UZKGE_API uint64_t uzkge_cuda_launch_count(void) { return g_launches.load(std::m
 
 UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
     if (!key) return fail(UZKGE_ERR_ARG, "configure: null key");
-    std::lock_guard<std::mutex> lock(g.mu);
     const std::string k(key);
-    if (k == "msm_lanes") {
-        if (value > 32 || (value & (value - 1))) return fail(UZKGE_ERR_ARG, "configure: msm_lanes must be 0 or a power of two <= 32");
-        int rc = ensure_init(-1);
-        if (rc != UZKGE_OK) return rc;
-        g.msm->force_lanes((uint32_t)value);
-        return UZKGE_OK;
-    }
-    if (k == "ntt_big_threads") {
-        if (value != 512 && value != 1024) return fail(UZKGE_ERR_ARG, "configure: ntt_big_threads is 512 or 1024");
-        int rc = ensure_init(-1);
-        if (rc != UZKGE_OK) return rc;
-        g.ntt->set_big_threads((uint32_t)value);
-        return UZKGE_OK;
-    }
-    if (k == "ntt_log_tile" || k == "ntt_max_log_r" || k == "ntt_two_pass_max") {
-        if (k == "ntt_log_tile") {
-            if (value < 4 || value > 12) return fail(UZKGE_ERR_ARG, "configure: ntt_log_tile in 4..12");
-            g.ntt_log_tile = (uint32_t)value;
-        } else if (k == "ntt_max_log_r") {
-            if (value < 4 || value > 12) return fail(UZKGE_ERR_ARG, "configure: ntt_max_log_r in 4..12");
-            g.ntt_max_log_r = (uint32_t)value;
-        } else {
-            g.ntt_two_pass_max = (uint32_t)value;
-        }
-        if (g.ready) {  // plans are cached per size: start over with the new limits
-            cudaStreamSynchronize(g.stream);
-            g.ntt.reset(new NttEngine(g.sm_count));
-            g.ntt->configure(g.ntt_log_tile, g.ntt_max_log_r, g.ntt_two_pass_max);
-        }
-        return UZKGE_OK;
-    }
-    if (k == "msm_affine") {
-        int rc = ensure_init(-1);
-        if (rc != UZKGE_OK) return rc;
-        g.msm->set_affine((uint32_t)value);
-        return UZKGE_OK;
-    }
     if (k == "quotient_min_blocks") {
         g_quotient_min_blocks = (int)value;
         return UZKGE_OK;
     }
-    return fail(UZKGE_ERR_ARG, "configure: unknown key");
+    bool rebuild_ntt = false;
+    {
+        std::lock_guard<std::mutex> reg(g_reg_mu);
+        if (k == "msm_lanes") {
+            if (value > 32 || (value & (value - 1))) return fail(UZKGE_ERR_ARG, "configure: msm_lanes must be 0 or a power of two <= 32");
+            g_cfg.msm_lanes = (uint32_t)value;
+        } else if (k == "ntt_big_threads") {
+            if (value != 512 && value != 1024) return fail(UZKGE_ERR_ARG, "configure: ntt_big_threads is 512 or 1024");
+            g_cfg.ntt_big_threads = (uint32_t)value;
+        } else if (k == "ntt_log_tile") {
+            if (value < 4 || value > 12) return fail(UZKGE_ERR_ARG, "configure: ntt_log_tile in 4..12");
+            g_cfg.ntt_log_tile = (uint32_t)value;
+            rebuild_ntt = true;
+        } else if (k == "ntt_max_log_r") {
+            if (value < 4 || value > 12) return fail(UZKGE_ERR_ARG, "configure: ntt_max_log_r in 4..12");
+            g_cfg.ntt_max_log_r = (uint32_t)value;
+            rebuild_ntt = true;
+        } else if (k == "ntt_two_pass_max") {
+            g_cfg.ntt_two_pass_max = (uint32_t)value;
+            rebuild_ntt = true;
+        } else if (k == "msm_affine") {
+            g_cfg.msm_affine = (uint32_t)value;
+        } else {
+            return fail(UZKGE_ERR_ARG, "configure: unknown key");
+        }
+    }
+    // apply to every device that is already up (devices initialised later read g_cfg)
+    for (int d = 0; d < UZ_MAX_DEVICES; d++) {
+        State* st;
+        {
+            std::lock_guard<std::mutex> reg(g_reg_mu);
+            st = g_states[d];
+        }
+        if (!st) continue;
+        std::lock_guard<std::mutex> lock(st->mu);
+        cudaSetDevice(st->device);
+        st->msm->force_lanes(g_cfg.msm_lanes);
+        st->msm->set_affine(g_cfg.msm_affine);
+        if (rebuild_ntt) {  // plans are cached per size: start over with the new limits
+            cudaDeviceSynchronize();
+            st->ntt.reset(new NttEngine(st->sm_count));
+            st->ntt->configure(g_cfg.ntt_log_tile, g_cfg.ntt_max_log_r, g_cfg.ntt_two_pass_max);
+        }
+        st->ntt->set_big_threads(g_cfg.ntt_big_threads);
+    }
+    return UZKGE_OK;
 }
 
 UZKGE_API int32_t uzkge_cuda_field_mul(int32_t field, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
@@ -904,6 +1035,315 @@ UZKGE_API int32_t uzkge_cuda_bench_field_mul(int32_t field, uint32_t iters, doub
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *muls_per_s = (double)grid * nt * 4.0 * iters / (best * 1e-3);
+    return UZKGE_OK;
+}
+
+}  // extern "C"
+
+// ---- several GPUs behind one process (`uzkge_cuda_init(device_count)`; 8e rows 1 and 2) ---------------------------------
+// The reference is ONE process (shuffle/src/sdk.rs:196-227 serialises proofs behind a mutex), so a Rust host binding this library
+// reaches the other GPUs of the box only if the library drives them itself.  A multi-device SRS handle owns one ordinary handle per
+// device; every call on it fans out to one worker thread per device (launch overhead and the H2D copies of the devices run side by
+// side) and the 96-byte partial results are combined on the host with G - 1 projective additions (ec.cuh's host twins).
+namespace {
+
+struct Pool {   // one persistent worker per device; leaked on purpose (threads blocked in a condition variable at exit)
+    struct Slot {
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv;
+        std::function<void()> fn;
+        bool has = false, done = true;
+    };
+    std::vector<Slot*> slots;
+    void ensure(size_t n) {
+        while (slots.size() < n) {
+            Slot* sl = new Slot();
+            sl->th = std::thread([sl] {
+                for (;;) {
+                    std::function<void()> fn;
+                    {
+                        std::unique_lock<std::mutex> lk(sl->mu);
+                        sl->cv.wait(lk, [sl] { return sl->has; });
+                        fn = std::move(sl->fn);
+                        sl->has = false;
+                    }
+                    fn();
+                    {
+                        std::lock_guard<std::mutex> lk(sl->mu);
+                        sl->done = true;
+                    }
+                    sl->cv.notify_all();
+                }
+            });
+            sl->th.detach();
+            slots.push_back(sl);
+        }
+    }
+    void start(size_t i, std::function<void()> fn) {
+        Slot* sl = slots[i];
+        {
+            std::lock_guard<std::mutex> lk(sl->mu);
+            sl->fn = std::move(fn);
+            sl->has = true;
+            sl->done = false;
+        }
+        sl->cv.notify_all();
+    }
+    void wait(size_t i) {
+        Slot* sl = slots[i];
+        std::unique_lock<std::mutex> lk(sl->mu);
+        sl->cv.wait(lk, [sl] { return sl->done; });
+    }
+};
+
+struct MultiSrs {
+    int mode = 0;                      // UZKGE_MULTI_SPLIT / UZKGE_MULTI_REPLICATED
+    size_t n = 0;
+    std::vector<int> devices;
+    std::vector<uint64_t> sub;         // the device's own handle
+    std::vector<size_t> lo, hi;        // split: the device holds bases [lo, hi)
+};
+std::mutex g_multi_mu;                 // one multi-device call at a time (they share the workers)
+Pool* g_pool = nullptr;
+std::vector<int> g_group;              // devices of uzkge_cuda_init_devices
+std::map<uint64_t, MultiSrs> g_multi;
+uint64_t g_multi_next = 1;
+
+struct JobResult {
+    int rc = UZKGE_OK;
+    std::string err;
+};
+// run job(i) for i < count on the workers, wait for all; the first failure (with its thread's message) is reported
+int fan_out(size_t count, const std::function<int(size_t)>& job) {
+    if (!g_pool) g_pool = new Pool();
+    g_pool->ensure(count);
+    std::vector<JobResult> res(count);
+    for (size_t i = 0; i < count; i++)
+        g_pool->start(i, [i, &res, &job] {
+            res[i].rc = job(i);
+            if (res[i].rc != UZKGE_OK) res[i].err = t_error;
+        });
+    for (size_t i = 0; i < count; i++) g_pool->wait(i);
+    for (size_t i = 0; i < count; i++)
+        if (res[i].rc != UZKGE_OK) {
+            t_error = res[i].err;
+            return res[i].rc;
+        }
+    return UZKGE_OK;
+}
+
+xyzz host_jac_to_xyzz(const uint64_t* j) {
+    jacobian p;
+    memcpy(&p, j, sizeof(jacobian));
+    if (fe_is_zero(p.z)) return xyzz_identity();
+    xyzz r;
+    r.x = p.x;
+    r.y = p.y;
+    r.zz = fe_sqr<FqP>(p.z);
+    r.zzz = fe_mul<FqP>(r.zz, p.z);
+    return r;
+}
+// out = sum of `count` Jacobian points (12 words each): the G - 1 projective additions that merge per-GPU partial sums
+void host_sum_jacobians(const uint64_t* parts, size_t count, uint64_t out[12]) {
+    xyzz acc = xyzz_identity();
+    for (size_t i = 0; i < count; i++) {
+        const xyzz q = host_jac_to_xyzz(parts + 12 * i);
+        xyzz_add(acc, q);
+    }
+    const jacobian r = xyzz_to_jacobian(acc);
+    memcpy(out, &r, sizeof(jacobian));
+}
+
+MultiSrs* find_multi(uint64_t handle) {
+    auto it = g_multi.find(handle);
+    return it == g_multi.end() ? nullptr : &it->second;
+}
+
+}  // namespace
+
+extern "C" {
+
+UZKGE_API int32_t uzkge_cuda_init_devices(int32_t device_count) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(UZKGE_ERR_NO_DEVICE, "no CUDA device: uzkge-b200 has no CPU path");
+    }
+    if (device_count < 0 || device_count > count || device_count > UZ_MAX_DEVICES)
+        return fail(UZKGE_ERR_NO_DEVICE, "init_devices: more devices requested than visible");
+    const int use = device_count == 0 ? (count < UZ_MAX_DEVICES ? count : UZ_MAX_DEVICES) : device_count;
+    std::lock_guard<std::mutex> multi(g_multi_mu);
+    for (int d = 0; d < use; d++) {
+        API_ENTER(d);
+        // peer access: lets one device's kernels and copies reach another's memory over NVLink (ignored where unsupported)
+        for (int o = 0; o < use; o++) {
+            if (o == d) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, d, o) == cudaSuccess && can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(o, 0);
+                if (e != cudaSuccess) cudaGetLastError();   // already enabled
+            }
+        }
+    }
+    g_group.clear();
+    for (int d = 0; d < use; d++) g_group.push_back(d);
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_group_size(void) {
+    std::lock_guard<std::mutex> multi(g_multi_mu);
+    return (int32_t)g_group.size();
+}
+
+UZKGE_API int32_t uzkge_cuda_srs_upload(const uint64_t* affine_xy, size_t n, uint32_t window_bits, uint64_t* handle) {
+    return srs_upload_one(-1, affine_xy, n, window_bits, handle);
+}
+
+UZKGE_API int32_t uzkge_cuda_srs_upload_multi(const uint64_t* affine_xy, size_t n, uint32_t window_bits, int32_t mode, uint64_t* handle) {
+    if (!affine_xy || !handle) return fail(UZKGE_ERR_ARG, "srs_upload_multi: null pointer");
+    if (mode != UZKGE_MULTI_SPLIT && mode != UZKGE_MULTI_REPLICATED) return fail(UZKGE_ERR_ARG, "srs_upload_multi: mode");
+    std::lock_guard<std::mutex> multi(g_multi_mu);
+    if (g_group.empty()) return fail(UZKGE_ERR_NO_DEVICE, "srs_upload_multi: call uzkge_cuda_init_devices first");
+    if (n == 0) return fail(UZKGE_ERR_SIZE, "srs_upload_multi: empty SRS");
+    MultiSrs m;
+    m.mode = mode;
+    m.n = n;
+    size_t G = g_group.size();
+    if (mode == UZKGE_MULTI_SPLIT && G > n) G = n;
+    const size_t base = n / G, rem = n % G;
+    for (size_t i = 0; i < G; i++) {
+        m.devices.push_back(g_group[i]);
+        const size_t lo = mode == UZKGE_MULTI_SPLIT ? i * base + (i < rem ? i : rem) : 0;
+        const size_t hi = mode == UZKGE_MULTI_SPLIT ? lo + base + (i < rem ? 1 : 0) : n;
+        m.lo.push_back(lo);
+        m.hi.push_back(hi);
+    }
+    m.sub.assign(G, 0);
+    int rc = fan_out(G, [&](size_t i) { return srs_upload_one(m.devices[i], affine_xy + 8 * m.lo[i], m.hi[i] - m.lo[i], window_bits, &m.sub[i]); });
+    if (rc != UZKGE_OK) {
+        const std::string keep = t_error;
+        for (size_t i = 0; i < G; i++)
+            if (m.sub[i]) srs_free_one(m.sub[i]);
+        t_error = keep;
+        return rc;
+    }
+    const uint64_t h = HANDLE_MULTI | g_multi_next++;
+    g_multi[h] = m;
+    *handle = h;
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_srs_free(uint64_t handle) {
+    if (!(handle & HANDLE_MULTI)) return srs_free_one(handle);
+    std::lock_guard<std::mutex> multi(g_multi_mu);
+    MultiSrs* m = find_multi(handle);
+    if (!m) return fail(UZKGE_ERR_HANDLE, "srs_free: unknown handle");
+    int rc = UZKGE_OK;
+    for (uint64_t h : m->sub) {
+        const int r = srs_free_one(h);
+        if (r != UZKGE_OK) rc = r;
+    }
+    g_multi.erase(handle);
+    return rc;
+}
+
+UZKGE_API int32_t uzkge_cuda_srs_info(uint64_t handle, uzkge_srs_info* info) {
+    if (!(handle & HANDLE_MULTI)) return srs_info_one(handle, info);
+    if (!info) return fail(UZKGE_ERR_ARG, "srs_info: null pointer");
+    std::lock_guard<std::mutex> multi(g_multi_mu);
+    MultiSrs* m = find_multi(handle);
+    if (!m) return fail(UZKGE_ERR_HANDLE, "srs_info: unknown handle");
+    uzkge_srs_info sum = {};
+    for (size_t i = 0; i < m->sub.size(); i++) {
+        uzkge_srs_info one;
+        const int rc = srs_info_one(m->sub[i], &one);
+        if (rc != UZKGE_OK) return rc;
+        if (i == 0) sum = one;
+        else {
+            sum.device_bytes += one.device_bytes;
+            if (one.precompute_ms > sum.precompute_ms) sum.precompute_ms = one.precompute_ms;
+        }
+    }
+    sum.n = m->n;
+    sum.reserved = (uint32_t)m->sub.size();   // number of devices behind the handle
+    *info = sum;
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_msm_g1(uint64_t handle, size_t base_offset, const uint64_t* scalars, size_t n, uint64_t out_jac[12]) {
+    if (!(handle & HANDLE_MULTI)) return msm_g1_one(handle, base_offset, scalars, n, out_jac);
+    if (!out_jac || (n && !scalars)) return fail(UZKGE_ERR_ARG, "msm_g1: null pointer");
+    std::lock_guard<std::mutex> multi(g_multi_mu);
+    MultiSrs* m = find_multi(handle);
+    if (!m) return fail(UZKGE_ERR_HANDLE, "msm_g1: unknown handle");
+    if (base_offset > m->n || n > m->n - base_offset) return fail(UZKGE_ERR_SIZE, "msm_g1: range outside the SRS");
+    if (m->mode == UZKGE_MULTI_REPLICATED) return msm_g1_one(m->sub[0], base_offset, scalars, n, out_jac);
+    // split: device i computes the part of [base_offset, base_offset + n) that falls into its slice
+    const size_t G = m->sub.size();
+    std::vector<uint64_t> parts(12 * G, 0);
+    int rc = fan_out(G, [&](size_t i) {
+        const size_t a = base_offset > m->lo[i] ? base_offset : m->lo[i];
+        const size_t b = base_offset + n < m->hi[i] ? base_offset + n : m->hi[i];
+        if (b <= a) return (int)UZKGE_OK;            // Z = 0: identity
+        return (int)msm_g1_one(m->sub[i], a - m->lo[i], scalars + 4 * (a - base_offset), b - a, &parts[12 * i]);
+    });
+    if (rc != UZKGE_OK) return rc;
+    host_sum_jacobians(parts.data(), G, out_jac);
+    return UZKGE_OK;
+}
+
+UZKGE_API int32_t uzkge_cuda_msm_g1_batch(uint64_t handle, const uint64_t* const* scalars, const size_t* n, size_t k, uint64_t* out_jac) {
+    if (!(handle & HANDLE_MULTI)) return msm_g1_batch_one(handle, scalars, n, k, out_jac);
+    if (k && (!scalars || !n || !out_jac)) return fail(UZKGE_ERR_ARG, "msm_g1_batch: null pointer");
+    std::lock_guard<std::mutex> multi(g_multi_mu);
+    MultiSrs* m = find_multi(handle);
+    if (!m) return fail(UZKGE_ERR_HANDLE, "msm_g1: unknown handle");
+    if (k == 0) return UZKGE_OK;
+    for (size_t j = 0; j < k; j++) {
+        if (n[j] > m->n) return fail(UZKGE_ERR_SIZE, "msm_g1: more scalars than SRS points");
+        if (n[j] && !scalars[j]) return fail(UZKGE_ERR_ARG, "msm_g1: null scalar vector");
+    }
+    const size_t G = m->sub.size();
+    if (m->mode == UZKGE_MULTI_REPLICATED) {
+        // the independent commitments of a round (plonk/prover.rs:132-192, helpers.rs:1323-1408) dealt to the devices: MSM j on
+        // device j % G, each device runs its share as one batch
+        std::vector<std::vector<const uint64_t*>> sc(G);
+        std::vector<std::vector<size_t>> nn(G), idx(G);
+        std::vector<std::vector<uint64_t>> outs(G);
+        for (size_t j = 0; j < k; j++) {
+            sc[j % G].push_back(scalars[j]);
+            nn[j % G].push_back(n[j]);
+            idx[j % G].push_back(j);
+        }
+        for (size_t i = 0; i < G; i++) outs[i].assign(12 * sc[i].size() + 12, 0);
+        int rc = fan_out(G, [&](size_t i) {
+            if (sc[i].empty()) return (int)UZKGE_OK;
+            return (int)msm_g1_batch_one(m->sub[i], sc[i].data(), nn[i].data(), sc[i].size(), outs[i].data());
+        });
+        if (rc != UZKGE_OK) return rc;
+        for (size_t i = 0; i < G; i++)
+            for (size_t t = 0; t < idx[i].size(); t++) memcpy(out_jac + 12 * idx[i][t], &outs[i][12 * t], 96);
+        return UZKGE_OK;
+    }
+    // split: every device runs all k MSMs over its slice (a prefix of the SRS meets a slice in a prefix of the slice)
+    std::vector<std::vector<uint64_t>> parts(G, std::vector<uint64_t>(12 * k, 0));
+    int rc = fan_out(G, [&](size_t i) {
+        std::vector<const uint64_t*> sc(k);
+        std::vector<size_t> nn(k);
+        for (size_t j = 0; j < k; j++) {
+            const size_t b = n[j] < m->hi[i] ? n[j] : m->hi[i];
+            nn[j] = b > m->lo[i] ? b - m->lo[i] : 0;
+            sc[j] = nn[j] ? scalars[j] + 4 * m->lo[i] : nullptr;
+        }
+        return (int)msm_g1_batch_one(m->sub[i], sc.data(), nn.data(), k, parts[i].data());
+    });
+    if (rc != UZKGE_OK) return rc;
+    std::vector<uint64_t> col(12 * G);
+    for (size_t j = 0; j < k; j++) {
+        for (size_t i = 0; i < G; i++) memcpy(&col[12 * i], &parts[i][12 * j], 96);
+        host_sum_jacobians(col.data(), G, out_jac + 12 * j);
+    }
     return UZKGE_OK;
 }
 

@@ -76,7 +76,11 @@ struct Profiler {
         recs.clear();
     }
 };
-extern Profiler g_prof;
+// one profiler per device (events belong to the device they were created on); engines reach theirs through the CUDA runtime's
+// current device, which every entry point has set before it calls them
+static constexpr int UZ_MAX_DEVICES = 16;
+Profiler& prof_for_current_device();
+#define g_prof (::uz::prof_for_current_device())
 enum MsmPhase { MSM_PH_RECODE = 0, MSM_PH_SORT, MSM_PH_OFFSETS, MSM_PH_ACCUMULATE, MSM_PH_LARGE, MSM_PH_REDUCE };
 enum NttPhase { NTT_PH_RADIX3 = 0, NTT_PH_PASS0, NTT_PH_PASS1, NTT_PH_PASS2 };
 

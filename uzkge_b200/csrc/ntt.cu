@@ -377,11 +377,13 @@ static cudaError_t launch_pass(const NttKernelArgs& ka, cudaStream_t st) {
     const NttPass& p = ka.p;
     const size_t T = (size_t)1 << (p.logR + p.logC);
     const size_t smem = T * 32;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[UZ_MAX_DEVICES] = {};   // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
         if (e != cudaSuccess) return e;
-        configured = 200 * 1024;
+        configured[dev] = 200 * 1024;
     }
     const uint32_t grid = p.inner_tiles * p.outer * p.batch;
     ntt_pass_kernel<NT><<<grid, NT, smem, st>>>(ka);

@@ -72,6 +72,11 @@ class QuotientShuffleArgs(C.Structure):
 _SIGNATURES = {
     "uzkge_cuda_init": (C.c_int32, [C.c_int32]),
     "uzkge_cuda_device_count": (C.c_int32, []),
+    "uzkge_cuda_set_device": (C.c_int32, [C.c_int32]),
+    "uzkge_cuda_get_device": (C.c_int32, []),
+    "uzkge_cuda_init_devices": (C.c_int32, [C.c_int32]),
+    "uzkge_cuda_group_size": (C.c_int32, []),
+    "uzkge_cuda_srs_upload_multi": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int32, u64p]),
     "uzkge_cuda_last_error": (C.c_char_p, []),
     "uzkge_cuda_version": (C.c_char_p, []),
     "uzkge_cuda_srs_upload": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_uint32, u64p]),
@@ -209,6 +214,31 @@ def init(device: int = -1) -> None:
 
 def device_count() -> int:
     return int(lib().uzkge_cuda_device_count())
+
+
+def set_device(device: int) -> None:
+    check(lib().uzkge_cuda_set_device(device))
+
+
+def get_device() -> int:
+    return int(lib().uzkge_cuda_get_device())
+
+
+def init_devices(device_count: int = 0) -> int:
+    """One process, several GPUs: initialise devices 0 .. device_count - 1 (0 = all visible) as the device group; returns its size."""
+    check(lib().uzkge_cuda_init_devices(device_count))
+    return int(lib().uzkge_cuda_group_size())
+
+
+MULTI_SPLIT, MULTI_REPLICATED = 0, 1
+
+
+def srs_upload_multi(affine_xy: np.ndarray, mode: int = MULTI_SPLIT, window_bits: int = 0) -> int:
+    """The SRS over the device group (init_devices): points split per GPU, or replicated for dealing a round's commitments."""
+    pts = as_u64(affine_xy, 8)
+    h = C.c_uint64(0)
+    check(lib().uzkge_cuda_srs_upload_multi(ptr(pts), pts.shape[0], window_bits, mode, C.byref(h)), CommitmentError)
+    return int(h.value)
 
 
 def version() -> str:
