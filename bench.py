@@ -133,6 +133,54 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+
+# ------------------------------------------------------------------------------------------------ roofline inputs
+# ncu `--set full` captures of the CURRENT kernels, exported with `--page raw --csv` (profiles/README.md says how each was taken)
+TRAFFIC_FILES = {"msm": ["profiles/r2_msm_accumulate_raw.csv", "profiles/r1c_msm_raw.csv"],
+                 "ntt": ["profiles/r2_ntt_raw.csv", "profiles/r1c_ntt_raw.csv"]}
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def ncu_traffic(kind: str, kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch whose name contains `kernel_substr`, read from the committed
+    ncu raw page (per launch).  Returns (bytes or None, source description)."""
+    import csv
+
+    for rel in TRAFFIC_FILES[kind]:
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path):
+            continue
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            for r in rows[2:]:
+                if kernel_substr in r[ik]:
+                    total = float(r[ir].replace(",", "")) * _UNIT[units[ir]] + float(r[iw].replace(",", "")) * _UNIT[units[iw]]
+                    return total, f"{rel}: dram__bytes_read.sum + dram__bytes_write.sum of `{r[ik]}` (ncu --set full, one launch)"
+        except Exception as exc:  # a malformed capture must not break the bench line
+            return None, f"{rel}: unreadable ({exc!r})"
+    return None, "no ncu capture committed for this kernel"
+
+
+def imad_probe(gpu_index: int) -> dict:
+    """The integer roof from a program that shares no code with the library (scripts/cuda/pipe_probe.cu: dependent IMAD.WIDE chains
+    on every SM, CUDA events).  Returns {} when the binary is missing (build() compiles it)."""
+    exe = os.path.join(ROOT, "scripts", "cuda", "pipe_probe")
+    if not os.path.exists(exe):
+        return {}
+    try:
+        out = subprocess.run([exe, "--json", str(gpu_index)], capture_output=True, text=True, timeout=120)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception:
+        return {}
+
+
+# multiplier-pipe instructions per field product (ff.cuh; SASS excerpt in profiles/r2_fe_mul_sass.txt): 8 x (8 + 8 + 1) for fe_mul,
+# 36 + 8 x 9 for the dedicated fe_sqr
+IMAD_PER_MUL, IMAD_PER_SQR = 136, 108
+IMAD_PER_MADD = 8 * IMAD_PER_MUL + 2 * IMAD_PER_SQR      # XYZZ mixed addition: 8 M + 2 S
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank: int, world: int) -> int:
     """The reference's CPU path for the same metric: no Rust toolchain exists here or on the GPU box and the
@@ -194,6 +242,7 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
 
     from uzkge_b200 import KZGCommitmentSchemeBN254, ffi, plonk
     from uzkge_b200 import dist as udist
+    from uzkge_b200.native import NativeProver
     from uzkge_b200.rng import ChaChaRng
     from uzkge_b200.transcript import Transcript
 
@@ -211,6 +260,7 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
     for lg, witness, shuffle_features, split in runs:
         n = 1 << lg
         steps = K if lg <= 18 else max(2, min(K, 5))
+        torch.cuda.reset_peak_memory_stats()          # per-size peak (torch allocations); the library's own arenas are in device_used_gib
         t0 = time.perf_counter()
         lagrange = None
         if split:
@@ -234,8 +284,17 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
         wit_pinned.array[:] = cs.get_witness_array()
         wit_host = wit_pinned.array
         wit = plonk.DevVec.from_numpy(wit_host, dev)
+        # one GPU: the compiled prover behind the C ABI (uzkge_cuda_plonk_prove); the Python mirror is timed beside it.  A proof split
+        # over the GPUs of the box is driven by the mirror (dist.SplitCommitter)
+        native = None if split else NativeProver(cs, params, pcs, lagrange)
+
+        def prove(w, timings=None):
+            if native is not None:
+                return native.prove(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), w, timings=timings)
+            return plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, w, timings=timings, lagrange_pcs=lagrange)
+
         for _ in range(min(W, 3)):
-            proof = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit, lagrange_pcs=lagrange)
+            proof = prove(wit)
         torch.cuda.synchronize()
         if not split and barrier:
             barrier()
@@ -243,7 +302,7 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
         l0 = ffi.launch_count()
         t0 = time.perf_counter()
         for _ in range(steps):
-            plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit, timings=timings, lagrange_pcs=lagrange)
+            prove(wit, timings)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / steps
         launches = (ffi.launch_count() - l0) // steps
@@ -251,10 +310,25 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
             barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            proof2 = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit_host, lagrange_pcs=lagrange)
+            proof2 = prove(wit_host)
         torch.cuda.synchronize()
         dt_e2e = (time.perf_counter() - t0) / steps
         same = all(a == b for a, b in zip(proof.cm_t_vec + [proof.opening_witness_zeta], proof2.cm_t_vec + [proof2.opening_witness_zeta]))
+        mirror_ms, ops = None, None
+        if native is not None:
+            ops = {k: native.last_stats[k] for k in ("msm", "ifft_n", "fft_n", "coset_fft_m", "coset_ifft_m", "evals")}
+            ops["quotient_points"] = int(params.m)
+            msteps = max(1, min(steps, 5))
+            mproof = plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit, lagrange_pcs=lagrange)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(msteps):
+                plonk.prover(ChaChaRng.from_seed(bytes(32)), Transcript(b"bench"), pcs, cs, params, wit, lagrange_pcs=lagrange)
+            torch.cuda.synchronize()
+            mirror_ms = (time.perf_counter() - t0) / msteps * 1e3
+            if mproof.to_bytes_be() != proof.to_bytes_be():
+                raise SystemExit("bench.py: the compiled prover's proof differs from the Python mirror's -- refusing to report a number")
+            native.close()
         if split:
             pcs.shutdown()
             window_bits = ffi.srs_info(pcs.handle)["window_bits"]
@@ -272,9 +346,12 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
             "e2e_proofs_per_s": proofs_in_flight / dt_e2e,
             "h2d_bytes_per_step": int(wit_host.nbytes), "d2h_bytes_per_step": 13 * 96 + 16 * 32, "steps": steps,
             "launches_per_proof": int(launches), "rounds_ms": {k: v / steps for k, v in timings.items()},
-            "ops_per_proof": {"msm": 13, "ifft_n": 6, "coset_fft_6n": 6, "coset_ifft_6n": 1, "quotient_points": int(params.m), "evals": 16},
+            "prover": "uzkge_cuda_plonk_prove (compiled, one C-ABI call per proof)" if native is not None else "uzkge_b200.plonk.prover (Python mirror, one C-ABI call per operation)",
+            "python_mirror_prove_ms": mirror_ms,
+            "ops_per_proof": ops, "ops_source": "counted by the prover (uzkge_plonk_proof)" if ops else None,
             "setup_s": setup_s, "deterministic": bool(same),
             "window_bits": window_bits, "hbm_peak_gib": torch.cuda.max_memory_allocated() / 2**30,
+            "device_used_gib": (lambda fr_, tot_: (tot_ - fr_) / 2**30)(*torch.cuda.mem_get_info()),
         })
         pcs.close()
         if lagrange is not None:
@@ -314,10 +391,19 @@ def _app_circuit_proofs(dev, K: int, W: int, name: str, cs, build_s: float, shuf
     wit_pinned.array[:] = cs.get_witness_array()
     wit_host = wit_pinned.array
 
+    from uzkge_b200.native import NativeProver
+
+    native = NativeProver(cs, params, pcs, lagrange, True)
+
     def prove(w, timings=None):
         tr = Transcript(label)
         tr.append_u64(count)
-        return plonk.prover(ChaChaRng.from_seed(bytes(32)), tr, pcs, cs, params, w, timings=timings, lagrange_pcs=lagrange, lagrange_all=True)
+        return native.prove(ChaChaRng.from_seed(bytes(32)), tr, w, timings=timings)
+
+    def prove_mirror(w):
+        tr = Transcript(label)
+        tr.append_u64(count)
+        return plonk.prover(ChaChaRng.from_seed(bytes(32)), tr, pcs, cs, params, w, lagrange_pcs=lagrange, lagrange_all=True)
 
     wit = plonk.DevVec.from_numpy(wit_host, dev)
     for _ in range(max(W, 3)):
@@ -337,6 +423,18 @@ def _app_circuit_proofs(dev, K: int, W: int, name: str, cs, build_s: float, shuf
     torch.cuda.synchronize()
     dt_e2e = (time.perf_counter() - t0) / K
     n_msm, n_sel = (16, 3) if shuffle else (13, 0)
+    ops = {k: native.last_stats[k] for k in ("msm", "ifft_n", "fft_n", "coset_fft_m", "coset_ifft_m", "evals")}
+    ops["quotient_points"] = int(params.m)
+    mproof = prove_mirror(wit)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(min(K, 10)):
+        prove_mirror(wit)
+    torch.cuda.synchronize()
+    mirror_ms = (time.perf_counter() - t0) / min(K, 10) * 1e3
+    if mproof.to_bytes_be() != proof.to_bytes_be():
+        raise RuntimeError("the compiled prover's proof differs from the Python mirror's")
+    native.close()
     res = {
         "circuit": name, "log_n": n.bit_length() - 1, "n_gpus": 1, "mode": "single", "witness": "the application's gadgets",
         "lagrange_commitments": True, "lagrange_all": True, "feature_set": "shuffle" if shuffle else "default",
@@ -344,8 +442,8 @@ def _app_circuit_proofs(dev, K: int, W: int, name: str, cs, build_s: float, shuf
         "prove_ms": dt * 1e3, "proofs_per_s": 1 / dt, "e2e_prove_ms": dt_e2e * 1e3, "e2e_proofs_per_s": 1 / dt_e2e,
         "h2d_bytes_per_step": int(wit_host.nbytes) + n_sel * n * 4, "d2h_bytes_per_step": n_msm * 96 + (20 if shuffle else 16) * 32, "steps": K,
         "launches_per_proof": int(launches), "rounds_ms": {k: v / K for k, v in timings.items()},
-        "ops_per_proof": {"msm": n_msm, "ifft_n": 7 + n_sel, "fft_n": 7, "coset_fft_6n": 7 + n_sel, "coset_ifft_6n": 1,
-                          "quotient_points": int(params.m), "evals": 20 if shuffle else 16},
+        "prover": "uzkge_cuda_plonk_prove (compiled, one C-ABI call per proof)", "python_mirror_prove_ms": mirror_ms,
+        "ops_per_proof": ops, "ops_source": "counted by the prover (uzkge_plonk_proof)",
         "build_cs_host_s": build_s, "setup_s": setup_s, "refresh_public_key_ms": refresh_ms,
         "deterministic": proof.to_bytes_be() == proof2.to_bytes_be(),
     }
@@ -716,8 +814,13 @@ def main() -> int:
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
     launches = ffi.launch_count() - launches0
 
-    # integer-pipe roof, measured live: dependent Montgomery-multiplication chains on every SM
+    # integer-pipe roof, measured live twice: by the independent probe (IMAD.WIDE issue rate, no library code) and by the library's
+    # own dependent Montgomery-multiplication chains; the roofline's peak is the probe's
+    probe = imad_probe(local_rank) if rank == 0 else {}
     fq_peak = ffi.bench_field_mul("fq", 2000)
+    imad_peak = probe.get("imad_wide_per_s") or fq_peak * IMAD_PER_MUL
+    imad_peak_src = ("scripts/cuda/pipe_probe --json (independent of the library: dependent IMAD.WIDE chains on every SM, CUDA events, "
+                     "this run)" if probe else "library loop x 136 (pipe_probe binary missing)")
 
     # -------------------------------------------------------------------------------------------- CPU baseline (rank 0, N = 1)
     cpu_baseline = None
@@ -728,7 +831,7 @@ def main() -> int:
         cores = oc.num_threads()
         if "msm" in results:
             r = results["msm"]
-            m = 1 << 18
+            m = r["n"]
             t0 = time.time()
             want = oc.msm_g1(r["bases"][:m], r["host0"][:m])
             dt = time.time() - t0
@@ -736,7 +839,7 @@ def main() -> int:
             if not np.array_equal(oc.g1_to_affine(got), oc.g1_to_affine(want)):
                 raise SystemExit("bench.py: GPU MSM result differs from the CPU oracle -- refusing to report a number")
             cpu_baseline = {"value": m / dt, "unit": "points/s", "cores": cores, "kind": "port",
-                            "sample": f"one 2^18-point MSM (first quarter of the workload's bases and scalars), {dt:.2f} s; "
+                            "sample": f"one full 2^{LOG_MSM}-point MSM (the workload's bases and first scalar set), {dt:.2f} s; "
                                       "result compared with the GPU's (affine) before timing was accepted"}
         if "plonk" in results and results["plonk"]["sizes"]:
             # the reference's prover cannot run here (no Rust): a LOWER BOUND of its CPU time is the MSM / NTT inventory of one
@@ -780,17 +883,27 @@ def main() -> int:
 
     def msm_block(r):
         n_total = r["n"] * world
+        traffic, traffic_src = ncu_traffic("msm", "msm_accumulate_kernel")
+        acc_imad = r["acc_fq_mul"] / 10.0 * IMAD_PER_MADD
         return {
             "metric": "bn254_g1_msm_2^20_points_per_s", "value": n_total / (r["ms"] * 1e-3), "unit": "points/s",
             "ms_per_step": r["ms"],
             "e2e": {"value": n_total / (r["e2e_ms"] * 1e-3), "unit": "points/s", "ms_per_step": r["e2e_ms"],
                     "h2d_bytes_per_step": 32 * r["n"], "d2h_bytes_per_step": 96},
-            "roofline": {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": 96.0 * r["n"] / (r["acc_ms"] * 1e-3) / 1e9,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": 96.0 * r["n"] / (r["acc_ms"] * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": 1.791135e9 + 62.801664e6, "traffic_source": "ncu --set full, profiles/r1c_msm_raw.csv (dram read + write per "
-                         "launch at 2^20, c = 20: 13.1 M random 64-byte table gathers)", "kernel_ms": r["acc_ms"], "peak_source": peak_src,
-                         "note": "MSM is integer-pipe bound, never HBM bound (SURVEY 8d): see int_roofline"},
-            # 10 Fq products per mixed addition; the first point of a bucket is a copy: N*W - 2^(c-1) additions
+            # the binding roof: the multiplier (fmaheavy) pipe.  N*W - 2^(c-1) mixed additions (the first point of a bucket is a copy)
+            # of 8 M + 2 S each; peak = IMAD.WIDE issue rate measured by the independent probe in this run
+            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": acc_imad / (r["acc_ms"] * 1e-3) / 1e12,
+                         "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": acc_imad / (r["acc_ms"] * 1e-3) / imad_peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": r["acc_ms"], "peak_source": imad_peak_src,
+                         "peak_issue_model": probe.get("model_per_s", 0) / 1e12 or None,
+                         "peak_library_loop": fq_peak * IMAD_PER_MUL / 1e12,
+                         "algorithmic": {"mixed_additions": r["acc_fq_mul"] / 10.0, "imad_per_mixed_addition": IMAD_PER_MADD,
+                                         "fq_products": r["acc_fq_mul"], "bytes": 96.0 * r["n"]},
+                         "note": "MSM is integer-pipe bound, never HBM bound (SURVEY 8d): the HBM view is in hbm_roofline"},
+            "hbm_roofline": {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": 96.0 * r["n"] / (r["acc_ms"] * 1e-3) / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s", "frac": 96.0 * r["n"] / (r["acc_ms"] * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": traffic, "peak_source": peak_src},
+            # the same kernel in field products against the library's own multiplier loop (kept for continuity with round 1)
             "int_roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": r["acc_fq_mul"] / (r["acc_ms"] * 1e-3) / 1e9,
                              "peak": fq_peak / 1e9, "unit": "G Fq-mul/s", "frac": r["acc_fq_mul"] / (r["acc_ms"] * 1e-3) / fq_peak,
                              "fq_mul": r["acc_fq_mul"],
@@ -805,21 +918,22 @@ def main() -> int:
         passes = sum(1 for k in ("pass0", "pass1", "pass2") if r["phases_ms"][k] > 0)
         top = max(("pass0", "pass1", "pass2"), key=lambda k: r["phases_ms"][k])
         top_ms = r["phases_ms"][top]
+        traffic, traffic_src = ncu_traffic("ntt", "ntt_pass_kernel")
+        fr_mul = r["n"] / 2 * lg + r["n"] * (passes - 1)
         b = {
             "metric": "bn254_fr_ntt_2^22_elements_per_s", "value": r["n"] * world / (r["ms"] * 1e-3), "unit": "elements/s",
             "ms_per_step": r["ms"],
             "e2e": {"value": r["n"] * world / (r["e2e_ms"] * 1e-3), "unit": "elements/s", "ms_per_step": r["e2e_ms"],
                     "h2d_bytes_per_step": 32 * r["n"], "d2h_bytes_per_step": 32 * r["n"]},
+            # north star: HBM GB/s per pass -- and the multiplier pipe, which is what binds a 256-bit transform
             "roofline": {"bound": "hbm", "kernel": f"ntt_pass_kernel ({top})", "achieved": 64.0 * r["n"] / (top_ms * 1e-3) / 1e9,
                          "peak": hbm_peak, "unit": "GB/s", "frac": 64.0 * r["n"] / (top_ms * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": 134.431744e6 + 85.389312e6, "traffic_source": "ncu --set full, profiles/r1c_ntt_raw.csv (pass 0 of a 2^22 "
-                         "transform: dram read + write; part of the 128 MiB written stays in L2)", "kernel_ms": top_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": top_ms,
                          "peak_source": peak_src, "passes": passes},
             # Fr products per transform: (N/2) log2 N butterflies + N inter-pass twiddles per pass boundary
-            "int_roofline": {"bound": "imad", "achieved": (r["n"] / 2 * lg + r["n"] * (passes - 1)) / (r["ms"] * 1e-3) / 1e9,
-                             "peak": fq_peak / 1e9, "unit": "G Fr-mul/s",
-                             "frac": (r["n"] / 2 * lg + r["n"] * (passes - 1)) / (r["ms"] * 1e-3) / fq_peak,
-                             "fr_mul": r["n"] / 2 * lg + r["n"] * (passes - 1)},
+            "int_roofline": {"bound": "imad", "achieved": fr_mul * IMAD_PER_MUL / (r["ms"] * 1e-3) / 1e12,
+                             "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": fr_mul * IMAD_PER_MUL / (r["ms"] * 1e-3) / imad_peak,
+                             "fr_mul": fr_mul, "peak_source": imad_peak_src, "peak_library_loop": fq_peak * IMAD_PER_MUL / 1e12},
             "phases_ms": r["phases_ms"], "e2e_roundtrip_ok": r["roundtrip_ok"], "single_call_e2e_ms": r["e2e_single_ms"],
             "e2e_note": "e2e: uzkge_cuda_ntt_fr_batch, 8 host vectors per call, H2D / transform / D2H on three streams (PCIe full duplex); "
                         "single_call_e2e_ms: one uzkge_cuda_ntt_fr call per transform (copy in, transform, copy out in sequence)",
@@ -857,7 +971,7 @@ def main() -> int:
                           "steps under the accumulate kernel); detail.single_call_ms is one MSM per call",
             "l2": "inputs rotate over 8 x 32 MiB scalar sets / 4 x 128 MiB vectors (> 126 MB L2); the MSM's window tables are 0.8 GiB",
         },
-        "e2e": blk["e2e"], "roofline": blk["roofline"], "int_roofline": blk["int_roofline"],
+        "e2e": blk["e2e"], "roofline": blk["roofline"], "int_roofline": blk["int_roofline"], "hbm_roofline": blk.get("hbm_roofline"),
         "gpu_launches": int(launches), "clocks": clocks,
         "cpu_baseline": cpu_baseline if head == "msm" else blk.get("cpu_baseline"),
         "detail": {k: v for k, v in blk.items() if k in ("phases_ms", "single_call_ms", "single_call_e2e_ms", "window_bits", "windows", "srs_device_bytes",

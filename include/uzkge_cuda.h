@@ -141,8 +141,8 @@ UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]);
  * is copied and, in the steady state, nothing synchronises: this is what a device-resident prover pipeline and the
  * HBM-resident benchmark call.  d_out may equal d_in for the NTT; d_scratch holds domain_size elements.
  * Exceptions (first-use set-up, hence not CUDA-graph capturable until warmed up): the FIRST transform of a domain size, and the first
- * use of a (size, coset shift) pair, build their twiddle / coset tables (cudaMalloc + one stream synchronisation); at most 8 coset
- * tables are kept per device, rotating more than 8 (size, shift) pairs rebuilds them (cudaFree + cudaMalloc);
+ * use of a (size, coset shift) pair, build their twiddle / coset tables (cudaMalloc + one stream synchronisation); at most 16 coset
+ * tables (and 8 GiB of them) are kept per device, rotating more (size, shift) pairs rebuilds them (cudaFree + cudaMalloc);
  * uzkge_cuda_grand_product_fr_device and uzkge_cuda_fr_trimmed_len_device read one value back and say so below. */
 UZKGE_API int32_t uzkge_cuda_msm_g1_device(uint64_t handle, size_t base_offset, const void* d_scalars, size_t n, void* d_out_jac, void* stream);
 /* k MSMs over srs[base_offset ..] in one pass (one sort, one accumulate launch, concurrent reductions); d_scalars is a HOST
@@ -151,6 +151,13 @@ UZKGE_API int32_t uzkge_cuda_msm_g1_batch_device(uint64_t handle, size_t base_of
                                                  size_t k, void* d_out_jac, void* stream);
 UZKGE_API int32_t uzkge_cuda_ntt_fr_device(const void* d_in, void* d_out, void* d_scratch, size_t len_in, size_t domain_size,
                                  int32_t inverse, const uint64_t* coset_shift_host, void* stream);
+
+/* k <= 16 independent transforms over ONE domain (and coset shift) in one launch per pass -- the 5 (+3) wire interpolations and the
+ * 5 (+3) coset evaluations of a prover round (plonk/prover.rs:155-170, helpers.rs:256-266): a 2^14-point vector alone fills a tenth
+ * of the SMs and its passes are launch-bound.  d_ins / d_outs / len_in: HOST arrays of k device pointers / lengths; d_scratch holds
+ * k * domain_size elements.  d_outs[j] may equal d_ins[j]; distinct vectors must not overlap. */
+UZKGE_API int32_t uzkge_cuda_ntt_fr_batch_device(const void* const* d_ins, void* const* d_outs, void* d_scratch, const size_t* len_in, size_t k,
+                                                 size_t domain_size, int32_t inverse, const uint64_t* coset_shift_host, void* stream);
 
 /* Cross-GPU step of a distributed transform of size n_total = G * L over G = 2^log_ranks ranks (four-step NTT, SURVEY 8e:
  * "NTTs of size 2^22 and above use a four-step transpose over NVLink with NCCL all-to-all").  d_in holds G rows of
@@ -249,6 +256,10 @@ UZKGE_API int32_t uzkge_cuda_fr_add_sparse_device(void* d_poly, const size_t* id
 UZKGE_API int32_t uzkge_cuda_fr_powers_device(const uint64_t base_host[4], const uint64_t* scale_host, size_t n, void* d_out, void* stream);
 /* out[i] = src[idx[i]], idx: n uint32 on the device: ConstraintSystem::extend_witness (plonk/constraint_system/mod.rs:103-111). */
 UZKGE_API int32_t uzkge_cuda_fr_gather_device(const void* d_src, const void* d_idx_u32, size_t n, void* d_out, void* stream);
+/* dst[dst_idx[j]] = src[src_idx[j]], j < k; both index arrays are uint32 on the device: pi_poly's evaluation vector (the public inputs on
+ * their constraint rows, plonk/helpers.rs:111-131) filled straight from the device-resident witness. */
+UZKGE_API int32_t uzkge_cuda_fr_gather_scatter_device(const void* d_src, const void* d_src_idx_u32, void* d_dst, const void* d_dst_idx_u32, size_t k,
+                                                      void* stream);
 /* out[i] = a[i] * b[i], i < n (witness generation of synthetic circuits; FpPolynomial's pointwise products). */
 UZKGE_API int32_t uzkge_cuda_fr_mul_device(const void* d_a, const void* d_b, size_t n, void* d_out, void* stream);
 /* *len_out = number of coefficients after FpPolynomial::from_coefs' trailing-zero trim (field_polynomial.rs:86-90): 1 + the largest
@@ -264,6 +275,90 @@ UZKGE_API int32_t uzkge_cuda_grand_product_fr_device(const void* d_num, const vo
 UZKGE_API int32_t uzkge_cuda_plonk_z_evals_fr_device(const void* const d_w[5], const void* const d_sigma[5], const void* d_group,
                                                      const uint64_t* k_host, const uint64_t beta_host[4], const uint64_t gamma_host[4], size_t n,
                                                      void* d_z, void* d_tmp, void* stream);
+
+/* ---- the whole prover behind the boundary ---------------------------------------------------------------------
+ * prover_with_lagrange (plonk/prover.rs:88-394) as ONE call: the caller (the patched Rust body) keeps what is serial and cheap -- building
+ * the constraint system, transcript_init_plonk (plonk/transcript.rs:8-31), the RNG draws -- and hands over everything that touches a
+ * polynomial.  All five rounds run device-resident; the library hashes the Fiat-Shamir transcript itself (Keccak-256, same bytes as
+ * utils/transcript.rs) between the rounds.
+ *
+ * 1. uzkge_cuda_plonk_params_upload: once per circuit, from PlonkProverParams (plonk/indexer.rs:77-139).  Only the COEFFICIENT forms and the
+ *    permutation travel (host pointers, Montgomery Fr; `len` coefficients each, a NULL pointer or len 0 is the zero polynomial); the
+ *    evaluations on the quotient coset (q_coset_evals, s_coset_evals, ... 6 n values per polynomial in the reference's struct) are
+ *    recomputed on the device, as are `group`, `coset_quotient`, l1 and Z_H^-1 on the coset.
+ * 2. uzkge_cuda_srs_upload_lagrange_commit: the bases of the `commit` closure of prover_with_lagrange (prover.rs:131-146) as one SRS:
+ *    [L_0(tau) G .. L_(n-1)(tau) G | SRS[0..3) | SRS[n..n+3)], so that lagrange_pcs.commit(evals) + apply_blind_factors(blinds, n)
+ *    (kzg_poly_commitment.rs:299-313) is a single MSM over [evals | b | -b].
+ * 3. uzkge_cuda_plonk_prove. */
+typedef struct {
+    uint64_t n;                          /* cs.size(), a power of two */
+    uint64_t m;                          /* cs.quot_eval_dom_size(): 6 n (n > 8) or 16 n */
+    uint64_t num_vars;                   /* witness length */
+    const uint32_t* wiring;              /* 5 n variable indices, wire-major: ConstraintSystem::extend_witness (constraint_system/mod.rs:103-111) */
+    const uint64_t* permutation;         /* 5 n positions (usize as u64): PlonkProverParams::permutation */
+    uint64_t k[5][4];                    /* verifier_params.k, Montgomery */
+    const uint64_t* q_polys[9];          /* N_SELECTORS = 9 */
+    size_t q_len[9];
+    const uint64_t* s_polys[5];
+    size_t s_len[5];
+    const uint64_t* qb_poly;
+    size_t qb_len;
+    const uint64_t* q_prk_polys[4];
+    size_t q_prk_len[4];
+    uint64_t anemoi_generator[4], anemoi_generator_inv[4];
+    const uint64_t* public_vars_constraint_indices;   /* n_public rows */
+    const uint64_t* public_vars_witness_indices;      /* n_public variable indices */
+    size_t n_public;
+    int32_t shuffle;                     /* 1: the `shuffle` feature set (zshuffle, zmatchmaking): the fields below are read */
+    int32_t reserved;
+    const uint64_t* q_ecc_poly;
+    size_t q_ecc_len;
+    const uint64_t* q_shuffle_generator_polys[12];
+    size_t gen_len[12];
+    const uint64_t* q_shuffle_public_key_polys[12];
+    size_t pk_len[12];
+    uint64_t edwards_a[4];
+} uzkge_plonk_params_desc;
+UZKGE_API int32_t uzkge_cuda_plonk_params_upload(const uzkge_plonk_params_desc* desc, uint64_t* params_handle);
+/* refresh_prover_params_public_key (shuffle/src/gen_params/params.rs:57-129): replace the 12 public-key selector polynomials. */
+UZKGE_API int32_t uzkge_cuda_plonk_params_set_public_key(uint64_t params_handle, const uint64_t* const polys[12], const size_t len[12]);
+UZKGE_API int32_t uzkge_cuda_plonk_params_free(uint64_t params_handle);
+/* lagrange_xy: the n points of the size-n Lagrange SRS; monomial_xy: at least n + 3 points of the monomial SRS (only [0, 3) and
+ * [n, n + 3) are read -- exactly what the bundled srs-padding.bin keeps, gen_params/mod.rs:147-171). */
+UZKGE_API int32_t uzkge_cuda_srs_upload_lagrange_commit(const uint64_t* lagrange_xy, size_t n, const uint64_t* monomial_xy, size_t monomial_len,
+                                                        uint32_t window_bits, uint64_t* handle);
+
+typedef struct {
+    uint64_t params;                     /* uzkge_cuda_plonk_params_upload */
+    uint64_t srs;                        /* monomial SRS (>= n + 3 points); may be 0 when lagrange_all is set */
+    uint64_t lagrange_srs;               /* uzkge_cuda_srs_upload_lagrange_commit, or 0: every commitment over the monomial SRS */
+    int32_t lagrange_all;                /* 1: also the witness selectors, quotient pieces and opening proofs over the Lagrange bases
+                                            (helpers.rs:1363-1391, pcs.rs:139-163) -- required when the monomial SRS has holes */
+    int32_t witness_on_device;           /* 0: `witness` is a host pointer; 1: a device pointer */
+    const uint64_t* witness;             /* num_vars Montgomery Fr */
+    const uint64_t* w_sel_evals[3];      /* shuffle feature set: compute_witness_selectors (turbo/mod.rs:171-191), n Fr each (host);
+                                            all NULL when the circuit has no remark gate */
+    const uint64_t* blinds;              /* the prover's Fr::rand draws in the reference's order (Montgomery): wires 3,3,3,2,2;
+                                            [3 x 2 witness selectors]; z 3; 5 quotient-split blinds -- 21 values, 27 with shuffle */
+    size_t n_blinds;
+    const uint8_t* transcript;           /* transcript state after transcript_init_plonk */
+    size_t transcript_len;
+} uzkge_plonk_prove_args;
+/* PlonkProof (plonk/indexer.rs:33-75).  Commitments: affine x, y in Montgomery form (x = y = 0: the identity); evaluations: Montgomery Fr. */
+typedef struct {
+    uint64_t cm_w[5][8], cm_w_sel[3][8], cm_t[5][8], cm_z[8];
+    uint64_t prk_3_poly_eval_zeta[4], prk_4_poly_eval_zeta[4];
+    uint64_t w_polys_eval_zeta[5][4], w_polys_eval_zeta_omega[3][4], z_eval_zeta_omega[4], s_polys_eval_zeta[4][4];
+    uint64_t q_ecc_poly_eval_zeta[4], w_sel_polys_eval_zeta[3][4];
+    uint64_t opening_witness_zeta[8], opening_witness_zeta_omega[8];
+    uint8_t transcript_state[32];        /* the transcript after the proof: the state is always one 32-byte slot here */
+    uint32_t launches;                   /* kernels launched for this proof */
+    uint32_t msm, ifft_n, fft_n, coset_fft_m, coset_ifft_m, evals;    /* what ran: the proof's operation inventory */
+    double rounds_ms[6];                 /* wall clock per stage: wires, z, quotient, commit t, evaluations + r, openings */
+} uzkge_plonk_proof;
+/* Errors: UZKGE_ERR_SIZE = a polynomial does not fit the SRS (the reference's DegreeError: an unsatisfied witness makes the quotient
+ * too long) or too few blinds; UZKGE_ERR_ARG = the opening remainder is not zero (PCSProveEvalError) / bad arguments. */
+UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* args, uzkge_plonk_proof* proof);
 
 /* ---- small group helpers (combine per-GPU partial MSMs; blinds) --------------------------------------
  * out = a + b on Jacobian points (host pointers, tiny device kernel).  Used for the G - 1 projective adds

@@ -15,6 +15,7 @@
 #include <array>
 #include <cstdint>
 #include <cstring>
+#include <stdexcept>
 #include <vector>
 
 extern "C" {
@@ -128,10 +129,19 @@ class Transcript {
     std::vector<uint8_t> state;
 
     explicit Transcript(const std::vector<uint8_t>& msg) { append_message(msg.data(), msg.size()); }
+    // resume from a serialised state (what the caller of uzkge_cuda_plonk_prove hands over after transcript_init_plonk)
+    static Transcript from_state(const uint8_t* bytes, size_t len) {
+        Transcript t("");
+        t.state.assign(bytes, bytes + len);
+        return t;
+    }
     explicit Transcript(const char* label) { append_message(reinterpret_cast<const uint8_t*>(label), std::strlen(label)); }
 
+    // utils/transcript.rs:20-30: short messages are left-padded to one slot, longer ones must be whole slots (the reference asserts
+    // `len % SLOT_SIZE == 0`): a misaligned message fails here instead of silently diverging from the reference's transcript
     void append_message(const uint8_t* msg, size_t len) {
-        if (len < SLOT_SIZE) state.insert(state.end(), SLOT_SIZE - len, 0);   // left-padded to one slot
+        if (len >= SLOT_SIZE && len % SLOT_SIZE != 0) throw std::invalid_argument("Transcript::append_message: length must be a multiple of 32");
+        if (len < SLOT_SIZE) state.insert(state.end(), SLOT_SIZE - len, 0);
         state.insert(state.end(), msg, msg + len);
     }
     void append_u64(uint64_t a) {

@@ -268,6 +268,15 @@ static int run_serial(int argc, char** argv) {
     const Limbs c2 = tr.get_challenge_field_elem();
     print_hex("challenge1", FR.from_mont(c1));
     print_hex("challenge2", FR.from_mont(c2));
+    // utils/transcript.rs:20-30 asserts whole slots for messages of 32 bytes and more: the C++ twin must refuse them too
+    bool refused = false;
+    try {
+        const uint8_t junk[40] = {};
+        tr.append_message(junk, sizeof junk);
+    } catch (const std::invalid_argument&) {
+        refused = true;
+    }
+    CHECK(refused);
     return failures;
 }
 

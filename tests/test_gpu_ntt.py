@@ -155,3 +155,34 @@ def test_batch_host_transforms_match_single_calls(gpu, oc, n):
         gpu.ntt_fr_batch_inplace(bufs, lens, n, inverse=inverse, coset_shift=cs)
         for j in range(k):
             assert np.array_equal(bufs[j], want[j]), (inverse, cs is not None, j)
+
+
+@pytest.mark.parametrize("n,k", [(1 << 10, 3), (1 << 14, 8), (3 << 13, 5), (3 << 14, 16), (1 << 17, 2)])
+def test_batched_device_transforms_match_oracle(gpu, oc, n, k):
+    """uzkge_cuda_ntt_fr_batch_device: k vectors of one domain in one launch per pass (the prover's rounds), ragged inputs, every
+    variant, in place and out of place -- each vector equals the oracle's single transform."""
+    import torch
+
+    shift = oc.random_fr(1, 909)[0]
+    xs = [oc.random_fr(n - 37 * j if j % 2 else n, 3000 + j + n % 11) for j in range(k)]
+    d_in = [torch.zeros(4 * n, dtype=torch.int64, device="cuda") for _ in range(k)]
+    d_out = [torch.zeros(4 * n, dtype=torch.int64, device="cuda") for _ in range(k)]
+    scratch = torch.empty(4 * n * k, dtype=torch.int64, device="cuda")
+    for inverse in (False, True):
+        for cs in (None, shift):
+            for j in range(k):
+                d_in[j].zero_()
+                d_in[j][: 4 * xs[j].shape[0]].copy_(torch.from_numpy(xs[j].view(np.int64).reshape(-1)))
+            gpu.ntt_fr_batch_device([t.data_ptr() for t in d_in], [t.data_ptr() for t in d_out], scratch.data_ptr(),
+                                    [x.shape[0] for x in xs], n, inverse, cs)
+            torch.cuda.synchronize()
+            for j in range(k):
+                want = oc.ntt_fr(xs[j], n, inverse, cs)
+                assert np.array_equal(d_out[j].cpu().numpy().view(np.uint64).reshape(n, 4), want), (n, k, j, inverse, cs is not None)
+    # in place
+    gpu.ntt_fr_batch_device([t.data_ptr() for t in d_in], [t.data_ptr() for t in d_in], scratch.data_ptr(), [n] * k, n)
+    torch.cuda.synchronize()
+    for j in range(k):
+        full = np.zeros((n, 4), dtype=np.uint64)
+        full[: xs[j].shape[0]] = xs[j]
+        assert np.array_equal(d_in[j].cpu().numpy().view(np.uint64).reshape(n, 4), oc.ntt_fr(full, n))

@@ -130,6 +130,12 @@ int engine_fail(int rc, const char* what) {
     return fail(rc, what);
 }
 
+}  // namespace
+namespace uz {
+int api_fail(int code, const char* what) { return fail(code, what); }   // for the other translation units (prover.cu)
+}
+namespace {
+
 // SRS handles carry their device: bits 48..55 = device + 1, bit 63 = multi-device handle (see the bottom of this file)
 constexpr uint64_t HANDLE_MULTI = 1ull << 63;
 inline int handle_device(uint64_t h) { return (int)((h >> 48) & 0xff) - 1; }
@@ -512,6 +518,28 @@ UZKGE_API int32_t uzkge_cuda_ntt_fr_device(const void* d_in, void* d_out, void* 
     return engine_fail(rc, "ntt_fr_device");
 }
 
+UZKGE_API int32_t uzkge_cuda_ntt_fr_batch_device(const void* const* d_ins, void* const* d_outs, void* d_scratch, const size_t* len_in, size_t k,
+                                                 size_t domain_size, int32_t inverse, const uint64_t* coset_shift_host, void* stream) {
+    if (k == 0) return UZKGE_OK;
+    if (!d_ins || !d_outs || !d_scratch || !len_in) return fail(UZKGE_ERR_ARG, "ntt_fr_batch_device: null pointer");
+    if (k > NTT_MAX_BATCH) return fail(UZKGE_ERR_SIZE, "ntt_fr_batch_device: at most 16 vectors per call");
+    API_ENTER(-1);
+    bool ok = false;
+    ntt_root_of_unity(domain_size, &ok);
+    if (!ok || domain_size % 9 == 0) return fail(UZKGE_ERR_SIZE, "ntt_fr_batch_device: domain size must be 2^k or 3 * 2^k");
+    uint64_t lens[NTT_MAX_BATCH];
+    for (size_t j = 0; j < k; j++) {
+        if (!d_ins[j] || !d_outs[j]) return fail(UZKGE_ERR_ARG, "ntt_fr_batch_device: null vector");
+        if (len_in[j] > domain_size) return fail(UZKGE_ERR_SIZE, "ntt_fr_batch_device: input longer than the domain");
+        lens[j] = len_in[j];
+    }
+    fe shift;
+    if (coset_shift_host) memcpy(&shift, coset_shift_host, sizeof(fe));
+    int rc = g.ntt->run_batch((const fe* const*)d_ins, (fe* const*)d_outs, (fe*)d_scratch, lens, (uint32_t)k, domain_size, inverse != 0,
+                              coset_shift_host ? &shift : nullptr, (cudaStream_t)stream);
+    return engine_fail(rc, "ntt_fr_batch_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_ntt_cross_fr_device(const void* d_in, void* d_out, uint32_t log_ranks, size_t cols, size_t col_offset,
                                                  size_t n_total, int32_t inverse, void* stream) {
     if (!d_in || !d_out || d_in == d_out) return fail(UZKGE_ERR_ARG, "ntt_cross_fr_device: null or aliasing pointers");
@@ -721,6 +749,14 @@ UZKGE_API int32_t uzkge_cuda_fr_gather_device(const void* d_src, const void* d_i
     int rc = fr_gather_run(d_src, d_idx_u32, n, d_out, (cudaStream_t)stream);
     if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_gather_device: null pointer");
     return engine_fail(rc, "fr_gather_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_fr_gather_scatter_device(const void* d_src, const void* d_src_idx_u32, void* d_dst, const void* d_dst_idx_u32, size_t k,
+                                                      void* stream) {
+    API_ENTER(-1);
+    int rc = fr_gather_scatter_run(d_src, d_src_idx_u32, d_dst, d_dst_idx_u32, k, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_gather_scatter_device: null pointer");
+    return engine_fail(rc, "fr_gather_scatter_device");
 }
 
 UZKGE_API int32_t uzkge_cuda_fr_mul_device(const void* d_a, const void* d_b, size_t n, void* d_out, void* stream) {

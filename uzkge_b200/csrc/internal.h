@@ -107,6 +107,8 @@ struct NttCoset {
 };
 
 
+static constexpr uint32_t NTT_MAX_BATCH = 16;
+
 class NttEngine {
 public:
     explicit NttEngine(int sm_count) : sm_count_(sm_count) {}
@@ -119,6 +121,9 @@ public:
     }
     int run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, uint64_t n, bool inverse, const fe* coset_shift,
             cudaStream_t st);
+    // k <= NTT_MAX_BATCH vectors over one domain, one launch per pass (blockIdx.y = vector); d_scratch: k * n elements
+    int run_batch(const fe* const* d_in, fe* const* d_out, fe* d_scratch, const uint64_t* len_in, uint32_t k, uint64_t n, bool inverse,
+                  const fe* coset_shift, cudaStream_t st);
     // cross-rank step of a distributed transform (see ntt.cu)
     int cross(const fe* d_in, fe* d_out, uint32_t log_g, uint64_t cols, uint64_t col_offset, uint64_t n_total, bool inverse,
               cudaStream_t st);
@@ -167,6 +172,7 @@ struct MsmSrs {
     affine* tables = nullptr;  // windows x n affine points: table f holds 2^(c*f) * P_i
     MsmWork work[2];
     size_t cub_temp_bytes = 0;
+    size_t reduce_bytes = 0;   // reduction workspace of one slot (the slots' workspaces are contiguous)
 };
 
 // inverse transform over G1 points: Lagrange SRS from the monomial SRS (ec_ntt.cu)
@@ -183,7 +189,8 @@ int msm_affine_accumulate(const MsmSrs* s, const MsmWork& w, void* aff_ws, uint6
 size_t msm_reduce_workspace_bytes(uint32_t c, uint32_t sm_count);
 ReducePlan* msm_reduce_plan_create(uint32_t c, uint32_t sm_count, xyzz* buckets, void* workspace, uint32_t* ticket);
 void msm_reduce_plan_destroy(ReducePlan* p);
-int msm_reduce_run(const ReducePlan* p, jacobian* d_out, cudaStream_t st);
+int msm_reduce_run(const ReducePlan* p, uint32_t k, const xyzz* buckets, size_t bucket_stride, size_t ws_stride_bytes, jacobian* d_out,
+                   cudaStream_t st);
 
 class MsmEngine {
 public:
@@ -255,6 +262,7 @@ int fr_lincomb_run(const void* const* d_polys, const size_t* lens, const uint64_
 int fr_add_sparse_run(void* d_poly, const size_t* idx, const uint64_t* vals, size_t k, cudaStream_t st);
 int fr_powers_run(const uint64_t* base, const uint64_t* scale, size_t n, void* d_out, cudaStream_t st);
 int fr_gather_run(const void* d_src, const void* d_idx, size_t n, void* d_out, cudaStream_t st);
+int fr_gather_scatter_run(const void* d_src, const void* d_src_idx, void* d_dst, const void* d_dst_idx, size_t k, cudaStream_t st);
 int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out, cudaStream_t st);
 int fr_trimmed_len_run(const void* d_poly, size_t n, unsigned long long* d_scratch, size_t* len_out, cudaStream_t st);
 int plonk_z_evals_run(PolyEngine* poly, const void* const d_w[5], const void* const d_sigma[5], const void* d_group, const uint64_t* k,

@@ -478,6 +478,7 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     s->nbuckets = (1u << (c - 1)) + 1;  // 0 (zero digit, always empty) .. 2^(c-1)
     const size_t reduce_bytes = msm_reduce_workspace_bytes(c, (uint32_t)sm_count_);
     if (reduce_bytes == 0) return UZKGE_ERR_SIZE;
+    s->reduce_bytes = reduce_bytes;
     s->slots = choose_batch_slots(n, s->nbuckets, windows, reduce_bytes);
     const size_t m = (size_t)windows * n;          // entries of one full-size MSM
     const size_t m_all = m * s->slots;
@@ -777,30 +778,9 @@ int MsmEngine::stage_accumulate(MsmSrs* s, MsmWork& w, const GroupPlan& plan, cu
     return UZKGE_OK;
 }
 
-// the k bucket reductions are latency-bound chains of small kernels: run them side by side on auxiliary streams
+// the k bucket reductions of a batch: one launch per level, the slot is the grid's second dimension (msm_reduce.cu)
 int MsmEngine::stage_reduce(MsmSrs* s, MsmWork& w, uint32_t k, jacobian* d_out, cudaStream_t st) {
-    if (k == 1) return msm_reduce_run(w.reduce[0], d_out, st);
-    while (aux_.size() < k - 1) {
-        cudaStream_t a;
-        cudaEvent_t ev;
-        UZ_CUDA_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-        UZ_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        aux_.push_back(a);
-        join_.push_back(ev);
-    }
-    if (!fork_) UZ_CUDA_TRY(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
-    UZ_CUDA_TRY(cudaEventRecord(fork_, st));
-    for (uint32_t j = 0; j < k; j++) {
-        cudaStream_t sj = j == 0 ? st : aux_[j - 1];
-        if (j) UZ_CUDA_TRY(cudaStreamWaitEvent(sj, fork_, 0));
-        const int rc = msm_reduce_run(w.reduce[j], d_out + j, sj);
-        if (rc != UZKGE_OK) return rc;
-        if (j) {
-            UZ_CUDA_TRY(cudaEventRecord(join_[j - 1], sj));
-            UZ_CUDA_TRY(cudaStreamWaitEvent(st, join_[j - 1], 0));
-        }
-    }
-    return UZKGE_OK;
+    return msm_reduce_run(w.reduce[0], k, w.buckets, s->nbuckets, s->reduce_bytes, d_out, st);
 }
 
 static int msm_check_group(const MsmSrs* s, size_t base_offset, const size_t* n, size_t k) {

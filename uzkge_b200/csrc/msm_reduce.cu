@@ -27,6 +27,21 @@ namespace uz {
 
 static constexpr int SUM_NT = 128;  // 4 warps per CTA, one per SM sub-partition
 
+// The k reductions of a batch run in ONE launch per level: blockIdx.y is the slot, and every pointer of slot 0's plan is moved into
+// slot j's copy of the same layout -- by j * bucket_stride when it points into the bucket array, else by j * ws_stride (the
+// reduction workspaces of the slots are laid out identically, msm.cu: MsmEngine::upload).
+struct SlotMap {
+    const xyzz* bucket_lo;
+    const xyzz* bucket_hi;
+    size_t bucket_stride, ws_stride;   // in xyzz units
+    uint32_t ticket_stride;            // in uint32 units
+};
+template <class T>
+__device__ __forceinline__ T* slot_ptr(T* p, const SlotMap& m, uint32_t j) {
+    const xyzz* q = (const xyzz*)p;
+    return (T*)(q + (size_t)j * ((q >= m.bucket_lo && q < m.bucket_hi) ? m.bucket_stride : m.ws_stride));
+}
+
 // ------------------------------------------------------------------ level 0: strip sums over the buckets
 // thread t < rows * nq : RP[hi][q] = sum of the LR consecutive entries of row hi starting at q * LR
 // thread t >= rows * nq: CP[s][lo] = sum of the LC entries of column lo in rows s * LC ..
@@ -36,7 +51,10 @@ struct StripArgs {
     xyzz* cp;
     uint32_t rows, cols, lr, lc;
 };
-__global__ void __launch_bounds__(256, 2) msm_strips_kernel(const StripArgs a) {
+__global__ void __launch_bounds__(256, 2) msm_strips_kernel(StripArgs a, const SlotMap sm) {
+    a.src = slot_ptr(a.src, sm, blockIdx.y);
+    a.rp = slot_ptr(a.rp, sm, blockIdx.y);
+    a.cp = slot_ptr(a.cp, sm, blockIdx.y);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nq = a.cols / a.lr, ns = a.rows / a.lc;
     const uint32_t n_rp = a.rows * nq;
@@ -76,7 +94,7 @@ struct SumsArgs {
     SumFamily f[8];
     uint32_t nfam, total;
 };
-__global__ void __launch_bounds__(SUM_NT) msm_sums_kernel(const SumsArgs a) {
+__global__ void __launch_bounds__(SUM_NT) msm_sums_kernel(const SumsArgs a, const SlotMap sm) {
     __shared__ xyzz bufs[SUM_NT / 32][32];
     uint32_t o = blockIdx.x * (SUM_NT / 32) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
@@ -87,7 +105,7 @@ __global__ void __launch_bounds__(SUM_NT) msm_sums_kernel(const SumsArgs a) {
         k++;
     }
     const SumFamily& f = a.f[k];
-    const xyzz* base = f.src + (size_t)o * f.ostride;
+    const xyzz* base = slot_ptr(f.src, sm, blockIdx.y) + (size_t)o * f.ostride;
     xyzz acc = xyzz_identity();
     if (lane < f.count) acc = ld_xyzz(base + (size_t)lane * f.estride);
 #pragma unroll 1
@@ -98,7 +116,7 @@ __global__ void __launch_bounds__(SUM_NT) msm_sums_kernel(const SumsArgs a) {
     uint32_t n = 1;
     while (n < f.count && n < 32) n <<= 1;
     warp_team_tree(buf, n);
-    if (lane == 0) st_xyzz(f.dst + o, buf[0]);
+    if (lane == 0) st_xyzz(slot_ptr(f.dst, sm, blockIdx.y) + o, buf[0]);
 }
 
 // ------------------------------------------------------------------ leaves: one warp per (array, bit) item
@@ -116,7 +134,10 @@ struct FinalArgs {
     uint32_t* ticket;
     jacobian* out;
 };
-__global__ void __launch_bounds__(SUM_NT) msm_leaves_kernel(const FinalArgs a) {
+__global__ void __launch_bounds__(SUM_NT) msm_leaves_kernel(const FinalArgs a, const SlotMap sm) {
+    xyzz* const partial = slot_ptr(a.partial, sm, blockIdx.y);
+    uint32_t* const ticket = a.ticket + (size_t)blockIdx.y * sm.ticket_stride;
+    jacobian* const out = a.out + blockIdx.y;
     __shared__ xyzz bufs[SUM_NT / 32][32];
     __shared__ uint32_t is_last;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,7 +146,7 @@ __global__ void __launch_bounds__(SUM_NT) msm_leaves_kernel(const FinalArgs a) {
     if (w < a.nitems) {
         const FinalItem& it = a.it[w];
         xyzz v = xyzz_identity();
-        if (lane < it.len && (it.bit < 0 || ((lane >> it.bit) & 1))) v = ld_xyzz(it.src + lane);
+        if (lane < it.len && (it.bit < 0 || ((lane >> it.bit) & 1))) v = ld_xyzz(slot_ptr(it.src, sm, blockIdx.y) + lane);
         buf[lane] = v;
         __syncwarp();
         uint32_t n = 1;
@@ -134,28 +155,28 @@ __global__ void __launch_bounds__(SUM_NT) msm_leaves_kernel(const FinalArgs a) {
         v = buf[0];
 #pragma unroll 1
         for (uint32_t i = 0; i < it.shift; i++) v = team4_dbl(v);
-        if (lane == 0) st_xyzz(a.partial + w, v);
+        if (lane == 0) st_xyzz(partial + w, v);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last || warp != 0) return;
     __threadfence();
     xyzz v = xyzz_identity();
-    if (lane < a.nitems) v = ld_xyzz(a.partial + lane);
-    if (lane + 32 < a.nitems) v = xyzz_add_call(v, ld_xyzz(a.partial + lane + 32));
+    if (lane < a.nitems) v = ld_xyzz(partial + lane);
+    if (lane + 32 < a.nitems) v = xyzz_add_call(v, ld_xyzz(partial + lane + 32));
     buf[lane] = v;
     __syncwarp();
     warp_team_tree(buf, 32);
     if (lane == 0) {
         const jacobian j = xyzz_to_jacobian<FqCall>(buf[0]);
-        st_fe(&a.out->x, j.x);
-        st_fe(&a.out->y, j.y);
-        st_fe(&a.out->z, j.z);
-        *a.ticket = 0;
+        st_fe(&out->x, j.x);
+        st_fe(&out->y, j.y);
+        st_fe(&out->z, j.z);
+        *ticket = 0;
     }
 }
 
@@ -281,19 +302,28 @@ ReducePlan* msm_reduce_plan_create(uint32_t c, uint32_t sm_count, xyzz* buckets,
 }
 void msm_reduce_plan_destroy(ReducePlan* p) { delete p; }
 
-int msm_reduce_run(const ReducePlan* p, jacobian* d_out, cudaStream_t st) {
+// k reductions (slots 0 .. k - 1 of one workspace, plan of slot 0) in one launch per level; d_out receives k consecutive points
+int msm_reduce_run(const ReducePlan* p, uint32_t k, const xyzz* buckets, size_t bucket_stride, size_t ws_stride_bytes, jacobian* d_out,
+                   cudaStream_t st) {
+    if (k == 0) return UZKGE_OK;
+    SlotMap sm;
+    sm.bucket_lo = buckets;
+    sm.bucket_hi = buckets + bucket_stride;
+    sm.bucket_stride = bucket_stride;
+    sm.ws_stride = ws_stride_bytes / sizeof(xyzz);
+    sm.ticket_stride = 256 / 4;
     uint32_t launches = 0;
     if (p->has_strips) {
-        msm_strips_kernel<<<(p->strip_threads + 255) / 256, 256, 0, st>>>(p->strips);
+        msm_strips_kernel<<<dim3((p->strip_threads + 255) / 256, k), 256, 0, st>>>(p->strips, sm);
         launches++;
     }
     for (const SumsArgs& sa : p->passes) {
-        msm_sums_kernel<<<(sa.total + SUM_NT / 32 - 1) / (SUM_NT / 32), SUM_NT, 0, st>>>(sa);
+        msm_sums_kernel<<<dim3((sa.total + SUM_NT / 32 - 1) / (SUM_NT / 32), k), SUM_NT, 0, st>>>(sa, sm);
         launches++;
     }
     FinalArgs fa = p->fin;
     fa.out = d_out;
-    msm_leaves_kernel<<<(fa.nitems + SUM_NT / 32 - 1) / (SUM_NT / 32), SUM_NT, 0, st>>>(fa);
+    msm_leaves_kernel<<<dim3((fa.nitems + SUM_NT / 32 - 1) / (SUM_NT / 32), k), SUM_NT, 0, st>>>(fa, sm);
     launches++;
     UZ_COUNT_LAUNCH(launches);
     return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;

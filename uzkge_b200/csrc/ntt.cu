@@ -17,6 +17,8 @@
 // multiplier latency better than instruction-level parallelism does.
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "devmem.cuh"
 #include "internal.h"
 #include "ntt_plan.h"
@@ -51,12 +53,16 @@ __device__ __forceinline__ fe pow2l(const fe* lo, const fe* hi, uint64_t e) {
     return fe_mul<FrP>(a, ldg_fe(hi + h));
 }
 
+// up to NTT_MAX_BATCH independent vectors of one domain travel through a pass in ONE launch: blockIdx.y is the vector
+struct NttJobs {
+    const fe* in[NTT_MAX_BATCH];
+    fe* out[NTT_MAX_BATCH];
+    uint64_t len_in[NTT_MAX_BATCH];
+};
 struct NttKernelArgs {
     NttPass p;
-    const fe* in;
-    fe* out;
+    NttJobs jobs;
     uint64_t n;
-    uint64_t len_in;
     const fe* stage_tab;
     const fe* w_lo;
     const fe* w_hi;
@@ -81,6 +87,9 @@ __global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
     tile /= p.inner_tiles;
     const uint32_t o = tile % p.outer;
     const uint32_t b = tile / p.outer;
+    const fe* const in = a.jobs.in[blockIdx.y];
+    fe* const out = a.jobs.out[blockIdx.y];
+    const uint64_t len_in = a.jobs.len_in[blockIdx.y];
 
     // ---- load (+ zero padding, + coset pre-scale on the very first read of the input)
     for (uint32_t idx = threadIdx.x; idx < T; idx += NT) {
@@ -94,10 +103,10 @@ __global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
         }
         const uint64_t g = ntt_in_index(p, b, o, t, r, c);
         fe x;
-        if (a.zero_pad && g >= a.len_in) {
+        if (a.zero_pad && g >= len_in) {
             x = fe_zero();
         } else {
-            x = ld_fe(a.in + g);
+            x = ld_fe(in + g);
             if (a.pre_coset) x = fe_mul<FrP>(x, ldg_fe(a.g_full + g));
         }
         tv.st(tv.pos(r, c), x);
@@ -135,15 +144,14 @@ __global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
             else if (a.has_scale)
                 x = fe_mul<FrP>(x, a.scale);
         }
-        st_fe(a.out + g, x);
+        st_fe(out + g, x);
     }
 }
 
 // radix-3 pre-pass for N = 3 * M:  y[k*M + n] = w_N^(n*k) * sum_{m<3} x[m*M + n] * w_3^(m*k)
 struct Radix3Args {
-    const fe* in;
-    fe* out;
-    uint64_t m, len_in;
+    NttJobs jobs;
+    uint64_t m;
     const fe* w_lo;
     const fe* w_hi;
     const fe* g_full;
@@ -154,12 +162,15 @@ struct Radix3Args {
 __global__ void __launch_bounds__(256) ntt_radix3_kernel(const Radix3Args a) {
     const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= a.m) return;
+    const fe* const in = a.jobs.in[blockIdx.y];
+    fe* const out = a.jobs.out[blockIdx.y];
+    const uint64_t len_in = a.jobs.len_in[blockIdx.y];
     fe x[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const uint64_t g = (uint64_t)i * a.m + n;
-        if (g < a.len_in) {
-            x[i] = ld_fe(a.in + g);
+        if (g < len_in) {
+            x[i] = ld_fe(in + g);
             if (a.pre_coset) x[i] = fe_mul<FrP>(x[i], ldg_fe(a.g_full + g));
         } else {
             x[i] = fe_zero();
@@ -172,9 +183,9 @@ __global__ void __launch_bounds__(256) ntt_radix3_kernel(const Radix3Args a) {
     fe y2 = fe_add<FrP>(fe_add<FrP>(x[0], b2), c2);
     y1 = fe_mul<FrP>(y1, ldg_fe(a.tw3 + n));
     y2 = fe_mul<FrP>(y2, ldg_fe(a.tw3 + a.m + n));
-    st_fe(a.out + n, y0);
-    st_fe(a.out + a.m + n, y1);
-    st_fe(a.out + 2 * a.m + n, y2);
+    st_fe(out + n, y0);
+    st_fe(out + a.m + n, y1);
+    st_fe(out + 2 * a.m + n, y2);
 }
 
 // ---- cross-GPU step of a distributed transform of size N = G * L (G = 2, 4, 8 ranks, L = N / G per rank).
@@ -323,7 +334,11 @@ const NttDomain* NttEngine::domain(uint64_t n, cudaStream_t st) {
             if (d.plan.pass[i].tw_mul) elems += n;
         if (d.plan.mixed) elems += 2 * d.plan.m;
         if (elems) {
-            if (cudaMalloc(&d.tw_all, sizeof(fe) * elems) != cudaSuccess) return nullptr;
+            if (cudaMalloc(&d.tw_all, sizeof(fe) * elems) != cudaSuccess) {
+                cudaStreamSynchronize(st);   // the power tables are still being written
+                cudaFree(d.w_lo);
+                return nullptr;
+            }
             fe* cur = d.tw_all;
             for (uint32_t i = 0; i < d.plan.npass; i++) {
                 const NttPass& p = d.plan.pass[i];
@@ -341,7 +356,11 @@ const NttDomain* NttEngine::domain(uint64_t n, cudaStream_t st) {
         }
     }
     // tables are built once; later calls may come on other streams
-    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaFree(d.w_lo);
+        if (d.tw_all) cudaFree(d.tw_all);
+        return nullptr;
+    }
     auto res = domains_.emplace(n, d);
     return &res.first->second;
 }
@@ -349,8 +368,14 @@ const NttDomain* NttEngine::domain(uint64_t n, cudaStream_t st) {
 const NttCoset* NttEngine::coset(uint64_t n, const fe& g, bool with_ninv, const NttDomain* d, cudaStream_t st) {
     for (auto& c : cosets_)
         if (c.n == n && c.with_ninv == with_ninv && fe_eq(c.g, g)) return &c;
-    if (cosets_.size() >= 8) {  // tiny FIFO cache: the prover uses one shift (k[1]) and its inverse
-        cudaStreamSynchronize(st);
+    // FIFO cache: the prover uses one shift (k[1]) and its inverse per domain; the coset-by-coset quotient round six more.  At most
+    // 16 tables and 8 GiB are kept (a table is n field elements)
+    auto table_bytes = [](uint64_t m) { return sizeof(fe) * ((size_t)(1u << NTT_LOG_TWLO) + (m >> NTT_LOG_TWLO) + 1 + m); };
+    size_t held = 0;
+    for (auto& c : cosets_) held += table_bytes(c.n);
+    while (!cosets_.empty() && (cosets_.size() >= 16 || held + table_bytes(n) > ((size_t)8 << 30))) {
+        cudaDeviceSynchronize();   // users of the evicted table may be on any stream
+        held -= table_bytes(cosets_.front().n);
         cudaFree(cosets_.front().g_lo);
         cosets_.erase(cosets_.begin());
     }
@@ -367,13 +392,16 @@ const NttCoset* NttEngine::coset(uint64_t n, const fe& g, bool with_ninv, const 
     ntt_build_pow_tables<<<(tot + 127) / 128, 128, 0, st>>>(g, with_ninv ? d->n_inv : fe_one<FrP>(), c.g_lo, c.g_hi, c.n_hi);
     ntt_expand_pow_table<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.g_lo, c.g_hi, c.g_full, n);
     UZ_COUNT_LAUNCH(2);
-    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaFree(c.g_lo);
+        return nullptr;
+    }
     cosets_.push_back(c);
     return &cosets_.back();
 }
 
 template <int NT>
-static cudaError_t launch_pass(const NttKernelArgs& ka, cudaStream_t st) {
+static cudaError_t launch_pass(const NttKernelArgs& ka, uint32_t k, cudaStream_t st) {
     const NttPass& p = ka.p;
     const size_t T = (size_t)1 << (p.logR + p.logC);
     const size_t smem = T * 32;
@@ -386,7 +414,7 @@ static cudaError_t launch_pass(const NttKernelArgs& ka, cudaStream_t st) {
         configured[dev] = 200 * 1024;
     }
     const uint32_t grid = p.inner_tiles * p.outer * p.batch;
-    ntt_pass_kernel<NT><<<grid, NT, smem, st>>>(ka);
+    ntt_pass_kernel<NT><<<dim3(grid, k), NT, smem, st>>>(ka);
     UZ_COUNT_LAUNCH(1);
     return cudaGetLastError();
 }
@@ -395,9 +423,24 @@ static cudaError_t launch_pass(const NttKernelArgs& ka, cudaStream_t st) {
 // d_in == d_out is allowed.
 int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, uint64_t n, bool inverse,
                    const fe* coset_shift /* host, Montgomery, or null */, cudaStream_t st) {
+    return run_batch(&d_in, &d_out, d_scratch, &len_in, 1, n, inverse, coset_shift, st);
+}
+
+// k <= NTT_MAX_BATCH independent transforms over the same domain (and coset), one launch per pass; d_scratch: k * n elements.
+// The prover's rounds transform 5-8 polynomials of 2^13..2^14 coefficients at a time: one such vector is 16 tiles, i.e. a tenth of
+// the GPU's SMs, and its passes are launch-bound.
+int NttEngine::run_batch(const fe* const* d_in, fe* const* d_out, fe* d_scratch, const uint64_t* len_in, uint32_t k, uint64_t n, bool inverse,
+                         const fe* coset_shift, cudaStream_t st) {
+    if (k == 0) return UZKGE_OK;
+    if (k > NTT_MAX_BATCH) return UZKGE_ERR_SIZE;
     const NttDomain* d = domain(n, st);
     if (!d) return UZKGE_ERR_SIZE;
-    if (len_in > n) return UZKGE_ERR_SIZE;
+    bool any_pad = false;
+    for (uint32_t j = 0; j < k; j++) {
+        if (len_in[j] > n) return UZKGE_ERR_SIZE;
+        if (!d_in[j] || !d_out[j]) return UZKGE_ERR_ARG;
+        any_pad = any_pad || len_in[j] < n;
+    }
     const NttCoset* cs = nullptr;
     if (coset_shift) {
         cs = coset(n, *coset_shift, inverse, d, st);
@@ -405,14 +448,18 @@ int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, ui
     }
     const NttPlan& pl = d->plan;
     const int prof = g_prof.begin(Profiler::NTT, st);
-    const fe* src = d_in;
+    NttJobs cur;          // where each vector currently lives
+    memset(&cur, 0, sizeof cur);
+    for (uint32_t j = 0; j < k; j++) {
+        cur.in[j] = d_in[j];
+        cur.len_in[j] = len_in[j];
+    }
     bool input_consumed = false;
     if (pl.mixed) {
         Radix3Args ra;
-        ra.in = d_in;
-        ra.out = d_scratch;
+        ra.jobs = cur;
+        for (uint32_t j = 0; j < k; j++) ra.jobs.out[j] = d_scratch + (uint64_t)j * n;
         ra.m = pl.m;
-        ra.len_in = len_in;
         ra.w_lo = d->w_lo;
         ra.w_hi = d->w_hi;
         ra.g_full = cs ? cs->g_full : nullptr;
@@ -420,21 +467,20 @@ int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, ui
         ra.w3 = d->w3;
         ra.w3sq = d->w3sq;
         ra.pre_coset = (cs && !inverse) ? 1 : 0;
-        ntt_radix3_kernel<<<(unsigned)((pl.m + 255) / 256), 256, 0, st>>>(ra);
+        ntt_radix3_kernel<<<dim3((unsigned)((pl.m + 255) / 256), k), 256, 0, st>>>(ra);
         UZ_COUNT_LAUNCH(1);
         if (cudaGetLastError() != cudaSuccess) return UZKGE_ERR_CUDA;
         g_prof.mark(prof, NTT_PH_RADIX3, st);
-        src = d_scratch;
+        for (uint32_t j = 0; j < k; j++) cur.in[j] = ra.jobs.out[j];
         input_consumed = true;
     }
     for (uint32_t i = 0; i < pl.npass; i++) {
         NttKernelArgs ka;
         ka.p = pl.pass[i];
-        ka.in = src;
+        ka.jobs = cur;
         // non-last passes write into scratch (in place once the data lives there); the last pass writes d_out
-        ka.out = ka.p.last ? d_out : d_scratch;
+        for (uint32_t j = 0; j < k; j++) ka.jobs.out[j] = ka.p.last ? d_out[j] : d_scratch + (uint64_t)j * n;
         ka.n = n;
-        ka.len_in = len_in;
         ka.stage_tab = d->stage;
         ka.w_lo = d->w_lo;
         ka.w_hi = d->w_hi;
@@ -444,25 +490,27 @@ int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, ui
         ka.tw_pass = d->tw_pass[i];
         ka.scale = d->n_inv;
         ka.inverse = inverse ? 1 : 0;
-        ka.zero_pad = (!input_consumed && len_in < n) ? 1 : 0;
+        ka.zero_pad = (!input_consumed && any_pad) ? 1 : 0;
         ka.pre_coset = (!input_consumed && cs && !inverse) ? 1 : 0;
         ka.post_coset = (ka.p.last && cs && inverse) ? 1 : 0;
         ka.has_scale = (ka.p.last && inverse && !cs) ? 1 : 0;
         // a single-tile last pass may run in place; a multi-tile last pass transposes and must not alias
-        if (ka.p.last && ka.in == ka.out && (ka.p.inner_tiles * ka.p.outer * ka.p.batch) > 1) return UZKGE_ERR_INTERNAL;
+        if (ka.p.last && (ka.p.inner_tiles * ka.p.outer * ka.p.batch) > 1)
+            for (uint32_t j = 0; j < k; j++)
+                if (ka.jobs.in[j] == ka.jobs.out[j]) return UZKGE_ERR_INTERNAL;
         const uint32_t T = 1u << (ka.p.logR + ka.p.logC);
         cudaError_t e;
         if (T >= 4096 && cfg_big_threads_ == 1024)
-            e = launch_pass<1024>(ka, st);
+            e = launch_pass<1024>(ka, k, st);
         else if (T >= 2048)
-            e = launch_pass<512>(ka, st);
+            e = launch_pass<512>(ka, k, st);
         else if (T >= 512)
-            e = launch_pass<256>(ka, st);
+            e = launch_pass<256>(ka, k, st);
         else
-            e = launch_pass<64>(ka, st);
+            e = launch_pass<64>(ka, k, st);
         if (e != cudaSuccess) return UZKGE_ERR_CUDA;
         g_prof.mark(prof, NTT_PH_PASS0 + (int)i, st);
-        src = ka.out;
+        for (uint32_t j = 0; j < k; j++) cur.in[j] = ka.jobs.out[j];
         input_consumed = true;
     }
     return UZKGE_OK;

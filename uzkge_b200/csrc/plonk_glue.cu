@@ -74,6 +74,14 @@ __global__ void __launch_bounds__(256) fr_gather_kernel(const fe* __restrict__ s
     st_fe(out + i, ld_fe(src + idx[i]));
 }
 
+// dst[dst_idx[j]] = src[src_idx[j]]: the public-input rows of pi_poly's evaluation vector, straight from the witness (helpers.rs:111-131)
+__global__ void __launch_bounds__(256) fr_gather_scatter_kernel(const fe* __restrict__ src, const uint32_t* __restrict__ src_idx,
+                                                                fe* __restrict__ dst, const uint32_t* __restrict__ dst_idx, uint64_t k) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    st_fe(dst + dst_idx[j], ld_fe(src + src_idx[j]));
+}
+
 __global__ void __launch_bounds__(256) fr_mul_kernel(const fe* __restrict__ a, const fe* __restrict__ b, uint64_t n, fe* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -174,6 +182,14 @@ int fr_gather_run(const void* d_src, const void* d_idx, size_t n, void* d_out, c
     if (n == 0) return UZKGE_OK;
     if (!d_src || !d_idx || !d_out) return UZKGE_ERR_ARG;
     fr_gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const fe*)d_src, (const uint32_t*)d_idx, n, (fe*)d_out);
+    UZ_COUNT_LAUNCH(1);
+    return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
+}
+
+int fr_gather_scatter_run(const void* d_src, const void* d_src_idx, void* d_dst, const void* d_dst_idx, size_t k, cudaStream_t st) {
+    if (k == 0) return UZKGE_OK;
+    if (!d_src || !d_src_idx || !d_dst || !d_dst_idx) return UZKGE_ERR_ARG;
+    fr_gather_scatter_kernel<<<blocks_for(k, 256), 256, 0, st>>>((const fe*)d_src, (const uint32_t*)d_src_idx, (fe*)d_dst, (const uint32_t*)d_dst_idx, k);
     UZ_COUNT_LAUNCH(1);
     return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
 }

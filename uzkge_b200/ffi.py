@@ -99,6 +99,10 @@ _SIGNATURES = {
         C.c_int32,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p],
     ),
+    "uzkge_cuda_ntt_fr_batch_device": (
+        C.c_int32,
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_size_t), C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p],
+    ),
     "uzkge_cuda_ntt_cross_fr_device": (
         C.c_int32,
         [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p],
@@ -131,6 +135,7 @@ _SIGNATURES = {
     "uzkge_cuda_fr_add_sparse_device": (C.c_int32, [C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_fr_powers_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_fr_gather_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_fr_gather_scatter_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_fr_mul_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_fr_trimmed_len_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]),
     "uzkge_cuda_grand_product_fr_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -139,6 +144,12 @@ _SIGNATURES = {
         [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
          C.c_void_p, C.c_void_p],
     ),
+    # the compiled prover (csrc/prover.cu); native.py declares the structures behind the void pointers
+    "uzkge_cuda_plonk_params_upload": (C.c_int32, [C.c_void_p, u64p]),
+    "uzkge_cuda_plonk_params_set_public_key": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "uzkge_cuda_plonk_params_free": (C.c_int32, [C.c_uint64]),
+    "uzkge_cuda_srs_upload_lagrange_commit": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, u64p]),
+    "uzkge_cuda_plonk_prove": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "uzkge_cuda_g1_add": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_g1_to_affine": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "uzkge_cuda_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -404,6 +415,18 @@ def ntt_fr_device(d_in: int, d_out: int, d_scratch: int, len_in: int, domain_siz
                                        ptr(shift) if shift is not None else None, stream),
         FFTError,
     )
+
+
+def ntt_fr_batch_device(d_ins, d_outs, d_scratch: int, len_in, domain_size: int, inverse: bool = False, coset_shift=None,
+                        stream: int = 0) -> None:
+    """k transforms over one domain in one launch per pass; d_scratch holds k * domain_size elements."""
+    k = len(d_ins)
+    ins = (C.c_void_p * k)(*d_ins)
+    outs = (C.c_void_p * k)(*d_outs)
+    lens = (C.c_size_t * k)(*len_in)
+    shift = as_u64(coset_shift, 4) if coset_shift is not None else None
+    check(lib().uzkge_cuda_ntt_fr_batch_device(ins, outs, d_scratch, lens, k, domain_size, 1 if inverse else 0,
+                                               ptr(shift) if shift is not None else None, stream), FFTError)
 
 
 def ntt_cross_fr_device(d_in: int, d_out: int, log_ranks: int, cols: int, col_offset: int, n_total: int,
