@@ -252,6 +252,10 @@ UZKGE_API int32_t uzkge_cuda_fr_lincomb_device(const void* const* d_polys, const
  * hide_polynomial (plonk/helpers.rs:139-154) and split_t_and_commit (helpers.rs:1351-1361). */
 #define UZKGE_SPARSE_MAX 16
 UZKGE_API int32_t uzkge_cuda_fr_add_sparse_device(void* d_poly, const size_t* idx, const uint64_t* vals_host, size_t k, void* stream);
+/* polys[j][idx[j]] += vals[j], j < k <= UZKGE_SPARSE_MULTI_MAX, over SEVERAL polynomials in one launch; the k entries must address distinct
+ * elements (they are applied in parallel): the blinds of all the polynomials of a prover round (helpers.rs:139-154). */
+#define UZKGE_SPARSE_MULTI_MAX 64
+UZKGE_API int32_t uzkge_cuda_fr_add_sparse_multi_device(void* const* d_polys, const size_t* idx, const uint64_t* vals_host, size_t k, void* stream);
 /* out[i] = scale * base^i, i < n (scale NULL = 1): `domain.elements()` and the coset k[1] * w_m^i (plonk/indexer.rs:276-282). */
 UZKGE_API int32_t uzkge_cuda_fr_powers_device(const uint64_t base_host[4], const uint64_t* scale_host, size_t n, void* d_out, void* stream);
 /* out[i] = src[idx[i]], idx: n uint32 on the device: ConstraintSystem::extend_witness (plonk/constraint_system/mod.rs:103-111). */

@@ -45,9 +45,18 @@ if apk is not None:
 wit = plonk.DevVec.from_numpy(cs.get_witness_array(), dev)
 
 
+native = None
+if os.environ.get("PROVER", "native") == "native":       # the compiled prover (uzkge_cuda_plonk_prove); PROVER=mirror: the Python mirror
+    from uzkge_b200.native import NativeProver
+
+    native = NativeProver(cs, params, pcs, lagrange, True)
+
+
 def prove():
     tr = Transcript(label)
     tr.append_u64(count)
+    if native is not None:
+        return native.prove(ChaChaRng.from_seed(bytes(32)), tr, wit)
     return plonk.prover(ChaChaRng.from_seed(bytes(32)), tr, pcs, cs, params, wit, lagrange_pcs=lagrange, lagrange_all=True)
 
 

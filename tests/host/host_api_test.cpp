@@ -280,9 +280,130 @@ static int run_serial(int argc, char** argv) {
     return failures;
 }
 
+// ---- a compiled host calling the prover behind the C ABI (what the patched Rust body of prover_with_lagrange does): the job file
+// (written by tests/test_gpu_zz_host_cpp.py from the zshuffle circuit) holds tagged records  u64 tag | u64 bytes | payload.
+// Prints the proof in PlonkProof::to_bytes_be order (plonk/indexer.rs:538-590) as hex; the Python test compares it with plonk.py's.
+namespace job {
+enum Tag : uint64_t { SIZES = 1, WIRING, PERM, K, Q, S, QB, PRK, ANEMOI, PUB_ROWS, PUB_WIT, Q_ECC, GEN, PK, EDWARDS, WITNESS, W_SEL, BLINDS, TRANSCRIPT,
+                      SRS, LAGRANGE, FLAGS };
+struct Rec {
+    uint64_t tag;
+    std::vector<uint8_t> data;
+};
+static std::vector<Rec> load(const char* path) {
+    std::vector<Rec> out;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return out;
+    uint64_t hdr[2];
+    while (std::fread(hdr, 8, 2, f) == 2) {
+        Rec r{hdr[0], std::vector<uint8_t>(hdr[1])};
+        if (hdr[1] && std::fread(r.data.data(), 1, hdr[1], f) != hdr[1]) break;
+        out.push_back(std::move(r));
+    }
+    std::fclose(f);
+    return out;
+}
+}  // namespace job
+
+static void put_point(std::string& hex, const uint64_t aff[8]) {
+    static const char* d = "0123456789abcdef";
+    for (int c = 0; c < 2; c++) {
+        const auto b = to_bytes_be(FQ.from_mont({aff[4 * c], aff[4 * c + 1], aff[4 * c + 2], aff[4 * c + 3]}));
+        for (uint8_t v : b) {
+            hex.push_back(d[v >> 4]);
+            hex.push_back(d[v & 15]);
+        }
+    }
+}
+static void put_scalar(std::string& hex, const uint64_t m[4]) {
+    static const char* d = "0123456789abcdef";
+    const auto b = to_bytes_be(FR.from_mont({m[0], m[1], m[2], m[3]}));
+    for (uint8_t v : b) {
+        hex.push_back(d[v >> 4]);
+        hex.push_back(d[v & 15]);
+    }
+}
+
+static int run_prove(const char* path) {
+    const auto recs = job::load(path);
+    if (recs.empty()) {
+        std::printf("FAIL: cannot read %s\n", path);
+        return 1;
+    }
+    uzkge_plonk_params_desc d;
+    std::memset(&d, 0, sizeof d);
+    uzkge_plonk_prove_args a;
+    std::memset(&a, 0, sizeof a);
+    const uint64_t *srs = nullptr, *lag = nullptr;
+    size_t srs_n = 0, lag_n = 0, nq = 0, ns = 0, nprk = 0, ngen = 0, npk = 0, nsel = 0;
+    for (const auto& r : recs) {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(r.data.data());
+        const size_t elems = r.data.size() / 32;
+        switch (r.tag) {
+            case job::SIZES: d.n = w[0]; d.m = w[1]; d.num_vars = w[2]; d.shuffle = (int32_t)w[3]; break;
+            case job::WIRING: d.wiring = reinterpret_cast<const uint32_t*>(w); break;
+            case job::PERM: d.permutation = w; break;
+            case job::K: std::memcpy(d.k, w, sizeof d.k); break;
+            case job::Q: d.q_polys[nq] = elems ? w : nullptr; d.q_len[nq++] = elems; break;
+            case job::S: d.s_polys[ns] = elems ? w : nullptr; d.s_len[ns++] = elems; break;
+            case job::QB: d.qb_poly = elems ? w : nullptr; d.qb_len = elems; break;
+            case job::PRK: d.q_prk_polys[nprk] = elems ? w : nullptr; d.q_prk_len[nprk++] = elems; break;
+            case job::ANEMOI: std::memcpy(d.anemoi_generator, w, 32); std::memcpy(d.anemoi_generator_inv, w + 4, 32); break;
+            case job::PUB_ROWS: d.public_vars_constraint_indices = w; d.n_public = r.data.size() / 8; break;
+            case job::PUB_WIT: d.public_vars_witness_indices = w; break;
+            case job::Q_ECC: d.q_ecc_poly = elems ? w : nullptr; d.q_ecc_len = elems; break;
+            case job::GEN: d.q_shuffle_generator_polys[ngen] = elems ? w : nullptr; d.gen_len[ngen++] = elems; break;
+            case job::PK: d.q_shuffle_public_key_polys[npk] = elems ? w : nullptr; d.pk_len[npk++] = elems; break;
+            case job::EDWARDS: std::memcpy(d.edwards_a, w, 32); break;
+            case job::WITNESS: a.witness = w; break;
+            case job::W_SEL: a.w_sel_evals[nsel++] = w; break;
+            case job::BLINDS: a.blinds = w; a.n_blinds = elems; break;
+            case job::TRANSCRIPT: a.transcript = r.data.data(); a.transcript_len = r.data.size(); break;
+            case job::SRS: srs = w; srs_n = r.data.size() / 64; break;
+            case job::LAGRANGE: lag = w; lag_n = r.data.size() / 64; break;
+            case job::FLAGS: a.lagrange_all = (int32_t)w[0]; break;
+            default: break;
+        }
+    }
+    auto ok = [](int32_t rc, const char* what) {
+        if (rc != UZKGE_OK) std::printf("FAIL %s: %d %s\n", what, rc, uzkge_cuda_last_error());
+        return rc == UZKGE_OK;
+    };
+    if (!ok(uzkge_cuda_init(0), "init")) return 1;
+    if (!ok(uzkge_cuda_srs_upload(srs, srs_n, 0, &a.srs), "srs_upload")) return 1;
+    if (lag && !ok(uzkge_cuda_srs_upload_lagrange_commit(lag, lag_n, srs, srs_n, 0, &a.lagrange_srs), "srs_upload_lagrange_commit")) return 1;
+    if (!ok(uzkge_cuda_plonk_params_upload(&d, &a.params), "plonk_params_upload")) return 1;
+    uzkge_plonk_proof pr;
+    if (!ok(uzkge_cuda_plonk_prove(&a, &pr), "plonk_prove")) return 1;
+    std::string hex;
+    for (int i = 0; i < 5; i++) put_point(hex, pr.cm_w[i]);
+    if (d.shuffle)
+        for (int i = 0; i < 3; i++) put_point(hex, pr.cm_w_sel[i]);
+    for (int i = 0; i < 5; i++) put_point(hex, pr.cm_t[i]);
+    put_point(hex, pr.cm_z);
+    put_scalar(hex, pr.prk_3_poly_eval_zeta);
+    put_scalar(hex, pr.prk_4_poly_eval_zeta);
+    for (int i = 0; i < 5; i++) put_scalar(hex, pr.w_polys_eval_zeta[i]);
+    for (int i = 0; i < 3; i++) put_scalar(hex, pr.w_polys_eval_zeta_omega[i]);
+    put_scalar(hex, pr.z_eval_zeta_omega);
+    for (int i = 0; i < 4; i++) put_scalar(hex, pr.s_polys_eval_zeta[i]);
+    if (d.shuffle) {
+        put_scalar(hex, pr.q_ecc_poly_eval_zeta);
+        for (int i = 0; i < 3; i++) put_scalar(hex, pr.w_sel_polys_eval_zeta[i]);
+    }
+    put_point(hex, pr.opening_witness_zeta);
+    put_point(hex, pr.opening_witness_zeta_omega);
+    std::printf("proof %s\nmsm %u launches %u\nPASS prove\n", hex.c_str(), pr.msm, pr.launches);
+    uzkge_cuda_plonk_params_free(a.params);
+    uzkge_cuda_srs_free(a.srs);
+    if (a.lagrange_srs) uzkge_cuda_srs_free(a.lagrange_srs);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     const std::string mode = argc > 1 ? argv[1] : "gpu";
     oracle_init();
+    if (mode == "prove") return run_prove(argc > 2 ? argv[2] : "");
     if (mode == "serial") {
         const int f = run_serial(argc, argv);
         std::printf(f ? "FAILED (%d)\n" : "PASS serial\n", f);

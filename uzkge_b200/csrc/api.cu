@@ -737,6 +737,14 @@ UZKGE_API int32_t uzkge_cuda_fr_add_sparse_device(void* d_poly, const size_t* id
     return engine_fail(rc, "fr_add_sparse_device");
 }
 
+UZKGE_API int32_t uzkge_cuda_fr_add_sparse_multi_device(void* const* d_polys, const size_t* idx, const uint64_t* vals_host, size_t k, void* stream) {
+    API_ENTER(-1);
+    int rc = fr_add_sparse_multi_run(d_polys, idx, vals_host, k, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_add_sparse_multi_device: null pointer");
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "fr_add_sparse_multi_device: k <= UZKGE_SPARSE_MULTI_MAX");
+    return engine_fail(rc, "fr_add_sparse_multi_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_fr_powers_device(const uint64_t base_host[4], const uint64_t* scale_host, size_t n, void* d_out, void* stream) {
     API_ENTER(-1);
     int rc = fr_powers_run(base_host, scale_host, n, d_out, (cudaStream_t)stream);

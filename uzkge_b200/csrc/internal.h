@@ -260,6 +260,7 @@ int plonk_quotient_run(const uzkge_quotient_args* args, const uzkge_quotient_shu
 // ---------------------------------------------------------------- elementwise prover glue (plonk_glue.cu)
 int fr_lincomb_run(const void* const* d_polys, const size_t* lens, const uint64_t* coefs, size_t k, void* d_out, size_t out_len, cudaStream_t st);
 int fr_add_sparse_run(void* d_poly, const size_t* idx, const uint64_t* vals, size_t k, cudaStream_t st);
+int fr_add_sparse_multi_run(void* const* d_polys, const size_t* idx, const uint64_t* vals, size_t k, cudaStream_t st);
 int fr_powers_run(const uint64_t* base, const uint64_t* scale, size_t n, void* d_out, cudaStream_t st);
 int fr_gather_run(const void* d_src, const void* d_idx, size_t n, void* d_out, cudaStream_t st);
 int fr_gather_scatter_run(const void* d_src, const void* d_src_idx, void* d_dst, const void* d_dst_idx, size_t k, cudaStream_t st);

@@ -28,7 +28,7 @@
 namespace uz {
 
 static constexpr int ACC_NT = 256;            // threads per CTA of the accumulate kernel
-static constexpr uint32_t LARGE_SLICE = 1024; // entries per warp slice of an oversized bucket
+static constexpr uint32_t LARGE_SLICE_MIN = 128, LARGE_SLICE_MAX = 1024;  // entries per warp slice of an oversized bucket (chosen per run)
 static constexpr int LARGE_NT = 256;
 
 // ------------------------------------------------------------------ digits + counting sort by bucket
@@ -191,6 +191,7 @@ struct LargeArgs {
     xyzz* slice_sums;       // one per slice
     uint32_t large_cap;
     uint32_t max_slices;
+    uint32_t slice;         // entries per slice: a lane adds slice / 32 points in a dependent chain
 };
 
 __global__ void __launch_bounds__(1024) msm_large_plan_kernel(const LargeArgs a) {
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(1024) msm_large_plan_kernel(const LargeArgs a)
         uint32_t cnt = 0;
         if (k < nl) {
             const uint32_t b = a.large_list[1 + k];
-            cnt = (a.offsets[b + 1] - a.offsets[b] + LARGE_SLICE - 1) / LARGE_SLICE;
+            cnt = (a.offsets[b + 1] - a.offsets[b] + a.slice - 1) / a.slice;
         }
         uint32_t x = cnt;  // inclusive warp scan
 #pragma unroll
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(1024) msm_large_plan_kernel(const LargeArgs a)
     if (threadIdx.x == 0) a.slice_start[nl] = carry_s;
 }
 
-// one WARP per slice of LARGE_SLICE entries: lanes stride over the slice, then a shuffle tree.  The grid is a fixed
+// one WARP per slice of a.slice entries: lanes stride over the slice, then a shuffle tree.  The grid is a fixed
 // number of CTAs; warps walk the slice list (its length is only known on the device).
 __global__ void __launch_bounds__(LARGE_NT, 2) msm_large_accumulate_kernel(const LargeArgs a) {
     extern __shared__ uint4 acc_smem[];
@@ -242,8 +243,8 @@ __global__ void __launch_bounds__(LARGE_NT, 2) msm_large_accumulate_kernel(const
             if (a.slice_start[mid] <= s) lo = mid; else hi = mid;
         }
         const uint32_t b = a.large_list[1 + lo];
-        const uint32_t first = a.offsets[b] + (s - a.slice_start[lo]) * LARGE_SLICE;
-        const uint32_t end = min(first + LARGE_SLICE, a.offsets[b + 1]);
+        const uint32_t first = a.offsets[b] + (s - a.slice_start[lo]) * a.slice;
+        const uint32_t end = min(first + a.slice, a.offsets[b + 1]);
         xyzz acc = xyzz_identity();
         accumulate_segment<LARGE_NT>(acc, a.tables, a.vals, first + lane, end, 32, acc_smem);
 #pragma unroll 1
@@ -486,7 +487,7 @@ int MsmEngine::upload(const uint64_t* affine_xy_host, size_t n, uint32_t window_
     if (m_all >= (1ull << 31)) return UZKGE_ERR_SIZE;
     // segments longer than max(8 * mean, 64 * lanes) are "large": at most nb_all / 8 of them can exist
     s->large_cap = (uint32_t)(nb_all / 8 + 2);
-    s->max_slices = (uint32_t)(m_all / LARGE_SLICE + s->large_cap);
+    s->max_slices = (uint32_t)(m_all / LARGE_SLICE_MIN + s->large_cap);
 
     size_t total = 0;
     auto take = [&](size_t bytes) {
@@ -628,6 +629,7 @@ struct MsmEngine::GroupPlan {
     uint64_t m = 0;        // sorted entries of the group
     double mean = 0;       // mean bucket load
     const uint32_t* order = nullptr;
+    uint32_t n_max = 0;    // points of the largest MSM of the group
     bool empty = false;
 };
 
@@ -644,6 +646,7 @@ int MsmEngine::stage_sort(MsmSrs* s, MsmWork& w, size_t base_offset, const fe* c
         if (n[j] > n_max) n_max = (uint32_t)n[j];
     }
     plan->k = k;
+    plan->n_max = n_max;
     plan->empty = n_all == 0;
     if (plan->empty) return UZKGE_OK;
     da.c = s->c;
@@ -768,6 +771,12 @@ int MsmEngine::stage_accumulate(MsmSrs* s, MsmWork& w, const GroupPlan& plan, cu
     la.slice_sums = w.slice_sums;
     la.large_cap = s->large_cap;
     la.max_slices = s->max_slices;
+    // slice length: a bucket holds at most one entry per point, so n_max / 1024 keeps the slices of the largest possible bucket
+    // (summed by ONE warp in msm_large_finish_kernel) around a thousand, while small problems -- a prover round's batch of 2^14-point
+    // commitments over bit / small-integer witnesses -- get short dependent chains (4 points per lane instead of 32: measured
+    // 286 -> us on zshuffle-52's round 1)
+    la.slice = LARGE_SLICE_MIN;
+    while (la.slice < LARGE_SLICE_MAX && la.slice < plan.n_max / 1024) la.slice <<= 1;
     // the list lengths are only known on the device: fixed grids whose warps walk the lists
     msm_large_plan_kernel<<<1, 1024, 0, st>>>(la);
     msm_large_accumulate_kernel<<<sm_count_ * 4, LARGE_NT, 2 * 4 * LARGE_NT * sizeof(uint4), st>>>(la);

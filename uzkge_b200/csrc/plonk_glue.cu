@@ -74,6 +74,21 @@ __global__ void __launch_bounds__(256) fr_gather_kernel(const fe* __restrict__ s
     st_fe(out + i, ld_fe(src + idx[i]));
 }
 
+// polys[j][idx[j]] += v[j] for k <= UZKGE_SPARSE_MULTI_MAX entries addressing DISTINCT elements (one thread each): the blinds of all the
+// polynomials of a prover round in one launch
+struct SparseMultiArgs {
+    fe* p[UZKGE_SPARSE_MULTI_MAX];
+    uint64_t idx[UZKGE_SPARSE_MULTI_MAX];
+    fe v[UZKGE_SPARSE_MULTI_MAX];
+    uint32_t k;
+};
+__global__ void __launch_bounds__(64) fr_add_sparse_multi_kernel(const __grid_constant__ SparseMultiArgs a) {
+    const uint32_t j = threadIdx.x;
+    if (j >= a.k) return;
+    fe* q = a.p[j] + a.idx[j];
+    st_fe(q, fe_add<FrP>(ld_fe(q), a.v[j]));
+}
+
 // dst[dst_idx[j]] = src[src_idx[j]]: the public-input rows of pi_poly's evaluation vector, straight from the witness (helpers.rs:111-131)
 __global__ void __launch_bounds__(256) fr_gather_scatter_kernel(const fe* __restrict__ src, const uint32_t* __restrict__ src_idx,
                                                                 fe* __restrict__ dst, const uint32_t* __restrict__ dst_idx, uint64_t k) {
@@ -157,6 +172,24 @@ int fr_add_sparse_run(void* d_poly, const size_t* idx, const uint64_t* vals, siz
     }
     a.k = (uint32_t)k;
     fr_add_sparse_kernel<<<1, 32, 0, st>>>((fe*)d_poly, a);
+    UZ_COUNT_LAUNCH(1);
+    return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
+}
+
+int fr_add_sparse_multi_run(void* const* d_polys, const size_t* idx, const uint64_t* vals, size_t k, cudaStream_t st) {
+    if (k == 0) return UZKGE_OK;
+    if (k > UZKGE_SPARSE_MULTI_MAX) return UZKGE_ERR_SIZE;
+    if (!d_polys || !idx || !vals) return UZKGE_ERR_ARG;
+    SparseMultiArgs a;
+    memset(&a, 0, sizeof(a));
+    for (size_t j = 0; j < k; j++) {
+        if (!d_polys[j]) return UZKGE_ERR_ARG;
+        a.p[j] = (fe*)d_polys[j];
+        a.idx[j] = idx[j];
+        memcpy(&a.v[j], vals + 4 * j, sizeof(fe));
+    }
+    a.k = (uint32_t)k;
+    fr_add_sparse_multi_kernel<<<1, 64, 0, st>>>(a);
     UZ_COUNT_LAUNCH(1);
     return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
 }

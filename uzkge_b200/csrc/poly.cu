@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(PT) horner_tile_agg_kernel(const fe* __restric
 __global__ void __launch_bounds__(1024) horner_carry_kernel(const fe* __restrict__ agg, uint32_t nt, const Pow2Table zt, fe* __restrict__ carry,
                                                             fe* __restrict__ total) {
     __shared__ fe sh[1024];
-    const uint32_t per = (nt + 1023) / 1024;  // tiles per thread
+    const uint32_t NTH = blockDim.x;          // a power of two <= 1024, sized to the tile count by the host (a 1024-thread scan
+                                              // over 16 tiles spends 10 rounds of 32 warps on one SM: 44 us at n = 2^14)
+    const uint32_t per = (nt + NTH - 1) / NTH;  // tiles per thread
     const uint32_t lo = threadIdx.x * per, hi = min(lo + per, nt);
     const fe zt_tile = zt.p[LOG_TILE];
     // thread aggregate over its tiles: A = sum_{b in [lo, hi)} agg[b] z^(TILE (b - lo))
@@ -72,9 +74,9 @@ __global__ void __launch_bounds__(1024) horner_carry_kernel(const fe* __restrict
     const fe zper = z_pow(zt, (uint64_t)per << LOG_TILE);  // z^(TILE * per)
     fe zs = zper;
     fe mine = a;
-    for (uint32_t stride = 1; stride < 1024; stride <<= 1) {
+    for (uint32_t stride = 1; stride < NTH; stride <<= 1) {
         fe other = fe_zero();
-        const bool has = threadIdx.x + stride < 1024;
+        const bool has = threadIdx.x + stride < NTH;
         if (has) other = sh[threadIdx.x + stride];
         __syncthreads();
         if (has) mine = fe_add<FrP>(mine, fe_mul<FrP>(other, zs));
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(1024) horner_carry_kernel(const fe* __restrict
         zs = fe_sqr<FrP>(zs);
     }
     // carry entering thread t's range from above = inclusive suffix of thread t + 1
-    fe cin = threadIdx.x + 1 < 1024 ? sh[threadIdx.x + 1] : fe_zero();
+    fe cin = threadIdx.x + 1 < NTH ? sh[threadIdx.x + 1] : fe_zero();
     // walk down the thread's tiles
     for (uint32_t b = hi; b > lo; b--) {
         st_fe(carry + b - 1, cin);
@@ -225,14 +227,15 @@ __global__ void __launch_bounds__(PT) prod_tile_agg_kernel(const fe* __restrict_
 // exclusive scan of the tile aggregates (one CTA): carry[b] = prod_{b' < b} agg[b'];  total = prod of all
 __global__ void __launch_bounds__(1024) prod_carry_kernel(const fe* __restrict__ agg, uint32_t nt, fe* __restrict__ carry, fe* __restrict__ total) {
     __shared__ fe sh[1024];
-    const uint32_t per = (nt + 1023) / 1024;
+    const uint32_t NTH = blockDim.x;   // a power of two <= 1024 (see horner_carry_kernel)
+    const uint32_t per = (nt + NTH - 1) / NTH;
     const uint32_t lo = threadIdx.x * per, hi = min(lo + per, nt);
     fe p = fe_one<FrP>();
     for (uint32_t b = lo; b < hi; b++) p = fe_mul<FrP>(p, ld_fe(agg + b));
     sh[threadIdx.x] = p;
     __syncthreads();
     fe mine = p;
-    for (uint32_t stride = 1; stride < 1024; stride <<= 1) {
+    for (uint32_t stride = 1; stride < NTH; stride <<= 1) {
         fe other = fe_one<FrP>();
         const bool has = threadIdx.x >= stride;
         if (has) other = sh[threadIdx.x - stride];
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(1024) prod_carry_kernel(const fe* __restrict__
         st_fe(carry + b, cin);
         cin = fe_mul<FrP>(cin, ld_fe(agg + b));
     }
-    if (threadIdx.x == 1023) st_fe(total, sh[1023]);
+    if (threadIdx.x == NTH - 1) st_fe(total, sh[NTH - 1]);
 }
 
 template <bool REVERSE>
@@ -294,6 +297,13 @@ __global__ void __launch_bounds__(256) grand_product_combine_kernel(const fe* __
 }
 
 // ------------------------------------------------------------------ host side
+// threads of the one-CTA carry scans: the tile count rounded up to a power of two, between one warp and 1024
+static unsigned carry_threads(uint32_t nt) {
+    unsigned t = 32;
+    while (t < nt && t < 1024) t <<= 1;
+    return t;
+}
+
 static Pow2Table make_pow2(const fe& z) {
     Pow2Table t;
     fe p = z;
@@ -327,7 +337,7 @@ int PolyEngine::horner(const fe* d_c, uint64_t n, const fe& z, fe* d_quot, fe* d
     fe* carry = agg + nt;
     const Pow2Table zt = make_pow2(z);
     horner_tile_agg_kernel<<<nt, PT, 0, st>>>(d_c, n, zt, agg);
-    horner_carry_kernel<<<1, 1024, 0, st>>>(agg, nt, zt, carry, d_value);
+    horner_carry_kernel<<<1, carry_threads(nt), 0, st>>>(agg, nt, zt, carry, d_value);
     if (d_quot && n > 1) horner_apply_kernel<<<nt, PT, 0, st>>>(d_c, n, zt, carry, d_quot);
     UZ_COUNT_LAUNCH(d_quot && n > 1 ? 3 : 2);
     return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
@@ -368,7 +378,7 @@ static int product_scan(void** ws, size_t* cap, const fe* d_a, uint64_t n, fe* d
     fe* agg = (fe*)*ws;
     fe* carry = agg + nt;
     prod_tile_agg_kernel<REVERSE><<<nt, PT, 0, st>>>(d_a, n, agg);
-    prod_carry_kernel<<<1, 1024, 0, st>>>(agg, nt, carry, d_total);
+    prod_carry_kernel<<<1, carry_threads(nt), 0, st>>>(agg, nt, carry, d_total);
     prod_apply_kernel<REVERSE><<<nt, PT, 0, st>>>(d_a, n, carry, d_out);
     UZ_COUNT_LAUNCH(3);
     return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;

@@ -435,36 +435,49 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
     cudaStream_t st = P.st;
 
     // ---- helpers over this proof's buffers
-    // hide_polynomial (helpers.rs:139-154): f += (b_0 + b_1 X + ...) (X^zeroing_degree - 1); returns the blinds
-    auto hide = [&](Poly& f, size_t hiding, std::vector<Limbs>* out) -> int {
-        size_t idx[2 * N_BLIND_SLOTS];
-        u64 vals[2 * N_BLIND_SLOTS * 4];
-        for (size_t i = 0; i < hiding; i++) {
-            const Limbs b = next_blind(), nb = FR.neg(b);
-            out->push_back(b);
-            idx[2 * i] = i;
-            idx[2 * i + 1] = n + i;
-            memcpy(vals + 8 * i, b.data(), 32);
-            memcpy(vals + 8 * i + 4, nb.data(), 32);
+    // sparse updates of a round (blinds) are collected and applied in one launch
+    struct Sparse {
+        std::vector<void*> p;
+        std::vector<size_t> idx;
+        std::vector<u64> vals;
+        void add(u64* poly, size_t i, const Limbs& v) {
+            p.push_back(poly);
+            idx.push_back(i);
+            vals.insert(vals.end(), v.begin(), v.end());
         }
-        TRY(uzkge_cuda_fr_add_sparse_device(f.p, idx, vals, 2 * hiding, st));
+    } sparse;
+    auto flush_sparse = [&]() -> int {
+        for (size_t j0 = 0; j0 < sparse.p.size(); j0 += UZKGE_SPARSE_MULTI_MAX) {
+            const size_t kk = sparse.p.size() - j0 < UZKGE_SPARSE_MULTI_MAX ? sparse.p.size() - j0 : UZKGE_SPARSE_MULTI_MAX;
+            TRY(uzkge_cuda_fr_add_sparse_multi_device(sparse.p.data() + j0, sparse.idx.data() + j0, sparse.vals.data() + 4 * j0, kk, st));
+        }
+        sparse = Sparse();
+        return UZKGE_OK;
+    };
+    // hide_polynomial (helpers.rs:139-154): f += (b_0 + b_1 X + ...) (X^zeroing_degree - 1); returns the blinds (queued: flush_sparse)
+    auto hide = [&](Poly& f, size_t hiding, std::vector<Limbs>* out) -> int {
+        for (size_t i = 0; i < hiding; i++) {
+            const Limbs b = next_blind();
+            out->push_back(b);
+            sparse.add(f.p, i, b);
+            sparse.add(f.p, n + i, FR.neg(b));
+        }
         if (f.len < n + hiding) f.len = n + hiding;
         return UZKGE_OK;
     };
-    // slots [first, first + 6) <- [b_0 b_1 b_2 | -b_0 -b_1 -b_2] (missing blinds are zero): the blind terms of a Lagrange commitment
+    // slots [first, first + 6) <- [b_0 b_1 b_2 | -b_0 -b_1 -b_2] (missing blinds are zero): the blind terms of a Lagrange commitment.
+    // The caller zeroes the slots first; the values travel as kernel arguments (a copy from pageable memory would synchronise)
     auto set_blind_slots = [&](u64* buf, size_t first, const std::vector<Limbs>& blinds) -> int {
-        // values travel as kernel arguments (a copy from pageable host memory would synchronise the stream)
-        size_t idx[2 * N_BLIND_SLOTS];
-        u64 rows[2 * N_BLIND_SLOTS * 4];
         for (size_t i = 0; i < blinds.size(); i++) {
-            const Limbs nb = FR.neg(blinds[i]);
-            idx[2 * i] = first + i;
-            idx[2 * i + 1] = first + N_BLIND_SLOTS + i;
-            memcpy(rows + 8 * i, blinds[i].data(), 32);
-            memcpy(rows + 8 * i + 4, nb.data(), 32);
+            sparse.add(buf, first + i, blinds[i]);
+            sparse.add(buf, first + N_BLIND_SLOTS + i, FR.neg(blinds[i]));
         }
-        CU(cudaMemsetAsync(buf + 4 * first, 0, 2 * N_BLIND_SLOTS * 32, st));
-        return uzkge_cuda_fr_add_sparse_device(buf, idx, rows, 2 * blinds.size(), st);
+        return UZKGE_OK;
+    };
+    // zero the 8-element tails that follow the n values of `count` consecutive stride-spaced vectors
+    auto zero_tails = [&](u64* base, size_t count) -> int {
+        CU(cudaMemset2DAsync(base + 4 * n, stride * 32, 0, TAIL * 32, count, st));
+        return UZKGE_OK;
     };
     // commit k vectors over one SRS; `overlap` (device work that does not depend on them) is enqueued behind the MSMs, the results are
     // read back on the side stream so that the host can hash while the GPU keeps working.  out_aff: k x 8 words (affine, Montgomery)
@@ -579,6 +592,7 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
         for (size_t i = 0; i < N_WIRES; i++) TRY(hide(w_polys[i], HIDING[i], &w_blinds[i]));     // the RNG order: wires, then selectors
         if (shuffle)
             for (size_t i = 0; i < 3; i++) TRY(hide(w_sel_polys[i], 2, &w_sel_blinds[i]));
+        TRY(flush_sparse());
     }
     // the quotient round's coset evaluations of these polynomials depend on no challenge: they run behind the MSMs
     auto wire_cosets = [&]() -> int {
@@ -604,6 +618,7 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
         u64 wire_scheme = a->srs, sel_scheme = a->srs;
         size_t wire_n = srs_n, sel_n = srs_n;
         if (lagrange) {
+            TRY(zero_tails(P.ext, N_WIRES));
             for (size_t i = 0; i < N_WIRES; i++) {
                 TRY(set_blind_slots(P.ext, i * stride + n, w_blinds[i]));
                 wires.push_back({P.ext + 4 * i * stride, n + 2 * N_BLIND_SLOTS});
@@ -615,6 +630,7 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
         }
         if (shuffle) {
             if (lagrange_all) {
+                TRY(zero_tails(P.sel_ev, 3));
                 for (size_t i = 0; i < 3; i++) {
                     TRY(set_blind_slots(P.sel_ev, i * stride + n, w_sel_blinds[i]));
                     sels.push_back({P.sel_ev + 4 * i * stride, n + 2 * N_BLIND_SLOTS});
@@ -625,6 +641,7 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
                 for (size_t i = 0; i < 3; i++) sels.push_back({w_sel_polys[i].p, w_sel_polys[i].len});
             }
         }
+        TRY(flush_sparse());
         u64 aff[8 * 8];
         if (shuffle && sel_scheme == wire_scheme) {
             std::vector<Msm> all = wires;
@@ -658,13 +675,17 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
         TRY(ifft(P, P.z_ev, z_poly.p, n));
         proof->ifft_n++;
         TRY(hide(z_poly, 3, &z_blinds));
+        if (lagrange) {
+            TRY(zero_tails(P.z_ev, 1));
+            TRY(set_blind_slots(P.z_ev, n, z_blinds));
+        }
+        TRY(flush_sparse());
         auto z_coset = [&]() -> int {
             proof->coset_fft_m++;
             return coset_fft(P, z_poly, P.coset[6]);
         };
         u64 aff[8];
         if (lagrange) {
-            TRY(set_blind_slots(P.z_ev, n, z_blinds));
             TRY(commit(a->lagrange_srs, lag_n, {{P.z_ev, n + 2 * N_BLIND_SLOTS}}, aff, z_coset));
         } else {
             TRY(commit(a->srs, srs_n, {{z_poly.p, z_poly.len}}, aff, z_coset));
@@ -742,19 +763,16 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
             const Limbs neg_prev = FR.neg(prev);
             if (i != N_WIRES - 1) {
                 // coefs.resize(n + 3); coefs[n + 2] += rand; coefs[0] -= prev   (helpers.rs:1351-1354)
-                const size_t idx[2] = {piece, 0};
-                u64 vals[8];
-                memcpy(vals, rand.data(), 32);
-                memcpy(vals + 4, neg_prev.data(), 32);
-                TRY(uzkge_cuda_fr_add_sparse_device(t_polys[i].p, idx, vals, 2, st));
+                sparse.add(t_polys[i].p, piece, rand);
+                sparse.add(t_polys[i].p, 0, neg_prev);
                 t_polys[i].len = piece + 1;
             } else {
-                const size_t idx[1] = {0};
-                TRY(uzkge_cuda_fr_add_sparse_device(t_polys[i].p, idx, neg_prev.data(), 1, st));
+                sparse.add(t_polys[i].p, 0, neg_prev);
                 if (t_polys[i].len < 1) t_polys[i].len = 1;
             }
             prev = rand;
         }
+        TRY(flush_sparse());
         u64 aff[5 * 8];
         if (lagrange_all) {
             TRY(commit_coefs_lagrange(std::vector<Poly>(t_polys, t_polys + 5), aff));

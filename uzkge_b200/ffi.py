@@ -133,6 +133,7 @@ _SIGNATURES = {
         [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p],
     ),
     "uzkge_cuda_fr_add_sparse_device": (C.c_int32, [C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uzkge_cuda_fr_add_sparse_multi_device": (C.c_int32, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_fr_powers_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_fr_gather_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_fr_gather_scatter_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
