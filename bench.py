@@ -919,7 +919,11 @@ def main() -> int:
         top = max(("pass0", "pass1", "pass2"), key=lambda k: r["phases_ms"][k])
         top_ms = r["phases_ms"][top]
         traffic, traffic_src = ncu_traffic("ntt", "ntt_pass_kernel")
-        fr_mul = r["n"] / 2 * lg + r["n"] * (passes - 1)
+        # Fr products the passes execute (ntt.cu): a pass over a 2^b digit runs b radix-2 stages; the last has no twiddle, and in
+        # stage h the butterflies with twiddle index 0 (1 of every h) skip the product -- (N/2)(b - 2 + 2^(1-b)) per pass -- plus
+        # N inter-pass twiddle products per pass boundary (digits: ntt_plan.h splits log2 N evenly, larger digits first)
+        digits = [lg // passes + (1 if i < lg % passes else 0) for i in range(passes)]
+        fr_mul = sum(r["n"] / 2 * (b_ - 2 + 2.0 ** (1 - b_)) for b_ in digits) + r["n"] * (passes - 1)
         b = {
             "metric": "bn254_fr_ntt_2^22_elements_per_s", "value": r["n"] * world / (r["ms"] * 1e-3), "unit": "elements/s",
             "ms_per_step": r["ms"],
@@ -930,7 +934,6 @@ def main() -> int:
                          "peak": hbm_peak, "unit": "GB/s", "frac": 64.0 * r["n"] / (top_ms * 1e-3) / 1e9 / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": top_ms,
                          "peak_source": peak_src, "passes": passes},
-            # Fr products per transform: (N/2) log2 N butterflies + N inter-pass twiddles per pass boundary
             "int_roofline": {"bound": "imad", "achieved": fr_mul * IMAD_PER_MUL / (r["ms"] * 1e-3) / 1e12,
                              "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": fr_mul * IMAD_PER_MUL / (r["ms"] * 1e-3) / imad_peak,
                              "fr_mul": fr_mul, "peak_source": imad_peak_src, "peak_library_loop": fq_peak * IMAD_PER_MUL / 1e12},

@@ -758,6 +758,174 @@ void oracle_fr_weighted_sums(const uint64_t *s, size_t n, uint64_t *s0_out, uint
     memcpy(s0_out, &s0, 32);
     memcpy(s1_out, &s1, 32);
 }
+/* ------------------------------------------------------------------ TurboPlonK prover pieces (CPU prover baseline)
+ * The bulk steps of prover_with_lagrange (/root/reference/uzkge/src/plonk/prover.rs:88-394) that are neither an MSM nor a
+ * transform, for oracle/cpu_prover.py (the proofs/s CPU baseline, default feature set).  Parallel where the reference is
+ * (t_poly's cfg_into_iter over the evaluation points, helpers.rs:284), serial where it is serial. */
+static inline void fp_pow5(const field_t *F, fe *o, const fe *a) {
+    fe a2, a4;
+    fp_sqr(F, &a2, a);
+    fp_sqr(F, &a4, &a2);
+    fp_mul(F, o, &a4, a);
+}
+/* t_poly's loop body, helpers.rs:284-669, terms 1-11 (build without the `shuffle` feature), times 1 / Z_H:
+ * cols = w[5] q[9] pi z s[5] coset_quotient l1 qb prk[4] (28 columns of m elements), sc = k[5] alpha beta gamma g g_inv */
+void oracle_plonk_quotient(const uint64_t *const *cols, const uint64_t *sc, const uint64_t *z_h_inv, size_t factor, size_t m,
+                           uint64_t *out) {
+    oracle_init();
+    const field_t *F = &FR;
+    const fe *k = (const fe *)sc, *alpha = k + 5, *beta = k + 6, *gamma = k + 7, *g = k + 8, *g_inv = k + 9;
+    fe a[10], g2p1;
+    a[0] = F->r;
+    for (int i = 1; i < 10; i++) fp_mul(F, &a[i], &a[i - 1], alpha);
+    fp_mul(F, &g2p1, g, g);
+    fp_add(F, &g2p1, &g2p1, &F->r);
+#define COL(c, i) ((const fe *)cols[c] + (i))
+#pragma omp parallel for schedule(static)
+    for (size_t p = 0; p < m; p++) {
+        const size_t pn = (p + factor) % m;
+        fe w[5], t, u, num, term2, term3;
+        for (int j = 0; j < 5; j++) w[j] = *COL(j, p);
+        /* term 1: the gate function (turbo/mod.rs:193-222) */
+        memset(&num, 0, sizeof(fe));
+        for (int j = 0; j < 4; j++) { fp_mul(F, &t, COL(5 + j, p), &w[j]); fp_add(F, &num, &num, &t); }
+        fe w01, w23;
+        fp_mul(F, &w01, &w[0], &w[1]);
+        fp_mul(F, &w23, &w[2], &w[3]);
+        fp_mul(F, &t, COL(9, p), &w01); fp_add(F, &num, &num, &t);
+        fp_mul(F, &t, COL(10, p), &w23); fp_add(F, &num, &num, &t);
+        fp_add(F, &num, &num, COL(11, p));
+        fp_add(F, &num, &num, COL(14, p));                      /* public input */
+        fp_mul(F, &t, &w01, &w23); fp_mul(F, &t, &t, &w[4]); fp_mul(F, &t, &t, COL(12, p)); fp_add(F, &num, &num, &t);
+        fp_mul(F, &t, COL(13, p), &w[4]); fp_sub(F, &num, &num, &t);
+        /* terms 2, 3: the permutation argument */
+        const fe *z = COL(15, p), *zn = COL(15, pn), *cq = COL(21, p);
+        fp_mul(F, &term2, alpha, z);
+        fp_mul(F, &term3, alpha, zn);
+        for (int j = 0; j < 5; j++) {
+            fp_mul(F, &t, beta, &k[j]); fp_mul(F, &t, &t, cq); fp_add(F, &t, &t, &w[j]); fp_add(F, &t, &t, gamma);
+            fp_mul(F, &term2, &term2, &t);
+            fp_mul(F, &t, beta, COL(16 + j, p)); fp_add(F, &t, &t, &w[j]); fp_add(F, &t, &t, gamma);
+            fp_mul(F, &term3, &term3, &t);
+        }
+        fp_add(F, &num, &num, &term2);
+        fp_sub(F, &num, &num, &term3);
+        /* term 4: L_1 (z - 1) */
+        fp_sub(F, &t, z, &F->r); fp_mul(F, &t, &t, COL(22, p)); fp_mul(F, &t, &t, &a[2]); fp_add(F, &num, &num, &t);
+        /* terms 5-7: boolean constraints on wires 1..3 */
+        for (int j = 1; j <= 3; j++) {
+            fp_sub(F, &t, &w[j], &F->r); fp_mul(F, &t, &t, &w[j]); fp_mul(F, &t, &t, COL(23, p)); fp_mul(F, &t, &t, &a[2 + j]);
+            fp_add(F, &num, &num, &t);
+        }
+        /* terms 8-11: Anemoi round */
+        const fe *w0n = COL(0, pn), *w1n = COL(1, pn), *w2n = COL(2, pn);
+        const fe *prk1 = COL(24, p), *prk2 = COL(25, p), *prk3 = COL(26, p), *prk4 = COL(27, p);
+        fe w30, w21, w320, w221, tmp, p5, e;
+        fp_add(F, &w30, &w[0], &w[3]); fp_add(F, &w21, &w[1], &w[2]);
+        fp_add(F, &w320, &w[0], &w30); fp_add(F, &w221, &w[1], &w21);
+        fp_mul(F, &tmp, g, &w21); fp_add(F, &tmp, &tmp, &w30); fp_add(F, &tmp, &tmp, prk3);
+        fp_sub(F, &t, &tmp, w2n); fp_pow5(F, &p5, &t);
+        /* 8 */
+        fp_sqr(F, &u, &tmp); fp_mul(F, &u, &u, g); fp_add(F, &e, &p5, &u);
+        fp_mul(F, &u, g, &w221); fp_add(F, &u, &u, &w320); fp_add(F, &u, &u, prk1); fp_sub(F, &e, &e, &u);
+        fp_mul(F, &e, &e, prk3); fp_mul(F, &e, &e, &a[6]); fp_sub(F, &num, &num, &e);
+        /* 10 */
+        fp_sqr(F, &u, w2n); fp_mul(F, &u, &u, g); fp_add(F, &e, &p5, &u); fp_add(F, &e, &e, g_inv); fp_sub(F, &e, &e, w0n);
+        fp_mul(F, &e, &e, prk3); fp_mul(F, &e, &e, &a[8]); fp_sub(F, &num, &num, &e);
+        fp_mul(F, &tmp, g, &w30); fp_mul(F, &u, &g2p1, &w21); fp_add(F, &tmp, &tmp, &u); fp_add(F, &tmp, &tmp, prk4);
+        fp_sub(F, &t, &tmp, &w[4]); fp_pow5(F, &p5, &t);
+        /* 9 */
+        fp_sqr(F, &u, &tmp); fp_mul(F, &u, &u, g); fp_add(F, &e, &p5, &u);
+        fp_mul(F, &u, g, &w320); fp_mul(F, &t, &g2p1, &w221); fp_add(F, &u, &u, &t); fp_add(F, &u, &u, prk2); fp_sub(F, &e, &e, &u);
+        fp_mul(F, &e, &e, prk3); fp_mul(F, &e, &e, &a[7]); fp_sub(F, &num, &num, &e);
+        /* 11 */
+        fp_sqr(F, &u, &w[4]); fp_mul(F, &u, &u, g); fp_add(F, &e, &p5, &u); fp_add(F, &e, &e, g_inv); fp_sub(F, &e, &e, w1n);
+        fp_mul(F, &e, &e, prk3); fp_mul(F, &e, &e, &a[9]); fp_sub(F, &num, &num, &e);
+        fp_mul(F, (fe *)out + p, &num, (const fe *)z_h_inv + (p % factor));
+    }
+#undef COL
+}
+/* z_poly's evaluations, helpers.rs:160-220: z[0] = 1, z[i+1] = z[i] * prod_j (w_j[i] + gamma + beta k_j g^i)
+ *                                                                  / prod_j (w_j[i] + gamma + beta * sigma(j, i))
+ * with one batch inversion of the n - 1 denominators.  perm holds the 5n targets of compute_permutation. */
+int oracle_plonk_z_evals(const uint64_t *w_ext, const uint64_t *perm, const uint64_t *k5, const uint64_t *group,
+                         const uint64_t *beta, const uint64_t *gamma, size_t n, uint64_t *out) {
+    oracle_init();
+    const field_t *F = &FR;
+    const fe *w = (const fe *)w_ext, *k = (const fe *)k5, *grp = (const fe *)group;
+    fe *z = (fe *)out;
+    fe *num = (fe *)malloc(sizeof(fe) * n), *den = (fe *)malloc(sizeof(fe) * n), *pre = (fe *)malloc(sizeof(fe) * n);
+    if (!num || !den || !pre) { free(num); free(den); free(pre); return 1; }
+    fe bk[5];
+    for (int j = 0; j < 5; j++) fp_mul(F, &bk[j], (const fe *)beta, &k[j]);
+    const size_t n1 = n ? n - 1 : 0;
+#pragma omp parallel for schedule(static) if (n >= 4096)
+    for (size_t i = 0; i < n1; i++) {
+        fe a = F->r, b = F->r, t;
+        for (int j = 0; j < 5; j++) {
+            const fe *f = &w[j * n + i];
+            fp_mul(F, &t, &bk[j], &grp[i]); fp_add(F, &t, &t, f); fp_add(F, &t, &t, (const fe *)gamma);
+            fp_mul(F, &a, &a, &t);
+            const uint64_t pp = perm[j * n + i];
+            fp_mul(F, &t, &bk[pp / n], &grp[pp % n]); fp_add(F, &t, &t, f); fp_add(F, &t, &t, (const fe *)gamma);
+            fp_mul(F, &b, &b, &t);
+        }
+        num[i] = a;
+        den[i] = b;
+    }
+    /* batch inversion (ark_ff::batch_inversion skips zeros) */
+    fe acc = F->r;
+    for (size_t i = 0; i + 1 < n; i++) {
+        pre[i] = acc;
+        if (!fe_is_zero(&den[i])) fp_mul(F, &acc, &acc, &den[i]);
+    }
+    fp_inv(F, &acc, &acc);
+    for (size_t i = n - 1; i-- > 0;) {
+        if (fe_is_zero(&den[i])) continue;
+        fe inv;
+        fp_mul(F, &inv, &acc, &pre[i]);
+        fp_mul(F, &acc, &acc, &den[i]);
+        den[i] = inv;
+    }
+    z[0] = F->r;
+    for (size_t i = 0; i + 1 < n; i++) {
+        fe t;
+        fp_mul(F, &t, &z[i], &num[i]);
+        fp_mul(F, &z[i + 1], &t, &den[i]);
+    }
+    free(num); free(den); free(pre);
+    return 0;
+}
+/* out[i] = sum_j scalars[j] * polys[j][i], i < L (coefficients beyond lens[j] are zero): r_poly / batch_prove's h */
+void oracle_fr_lincomb(const uint64_t *const *polys, const uint64_t *lens, const uint64_t *scalars, size_t cnt, uint64_t *out, size_t L) {
+    oracle_init();
+    const field_t *F = &FR;
+#pragma omp parallel for schedule(static) if (L >= 4096)
+    for (size_t i = 0; i < L; i++) {
+        fe acc, t;
+        memset(&acc, 0, sizeof(fe));
+        for (size_t j = 0; j < cnt; j++) {
+            if (i >= lens[j]) continue;
+            fp_mul(F, &t, (const fe *)scalars + j, (const fe *)polys[j] + i);
+            fp_add(F, &acc, &acc, &t);
+        }
+        ((fe *)out)[i] = acc;
+    }
+}
+/* c(X) = q(X) (X - z) + rem: synthetic division, q has n - 1 coefficients */
+void oracle_fr_div_linear(const uint64_t *coefs, size_t n, const uint64_t *z, uint64_t *quot, uint64_t *rem) {
+    oracle_init();
+    const field_t *F = &FR;
+    const fe *c = (const fe *)coefs;
+    fe acc;
+    memset(&acc, 0, sizeof(fe));
+    for (size_t i = n; i-- > 0;) {
+        fp_mul(F, &acc, &acc, (const fe *)z);
+        fp_add(F, &acc, &acc, &c[i]);
+        if (i > 0) ((fe *)quot)[i - 1] = acc;
+    }
+    memcpy(rem, &acc, 32);
+}
 /* torchrun exports OMP_NUM_THREADS=1; the CPU arm of bench.py asks for every host core explicitly */
 void oracle_set_num_threads(int n) {
 #ifdef _OPENMP

@@ -13,29 +13,45 @@
 
 template <int MODE>
 __global__ void __launch_bounds__(256) probe(unsigned long long* sink, double* dsink, int iters) {
-    unsigned long long a[8];
+    unsigned lo[8], hi[8], xa[8], xb[8];
     double d[8];
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        a[i] = t * 8 + i + 1;
+        lo[i] = t * 8 + i + 1;
+        hi[i] = i;
+        xa[i] = t + i;
+        xb[i] = t ^ i;
         d[i] = 1.0 + 1e-9 * (t + i);
     }
     const unsigned m = 0x9E3779B1u + t;
     const double dm = 1.0000001;
 #pragma unroll 1
-    for (int it = 0; it < iters; it++) {
+    for (int it = 0; it < iters; it += 16) {
+        // inline PTX so that the loop body is 128 multiplier instructions (8 independent accumulator chains x 16): left to
+        // itself nvcc re-materialises the 64-bit addend with MOV / IMAD.MOV pairs, which share the pipe and halve the figure
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (MODE != 1) a[i] = (unsigned long long)(unsigned)a[i] * m + a[i];   // IMAD.WIDE
-            if (MODE != 0) d[i] = fma(d[i], dm, 1e-12);                             // DFMA
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                // what ff.cuh issues: a mad.lo.cc / madc.hi pair on one 64-bit accumulator, which ptxas fuses into ONE
+                // IMAD.WIDE.U32 with the addend inside the instruction (a plain mad.wide.u32 is split into IMAD.WIDE + IADD3 +
+                // IADD3.X, and every extra instruction takes an issue slot away from the multiplier).  The multiplicand is the
+                // low word of the NEIGHBOURING chain: nothing is loop-invariant for ptxas to hoist
+                if (MODE != 1 && MODE != 4)
+                    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+                                 : "+r"(lo[i]), "+r"(hi[i]) : "r"(lo[(i + 1) & 7]), "r"(m));
+                if (MODE == 1 || MODE == 2) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dm), "d"(1e-12));   // DFMA
+                // MODE 3: one add-with-carry pair (IADD3 + IADD3.X, the ALU pipe) beside every multiplier instruction; 4: those alone
+                if (MODE >= 3) asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %2;" : "+r"(xa[i]), "+r"(xb[i]) : "r"(m));
+            }
         }
     }
     unsigned long long s = 0;
     double ds = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        s += a[i];
+        s += (((unsigned long long)hi[i] << 32) | lo[i]) + xa[i] + xb[i];
         ds += d[i];
     }
     if (s == 0x1234567ull) sink[t] = s;
@@ -92,5 +108,7 @@ int main(int argc, char** argv) {
     printf("IMAD.WIDE alone : %8.2f T/s\n", imad / 1e12);
     printf("DFMA alone      : %8.2f T/s\n", dfma / 1e12);
     printf("interleaved     : %8.2f T/s of each (IMAD.WIDE + DFMA issued by the same warps)\n", both / 1e12);
+    const double mix = run<3>(iters), adds = run<4>(iters);
+    printf("IMAD.WIDE + 2 IADD3 per multiplier instruction: %8.2f T IMAD.WIDE/s;  the IADD3 pairs alone: %8.2f T pairs/s\n", mix / 1e12, adds / 1e12);
     return 0;
 }

@@ -32,7 +32,15 @@ struct TileView {
     uint4* lo;
     uint4* hi;
     uint32_t logC, cmask;
-    __device__ __forceinline__ uint32_t pos(uint32_t r, uint32_t c) const { return (r << logC) | ((c + r) & cmask); }
+    // A quarter-warp (8 lanes x 16 bytes = one 128-byte wavefront) must hit 8 distinct slots mod 8.  With C >= 8 it stays inside
+    // one row and the rotation by r suffices.  With C = 4 it spans two rows, which the stage / store walks pick 2h or R/2 apart
+    // (same low row bit): bit 2 of the slot is therefore the low row bit XOR the parity of the remaining row bits, so that two
+    // rows differing in exactly one bit never share a half.
+    __device__ __forceinline__ uint32_t pos(uint32_t r, uint32_t c) const {
+        uint32_t p = (r << logC) | ((c + r) & cmask);
+        if (logC == 2) p ^= (__popc(r >> 1) & 1u) << 2;
+        return p;
+    }
     __device__ __forceinline__ fe ld(uint32_t p) const {
         fe x;
         uint4 a = lo[p], b = hi[p];
@@ -117,14 +125,25 @@ __global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
     for (int s = (int)logR - 1; s >= 0; s--) {
         const uint32_t h = 1u << s;
         const uint32_t tw_shift = logR - 1 - s;
+        // butterfly -> thread mapping: where a warp would otherwise mix twiddle indices, walk the 2h-row blocks first so that
+        // all 32 lanes share j -- the twiddle load is a broadcast, and the warps with j == 0 (w = 1: half of the butterflies
+        // at h = 2, a quarter at h = 4, ...) skip the product altogether: ~N/2 of the (N/2)(log2 R - 1) products of a pass
+        const uint32_t log_nblk = logR - 1 - s;
+        const bool by_block = logC >= 2 && logC + log_nblk >= 5;
         for (uint32_t bb = threadIdx.x; bb < (T >> 1); bb += NT) {
             const uint32_t c = bb & (C - 1), pr = bb >> logC;
-            const uint32_t j = pr & (h - 1);
-            const uint32_t r = ((pr >> s) << (s + 1)) | j;
+            uint32_t j, r;
+            if (by_block) {
+                j = pr >> log_nblk;
+                r = ((pr & ((1u << log_nblk) - 1)) << (s + 1)) | j;
+            } else {
+                j = pr & (h - 1);
+                r = ((pr >> s) << (s + 1)) | j;
+            }
             const uint32_t p0 = tv.pos(r, c), p1 = tv.pos(r + h, c);
             const fe u = tv.ld(p0), v = tv.ld(p1);
             fe d = fe_sub<FrP>(u, v);
-            if (s > 0) d = fe_mul<FrP>(d, ldg_fe(a.stage_tab + (size_t)(j << tw_shift) * p.stage_stride));
+            if (j) d = fe_mul<FrP>(d, ldg_fe(a.stage_tab + (size_t)(j << tw_shift) * p.stage_stride));
             tv.st(p0, fe_add<FrP>(u, v));
             tv.st(p1, d);
         }
