@@ -182,6 +182,19 @@ IMAD_PER_MUL, IMAD_PER_SQR = 136, 108
 IMAD_PER_MADD = 8 * IMAD_PER_MUL + 2 * IMAD_PER_SQR      # XYZZ mixed addition: 8 M + 2 S
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def headline_config(head: str, world: int) -> dict:
+    """The `config` of the JSON line -- the SAME dictionary in both arms (`--impl ours` and `--impl reference`), so that the driver
+    compares like with like; what is specific to one arm lives in that arm's `detail` / `reference_note`."""
+    return {
+        "workload": ("BN254 G1 variable-base MSM, 2^20 points per GPU, bases resident (affine KZG SRS), uniform Fr scalars"
+                     if head == "msm" else "BN254 Fr radix-2 NTT 2^22, natural order in/out"),
+        "parallelism": f"{world} process(es), one per GPU; MSM points split per GPU, partial sums all-gathered (96 B) and added",
+        "pipelining": "GPU arm: the K steps are submitted in one batch call and software-pipelined by the engine (sort / reduce of "
+                      "neighbouring steps under the accumulate kernel); detail.single_call_ms is one MSM per call",
+        "l2": "GPU arm: inputs rotate over 8 x 32 MiB scalar sets / 4 x 128 MiB vectors (> 126 MB L2); the MSM's window tables are 0.8 GiB",
+    }
+
+
 def run_reference(args, rank: int, world: int) -> int:
     """The reference's CPU path for the same metric: no Rust toolchain exists here or on the GPU box and the
     arithmetic lives in un-vendored arkworks forks, so this arm times the oracle port
@@ -192,10 +205,48 @@ def run_reference(args, rank: int, world: int) -> int:
 
     oc.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1: use every host core we may use
     cores = oc.num_threads()
-    log_n = LOG_MSM if args.workload != "ntt" else LOG_NTT
+    log_n = LOG_MSM if args.workload not in ("ntt", "plonk") else (LOG_NTT if args.workload == "ntt" else int(args.plonk_logs.split(",")[0]))
     n = 1 << log_n
+    units = n
     t_setup = time.time()
-    if args.workload != "ntt":
+    if args.workload == "plonk":
+        # a complete CPU proof per step: the compiled CPU prover (oracle/cpu_prover.py + oracle.c) on a synthetic circuit of add / mul
+        # gates in 8 layers (the shape of plonk.TurboCS.synthetic), SRS = random curve points (the prover never needs the trapdoor)
+        from oracle import cpu_prover as cpp
+        from oracle import plonk_prover as opp
+
+        rnd = np.random.default_rng(0xB2000004)
+        sel = np.zeros((9, n), dtype=np.int64)
+        wir = np.zeros((5, n), dtype=np.int64)
+        sel[6, 1] = 1
+        sel[8, :2] = 1
+        wir[:, 1] = 1
+        g = n - 2
+        per = [g // 8 + (1 if i < g % 8 else 0) for i in range(8)]
+        n_inputs = max(per[0], 2)
+        wit = [0, 1] + [int(x) for x in rnd.integers(1, 1 << 62, n_inputs)]
+        prev_lo, prev_n, row = 2, n_inputs, 2
+        for cnt in per:
+            a_, b_ = prev_lo + rnd.integers(0, prev_n, cnt), prev_lo + rnd.integers(0, prev_n, cnt)
+            mul = rnd.integers(0, 2, cnt).astype(bool)
+            var = len(wit)
+            wir[0, row:row + cnt], wir[1, row:row + cnt], wir[4, row:row + cnt] = a_, b_, np.arange(var, var + cnt)
+            sel[0, row:row + cnt] = sel[1, row:row + cnt] = ~mul
+            sel[4, row:row + cnt] = mul
+            sel[8, row:row + cnt] = 1
+            wit += [(wit[x] * wit[y] if m_ else wit[x] + wit[y]) % FR for x, y, m_ in zip(a_.tolist(), b_.tolist(), mul.tolist())]
+            prev_lo, prev_n, row = var, cnt, row + cnt
+        table = cpp.A([0, 1])
+        acs = cpp.ArrayCS([table[sel[i]] for i in range(9)], wir)
+        cpcs = cpp.CpuKzg(oc.g1_random_points(n + 3, 0xB2000006))
+        cP = cpp.indexer(acs, cpcs)
+        wit_arr = cpp.A(wit)
+        units = 1
+
+        def step(i):
+            cpp.prover(opp.ChaCha(bytes(32)), opp.Transcript(b"bench"), cpcs, acs, cP, wit_arr)
+        metric, unit, wl = "turboplonk_synthetic_proofs_per_s", "proofs/s", f"synthetic TurboPlonK circuit, 2^{log_n} gates, full prove"
+    elif args.workload != "ntt":
         pts = oc.g1_random_points(n, 0xB2000001)
         scal = [oc.random_fr(n, 0xB2000002 + i) for i in range(2)]
 
@@ -214,13 +265,17 @@ def run_reference(args, rank: int, world: int) -> int:
     for i in range(args.steps):
         step(i)
     dt = time.time() - t0
-    v = n * args.steps / dt
+    v = units * args.steps / dt
+    head = "msm" if args.workload not in ("ntt", "plonk") else args.workload
     line = {
         "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 limbs (256-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": wl, "where": "host CPU", "note": "oracle port of arkworks' algorithms (no Rust toolchain: the "
-                   "reference itself cannot be built); full workload per step", "setup_s": round(t0 - t_setup, 1)},
+        "config": headline_config(head, args.gpus) if head != "plonk" else {"workload": wl + ", witness resident in HBM"},
+        "reference_note": {"workload": wl, "where": "host CPU", "note": "oracle port of arkworks' algorithms (no Rust toolchain: the "
+                           "reference itself cannot be built); full workload per step; MSM bases are random curve points in host "
+                           "memory (the GPU arm's are a powers-of-tau SRS: the cost of an MSM does not depend on which points)",
+                           "setup_s": round(t0 - t_setup, 1)},
         "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": f"{args.steps} x full {wl}"},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -353,6 +408,15 @@ def plonk_proofs(args, dev, K: int, W: int, rank: int = 0, world: int = 1, barri
             "window_bits": window_bits, "hbm_peak_gib": torch.cuda.max_memory_allocated() / 2**30,
             "device_used_gib": (lambda fr_, tot_: (tot_ - fr_) / 2**30)(*torch.cuda.mem_get_info()),
         })
+        if world == 1 and lg <= 16 and not shuffle_features and "_cpu_inputs" not in out:
+            # what the CPU prover of the cpu_baseline leg needs to prove the SAME statement: the circuit as arrays, the witness, the SRS
+            # points, and the GPU's proof to hold the CPU's against
+            out["_cpu_inputs"] = {
+                "log_n": lg, "selectors": np.array(cs.selectors), "wiring": np.array(cs.wiring), "witness": np.array(wit_host),
+                "boolean": list(getattr(cs, "boolean_constraint_indices", [])),
+                "pub_constraint": list(cs.public_vars_constraint_indices), "pub_witness": list(cs.public_vars_witness_indices),
+                "srs": np.array(pcs.public_parameter_group_1), "proof_bytes": proof.to_bytes_be(), "gpu_prove_ms": dt * 1e3,
+            }
         pcs.close()
         if lagrange is not None:
             lagrange.close()
@@ -824,6 +888,7 @@ def main() -> int:
 
     # -------------------------------------------------------------------------------------------- CPU baseline (rank 0, N = 1)
     cpu_baseline = None
+    cpu_in = results.get("plonk", {}).pop("_cpu_inputs", None)      # arrays: never part of the JSON line
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu as oc  # the checker / CPU arm only
 
@@ -841,30 +906,31 @@ def main() -> int:
             cpu_baseline = {"value": m / dt, "unit": "points/s", "cores": cores, "kind": "port",
                             "sample": f"one full 2^{LOG_MSM}-point MSM (the workload's bases and first scalar set), {dt:.2f} s; "
                                       "result compared with the GPU's (affine) before timing was accepted"}
-        if "plonk" in results and results["plonk"]["sizes"]:
-            # the reference's prover cannot run here (no Rust): a LOWER BOUND of its CPU time is the MSM / NTT inventory of one
-            # proof replayed on the oracle port (13 MSMs of n + 3 points, 7 iFFT(n), 7 coset FFT(6n), 1 coset iFFT(6n)); the
-            # quotient map, evaluations, divisions and circuit bookkeeping of the real prover come on top
-            sz = results["plonk"]["sizes"][0]
-            lgp = sz["log_n"]
-            if lgp <= 16:
-                npl = 1 << lgp
-                pts = oc.g1_random_points(npl + 3, 0xB2000006)
-                scal = oc.random_fr(npl + 3, 0xB2000007)
-                vec_n, vec_m = oc.random_fr(npl, 0xB2000008), oc.random_fr(6 * npl, 0xB2000009)
-                t0 = time.time()
-                for _ in range(13):
-                    oc.msm_g1(pts, scal)
-                for _ in range(7):
-                    oc.ntt_fr(vec_n, npl, inverse=True)
-                for _ in range(7):
-                    oc.ntt_fr(vec_m, 6 * npl)
-                oc.ntt_fr(vec_m, 6 * npl, inverse=True)
-                dt = time.time() - t0
-                results["plonk"]["cpu_baseline"] = {
-                    "value": 1.0 / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
-                    "sample": f"MSM + NTT inventory of one 2^{lgp}-gate proof on the oracle port, {dt:.2f} s: an upper bound of the CPU "
-                              "prover's proofs/s (its quotient map, evaluations and divisions are not included)"}
+        if cpu_in is not None:
+            # a complete CPU proof of the same statement by the compiled CPU prover (oracle/cpu_prover.py + oracle.c: arkworks'
+            # Pippenger and radix-2 transforms restated, the quotient map over all cores, serial Horner / division as in the
+            # reference), accepted as a baseline only if its proof equals the GPU's byte for byte
+            from oracle import cpu_prover as cpp
+            from oracle import plonk_prover as opp
+
+            acs = cpp.ArrayCS(cpu_in["selectors"], cpu_in["wiring"], cpu_in["boolean"], cpu_in["pub_constraint"], cpu_in["pub_witness"])
+            cpcs = cpp.CpuKzg(cpu_in["srs"])
+            t0 = time.time()
+            cP = cpp.indexer(acs, cpcs)
+            idx_s = time.time() - t0
+            reps, t0 = 0, time.time()
+            while reps < 3 or (time.time() - t0 < 5.0 and reps < 20):
+                cproof = cpp.prover(opp.ChaCha(bytes(32)), opp.Transcript(b"bench"), cpcs, acs, cP, cpu_in["witness"])
+                reps += 1
+            dt = (time.time() - t0) / reps
+            if opp.proof_to_bytes_be(cproof) != cpu_in["proof_bytes"]:
+                raise SystemExit("bench.py: the CPU prover's proof differs from the GPU's -- refusing to report a number")
+            results["plonk"]["cpu_baseline"] = {
+                "value": 1.0 / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
+                "sample": f"{reps} complete proofs of the 2^{cpu_in['log_n']}-gate synthetic circuit (same circuit, witness, SRS, RNG seed and "
+                          f"transcript label as the GPU's first PlonK row), {dt * 1e3:.0f} ms each (indexer {idx_s:.1f} s, not timed); "
+                          "proof bytes equal to the GPU's",
+                "prove_ms": dt * 1e3, "gpu_prove_ms": cpu_in["gpu_prove_ms"]}
         if "ntt" in results:
             r = results["ntt"]
             t0 = time.time()
@@ -966,14 +1032,7 @@ def main() -> int:
         "metric": blk["metric"], "value": blk["value"], "unit": blk["unit"], "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 limbs (256-bit Montgomery, IMAD carry chains)", "data": "synthetic",
-        "config": {
-            "workload": ("BN254 G1 variable-base MSM, 2^20 points per GPU, powers-of-tau bases resident in HBM, uniform Fr scalars"
-                         if head == "msm" else "BN254 Fr radix-2 NTT 2^22, natural order in/out"),
-            "parallelism": f"{world} process(es), one per GPU; MSM points split per GPU, partial sums all-gathered (96 B) and added",
-            "pipelining": "the K steps are submitted in one batch call and software-pipelined by the engine (sort / reduce of neighbouring "
-                          "steps under the accumulate kernel); detail.single_call_ms is one MSM per call",
-            "l2": "inputs rotate over 8 x 32 MiB scalar sets / 4 x 128 MiB vectors (> 126 MB L2); the MSM's window tables are 0.8 GiB",
-        },
+        "config": headline_config(head, world),
         "e2e": blk["e2e"], "roofline": blk["roofline"], "int_roofline": blk["int_roofline"], "hbm_roofline": blk.get("hbm_roofline"),
         "gpu_launches": int(launches), "clocks": clocks,
         "cpu_baseline": cpu_baseline if head == "msm" else blk.get("cpu_baseline"),

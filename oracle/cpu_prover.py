@@ -51,7 +51,9 @@ def _lib():
 
 # ---------------------------------------------------------------- representation: (len, 4) uint64 Montgomery limbs
 def A(xs) -> np.ndarray:
-    return bn.ints_to_array([x % FR for x in xs], FR, mont=True)
+    if isinstance(xs, np.ndarray) and xs.dtype == np.uint64:
+        return np.ascontiguousarray(xs).reshape(-1, 4)        # already Montgomery limbs
+    return bn.ints_to_array([int(x) % FR for x in xs], FR, mont=True)
 
 
 def I(a) -> list[int]:
@@ -116,6 +118,52 @@ def div_linear(coefs: np.ndarray, z: int):
     return quot[: max(n - 1, 0)], I(rem.reshape(1, 4))[0]
 
 
+class ArrayCS:
+    """A circuit handed over as arrays (the layout of the product's TurboCS: selectors (9, n, 4) Montgomery limbs, wiring (5, n)
+    variable numbers) with the interface the indexer / prover below use.  No Anemoi rows unless `anemoi_prk` (4, n, 4) is given."""
+
+    def __init__(self, selectors, wiring, boolean_constraint_indices=(), public_vars_constraint_indices=(),
+                 public_vars_witness_indices=(), anemoi_prk=None, anemoi_generator=0, anemoi_generator_inv=0):
+        self.selectors = [np.ascontiguousarray(s_, dtype=np.uint64) for s_ in selectors]
+        self.wiring = np.asarray(wiring, dtype=np.int64)
+        self.size = int(self.wiring.shape[1])
+        self.boolean_constraint_indices = list(boolean_constraint_indices)
+        self.public_vars_constraint_indices = list(public_vars_constraint_indices)
+        self.public_vars_witness_indices = list(public_vars_witness_indices)
+        self.anemoi_prk = anemoi_prk
+        self.anemoi_generator, self.anemoi_generator_inv = anemoi_generator, anemoi_generator_inv
+
+    def quot_eval_dom_size(self):
+        return self.size * 6 if self.size > 8 else self.size * 16
+
+    def compute_permutation(self):
+        """constraint_system/mod.rs:54-84 (as in oracle.plonk_prover.TurboCS)."""
+        v = self.wiring.reshape(-1).tolist()
+        perm = [0] * len(v)
+        last, first = {}, {}
+        for i, var in enumerate(v):
+            if var in last:
+                perm[last[var]] = i
+            else:
+                first[var] = i
+            last[var] = i
+        for var, i in last.items():
+            perm[i] = first[var]
+        return perm
+
+    def compute_anemoi_jive_selectors(self):
+        if self.anemoi_prk is not None:
+            return [np.ascontiguousarray(e, dtype=np.uint64) for e in self.anemoi_prk]
+        return [np.zeros((self.size, 4), dtype=np.uint64) for _ in range(4)]
+
+    def extend_witness(self, witness):
+        return np.ascontiguousarray(np.asarray(witness, dtype=np.uint64).reshape(-1, 4)[self.wiring.reshape(-1)])
+
+    @staticmethod
+    def get_hiding_degree(idx):
+        return 3 if idx < 3 else 2
+
+
 class CpuKzg:
     """KZG over an explicit SRS (affine points, (len, 8) uint64 Montgomery): every commitment is a real Pippenger MSM."""
 
@@ -140,7 +188,7 @@ def indexer(cs, pcs: CpuKzg):
     cq = [k[1]] * m
     for i in range(1, m):
         cq[i] = cq[i - 1] * root_m % FR
-    perm = cs.compute_permutation()
+    perm = [int(p) for p in cs.compute_permutation()]
     enc = [k[p // n] * group[p % n] % FR for p in perm]
 
     def pre(evals_ints):
@@ -240,12 +288,16 @@ def prover(rng, tr, pcs: CpuKzg, cs, P, witness):
     """Same arguments and the same proof dictionary as oracle.plonk_prover.prover (default feature set)."""
     n, vp = P["n"], P["vp"]
     k, root = vp["k"], P["root"]
-    online = [witness[i] for i in cs.public_vars_witness_indices]
+    if isinstance(witness, np.ndarray):
+        witness = witness.reshape(-1, 4)
+        online = I(witness[list(cs.public_vars_witness_indices)]) if cs.public_vars_witness_indices else []
+    else:
+        online = [witness[i] for i in cs.public_vars_witness_indices]
     pp.transcript_init_plonk(tr, vp, online, root)
-    pi_evals = [0] * n
-    for pos, ci in enumerate(cs.public_vars_constraint_indices):
-        pi_evals[ci] = online[pos]
-    pi = ifft(A(pi_evals), n)
+    pi_arr = np.zeros((n, 4), dtype=np.uint64)
+    if online:
+        pi_arr[list(cs.public_vars_constraint_indices)] = A(online)
+    pi = ifft(pi_arr, n)
     w_ext = A(cs.extend_witness(witness))
     w_polys, cm_w = [], []
     for i in range(N_WIRES):

@@ -38,3 +38,15 @@ def test_pieces_against_python_integers():
     assert cp.I(lc) == [(3 * x + (5 * x if i < 4 else 0)) % bn.FR for i, x in enumerate(xs)]
     assert cp.p_eval(a, 11) == pp.p_eval(xs, 11)
     assert cp.I(cp.trim(cp.A([1, 2, 0, 0]))) == [1, 2] and cp.I(cp.trim(cp.A([0, 0]))) == [0]
+
+
+def test_array_circuit_gives_the_same_proof():
+    """The array hand-over bench.py uses (the product's TurboCS layout) against the list-based circuit."""
+    cs = build_circuit(pp.TurboCS(), 30, 9, n_public=2, n_boolean=1)
+    pcs = pp.Kzg(cs.size + 2, 0xABCDEF)
+    cpcs = cp.CpuKzg(bn.affine_to_array(pcs.srs))
+    acs = cp.ArrayCS([cp.A(s) for s in cs.selectors], np.array(cs.wiring), cs.boolean_constraint_indices,
+                     cs.public_vars_constraint_indices, cs.public_vars_witness_indices)
+    want = cp.prover(pp.ChaCha(bytes(32)), pp.Transcript(b"arr"), cpcs, cs, cp.indexer(cs, cpcs), cs.witness)
+    got = cp.prover(pp.ChaCha(bytes(32)), pp.Transcript(b"arr"), cpcs, acs, cp.indexer(acs, cpcs), cp.A(cs.witness))
+    assert pp.proof_to_bytes_be(got) == pp.proof_to_bytes_be(want)
