@@ -241,6 +241,13 @@ typedef struct {
 UZKGE_API int32_t uzkge_cuda_plonk_quotient_shuffle_fr_device(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* shuffle,
                                                               void* d_out, void* stream);
 
+/* The same map (either feature set: shuffle may be NULL) on the points p = start + step * i, i < count, of the size-m arrays; d_out is
+ * written at the same positions.  (start, step, count) = (j, factor, n) is the coset g_j <w_n>, g_j = k[1] w_m^j, of the quotient
+ * domain: the omega-shifted point stays inside the coset, so the cosets of one quotient are independent jobs -- the unit by which a
+ * device group splits the round (uzkge_cuda_plonk_prove over a multi-device parameter handle). */
+UZKGE_API int32_t uzkge_cuda_plonk_quotient_range_fr_device(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* shuffle,
+                                                            uint64_t start, uint64_t step, uint64_t count, void* d_out, void* stream);
+
 /* ---- elementwise glue of a device-resident prover; DEVICE pointers, caller's stream, no copies, no sync ------
  * out[i] = sum_{j < k} coefs[j] * polys[j][i] for i < out_len, where polys[j][i] = 0 for i >= lens[j]; coefs: k Montgomery Fr on
  * the HOST.  Replaces the mul / add_assign chains of r_poly_or_comm (plonk/helpers.rs:716-745, 986-993) and of batch_prove
@@ -260,6 +267,9 @@ UZKGE_API int32_t uzkge_cuda_fr_add_sparse_multi_device(void* const* d_polys, co
 UZKGE_API int32_t uzkge_cuda_fr_powers_device(const uint64_t base_host[4], const uint64_t* scale_host, size_t n, void* d_out, void* stream);
 /* out[i] = src[idx[i]], idx: n uint32 on the device: ConstraintSystem::extend_witness (plonk/constraint_system/mod.rs:103-111). */
 UZKGE_API int32_t uzkge_cuda_fr_gather_device(const void* d_src, const void* d_idx_u32, size_t n, void* d_out, void* stream);
+/* dst[dst_start + dst_step * i] = src[src_start + src_step * i], i < count: one coset of an interleaved domain <-> a compact vector. */
+UZKGE_API int32_t uzkge_cuda_fr_strided_copy_device(const void* d_src, size_t src_start, size_t src_step, void* d_dst, size_t dst_start,
+                                                    size_t dst_step, size_t count, void* stream);
 /* dst[dst_idx[j]] = src[src_idx[j]], j < k; both index arrays are uint32 on the device: pi_poly's evaluation vector (the public inputs on
  * their constraint rows, plonk/helpers.rs:111-131) filled straight from the device-resident witness. */
 UZKGE_API int32_t uzkge_cuda_fr_gather_scatter_device(const void* d_src, const void* d_src_idx_u32, void* d_dst, const void* d_dst_idx_u32, size_t k,
@@ -324,6 +334,13 @@ typedef struct {
     uint64_t edwards_a[4];
 } uzkge_plonk_params_desc;
 UZKGE_API int32_t uzkge_cuda_plonk_params_upload(const uzkge_plonk_params_desc* desc, uint64_t* params_handle);
+/* The same parameters on every device of the group (uzkge_cuda_init_devices), uploaded side by side.  uzkge_cuda_plonk_prove over such
+ * a handle -- with `srs` / `lagrange_srs` multi-device handles in UZKGE_MULTI_SPLIT mode -- produces ONE proof on all the GPUs: every
+ * device runs the prover on replicated polynomials (same witness, blinds and transcript, so the same challenges), but commits only its
+ * slice of the SRS points (the 96-byte partial sums are added on the host: "MSM points are split per GPU") and evaluates the quotient
+ * only on its cosets of the 6n domain, which the devices exchange over peer memory before the inverse transform.  The proof is
+ * byte-identical to the single-device proof.  set_public_key / free accept the handle. */
+UZKGE_API int32_t uzkge_cuda_plonk_params_upload_multi(const uzkge_plonk_params_desc* desc, uint64_t* params_handle);
 /* refresh_prover_params_public_key (shuffle/src/gen_params/params.rs:57-129): replace the 12 public-key selector polynomials. */
 UZKGE_API int32_t uzkge_cuda_plonk_params_set_public_key(uint64_t params_handle, const uint64_t* const polys[12], const size_t len[12]);
 UZKGE_API int32_t uzkge_cuda_plonk_params_free(uint64_t params_handle);
@@ -331,6 +348,9 @@ UZKGE_API int32_t uzkge_cuda_plonk_params_free(uint64_t params_handle);
  * [n, n + 3) are read -- exactly what the bundled srs-padding.bin keeps, gen_params/mod.rs:147-171). */
 UZKGE_API int32_t uzkge_cuda_srs_upload_lagrange_commit(const uint64_t* lagrange_xy, size_t n, const uint64_t* monomial_xy, size_t monomial_len,
                                                         uint32_t window_bits, uint64_t* handle);
+/* The same SRS split over the device group (UZKGE_MULTI_SPLIT), for uzkge_cuda_plonk_prove over a multi-device parameter handle. */
+UZKGE_API int32_t uzkge_cuda_srs_upload_lagrange_commit_multi(const uint64_t* lagrange_xy, size_t n, const uint64_t* monomial_xy,
+                                                              size_t monomial_len, uint32_t window_bits, uint64_t* handle);
 
 typedef struct {
     uint64_t params;                     /* uzkge_cuda_plonk_params_upload */

@@ -33,6 +33,7 @@ using namespace uz;
 
 namespace uz {
 extern int g_quotient_min_blocks;  // quotient.cu
+static int g_virtual_devices = 0;   // tests: group members cycle over the visible GPUs (uzkge_cuda_configure "virtual_devices")
 }
 
 namespace {
@@ -720,6 +721,23 @@ UZKGE_API int32_t uzkge_cuda_plonk_quotient_shuffle_fr_device(const uzkge_quotie
     return engine_fail(rc, "plonk_quotient_shuffle_fr_device");
 }
 
+UZKGE_API int32_t uzkge_cuda_plonk_quotient_range_fr_device(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* shuffle,
+                                                            uint64_t start, uint64_t step, uint64_t count, void* d_out, void* stream) {
+    API_ENTER(-1);
+    int rc = plonk_quotient_range_run(args, shuffle, start, step, count, d_out, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "plonk_quotient_range_fr_device: null pointer");
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "plonk_quotient_range_fr_device: m a multiple of factor <= 16, start + step * (count - 1) < m");
+    return engine_fail(rc, "plonk_quotient_range_fr_device");
+}
+
+UZKGE_API int32_t uzkge_cuda_fr_strided_copy_device(const void* d_src, size_t src_start, size_t src_step, void* d_dst, size_t dst_start,
+                                                    size_t dst_step, size_t count, void* stream) {
+    API_ENTER(-1);
+    int rc = fr_strided_copy_run(d_src, src_start, src_step, d_dst, dst_start, dst_step, count, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "fr_strided_copy_device: null pointer");
+    return engine_fail(rc, "fr_strided_copy_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_fr_lincomb_device(const void* const* d_polys, const size_t* lens, const uint64_t* coefs_host, size_t k,
                                                void* d_out, size_t out_len, void* stream) {
     API_ENTER(-1);
@@ -983,6 +1001,11 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
         g_quotient_min_blocks = (int)value;
         return UZKGE_OK;
     }
+    if (k == "virtual_devices") {   // tests: the next uzkge_cuda_init_devices builds a group of `value` members over the visible GPUs
+        if (value > UZ_MAX_DEVICES) return fail(UZKGE_ERR_ARG, "configure: virtual_devices <= 16");
+        g_virtual_devices = (int)value;
+        return UZKGE_OK;
+    }
     bool rebuild_ntt = false;
     {
         std::lock_guard<std::mutex> reg(g_reg_mu);
@@ -1206,6 +1229,25 @@ MultiSrs* find_multi(uint64_t handle) {
 
 }  // namespace
 
+// ---- what prover.cu needs of the device group (declared in internal.h)
+namespace uz {
+std::mutex& group_mutex() { return g_multi_mu; }
+std::vector<int> group_devices_locked() { return g_group; }
+int group_fan_out(size_t count, const std::function<int(size_t)>& job) { return fan_out(count, job); }
+void group_sum_jacobians(const uint64_t* parts, size_t count, uint64_t out[12]) { host_sum_jacobians(parts, count, out); }
+bool group_srs_parts_locked(uint64_t handle, GroupSrsParts* out) {
+    MultiSrs* m = find_multi(handle);
+    if (!m) return false;
+    out->mode = m->mode;
+    out->n = m->n;
+    out->devices = m->devices;
+    out->sub = m->sub;
+    out->lo = m->lo;
+    out->hi = m->hi;
+    return true;
+}
+}  // namespace uz
+
 extern "C" {
 
 UZKGE_API int32_t uzkge_cuda_init_devices(int32_t device_count) {
@@ -1231,7 +1273,13 @@ UZKGE_API int32_t uzkge_cuda_init_devices(int32_t device_count) {
         }
     }
     g_group.clear();
-    for (int d = 0; d < use; d++) g_group.push_back(d);
+    if (g_virtual_devices > 0) {
+        // a group with more members than GPUs: member i lives on device i % use.  Every member still owns its SRS slice, parameter
+        // copy and streams, so the group code paths run unchanged -- how the one-GPU test box exercises them
+        for (int i = 0; i < g_virtual_devices; i++) g_group.push_back(i % use);
+    } else {
+        for (int d = 0; d < use; d++) g_group.push_back(d);
+    }
     return UZKGE_OK;
 }
 

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <functional>
+#include <mutex>
 #include <map>
 #include <vector>
 
@@ -256,6 +258,9 @@ private:
 
 // ---------------------------------------------------------------- PlonK quotient map (quotient.cu)
 int plonk_quotient_run(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* shuffle, void* d_out, cudaStream_t st);
+// the same map on the points start + step * idx, idx < count, of the size-m arrays
+int plonk_quotient_range_run(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* shuffle, uint64_t start, uint64_t step,
+                             uint64_t count, void* d_out, cudaStream_t st);
 
 // ---------------------------------------------------------------- elementwise prover glue (plonk_glue.cu)
 int fr_lincomb_run(const void* const* d_polys, const size_t* lens, const uint64_t* coefs, size_t k, void* d_out, size_t out_len, cudaStream_t st);
@@ -265,9 +270,26 @@ int fr_powers_run(const uint64_t* base, const uint64_t* scale, size_t n, void* d
 int fr_gather_run(const void* d_src, const void* d_idx, size_t n, void* d_out, cudaStream_t st);
 int fr_gather_scatter_run(const void* d_src, const void* d_src_idx, void* d_dst, const void* d_dst_idx, size_t k, cudaStream_t st);
 int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out, cudaStream_t st);
+// d_dst[dst_start + dst_step * i] = d_src[src_start + src_step * i], i < count
+int fr_strided_copy_run(const void* d_src, size_t src_start, size_t src_step, void* d_dst, size_t dst_start, size_t dst_step, size_t count,
+                        cudaStream_t st);
 int fr_trimmed_len_run(const void* d_poly, size_t n, unsigned long long* d_scratch, size_t* len_out, cudaStream_t st);
 int plonk_z_evals_run(PolyEngine* poly, const void* const d_w[5], const void* const d_sigma[5], const void* d_group, const uint64_t* k,
                       const uint64_t* beta, const uint64_t* gamma, size_t n, void* d_z, void* d_tmp, cudaStream_t st);
+
+// ---------------------------------------------------------------- the device group (api.cu) as prover.cu sees it
+struct GroupSrsParts {      // a multi-device SRS handle: member i owns bases [lo[i], hi[i]) behind its own single-device handle
+    int mode = 0;
+    size_t n = 0;
+    std::vector<int> devices;
+    std::vector<uint64_t> sub;
+    std::vector<size_t> lo, hi;
+};
+std::mutex& group_mutex();                       // one multi-device call at a time (the calls share the worker threads)
+std::vector<int> group_devices_locked();         // members' devices (group_mutex held)
+bool group_srs_parts_locked(uint64_t handle, GroupSrsParts* out);
+int group_fan_out(size_t count, const std::function<int(size_t)>& job);   // job(i) on worker i, all in parallel; first failure reported
+void group_sum_jacobians(const uint64_t* parts, size_t count, uint64_t out[12]);
 
 static inline int cuda_err_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? UZKGE_ERR_OOM : UZKGE_ERR_CUDA; }
 

@@ -227,6 +227,22 @@ int fr_gather_scatter_run(const void* d_src, const void* d_src_idx, void* d_dst,
     return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
 }
 
+// one coset of an interleaved domain <-> a compact vector (the quotient round split by cosets: prover.cu)
+__global__ void __launch_bounds__(256) fr_strided_copy_kernel(const fe* src, size_t src_start, size_t src_step, fe* dst, size_t dst_start,
+                                                              size_t dst_step, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) st_fe(dst + dst_start + dst_step * i, ld_fe(src + src_start + src_step * i));
+}
+
+int fr_strided_copy_run(const void* d_src, size_t src_start, size_t src_step, void* d_dst, size_t dst_start, size_t dst_step, size_t count,
+                        cudaStream_t st) {
+    if (count == 0) return UZKGE_OK;
+    if (!d_src || !d_dst) return UZKGE_ERR_ARG;
+    fr_strided_copy_kernel<<<blocks_for(count, 256), 256, 0, st>>>((const fe*)d_src, src_start, src_step, (fe*)d_dst, dst_start, dst_step, count);
+    UZ_COUNT_LAUNCH(1);
+    return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
+}
+
 int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out, cudaStream_t st) {
     if (n == 0) return UZKGE_OK;
     if (!d_a || !d_b || !d_out) return UZKGE_ERR_ARG;

@@ -14,12 +14,14 @@
 // Host code only: no kernel lives here.  No CPU fallback: every polynomial operation is a device call.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/uzkge_transcript.hpp"
@@ -116,6 +118,9 @@ struct Params {
     u64 *scratch = nullptr, *coset[8] = {}, *w_sel_coset[3] = {}, *wit = nullptr, *ext = nullptr, *sel_ev = nullptr, *z_ev = nullptr, *ztmp = nullptr;
     u64 *polys = nullptr;      // 16 buffers of stride elements: w[5], w_sel[3], z, t[5], r, (spare)
     u64 *pi = nullptr, *sh = nullptr, *q1 = nullptr, *q2 = nullptr, *lag_buf = nullptr, *small = nullptr;
+    // device group (uzkge_cuda_plonk_params_upload_multi): compact coset vectors (10 x n), the exchanged quotient cosets (m elements,
+    // coset j at [j n, (j + 1) n)) and the saved head coefficients of the polynomials folded onto a coset
+    u64 *cbuf = nullptr, *tcos = nullptr, *fold_save = nullptr;
     u64* pinned = nullptr;     // host, page-locked: results of the small device-to-host reads
     cudaStream_t st = nullptr, side = nullptr;
     cudaEvent_t ev = nullptr;
@@ -127,6 +132,38 @@ struct Params {
 std::mutex g_params_mu;
 std::map<u64, std::unique_ptr<Params>> g_params;
 u64 g_params_next = 1;
+// a multi-device parameter handle (bit 62) owns one ordinary handle per member of the device group
+constexpr u64 PARAMS_MULTI = 1ull << 62;
+std::map<u64, std::vector<u64>> g_multi_params;
+
+// ---- one proof on the whole device group: every member (one worker thread each) runs the prover below on replicated polynomials and
+// meets the others only here.  The members' transcripts stay identical because every commitment is the sum of all partial sums.
+struct SpinBarrier {        // the members are dedicated threads that meet a dozen times per proof: spin, do not sleep
+    std::atomic<uint32_t> count{0}, gen{0};
+    std::atomic<bool> aborted{false};
+    uint32_t members = 1;
+    bool wait() {           // false: a member failed, the proof is abandoned
+        const uint32_t g = gen.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == members) {
+            count.store(0, std::memory_order_relaxed);
+            gen.fetch_add(1, std::memory_order_release);
+        } else {
+            while (gen.load(std::memory_order_acquire) == g) {
+                if (aborted.load(std::memory_order_relaxed)) return false;
+                std::this_thread::yield();
+            }
+        }
+        return !aborted.load(std::memory_order_relaxed);
+    }
+    void abort() { aborted.store(true); }
+};
+struct Group {
+    size_t G = 1;
+    SpinBarrier bar;
+    std::vector<u64> partial;            // [2][G][16][12]: the members' partial sums of a commitment batch, double-buffered by batch parity
+    uz::GroupSrsParts srs, lag;          // the monomial SRS / the Lagrange commitment SRS, split over the members
+    std::vector<Params*> params;         // the members' parameter sets (tcos: where a member receives the others' quotient cosets)
+};
 
 int dev_alloc(Params& P, size_t elems, u64** out, bool zero) {
     void* p = nullptr;
@@ -156,8 +193,11 @@ int coset_fft(Params& P, const Poly& f, u64* out) {
 }
 // k transforms over one domain: batched launches where the workspace allows, else one by one
 int ntt_many(Params& P, const u64* const* ins, u64* const* outs, const size_t* lens, size_t k, size_t size, int inverse, const u64* shift) {
-    for (size_t j0 = 0; j0 < k; j0 += P.ntt_batch) {
-        const size_t kk = k - j0 < P.ntt_batch ? k - j0 : P.ntt_batch;
+    size_t batch = P.ntt_batch * P.m / size;       // the scratch vector holds ntt_batch * m elements
+    if (batch > uz::NTT_MAX_BATCH) batch = uz::NTT_MAX_BATCH;
+    if (P.ntt_batch == 1) batch = 1;               // large circuits: one vector fills the GPU, batching buys nothing
+    for (size_t j0 = 0; j0 < k; j0 += batch) {
+        const size_t kk = k - j0 < batch ? k - j0 : batch;
         if (kk == 1)
             TRY(uzkge_cuda_ntt_fr_device(ins[j0], outs[j0], P.scratch, lens[j0], size, inverse, shift, P.st));
         else
@@ -199,6 +239,17 @@ UZKGE_API int32_t uzkge_cuda_srs_upload_lagrange_commit(const uint64_t* lagrange
     memcpy(pts.data() + n * 8, monomial_xy, N_BLIND_SLOTS * 64);
     memcpy(pts.data() + (n + N_BLIND_SLOTS) * 8, monomial_xy + n * 8, N_BLIND_SLOTS * 64);
     return uzkge_cuda_srs_upload(pts.data(), n + 2 * N_BLIND_SLOTS, window_bits, handle);
+}
+
+UZKGE_API int32_t uzkge_cuda_srs_upload_lagrange_commit_multi(const uint64_t* lagrange_xy, size_t n, const uint64_t* monomial_xy, size_t monomial_len,
+                                                              uint32_t window_bits, uint64_t* handle) {
+    if (!lagrange_xy || !monomial_xy || !handle) return uz::api_fail(UZKGE_ERR_ARG, "srs_upload_lagrange_commit_multi: null pointer");
+    if (n == 0 || monomial_len < n + N_BLIND_SLOTS) return uz::api_fail(UZKGE_ERR_SIZE, "srs_upload_lagrange_commit_multi: the monomial SRS must hold n + 3 points");
+    std::vector<u64> pts((n + 2 * N_BLIND_SLOTS) * 8);
+    memcpy(pts.data(), lagrange_xy, n * 64);
+    memcpy(pts.data() + n * 8, monomial_xy, N_BLIND_SLOTS * 64);
+    memcpy(pts.data() + (n + N_BLIND_SLOTS) * 8, monomial_xy + n * 8, N_BLIND_SLOTS * 64);
+    return uzkge_cuda_srs_upload_multi(pts.data(), n + 2 * N_BLIND_SLOTS, window_bits, UZKGE_MULTI_SPLIT, handle);
 }
 
 UZKGE_API int32_t uzkge_cuda_plonk_params_upload(const uzkge_plonk_params_desc* d, uint64_t* params_handle) {
@@ -347,6 +398,17 @@ UZKGE_API int32_t uzkge_cuda_plonk_params_upload(const uzkge_plonk_params_desc* 
 
 UZKGE_API int32_t uzkge_cuda_plonk_params_set_public_key(uint64_t params_handle, const uint64_t* const polys[12], const size_t len[12]) {
     if (!polys || !len) return uz::api_fail(UZKGE_ERR_ARG, "plonk_params_set_public_key: null pointer");
+    if (params_handle & PARAMS_MULTI) {
+        std::vector<u64> subs;
+        {
+            std::lock_guard<std::mutex> lock(g_params_mu);
+            auto it = g_multi_params.find(params_handle);
+            if (it == g_multi_params.end()) return uz::api_fail(UZKGE_ERR_HANDLE, "plonk_params_set_public_key: unknown handle");
+            subs = it->second;
+        }
+        for (u64 h : subs) TRY(uzkge_cuda_plonk_params_set_public_key(h, polys, len));
+        return UZKGE_OK;
+    }
     Params* Pp;
     {
         std::lock_guard<std::mutex> lock(g_params_mu);
@@ -373,6 +435,22 @@ UZKGE_API int32_t uzkge_cuda_plonk_params_set_public_key(uint64_t params_handle,
 }
 
 UZKGE_API int32_t uzkge_cuda_plonk_params_free(uint64_t params_handle) {
+    if (params_handle & PARAMS_MULTI) {
+        std::vector<u64> subs;
+        {
+            std::lock_guard<std::mutex> lock(g_params_mu);
+            auto it = g_multi_params.find(params_handle);
+            if (it == g_multi_params.end()) return uz::api_fail(UZKGE_ERR_HANDLE, "plonk_params_free: unknown handle");
+            subs = it->second;
+            g_multi_params.erase(it);
+        }
+        int rc = UZKGE_OK;
+        for (u64 h : subs) {
+            const int r = uzkge_cuda_plonk_params_free(h);
+            if (r != UZKGE_OK) rc = r;
+        }
+        return rc;
+    }
     std::unique_ptr<Params> victim;
     {
         std::lock_guard<std::mutex> lock(g_params_mu);
@@ -386,8 +464,14 @@ UZKGE_API int32_t uzkge_cuda_plonk_params_free(uint64_t params_handle) {
     return UZKGE_OK;
 }
 
-UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof) {
-    if (!a || !proof || !a->witness || !a->blinds || !a->transcript) return uz::api_fail(UZKGE_ERR_ARG, "plonk_prove: null pointer");
+}  // extern "C"
+
+namespace {
+
+// One proof.  grp == nullptr: the whole proof on the parameter set's device.  Otherwise this is member `rank` of a device group: the
+// same code on replicated data, except that a commitment covers only the member's slice of the SRS (the partial sums meet in
+// grp->partial) and the quotient is evaluated only on the member's cosets of the quotient domain (exchanged through Params::tcos).
+int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group* grp, size_t rank) {
     Params* Pp;
     {
         std::lock_guard<std::mutex> lock(g_params_mu);
@@ -398,6 +482,8 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
     Params& P = *Pp;
     std::lock_guard<std::mutex> lock(P.mu);
     TRY(uzkge_cuda_set_device(P.device));
+    const size_t G = grp ? grp->G : 1;
+    size_t commit_seq = 0;
     const size_t n = P.n, m = P.m, stride = P.stride;
     const bool shuffle = P.shuffle;
     const bool lagrange = a->lagrange_srs != 0;
@@ -408,12 +494,20 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
     size_t srs_n = 0, lag_n = 0;
     uzkge_srs_info info;
     if (a->srs) {
-        TRY(uzkge_cuda_srs_info(a->srs, &info));
-        srs_n = info.n;
+        if (grp) {
+            srs_n = grp->srs.n;       // resolved by the caller (the group call holds the registry's lock)
+        } else {
+            TRY(uzkge_cuda_srs_info(a->srs, &info));
+            srs_n = info.n;
+        }
     }
     if (lagrange) {
-        TRY(uzkge_cuda_srs_info(a->lagrange_srs, &info));
-        lag_n = info.n;
+        if (grp) {
+            lag_n = grp->lag.n;
+        } else {
+            TRY(uzkge_cuda_srs_info(a->lagrange_srs, &info));
+            lag_n = info.n;
+        }
         if (lag_n != n + 2 * N_BLIND_SLOTS) return uz::api_fail(UZKGE_ERR_SIZE, "plonk_prove: the Lagrange commitment SRS does not match the circuit size");
     }
     if (!lagrange_all && srs_n < n + 3) return uz::api_fail(UZKGE_ERR_SIZE, "plonk_prove: the monomial SRS must hold n + 3 points");
@@ -481,18 +575,34 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
     };
     // commit k vectors over one SRS; `overlap` (device work that does not depend on them) is enqueued behind the MSMs, the results are
     // read back on the side stream so that the host can hash while the GPU keeps working.  out_aff: k x 8 words (affine, Montgomery)
-    auto commit = [&](u64 handle, size_t handle_n, const std::vector<Msm>& v, u64* out_aff, const std::function<int()>& overlap) -> int {
+    auto commit = [&](u64 handle, const size_t handle_n, const std::vector<Msm>& v, u64* out_aff, const std::function<int()>& overlap) -> int {
         const size_t k = v.size();
         for (const Msm& x : v)
             if (x.len > handle_n) return uz::api_fail(UZKGE_ERR_SIZE, "plonk_prove: DegreeError (a polynomial does not fit the SRS: unsatisfied witness?)");
         u64* d_out = P.small;                     // 16 x 12 words
         const void* ptrs[16];
         size_t lens[16];
-        for (size_t j = 0; j < k; j++) {
-            ptrs[j] = v[j].p;
-            lens[j] = v[j].len;
+        if (k > 16) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: more than 16 commitments in one batch");
+        // a group member commits the part of every vector that falls into its slice [lo, hi) of the SRS
+        size_t lo = 0, hi = handle_n;
+        bool mine = true;
+        if (grp) {
+            const uz::GroupSrsParts& parts = (lagrange && handle == a->lagrange_srs) ? grp->lag : grp->srs;
+            mine = rank < parts.sub.size();
+            if (mine) {
+                handle = parts.sub[rank];
+                lo = parts.lo[rank];
+                hi = parts.hi[rank];
+            }
         }
-        if (k == 1)
+        for (size_t j = 0; j < k; j++) {
+            const size_t b = v[j].len < hi ? v[j].len : hi;
+            lens[j] = b > lo ? b - lo : 0;
+            ptrs[j] = v[j].p + 4 * (lens[j] ? lo : 0);
+        }
+        if (!mine)
+            CU(cudaMemsetAsync(d_out, 0, k * 96, st));      // Z = 0: the identity
+        else if (k == 1)
             TRY(uzkge_cuda_msm_g1_device(handle, 0, ptrs[0], lens[0], d_out, st));
         else
             TRY(uzkge_cuda_msm_g1_batch_device(handle, 0, ptrs, lens, k, d_out, st));
@@ -503,7 +613,20 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
         CU(cudaMemcpyAsync(P.pinned, d_out, k * 96, cudaMemcpyDeviceToHost, P.side));
         CU(cudaStreamSynchronize(P.side));
         // the next user of P.small is ordered after this read: it is enqueued on `st` only after the host has the results
-        batch_to_affine(P.pinned, k, out_aff);
+        if (!grp) {
+            batch_to_affine(P.pinned, k, out_aff);
+            return UZKGE_OK;
+        }
+        // "the partial G1 sums are combined with one projective add each": every member adds all G partial sums, in member order
+        u64* slots = grp->partial.data() + (commit_seq++ & 1) * G * 16 * 12;
+        memcpy(slots + rank * 16 * 12, P.pinned, k * 96);
+        if (!grp->bar.wait()) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: another member of the device group failed");
+        u64 sums[16 * 12], col[uz::UZ_MAX_DEVICES * 12];
+        for (size_t j = 0; j < k; j++) {
+            for (size_t r = 0; r < G; r++) memcpy(col + 12 * r, slots + (r * 16 + j) * 12, 96);
+            uz::group_sum_jacobians(col, G, sums + 12 * j);
+        }
+        batch_to_affine(sums, k, out_aff);
         return UZKGE_OK;
     };
     // coefficient vectors of up to n + 3 entries over the Lagrange bases (helpers.rs:1363-1391, pcs.rs:139-163): with f = f_lo + X^n f_hi,
@@ -541,9 +664,51 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
         }
     };
 
+    // ---- group members: the quotient round by cosets.  The m = factor * n points k[1] w_m^p are the cosets g_j <w_n>, g_j = k[1] w_m^j,
+    // p = factor * i + j.  On coset j a polynomial of n + 3 coefficients is a size-n coset transform of its coefficients folded with
+    // X^n = g_j^n, and the map of a coset needs nothing from the other cosets: member r takes the cosets j = r mod G
+    std::vector<size_t> my_cosets;
+    if (grp)
+        for (size_t j = rank; j < P.factor; j += G) my_cosets.push_back(j);
+    // fs[i] on this member's cosets, written to positions j + factor * i' of the size-m vector outs[i]
+    auto eval_on_my_cosets = [&](const Poly* fs, u64* const* outs, size_t k) -> int {
+        if (k > 10) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: more than 10 polynomials per coset pass");
+        for (size_t j : my_cosets) {
+            const Limbs g = FR.mul(P.k1, fr_pow_u64(P.root_m, (u64)j));
+            const Limbs gn = fr_pow_u64(g, (u64)n);
+            u64 fold[8];
+            memcpy(fold, FR.one.data(), 32);
+            memcpy(fold + 4, gn.data(), 32);
+            const u64* ins[10];
+            u64* cs[10];
+            size_t lens[10], extra[10];
+            for (size_t i = 0; i < k; i++) {
+                extra[i] = fs[i].len > n ? fs[i].len - n : 0;
+                if (extra[i] > TAIL) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: a polynomial exceeds n + 8 coefficients");
+                if (extra[i]) {     // head coefficients += g^n * tail, restored after the transform
+                    u64* save = P.fold_save + 4 * TAIL * i;
+                    CU(cudaMemcpyAsync(save, fs[i].p, extra[i] * 32, cudaMemcpyDeviceToDevice, st));
+                    const void* two[2] = {fs[i].p, fs[i].p + 4 * n};
+                    const size_t two_len[2] = {extra[i], extra[i]};
+                    TRY(uzkge_cuda_fr_lincomb_device(two, two_len, fold, 2, fs[i].p, extra[i], st));
+                }
+                ins[i] = fs[i].p;
+                cs[i] = P.cbuf + 4 * n * i;
+                lens[i] = fs[i].len < n ? (fs[i].len ? fs[i].len : 1) : n;
+            }
+            TRY(ntt_many(P, ins, cs, lens, k, n, 0, g.data()));
+            proof->fft_n += (uint32_t)k;
+            for (size_t i = 0; i < k; i++) {
+                if (extra[i]) CU(cudaMemcpyAsync(fs[i].p, P.fold_save + 4 * TAIL * i, extra[i] * 32, cudaMemcpyDeviceToDevice, st));
+                TRY(uzkge_cuda_fr_strided_copy_device(cs[i], 0, 1, outs[i], j, P.factor, n, st));
+            }
+        }
+        return UZKGE_OK;
+    };
+
     // ---- 0. witness into HBM; 1. the PI polynomial (helpers.rs:111-131)
     if (a->witness_on_device)
-        CU(cudaMemcpyAsync(P.wit, a->witness, P.num_vars * 32, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(P.wit, a->witness, P.num_vars * 32, grp ? cudaMemcpyDefault : cudaMemcpyDeviceToDevice, st));
     else
         CU(cudaMemcpyAsync(P.wit, a->witness, P.num_vars * 32, cudaMemcpyHostToDevice, st));
     Poly pi{P.pi, n};
@@ -596,6 +761,21 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
     }
     // the quotient round's coset evaluations of these polynomials depend on no challenge: they run behind the MSMs
     auto wire_cosets = [&]() -> int {
+        if (grp) {
+            Poly fs[8];
+            u64* dst[8];
+            size_t kk = 0;
+            for (size_t i = 0; i < N_WIRES; i++) {
+                fs[kk] = w_polys[i];
+                dst[kk++] = P.coset[i];
+            }
+            if (shuffle)
+                for (size_t i = 0; i < 3; i++) {
+                    fs[kk] = w_sel_polys[i];
+                    dst[kk++] = P.w_sel_coset[i];
+                }
+            return eval_on_my_cosets(fs, dst, kk);
+        }
         const u64* ins[8];
         u64* outs[8];
         size_t lens[8], k = 0;
@@ -681,6 +861,7 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
         }
         TRY(flush_sparse());
         auto z_coset = [&]() -> int {
+            if (grp) return eval_on_my_cosets(&z_poly, &P.coset[6], 1);
             proof->coset_fft_m++;
             return coset_fft(P, z_poly, P.coset[6]);
         };
@@ -698,8 +879,12 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
     // ---- 6. alpha;  7. t = numerator / Z_H on the coset k[1] <w_m>, back to coefficients (helpers.rs:223-678)
     const Limbs alpha = tr.get_challenge_field_elem();
     if (P.n_public) {
-        TRY(coset_fft(P, pi, P.coset[5]));
-        proof->coset_fft_m++;
+        if (grp) {
+            TRY(eval_on_my_cosets(&pi, &P.coset[5], 1));
+        } else {
+            TRY(coset_fft(P, pi, P.coset[5]));
+            proof->coset_fft_m++;
+        }
     }
     u64* t_buf = P.coset[7];
     {
@@ -733,9 +918,31 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
                 sa.gen[i] = P.gen_coset[i];
             }
             memcpy(sa.edwards_a, P.edwards_a.data(), 32);
-            TRY(uzkge_cuda_plonk_quotient_shuffle_fr_device(&qa, &sa, t_buf, st));
+            if (grp) {
+                for (size_t j : my_cosets) TRY(uzkge_cuda_plonk_quotient_range_fr_device(&qa, &sa, j, P.factor, n, t_buf, st));
+            } else {
+                TRY(uzkge_cuda_plonk_quotient_shuffle_fr_device(&qa, &sa, t_buf, st));
+            }
+        } else if (grp) {
+            for (size_t j : my_cosets) TRY(uzkge_cuda_plonk_quotient_range_fr_device(&qa, nullptr, j, P.factor, n, t_buf, st));
         } else {
             TRY(uzkge_cuda_plonk_quotient_fr_device(&qa, t_buf, st));
+        }
+        if (grp) {
+            // exchange: every member sends its cosets (compact, n values each) into every other member's Params::tcos over peer
+            // memory, and fills the rest of its own size-m vector from what it receives
+            for (size_t j : my_cosets) {
+                TRY(uzkge_cuda_fr_strided_copy_device(t_buf, j, P.factor, P.tcos, j * n, 1, n, st));
+                for (size_t r = 0; r < G; r++) {
+                    if (r == rank) continue;
+                    Params* Q = grp->params[r];
+                    CU(cudaMemcpyPeerAsync(Q->tcos + 4 * j * n, Q->device, P.tcos + 4 * j * n, P.device, n * 32, st));
+                }
+            }
+            CU(cudaStreamSynchronize(st));
+            if (!grp->bar.wait()) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: another member of the device group failed");
+            for (size_t j = 0; j < P.factor; j++)
+                if (j % G != rank) TRY(uzkge_cuda_fr_strided_copy_device(P.tcos, j * n, 1, t_buf, j, P.factor, n, st));
         }
         TRY(uzkge_cuda_ntt_fr_device(t_buf, t_buf, P.scratch, m, m, 1, P.k1_inv.data(), st));
         proof->coset_ifft_m++;
@@ -1038,6 +1245,105 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_
     }
     if (tr.state.size() == 32) memcpy(proof->transcript_state, tr.state.data(), 32);
     proof->launches = (uint32_t)(uzkge_cuda_launch_count() - launches0);
+    return UZKGE_OK;
+}
+
+// the proof over a multi-device parameter handle: one worker thread per member
+int prove_group(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, const std::vector<u64>& subs) {
+    std::lock_guard<std::mutex> multi(uz::group_mutex());
+    Group grp;
+    const size_t G = subs.size();
+    grp.G = G;
+    grp.bar.members = (uint32_t)G;
+    if (a->srs) {
+        if (!uz::group_srs_parts_locked(a->srs, &grp.srs) || grp.srs.mode != UZKGE_MULTI_SPLIT || grp.srs.sub.size() != G)
+            return uz::api_fail(UZKGE_ERR_HANDLE, "plonk_prove: a multi-device parameter handle needs UZKGE_MULTI_SPLIT SRS handles over the same group");
+    }
+    if (a->lagrange_srs) {
+        if (!uz::group_srs_parts_locked(a->lagrange_srs, &grp.lag) || grp.lag.mode != UZKGE_MULTI_SPLIT || grp.lag.sub.size() != G)
+            return uz::api_fail(UZKGE_ERR_HANDLE, "plonk_prove: a multi-device parameter handle needs UZKGE_MULTI_SPLIT SRS handles over the same group");
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_params_mu);
+        for (u64 h : subs) {
+            auto it = g_params.find(h);
+            if (it == g_params.end()) return uz::api_fail(UZKGE_ERR_HANDLE, "plonk_prove: unknown parameter handle");
+            grp.params.push_back(it->second.get());
+        }
+    }
+    grp.partial.assign(2 * G * 16 * 12, 0);
+    std::vector<uzkge_plonk_proof> proofs(G);
+    const int rc = uz::group_fan_out(G, [&](size_t r) {
+        uzkge_plonk_prove_args mine = *a;
+        mine.params = subs[r];
+        const int rc_r = prove_impl(&mine, &proofs[r], &grp, r);
+        if (rc_r != UZKGE_OK) grp.bar.abort();
+        return rc_r;
+    });
+    if (rc != UZKGE_OK) return rc;
+    for (size_t r = 1; r < G; r++)
+        if (memcmp(proofs[r].transcript_state, proofs[0].transcript_state, 32) != 0)
+            return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: the members of the device group disagree on the transcript");
+    *proof = proofs[0];
+    return UZKGE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof) {
+    if (!a || !proof || !a->witness || !a->blinds || !a->transcript) return uz::api_fail(UZKGE_ERR_ARG, "plonk_prove: null pointer");
+    if (a->params & PARAMS_MULTI) {
+        std::vector<u64> subs;
+        {
+            std::lock_guard<std::mutex> lock(g_params_mu);
+            auto it = g_multi_params.find(a->params);
+            if (it == g_multi_params.end()) return uz::api_fail(UZKGE_ERR_HANDLE, "plonk_prove: unknown parameter handle");
+            subs = it->second;
+        }
+        return prove_group(a, proof, subs);
+    }
+    return prove_impl(a, proof, nullptr, 0);
+}
+
+UZKGE_API int32_t uzkge_cuda_plonk_params_upload_multi(const uzkge_plonk_params_desc* d, uint64_t* params_handle) {
+    if (!d || !params_handle) return uz::api_fail(UZKGE_ERR_ARG, "plonk_params_upload_multi: null pointer");
+    std::vector<int> devices;
+    {
+        std::lock_guard<std::mutex> multi(uz::group_mutex());
+        devices = uz::group_devices_locked();
+    }
+    if (devices.empty()) return uz::api_fail(UZKGE_ERR_NO_DEVICE, "plonk_params_upload_multi: call uzkge_cuda_init_devices first");
+    const size_t G = devices.size();
+    std::vector<u64> subs(G, 0);
+    int rc;
+    {
+        std::lock_guard<std::mutex> multi(uz::group_mutex());
+        rc = uz::group_fan_out(G, [&](size_t r) {
+            TRY(uzkge_cuda_set_device(devices[r]));
+            TRY(uzkge_cuda_plonk_params_upload(d, &subs[r]));
+            Params* Pp;
+            {
+                std::lock_guard<std::mutex> lock(g_params_mu);
+                Pp = g_params[subs[r]].get();
+            }
+            Params& P = *Pp;
+            TRY(dev_alloc(P, 10 * P.n, &P.cbuf, false));
+            TRY(dev_alloc(P, P.m, &P.tcos, false));
+            TRY(dev_alloc(P, 10 * TAIL, &P.fold_save, false));
+            return (int)UZKGE_OK;
+        });
+    }
+    if (rc != UZKGE_OK) {
+        for (u64 h : subs)
+            if (h) uzkge_cuda_plonk_params_free(h);
+        return rc;
+    }
+    std::lock_guard<std::mutex> lock(g_params_mu);
+    const u64 h = PARAMS_MULTI | g_params_next++;
+    g_multi_params[h] = subs;
+    *params_handle = h;
     return UZKGE_OK;
 }
 

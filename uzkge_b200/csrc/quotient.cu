@@ -30,6 +30,9 @@ struct QuotientDev {
     fe z_h_inv[16];
     uint64_t m;
     uint32_t factor;
+    // the points this launch covers: p = start + step * idx, idx < count (the whole domain: 0, 1, m; one coset g_j <w_n> of it:
+    // j, factor, n -- the omega-shifted point p + factor stays inside the coset and p % factor = j picks the coset's Z_H^-1)
+    uint64_t start, step, count;
     fe* out;
     // `shuffle` feature set (terms 12-18, helpers.rs:416-640); unused otherwise
     const fe* w_sel[3];
@@ -103,8 +106,9 @@ __device__ __noinline__ fe quotient_shuffle_terms(const QuotientDev& a, uint64_t
 
 template <int MIN_BLOCKS, bool SHUFFLE>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) plonk_quotient_kernel(const QuotientDev a) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.m) return;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.count) return;
+    const uint64_t p = a.start + a.step * idx;
     const uint64_t pn = (p + a.factor) % a.m;  // the omega-shifted point (helpers.rs:308, 349-351)
     const fe one = fe_one<FrP>();
     fe w[5];
@@ -179,8 +183,15 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) plonk_quotient_kernel(const Q
 }
 
 int plonk_quotient_run(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* sh, void* d_out, cudaStream_t st) {
+    return plonk_quotient_range_run(args, sh, 0, 1, args ? args->m : 0, d_out, st);
+}
+
+int plonk_quotient_range_run(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* sh, uint64_t start, uint64_t step,
+                             uint64_t count, void* d_out, cudaStream_t st) {
     if (!args || !d_out) return UZKGE_ERR_ARG;
     if (args->factor == 0 || args->factor > 16 || args->m == 0 || args->m % args->factor) return UZKGE_ERR_SIZE;
+    if (count == 0) return UZKGE_OK;
+    if (step == 0 || start >= args->m || (count - 1) > (args->m - 1 - start) / step) return UZKGE_ERR_SIZE;
     QuotientDev d;
     for (int j = 0; j < 5; j++) {
         d.w[j] = (const fe*)args->w[j];
@@ -232,7 +243,10 @@ int plonk_quotient_run(const uzkge_quotient_args* args, const uzkge_quotient_shu
     d.m = args->m;
     d.factor = (uint32_t)args->factor;
     d.out = (fe*)d_out;
-    const unsigned grid = (unsigned)((d.m + 127) / 128);
+    d.start = start;
+    d.step = step;
+    d.count = count;
+    const unsigned grid = (unsigned)((count + 127) / 128);
     if (sh)
         plonk_quotient_kernel<1, true><<<grid, 128, 0, st>>>(d);
     else if (g_quotient_min_blocks >= 4)

@@ -147,6 +147,10 @@ _SIGNATURES = {
     ),
     # the compiled prover (csrc/prover.cu); native.py declares the structures behind the void pointers
     "uzkge_cuda_plonk_params_upload": (C.c_int32, [C.c_void_p, u64p]),
+    "uzkge_cuda_plonk_params_upload_multi": (C.c_int32, [C.c_void_p, u64p]),
+    "uzkge_cuda_srs_upload_lagrange_commit_multi": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, u64p]),
+    "uzkge_cuda_plonk_quotient_range_fr_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_fr_strided_copy_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_plonk_params_set_public_key": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "uzkge_cuda_plonk_params_free": (C.c_int32, [C.c_uint64]),
     "uzkge_cuda_srs_upload_lagrange_commit": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, u64p]),

@@ -104,9 +104,11 @@ class NativeProver:
     cs, prover_params: a padded `plonk.TurboCS` and the `plonk.PlonkProverParams` `plonk.indexer` built for it (their coefficient forms
     are read back once and handed to uzkge_cuda_plonk_params_upload -- the same data the Rust struct holds on the host).
     pcs / lagrange_pcs: `KZGCommitmentSchemeBN254` over the monomial SRS / the size-n Lagrange SRS (None: monomial commitments only).
-    lagrange_all: commit everything over the Lagrange bases (None = decide from the SRS: on when the monomial SRS has holes below n)."""
+    lagrange_all: commit everything over the Lagrange bases (None = decide from the SRS: on when the monomial SRS has holes below n).
+    multi: ONE proof on every GPU of the device group (ffi.init_devices first): the parameters are uploaded to every member and the
+    SRS points split over them; `prove` is unchanged and returns the same bytes as the single-device prover."""
 
-    def __init__(self, cs, prover_params, pcs, lagrange_pcs=None, lagrange_all: bool | None = None):
+    def __init__(self, cs, prover_params, pcs, lagrange_pcs=None, lagrange_all: bool | None = None, multi: bool = False):
         from .plonk import unmont  # noqa: F401  (imported here: plonk imports torch)
 
         L = _lib()
@@ -176,16 +178,22 @@ class NativeProver:
                 put(d.q_shuffle_public_key_polys, d.pk_len, i, P.q_shuffle_public_key_polys[i])
             _fill4(d.edwards_a, _mont_limbs(vp.edwards_a, FR_MODULUS))
         h = C.c_uint64(0)
-        ffi.check(L.uzkge_cuda_plonk_params_upload(C.cast(C.pointer(d), C.c_void_p), C.byref(h)), ParameterError)
+        self.multi = bool(multi)
+        upload = L.uzkge_cuda_plonk_params_upload_multi if self.multi else L.uzkge_cuda_plonk_params_upload
+        ffi.check(upload(C.cast(C.pointer(d), C.c_void_p), C.byref(h)), ParameterError)
         self.handle = int(h.value)
         self._keep = []
         self.lagrange_handle = 0
+        self.srs_handle = self.pcs.handle if self.pcs is not None else 0
+        if self.multi and self.pcs is not None:
+            self.srs_handle = ffi.srs_upload_multi(pcs.public_parameter_group_1, ffi.MULTI_SPLIT, getattr(pcs, "window_bits", 0))
         if lagrange_pcs is not None:
             lag_pts = ffi.as_u64(lagrange_pcs.public_parameter_group_1, 8)
             mono = ffi.as_u64(pcs.public_parameter_group_1, 8)
             lh = C.c_uint64(0)
-            ffi.check(L.uzkge_cuda_srs_upload_lagrange_commit(ffi.ptr(lag_pts), self.n, ffi.ptr(mono), mono.shape[0],
-                                                              getattr(lagrange_pcs, "window_bits", 0), C.byref(lh)), ParameterError)
+            up = L.uzkge_cuda_srs_upload_lagrange_commit_multi if self.multi else L.uzkge_cuda_srs_upload_lagrange_commit
+            ffi.check(up(ffi.ptr(lag_pts), self.n, ffi.ptr(mono), mono.shape[0], getattr(lagrange_pcs, "window_bits", 0), C.byref(lh)),
+                      ParameterError)
             self.lagrange_handle = int(lh.value)
         self.last_stats: dict = {}
         self._sel_cache = None
@@ -224,7 +232,7 @@ class NativeProver:
             raw = fr_rand_mont(prng)
             blinds[j] = [(raw >> (64 * i)) & _M64 for i in range(4)]
         a = PlonkProveArgs()
-        a.params, a.srs, a.lagrange_srs = self.handle, (self.pcs.handle if self.pcs is not None else 0), self.lagrange_handle
+        a.params, a.srs, a.lagrange_srs = self.handle, self.srs_handle, self.lagrange_handle
         a.lagrange_all = 1 if self.lagrange_all else 0
         a.witness_on_device = 1 if on_device else 0
         a.witness = w_ptr
@@ -269,6 +277,9 @@ class NativeProver:
         if getattr(self, "lagrange_handle", 0):
             ffi.srs_free(self.lagrange_handle)
             self.lagrange_handle = 0
+        if getattr(self, "multi", False) and getattr(self, "srs_handle", 0):
+            ffi.srs_free(self.srs_handle)
+            self.srs_handle = 0
 
     def __del__(self):
         try:
