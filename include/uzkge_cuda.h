@@ -388,6 +388,10 @@ UZKGE_API int32_t uzkge_cuda_plonk_prove(const uzkge_plonk_prove_args* args, uzk
  * out = a + b on Jacobian points (host pointers, tiny device kernel).  Used for the G - 1 projective adds
  * that merge per-GPU partial sums. */
 UZKGE_API int32_t uzkge_cuda_g1_add(const uint64_t a_jac[12], const uint64_t b_jac[12], uint64_t out_jac[12]);
+/* d_out[j] = sum_{r < count} d_parts[r * stride + j], j < k (Jacobian, 12 words each; DEVICE pointers, caller's stream, no sync; d_out
+ * may alias the first k parts): the combine step after the k partial sums of every GPU of a point-split MSM batch were gathered
+ * rank-major (NCCL all-gather of k * 96 bytes per GPU). */
+UZKGE_API int32_t uzkge_cuda_g1_sum_device(const void* d_parts_jac, size_t count, size_t stride, size_t k, void* d_out_jac, void* stream);
 /* Jacobian -> affine (x = y = 0 for the identity): the normalisation `into_affine` performs before a
  * commitment is serialised (kzg_poly_commitment.rs:37-53). */
 UZKGE_API int32_t uzkge_cuda_g1_to_affine(const uint64_t in_jac[12], uint64_t out_affine[8]);

@@ -384,3 +384,30 @@ def test_largest_size_against_the_trapdoor(gpu, oc):
         assert same_point(oc, gpu.msm_g1(h, f), want)
     finally:
         gpu.srs_free(h)
+
+
+def test_partial_sums_are_combined_on_the_device(gpu, oc):
+    """uzkge_cuda_g1_sum_device: out[j] = sum_r parts[r * stride + j] -- the N - 1 projective additions after the all-gather of a
+    point-split MSM batch -- against the oracle's Jacobian addition, with identity and repeated points among the parts."""
+    import torch
+
+    pts = oc.g1_random_points(12, 9100)
+    one = oc.fq_to_mont(np.array([[1, 0, 0, 0]], dtype=np.uint64))[0]
+    jac = np.zeros((4, 3, 12), dtype=np.uint64)                   # 4 "ranks" x 3 results
+    for r in range(4):
+        for j in range(3):
+            jac[r, j, :8] = pts[3 * r + j]
+            jac[r, j, 8:] = one
+    jac[1, 0] = 0                                                 # the identity (Z = 0)
+    jac[2, 1] = jac[0, 1]                                         # P + P inside the sum
+    d = torch.from_numpy(jac.view(np.int64).reshape(-1)).cuda()
+    out = torch.zeros(3 * 12, dtype=torch.int64, device="cuda")
+    gpu.g1_sum_device(d.data_ptr(), 4, out.data_ptr(), 0, k=3)
+    got = out.cpu().numpy().view(np.uint64).reshape(3, 12)
+    for j in range(3):
+        acc = jac[0, j]
+        for r in range(1, 4):
+            acc = oc.g1_add_jac(acc, jac[r, j])
+        assert np.array_equal(oc.g1_to_affine(got[j]), oc.g1_to_affine(acc)), j
+    gpu.g1_sum_device(d.data_ptr(), 1, out.data_ptr(), 0)          # a single part: a copy
+    assert np.array_equal(oc.g1_to_affine(out.cpu().numpy().view(np.uint64)[:12]), oc.g1_to_affine(jac[0, 0]))

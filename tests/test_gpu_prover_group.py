@@ -42,12 +42,13 @@ def _prove_both(cs, params, pcs, lagrange, lagrange_all, label=b"group", seed=by
     return out
 
 
-@pytest.mark.parametrize("members", [2, 3, 8])
+@pytest.mark.parametrize("members", [0, 2, 3, 8])
 def test_group_proof_equals_single_device_proof(gpu, members):
+    """members = 0: the real GPUs of the box (a group of one on a one-GPU box, NVLink peers under gpurun --gpus N)."""
     from uzkge_b200 import KZGCommitmentSchemeBN254, plonk
 
     try:
-        assert _group(gpu, members) == members
+        assert _group(gpu, members) == (members or gpu.device_count())
         for n_gates, n_public, n_boolean in ((100, 3, 2), (900, 0, 0)):
             cs = build_circuit(plonk.TurboCS(), n_gates, 40 + n_gates, n_public, n_boolean)
             pcs = KZGCommitmentSchemeBN254.new(cs.size + 2, plonk.mont(TAU))

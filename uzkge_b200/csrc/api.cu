@@ -849,6 +849,14 @@ UZKGE_API int32_t uzkge_cuda_g1_add(const uint64_t a_jac[12], const uint64_t b_j
     return UZKGE_OK;
 }
 
+UZKGE_API int32_t uzkge_cuda_g1_sum_device(const void* d_parts_jac, size_t count, size_t stride, size_t k, void* d_out_jac, void* stream) {
+    if (!d_parts_jac || !d_out_jac) return fail(UZKGE_ERR_ARG, "g1_sum_device: null pointer");
+    if (count == 0 || count > 1024 || k == 0 || k > (1u << 20) || stride < k) return fail(UZKGE_ERR_SIZE, "g1_sum_device: 1 <= count <= 1024, 1 <= k <= stride");
+    API_ENTER(-1);
+    return engine_fail(g.msm->g1_sum((const jacobian*)d_parts_jac, (uint32_t)count, (uint32_t)stride, (uint32_t)k, (jacobian*)d_out_jac, (cudaStream_t)stream),
+                       "g1_sum_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_g1_to_affine(const uint64_t in_jac[12], uint64_t out_affine[8]) {
     if (!in_jac || !out_affine) return fail(UZKGE_ERR_ARG, "g1_to_affine: null pointer");
     API_ENTER(-1);

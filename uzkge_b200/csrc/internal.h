@@ -212,6 +212,7 @@ public:
     int run_pipelined(MsmSrs* s, size_t base_offset, const fe* const* d_scalars, const size_t* n, size_t k, jacobian* d_out,
                       cudaStream_t st, const cudaEvent_t* ready = nullptr);
     int g1_add(const jacobian* d_a, const jacobian* d_b, jacobian* d_out, cudaStream_t st);
+    int g1_sum(const jacobian* d_parts, uint32_t count, uint32_t stride, uint32_t k, jacobian* d_out, cudaStream_t st);
     int g1_to_affine(const jacobian* d_in, affine* d_out, cudaStream_t st);
     int powers_of_tau(const fe& tau, uint64_t first, uint32_t count, affine* d_out, cudaStream_t st);
     int fixed_base_mul(const fe* d_scalars, uint32_t count, affine* d_out, cudaStream_t st);

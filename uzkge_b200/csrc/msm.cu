@@ -303,6 +303,21 @@ __global__ void g1_add_kernel(const jacobian* a, const jacobian* b, jacobian* ou
     st_fe(&out->y, j.y);
     st_fe(&out->z, j.z);
 }
+// out[j] = sum_{r < count} parts[r * stride + j], j < k: the N - 1 projective additions that merge per-GPU partial sums (k results of
+// a batch, gathered rank-major), without leaving the device
+__global__ void g1_sum_kernel(const jacobian* parts, uint32_t count, uint32_t stride, uint32_t k, jacobian* out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    xyzz acc = jacobian_to_xyzz(ld_jacobian(parts + j));
+    for (uint32_t i = 1; i < count; i++) {
+        const xyzz y = jacobian_to_xyzz(ld_jacobian(parts + (size_t)i * stride + j));
+        xyzz_add(acc, y);
+    }
+    const jacobian r = xyzz_to_jacobian(acc);
+    st_fe(&out[j].x, r.x);
+    st_fe(&out[j].y, r.y);
+    st_fe(&out[j].z, r.z);
+}
 __global__ void g1_to_affine_kernel(const jacobian* in, affine* out) {
     const affine r = xyzz_to_affine(jacobian_to_xyzz(ld_jacobian(in)));
     st_affine(out, r);
@@ -922,6 +937,13 @@ int MsmEngine::small_msm(const MsmSrs* s, const size_t* idx, const uint64_t* sca
 
 int MsmEngine::g1_add(const jacobian* d_a, const jacobian* d_b, jacobian* d_out, cudaStream_t st) {
     g1_add_kernel<<<1, 1, 0, st>>>(d_a, d_b, d_out);
+    UZ_COUNT_LAUNCH(1);
+    UZ_CUDA_TRY(cudaGetLastError());
+    return UZKGE_OK;
+}
+int MsmEngine::g1_sum(const jacobian* d_parts, uint32_t count, uint32_t stride, uint32_t k, jacobian* d_out, cudaStream_t st) {
+    if (count == 0 || k == 0) return UZKGE_ERR_SIZE;
+    g1_sum_kernel<<<(k + 31) / 32, 32, 0, st>>>(d_parts, count, stride, k, d_out);
     UZ_COUNT_LAUNCH(1);
     UZ_CUDA_TRY(cudaGetLastError());
     return UZKGE_OK;

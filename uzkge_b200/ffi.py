@@ -156,6 +156,7 @@ _SIGNATURES = {
     "uzkge_cuda_srs_upload_lagrange_commit": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, u64p]),
     "uzkge_cuda_plonk_prove": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "uzkge_cuda_g1_add": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_g1_sum_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_g1_to_affine": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "uzkge_cuda_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "uzkge_cuda_host_free": (C.c_int32, [C.c_void_p]),
@@ -607,6 +608,11 @@ def plonk_z_evals_fr_device(d_w, d_sigma, d_group: int, k, beta, gamma, n: int, 
     assert kk.shape[0] == 5
     check(lib().uzkge_cuda_plonk_z_evals_fr_device(ww, ss, d_group, ptr(kk), ptr(as_u64(beta).reshape(4)), ptr(as_u64(gamma).reshape(4)),
                                                    n, d_z, d_tmp, stream))
+
+
+def g1_sum_device(d_parts: int, count: int, d_out: int, stream: int = 0, k: int = 1, stride: int | None = None) -> None:
+    """d_out[j] = sum_r d_parts[r * stride + j], j < k (device pointers to Jacobian points): the combine of gathered per-GPU partial sums."""
+    check(lib().uzkge_cuda_g1_sum_device(d_parts, count, k if stride is None else stride, k, d_out, stream), CommitmentError)
 
 
 def g1_add(a_jac, b_jac) -> np.ndarray:
