@@ -177,6 +177,13 @@ UZKGE_API int32_t uzkge_cuda_ntt_cross_rows_fr_device(const void* const* d_in_ro
  * cudaIpcOpenMemHandle.  `handle` is 64 opaque bytes to ship through any host channel (torch.distributed all_gather_object). */
 UZKGE_API int32_t uzkge_cuda_dev_alloc(size_t bytes, void** d_ptr);
 UZKGE_API int32_t uzkge_cuda_dev_free(void* d_ptr);
+/* The local size-n transform of a distributed four-step transform with the NATURAL output order folded into its final store: rank
+ * `rank` of 2^log_ranks holds, after the cross step, row k1 = rank; output k2 of its size-n transform is X[k1 + G k2] of the whole
+ * transform and is written straight into its owner's contiguous slice, d_out_rows[k2 / (n / G)] + k1 + G (k2 mod n / G), over peer
+ * memory -- no third exchange.  d_in: n elements (left intact: the passes work in d_scratch, n elements); d_out_rows: HOST array of G
+ * device pointers (peer mappings). */
+UZKGE_API int32_t uzkge_cuda_ntt_fr_scatter_device(const void* d_in, void* const* d_out_rows, void* d_scratch, size_t n, int32_t inverse,
+                                                   uint32_t log_ranks, uint32_t rank, void* stream);
 /* Synchronous host <-> device copies for callers without their own CUDA binding (the Rust crate, the C++ host layer): ordered with
  * the *_device entry points called with stream = NULL.  What `Vec<Fr>` <-> device buffer conversions of a device-resident
  * prover_with_lagrange (plonk/prover.rs:88-394) need at its ends. */

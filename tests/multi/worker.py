@@ -61,8 +61,13 @@ for lg in (16, 22):
     peer = udist.PeerNtt(n, rank, world, dev)
     peer.x_view.copy_(mine)
     okp = np.array_equal(to_np(peer.transform()), want[rank::world])
-    peer.close()
     checks[f"ntt_four_step_peer_memory_2^{lg}_vs_oracle"] = agree(okp)
+    # natural output folded into the local transform's final store over peer memory (no third exchange), forward and back
+    okn = np.array_equal(to_np(peer.transform_natural()), want[rank * L:(rank + 1) * L])
+    peer.x_view.copy_(peer.y_view)
+    okn = okn and bool(torch.equal(peer.transform_natural(inverse=True), mine))
+    peer.close()
+    checks[f"ntt_four_step_peer_memory_natural_output_2^{lg}_vs_oracle"] = agree(okn)
 
 # 2. the point-split MSM against the oracle (2^16) and against the single-GPU MSM (2^20)
 for lg in (16, 20):

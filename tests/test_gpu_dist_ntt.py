@@ -79,6 +79,36 @@ def test_peer_fused_cross_step_matches_oracle(gpu, oc, world, log_n):
             assert np.array_equal(outs[r], ref[r::world]), (inverse, r)
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("log_n", [6, 13, 18, 22])
+def test_natural_output_folded_into_the_final_store(gpu, oc, world, log_n):
+    """uzkge_cuda_ntt_fr_scatter_device: the local transform of the four-step whose last pass writes every output into its OWNER's
+    natural slice (dist.PeerNtt.transform_natural does this over peer memory: no third exchange).  Ranks emulated on one GPU:
+    the "peer" slices are buffers of the same device.  Forward and inverse, against the oracle's single transform."""
+    if log_n == 22 and world != 8:
+        pytest.skip("the full size once")
+    n = 1 << log_n
+    L, S, log_g = n // world, n // world // world, world.bit_length() - 1
+    x = oc.random_fr(n, 80 + log_n + world)
+    want = oc.ntt_fr(x, n) if log_n < 20 else gpu.ntt_fr(x, n)
+    for inverse in (False, True):
+        src = want if inverse else x
+        ref = x if inverse else want
+        xs = [to_dev(src[r * L:(r + 1) * L]) for r in range(world)]
+        rows = [torch.zeros(4 * L, dtype=torch.int64, device="cuda") for _ in range(world)]
+        for r in range(world):
+            off = 32 * r * S
+            gpu.ntt_cross_rows_fr_device([t.data_ptr() + off for t in xs], [t.data_ptr() + off for t in rows], log_g, S, r * S, n, inverse)
+        nat = [torch.zeros(4 * L, dtype=torch.int64, device="cuda") for _ in range(world)]
+        scr = torch.empty(4 * L, dtype=torch.int64, device="cuda")
+        for r in range(world):
+            keep = rows[r].clone()
+            gpu.ntt_fr_scatter_device(rows[r].data_ptr(), [t.data_ptr() for t in nat], scr.data_ptr(), L, inverse, log_g, r)
+            assert torch.equal(rows[r], keep)                # the input is left intact
+        got = np.concatenate([to_np(t) for t in nat])
+        assert np.array_equal(got, ref), inverse
+
+
 def test_ipc_export_of_library_buffers(gpu):
     """Buffers from uzkge_cuda_dev_alloc can be exported for other processes (dist.PeerNtt maps them on the peer GPUs; opening
     a handle needs a second process, covered by scripts/dist_check.py under torchrun)."""

@@ -560,6 +560,26 @@ UZKGE_API int32_t uzkge_cuda_ntt_cross_rows_fr_device(const void* const* d_in_ro
     return engine_fail(rc, "ntt_cross_rows_fr_device");
 }
 
+UZKGE_API int32_t uzkge_cuda_ntt_fr_scatter_device(const void* d_in, void* const* d_out_rows, void* d_scratch, size_t n, int32_t inverse,
+                                                   uint32_t log_ranks, uint32_t rank, void* stream) {
+    if (!d_in || !d_out_rows || !d_scratch) return fail(UZKGE_ERR_ARG, "ntt_fr_scatter_device: null pointer");
+    if (log_ranks < 1 || log_ranks > 3 || rank >= (1u << log_ranks)) return fail(UZKGE_ERR_SIZE, "ntt_fr_scatter_device: 2, 4 or 8 ranks");
+    API_ENTER(-1);
+    NttScatter sc;
+    for (uint32_t r = 0; r < 8; r++) {
+        sc.rows[r] = r < (1u << log_ranks) ? (fe*)d_out_rows[r] : nullptr;
+        if (r < (1u << log_ranks) && !sc.rows[r]) return fail(UZKGE_ERR_ARG, "ntt_fr_scatter_device: null row pointer");
+    }
+    sc.log_g = log_ranks;
+    sc.k1 = rank;
+    const fe* in = (const fe*)d_in;
+    fe* out = (fe*)d_scratch;             // unused by the scattering last pass (the earlier passes work in the scratch vector)
+    const uint64_t len = n;
+    int rc = g.ntt->run_batch(&in, &out, (fe*)d_scratch, &len, 1, n, inverse != 0, nullptr, (cudaStream_t)stream, &sc);
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "ntt_fr_scatter_device: n must be a power of two, at least the number of ranks");
+    return engine_fail(rc, "ntt_fr_scatter_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_dev_alloc(size_t bytes, void** d_ptr) {
     if (!d_ptr) return fail(UZKGE_ERR_ARG, "dev_alloc: null pointer");
     API_ENTER(-1);

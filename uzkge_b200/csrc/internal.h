@@ -111,6 +111,13 @@ struct NttCoset {
 
 static constexpr uint32_t NTT_MAX_BATCH = 16;
 
+// the last pass of a distributed transform's local step stores into the owners' natural slices (peer memory): see ntt.cu
+struct NttScatter {
+    fe* rows[8];        // rank r's natural output slice (n elements each)
+    uint32_t log_g;     // log2 of the number of ranks
+    uint32_t k1;        // this rank
+};
+
 class NttEngine {
 public:
     explicit NttEngine(int sm_count) : sm_count_(sm_count) {}
@@ -125,7 +132,7 @@ public:
             cudaStream_t st);
     // k <= NTT_MAX_BATCH vectors over one domain, one launch per pass (blockIdx.y = vector); d_scratch: k * n elements
     int run_batch(const fe* const* d_in, fe* const* d_out, fe* d_scratch, const uint64_t* len_in, uint32_t k, uint64_t n, bool inverse,
-                  const fe* coset_shift, cudaStream_t st);
+                  const fe* coset_shift, cudaStream_t st, const NttScatter* scatter = nullptr);
     // cross-rank step of a distributed transform (see ntt.cu)
     int cross(const fe* d_in, fe* d_out, uint32_t log_g, uint64_t cols, uint64_t col_offset, uint64_t n_total, bool inverse,
               cudaStream_t st);

@@ -80,9 +80,14 @@ struct NttKernelArgs {
     const fe* tw_pass;  // inter-pass twiddles of this pass, one entry per output position (resident in HBM)
     fe scale;        // 1/N (inverse without coset)
     uint32_t inverse, pre_coset, post_coset, has_scale, zero_pad;
+    // SCATTER instantiation only (the local transform of a distributed four-step, rank k1 of G = 2^scatter_log_g): the last pass stores
+    // output k2 of this size-L transform -- X[k1 + G k2] of the whole transform -- straight into its owner's natural slice over peer
+    // memory: rank k2 >> scatter_shift (scatter_shift = log2(L / G)), position k1 + G (k2 mod L / G).  No third exchange.
+    fe* scatter_rows[8];
+    uint32_t scatter_log_g, scatter_shift, scatter_k1;
 };
 
-template <int NT>
+template <int NT, bool SCATTER>
 __global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
     extern __shared__ uint4 ntt_smem[];
     const NttPass& p = a.p;
@@ -163,7 +168,13 @@ __global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
             else if (a.has_scale)
                 x = fe_mul<FrP>(x, a.scale);
         }
-        st_fe(out + g, x);
+        if (SCATTER && p.last) {
+            const uint64_t owner = g >> a.scatter_shift;
+            const uint64_t pos = a.scatter_k1 + ((g & ((1ull << a.scatter_shift) - 1)) << a.scatter_log_g);
+            st_fe(a.scatter_rows[owner] + pos, x);
+        } else {
+            st_fe(out + g, x);
+        }
     }
 }
 
@@ -419,7 +430,7 @@ const NttCoset* NttEngine::coset(uint64_t n, const fe& g, bool with_ninv, const 
     return &cosets_.back();
 }
 
-template <int NT>
+template <int NT, bool SCATTER = false>
 static cudaError_t launch_pass(const NttKernelArgs& ka, uint32_t k, cudaStream_t st) {
     const NttPass& p = ka.p;
     const size_t T = (size_t)1 << (p.logR + p.logC);
@@ -428,12 +439,12 @@ static cudaError_t launch_pass(const NttKernelArgs& ka, uint32_t k, cudaStream_t
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > 48 * 1024 && smem > configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<NT, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
         if (e != cudaSuccess) return e;
         configured[dev] = 200 * 1024;
     }
     const uint32_t grid = p.inner_tiles * p.outer * p.batch;
-    ntt_pass_kernel<NT><<<dim3(grid, k), NT, smem, st>>>(ka);
+    ntt_pass_kernel<NT, SCATTER><<<dim3(grid, k), NT, smem, st>>>(ka);
     UZ_COUNT_LAUNCH(1);
     return cudaGetLastError();
 }
@@ -449,9 +460,11 @@ int NttEngine::run(const fe* d_in, fe* d_out, fe* d_scratch, uint64_t len_in, ui
 // The prover's rounds transform 5-8 polynomials of 2^13..2^14 coefficients at a time: one such vector is 16 tiles, i.e. a tenth of
 // the GPU's SMs, and its passes are launch-bound.
 int NttEngine::run_batch(const fe* const* d_in, fe* const* d_out, fe* d_scratch, const uint64_t* len_in, uint32_t k, uint64_t n, bool inverse,
-                         const fe* coset_shift, cudaStream_t st) {
+                         const fe* coset_shift, cudaStream_t st, const NttScatter* scatter) {
     if (k == 0) return UZKGE_OK;
     if (k > NTT_MAX_BATCH) return UZKGE_ERR_SIZE;
+    if (scatter && (k != 1 || scatter->log_g < 1 || scatter->log_g > 3 || (n & (n - 1)) || (n >> scatter->log_g) == 0 || scatter->k1 >= (1u << scatter->log_g)))
+        return UZKGE_ERR_SIZE;
     const NttDomain* d = domain(n, st);
     if (!d) return UZKGE_ERR_SIZE;
     bool any_pad = false;
@@ -513,13 +526,31 @@ int NttEngine::run_batch(const fe* const* d_in, fe* const* d_out, fe* d_scratch,
         ka.pre_coset = (!input_consumed && cs && !inverse) ? 1 : 0;
         ka.post_coset = (ka.p.last && cs && inverse) ? 1 : 0;
         ka.has_scale = (ka.p.last && inverse && !cs) ? 1 : 0;
+        const bool scat = scatter && ka.p.last;
+        if (scat) {
+            uint32_t lg = 0;
+            while ((1ull << lg) < n) lg++;
+            for (uint32_t r = 0; r < 8; r++) ka.scatter_rows[r] = r < (1u << scatter->log_g) ? scatter->rows[r] : nullptr;
+            ka.scatter_log_g = scatter->log_g;
+            ka.scatter_shift = lg - scatter->log_g;
+            ka.scatter_k1 = scatter->k1;
+        }
         // a single-tile last pass may run in place; a multi-tile last pass transposes and must not alias
-        if (ka.p.last && (ka.p.inner_tiles * ka.p.outer * ka.p.batch) > 1)
+        if (!scat && ka.p.last && (ka.p.inner_tiles * ka.p.outer * ka.p.batch) > 1)
             for (uint32_t j = 0; j < k; j++)
                 if (ka.jobs.in[j] == ka.jobs.out[j]) return UZKGE_ERR_INTERNAL;
         const uint32_t T = 1u << (ka.p.logR + ka.p.logC);
         cudaError_t e;
-        if (T >= 4096 && cfg_big_threads_ == 1024)
+        if (scat) {
+            if (T >= 4096 && cfg_big_threads_ == 1024)
+                e = launch_pass<1024, true>(ka, k, st);
+            else if (T >= 2048)
+                e = launch_pass<512, true>(ka, k, st);
+            else if (T >= 512)
+                e = launch_pass<256, true>(ka, k, st);
+            else
+                e = launch_pass<64, true>(ka, k, st);
+        } else if (T >= 4096 && cfg_big_threads_ == 1024)
             e = launch_pass<1024>(ka, k, st);
         else if (T >= 2048)
             e = launch_pass<512>(ka, k, st);

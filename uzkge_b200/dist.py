@@ -202,11 +202,12 @@ class PeerNtt:
         self.L, self.S, self.log_g = _check_dist_sizes(n_total, world)
         nbytes = 32 * self.L
         self.x, self.rows, self.y, self.scratch = (ffi.dev_alloc(nbytes) for _ in range(4))
-        mine = (ffi.ipc_export(self.x), ffi.ipc_export(self.rows))
+        mine = (ffi.ipc_export(self.x), ffi.ipc_export(self.rows), ffi.ipc_export(self.y))
         handles = [None] * world
         dist.all_gather_object(handles, mine, group=group)
         self.peer_x = [self.x if r == rank else ffi.ipc_open(handles[r][0]) for r in range(world)]
         self.peer_rows = [self.rows if r == rank else ffi.ipc_open(handles[r][1]) for r in range(world)]
+        self.peer_y = [self.y if r == rank else ffi.ipc_open(handles[r][2]) for r in range(world)]
         self.x_view = torch.as_tensor(_RawDeviceArray(self.x, 4 * self.L), device=device)
         self.y_view = torch.as_tensor(_RawDeviceArray(self.y, 4 * self.L), device=device)
         self._flag = torch.zeros(1, dtype=torch.float32, device=device)
@@ -226,6 +227,19 @@ class PeerNtt:
         ffi.ntt_fr_device(self.rows, self.y, self.scratch, self.L, self.L, inverse, None)
         return self.y_view
 
+    def transform_natural(self, inverse: bool = False):
+        """The same transform with NATURAL output: `y_view` of rank r receives X[r L .. (r + 1) L).  The local transform's last pass
+        stores every output straight into its owner's slice over peer memory (uzkge_cuda_ntt_fr_scatter_device): no third exchange,
+        one more stream-ordered barrier so that every rank's stores have landed before the result is read."""
+        off = 32 * self.rank * self.S
+        self._barrier()
+        ffi.ntt_cross_rows_fr_device([p + off for p in self.peer_x], [p + off for p in self.peer_rows], self.log_g, self.S,
+                                     self.rank * self.S, self.n_total, inverse)
+        self._barrier()
+        ffi.ntt_fr_scatter_device(self.rows, self.peer_y, self.scratch, self.L, inverse, self.log_g, self.rank)
+        self._barrier()
+        return self.y_view
+
     def close(self):
         import torch
         import torch.distributed as dist
@@ -236,6 +250,7 @@ class PeerNtt:
             if r != self.rank:
                 ffi.ipc_close(self.peer_x[r])
                 ffi.ipc_close(self.peer_rows[r])
+                ffi.ipc_close(self.peer_y[r])
         dist.barrier(group=self.group)
         for p in (self.x, self.rows, self.y, self.scratch):
             ffi.dev_free(p)

@@ -111,6 +111,7 @@ _SIGNATURES = {
         C.c_int32,
         [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p],
     ),
+    "uzkge_cuda_ntt_fr_scatter_device": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "uzkge_cuda_dev_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "uzkge_cuda_dev_free": (C.c_int32, [C.c_void_p]),
     "uzkge_cuda_dev_copy_in": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -439,6 +440,12 @@ def ntt_cross_fr_device(d_in: int, d_out: int, log_ranks: int, cols: int, col_of
                         inverse: bool = False, stream: int = 0) -> None:
     check(lib().uzkge_cuda_ntt_cross_fr_device(d_in, d_out, log_ranks, cols, col_offset, n_total, 1 if inverse else 0, stream),
           FFTError)
+
+
+def ntt_fr_scatter_device(d_in: int, d_out_rows, d_scratch: int, n: int, inverse: bool, log_ranks: int, rank: int, stream: int = 0) -> None:
+    """The local transform of a distributed four-step whose last pass stores into the owners' natural slices (peer memory)."""
+    rows = (C.c_void_p * len(d_out_rows))(*d_out_rows)
+    check(lib().uzkge_cuda_ntt_fr_scatter_device(d_in, rows, d_scratch, n, 1 if inverse else 0, log_ranks, rank, stream), FFTError)
 
 
 def ntt_cross_rows_fr_device(d_in_rows, d_out_rows, log_ranks: int, cols: int, col_offset: int, n_total: int,
