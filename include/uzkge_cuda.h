@@ -255,6 +255,13 @@ UZKGE_API int32_t uzkge_cuda_plonk_quotient_shuffle_fr_device(const uzkge_quotie
 UZKGE_API int32_t uzkge_cuda_plonk_quotient_range_fr_device(const uzkge_quotient_args* args, const uzkge_quotient_shuffle_args* shuffle,
                                                             uint64_t start, uint64_t step, uint64_t count, void* d_out, void* stream);
 
+/* The inverse of that split: d_u holds, for every coset j < factor, u_j = the size-n coset iFFT (shift g_j^-1) of the quotient's values
+ * on coset j (compact, u_j at [j n, (j + 1) n)); d_out receives the factor * n coefficients of t -- what coset_ifft_with_domain over the
+ * whole 6n domain (helpers.rs:673-677) returns.  Per coefficient index r a factor-point inverse DFT over the cosets (11 products for
+ * factor = 6).  k1: the quotient coset's shift k[1] (host, Montgomery).  d_out must not alias d_u. */
+UZKGE_API int32_t uzkge_cuda_plonk_coset_combine_fr_device(const void* d_u, size_t n, size_t factor, const uint64_t k1_host[4], void* d_out,
+                                                           void* stream);
+
 /* ---- elementwise glue of a device-resident prover; DEVICE pointers, caller's stream, no copies, no sync ------
  * out[i] = sum_{j < k} coefs[j] * polys[j][i] for i < out_len, where polys[j][i] = 0 for i >= lens[j]; coefs: k Montgomery Fr on
  * the HOST.  Replaces the mul / add_assign chains of r_poly_or_comm (plonk/helpers.rs:716-745, 986-993) and of batch_prove

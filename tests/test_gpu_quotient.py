@@ -124,3 +124,62 @@ def test_quotient_pipeline_divisibility(gpu, oc, bn):
     torch.cuda.synchronize()
     t_bad = FpPolynomial.coset_ifft_with_domain(dom_m, out.cpu().numpy().view(np.uint64).reshape(m, 4), k1_inv)
     assert t_bad.degree() >= 5 * n
+
+
+@pytest.mark.parametrize("n,factor", [(8, 16), (64, 6), (2048, 6)])
+def test_quotient_map_coset_by_coset(gpu, oc, bn, n, factor):
+    """uzkge_cuda_plonk_quotient_range_fr_device on (start, step, count) = (j, factor, n) -- the coset g_j <w_n> of the quotient domain,
+    the unit by which a device group splits the round: the `factor` coset launches together write exactly what the whole-domain launch
+    writes, and each touches only its own points."""
+    m = n * factor
+    arrays, seed = {}, 300
+    for name, cnt in (("w", 5), ("q", 9), ("s", 5), ("q_prk", 4)):
+        arrays[name] = [dev(oc.random_fr(m, seed + i)) for i in range(cnt)]
+        seed += cnt
+    for name in ("pi", "z", "coset_quotient", "l1", "qb"):
+        arrays[name] = dev(oc.random_fr(m, seed))
+        seed += 1
+    sc = oc.random_fr(5, 998)
+    zh = oc.random_fr(factor, 78)
+    k = bn.ints_to_array(K, bn.FR)
+    ptr = lambda t: t.data_ptr()
+
+    def run(out, point_range=None):
+        gpu.plonk_quotient_fr_device(
+            [ptr(t) for t in arrays["w"]], [ptr(t) for t in arrays["q"]], ptr(arrays["pi"]), ptr(arrays["z"]), [ptr(t) for t in arrays["s"]],
+            ptr(arrays["coset_quotient"]), ptr(arrays["l1"]), ptr(arrays["qb"]), [ptr(t) for t in arrays["q_prk"]], k, sc[0], sc[1], sc[2],
+            sc[3], oc.fr_inv(sc[3]), zh, m, factor, out.data_ptr(), point_range=point_range)
+
+    whole = torch.empty(4 * m, dtype=torch.int64, device="cuda")
+    run(whole)
+    parts = torch.full((4 * m,), -1, dtype=torch.int64, device="cuda")
+    for j in range(factor):
+        before = parts.clone()
+        run(parts, (j, factor, n))
+        changed = (parts.view(m, 4) != before.view(m, 4)).any(dim=1).nonzero().flatten()
+        assert bool(((changed % factor) == j).all())                 # only coset j's points were written
+    assert torch.equal(parts, whole)
+    with pytest.raises(Exception):
+        run(parts, (1, factor, n + 1))                               # runs past the domain
+
+
+@pytest.mark.parametrize("log_n,factor", [(3, 16), (6, 6), (12, 6)])
+def test_coefficients_from_per_coset_inverse_transforms(gpu, oc, bn, log_n, factor):
+    """uzkge_cuda_plonk_coset_combine_fr_device: a polynomial t of factor * n coefficients, evaluated on the coset k1 <w_m> (the oracle's
+    coset FFT), is recovered from its values coset by coset: strided copy of coset j, size-n coset iFFT with shift g_j^-1
+    (g_j = k1 w_m^j), and the factor-point inverse DFT over the cosets -- what coset_ifft_with_domain over the whole domain returns."""
+    n = 1 << log_n
+    m = n * factor
+    t = oc.random_fr(m, 555 + log_n)
+    k1 = bn.ints_to_array([K[1]], bn.FR)[0]
+    evals = dev(oc.ntt_fr(t, m, coset=k1))
+    w_m = bn.root_of_unity(m)
+    u = torch.empty(4 * m, dtype=torch.int64, device="cuda")
+    tmp, scr = torch.empty(4 * n, dtype=torch.int64, device="cuda"), torch.empty(4 * n, dtype=torch.int64, device="cuda")
+    for j in range(factor):
+        g_inv = bn.ints_to_array([pow(K[1] * pow(w_m, j, bn.FR) % bn.FR, -1, bn.FR)], bn.FR)[0]
+        gpu.fr_strided_copy_device(evals.data_ptr(), j, factor, tmp.data_ptr(), 0, 1, n)
+        gpu.ntt_fr_device(tmp.data_ptr(), u.data_ptr() + 32 * j * n, scr.data_ptr(), n, n, True, g_inv)
+    out = torch.empty(4 * m, dtype=torch.int64, device="cuda")
+    gpu.plonk_coset_combine_fr_device(u.data_ptr(), n, factor, k1, out.data_ptr())
+    assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(m, 4), t)

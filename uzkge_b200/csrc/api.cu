@@ -750,6 +750,14 @@ UZKGE_API int32_t uzkge_cuda_plonk_quotient_range_fr_device(const uzkge_quotient
     return engine_fail(rc, "plonk_quotient_range_fr_device");
 }
 
+UZKGE_API int32_t uzkge_cuda_plonk_coset_combine_fr_device(const void* d_u, size_t n, size_t factor, const uint64_t k1_host[4], void* d_out, void* stream) {
+    API_ENTER(-1);
+    int rc = plonk_coset_combine_run(d_u, n, factor, k1_host, d_out, (cudaStream_t)stream);
+    if (rc == UZKGE_ERR_ARG) return fail(rc, "plonk_coset_combine_fr_device: null pointer");
+    if (rc == UZKGE_ERR_SIZE) return fail(rc, "plonk_coset_combine_fr_device: n a power of two, factor <= 16, factor * n a supported domain");
+    return engine_fail(rc, "plonk_coset_combine_fr_device");
+}
+
 UZKGE_API int32_t uzkge_cuda_fr_strided_copy_device(const void* d_src, size_t src_start, size_t src_step, void* d_dst, size_t dst_start,
                                                     size_t dst_step, size_t count, void* stream) {
     API_ENTER(-1);

@@ -278,6 +278,8 @@ int fr_powers_run(const uint64_t* base, const uint64_t* scale, size_t n, void* d
 int fr_gather_run(const void* d_src, const void* d_idx, size_t n, void* d_out, cudaStream_t st);
 int fr_gather_scatter_run(const void* d_src, const void* d_src_idx, void* d_dst, const void* d_dst_idx, size_t k, cudaStream_t st);
 int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out, cudaStream_t st);
+// t's f n coefficients from the f per-coset inverse transforms u_j (f x n, compact); k1: the quotient coset's shift (host, Montgomery)
+int plonk_coset_combine_run(const void* d_u, size_t n, size_t factor, const uint64_t* k1, void* d_out, cudaStream_t st);
 // d_dst[dst_start + dst_step * i] = d_src[src_start + src_step * i], i < count
 int fr_strided_copy_run(const void* d_src, size_t src_start, size_t src_step, void* d_dst, size_t dst_start, size_t dst_step, size_t count,
                         cudaStream_t st);

@@ -243,6 +243,94 @@ int fr_strided_copy_run(const void* d_src, size_t src_start, size_t src_step, vo
     return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
 }
 
+// ---- the quotient's coefficients from its per-coset inverse transforms (the quotient round split by cosets, prover.cu).
+// t(X) = sum_r X^r T_r(X^n), T_r(Y) = sum_{c < f} t[r + n c] Y^c.  On the coset g_j <w_n> X^n is the constant K e_f^j (K = k1^n, e_f the
+// primitive f-th root w_m^n), so the size-n coset iFFT of t's values on coset j is u_j[r] = T_r(K e_f^j), and per r an f-point
+// inverse DFT recovers t[r + n c] = K^-c / f * sum_j u_j[r] e_f^(-j c).
+struct CosetCombineArgs {
+    const fe* u;      // f x n: u_j at [j n, (j + 1) n)
+    fe* out;          // f n coefficients
+    uint64_t n;
+    uint32_t f;
+    fe e_pow[16];     // e^k, e = e_f^-1
+    fe scale[16];     // K^-c / f
+};
+// f = 6: e is a primitive 6th root of unity, e^2 = e - 1 and e^3 = -1, so e^k v is one of v, ev, ev - v and their negatives: ONE product
+// per input, six for the scales -- 11 per r instead of the 36 of the general form below
+__global__ void __launch_bounds__(128) plonk_coset_combine6_kernel(const __grid_constant__ CosetCombineArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    fe S[6];
+    const fe v0 = ld_fe(a.u + r);
+#pragma unroll
+    for (int c = 0; c < 6; c++) S[c] = v0;
+#pragma unroll
+    for (int j = 1; j < 6; j++) {
+        const fe v = ld_fe(a.u + (uint64_t)j * a.n + r);
+        const fe b = fe_mul<FrP>(v, a.e_pow[1]);
+        const fe d = fe_sub<FrP>(b, v);          // e^2 v
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            const int k = (j * c) % 6;           // compile-time after unrolling
+            if (k == 0) S[c] = fe_add<FrP>(S[c], v);
+            else if (k == 1) S[c] = fe_add<FrP>(S[c], b);
+            else if (k == 2) S[c] = fe_add<FrP>(S[c], d);
+            else if (k == 3) S[c] = fe_sub<FrP>(S[c], v);
+            else if (k == 4) S[c] = fe_sub<FrP>(S[c], b);
+            else S[c] = fe_sub<FrP>(S[c], d);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) st_fe(a.out + (uint64_t)c * a.n + r, fe_mul<FrP>(S[c], a.scale[c]));
+}
+__global__ void __launch_bounds__(128) plonk_coset_combine_kernel(const __grid_constant__ CosetCombineArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    for (uint32_t c = 0; c < a.f; c++) {
+        fe acc = fe_zero();
+        for (uint32_t j = 0; j < a.f; j++) {
+            const fe v = ld_fe(a.u + (uint64_t)j * a.n + r);
+            const uint32_t k = (j * c) % a.f;
+            acc = fe_add<FrP>(acc, k ? fe_mul<FrP>(v, a.e_pow[k]) : v);
+        }
+        st_fe(a.out + (uint64_t)c * a.n + r, fe_mul<FrP>(acc, a.scale[c]));
+    }
+}
+
+int plonk_coset_combine_run(const void* d_u, size_t n, size_t factor, const uint64_t* k1, void* d_out, cudaStream_t st) {
+    if (!d_u || !d_out || !k1) return UZKGE_ERR_ARG;
+    if (n == 0 || (n & (n - 1)) || factor == 0 || factor > 16) return UZKGE_ERR_SIZE;
+    bool ok = false;
+    const fe w_m = ntt_root_of_unity((uint64_t)n * factor, &ok);
+    if (!ok) return UZKGE_ERR_SIZE;
+    CosetCombineArgs a;
+    memset(&a, 0, sizeof a);
+    a.u = (const fe*)d_u;
+    a.out = (fe*)d_out;
+    a.n = n;
+    a.f = (uint32_t)factor;
+    const fe e = fe_inv<FrP>(fe_pow_u64<FrP>(w_m, n));        // e_f^-1
+    fe kk;
+    memcpy(&kk, k1, sizeof(fe));
+    const fe K_inv = fe_inv<FrP>(fe_pow_u64<FrP>(kk, n));
+    fe ff = fe_zero();
+    ff.l[0] = (uint32_t)factor;
+    fe sc = fe_inv<FrP>(fe_to_mont<FrP>(ff));
+    fe ep = fe_one<FrP>();
+    for (uint32_t c = 0; c < factor; c++) {
+        a.e_pow[c] = ep;
+        a.scale[c] = sc;
+        ep = fe_mul<FrP>(ep, e);
+        sc = fe_mul<FrP>(sc, K_inv);
+    }
+    if (factor == 6)
+        plonk_coset_combine6_kernel<<<blocks_for(n, 128), 128, 0, st>>>(a);
+    else
+        plonk_coset_combine_kernel<<<blocks_for(n, 128), 128, 0, st>>>(a);
+    UZ_COUNT_LAUNCH(1);
+    return cudaGetLastError() == cudaSuccess ? UZKGE_OK : UZKGE_ERR_CUDA;
+}
+
 int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out, cudaStream_t st) {
     if (n == 0) return UZKGE_OK;
     if (!d_a || !d_b || !d_out) return UZKGE_ERR_ARG;

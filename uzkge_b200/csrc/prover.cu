@@ -161,6 +161,7 @@ struct Group {
     size_t G = 1;
     SpinBarrier bar;
     std::vector<u64> partial;            // [2][G][16][12]: the members' partial sums of a commitment batch, double-buffered by batch parity
+    std::vector<u64> evals;              // [32][4]: the round-4 evaluations, each computed by one member
     uz::GroupSrsParts srs, lag;          // the monomial SRS / the Lagrange commitment SRS, split over the members
     std::vector<Params*> params;         // the members' parameter sets (tcos: where a member receives the others' quotient cosets)
 };
@@ -929,10 +930,15 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
             TRY(uzkge_cuda_plonk_quotient_fr_device(&qa, t_buf, st));
         }
         if (grp) {
-            // exchange: every member sends its cosets (compact, n values each) into every other member's Params::tcos over peer
-            // memory, and fills the rest of its own size-m vector from what it receives
+            // back to coefficients, coset by coset: the size-n coset iFFT of the values on coset j is u_j[r] = T_r(g_j^n), where
+            // t(X) = sum_r X^r T_r(X^n).  Every member sends its u_j (compact, n values) into every other member's Params::tcos over
+            // peer memory; a factor-point inverse DFT per r over the cosets then gives t's coefficients -- no transform of the whole
+            // 6n domain, and nothing but the cosets crosses NVLink
             for (size_t j : my_cosets) {
-                TRY(uzkge_cuda_fr_strided_copy_device(t_buf, j, P.factor, P.tcos, j * n, 1, n, st));
+                const Limbs g_inv = FR.inverse(FR.mul(P.k1, fr_pow_u64(P.root_m, (u64)j)));
+                TRY(uzkge_cuda_fr_strided_copy_device(t_buf, j, P.factor, P.cbuf, 0, 1, n, st));
+                TRY(uzkge_cuda_ntt_fr_device(P.cbuf, P.tcos + 4 * j * n, P.scratch, n, n, 1, g_inv.data(), st));
+                proof->ifft_n++;
                 for (size_t r = 0; r < G; r++) {
                     if (r == rank) continue;
                     Params* Q = grp->params[r];
@@ -941,11 +947,11 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
             }
             CU(cudaStreamSynchronize(st));
             if (!grp->bar.wait()) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: another member of the device group failed");
-            for (size_t j = 0; j < P.factor; j++)
-                if (j % G != rank) TRY(uzkge_cuda_fr_strided_copy_device(P.tcos, j * n, 1, t_buf, j, P.factor, n, st));
+            TRY(uzkge_cuda_plonk_coset_combine_fr_device(P.tcos, n, P.factor, P.k1.data(), t_buf, st));
+        } else {
+            TRY(uzkge_cuda_ntt_fr_device(t_buf, t_buf, P.scratch, m, m, 1, P.k1_inv.data(), st));
+            proof->coset_ifft_m++;
         }
-        TRY(uzkge_cuda_ntt_fr_device(t_buf, t_buf, P.scratch, m, m, 1, P.k1_inv.data(), st));
-        proof->coset_ifft_m++;
     }
     size_t coefs_len = 0;
     TRY(uzkge_cuda_fr_trimmed_len_device(t_buf, m, &coefs_len, st));
@@ -1021,10 +1027,32 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
         memcpy(points, zeta.data(), 32);
         memcpy(points + 4, zeta_omega.data(), 32);
         u64* d_vals = P.small + 16 * 12;
-        TRY(uzkge_cuda_poly_eval_batch_fr_device(polys, lens, pt, n_ev, points, 2, d_vals, st));
-        CU(cudaMemcpyAsync(P.pinned, d_vals, n_ev * 32, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        for (size_t j = 0; j < n_ev; j++) ev[j] = load(P.pinned + 4 * j);
+        if (grp) {
+            // the polynomials are replicated, so the evaluations are dealt to the members (entry j to member j mod G) and shared
+            // through host memory: 32 bytes each
+            const void* my_polys[19];
+            size_t my_lens[19], my_idx[19], mine = 0;
+            uint32_t my_pt[19];
+            for (size_t j = rank; j < n_ev; j += G) {
+                my_polys[mine] = polys[j];
+                my_lens[mine] = lens[j];
+                my_pt[mine] = pt[j];
+                my_idx[mine++] = j;
+            }
+            if (mine) {
+                TRY(uzkge_cuda_poly_eval_batch_fr_device(my_polys, my_lens, my_pt, mine, points, 2, d_vals, st));
+                CU(cudaMemcpyAsync(P.pinned, d_vals, mine * 32, cudaMemcpyDeviceToHost, st));
+            }
+            CU(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < mine; i++) memcpy(grp->evals.data() + 4 * my_idx[i], P.pinned + 4 * i, 32);
+            if (!grp->bar.wait()) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: another member of the device group failed");
+            for (size_t j = 0; j < n_ev; j++) ev[j] = load(grp->evals.data() + 4 * j);
+        } else {
+            TRY(uzkge_cuda_poly_eval_batch_fr_device(polys, lens, pt, n_ev, points, 2, d_vals, st));
+            CU(cudaMemcpyAsync(P.pinned, d_vals, n_ev * 32, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (size_t j = 0; j < n_ev; j++) ev[j] = load(P.pinned + 4 * j);
+        }
         proof->evals += (uint32_t)n_ev;
     }
     const Limbs* we = ev;               // w_polys_eval_zeta
@@ -1272,6 +1300,7 @@ int prove_group(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, const
         }
     }
     grp.partial.assign(2 * G * 16 * 12, 0);
+    grp.evals.assign(32 * 4, 0);
     std::vector<uzkge_plonk_proof> proofs(G);
     const int rc = uz::group_fan_out(G, [&](size_t r) {
         uzkge_plonk_prove_args mine = *a;

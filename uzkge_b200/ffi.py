@@ -151,6 +151,7 @@ _SIGNATURES = {
     "uzkge_cuda_plonk_params_upload_multi": (C.c_int32, [C.c_void_p, u64p]),
     "uzkge_cuda_srs_upload_lagrange_commit_multi": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, u64p]),
     "uzkge_cuda_plonk_quotient_range_fr_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "uzkge_cuda_plonk_coset_combine_fr_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uzkge_cuda_fr_strided_copy_device": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "uzkge_cuda_plonk_params_set_public_key": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "uzkge_cuda_plonk_params_free": (C.c_int32, [C.c_uint64]),
@@ -524,10 +525,11 @@ def grand_product_fr(num, den) -> np.ndarray:
 
 
 def plonk_quotient_fr_device(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, alpha, beta, gamma, anemoi_g, anemoi_g_inv,
-                             z_h_inv, m: int, factor: int, d_out: int, stream: int = 0, shuffle=None) -> None:
+                             z_h_inv, m: int, factor: int, d_out: int, stream: int = 0, shuffle=None, point_range=None) -> None:
     """Device pointers (ints) for the arrays, numpy Montgomery limbs for the scalars; see uzkge_quotient_args.
     shuffle: None, or a dict {w_sel: 3 pointers, q_ecc: pointer, pk: 12 pointers, gen: 12 pointers, edwards_a: limbs} for the
-    `shuffle` feature set (uzkge_cuda_plonk_quotient_shuffle_fr_device)."""
+    `shuffle` feature set (uzkge_cuda_plonk_quotient_shuffle_fr_device).
+    point_range: None (all m points) or (start, step, count): only the points start + step * i (uzkge_cuda_plonk_quotient_range_fr_device)."""
     a = QuotientArgs()
     for j in range(5):
         a.w[j], a.s[j] = w[j], s[j]
@@ -545,7 +547,10 @@ def plonk_quotient_fr_device(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, a
         a.z_h_inv[i][:] = [int(x) for x in zh[i]]
     a.m, a.factor = m, factor
     if shuffle is None:
-        check(lib().uzkge_cuda_plonk_quotient_fr_device(C.byref(a), d_out, stream))
+        if point_range is not None:
+            check(lib().uzkge_cuda_plonk_quotient_range_fr_device(C.byref(a), None, *[int(x) for x in point_range], d_out, stream))
+        else:
+            check(lib().uzkge_cuda_plonk_quotient_fr_device(C.byref(a), d_out, stream))
         return
     b = QuotientShuffleArgs()
     for j in range(3):
@@ -554,7 +559,21 @@ def plonk_quotient_fr_device(w, q, pi, z, s, coset_quotient, l1, qb, q_prk, k, a
     for j in range(12):
         b.pk[j], b.gen[j] = shuffle["pk"][j], shuffle["gen"][j]
     b.edwards_a[:] = [int(x) for x in as_u64(shuffle["edwards_a"]).reshape(4)]
+    if point_range is not None:
+        check(lib().uzkge_cuda_plonk_quotient_range_fr_device(C.byref(a), C.byref(b), *[int(x) for x in point_range], d_out, stream))
+        return
     check(lib().uzkge_cuda_plonk_quotient_shuffle_fr_device(C.byref(a), C.byref(b), d_out, stream))
+
+
+def plonk_coset_combine_fr_device(d_u: int, n: int, factor: int, k1, d_out: int, stream: int = 0) -> None:
+    """t's factor * n coefficients from the per-coset inverse transforms u_j (compact, factor x n); k1: Montgomery limbs."""
+    check(lib().uzkge_cuda_plonk_coset_combine_fr_device(d_u, n, factor, ptr(as_u64(k1).reshape(4)), d_out, stream))
+
+
+def fr_strided_copy_device(d_src: int, src_start: int, src_step: int, d_dst: int, dst_start: int, dst_step: int, count: int,
+                           stream: int = 0) -> None:
+    """dst[dst_start + dst_step * i] = src[src_start + src_step * i], i < count."""
+    check(lib().uzkge_cuda_fr_strided_copy_device(d_src, src_start, src_step, d_dst, dst_start, dst_step, count, stream))
 
 
 LINCOMB_MAX = 24
