@@ -136,8 +136,8 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ roofline inputs
 # ncu `--set full` captures of the CURRENT kernels, exported with `--page raw --csv` (profiles/README.md says how each was taken)
-TRAFFIC_FILES = {"msm": ["profiles/r2_msm_accumulate_raw.csv", "profiles/r1c_msm_raw.csv"],
-                 "ntt": ["profiles/r2_ntt_raw.csv", "profiles/r1c_ntt_raw.csv"]}
+TRAFFIC_FILES = {"msm": ["profiles/r2b_msm_raw.csv", "profiles/r2_msm_accumulate_raw.csv", "profiles/r1c_msm_raw.csv"],
+                 "ntt": ["profiles/r2b_ntt_raw.csv", "profiles/r2_ntt_raw.csv", "profiles/r1c_ntt_raw.csv"]}
 _UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 

@@ -27,9 +27,13 @@ ncu -i $O/r2b_ntt.ncu-rep --page details > $O/r2b_ntt_details.txt 2>/dev/null
 run python scripts/gpu_plonk_once.py 20 2 > $O/plonk_plain.log 2>&1 \
   && run $NCU --set full -k regex:"plonk_quotient_kernel|plonk_perm_terms|horner|prod_|grand_product|fr_lincomb" -c 24 -f -o $O/r2b_plonk python scripts/gpu_plonk_once.py 20 1 > $O/ncu_plonk.log 2>&1
 ncu -i $O/r2b_plonk.ncu-rep --page raw --csv > $O/r2b_plonk_raw.csv 2>/dev/null
+ncu -i $O/r2b_plonk.ncu-rep --page details > $O/r2b_plonk_details.txt 2>/dev/null
 
 # 5. one zshuffle-52 proof by the compiled prover: launch list
 run python scripts/gpu_zshuffle_profile.py ncu > $O/zshuffle_plain.log 2>&1 \
   && run $NCU --profile-from-start off --metrics gpu__time_duration.sum --csv --log-file $O/r2b_zshuffle_launches.csv python scripts/gpu_zshuffle_profile.py ncu > $O/ncu_zshuffle.log 2>&1
-rm -f $O/*.ncu-rep.tmp
+# 6. where the host spends a zshuffle-52 proof (cProfile around the compiled prover's caller)
+run python scripts/gpu_zshuffle_profile.py host > $O/r2b_zshuffle_host_profile.txt 2>&1
+# the reports themselves stay on the box (gpurun_out/ carries at most 64 MiB back): the exported pages above are what is kept
+rm -f $O/*.ncu-rep $O/*.ncu-rep.tmp
 ls -la $O

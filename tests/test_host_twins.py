@@ -163,3 +163,14 @@ def test_ntt_plan_emulation_matches_oracle(uz, oc, cfg):
                     assert np.array_equal(buf, want), (cfg, n, inverse, coset is not None, len_in, npass.value)
     if cfg != (12, 11, 22):
         assert {1, 2, 3} <= seen
+
+
+def test_public_inputs_leave_montgomery_form_in_one_c_call(bn, oc):
+    """uzkge_host_fr_mont_to_be (csrc/hostutil.c): Montgomery limbs -> the canonical big-endian strings that enter the transcript
+    (plonk/transcript.rs:27-30), against Python integers, edge values included."""
+    from uzkge_b200.transcript import fr_mont_rows_to_bytes_be
+
+    xs = [0, 1, bn.FR - 1, (1 << 253) + 17] + bn.array_to_ints(oc.random_fr(500, 12), bn.FR)
+    got = fr_mont_rows_to_bytes_be(bn.ints_to_array(xs, bn.FR))
+    assert got == b"".join(x.to_bytes(32, "big") for x in xs)
+    assert fr_mont_rows_to_bytes_be(np.zeros((0, 4), dtype=np.uint64)) == b""

@@ -5,6 +5,8 @@
  *
  *   uzkge_host_keccak256      Keccak-256 with the original 0x01 padding   (utils/transcript.rs:60-62)
  *   uzkge_host_chacha20_block one 64-byte ChaCha20 block, 64-bit counter  (rand_chacha 0.3 `ChaCha20Rng`, stream 0)
+ *   uzkge_host_fr_mont_to_be  n Montgomery Fr elements -> canonical 32-byte big-endian strings, the form in which public inputs
+ *                             enter the transcript (`into_bigint().to_bytes_be()`, plonk/transcript.rs:27-30)
  */
 #include <stddef.h>
 #include <stdint.h>
@@ -83,4 +85,45 @@ API void uzkge_host_chacha20_block(const uint32_t key[8], uint64_t counter, uint
         QR(s[0], s[5], s[10], s[15]); QR(s[1], s[6], s[11], s[12]); QR(s[2], s[7], s[8], s[13]); QR(s[3], s[4], s[9], s[14]);
     }
     for (int i = 0; i < 16; i++) out[i] = s[i] + in[i];
+}
+
+/* ---- BN254 Fr out of Montgomery form: one REDC pass per element (multiplication by 1) */
+typedef unsigned __int128 u128;
+static const uint64_t FR_P[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+static const uint64_t FR_INV = 0xc2e1f593efffffffULL;   /* -p^-1 mod 2^64 */
+
+API void uzkge_host_fr_mont_to_be(const uint64_t* limbs, size_t n, uint8_t* out) {
+    for (size_t e = 0; e < n; e++) {
+        uint64_t t[5] = {limbs[4 * e], limbs[4 * e + 1], limbs[4 * e + 2], limbs[4 * e + 3], 0};
+        for (int i = 0; i < 4; i++) {
+            const uint64_t m = t[0] * FR_INV;
+            u128 c = (u128)m * FR_P[0] + t[0];
+            c >>= 64;
+            for (int j = 1; j < 4; j++) {
+                c += (u128)m * FR_P[j] + t[j];
+                t[j - 1] = (uint64_t)c;
+                c >>= 64;
+            }
+            c += t[4];
+            t[3] = (uint64_t)c;
+            t[4] = (uint64_t)(c >> 64);
+        }
+        /* t < 2p: one conditional subtraction */
+        uint64_t d[4];
+        u128 b = 0;
+        int ge = 1;
+        for (int j = 3; j >= 0; j--)
+            if (t[j] != FR_P[j]) { ge = t[j] > FR_P[j]; break; }
+        if (t[4] || ge) {
+            for (int j = 0; j < 4; j++) {
+                const u128 x = (u128)t[j] - FR_P[j] - (uint64_t)b;
+                d[j] = (uint64_t)x;
+                b = (x >> 64) & 1;
+            }
+        } else {
+            memcpy(d, t, sizeof d);
+        }
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 8; k++) out[32 * e + 8 * (3 - j) + (7 - k)] = (uint8_t)(d[j] >> (8 * k));
+    }
 }

@@ -16,7 +16,7 @@ from . import ffi
 from .errors import DegreeError, ParameterError, UzkgeError
 from .poly_commit import FR_MODULUS, KZGCommitment
 from .rng import fr_rand_mont
-from .transcript import transcript_init_plonk
+from .transcript import Transcript, fr_mont_rows_to_bytes_be, transcript_init_plonk
 
 _M64 = 0xFFFFFFFFFFFFFFFF
 _FR_R_INV = pow((1 << 256) % FR_MODULUS, -1, FR_MODULUS)
@@ -197,6 +197,8 @@ class NativeProver:
             self.lagrange_handle = int(lh.value)
         self.last_stats: dict = {}
         self._sel_cache = None
+        self._tinit_prefix = None
+        self._pub_idx = None
 
     def refresh_public_key(self) -> None:
         """After plonk.refresh_prover_params_public_key changed the 12 public-key selector polynomials of `prover_params`."""
@@ -217,15 +219,27 @@ class NativeProver:
             raise ParameterError("witness length != num_vars")
         idx = cs.public_vars_witness_indices
         if on_device:
-            rows = w.numpy()[idx] if idx else np.zeros((0, 4), dtype=np.uint64)
+            if idx:
+                import torch
+
+                if self._pub_idx is None or self._pub_idx.device != w.t.device:
+                    self._pub_idx = torch.as_tensor(np.asarray(idx, dtype=np.int64), device=w.t.device)
+                rows = w.t.view(-1, 4)[self._pub_idx].cpu().numpy().view(np.uint64)      # the public inputs only, not the witness
+            else:
+                rows = np.zeros((0, 4), dtype=np.uint64)
             w_ptr, keep_w = w.ptr, w
         else:
             wa = ffi.as_u64(w, 4)
             rows = wa[idx] if idx else np.zeros((0, 4), dtype=np.uint64)
             w_ptr, keep_w = wa.ctypes.data, wa
-        raw = np.ascontiguousarray(rows).tobytes()          # little-endian limbs: 32 bytes per value
-        online = [int.from_bytes(raw[32 * i: 32 * i + 32], "little") * _FR_R_INV % FR_MODULUS for i in range(len(idx))]
-        transcript_init_plonk(transcript, self.vp, online, self.P.root)
+        # transcript_init_plonk (plonk/transcript.rs:8-31): everything but the public inputs is fixed per circuit
+        if self._tinit_prefix is None:
+            pre = Transcript(b"")
+            pre.state = bytearray()
+            transcript_init_plonk(pre, self.vp, [], self.P.root)
+            self._tinit_prefix = bytes(pre.state)
+        transcript.state.extend(self._tinit_prefix)
+        transcript.state.extend(fr_mont_rows_to_bytes_be(rows))
         n_blinds = 21 + (6 if self.shuffle else 0)
         blinds = np.zeros((n_blinds, 4), dtype=np.uint64)
         for j in range(n_blinds):

@@ -77,6 +77,8 @@ def host_lib():
         L.uzkge_host_keccak256.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
         L.uzkge_host_chacha20_block.restype = None
         L.uzkge_host_chacha20_block.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+        L.uzkge_host_fr_mont_to_be.restype = None
+        L.uzkge_host_fr_mont_to_be.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
         _host = L
     return _host
 
@@ -87,6 +89,21 @@ def keccak256(data: bytes) -> bytes:
     out = C.create_string_buffer(32)
     data = bytes(data)
     host_lib().uzkge_host_keccak256(data, len(data), out)
+    return out.raw
+
+
+def fr_mont_rows_to_bytes_be(rows) -> bytes:
+    """(k, 4) uint64 Montgomery limbs -> k canonical 32-byte big-endian strings, concatenated (one C call: a circuit's hundreds of
+    public inputs enter the transcript in this form, plonk/transcript.rs:27-30)."""
+    import ctypes as C
+
+    import numpy as np
+
+    a = np.ascontiguousarray(rows, dtype=np.uint64).reshape(-1, 4)
+    out = C.create_string_buffer(32 * a.shape[0]) if a.shape[0] else None
+    if a.shape[0] == 0:
+        return b""
+    host_lib().uzkge_host_fr_mont_to_be(a.ctypes.data, a.shape[0], out)
     return out.raw
 
 
