@@ -1037,6 +1037,12 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
         g_quotient_min_blocks = (int)value;
         return UZKGE_OK;
     }
+    if (k == "l2_fetch_granularity") {   // bytes fetched from HBM on an L2 miss (32, 64 or 128): the MSM's 64-byte table gathers
+        if (value != 32 && value != 64 && value != 128) return fail(UZKGE_ERR_ARG, "configure: l2_fetch_granularity is 32, 64 or 128");
+        API_ENTER(-1);
+        CUDA_OR_FAIL(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value), "configure: cudaLimitMaxL2FetchGranularity");
+        return UZKGE_OK;
+    }
     if (k == "virtual_devices") {   // tests: the next uzkge_cuda_init_devices builds a group of `value` members over the visible GPUs
         if (value > UZ_MAX_DEVICES) return fail(UZKGE_ERR_ARG, "configure: virtual_devices <= 16");
         g_virtual_devices = (int)value;
