@@ -12,11 +12,15 @@ A step = one pass of the hot path over one batch of synthetic input:
         steps travel in ONE batch call, which the engine software-pipelines (`detail.single_call_ms`: one MSM per call).
         N > 1: the job is ONE MSM over N * 2^20 points; rank r owns slice r (bases resident on its GPU) and the
         N partial sums (96 B each) are all-gathered and added -- weak scaling, no other collective.
-  ntt : one forward 2^22 Fr NTT, natural order in and out (block "ntt"; replicas at N > 1: it fits one GPU), and at N > 1 ONE
-        2^24 four-step transform over the N GPUs (block "ntt_distributed": exchanges fused into the kernel over peer memory,
-        next to the NCCL all-to-all version).
+  ntt : one forward 2^22 Fr NTT, natural order in and out (block "ntt"; replicas at N > 1: it fits one GPU).
   plonk : one complete proof of a synthetic TurboPlonK circuit (block "plonk": 2^14 and 2^22 gates, default and shuffle feature
-        sets, uniform and bits witnesses; N > 1: replicas for throughput, one proof split over the GPUs for latency).
+        sets, uniform and bits witnesses, the zshuffle-52 and zmatchmaking circuits; compiled prover behind the C ABI, the Python
+        mirror timed beside it; `cpu_baseline`: a complete CPU proof of the same statement, bytes compared).  N > 1: replicas for
+        throughput, and ONE 2^22 proof three ways: "device_group" (one process drives all N GPUs through one C-ABI call per
+        proof), "msm_split" (round 1's Python split prover, one process per GPU), "replicas".
+  strong scaling (N > 1, blocks "msm_strong", "ntt_strong", "ntt_distributed"): ONE 2^20 MSM and ONE 2^22 / 2^24 transform over the
+        N GPUs, each with the single-GPU time of the same run, the efficiency and the bytes exchanged; the transforms with cyclic
+        and natural output, over peer memory (exchanges fused into the kernels) and over NCCL all-to-alls.
 The JSON line's top level is the MSM (`value` device-resident with CUDA events on the launching stream, max over ranks; `e2e`
 through the host-pointer C ABI a Rust caller uses: pinned host buffers, H2D + D2H inside the timed region; `roofline`,
 `int_roofline`, `cpu_baseline`, `clocks`, `gpu_launches`).  Inputs rotate over more distinct buffers than fit in the 126 MB L2

@@ -132,6 +132,12 @@ UZKGE_API int32_t uzkge_cuda_ntt_fr(uint64_t* inout, size_t len_in, size_t domai
  * the first len_in[j] are the input. */
 UZKGE_API int32_t uzkge_cuda_ntt_fr_batch(uint64_t* const* inouts, const size_t* len_in, size_t k, size_t domain_size, int32_t inverse,
                                           const uint64_t* coset_shift);
+/* ONE transform over the whole device group (uzkge_cuda_init_devices; 2, 4 or 8 GPUs), same contract as uzkge_cuda_ntt_fr: the
+ * four-step decomposition with both exchanges done by the kernels' own loads and stores over peer memory (NVLink) and the natural
+ * output order folded into the last pass.  Every GPU moves only its 1/G of the vector over its own host link, which is what bounds a
+ * host-pointer transform.  2^k domains of at least G^2 points; anything else is forwarded to uzkge_cuda_ntt_fr on the calling
+ * thread's device. */
+UZKGE_API int32_t uzkge_cuda_ntt_fr_multi(uint64_t* inout, size_t len_in, size_t domain_size, int32_t inverse, const uint64_t* coset_shift);
 /* generator of the size-n domain (Montgomery), for the Rust side's consistency assert against
  * `domain.group_gen`; UZKGE_ERR_SIZE if n is not 3^a 2^b with a <= 2, b <= 28. */
 UZKGE_API int32_t uzkge_cuda_fr_root_of_unity(size_t n, uint64_t out[4]);

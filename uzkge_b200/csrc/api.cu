@@ -1273,6 +1273,19 @@ MultiSrs* find_multi(uint64_t handle) {
 
 // ---- what prover.cu needs of the device group (declared in internal.h)
 namespace uz {
+bool SpinBarrier::wait() {
+    const uint32_t gen0 = gen.load(std::memory_order_acquire);
+    if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == members) {
+        count.store(0, std::memory_order_relaxed);
+        gen.fetch_add(1, std::memory_order_release);
+    } else {
+        while (gen.load(std::memory_order_acquire) == gen0) {
+            if (aborted.load(std::memory_order_relaxed)) return false;
+            std::this_thread::yield();
+        }
+    }
+    return !aborted.load(std::memory_order_relaxed);
+}
 std::mutex& group_mutex() { return g_multi_mu; }
 std::vector<int> group_devices_locked() { return g_group; }
 int group_fan_out(size_t count, const std::function<int(size_t)>& job) { return fan_out(count, job); }
@@ -1479,6 +1492,122 @@ UZKGE_API int32_t uzkge_cuda_msm_g1_batch(uint64_t handle, const uint64_t* const
         host_sum_jacobians(col.data(), G, out_jac + 12 * j);
     }
     return UZKGE_OK;
+}
+
+// One transform over the whole device group, host pointers in and out ("NTTs of size 2^22 and above use a four-step transpose over
+// NVLink"): member r uploads slice r of the input over ITS host link, the cross-rank kernel loads its column block straight from every
+// member's slice and stores row k1 into member k1's buffer (peer memory: both exchanges are the kernel's own loads and stores), the
+// size-n/G local transform's last pass stores into the owners' natural slices, and member r returns slice r of the result.  Three
+// host-side barriers order the members.  Falls back to the single-device call where the four-step does not apply (group of 1, 3, 5..
+// members, 3 * 2^k domains, sizes below G^2).
+namespace {
+struct GroupNttBufs {
+    DevBuf x, rows, nat, tmp;
+};
+std::vector<GroupNttBufs> g_group_ntt;      // one per group member (guarded by g_multi_mu)
+}  // namespace
+
+UZKGE_API int32_t uzkge_cuda_ntt_fr_multi(uint64_t* inout, size_t len_in, size_t domain_size, int32_t inverse, const uint64_t* coset_shift) {
+    if (!inout) return fail(UZKGE_ERR_ARG, "ntt_fr_multi: null pointer");
+    if (inverse != 0 && inverse != 1) return fail(UZKGE_ERR_ARG, "ntt_fr_multi: inverse must be 0 or 1");
+    if (len_in > domain_size) return fail(UZKGE_ERR_SIZE, "ntt_fr_multi: input longer than the domain");
+    std::lock_guard<std::mutex> multi(g_multi_mu);
+    const size_t G = g_group.size();
+    const size_t n = domain_size;
+    uint32_t log_g = 0;
+    while ((1ull << log_g) < G) log_g++;
+    if (G < 2 || G > 8 || (1ull << log_g) != G || n == 0 || (n & (n - 1)) || n < G * G)
+        return uzkge_cuda_ntt_fr(inout, len_in, domain_size, inverse, coset_shift);
+    const size_t L = n / G, S = L / G;
+    if (g_group_ntt.size() != G) g_group_ntt.assign(G, GroupNttBufs());
+    fe shift = fe_one<FrP>();
+    if (coset_shift) memcpy(&shift, coset_shift, sizeof(fe));
+    std::vector<fe*> X(G, nullptr), R(G, nullptr), N(G, nullptr);
+    SpinBarrier bar;
+    bar.members = (uint32_t)G;
+    // one phase of member r under its device's lock (never held across a barrier: two members may share a device in a virtual group)
+    auto phase = [&](size_t r, const std::function<int(State&, GroupNttBufs&)>& body) -> int {
+        State* st = nullptr;
+        int rc = enter_state(g_group[r], &st);
+        if (rc != UZKGE_OK) return rc;
+        std::lock_guard<std::mutex> lock(st->mu);
+        cudaError_t e = cudaSetDevice(st->device);
+        if (e != cudaSuccess) return fail_cuda("cudaSetDevice", e);
+        return body(*st, g_group_ntt[r]);
+    };
+    // x[j] *= shift^(first + j) on `count` elements (the coset scaling of mul_var_assign, field_polynomial.rs:470-477)
+    auto scale_by_powers = [&](State& dv, fe* v, fe* tmp, size_t first, size_t count) -> int {
+        const fe start = fe_pow_u64<FrP>(shift, first);
+        int rc = fr_powers_run((const uint64_t*)&shift, (const uint64_t*)&start, count, tmp, dv.stream);
+        if (rc != UZKGE_OK) return rc;
+        return fr_mul_run(v, tmp, count, v, dv.stream);
+    };
+    auto member = [&](size_t r) -> int {
+        int rc = phase(r, [&](State& dv, GroupNttBufs& b) -> int {
+            CUDA_OR_FAIL(b.x.reserve(L * sizeof(fe)), "ntt_fr_multi: buffer");
+            CUDA_OR_FAIL(b.rows.reserve(L * sizeof(fe)), "ntt_fr_multi: buffer");
+            CUDA_OR_FAIL(b.nat.reserve(L * sizeof(fe)), "ntt_fr_multi: buffer");
+            CUDA_OR_FAIL(b.tmp.reserve(L * sizeof(fe)), "ntt_fr_multi: buffer");
+            X[r] = (fe*)b.x.p;
+            R[r] = (fe*)b.rows.p;
+            N[r] = (fe*)b.nat.p;
+            const size_t lo = r * L;
+            const size_t have = len_in > lo ? (len_in - lo < L ? len_in - lo : L) : 0;
+            if (have) CUDA_OR_FAIL(cudaMemcpyAsync(X[r], inout + 4 * lo, have * sizeof(fe), cudaMemcpyHostToDevice, dv.stream), "ntt_fr_multi: H2D");
+            if (have < L) CUDA_OR_FAIL(cudaMemsetAsync(X[r] + have, 0, (L - have) * sizeof(fe), dv.stream), "ntt_fr_multi: zero padding");
+            if (coset_shift && !inverse && have) {
+                const int rc2 = scale_by_powers(dv, X[r], (fe*)b.tmp.p, lo, have);
+                if (rc2 != UZKGE_OK) return engine_fail(rc2, "ntt_fr_multi: coset scaling");
+            }
+            CUDA_OR_FAIL(cudaStreamSynchronize(dv.stream), "ntt_fr_multi: upload");
+            return UZKGE_OK;
+        });
+        if (rc != UZKGE_OK) return rc;
+        if (!bar.wait()) return fail(UZKGE_ERR_INTERNAL, "ntt_fr_multi: another member of the device group failed");
+        rc = phase(r, [&](State& dv, GroupNttBufs&) -> int {
+            const fe* in_rows[8];
+            fe* out_rows[8];
+            for (size_t i = 0; i < G; i++) {
+                in_rows[i] = X[i] + r * S;
+                out_rows[i] = R[i] + r * S;
+            }
+            const int rc2 = dv.ntt->cross_rows(in_rows, out_rows, log_g, S, r * S, n, inverse != 0, dv.stream);
+            if (rc2 != UZKGE_OK) return engine_fail(rc2, "ntt_fr_multi: cross step");
+            CUDA_OR_FAIL(cudaStreamSynchronize(dv.stream), "ntt_fr_multi: cross step");
+            return UZKGE_OK;
+        });
+        if (rc != UZKGE_OK) return rc;
+        if (!bar.wait()) return fail(UZKGE_ERR_INTERNAL, "ntt_fr_multi: another member of the device group failed");
+        rc = phase(r, [&](State& dv, GroupNttBufs& b) -> int {
+            NttScatter sc;
+            for (size_t i = 0; i < 8; i++) sc.rows[i] = i < G ? N[i] : nullptr;
+            sc.log_g = log_g;
+            sc.k1 = (uint32_t)r;
+            const fe* in = R[r];
+            fe* out = (fe*)b.tmp.p;
+            const uint64_t len = L;
+            const int rc2 = dv.ntt->run_batch(&in, &out, (fe*)b.tmp.p, &len, 1, L, inverse != 0, nullptr, dv.stream, &sc);
+            if (rc2 != UZKGE_OK) return engine_fail(rc2, "ntt_fr_multi: local transform");
+            CUDA_OR_FAIL(cudaStreamSynchronize(dv.stream), "ntt_fr_multi: local transform");
+            return UZKGE_OK;
+        });
+        if (rc != UZKGE_OK) return rc;
+        if (!bar.wait()) return fail(UZKGE_ERR_INTERNAL, "ntt_fr_multi: another member of the device group failed");
+        return phase(r, [&](State& dv, GroupNttBufs& b) -> int {
+            if (coset_shift && inverse) {
+                const int rc2 = scale_by_powers(dv, N[r], (fe*)b.tmp.p, r * L, L);
+                if (rc2 != UZKGE_OK) return engine_fail(rc2, "ntt_fr_multi: coset scaling");
+            }
+            CUDA_OR_FAIL(cudaMemcpyAsync(inout + 4 * r * L, N[r], L * sizeof(fe), cudaMemcpyDeviceToHost, dv.stream), "ntt_fr_multi: D2H");
+            CUDA_OR_FAIL(cudaStreamSynchronize(dv.stream), "ntt_fr_multi: execution");
+            return UZKGE_OK;
+        });
+    };
+    return fan_out(G, [&](size_t r) {
+        const int rc = member(r);
+        if (rc != UZKGE_OK) bar.abort();
+        return rc;
+    });
 }
 
 }  // extern "C"

@@ -287,6 +287,16 @@ int fr_trimmed_len_run(const void* d_poly, size_t n, unsigned long long* d_scrat
 int plonk_z_evals_run(PolyEngine* poly, const void* const d_w[5], const void* const d_sigma[5], const void* d_group, const uint64_t* k,
                       const uint64_t* beta, const uint64_t* gamma, size_t n, void* d_z, void* d_tmp, cudaStream_t st);
 
+// The members of a device group are dedicated worker threads that meet a few times per call: spin, do not sleep.  wait() returns
+// false when a member failed and the call is abandoned.
+struct SpinBarrier {
+    std::atomic<uint32_t> count{0}, gen{0};
+    std::atomic<bool> aborted{false};
+    uint32_t members = 1;
+    bool wait();
+    void abort() { aborted.store(true); }
+};
+
 // ---------------------------------------------------------------- the device group (api.cu) as prover.cu sees it
 struct GroupSrsParts {      // a multi-device SRS handle: member i owns bases [lo[i], hi[i]) behind its own single-device handle
     int mode = 0;

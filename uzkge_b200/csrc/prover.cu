@@ -138,25 +138,7 @@ std::map<u64, std::vector<u64>> g_multi_params;
 
 // ---- one proof on the whole device group: every member (one worker thread each) runs the prover below on replicated polynomials and
 // meets the others only here.  The members' transcripts stay identical because every commitment is the sum of all partial sums.
-struct SpinBarrier {        // the members are dedicated threads that meet a dozen times per proof: spin, do not sleep
-    std::atomic<uint32_t> count{0}, gen{0};
-    std::atomic<bool> aborted{false};
-    uint32_t members = 1;
-    bool wait() {           // false: a member failed, the proof is abandoned
-        const uint32_t g = gen.load(std::memory_order_acquire);
-        if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == members) {
-            count.store(0, std::memory_order_relaxed);
-            gen.fetch_add(1, std::memory_order_release);
-        } else {
-            while (gen.load(std::memory_order_acquire) == g) {
-                if (aborted.load(std::memory_order_relaxed)) return false;
-                std::this_thread::yield();
-            }
-        }
-        return !aborted.load(std::memory_order_relaxed);
-    }
-    void abort() { aborted.store(true); }
-};
+using uz::SpinBarrier;
 struct Group {
     size_t G = 1;
     SpinBarrier bar;

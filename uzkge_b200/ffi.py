@@ -111,6 +111,7 @@ _SIGNATURES = {
         C.c_int32,
         [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p],
     ),
+    "uzkge_cuda_ntt_fr_multi": (C.c_int32, [u64p, C.c_size_t, C.c_size_t, C.c_int32, u64p]),
     "uzkge_cuda_ntt_fr_scatter_device": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "uzkge_cuda_dev_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "uzkge_cuda_dev_free": (C.c_int32, [C.c_void_p]),
@@ -375,6 +376,16 @@ def ntt_fr(data: np.ndarray, domain_size: int, inverse: bool = False, coset_shif
         FFTError,
     )
     return buf
+
+
+def ntt_fr_multi_inplace(buf: np.ndarray, len_in: int, domain_size: int, inverse: bool = False, coset_shift=None) -> None:
+    """uzkge_cuda_ntt_fr_multi: the same contract as ntt_fr_inplace, ONE transform over the whole device group (init_devices)."""
+    assert buf.dtype == np.uint64 and buf.flags["C_CONTIGUOUS"] and buf.size >= 4 * domain_size
+    shift = as_u64(coset_shift, 4) if coset_shift is not None else None
+    check(
+        lib().uzkge_cuda_ntt_fr_multi(ptr(buf), len_in, domain_size, 1 if inverse else 0, ptr(shift) if shift is not None else None),
+        FFTError,
+    )
 
 
 def ntt_fr_inplace(buf: np.ndarray, len_in: int, domain_size: int, inverse: bool = False, coset_shift=None) -> None:
