@@ -976,6 +976,47 @@ def main() -> int:
         results["ntt_distributed"] = strong[24]
         results["ntt_strong"] = strong[22]
 
+    # -------------------------------------------------------------------------------------------- ONE host-pointer transform on all N GPUs
+    if args.workload in ("all", "both", "ntt") and world in (2, 4, 8):
+        import datetime
+
+        store = dist.distributed_c10d._get_default_store()
+        key = "uzkge_group_ntt_done"
+        if rank != 0:
+            torch.cuda.synchronize()
+            store.wait([key], datetime.timedelta(minutes=30))      # this rank's GPU belongs to rank 0's device group meanwhile
+        else:
+            ffi.configure("virtual_devices", 0)
+            if ffi.init_devices(world) != world:
+                raise SystemExit("bench.py: the device group does not cover the GPUs of the job")
+            n = 1 << LOG_NTT
+            hx = results["ntt"]["hx"]
+            pin = ffi.PinnedArray((n, 4))
+            pin.array[:] = hx
+            for i in range(4):
+                ffi.ntt_fr_multi_inplace(pin.array, n, n, bool(i & 1))
+            t0 = time.perf_counter()
+            for i in range(K):
+                ffi.ntt_fr_multi_inplace(pin.array, n, n, bool(i & 1))     # forward / inverse alternate: the data stays bounded
+            group_ms = (time.perf_counter() - t0) * 1e3 / K
+            ok = bool(np.array_equal(pin.array, hx)) if K % 2 == 0 else None
+            fwd = np.array(pin.array) if K % 2 == 0 else None
+            if fwd is not None:
+                ffi.ntt_fr_multi_inplace(fwd, n, n, False)
+                ok = ok and bool(np.array_equal(fwd, ffi.ntt_fr(hx, n)))        # the group's transform == the single-GPU transform
+            pin.free()
+            one = results["ntt"]["e2e_single_ms"]
+            results["ntt_group_e2e"] = {
+                "metric": "bn254_fr_ntt_2^22_elements_per_s (ONE host-pointer transform on N GPUs, one process)", "n_gpus": world,
+                "value": n / (group_ms * 1e-3), "unit": "elements/s", "ms_per_step": group_ms, "single_gpu_single_call_ms": one,
+                "speedup": one / group_ms, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n, "parity_ok": ok,
+                "what": "uzkge_cuda_ntt_fr_multi from ONE process: every GPU uploads / returns 1/N of the vector over its own host link, "
+                        "four-step over peer memory in between (cross kernel, local transform storing into the owners' natural "
+                        "slices); compared with ONE uzkge_cuda_ntt_fr call on one GPU (copy in, transform, copy out)",
+            }
+            store.set(key, "1")
+        barrier()
+
     # -------------------------------------------------------------------------------------------- PlonK (rank 0, N = 1)
     if args.workload in ("all", "plonk"):
         results["plonk"] = plonk_proofs(args, dev, K, W, rank, world, barrier, max_over_ranks)
@@ -1155,7 +1196,7 @@ def main() -> int:
         line["ntt"] = ntt_block(results["ntt"])
     if "plonk" in results:
         line["plonk"] = results["plonk"]
-    for key in ("msm_strong", "ntt_strong", "ntt_distributed"):
+    for key in ("msm_strong", "ntt_strong", "ntt_distributed", "ntt_group_e2e"):
         if key in results:
             line[key] = results[key]
     emit(line)

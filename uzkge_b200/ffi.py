@@ -111,7 +111,7 @@ _SIGNATURES = {
         C.c_int32,
         [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p],
     ),
-    "uzkge_cuda_ntt_fr_multi": (C.c_int32, [u64p, C.c_size_t, C.c_size_t, C.c_int32, u64p]),
+    "uzkge_cuda_ntt_fr_multi": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p]),
     "uzkge_cuda_ntt_fr_scatter_device": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "uzkge_cuda_dev_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "uzkge_cuda_dev_free": (C.c_int32, [C.c_void_p]),
