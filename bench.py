@@ -1006,6 +1006,48 @@ def main() -> int:
                 ok = ok and bool(np.array_equal(fwd, ffi.ntt_fr(hx, n)))        # the group's transform == the single-GPU transform
             pin.free()
             one = results["ntt"]["e2e_single_ms"]
+            if "msm" in results:
+                # the round's independent commitments dealt to the GPUs (plonk/prover.rs:132-192, helpers.rs:1323-1408) and
+                # one commitment split by points (row 1), both through the host-pointer calls a Rust caller makes, from ONE process
+                rm = results["msm"]
+                nm, kk = rm["n"], 8
+                vecs = [random_fr(nm, 0xB2000020 + j) for j in range(kk)]
+                pins = [ffi.PinnedArray((nm, 4)) for _ in range(kk)]
+                for pa, v in zip(pins, vecs):
+                    pa.array[:] = v
+                arrs = [pa.array for pa in pins]
+                h_rep = ffi.srs_upload_multi(rm["bases"], ffi.MULTI_REPLICATED, args.window_bits)
+                h_split = ffi.srs_upload_multi(rm["bases"], ffi.MULTI_SPLIT, args.window_bits)
+
+                def wall(fn, reps=5):
+                    fn()
+                    t0 = time.perf_counter()
+                    for _ in range(reps):
+                        out = fn()
+                    return (time.perf_counter() - t0) * 1e3 / reps, out
+
+                t_one, o_one = wall(lambda: ffi.msm_g1_batch(rm["handle"], arrs))
+                t_rep, o_rep = wall(lambda: ffi.msm_g1_batch(h_rep, arrs))
+                t_spl, o_spl = wall(lambda: ffi.msm_g1_batch(h_split, arrs))
+                t_one1, o_one1 = wall(lambda: ffi.msm_g1(rm["handle"], arrs[0]))
+                t_spl1, o_spl1 = wall(lambda: ffi.msm_g1(h_split, arrs[0]))
+                same = all(np.array_equal(ffi.g1_to_affine(o_one[j]), ffi.g1_to_affine(o_rep[j])) and
+                           np.array_equal(ffi.g1_to_affine(o_one[j]), ffi.g1_to_affine(o_spl[j])) for j in range(kk))
+                same = same and bool(np.array_equal(ffi.g1_to_affine(o_one1), ffi.g1_to_affine(o_spl1)))
+                results["commit_group_e2e"] = {
+                    "n_gpus": world, "points": nm, "commitments_per_round": kk, "parity_ok": bool(same),
+                    "one_gpu_round_ms": t_one, "dealt_round_ms": t_rep, "point_split_round_ms": t_spl,
+                    "dealt_speedup": t_one / t_rep, "point_split_speedup": t_one / t_spl,
+                    "one_gpu_single_commit_ms": t_one1, "point_split_single_commit_ms": t_spl1,
+                    "what": f"{kk} independent 2^{LOG_MSM}-point commitments (a prover round) through uzkge_cuda_msm_g1_batch on host scalars, "
+                            "from ONE process: on one GPU; dealt to the N GPUs (UZKGE_MULTI_REPLICATED: MSM j on GPU j mod N); every MSM "
+                            "split by points over the N GPUs (UZKGE_MULTI_SPLIT, partial sums added on the host).  H2D of the scalars "
+                            "(32 MiB per commitment) inside every figure; results compared",
+                }
+                ffi.srs_free(h_rep)
+                ffi.srs_free(h_split)
+                for pa in pins:
+                    pa.free()
             results["ntt_group_e2e"] = {
                 "metric": "bn254_fr_ntt_2^22_elements_per_s (ONE host-pointer transform on N GPUs, one process)", "n_gpus": world,
                 "value": n / (group_ms * 1e-3), "unit": "elements/s", "ms_per_step": group_ms, "single_gpu_single_call_ms": one,
@@ -1196,7 +1238,7 @@ def main() -> int:
         line["ntt"] = ntt_block(results["ntt"])
     if "plonk" in results:
         line["plonk"] = results["plonk"]
-    for key in ("msm_strong", "ntt_strong", "ntt_distributed", "ntt_group_e2e"):
+    for key in ("msm_strong", "ntt_strong", "ntt_distributed", "ntt_group_e2e", "commit_group_e2e"):
         if key in results:
             line[key] = results[key]
     emit(line)

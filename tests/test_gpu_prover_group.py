@@ -85,6 +85,35 @@ def test_group_proof_of_the_shuffle_feature_set(gpu):
         _group(gpu, 0)
 
 
+def test_group_parameters_take_a_new_public_key(gpu):
+    """uzkge_cuda_plonk_params_set_public_key on a multi-device handle: parameters uploaded to the group BEFORE the joint key was loaded
+    prove, after the refresh, the bytes of a single-device prover built after it (shuffle/src/gen_params/params.rs:57-129)."""
+    from uzkge_b200 import KZGCommitmentSchemeBN254, plonk
+    from uzkge_b200.native import NativeProver
+    from uzkge_b200.rng import ChaChaRng
+    from uzkge_b200.transcript import Transcript
+
+    try:
+        assert _group(gpu, 3) == 3
+        inp = shuffle_inputs(1, 9)
+        cs, _ = build_shuffle_circuit(plonk.TurboCS(), inp)
+        pcs = KZGCommitmentSchemeBN254.new(cs.size + 2, plonk.mont(TAU))
+        params = plonk.indexer(cs, pcs, shuffle=True)
+        early = NativeProver(cs, params, pcs, multi=True)
+        plonk.refresh_prover_params_public_key(cs, params, pcs, inp["pk"])
+        early.refresh_public_key()
+        late = NativeProver(cs, params, pcs)
+        wit = cs.get_witness_array()
+        a = early.prove(ChaChaRng.from_seed(bytes(32)), Transcript(b"k"), wit).to_bytes_be()
+        b = late.prove(ChaChaRng.from_seed(bytes(32)), Transcript(b"k"), wit).to_bytes_be()
+        assert a == b and len(a) == 1632
+        early.close()
+        late.close()
+        pcs.close()
+    finally:
+        _group(gpu, 0)
+
+
 def test_group_prover_rejects_what_it_cannot_run(gpu):
     from uzkge_b200 import KZGCommitmentSchemeBN254, plonk
     from uzkge_b200.native import NativeProver
