@@ -42,12 +42,16 @@ def _prove_both(cs, params, pcs, lagrange, lagrange_all, label=b"group", seed=by
     return out
 
 
+@pytest.mark.parametrize("deal", [False, True])
 @pytest.mark.parametrize("members", [0, 2, 3, 8])
-def test_group_proof_equals_single_device_proof(gpu, members):
-    """members = 0: the real GPUs of the box (a group of one on a one-GPU box, NVLink peers under gpurun --gpus N)."""
+def test_group_proof_equals_single_device_proof(gpu, members, deal):
+    """members = 0: the real GPUs of the box (a group of one on a one-GPU box, NVLink peers under gpurun --gpus N).
+    deal: the large-circuit path forced onto these small circuits -- a round's interpolations and the linearisation polynomial are
+    dealt to the members, who pull each other's results over peer memory (default: from 2^19 gates on)."""
     from uzkge_b200 import KZGCommitmentSchemeBN254, plonk
 
     try:
+        gpu.configure("group_deal_min_log_n", 0 if deal else 19)
         assert _group(gpu, members) == (members or gpu.device_count())
         for n_gates, n_public, n_boolean in ((100, 3, 2), (900, 0, 0)):
             cs = build_circuit(plonk.TurboCS(), n_gates, 40 + n_gates, n_public, n_boolean)
@@ -61,14 +65,17 @@ def test_group_proof_equals_single_device_proof(gpu, members):
             pcs.close()
             lagrange.close()
     finally:
+        gpu.configure("group_deal_min_log_n", 19)
         _group(gpu, 0)
 
 
-def test_group_proof_of_the_shuffle_feature_set(gpu):
+@pytest.mark.parametrize("deal", [False, True])
+def test_group_proof_of_the_shuffle_feature_set(gpu, deal):
     """zshuffle's circuit (2 cards) with its 1632-byte proof format: witness selectors, quotient terms 12-18, all-Lagrange route."""
     from uzkge_b200 import KZGCommitmentSchemeBN254, plonk
 
     try:
+        gpu.configure("group_deal_min_log_n", 0 if deal else 19)
         assert _group(gpu, 4) == 4
         inp = shuffle_inputs(2, 77)
         cs, _ = build_shuffle_circuit(plonk.TurboCS(), inp)
@@ -82,6 +89,7 @@ def test_group_proof_of_the_shuffle_feature_set(gpu):
         pcs.close()
         lagrange.close()
     finally:
+        gpu.configure("group_deal_min_log_n", 19)
         _group(gpu, 0)
 
 

@@ -33,6 +33,7 @@ using namespace uz;
 
 namespace uz {
 extern int g_quotient_min_blocks;  // quotient.cu
+extern int g_group_deal_min_log_n; // prover.cu
 static int g_virtual_devices = 0;   // tests: group members cycle over the visible GPUs (uzkge_cuda_configure "virtual_devices")
 }
 
@@ -1035,6 +1036,11 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
     const std::string k(key);
     if (k == "quotient_min_blocks") {
         g_quotient_min_blocks = (int)value;
+        return UZKGE_OK;
+    }
+    if (k == "group_deal_min_log_n") {   // circuits of at least 2^value gates: a device group deals interpolations / r to its members
+        if (value > 28) return fail(UZKGE_ERR_ARG, "configure: group_deal_min_log_n <= 28");
+        g_group_deal_min_log_n = (int)value;
         return UZKGE_OK;
     }
     if (k == "l2_fetch_granularity") {   // bytes fetched from HBM on an L2 miss (32, 64 or 128): the MSM's 64-byte table gathers

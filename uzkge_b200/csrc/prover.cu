@@ -29,6 +29,10 @@
 
 namespace uz {
 int api_fail(int code, const char* what);   // api.cu: sets the calling thread's error message
+// device groups deal a round's interpolations and the linearisation polynomial to their members from this circuit size on (below it a
+// round's transforms are one batched launch per pass and the extra barriers cost more than they save); uzkge_cuda_configure
+// "group_deal_min_log_n"
+int g_group_deal_min_log_n = 19;
 }
 
 namespace {
@@ -119,8 +123,8 @@ struct Params {
     u64 *polys = nullptr;      // 16 buffers of stride elements: w[5], w_sel[3], z, t[5], r, (spare)
     u64 *pi = nullptr, *sh = nullptr, *q1 = nullptr, *q2 = nullptr, *lag_buf = nullptr, *small = nullptr;
     // device group (uzkge_cuda_plonk_params_upload_multi): compact coset vectors (10 x n), the exchanged quotient cosets (m elements,
-    // coset j at [j n, (j + 1) n)) and the saved head coefficients of the polynomials folded onto a coset
-    u64 *cbuf = nullptr, *tcos = nullptr, *fold_save = nullptr;
+    // coset j at [j n, (j + 1) n))
+    u64 *cbuf = nullptr, *tcos = nullptr;
     u64* pinned = nullptr;     // host, page-locked: results of the small device-to-host reads
     cudaStream_t st = nullptr, side = nullptr;
     cudaEvent_t ev = nullptr;
@@ -532,10 +536,18 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
         return UZKGE_OK;
     };
     // hide_polynomial (helpers.rs:139-154): f += (b_0 + b_1 X + ...) (X^zeroing_degree - 1); returns the blinds (queued: flush_sparse)
+    // group members on large circuits DEAL the interpolations of a round (job j to member j mod G) and pull the others' results
+    // over peer memory; a dealt polynomial is blinded by its owner only.  owner_of_buf[b]: the member that produces poly_buf(b), -1 = all
+    const bool deal = grp && G > 1 && n >= ((size_t)1 << uz::g_group_deal_min_log_n);
+    int owner_of_buf[16];
+    for (int b = 0; b < 16; b++) owner_of_buf[b] = -1;
     auto hide = [&](Poly& f, size_t hiding, std::vector<Limbs>* out) -> int {
+        const size_t buf = (size_t)(f.p - P.polys) / (4 * stride);
+        const bool apply = !deal || buf >= 16 || owner_of_buf[buf] < 0 || (size_t)owner_of_buf[buf] == rank;
         for (size_t i = 0; i < hiding; i++) {
             const Limbs b = next_blind();
             out->push_back(b);
+            if (!apply) continue;
             sparse.add(f.p, i, b);
             sparse.add(f.p, n + i, FR.neg(b));
         }
@@ -664,36 +676,48 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
             memcpy(fold + 4, gn.data(), 32);
             const u64* ins[10];
             u64* cs[10];
-            size_t lens[10], extra[10];
+            size_t lens[10];
             for (size_t i = 0; i < k; i++) {
-                extra[i] = fs[i].len > n ? fs[i].len - n : 0;
-                if (extra[i] > TAIL) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: a polynomial exceeds n + 8 coefficients");
-                if (extra[i]) {     // head coefficients += g^n * tail, restored after the transform
-                    u64* save = P.fold_save + 4 * TAIL * i;
-                    CU(cudaMemcpyAsync(save, fs[i].p, extra[i] * 32, cudaMemcpyDeviceToDevice, st));
-                    const void* two[2] = {fs[i].p, fs[i].p + 4 * n};
-                    const size_t two_len[2] = {extra[i], extra[i]};
-                    TRY(uzkge_cuda_fr_lincomb_device(two, two_len, fold, 2, fs[i].p, extra[i], st));
-                }
-                ins[i] = fs[i].p;
+                // the transform's input is a COPY of the first n coefficients with the tail folded in (head += g^n * tail): the
+                // polynomial itself is never touched -- other members of the group may be reading it over peer memory
+                const size_t extra = fs[i].len > n ? fs[i].len - n : 0;
+                if (extra > TAIL) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: a polynomial exceeds n + 8 coefficients");
                 cs[i] = P.cbuf + 4 * n * i;
                 lens[i] = fs[i].len < n ? (fs[i].len ? fs[i].len : 1) : n;
+                CU(cudaMemcpyAsync(cs[i], fs[i].p, lens[i] * 32, cudaMemcpyDeviceToDevice, st));
+                if (extra) {
+                    const void* two[2] = {cs[i], fs[i].p + 4 * n};
+                    const size_t two_len[2] = {extra, extra};
+                    TRY(uzkge_cuda_fr_lincomb_device(two, two_len, fold, 2, cs[i], extra, st));
+                }
+                ins[i] = cs[i];
             }
-            TRY(ntt_many(P, ins, cs, lens, k, n, 0, g.data()));
+            TRY(ntt_many(P, ins, cs, lens, k, n, 0, g.data()));      // in place in the compact buffers
             proof->fft_n += (uint32_t)k;
-            for (size_t i = 0; i < k; i++) {
-                if (extra[i]) CU(cudaMemcpyAsync(fs[i].p, P.fold_save + 4 * TAIL * i, extra[i] * 32, cudaMemcpyDeviceToDevice, st));
-                TRY(uzkge_cuda_fr_strided_copy_device(cs[i], 0, 1, outs[i], j, P.factor, n, st));
-            }
+            for (size_t i = 0; i < k; i++) TRY(uzkge_cuda_fr_strided_copy_device(cs[i], 0, 1, outs[i], j, P.factor, n, st));
         }
         return UZKGE_OK;
     };
 
     // ---- 0. witness into HBM; 1. the PI polynomial (helpers.rs:111-131)
-    if (a->witness_on_device)
+    if (a->witness_on_device) {
         CU(cudaMemcpyAsync(P.wit, a->witness, P.num_vars * 32, grp ? cudaMemcpyDefault : cudaMemcpyDeviceToDevice, st));
-    else
+    } else if (grp && G > 1) {
+        // a host witness crosses the host links once in total: member r uploads slice r, then pulls the other slices from its peers
+        auto lo_of = [&](size_t r) { return r * P.num_vars / G; };
+        const size_t lo = lo_of(rank), hi = lo_of(rank + 1);
+        if (hi > lo) CU(cudaMemcpyAsync(P.wit + 4 * lo, a->witness + 4 * lo, (hi - lo) * 32, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        if (!grp->bar.wait()) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: another member of the device group failed");
+        for (size_t r = 0; r < G; r++) {
+            if (r == rank) continue;
+            const size_t a0 = lo_of(r), a1 = lo_of(r + 1);
+            Params* Q = grp->params[r];
+            if (a1 > a0) CU(cudaMemcpyPeerAsync(P.wit + 4 * a0, P.device, Q->wit + 4 * a0, Q->device, (a1 - a0) * 32, st));
+        }
+    } else {
         CU(cudaMemcpyAsync(P.wit, a->witness, P.num_vars * 32, cudaMemcpyHostToDevice, st));
+    }
     Poly pi{P.pi, n};
     if (P.n_public) {
         CU(cudaMemsetAsync(P.pi, 0, n * 32, st));
@@ -735,12 +759,38 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
                     CU(cudaMemsetAsync(ev, 0, n * 32, st));
                 }
             }
-        TRY(ntt_many(P, ins, outs, lens, k, n, 1, nullptr));
+        if (deal) {
+            const u64* oins[8];
+            u64* oouts[8];
+            size_t olens[8], ok = 0;
+            for (size_t j = 0; j < k; j++) {
+                owner_of_buf[(size_t)(outs[j] - P.polys) / (4 * stride)] = (int)(j % G);
+                if (j % G != rank) continue;
+                oins[ok] = ins[j];
+                oouts[ok] = outs[j];
+                olens[ok++] = lens[j];
+            }
+            TRY(ntt_many(P, oins, oouts, olens, ok, n, 1, nullptr));
+        } else {
+            TRY(ntt_many(P, ins, outs, lens, k, n, 1, nullptr));
+        }
         proof->ifft_n += (uint32_t)k;
         for (size_t i = 0; i < N_WIRES; i++) TRY(hide(w_polys[i], HIDING[i], &w_blinds[i]));     // the RNG order: wires, then selectors
         if (shuffle)
             for (size_t i = 0; i < 3; i++) TRY(hide(w_sel_polys[i], 2, &w_sel_blinds[i]));
         TRY(flush_sparse());
+        if (deal) {
+            // every member's polynomials (blinds included) are complete: pull the others' over NVLink.  Nobody writes a wire
+            // polynomial after this point, so no second barrier is needed
+            CU(cudaStreamSynchronize(st));
+            if (!grp->bar.wait()) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: another member of the device group failed");
+            for (size_t j = 0; j < k; j++) {
+                if (j % G == rank) continue;
+                Params* Q = grp->params[j % G];
+                const size_t buf = (size_t)(outs[j] - P.polys) / (4 * stride);
+                CU(cudaMemcpyPeerAsync(P.poly_buf(buf), P.device, Q->poly_buf(buf), Q->device, stride * 32, st));
+            }
+        }
     }
     // the quotient round's coset evaluations of these polynomials depend on no challenge: they run behind the MSMs
     auto wire_cosets = [&]() -> int {
@@ -1128,27 +1178,40 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
         for (const Term& t : merged)
             if (t.f.len > rlen) rlen = t.f.len;
         r_poly = {P.poly_buf(14), rlen};
+        // group members on large circuits each form the coefficients [lo, hi) of r and pull the other ranges over peer memory
+        const size_t lo = deal ? rank * rlen / G : 0, hi = deal ? (rank + 1) * rlen / G : rlen;
         bool first = true;
         const size_t chunk = UZKGE_LINCOMB_MAX - 1;
-        for (size_t i0 = 0; i0 < merged.size(); i0 += chunk) {
+        for (size_t i0 = 0; i0 < merged.size() && hi > lo; i0 += chunk) {
             const void* ptrs[UZKGE_LINCOMB_MAX];
             size_t lens[UZKGE_LINCOMB_MAX];
             u64 cs[UZKGE_LINCOMB_MAX * 4];
             size_t kk = 0;
             for (size_t i = i0; i < merged.size() && i < i0 + chunk; i++) {
-                ptrs[kk] = merged[i].f.p;
-                lens[kk] = merged[i].f.len;
+                const size_t len = merged[i].f.len;
+                lens[kk] = len > lo ? (len < hi ? len - lo : hi - lo) : 0;
+                ptrs[kk] = merged[i].f.p + 4 * (lens[kk] ? lo : 0);
                 memcpy(cs + 4 * kk, merged[i].c.data(), 32);
                 kk++;
             }
             if (!first) {   // accumulate onto the partial sum
-                ptrs[kk] = r_poly.p;
-                lens[kk] = rlen;
+                ptrs[kk] = r_poly.p + 4 * lo;
+                lens[kk] = hi - lo;
                 memcpy(cs + 4 * kk, FR.one.data(), 32);
                 kk++;
             }
-            TRY(uzkge_cuda_fr_lincomb_device(ptrs, lens, cs, kk, r_poly.p, rlen, st));
+            TRY(uzkge_cuda_fr_lincomb_device(ptrs, lens, cs, kk, r_poly.p + 4 * lo, hi - lo, st));
             first = false;
+        }
+        if (deal) {
+            CU(cudaStreamSynchronize(st));
+            if (!grp->bar.wait()) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: another member of the device group failed");
+            for (size_t r = 0; r < G; r++) {
+                if (r == rank) continue;
+                const size_t a0 = r * rlen / G, a1 = (r + 1) * rlen / G;
+                Params* Q = grp->params[r];
+                if (a1 > a0) CU(cudaMemcpyPeerAsync(r_poly.p + 4 * a0, P.device, Q->poly_buf(14) + 4 * a0, Q->device, (a1 - a0) * 32, st));
+            }
         }
     }
     // r(zeta) is computed by the first opening's pass below: the remainder of (sum_j alpha^j p_j) / (X - zeta) is the combined value,
@@ -1342,7 +1405,6 @@ UZKGE_API int32_t uzkge_cuda_plonk_params_upload_multi(const uzkge_plonk_params_
             Params& P = *Pp;
             TRY(dev_alloc(P, 10 * P.n, &P.cbuf, false));
             TRY(dev_alloc(P, P.m, &P.tcos, false));
-            TRY(dev_alloc(P, 10 * TAIL, &P.fold_save, false));
             return (int)UZKGE_OK;
         });
     }
