@@ -1525,7 +1525,16 @@ UZKGE_API int32_t uzkge_cuda_ntt_fr_multi(uint64_t* inout, size_t len_in, size_t
     if (G < 2 || G > 8 || (1ull << log_g) != G || n == 0 || (n & (n - 1)) || n < G * G)
         return uzkge_cuda_ntt_fr(inout, len_in, domain_size, inverse, coset_shift);
     const size_t L = n / G, S = L / G;
-    if (g_group_ntt.size() != G) g_group_ntt.assign(G, GroupNttBufs());
+    if (g_group_ntt.size() != G) {     // the group changed: the old members' buffers go (a DevBuf does not free itself)
+        for (GroupNttBufs& b : g_group_ntt)
+            for (DevBuf* d : {&b.x, &b.rows, &b.nat, &b.tmp})
+                if (d->p) {
+                    cudaPointerAttributes at;
+                    if (cudaPointerGetAttributes(&at, d->p) == cudaSuccess && cudaSetDevice(at.device) == cudaSuccess) cudaFree(d->p);
+                    cudaGetLastError();
+                }
+        g_group_ntt.assign(G, GroupNttBufs());
+    }
     fe shift = fe_one<FrP>();
     if (coset_shift) memcpy(&shift, coset_shift, sizeof(fe));
     std::vector<fe*> X(G, nullptr), R(G, nullptr), N(G, nullptr);
