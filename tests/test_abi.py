@@ -54,6 +54,13 @@ def test_no_gpu_means_no_result(lib):
     h = C.c_uint64(0)
     pts = np.zeros((4, 8), dtype=np.uint64)
     assert lib.uzkge_cuda_srs_upload(ffi.ptr(pts), 4, 0, C.byref(h)) == ffi.ERR_NO_DEVICE
+    # the device group: nothing to form a group from, and the group calls refuse as well
+    assert lib.uzkge_cuda_init_devices(0) == ffi.ERR_NO_DEVICE
+    assert lib.uzkge_cuda_group_size() == 0
+    assert lib.uzkge_cuda_srs_upload_multi(ffi.ptr(pts), 4, 0, 0, C.byref(h)) == ffi.ERR_NO_DEVICE
+    assert lib.uzkge_cuda_ntt_fr_multi(ffi.ptr(buf), 8, 8, 0, None) == ffi.ERR_NO_DEVICE
+    assert not buf.any()
+    assert lib.uzkge_cuda_plonk_params_upload_multi(None, C.byref(h)) in (ffi.ERR_ARG, ffi.ERR_NO_DEVICE)
     with pytest.raises(BackendUnavailable):
         ffi.ntt_fr(buf, 8)
     with pytest.raises(BackendUnavailable):
