@@ -446,7 +446,8 @@ UZKGE_API uint64_t uzkge_cuda_launch_count(void);
 UZKGE_API int32_t uzkge_cuda_profile_enable(int32_t on);
 UZKGE_API int32_t uzkge_cuda_profile_read(int32_t kind, double phase_ms[8], uint64_t* runs);
 /* tuning knobs for experiments: "msm_lanes" (0 = auto, else 1..32 lanes per bucket), "ntt_log_tile",
- * "ntt_max_log_r", "ntt_two_pass_max" (affect plans created afterwards); "quotient_min_blocks"; "l2_fetch_granularity" (32 / 64 / 128:
+ * "ntt_max_log_r", "ntt_two_pass_max" (affect plans created afterwards); "ntt_radix4" (transforms of at least 2^value points walk two
+ * butterfly stages per shared-memory round trip; 0 = off, default 19); "quotient_min_blocks"; "l2_fetch_granularity" (32 / 64 / 128:
  * cudaLimitMaxL2FetchGranularity of the calling thread's device); "virtual_devices" (tests: the next uzkge_cuda_init_devices forms a
  * group of that many members over the visible GPUs, 0 = one member per GPU); "group_deal_min_log_n" (a device group deals a round's
  * interpolations and the linearisation polynomial to its members for circuits of at least 2^value gates; default 19). */

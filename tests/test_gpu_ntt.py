@@ -186,3 +186,18 @@ def test_batched_device_transforms_match_oracle(gpu, oc, n, k):
         full = np.zeros((n, 4), dtype=np.uint64)
         full[: xs[j].shape[0]] = xs[j]
         assert np.array_equal(d_in[j].cpu().numpy().view(np.uint64).reshape(n, 4), oc.ntt_fr(full, n))
+
+
+def test_radix4_stage_walk_matches_the_oracle_at_every_size(gpu, oc):
+    """The radix-4 walk of the tile passes (two butterfly stages per shared-memory round trip; default from 2^19 points on) forced onto
+    every size (uzkge_cuda_configure("ntt_radix4", 1)): 2^1..2^18 and 3 * 2^1..3 * 2^16, forward / inverse / coset / coset inverse,
+    against the oracle's transforms -- odd and even stage counts, 1-, 2- and 3-pass plans."""
+    try:
+        gpu.configure("ntt_radix4", 1)
+        k = oc.random_fr(1, 31)[0]
+        for n in [1 << l for l in range(1, 19)] + [3 << l for l in range(1, 17)]:
+            x = oc.random_fr(n, 100 + n % 97)
+            for inv, cs in ((False, None), (True, None), (False, k), (True, k)):
+                assert np.array_equal(gpu.ntt_fr(x, n, inv, cs), oc.ntt_fr(x, n, inverse=inv, coset=cs)), (n, inv, cs is not None)
+    finally:
+        gpu.configure("ntt_radix4", 19)

@@ -104,7 +104,7 @@ struct State {
 };
 struct Config {
     uint32_t ntt_log_tile = 10, ntt_max_log_r = 10, ntt_two_pass_max = 18;  // measured best on B200 (scripts/gpu_ntt_cfg.py)
-    uint32_t ntt_big_threads = 1024, msm_lanes = 0, msm_affine = 0;
+    uint32_t ntt_big_threads = 1024, msm_lanes = 0, msm_affine = 0, ntt_radix4 = 19;
 };
 std::mutex g_reg_mu;                  // guards the registry below (never held while a device's work is enqueued)
 State* g_states[UZ_MAX_DEVICES] = {};
@@ -180,6 +180,7 @@ int enter_state(int want, State** out) {
         fresh->ntt.reset(new NttEngine(fresh->sm_count));
         fresh->ntt->configure(g_cfg.ntt_log_tile, g_cfg.ntt_max_log_r, g_cfg.ntt_two_pass_max);
         fresh->ntt->set_big_threads(g_cfg.ntt_big_threads);
+        fresh->ntt->set_radix4(g_cfg.ntt_radix4);
         fresh->msm.reset(new MsmEngine(fresh->sm_count));
         fresh->msm->force_lanes(g_cfg.msm_lanes);
         fresh->msm->set_affine(g_cfg.msm_affine);
@@ -1060,6 +1061,9 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
         if (k == "msm_lanes") {
             if (value > 32 || (value & (value - 1))) return fail(UZKGE_ERR_ARG, "configure: msm_lanes must be 0 or a power of two <= 32");
             g_cfg.msm_lanes = (uint32_t)value;
+        } else if (k == "ntt_radix4") {
+            if (value > 28) return fail(UZKGE_ERR_ARG, "configure: ntt_radix4 is a minimum log2 size (0 = off), at most 28");
+            g_cfg.ntt_radix4 = (uint32_t)value;
         } else if (k == "ntt_big_threads") {
             if (value != 512 && value != 1024) return fail(UZKGE_ERR_ARG, "configure: ntt_big_threads is 512 or 1024");
             g_cfg.ntt_big_threads = (uint32_t)value;
@@ -1098,6 +1102,7 @@ UZKGE_API int32_t uzkge_cuda_configure(const char* key, uint64_t value) {
             st->ntt->configure(g_cfg.ntt_log_tile, g_cfg.ntt_max_log_r, g_cfg.ntt_two_pass_max);
         }
         st->ntt->set_big_threads(g_cfg.ntt_big_threads);
+        st->ntt->set_radix4(g_cfg.ntt_radix4);
     }
     return UZKGE_OK;
 }

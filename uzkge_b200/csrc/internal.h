@@ -123,6 +123,7 @@ public:
     explicit NttEngine(int sm_count) : sm_count_(sm_count) {}
     ~NttEngine();
     void set_big_threads(uint32_t nt) { cfg_big_threads_ = nt; }
+    void set_radix4(uint32_t on) { cfg_radix4_ = on; }
     void configure(uint32_t log_tile, uint32_t max_log_r, uint32_t two_pass_max) {
         cfg_log_tile_ = log_tile;
         cfg_max_log_r_ = max_log_r;
@@ -145,7 +146,7 @@ private:
     std::map<uint64_t, NttDomain> domains_;
     std::vector<NttCoset> cosets_;
     int sm_count_;
-    uint32_t cfg_log_tile_ = 10, cfg_max_log_r_ = 10, cfg_two_pass_max_ = 18, cfg_big_threads_ = 1024;
+    uint32_t cfg_log_tile_ = 10, cfg_max_log_r_ = 10, cfg_two_pass_max_ = 18, cfg_big_threads_ = 1024, cfg_radix4_ = 19;
 };
 
 // ---------------------------------------------------------------- MSM

@@ -87,8 +87,12 @@ struct NttKernelArgs {
     uint32_t scatter_log_g, scatter_shift, scatter_k1;
 };
 
-template <int NT, bool SCATTER>
-__global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
+// R4: two butterfly stages per shared-memory round trip (radix-4 items held in registers): half the LDS / STS / index arithmetic and
+// half the barriers of the radix-2 walk, the same products.  Held to 64 registers (4 resident CTAs per SM; at its natural 80 registers
+// and 3 CTAs it only ties the radix-2 walk).  Measured: 2^22 883 -> 864 us, 2^24 3711 -> 3637 us, 3 * 2^21 1457 -> 1427 us; slower below
+// 2^18 (2^14: 23.3 -> 26.9 us), so the engine uses it from 2^19 points on (uzkge_cuda_configure "ntt_radix4": minimum log2 size, 0 = off).
+template <int NT, bool SCATTER, bool R4 = false>
+__global__ void __launch_bounds__(NT, (R4 && NT == 256) ? 4 : 1) ntt_pass_kernel(const NttKernelArgs a) {
     extern __shared__ uint4 ntt_smem[];
     const NttPass& p = a.p;
     const uint32_t logR = p.logR, logC = p.logC;
@@ -127,7 +131,56 @@ __global__ void __launch_bounds__(NT) ntt_pass_kernel(const NttKernelArgs a) {
     __syncthreads();
 
     // ---- decimation-in-frequency stages: (u, v) -> (u + v, (u - v) * w_{2h}^j); result row = bitrev(k)
-    for (int s = (int)logR - 1; s >= 0; s--) {
+    int s_first = (int)logR - 1;
+    if (R4) {
+        // stages s (distance h) and s - 1 (distance q = h / 2) on the four rows r0, r0 + q, r0 + h, r0 + h + q, r0 = blk * 2h + j, j < q:
+        //   stage s    : (x0, x2) with twiddle w_{2h}^j, (x1, x3) with w_{2h}^(j + q)
+        //   stage s - 1: (a0, a1) and (a2, a3), both with w_h^j
+        for (; s_first >= 1; s_first -= 2) {
+            const int s = s_first;
+            const uint32_t h = 1u << s, q = h >> 1;
+            const uint32_t sh1 = logR - 1 - s, sh2 = logR - s;      // twiddle index shifts of the two stages
+            const uint32_t log_nblk = logR - 1 - s;
+            const bool by_block = logC >= 2 && logC + log_nblk >= 5;
+            for (uint32_t bb = threadIdx.x; bb < (T >> 2); bb += NT) {
+                const uint32_t c = bb & (C - 1), pr = bb >> logC;
+                uint32_t j, blk;
+                if (by_block) {
+                    j = pr >> log_nblk;
+                    blk = pr & ((1u << log_nblk) - 1);
+                } else {
+                    j = pr & (q - 1);
+                    blk = pr >> (s - 1);
+                }
+                const uint32_t r0 = (blk << (s + 1)) | j;
+                const uint32_t p0 = tv.pos(r0, c), p1 = tv.pos(r0 + q, c), p2 = tv.pos(r0 + h, c), p3 = tv.pos(r0 + h + q, c);
+                fe a0, a1, a2, a3;
+                {
+                    const fe x0 = tv.ld(p0), x2 = tv.ld(p2);
+                    a0 = fe_add<FrP>(x0, x2);
+                    a2 = fe_sub<FrP>(x0, x2);
+                    if (j) a2 = fe_mul<FrP>(a2, ldg_fe(a.stage_tab + (size_t)(j << sh1) * p.stage_stride));
+                }
+                {
+                    const fe x1 = tv.ld(p1), x3 = tv.ld(p3);
+                    a1 = fe_add<FrP>(x1, x3);
+                    a3 = fe_mul<FrP>(fe_sub<FrP>(x1, x3), ldg_fe(a.stage_tab + (size_t)((j + q) << sh1) * p.stage_stride));
+                }
+                tv.st(p0, fe_add<FrP>(a0, a1));
+                tv.st(p2, fe_add<FrP>(a2, a3));
+                fe b1 = fe_sub<FrP>(a0, a1), b3 = fe_sub<FrP>(a2, a3);
+                if (j) {
+                    const fe w2 = ldg_fe(a.stage_tab + (size_t)(j << sh2) * p.stage_stride);
+                    b1 = fe_mul<FrP>(b1, w2);
+                    b3 = fe_mul<FrP>(b3, w2);
+                }
+                tv.st(p1, b1);
+                tv.st(p3, b3);
+            }
+            __syncthreads();
+        }
+    }
+    for (int s = s_first; s >= 0; s--) {
         const uint32_t h = 1u << s;
         const uint32_t tw_shift = logR - 1 - s;
         // butterfly -> thread mapping: where a warp would otherwise mix twiddle indices, walk the 2h-row blocks first so that
@@ -430,21 +483,21 @@ const NttCoset* NttEngine::coset(uint64_t n, const fe& g, bool with_ninv, const 
     return &cosets_.back();
 }
 
-template <int NT, bool SCATTER = false>
+template <int NT, bool SCATTER = false, bool R4 = false>
 static cudaError_t launch_pass(const NttKernelArgs& ka, uint32_t k, cudaStream_t st) {
     const NttPass& p = ka.p;
     const size_t T = (size_t)1 << (p.logR + p.logC);
     const size_t smem = T * 32;
-    static size_t configured[UZ_MAX_DEVICES] = {};   // function attributes are per device
+    static size_t configured[UZ_MAX_DEVICES] = {};   // function attributes are per device (and per instantiation: the static is too)
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > 48 * 1024 && smem > configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<NT, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<NT, SCATTER, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
         if (e != cudaSuccess) return e;
         configured[dev] = 200 * 1024;
     }
     const uint32_t grid = p.inner_tiles * p.outer * p.batch;
-    ntt_pass_kernel<NT, SCATTER><<<dim3(grid, k), NT, smem, st>>>(ka);
+    ntt_pass_kernel<NT, SCATTER, R4><<<dim3(grid, k), NT, smem, st>>>(ka);
     UZ_COUNT_LAUNCH(1);
     return cudaGetLastError();
 }
@@ -550,6 +603,8 @@ int NttEngine::run_batch(const fe* const* d_in, fe* const* d_out, fe* d_scratch,
                 e = launch_pass<256, true>(ka, k, st);
             else
                 e = launch_pass<64, true>(ka, k, st);
+        } else if (cfg_radix4_ && n >= (1ull << cfg_radix4_) && T >= 512 && T < 2048) {
+            e = launch_pass<256, false, true>(ka, k, st);
         } else if (T >= 4096 && cfg_big_threads_ == 1024)
             e = launch_pass<1024>(ka, k, st);
         else if (T >= 2048)
