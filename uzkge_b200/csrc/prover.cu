@@ -122,9 +122,19 @@ struct Params {
     u64 *scratch = nullptr, *coset[8] = {}, *w_sel_coset[3] = {}, *wit = nullptr, *ext = nullptr, *sel_ev = nullptr, *z_ev = nullptr, *ztmp = nullptr;
     u64 *polys = nullptr;      // 16 buffers of stride elements: w[5], w_sel[3], z, t[5], r, (spare)
     u64 *pi = nullptr, *sh = nullptr, *q1 = nullptr, *q2 = nullptr, *lag_buf = nullptr, *small = nullptr;
-    // device group (uzkge_cuda_plonk_params_upload_multi): compact coset vectors (10 x n), the exchanged quotient cosets (m elements,
-    // coset j at [j n, (j + 1) n))
+    // device group (uzkge_cuda_plonk_params_upload_multi): one compact coset vector (n: the quotient map's output), the exchanged
+    // quotient cosets (m elements, coset j at [j n, (j + 1) n))
     u64 *cbuf = nullptr, *tcos = nullptr;
+    // a group member's own cosets j = rank mod G of the quotient domain in COMPACT form (n values each: element i = point j + factor i):
+    // the preprocessed columns, gathered once from the size-m evaluations above, and this proof's wires / z / pi / witness selectors.
+    // The quotient map of a coset then runs on contiguous vectors (the strided walk over the size-m arrays fetches 4x the bytes)
+    struct CosetCols {
+        size_t j = 0;
+        u64 *q[9] = {}, *s[5] = {}, *qb = nullptr, *prk[4] = {}, *l1 = nullptr, *coset_quotient = nullptr, *q_ecc = nullptr, *gen[12] = {}, *pk[12] = {};
+        u64* dyn = nullptr;      // 10 x n: w[5], w_sel[3], z, pi
+    };
+    std::vector<CosetCols> own_cosets;
+    size_t group_rank = 0, group_size = 1;
     u64* pinned = nullptr;     // host, page-locked: results of the small device-to-host reads
     cudaStream_t st = nullptr, side = nullptr;
     cudaEvent_t ev = nullptr;
@@ -206,6 +216,47 @@ int preprocess(Params& P, const u64* host, size_t len, Poly* poly, u64** coset) 
     CU(cudaMemcpyAsync(poly->p, host, len * 32, cudaMemcpyHostToDevice, P.st));
     TRY(dev_alloc(P, P.m, coset, false));
     return coset_fft(P, *poly, *coset);
+}
+
+// compact copy of coset j of a size-m column (shared zero columns stay shared: one compact zero vector)
+int coset_column(Params& P, const u64* col_m, size_t j, u64** out) {
+    if (col_m == P.zero_coset) {
+        *out = P.zero_coset;         // n zeros are a prefix of m zeros
+        return UZKGE_OK;
+    }
+    if (!*out || *out == P.zero_coset) TRY(dev_alloc(P, P.n, out, false));
+    return uzkge_cuda_fr_strided_copy_device(col_m, j, P.factor, *out, 0, 1, P.n, P.st);
+}
+// (re)build the compact public-key columns of a member's cosets (after uzkge_cuda_plonk_params_set_public_key)
+int coset_public_key_columns(Params& P) {
+    if (!P.shuffle) return UZKGE_OK;
+    for (Params::CosetCols& c : P.own_cosets)
+        for (int i = 0; i < 12; i++) TRY(coset_column(P, P.pk_coset[i], c.j, &c.pk[i]));
+    return UZKGE_OK;
+}
+// every preprocessed column of member `rank`'s cosets, plus the per-proof buffers
+int build_own_cosets(Params& P, size_t rank, size_t G) {
+    P.group_rank = rank;
+    P.group_size = G;
+    for (size_t j = rank; j < P.factor; j += G) {
+        Params::CosetCols c;
+        c.j = j;
+        for (int i = 0; i < 9; i++) TRY(coset_column(P, P.q_coset[i], j, &c.q[i]));
+        for (int i = 0; i < 5; i++) TRY(coset_column(P, P.s_coset[i], j, &c.s[i]));
+        TRY(coset_column(P, P.qb_coset, j, &c.qb));
+        for (int i = 0; i < 4; i++) TRY(coset_column(P, P.prk_coset[i], j, &c.prk[i]));
+        TRY(coset_column(P, P.l1_coset, j, &c.l1));
+        TRY(coset_column(P, P.coset_quotient, j, &c.coset_quotient));
+        if (P.shuffle) {
+            TRY(coset_column(P, P.q_ecc_coset, j, &c.q_ecc));
+            for (int i = 0; i < 12; i++) TRY(coset_column(P, P.gen_coset[i], j, &c.gen[i]));
+        }
+        TRY(dev_alloc(P, 10 * P.n, &c.dyn, true));       // pi stays zero without public inputs
+        P.own_cosets.push_back(c);
+    }
+    TRY(coset_public_key_columns(P));
+    CU(cudaStreamSynchronize(P.st));
+    return UZKGE_OK;
 }
 
 struct Msm {           // one commitment to make: scalars in HBM
@@ -417,6 +468,7 @@ UZKGE_API int32_t uzkge_cuda_plonk_params_set_public_key(uint64_t params_handle,
         if (len[i]) CU(cudaMemcpyAsync(P.pk[i].p, polys[i], len[i] * 32, cudaMemcpyHostToDevice, P.st));
         TRY(coset_fft(P, P.pk[i], P.pk_coset[i]));
     }
+    TRY(coset_public_key_columns(P));      // a group member keeps compact copies of its cosets' columns
     CU(cudaStreamSynchronize(P.st));
     return UZKGE_OK;
 }
@@ -662,14 +714,14 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
     // ---- group members: the quotient round by cosets.  The m = factor * n points k[1] w_m^p are the cosets g_j <w_n>, g_j = k[1] w_m^j,
     // p = factor * i + j.  On coset j a polynomial of n + 3 coefficients is a size-n coset transform of its coefficients folded with
     // X^n = g_j^n, and the map of a coset needs nothing from the other cosets: member r takes the cosets j = r mod G
-    std::vector<size_t> my_cosets;
-    if (grp)
-        for (size_t j = rank; j < P.factor; j += G) my_cosets.push_back(j);
-    // fs[i] on this member's cosets, written to positions j + factor * i' of the size-m vector outs[i]
-    auto eval_on_my_cosets = [&](const Poly* fs, u64* const* outs, size_t k) -> int {
+    if (grp && (P.group_rank != rank || P.group_size != G))
+        return uz::api_fail(UZKGE_ERR_HANDLE, "plonk_prove: the parameter set was not uploaded for this member of the device group");
+    // fs[i] on this member's cosets, into slot slots[i] of the coset's compact buffers (Params::CosetCols::dyn: w0..w4, w_sel0..2, z, pi)
+    enum { SLOT_W = 0, SLOT_W_SEL = 5, SLOT_Z = 8, SLOT_PI = 9 };
+    auto eval_on_my_cosets = [&](const Poly* fs, const size_t* slots, size_t k) -> int {
         if (k > 10) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: more than 10 polynomials per coset pass");
-        for (size_t j : my_cosets) {
-            const Limbs g = FR.mul(P.k1, fr_pow_u64(P.root_m, (u64)j));
+        for (const Params::CosetCols& c : P.own_cosets) {
+            const Limbs g = FR.mul(P.k1, fr_pow_u64(P.root_m, (u64)c.j));
             const Limbs gn = fr_pow_u64(g, (u64)n);
             u64 fold[8];
             memcpy(fold, FR.one.data(), 32);
@@ -678,11 +730,11 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
             u64* cs[10];
             size_t lens[10];
             for (size_t i = 0; i < k; i++) {
-                // the transform's input is a COPY of the first n coefficients with the tail folded in (head += g^n * tail): the
+                // the transform runs in place on a COPY of the first n coefficients with the tail folded in (head += g^n * tail): the
                 // polynomial itself is never touched -- other members of the group may be reading it over peer memory
                 const size_t extra = fs[i].len > n ? fs[i].len - n : 0;
                 if (extra > TAIL) return uz::api_fail(UZKGE_ERR_INTERNAL, "plonk_prove: a polynomial exceeds n + 8 coefficients");
-                cs[i] = P.cbuf + 4 * n * i;
+                cs[i] = c.dyn + 4 * n * slots[i];
                 lens[i] = fs[i].len < n ? (fs[i].len ? fs[i].len : 1) : n;
                 CU(cudaMemcpyAsync(cs[i], fs[i].p, lens[i] * 32, cudaMemcpyDeviceToDevice, st));
                 if (extra) {
@@ -692,9 +744,8 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
                 }
                 ins[i] = cs[i];
             }
-            TRY(ntt_many(P, ins, cs, lens, k, n, 0, g.data()));      // in place in the compact buffers
+            TRY(ntt_many(P, ins, cs, lens, k, n, 0, g.data()));
             proof->fft_n += (uint32_t)k;
-            for (size_t i = 0; i < k; i++) TRY(uzkge_cuda_fr_strided_copy_device(cs[i], 0, 1, outs[i], j, P.factor, n, st));
         }
         return UZKGE_OK;
     };
@@ -796,18 +847,17 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
     auto wire_cosets = [&]() -> int {
         if (grp) {
             Poly fs[8];
-            u64* dst[8];
-            size_t kk = 0;
+            size_t slots[8], kk = 0;
             for (size_t i = 0; i < N_WIRES; i++) {
                 fs[kk] = w_polys[i];
-                dst[kk++] = P.coset[i];
+                slots[kk++] = SLOT_W + i;
             }
             if (shuffle)
                 for (size_t i = 0; i < 3; i++) {
                     fs[kk] = w_sel_polys[i];
-                    dst[kk++] = P.w_sel_coset[i];
+                    slots[kk++] = SLOT_W_SEL + i;
                 }
-            return eval_on_my_cosets(fs, dst, kk);
+            return eval_on_my_cosets(fs, slots, kk);
         }
         const u64* ins[8];
         u64* outs[8];
@@ -894,7 +944,10 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
         }
         TRY(flush_sparse());
         auto z_coset = [&]() -> int {
-            if (grp) return eval_on_my_cosets(&z_poly, &P.coset[6], 1);
+            if (grp) {
+                const size_t slot = SLOT_Z;
+                return eval_on_my_cosets(&z_poly, &slot, 1);
+            }
             proof->coset_fft_m++;
             return coset_fft(P, z_poly, P.coset[6]);
         };
@@ -913,7 +966,8 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
     const Limbs alpha = tr.get_challenge_field_elem();
     if (P.n_public) {
         if (grp) {
-            TRY(eval_on_my_cosets(&pi, &P.coset[5], 1));
+            const size_t slot = SLOT_PI;
+            TRY(eval_on_my_cosets(&pi, &slot, 1));
         } else {
             TRY(coset_fft(P, pi, P.coset[5]));
             proof->coset_fft_m++;
@@ -951,30 +1005,54 @@ int prove_impl(const uzkge_plonk_prove_args* a, uzkge_plonk_proof* proof, Group*
                 sa.gen[i] = P.gen_coset[i];
             }
             memcpy(sa.edwards_a, P.edwards_a.data(), 32);
-            if (grp) {
-                for (size_t j : my_cosets) TRY(uzkge_cuda_plonk_quotient_range_fr_device(&qa, &sa, j, P.factor, n, t_buf, st));
-            } else {
-                TRY(uzkge_cuda_plonk_quotient_shuffle_fr_device(&qa, &sa, t_buf, st));
-            }
-        } else if (grp) {
-            for (size_t j : my_cosets) TRY(uzkge_cuda_plonk_quotient_range_fr_device(&qa, nullptr, j, P.factor, n, t_buf, st));
-        } else {
+            if (!grp) TRY(uzkge_cuda_plonk_quotient_shuffle_fr_device(&qa, &sa, t_buf, st));
+        } else if (!grp) {
             TRY(uzkge_cuda_plonk_quotient_fr_device(&qa, t_buf, st));
         }
         if (grp) {
-            // back to coefficients, coset by coset: the size-n coset iFFT of the values on coset j is u_j[r] = T_r(g_j^n), where
-            // t(X) = sum_r X^r T_r(X^n).  Every member sends its u_j (compact, n values) into every other member's Params::tcos over
-            // peer memory; a factor-point inverse DFT per r over the cosets then gives t's coefficients -- no transform of the whole
-            // 6n domain, and nothing but the cosets crosses NVLink
-            for (size_t j : my_cosets) {
-                const Limbs g_inv = FR.inverse(FR.mul(P.k1, fr_pow_u64(P.root_m, (u64)j)));
-                TRY(uzkge_cuda_fr_strided_copy_device(t_buf, j, P.factor, P.cbuf, 0, 1, n, st));
-                TRY(uzkge_cuda_ntt_fr_device(P.cbuf, P.tcos + 4 * j * n, P.scratch, n, n, 1, g_inv.data(), st));
+            // the map on each of this member's cosets, over the coset's COMPACT columns: a domain of n points with factor 1 (the
+            // omega-shifted point is the next element, Z_H^-1 is the coset's constant); then back to coefficients, coset by coset:
+            // the size-n coset iFFT of the values on coset j is u_j[r] = T_r(g_j^n), where t(X) = sum_r X^r T_r(X^n).  Every member
+            // sends its u_j (n values) into every other member's Params::tcos over peer memory; a factor-point inverse DFT per r
+            // over the cosets then gives t's coefficients -- no transform of the whole 6n domain, nothing but the cosets on NVLink
+            for (const Params::CosetCols& c : P.own_cosets) {
+                uzkge_quotient_args qc = qa;
+                for (size_t i = 0; i < N_WIRES; i++) {
+                    qc.w[i] = c.dyn + 4 * n * (SLOT_W + i);
+                    qc.s[i] = c.s[i];
+                }
+                for (size_t i = 0; i < N_SEL; i++) qc.q[i] = c.q[i];
+                qc.pi = c.dyn + 4 * n * SLOT_PI;
+                qc.z = c.dyn + 4 * n * SLOT_Z;
+                qc.coset_quotient = c.coset_quotient;
+                qc.l1 = c.l1;
+                qc.qb = c.qb;
+                for (size_t i = 0; i < 4; i++) qc.q_prk[i] = c.prk[i];
+                memset(qc.z_h_inv, 0, sizeof qc.z_h_inv);
+                memcpy(qc.z_h_inv[0], P.z_h_inv[c.j].data(), 32);
+                qc.m = n;
+                qc.factor = 1;
+                if (shuffle) {
+                    uzkge_quotient_shuffle_args sc;
+                    memset(&sc, 0, sizeof sc);
+                    for (size_t i = 0; i < 3; i++) sc.w_sel[i] = c.dyn + 4 * n * (SLOT_W_SEL + i);
+                    sc.q_ecc = c.q_ecc;
+                    for (size_t i = 0; i < 12; i++) {
+                        sc.pk[i] = c.pk[i];
+                        sc.gen[i] = c.gen[i];
+                    }
+                    memcpy(sc.edwards_a, P.edwards_a.data(), 32);
+                    TRY(uzkge_cuda_plonk_quotient_shuffle_fr_device(&qc, &sc, P.cbuf, st));
+                } else {
+                    TRY(uzkge_cuda_plonk_quotient_fr_device(&qc, P.cbuf, st));
+                }
+                const Limbs g_inv = FR.inverse(FR.mul(P.k1, fr_pow_u64(P.root_m, (u64)c.j)));
+                TRY(uzkge_cuda_ntt_fr_device(P.cbuf, P.tcos + 4 * c.j * n, P.scratch, n, n, 1, g_inv.data(), st));
                 proof->ifft_n++;
                 for (size_t r = 0; r < G; r++) {
                     if (r == rank) continue;
                     Params* Q = grp->params[r];
-                    CU(cudaMemcpyPeerAsync(Q->tcos + 4 * j * n, Q->device, P.tcos + 4 * j * n, P.device, n * 32, st));
+                    CU(cudaMemcpyPeerAsync(Q->tcos + 4 * c.j * n, Q->device, P.tcos + 4 * c.j * n, P.device, n * 32, st));
                 }
             }
             CU(cudaStreamSynchronize(st));
@@ -1403,8 +1481,9 @@ UZKGE_API int32_t uzkge_cuda_plonk_params_upload_multi(const uzkge_plonk_params_
                 Pp = g_params[subs[r]].get();
             }
             Params& P = *Pp;
-            TRY(dev_alloc(P, 10 * P.n, &P.cbuf, false));
+            TRY(dev_alloc(P, P.n, &P.cbuf, false));
             TRY(dev_alloc(P, P.m, &P.tcos, false));
+            TRY(build_own_cosets(P, r, G));
             return (int)UZKGE_OK;
         });
     }
