@@ -66,3 +66,34 @@ def test_our_arm_refuses_to_run_without_a_gpu():
         pytest.skip("a CUDA device is visible")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0 and out.stdout.strip() == "" and "no CPU path" in out.stderr
+
+
+def test_round2_lines_carry_the_binding_roof_the_cpu_prover_and_the_device_group():
+    """profiles/r2b_*: the roofline record is on the multiplier pipe with a peak that does not come from the library; the proofs/s
+    baseline is a complete CPU proof with the GPU's bytes; the two arms share one config; the multi-GPU lines hold the strong-scaling
+    blocks and ONE proof on the device group, all with parity flags set."""
+    d = _load("r2b_bench.json")
+    r = d["roofline"]
+    assert r["bound"] == "imad" and r["unit"] == "T IMAD/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert "pipe_probe" in r["peak_source"] and 0.85 < r["frac"] < 1.0 and abs(r["peak"] - r["peak_issue_model"]) / r["peak_issue_model"] < 0.05
+    assert "r2b_msm_raw.csv" in r["traffic_source"] and r["traffic"] > 1e9
+    assert d["hbm_roofline"]["bound"] == "hbm" and d["hbm_roofline"]["frac"] < 0.05
+    assert d["cpu_baseline"]["sample"].startswith("one full 2^20")
+    pb = d["plonk"]["cpu_baseline"]
+    assert pb["unit"] == "proofs/s" and "proof bytes equal to the GPU's" in pb["sample"] and pb["prove_ms"] > 10 * pb["gpu_prove_ms"]
+    for s in d["plonk"]["sizes"]:
+        assert s["prover"].startswith("uzkge_cuda_plonk_prove") and s["ops_per_proof"]["msm"] in (13, 16)
+    ref = json.loads(open(os.path.join(ROOT, "profiles", "r2b_bench_reference_arm.json")).read().strip().splitlines()[0])
+    assert ref["impl"] == "reference" and ref["config"] == d["config"] and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
+    one_gpu = [s for s in d["plonk"]["sizes"] if s["log_n"] == 22 and s["witness"] == "uniform"][0]["prove_ms"]
+    last = one_gpu
+    for n in (2, 4, 8):
+        m = _load(f"r2b_bench_{n}gpu.json")
+        assert m["n_gpus"] == n and abs(m["value"] - n * (1 << 20) / (m["ms_per_step"] * 1e-3)) / m["value"] < 1e-6
+        for key in ("msm_strong", "ntt_strong", "ntt_distributed", "ntt_group_e2e", "commit_group_e2e"):
+            assert m[key]["parity_ok"] is True, (n, key)
+        assert m["msm_strong"]["ms_per_step"] < m["msm_strong"]["single_gpu_ms"] and m["ntt_strong"]["ms_per_step"] < m["ntt_strong"]["single_gpu_ms"]
+        group = [s for s in m["plonk"]["sizes"] if s["mode"] == "device_group"][0]
+        split = [s for s in m["plonk"]["sizes"] if s["mode"] == "msm_split"][0]
+        assert group["log_n"] == 22 and group["prove_ms"] < split["prove_ms"] < one_gpu and group["prove_ms"] < last
+        last = group["prove_ms"]
